@@ -1,0 +1,16 @@
+"""gvdb-voxels_b200 — B200-native (sm_100a) ray-cast render path of NVIDIA/gvdb-voxels.
+
+Thin ctypes front end over the C ABI in include/gvdbx.h (libgvdbx.so, built in-tree by
+`make -C gvdb-voxels_b200` or `__graft_entry__.build()`).  The directory name contains a
+hyphen, so it is imported through `importlib` as module ``gvdb_voxels_b200``
+(see __graft_entry__.load_package()).
+
+There is no CPU fallback: every call that needs the device raises GvdbxError when the
+shared library or a CUDA device is missing.
+"""
+from .api import (  # noqa: F401
+    GvdbxError, Renderer, lib, lib_path,
+    SHADE_VOXEL, SHADE_TRILINEAR, SHADE_LEVELSET, SHADE_VOLUME, SHADE_OFF,
+    SAMPLER_TEX, SAMPLER_LINEAR, VDBINFO_BYTES, SCNINFO_BYTES,
+    EXPORTED_SYMBOLS,
+)

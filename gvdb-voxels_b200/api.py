@@ -1,0 +1,218 @@
+"""ctypes bindings for libgvdbx.so (include/gvdbx.h).
+
+Mirrors the reference call sequence of VolumeGVDB (src/gvdb_volume_gvdb.cpp):
+    PrepareVDB        :3946  -> Renderer.import_topology / import_topology_host
+    SetupAtlasAccess  :720   -> Renderer.import_atlas_host / import_atlas_array
+    CommitTransferFunc:4892  -> Renderer.set_transfer
+    Render            :4336  -> Renderer.render(scninfo, shade, out_ptr)
+    ReadRenderBuf     :4241  -> Renderer.read_buffer
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+SHADE_VOXEL, SHADE_TRILINEAR, SHADE_LEVELSET, SHADE_VOLUME, SHADE_OFF = 0, 4, 6, 7, 100
+SAMPLER_TEX, SAMPLER_LINEAR = 0, 1
+OPT_SAMPLER, OPT_BLOCK_W, OPT_BLOCK_H, OPT_COUNTERS = 1, 2, 3, 4
+VDBINFO_BYTES, SCNINFO_BYTES = 1232, 416
+
+EXPORTED_SYMBOLS = [
+    "gvdbx_create", "gvdbx_destroy", "gvdbx_last_error", "gvdbx_set_option",
+    "gvdbx_import_topology", "gvdbx_import_topology_host",
+    "gvdbx_import_atlas_array", "gvdbx_import_atlas_host", "gvdbx_set_transfer",
+    "gvdbx_render", "gvdbx_render_tiles", "gvdbx_tiles_per_rank", "gvdbx_assemble_tiles",
+    "gvdbx_render_debug", "gvdbx_read_buffer", "gvdbx_sync", "gvdbx_get_counters",
+    "gvdbx_sample_points",
+]
+
+
+class GvdbxError(RuntimeError):
+    pass
+
+
+class Counters(C.Structure):
+    _fields_ = [(n, C.c_uint64) for n in ("s_tri", "s_pt", "n_dda", "n_desc", "s_lut", "rays")]
+
+    def as_dict(self):
+        return {n: int(getattr(self, n)) for n, _ in self._fields_}
+
+
+def lib_path():
+    return os.path.join(os.path.dirname(os.path.abspath(__file__)), "libgvdbx.so")
+
+
+_LIB = None
+
+
+def lib():
+    """Load libgvdbx.so; fails loudly when the CUDA extension has not been built."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    p = lib_path()
+    if not os.path.exists(p):
+        raise GvdbxError(f"{p} is missing: build it with `make -C gvdb-voxels_b200` "
+                         "(there is no CPU fallback for the render path)")
+    L = C.CDLL(p)
+    vp, u64, i32 = C.c_void_p, C.c_uint64, C.c_int
+    L.gvdbx_create.argtypes = [C.POINTER(vp), i32, vp]
+    L.gvdbx_destroy.argtypes = [vp]
+    L.gvdbx_last_error.argtypes = [vp]
+    L.gvdbx_last_error.restype = C.c_char_p
+    L.gvdbx_set_option.argtypes = [vp, i32, i32]
+    L.gvdbx_import_topology.argtypes = [vp, vp]
+    L.gvdbx_import_topology_host.argtypes = [vp, vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(u64)]
+    L.gvdbx_import_atlas_array.argtypes = [vp, i32, vp, i32, i32, i32]
+    L.gvdbx_import_atlas_host.argtypes = [vp, i32, vp, i32, i32, i32]
+    L.gvdbx_set_transfer.argtypes = [vp, vp]
+    L.gvdbx_render.argtypes = [vp, vp, i32, i32, u64, i32, i32, i32, i32]
+    L.gvdbx_render_tiles.argtypes = [vp, vp, i32, i32, u64, i32, i32, i32]
+    L.gvdbx_tiles_per_rank.argtypes = [i32, i32, i32, i32]
+    L.gvdbx_assemble_tiles.argtypes = [vp, u64, u64, i32, i32, i32, i32]
+    L.gvdbx_render_debug.argtypes = [vp, vp, i32, i32, u64, u64]
+    L.gvdbx_read_buffer.argtypes = [vp, u64, vp, C.c_size_t]
+    L.gvdbx_sync.argtypes = [vp]
+    L.gvdbx_get_counters.argtypes = [vp, C.POINTER(Counters)]
+    L.gvdbx_sample_points.argtypes = [vp, i32, u64, i32, u64, u64]
+    for s in EXPORTED_SYMBOLS:
+        if s != "gvdbx_last_error":
+            getattr(L, s).restype = i32
+    _LIB = L
+    return L
+
+
+def _buf(b):
+    """bytes / numpy array -> (ctypes pointer, keep-alive object)."""
+    if isinstance(b, (bytes, bytearray)):
+        a = np.frombuffer(bytes(b), dtype=np.uint8)
+    else:
+        a = np.ascontiguousarray(b)
+    return a.ctypes.data_as(C.c_void_p), a
+
+
+class Renderer:
+    """One render context per CUDA device (the reference: one VolumeGVDB per device, gvdb_volume_gvdb.h:325)."""
+
+    def __init__(self, device=0, stream=None):
+        self._L = lib()
+        h = C.c_void_p()
+        rc = self._L.gvdbx_create(C.byref(h), int(device), C.c_void_p(stream or 0))
+        if rc != 0:
+            raise GvdbxError(f"gvdbx_create(device={device}) failed with {rc}: no CUDA device / no CPU fallback")
+        self._h = h
+        self.device = device
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.gvdbx_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc, what):
+        if rc != 0:
+            msg = self._L.gvdbx_last_error(self._h)
+            raise GvdbxError(f"{what} failed ({rc}): {msg.decode() if msg else ''}")
+
+    def set_option(self, opt, value):
+        self._ck(self._L.gvdbx_set_option(self._h, opt, int(value)), "gvdbx_set_option")
+
+    def set_sampler(self, sampler):
+        self.set_option(OPT_SAMPLER, sampler)
+
+    def set_block(self, w, h):
+        self.set_option(OPT_BLOCK_W, w)
+        self.set_option(OPT_BLOCK_H, h)
+
+    def set_counters(self, on):
+        self.set_option(OPT_COUNTERS, 1 if on else 0)
+
+    def import_topology(self, vdbinfo):
+        p, keep = _buf(vdbinfo)
+        assert keep.nbytes == VDBINFO_BYTES
+        self._ck(self._L.gvdbx_import_topology(self._h, p), "gvdbx_import_topology")
+
+    def import_topology_host(self, vdbinfo, pool0, pool1):
+        """pool0 / pool1: dict or list level -> bytes / uint8 array (reference pool dumps)."""
+        p, keep = _buf(vdbinfo)
+        assert keep.nbytes == VDBINFO_BYTES
+        a0 = (C.c_void_p * 10)()
+        a1 = (C.c_void_p * 10)()
+        n1 = (C.c_uint64 * 10)()
+        alive = []
+        for lev in range(10):
+            for arr, src in ((a0, pool0), (a1, pool1)):
+                b = src.get(lev) if isinstance(src, dict) else (src[lev] if lev < len(src) else None)
+                if b is None or len(b) == 0:
+                    arr[lev] = None
+                    continue
+                q, k = _buf(b)
+                alive.append(k)
+                arr[lev] = q
+                if arr is a1:
+                    n1[lev] = k.nbytes
+        self._ck(self._L.gvdbx_import_topology_host(self._h, p, a0, a1, n1), "gvdbx_import_topology_host")
+
+    def import_atlas_host(self, texels, chan=0):
+        a = np.ascontiguousarray(texels, dtype=np.float32)
+        assert a.ndim == 3, "atlas image must be [z][y][x]"
+        rz, ry, rx = a.shape
+        self._ck(self._L.gvdbx_import_atlas_host(self._h, chan, a.ctypes.data_as(C.c_void_p), rx, ry, rz),
+                 "gvdbx_import_atlas_host")
+
+    def import_atlas_array(self, cuarray, res_xyz, chan=0):
+        self._ck(self._L.gvdbx_import_atlas_array(self._h, chan, C.c_void_p(cuarray), *map(int, res_xyz)),
+                 "gvdbx_import_atlas_array")
+
+    def set_transfer(self, rgba):
+        a = np.ascontiguousarray(rgba, dtype=np.float32).reshape(-1)
+        assert a.size == 16384 * 4
+        self._ck(self._L.gvdbx_set_transfer(self._h, a.ctypes.data_as(C.c_void_p)), "gvdbx_set_transfer")
+
+    def render(self, scninfo, shade, out_ptr, chan=0, tile=None):
+        p, keep = _buf(scninfo)
+        assert keep.nbytes == SCNINFO_BYTES
+        x0, y0, w, h = tile if tile else (0, 0, 0, 0)
+        self._ck(self._L.gvdbx_render(self._h, p, shade, chan, int(out_ptr), x0, y0, w, h), "gvdbx_render")
+
+    def render_debug(self, scninfo, shade, out_ptr, dbg_ptr, chan=0):
+        p, keep = _buf(scninfo)
+        self._ck(self._L.gvdbx_render_debug(self._h, p, shade, chan, int(out_ptr), int(dbg_ptr)), "gvdbx_render_debug")
+
+    def render_tiles(self, scninfo, shade, packed_ptr, tile_size, rank, nranks, chan=0):
+        p, keep = _buf(scninfo)
+        self._ck(self._L.gvdbx_render_tiles(self._h, p, shade, chan, int(packed_ptr), tile_size, rank, nranks),
+                 "gvdbx_render_tiles")
+
+    def tiles_per_rank(self, width, height, tile_size, nranks):
+        return self._L.gvdbx_tiles_per_rank(width, height, tile_size, nranks)
+
+    def assemble_tiles(self, gathered_ptr, frame_ptr, width, height, tile_size, nranks):
+        self._ck(self._L.gvdbx_assemble_tiles(self._h, int(gathered_ptr), int(frame_ptr), width, height, tile_size, nranks),
+                 "gvdbx_assemble_tiles")
+
+    def read_buffer(self, buf_ptr, nbytes):
+        out = np.empty(nbytes, dtype=np.uint8)
+        self._ck(self._L.gvdbx_read_buffer(self._h, int(buf_ptr), out.ctypes.data_as(C.c_void_p), nbytes), "gvdbx_read_buffer")
+        return out
+
+    def read_into(self, buf_ptr, host_array):
+        self._ck(self._L.gvdbx_read_buffer(self._h, int(buf_ptr), host_array.ctypes.data_as(C.c_void_p), host_array.nbytes),
+                 "gvdbx_read_buffer")
+
+    def sync(self):
+        self._ck(self._L.gvdbx_sync(self._h), "gvdbx_sync")
+
+    def counters(self):
+        c = Counters()
+        self._ck(self._L.gvdbx_get_counters(self._h, C.byref(c)), "gvdbx_get_counters")
+        return c.as_dict()
+
+    def sample_points(self, xyz_ptr, n, out_tex_ptr, out_lin_ptr, chan=0):
+        self._ck(self._L.gvdbx_sample_points(self._h, chan, int(xyz_ptr), n, int(out_tex_ptr), int(out_lin_ptr)),
+                 "gvdbx_sample_points")

@@ -1,0 +1,502 @@
+// gvdbx_api.cu — C ABI (include/gvdbx.h) over the sm_100a kernels in gvdbx_device.cuh.
+//
+// Host-side counterpart of the reference's PrepareVDB / PrepareRender / Render / ReadRenderBuf
+// (src/gvdb_volume_gvdb.cpp:3946-3989, 4254-4306, 4336-4381, 4241-4251).  CUDA runtime API only; works under the
+// caller's current context; everything is stream-ordered on the stream given to gvdbx_create.
+#include "../../include/gvdbx.h"
+#include "gvdbx_device.cuh"
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+struct gvdbx_ctx {
+    int          device = 0;
+    cudaStream_t stream = nullptr;
+    std::string  err;
+    // options
+    int sampler = GX_SAMPLER_TEX, block_w = 8, block_h = 8, count = 0;
+    // topology
+    bool       have_topo = false;
+    GxVDBInfo  vdb;
+    int*       d_child[GX_MAXLEV] = {};
+    int4*      d_npos[GX_MAXLEV] = {};
+    GxLeafRec* d_leaf = nullptr;
+    // atlas
+    bool                have_atlas = false;
+    cudaArray_t         own_array = nullptr;
+    cudaTextureObject_t tex = 0;
+    float*              d_bricks = nullptr;
+    int                 ares[3] = {0, 0, 0};
+    // transfer function
+    float4* d_transfer = nullptr;
+    // counters
+    unsigned long long* d_counters = nullptr;
+};
+
+#define GX_CUDA(h, call)                                                                              \
+    do {                                                                                              \
+        cudaError_t e_ = (call);                                                                      \
+        if (e_ != cudaSuccess) {                                                                      \
+            (h)->err = std::string(#call) + ": " + cudaGetErrorName(e_) + " - " + cudaGetErrorString(e_); \
+            return GVDBX_E_CUDA;                                                                      \
+        }                                                                                             \
+    } while (0)
+
+static int gx_fail(gvdbx_t* h, int code, const std::string& msg) { if (h) h->err = msg; return code; }
+
+extern "C" int gvdbx_create(gvdbx_t** out, int cuda_device, void* cuda_stream)
+{
+    if (!out) return GVDBX_E_ARG;
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0 || cuda_device < 0 || cuda_device >= n) {
+        fprintf(stderr, "gvdbx_create: no usable CUDA device %d (%s); this library has no CPU path\n", cuda_device,
+                e == cudaSuccess ? "device index out of range" : cudaGetErrorString(e));
+        return GVDBX_E_CUDA;
+    }
+    if (cudaSetDevice(cuda_device) != cudaSuccess) return GVDBX_E_CUDA;
+    gvdbx_t* h = new gvdbx_ctx;
+    h->device = cuda_device;
+    h->stream = (cudaStream_t)cuda_stream;
+    if (cudaMalloc(&h->d_counters, 8 * sizeof(unsigned long long)) != cudaSuccess) { delete h; return GVDBX_E_CUDA; }
+    cudaMemset(h->d_counters, 0, 8 * sizeof(unsigned long long));
+    *out = h;
+    return GVDBX_OK;
+}
+
+static void gx_free_topology(gvdbx_t* h)
+{
+    for (int l = 0; l < GX_MAXLEV; l++) {
+        if (h->d_child[l]) cudaFree(h->d_child[l]);
+        if (h->d_npos[l]) cudaFree(h->d_npos[l]);
+        h->d_child[l] = nullptr; h->d_npos[l] = nullptr;
+    }
+    if (h->d_leaf) cudaFree(h->d_leaf);
+    h->d_leaf = nullptr;
+    h->have_topo = false;
+}
+static void gx_free_atlas(gvdbx_t* h)
+{
+    if (h->tex) cudaDestroyTextureObject(h->tex);
+    if (h->own_array) cudaFreeArray(h->own_array);
+    if (h->d_bricks) cudaFree(h->d_bricks);
+    h->tex = 0; h->own_array = nullptr; h->d_bricks = nullptr; h->have_atlas = false;
+}
+
+extern "C" int gvdbx_destroy(gvdbx_t* h)
+{
+    if (!h) return GVDBX_E_ARG;
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    gx_free_topology(h);
+    gx_free_atlas(h);
+    if (h->d_transfer) cudaFree(h->d_transfer);
+    if (h->d_counters) cudaFree(h->d_counters);
+    delete h;
+    return GVDBX_OK;
+}
+
+extern "C" const char* gvdbx_last_error(const gvdbx_t* h) { return h ? h->err.c_str() : "null handle"; }
+
+extern "C" int gvdbx_set_option(gvdbx_t* h, int option, int value)
+{
+    if (!h) return GVDBX_E_ARG;
+    switch (option) {
+    case GVDBX_OPT_SAMPLER:  if (value != 0 && value != 1) return gx_fail(h, GVDBX_E_ARG, "sampler must be 0 or 1"); h->sampler = value; break;
+    case GVDBX_OPT_BLOCK_W:  if (value < 1 || value > 32) return gx_fail(h, GVDBX_E_ARG, "block_w"); h->block_w = value; break;
+    case GVDBX_OPT_BLOCK_H:  if (value < 1 || value > 32) return gx_fail(h, GVDBX_E_ARG, "block_h"); h->block_h = value; break;
+    case GVDBX_OPT_COUNTERS: h->count = value ? 1 : 0; break;
+    default: return gx_fail(h, GVDBX_E_ARG, "unknown option");
+    }
+    if (h->block_w * h->block_h > 256) { h->block_w = 8; h->block_h = 8; return gx_fail(h, GVDBX_E_ARG, "block larger than 256 threads"); }
+    return GVDBX_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ topology
+extern "C" int gvdbx_import_topology(gvdbx_t* h, const void* vdbinfo)
+{
+    if (!h || !vdbinfo) return GVDBX_E_ARG;
+    GX_CUDA(h, cudaSetDevice(h->device));
+    GxVDBInfo v;
+    memcpy(&v, vdbinfo, sizeof v);
+    if (v.top_lev < 0 || v.top_lev >= GX_MAXLEV) return gx_fail(h, GVDBX_E_ARG, "top_lev out of range (0..4)");
+    if (v.clr_chan != GX_CHAN_UNDEF) return gx_fail(h, GVDBX_E_UNSUPPORTED, "colour channel (clr_chan) is not supported on this path");
+    if (v.atlas_apron != 1 || v.brick_res != GX_BRICK_DIM || v.res[0] != GX_BRICK_DIM - 2)
+        return gx_fail(h, GVDBX_E_UNSUPPORTED, "only 8^3 bricks with apron 1 are supported (brick_res 10)");
+    for (int l = 0; l <= v.top_lev; l++) {
+        if (v.dim[l] < 1 || v.dim[l] > 8 || v.res[l] != (1 << v.dim[l])) return gx_fail(h, GVDBX_E_ARG, "inconsistent dim/res");
+        if (v.nodecnt[l] <= 0 || v.nodelist[l] == 0) return gx_fail(h, GVDBX_E_ARG, "empty node pool below top_lev");
+        if (v.nodewid[l] < (int)sizeof(GxNode)) return gx_fail(h, GVDBX_E_ARG, "nodewid smaller than a node record");
+        if (l >= 1 && (v.childlist[l] == 0 || v.childwid[l] != 8 * (1 << (3 * v.dim[l]))))
+            return gx_fail(h, GVDBX_E_UNSUPPORTED, "child lists must be dense (bitmasks off): childwid = 8*res^3");
+    }
+    gx_free_topology(h);
+    for (int l = 1; l <= v.top_lev; l++) {
+        const int cells = 1 << (3 * v.dim[l]);
+        const size_t total = size_t(v.nodecnt[l]) * cells;
+        GX_CUDA(h, cudaMalloc(&h->d_child[l], total * sizeof(int)));
+        GX_CUDA(h, cudaMalloc(&h->d_npos[l], size_t(v.nodecnt[l]) * sizeof(int4)));
+        const int threads = 256;
+        const unsigned blocks = (unsigned)((total + threads - 1) / threads);
+        gx_build_child_table<<<blocks, threads, 0, h->stream>>>((const char*)v.nodelist[l], v.nodewid[l], v.nodecnt[l],
+                                                               (const char*)v.childlist[l], v.childwid[l], cells,
+                                                               h->d_child[l], h->d_npos[l]);
+        GX_CUDA(h, cudaGetLastError());
+    }
+    GX_CUDA(h, cudaMalloc(&h->d_leaf, size_t(v.nodecnt[0]) * sizeof(GxLeafRec)));
+    gx_build_leaf_table<<<(v.nodecnt[0] + 255) / 256, 256, 0, h->stream>>>((const char*)v.nodelist[0], v.nodewid[0], v.nodecnt[0],
+                                                                          v.brick_res, v.atlas_apron, v.atlas_cnt.x, v.atlas_cnt.y, h->d_leaf);
+    GX_CUDA(h, cudaGetLastError());
+    h->vdb = v;
+    h->have_topo = true;
+    return GVDBX_OK;
+}
+
+extern "C" int gvdbx_import_topology_host(gvdbx_t* h, const void* vdbinfo, const void* const* pool0, const void* const* pool1,
+                                          const uint64_t* pool1_bytes)
+{
+    if (!h || !vdbinfo || !pool0 || !pool1 || !pool1_bytes) return GVDBX_E_ARG;
+    GX_CUDA(h, cudaSetDevice(h->device));
+    GxVDBInfo v;
+    memcpy(&v, vdbinfo, sizeof v);
+    if (v.top_lev < 0 || v.top_lev >= GX_MAXLEV) return gx_fail(h, GVDBX_E_ARG, "top_lev out of range (0..4)");
+    std::vector<void*> tmp;
+    int rc = GVDBX_OK;
+    auto up = [&](const void* src, size_t bytes, uint64_t* dst) -> bool {
+        void* d = nullptr;
+        if (bytes == 0 || !src) { *dst = 0; return true; }
+        if (cudaMalloc(&d, bytes) != cudaSuccess) return false;
+        tmp.push_back(d);
+        if (cudaMemcpyAsync(d, src, bytes, cudaMemcpyHostToDevice, h->stream) != cudaSuccess) return false;
+        *dst = (uint64_t)d;
+        return true;
+    };
+    for (int l = 0; l <= v.top_lev && rc == GVDBX_OK; l++) {
+        if (!up(pool0[l], size_t(v.nodecnt[l]) * v.nodewid[l], &v.nodelist[l])) rc = GVDBX_E_CUDA;
+        if (l >= 1 && !up(pool1[l], (size_t)pool1_bytes[l], &v.childlist[l])) rc = GVDBX_E_CUDA;
+    }
+    if (rc == GVDBX_OK) rc = gvdbx_import_topology(h, &v);
+    else h->err = "pool upload failed";
+    cudaStreamSynchronize(h->stream);
+    for (void* d : tmp) cudaFree(d);
+    return rc;
+}
+
+// ------------------------------------------------------------------------------------------------ atlas
+static int gx_make_texture(gvdbx_t* h, cudaArray_t arr)
+{
+    // same descriptor as SetupAtlasAccess (gvdb_volume_gvdb.cpp:753-783): linear filter, element-type reads,
+    // unnormalised coordinates, clamp addressing
+    cudaResourceDesc rd;
+    memset(&rd, 0, sizeof rd);
+    rd.resType = cudaResourceTypeArray;
+    rd.res.array.array = arr;
+    cudaTextureDesc td;
+    memset(&td, 0, sizeof td);
+    td.filterMode = cudaFilterModeLinear;
+    td.readMode = cudaReadModeElementType;
+    td.addressMode[0] = td.addressMode[1] = td.addressMode[2] = cudaAddressModeClamp;
+    td.normalizedCoords = 0;
+    GX_CUDA(h, cudaCreateTextureObject(&h->tex, &rd, &td, nullptr));
+    return GVDBX_OK;
+}
+
+static int gx_repack(gvdbx_t* h, const float* d_linear, int rx, int ry, int rz)
+{
+    if (rx % GX_BRICK_DIM || ry % GX_BRICK_DIM || rz % GX_BRICK_DIM)
+        return gx_fail(h, GVDBX_E_UNSUPPORTED, "atlas resolution must be a multiple of the 10^3 brick");
+    const int cx = rx / GX_BRICK_DIM, cy = ry / GX_BRICK_DIM, cz = rz / GX_BRICK_DIM;
+    const size_t slots = size_t(cx) * cy * cz;
+    GX_CUDA(h, cudaMalloc(&h->d_bricks, slots * GX_BRICK_STRIDE * sizeof(float)));
+    gx_repack_atlas<<<(unsigned)slots, 256, 0, h->stream>>>(d_linear, rx, ry, rz, cx, cy, h->d_bricks);
+    GX_CUDA(h, cudaGetLastError());
+    h->ares[0] = rx; h->ares[1] = ry; h->ares[2] = rz;
+    return GVDBX_OK;
+}
+
+extern "C" int gvdbx_import_atlas_array(gvdbx_t* h, int chan, void* cuarray, int rx, int ry, int rz)
+{
+    if (!h || !cuarray || rx <= 0 || ry <= 0 || rz <= 0) return GVDBX_E_ARG;
+    if (chan != 0) return gx_fail(h, GVDBX_E_UNSUPPORTED, "only channel 0 (T_FLOAT) is supported");
+    GX_CUDA(h, cudaSetDevice(h->device));
+    gx_free_atlas(h);
+    int rc = gx_make_texture(h, (cudaArray_t)cuarray);
+    if (rc) return rc;
+    float* d_lin = nullptr;
+    GX_CUDA(h, cudaMalloc(&d_lin, size_t(rx) * ry * rz * sizeof(float)));
+    cudaMemcpy3DParms cp;
+    memset(&cp, 0, sizeof cp);
+    cp.srcArray = (cudaArray_t)cuarray;
+    cp.dstPtr = make_cudaPitchedPtr(d_lin, size_t(rx) * sizeof(float), rx, ry);
+    cp.extent = make_cudaExtent(rx, ry, rz);
+    cp.kind = cudaMemcpyDeviceToDevice;
+    cudaError_t e = cudaMemcpy3DAsync(&cp, h->stream);
+    if (e == cudaSuccess) rc = gx_repack(h, d_lin, rx, ry, rz);
+    cudaStreamSynchronize(h->stream);
+    cudaFree(d_lin);
+    if (e != cudaSuccess) { h->err = std::string("cudaMemcpy3DAsync: ") + cudaGetErrorString(e); return GVDBX_E_CUDA; }
+    if (rc) return rc;
+    h->have_atlas = true;
+    return GVDBX_OK;
+}
+
+extern "C" int gvdbx_import_atlas_host(gvdbx_t* h, int chan, const float* texels, int rx, int ry, int rz)
+{
+    if (!h || !texels || rx <= 0 || ry <= 0 || rz <= 0) return GVDBX_E_ARG;
+    if (chan != 0) return gx_fail(h, GVDBX_E_UNSUPPORTED, "only channel 0 (T_FLOAT) is supported");
+    GX_CUDA(h, cudaSetDevice(h->device));
+    gx_free_atlas(h);
+    cudaChannelFormatDesc fd = cudaCreateChannelDesc<float>();
+    GX_CUDA(h, cudaMalloc3DArray(&h->own_array, &fd, make_cudaExtent(rx, ry, rz), cudaArraySurfaceLoadStore));
+    cudaMemcpy3DParms cp;
+    memset(&cp, 0, sizeof cp);
+    cp.srcPtr = make_cudaPitchedPtr((void*)texels, size_t(rx) * sizeof(float), rx, ry);
+    cp.dstArray = h->own_array;
+    cp.extent = make_cudaExtent(rx, ry, rz);
+    cp.kind = cudaMemcpyHostToDevice;
+    GX_CUDA(h, cudaMemcpy3DAsync(&cp, h->stream));
+    int rc = gx_make_texture(h, h->own_array);
+    if (rc) return rc;
+    float* d_lin = nullptr;
+    const size_t bytes = size_t(rx) * ry * rz * sizeof(float);
+    GX_CUDA(h, cudaMalloc(&d_lin, bytes));
+    cudaError_t e = cudaMemcpyAsync(d_lin, texels, bytes, cudaMemcpyHostToDevice, h->stream);
+    if (e == cudaSuccess) rc = gx_repack(h, d_lin, rx, ry, rz);
+    cudaStreamSynchronize(h->stream);
+    cudaFree(d_lin);
+    if (e != cudaSuccess) { h->err = std::string("cudaMemcpyAsync: ") + cudaGetErrorString(e); return GVDBX_E_CUDA; }
+    if (rc) return rc;
+    h->have_atlas = true;
+    return GVDBX_OK;
+}
+
+extern "C" int gvdbx_set_transfer(gvdbx_t* h, const float* rgba_host)
+{
+    if (!h || !rgba_host) return GVDBX_E_ARG;
+    GX_CUDA(h, cudaSetDevice(h->device));
+    if (!h->d_transfer) GX_CUDA(h, cudaMalloc(&h->d_transfer, GVDBX_TRANSFER_ENTRIES * sizeof(float4)));
+    GX_CUDA(h, cudaMemcpyAsync(h->d_transfer, rgba_host, GVDBX_TRANSFER_ENTRIES * sizeof(float4), cudaMemcpyHostToDevice, h->stream));
+    GX_CUDA(h, cudaStreamSynchronize(h->stream));      // the host buffer may be reused by the caller
+    return GVDBX_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ render
+typedef void (*gx_kernel_t)(const GxParams);
+
+template <int MODE, int SAMPLER>
+static gx_kernel_t gx_pick_flags(int flags)
+{
+    switch (flags) {
+    case 0: return gx_render_kernel<MODE, SAMPLER, 0>;
+    case GX_FLAG_DEBUG | GX_FLAG_COUNT: return gx_render_kernel<MODE, SAMPLER, GX_FLAG_DEBUG | GX_FLAG_COUNT>;
+    case GX_FLAG_TILES: return gx_render_kernel<MODE, SAMPLER, GX_FLAG_TILES>;
+    }
+    return nullptr;
+}
+template <int MODE>
+static gx_kernel_t gx_pick_sampler(int sampler, int flags)
+{
+    return sampler == GX_SAMPLER_TEX ? gx_pick_flags<MODE, GX_SAMPLER_TEX>(flags) : gx_pick_flags<MODE, GX_SAMPLER_LINEAR>(flags);
+}
+static gx_kernel_t gx_pick(int mode, int sampler, int flags)
+{
+    switch (mode) {
+    case GX_MODE_VOXEL:     return gx_pick_sampler<GX_MODE_VOXEL>(sampler, flags);
+    case GX_MODE_TRILINEAR: return gx_pick_sampler<GX_MODE_TRILINEAR>(sampler, flags);
+    case GX_MODE_LEVELSET:  return gx_pick_sampler<GX_MODE_LEVELSET>(sampler, flags);
+    case GX_MODE_DEEP:      return gx_pick_sampler<GX_MODE_DEEP>(sampler, flags);
+    }
+    return nullptr;
+}
+
+static inline float3 f3(const GxF3& a) { return make_float3(a.x, a.y, a.z); }
+
+static int gx_fill_params(gvdbx_t* h, const void* scninfo, int shade_mode, int chan, GxParams& P, int& mode)
+{
+    if (!h || !scninfo) return GVDBX_E_ARG;
+    if (!h->have_topo) return gx_fail(h, GVDBX_E_STATE, "render before gvdbx_import_topology");
+    if (!h->have_atlas) return gx_fail(h, GVDBX_E_STATE, "render before gvdbx_import_atlas_*");
+    if (chan != 0) return gx_fail(h, GVDBX_E_UNSUPPORTED, "only channel 0 is supported");
+    switch (shade_mode) {
+    case GVDBX_SHADE_VOXEL:     mode = GX_MODE_VOXEL; break;
+    case GVDBX_SHADE_TRILINEAR: mode = GX_MODE_TRILINEAR; break;
+    case GVDBX_SHADE_LEVELSET:  mode = GX_MODE_LEVELSET; break;
+    case GVDBX_SHADE_VOLUME:    mode = GX_MODE_DEEP; break;
+    default: return gx_fail(h, GVDBX_E_UNSUPPORTED, "shade mode outside the hot path (supported: VOXEL 0, TRILINEAR 4, LEVELSET 6, VOLUME 7)");
+    }
+    GxScnInfo s;
+    memcpy(&s, scninfo, sizeof s);
+    if (s.width <= 0 || s.height <= 0) return gx_fail(h, GVDBX_E_ARG, "ScnInfo width/height");
+    memset(&P, 0, sizeof P);
+    P.width = s.width; P.height = s.height; P.camnear = s.camnear; P.camfar = s.camfar;
+    P.campos = f3(s.campos); P.cams = f3(s.cams); P.camu = f3(s.camu); P.camv = f3(s.camv);
+    P.light_pos = f3(s.light_pos); P.shadow_params = f3(s.shadow_params);
+    P.backclr = make_float4(s.backclr.x, s.backclr.y, s.backclr.z, s.backclr.w);
+    memcpy(P.xform, s.xform, sizeof P.xform);
+    memcpy(P.invxform, s.invxform, sizeof P.invxform);
+    memcpy(P.invxrot, s.invxrot, sizeof P.invxrot);
+    P.extinct = f3(s.extinct); P.steps = f3(s.steps); P.cutoff = f3(s.cutoff); P.thresh = f3(s.thresh);
+    P.transfer = h->d_transfer ? h->d_transfer : (const float4*)s.transfer;
+    if (mode == GX_MODE_DEEP && !P.transfer)
+        return gx_fail(h, GVDBX_E_STATE, "transfer function not on GPU (reference: 'Must call CommitTransferFunc')");
+    P.dbuf = (const float*)s.dbuf;
+    const GxVDBInfo& v = h->vdb;
+    for (int l = 0; l < GX_MAXLEV; l++) {
+        P.dim[l] = v.dim[l]; P.res[l] = v.res[l]; P.vdel[l] = f3(v.vdel[l]);
+        P.child[l] = h->d_child[l]; P.npos[l] = h->d_npos[l];
+    }
+    P.top_lev = v.top_lev; P.epsilon = v.epsilon; P.bmin = f3(v.bmin); P.bmax = f3(v.bmax);
+    P.leaf = h->d_leaf;
+    P.tex = h->tex; P.bricks = h->d_bricks;
+    P.counters = h->d_counters;
+    P.out_stride = s.width;
+    P.x0 = 0; P.y0 = 0; P.x1 = s.width; P.y1 = s.height;
+    return GVDBX_OK;
+}
+
+extern "C" int gvdbx_render(gvdbx_t* h, const void* scninfo, int shade_mode, int chan, uint64_t outbuf_d,
+                            int tx0, int ty0, int tw, int th)
+{
+    if (!h) return GVDBX_E_ARG;
+    GX_CUDA(h, cudaSetDevice(h->device));
+    if (shade_mode == GVDBX_SHADE_OFF) {    // gvdb_volume_gvdb.cpp:4340-4346
+        const GxScnInfo* s = (const GxScnInfo*)scninfo;
+        if (!s || !outbuf_d) return GVDBX_E_ARG;
+        GX_CUDA(h, cudaMemsetAsync((void*)outbuf_d, 0, size_t(s->width) * s->height * 4, h->stream));
+        return GVDBX_OK;
+    }
+    GxParams P; int mode = 0;
+    int rc = gx_fill_params(h, scninfo, shade_mode, chan, P, mode);
+    if (rc) return rc;
+    if (!outbuf_d) return gx_fail(h, GVDBX_E_ARG, "null output buffer");
+    if (tw > 0 && th > 0) {
+        if (tx0 < 0 || ty0 < 0 || tx0 + tw > P.width || ty0 + th > P.height) return gx_fail(h, GVDBX_E_ARG, "tile outside the frame");
+        P.x0 = tx0; P.y0 = ty0; P.x1 = tx0 + tw; P.y1 = ty0 + th;
+    }
+    P.out = (uchar4*)outbuf_d;
+    const int flags = h->count ? (GX_FLAG_DEBUG | GX_FLAG_COUNT) : 0;
+    float4* dbg_tmp = nullptr;
+    if (h->count) {     // counted renders reuse the debug variant; give it a scratch debug buffer
+        GX_CUDA(h, cudaMalloc(&dbg_tmp, size_t(P.width) * P.height * 48));
+        P.dbg = dbg_tmp;
+        GX_CUDA(h, cudaMemsetAsync(h->d_counters, 0, 8 * sizeof(unsigned long long), h->stream));
+    }
+    gx_kernel_t k = gx_pick(mode, h->sampler, flags);
+    dim3 block(h->block_w, h->block_h, 1);
+    dim3 grid((P.x1 - P.x0 + block.x - 1) / block.x, (P.y1 - P.y0 + block.y - 1) / block.y, 1);
+    k<<<grid, block, 0, h->stream>>>(P);
+    GX_CUDA(h, cudaGetLastError());
+    if (dbg_tmp) { cudaStreamSynchronize(h->stream); cudaFree(dbg_tmp); }
+    return GVDBX_OK;
+}
+
+extern "C" int gvdbx_render_debug(gvdbx_t* h, const void* scninfo, int shade_mode, int chan, uint64_t outbuf_d, uint64_t dbg_d)
+{
+    if (!h) return GVDBX_E_ARG;
+    GX_CUDA(h, cudaSetDevice(h->device));
+    GxParams P; int mode = 0;
+    int rc = gx_fill_params(h, scninfo, shade_mode, chan, P, mode);
+    if (rc) return rc;
+    if (!outbuf_d || !dbg_d) return gx_fail(h, GVDBX_E_ARG, "null output buffer");
+    P.out = (uchar4*)outbuf_d;
+    P.dbg = (float4*)dbg_d;
+    GX_CUDA(h, cudaMemsetAsync(h->d_counters, 0, 8 * sizeof(unsigned long long), h->stream));
+    gx_kernel_t k = gx_pick(mode, h->sampler, GX_FLAG_DEBUG | GX_FLAG_COUNT);
+    dim3 block(h->block_w, h->block_h, 1);
+    dim3 grid((P.width + block.x - 1) / block.x, (P.height + block.y - 1) / block.y, 1);
+    k<<<grid, block, 0, h->stream>>>(P);
+    GX_CUDA(h, cudaGetLastError());
+    return GVDBX_OK;
+}
+
+extern "C" int gvdbx_tiles_per_rank(int width, int height, int tile_size, int nranks)
+{
+    if (width <= 0 || height <= 0 || tile_size <= 0 || nranks <= 0) return GVDBX_E_ARG;
+    const int tiles = ((width + tile_size - 1) / tile_size) * ((height + tile_size - 1) / tile_size);
+    return (tiles + nranks - 1) / nranks;
+}
+
+extern "C" int gvdbx_render_tiles(gvdbx_t* h, const void* scninfo, int shade_mode, int chan, uint64_t packed_d,
+                                  int tile_size, int rank, int nranks)
+{
+    if (!h) return GVDBX_E_ARG;
+    GX_CUDA(h, cudaSetDevice(h->device));
+    GxParams P; int mode = 0;
+    int rc = gx_fill_params(h, scninfo, shade_mode, chan, P, mode);
+    if (rc) return rc;
+    if (!packed_d || nranks <= 0 || rank < 0 || rank >= nranks) return gx_fail(h, GVDBX_E_ARG, "rank/nranks/buffer");
+    if (tile_size <= 0 || tile_size % h->block_w || tile_size % h->block_h)
+        return gx_fail(h, GVDBX_E_ARG, "tile_size must be a multiple of the CTA tile");
+    P.out = (uchar4*)packed_d;
+    P.tile_size = tile_size;
+    P.tiles_x = (P.width + tile_size - 1) / tile_size;
+    P.ntiles = P.tiles_x * ((P.height + tile_size - 1) / tile_size);
+    P.rank = rank; P.nranks = nranks;
+    const int slots = (P.ntiles + nranks - 1) / nranks;
+    gx_kernel_t k = gx_pick(mode, h->sampler, GX_FLAG_TILES);
+    dim3 block(h->block_w, h->block_h, 1);
+    dim3 grid((tile_size / h->block_w) * (tile_size / h->block_h), slots, 1);
+    k<<<grid, block, 0, h->stream>>>(P);
+    GX_CUDA(h, cudaGetLastError());
+    return GVDBX_OK;
+}
+
+extern "C" int gvdbx_assemble_tiles(gvdbx_t* h, uint64_t gathered_d, uint64_t frame_d, int width, int height, int tile_size, int nranks)
+{
+    if (!h || !gathered_d || !frame_d || width <= 0 || height <= 0 || tile_size <= 0 || nranks <= 0) return GVDBX_E_ARG;
+    GX_CUDA(h, cudaSetDevice(h->device));
+    const int tiles_x = (width + tile_size - 1) / tile_size;
+    const int ntiles = tiles_x * ((height + tile_size - 1) / tile_size);
+    const int slots = (ntiles + nranks - 1) / nranks;
+    dim3 grid((tile_size * tile_size + 255) / 256, ntiles, 1);
+    gx_assemble_tiles<<<grid, 256, 0, h->stream>>>((const uchar4*)gathered_d, (uchar4*)frame_d, width, height, tile_size, tiles_x, ntiles, nranks, slots);
+    GX_CUDA(h, cudaGetLastError());
+    return GVDBX_OK;
+}
+
+extern "C" int gvdbx_read_buffer(gvdbx_t* h, uint64_t buf_d, void* host, size_t bytes)
+{
+    if (!h || !buf_d || !host) return GVDBX_E_ARG;
+    GX_CUDA(h, cudaSetDevice(h->device));
+    GX_CUDA(h, cudaMemcpyAsync(host, (const void*)buf_d, bytes, cudaMemcpyDeviceToHost, h->stream));
+    GX_CUDA(h, cudaStreamSynchronize(h->stream));
+    return GVDBX_OK;
+}
+
+extern "C" int gvdbx_sync(gvdbx_t* h)
+{
+    if (!h) return GVDBX_E_ARG;
+    GX_CUDA(h, cudaSetDevice(h->device));
+    GX_CUDA(h, cudaStreamSynchronize(h->stream));
+    return GVDBX_OK;
+}
+
+extern "C" int gvdbx_get_counters(gvdbx_t* h, gvdbx_counters* out)
+{
+    if (!h || !out) return GVDBX_E_ARG;
+    GX_CUDA(h, cudaSetDevice(h->device));
+    unsigned long long v[8];
+    GX_CUDA(h, cudaMemcpyAsync(v, h->d_counters, sizeof v, cudaMemcpyDeviceToHost, h->stream));
+    GX_CUDA(h, cudaStreamSynchronize(h->stream));
+    out->s_tri = v[0]; out->s_pt = v[1]; out->n_dda = v[2]; out->n_desc = v[3]; out->s_lut = v[4]; out->rays = v[5];
+    return GVDBX_OK;
+}
+
+extern "C" int gvdbx_sample_points(gvdbx_t* h, int chan, uint64_t xyz_d, int n, uint64_t out_tex_d, uint64_t out_lin_d)
+{
+    if (!h || !xyz_d || !out_tex_d || !out_lin_d || n <= 0) return GVDBX_E_ARG;
+    if (!h->have_atlas) return gx_fail(h, GVDBX_E_STATE, "no atlas imported");
+    if (chan != 0) return gx_fail(h, GVDBX_E_UNSUPPORTED, "only channel 0 is supported");
+    GX_CUDA(h, cudaSetDevice(h->device));
+    GxParams P;
+    memset(&P, 0, sizeof P);
+    P.tex = h->tex; P.bricks = h->d_bricks;
+    gx_sample_points_kernel<<<(n + 255) / 256, 256, 0, h->stream>>>(P, (const float*)xyz_d, n, h->ares[0] / GX_BRICK_DIM,
+                                                                   h->ares[1] / GX_BRICK_DIM, (float*)out_tex_d, (float*)out_lin_d);
+    GX_CUDA(h, cudaGetLastError());
+    return GVDBX_OK;
+}

@@ -1,0 +1,730 @@
+// gvdbx_device.cuh — device side of the B200-native GVDB ray-cast render path (sm_100a).
+//
+// What is computed (reference, relative to source/gvdb_library/kernels/):
+//   ray generation      cuda_gvdb_geom.cuh:48-63   (getViewPos / getViewRay)
+//   slab test           cuda_gvdb_geom.cuh:85-98   (rayBoxIntersect)
+//   hierarchical DDA    cuda_gvdb_dda.cuh:38-91    (HDDAState), cuda_gvdb_raycast.cuh:543-611 (rayCast)
+//   brick samplers      cuda_gvdb_raycast.cuh:227-265 (voxel), :281-300 (trilinear), :389-410 + :186-197 (level set),
+//                       :485-533 (deep) + cuda_gvdb_dda.cuh:20-23 (transfer)
+//   gradients           cuda_gvdb_raycast.cuh:132-157
+//   shading + packing   cuda_gvdb_module.cu:38-57, :60-181
+//
+// How it is laid out here (B200-first, not a translation):
+//   * all per-frame state (scene + tree geometry + table pointers) travels as ONE __grid_constant__ kernel parameter
+//     -> constant-bank reads, instead of the reference's VDBInfo struct in global memory (42 LDG sites per kernel);
+//   * the tree is traversed through compact tables built at import time: per level one int32 child table indexed by
+//     NODE index (4 B per cell, one dependent load per DDA step instead of node->mChildList->clist[b] = 3 loads of
+//     64 B + 8 B), one int4 position record per internal node and one 32-B record per leaf;
+//   * the brick atlas is available both as the caller's 3-D array through a texture object (bit-exact hardware
+//     trilinear) and re-laid out brick-major (4 KB per 10^3 brick, contiguous) for plain vectorisable loads with a
+//     software emulation of the texture unit's 1.8 fixed-point filtering;
+//   * warps are 8x4 pixel tiles; the per-level traversal stack lives in registers (levels 1..4), not local memory.
+//
+// Floating-point contract: SHADE_VOXEL output must be BIT-EXACT against the reference module compiled with its own
+// flag (--use_fast_math).  This file is therefore compiled with --use_fast_math too, and every expression on the
+// exact path keeps the reference's operand order, literal types (several literals are double) and division /
+// rsqrt / exp forms so that nvcc's contraction and approximation choices coincide.  Do not "simplify" them.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "gvdbx_types.h"
+
+#define GX_MODE_VOXEL     0
+#define GX_MODE_TRILINEAR 1
+#define GX_MODE_LEVELSET  2
+#define GX_MODE_DEEP      3
+
+#define GX_SAMPLER_TEX    0
+#define GX_SAMPLER_LINEAR 1
+
+#define GX_BRICK_STRIDE   1024     // floats per brick slot in the brick-major atlas (10^3 used, 4 KB aligned)
+#define GX_BRICK_DIM      10       // brick res incl. apron for the brick-major layout (res0 8 + 2*apron 1)
+
+// ------------------------------------------------------------------------------------------------ parameters
+struct alignas(16) GxLeafRec {     // 32 B, one per level-0 node
+    int px, py, pz;                // mPos   : index-space min corner
+    int base;                      // float offset of the brick in the brick-major atlas
+    int vx, vy, vz;                // mValue : atlas texel of the first interior voxel
+    int pad;
+};
+
+struct GxParams {
+    // ---- scene (ScnInfo fields the path reads)
+    int      width, height;
+    float    camnear, camfar;
+    float3   campos, cams, camu, camv;
+    float3   light_pos;
+    float3   shadow_params;        // x = SHADOWAMT, y = SHADOWBIAS
+    float4   backclr;
+    float    xform[16], invxform[16], invxrot[16];
+    float3   extinct;              // x = EXTINCT, y = ALBEDO
+    float3   steps;                // x = DIRECTSTEP, y = SHADOWSTEP, z = FINESTEP
+    float3   cutoff;               // x = MINVAL, y = ALPHACUT
+    float3   thresh;               // x = THRESH, y = VMIN, z = VMAX
+    const float4* transfer;
+    const float*  dbuf;
+    // ---- tree geometry (VDBInfo fields the path reads)
+    int      dim[GX_MAXLEV];
+    int      res[GX_MAXLEV];
+    float3   vdel[GX_MAXLEV];
+    int      top_lev;
+    float    epsilon;
+    float3   bmin, bmax;
+    // ---- compact traversal tables
+    const int*       child[GX_MAXLEV];   // child[lev][node * cells(lev) + b] = index at lev-1, or -1
+    const int4*      npos[GX_MAXLEV];    // npos[lev][node] = {mPos, 0}            (lev >= 1)
+    const GxLeafRec* leaf;               // leaf[node]                              (lev == 0)
+    // ---- atlas
+    cudaTextureObject_t tex;             // caller's 3-D array, linear filter, unnormalised, clamp
+    const float*        bricks;          // brick-major copy
+    // ---- output
+    uchar4*  out;
+    float4*  dbg;                        // 3 x 16 B per pixel (debug variant only)
+    unsigned long long* counters;        // 6 x u64 (count variant only)
+    int      out_stride;                 // pixels per output row
+    int      x0, y0, x1, y1;             // pixel rectangle [x0,x1) x [y0,y1)
+    // ---- tile-list mode (multi-GPU): tiles with id % nranks == rank, packed tile after tile
+    int      tile_size, tiles_x, ntiles, rank, nranks;
+};
+
+// ------------------------------------------------------------------------------------------------ small vector algebra
+// component-wise, written out so that operand order is explicit on the exact path
+__device__ __forceinline__ float3 gx3(float x, float y, float z) { return make_float3(x, y, z); }
+__device__ __forceinline__ float3 operator+(float3 a, float3 b) { return make_float3(a.x + b.x, a.y + b.y, a.z + b.z); }
+__device__ __forceinline__ float3 operator-(float3 a, float3 b) { return make_float3(a.x - b.x, a.y - b.y, a.z - b.z); }
+__device__ __forceinline__ float3 operator*(float3 a, float3 b) { return make_float3(a.x * b.x, a.y * b.y, a.z * b.z); }
+__device__ __forceinline__ float3 operator/(float3 a, float3 b) { return make_float3(a.x / b.x, a.y / b.y, a.z / b.z); }
+__device__ __forceinline__ float3 operator+(float3 a, float b)  { return make_float3(a.x + b, a.y + b, a.z + b); }
+__device__ __forceinline__ float3 operator-(float3 a, float b)  { return make_float3(a.x - b, a.y - b, a.z - b); }
+__device__ __forceinline__ float3 operator*(float3 a, float b)  { return make_float3(a.x * b, a.y * b, a.z * b); }
+__device__ __forceinline__ float3 operator*(float b, float3 a)  { return make_float3(b * a.x, b * a.y, b * a.z); }
+__device__ __forceinline__ float3 operator/(float b, float3 a)  { return make_float3(b / a.x, b / a.y, b / a.z); }
+__device__ __forceinline__ void   operator+=(float3& a, float3 b) { a.x += b.x; a.y += b.y; a.z += b.z; }
+__device__ __forceinline__ void   operator-=(float3& a, float3 b) { a.x -= b.x; a.y -= b.y; a.z -= b.z; }
+__device__ __forceinline__ float  gx_dot(float3 a, float3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+__device__ __forceinline__ float3 gx_normalize(float3 v) { float inv = rsqrtf(gx_dot(v, v)); return v * inv; }
+__device__ __forceinline__ float3 gx_floor(float3 a) { return make_float3(floorf(a.x), floorf(a.y), floorf(a.z)); }
+__device__ __forceinline__ float3 gx_fabs(float3 a) { return make_float3(fabsf(a.x), fabsf(a.y), fabsf(a.z)); }
+__device__ __forceinline__ float3 gx_f3(int3 a) { return make_float3(float(a.x), float(a.y), float(a.z)); }
+__device__ __forceinline__ int3   gx_i3(float3 a) { return make_int3(int(a.x), int(a.y), int(a.z)); }
+// column-major 4x4 times (v,1)  (cuda_math.cuh:1472)
+__device__ __forceinline__ float3 gx_mmult(const float* m, float3 v)
+{
+    float3 p;
+    p.x = v.x * m[0] + v.y * m[4] + v.z * m[8] + m[12];
+    p.y = v.x * m[1] + v.y * m[5] + v.z * m[9] + m[13];
+    p.z = v.x * m[2] + v.y * m[6] + v.z * m[10] + m[14];
+    return p;
+}
+
+// ------------------------------------------------------------------------------------------------ work counters
+struct GxCount { unsigned int s_tri, s_pt, n_dda, n_desc, s_lut, rays; };
+
+// ------------------------------------------------------------------------------------------------ samplers
+// Both take ATLAS-space coordinates exactly as the reference passes them to tex3D (p + o).
+template <int SAMPLER> struct GxSampler;
+
+template <> struct GxSampler<GX_SAMPLER_TEX> {
+    cudaTextureObject_t tex;
+    __device__ __forceinline__ GxSampler(const GxParams& P) : tex(P.tex) {}
+    __device__ __forceinline__ void enter(const GxLeafRec&) {}
+    // filtered fetch at atlas coordinate (x,y,z)
+    __device__ __forceinline__ float tri(float x, float y, float z) const { return tex3D<float>(tex, x, y, z); }
+    // exact voxel value at integer atlas texel (ix,iy,iz): texel centres sit at +0.5 -> filter weights are 0
+    __device__ __forceinline__ float point(float x, float y, float z) const { return tex3D<float>(tex, x, y, z); }
+};
+
+// Software model of the texture unit's trilinear filter on the brick-major layout.
+//   xB = x - 0.5 ; i = floor(xB) ; a = frac(xB) quantised to 8 fractional bits (1.8 fixed point), nearest
+// The two x-neighbours of a sample are adjacent floats; a brick is one contiguous 4 KB block, so a warp marching
+// through one brick touches at most 32 consecutive 128-B lines.
+#ifndef GX_TRI_VARIANT
+#define GX_TRI_VARIANT 0
+#endif
+__device__ __forceinline__ float gx_quant8(float a) { return floorf(a * 256.0f + 0.5f) * (1.0f / 256.0f); }
+
+template <> struct GxSampler<GX_SAMPLER_LINEAR> {
+    const float* bricks;
+    const float* b;      // current brick
+    float ox, oy, oz;    // atlas coordinate of the brick's texel (0,0,0) = mValue - apron
+    __device__ __forceinline__ GxSampler(const GxParams& P) : bricks(P.bricks), b(P.bricks), ox(0), oy(0), oz(0) {}
+    __device__ __forceinline__ void enter(const GxLeafRec& L)
+    {
+        b = bricks + L.base;
+        ox = float(L.vx - 1); oy = float(L.vy - 1); oz = float(L.vz - 1);
+    }
+    __device__ __forceinline__ float tri(float x, float y, float z) const
+    {
+        // brick-local continuous coordinate, shifted to texel-centre space
+        float xb = (x - ox) - 0.5f, yb = (y - oy) - 0.5f, zb = (z - oz) - 0.5f;
+        float fx = floorf(xb), fy = floorf(yb), fz = floorf(zb);
+        float ax = gx_quant8(xb - fx), ay = gx_quant8(yb - fy), az = gx_quant8(zb - fz);
+        int ix = int(fx), iy = int(fy), iz = int(fz);
+        // rounding may carry the weight to 1.0: fold into the next texel
+        if (ax >= 1.0f) { ax = 0.0f; ix++; }
+        if (ay >= 1.0f) { ay = 0.0f; iy++; }
+        if (az >= 1.0f) { az = 0.0f; iz++; }
+        int ix1 = min(ix + 1, GX_BRICK_DIM - 1), iy1 = min(iy + 1, GX_BRICK_DIM - 1), iz1 = min(iz + 1, GX_BRICK_DIM - 1);
+        ix = max(min(ix, GX_BRICK_DIM - 1), 0); iy = max(min(iy, GX_BRICK_DIM - 1), 0); iz = max(min(iz, GX_BRICK_DIM - 1), 0);
+        ix1 = max(ix1, 0); iy1 = max(iy1, 0); iz1 = max(iz1, 0);
+        const float* r00 = b + (iz * GX_BRICK_DIM + iy) * GX_BRICK_DIM;
+        const float* r10 = b + (iz * GX_BRICK_DIM + iy1) * GX_BRICK_DIM;
+        const float* r01 = b + (iz1 * GX_BRICK_DIM + iy) * GX_BRICK_DIM;
+        const float* r11 = b + (iz1 * GX_BRICK_DIM + iy1) * GX_BRICK_DIM;
+        float c000 = __ldg(r00 + ix), c100 = __ldg(r00 + ix1);
+        float c010 = __ldg(r10 + ix), c110 = __ldg(r10 + ix1);
+        float c001 = __ldg(r01 + ix), c101 = __ldg(r01 + ix1);
+        float c011 = __ldg(r11 + ix), c111 = __ldg(r11 + ix1);
+#if GX_TRI_VARIANT == 0
+        float x00 = c000 + ax * (c100 - c000), x10 = c010 + ax * (c110 - c010);
+        float x01 = c001 + ax * (c101 - c001), x11 = c011 + ax * (c111 - c011);
+        float y0 = x00 + ay * (x10 - x00), y1 = x01 + ay * (x11 - x01);
+        return y0 + az * (y1 - y0);
+#else
+        float bx = 1.0f - ax, by = 1.0f - ay, bz = 1.0f - az;
+        return bz * (by * (bx * c000 + ax * c100) + ay * (bx * c010 + ax * c110))
+             + az * (by * (bx * c001 + ax * c101) + ay * (bx * c011 + ax * c111));
+#endif
+    }
+    __device__ __forceinline__ float point(float x, float y, float z) const
+    {
+        int ix = int(x - ox), iy = int(y - oy), iz = int(z - oz);    // x = texel + 0.5 -> truncation gives the texel
+        return __ldg(b + (iz * GX_BRICK_DIM + iy) * GX_BRICK_DIM + ix);
+    }
+};
+
+// ------------------------------------------------------------------------------------------------ geometry
+// slab test: (tnear clamped to >= 0, tfar, 0 | NOHIT)                       cuda_gvdb_geom.cuh:85-98
+__device__ __forceinline__ float3 gx_ray_box(float3 rpos, float3 rdir, float3 vmin, float3 vmax)
+{
+    float t0 = (vmin.x - rpos.x) / rdir.x;
+    float t1 = (vmax.x - rpos.x) / rdir.x;
+    float t2 = (vmin.y - rpos.y) / rdir.y;
+    float t3 = (vmax.y - rpos.y) / rdir.y;
+    float t4 = (vmin.z - rpos.z) / rdir.z;
+    float t5 = (vmax.z - rpos.z) / rdir.z;
+    float tn = fmaxf(fmaxf(fminf(t0, t1), fminf(t2, t3)), fminf(t4, t5));
+    float tf = fminf(fminf(fmaxf(t0, t1), fmaxf(t2, t3)), fmaxf(t4, t5));
+    tn = (tn < 0) ? 0.0 : tn;
+    return make_float3(tn, tf, (tf < tn || tf < 0) ? GX_NOHIT : 0);
+}
+
+// ------------------------------------------------------------------------------------------------ hierarchical DDA
+struct GxDDA {
+    float3 pos, dir;
+    int3   pStep;
+    float3 tDel;
+    float3 t;
+    int3   p;
+    float3 tSide;
+    int3   mask;
+
+    __device__ __forceinline__ void set_ray(float3 startPos, float3 startDir, float3 startT)
+    {
+        pos = startPos; dir = startDir;
+        pStep = make_int3((dir.x > 0) ? 1 : -1, (dir.y > 0) ? 1 : -1, (dir.z > 0) ? 1 : -1);
+        t = startT;
+    }
+    // cuda_gvdb_dda.cuh:61-66
+    __device__ __forceinline__ void prepare(float3 vmin, float3 vdel)
+    {
+        tDel = gx_fabs(vdel / dir);
+        float3 pFlt = (pos + t.x * dir - vmin) / vdel;
+        tSide = ((gx_floor(pFlt) - pFlt + 0.5f) * gx_f3(pStep) + 0.5) * tDel + t.x;
+        p = gx_i3(gx_floor(pFlt));
+    }
+    // cuda_gvdb_dda.cuh:70-75 (brick: child size 1, no "+ t.x")
+    __device__ __forceinline__ void prepare_leaf(float3 vmin)
+    {
+        tDel = gx_fabs(1.0f / dir);
+        float3 pFlt = pos + t.x * dir - vmin;
+        tSide = ((gx_floor(pFlt) - pFlt + 0.5f) * gx_f3(pStep) + 0.5) * tDel;
+        p = gx_i3(gx_floor(pFlt));
+    }
+    // cuda_gvdb_dda.cuh:78-83 (tie rules: x beats z on <=, y beats x, z beats y)
+    __device__ __forceinline__ void next()
+    {
+        mask.x = int((tSide.x < tSide.y) & (tSide.x <= tSide.z));
+        mask.y = int((tSide.y < tSide.z) & (tSide.y <= tSide.x));
+        mask.z = int((tSide.z < tSide.x) & (tSide.z <= tSide.y));
+        t.y = mask.x ? tSide.x : (mask.y ? tSide.y : tSide.z);
+    }
+    // cuda_gvdb_dda.cuh:86-90
+    __device__ __forceinline__ void step()
+    {
+        t.x = t.y;
+        tSide += gx_f3(mask) * tDel;
+        p.x += mask.x * pStep.x; p.y += mask.y * pStep.y; p.z += mask.z * pStep.z;
+    }
+};
+
+// ------------------------------------------------------------------------------------------------ transfer function
+// cuda_gvdb_dda.cuh:20-23 — note the double-precision clamp and multiply.
+__device__ __forceinline__ float4 gx_transfer(const GxParams& P, float v)
+{
+    return __ldg(&P.transfer[int(min(1.0, max(0.0, (v - P.thresh.x) / (P.thresh.z - P.thresh.y))) * 16300.0f)]);
+}
+
+// depth-buffer clip: cuda_gvdb_raycast.cuh:343-370
+__device__ __forceinline__ float gx_depth_max(const GxParams& P, float3 rayDir, int px, int py)
+{
+    if (P.dbuf != nullptr) {
+        float3 w;
+        w.x = rayDir.x * P.xform[0] + rayDir.y * P.xform[4] + rayDir.z * P.xform[8];
+        w.y = rayDir.x * P.xform[1] + rayDir.y * P.xform[5] + rayDir.z * P.xform[9];
+        w.z = rayDir.x * P.xform[2] + rayDir.y * P.xform[6] + rayDir.z * P.xform[10];
+        float z = P.dbuf[(P.height - 1 - py) * P.width + px];
+        float n = P.camnear, f = P.camfar;
+        float lin = (-n * f / (f - n)) / (z - (f / (f - n)));
+        return lin / sqrtf(gx_dot(w, w));
+    }
+    return INFINITY;
+}
+
+// ------------------------------------------------------------------------------------------------ gradients
+// central differences at +-0.5 texel (the apron is one texel wide)   cuda_gvdb_raycast.cuh:132-157
+template <class S>
+__device__ __forceinline__ float3 gx_gradient(const S& smp, float3 p, GxCount& cnt, bool levelset)
+{
+    float3 g;
+    float xm = smp.tri(p.x - .5, p.y, p.z), xp = smp.tri(p.x + .5, p.y, p.z);
+    float ym = smp.tri(p.x, p.y - .5, p.z), yp = smp.tri(p.x, p.y + .5, p.z);
+    float zm = smp.tri(p.x, p.y, p.z - .5), zp = smp.tri(p.x, p.y, p.z + .5);
+    cnt.s_tri += 6;
+    if (levelset) { g.x = 1.0 * (xp - xm); g.y = 1.0 * (yp - ym); g.z = 1.0 * (zp - zm); }   // positive gradient
+    else          { g.x = 1.0 * (xm - xp); g.y = 1.0 * (ym - yp); g.z = 1.0 * (zm - zp); }   // negative gradient
+    return gx_normalize(g);
+}
+
+// ------------------------------------------------------------------------------------------------ brick functions
+struct GxHit { float3 hit, norm; float4 clr; float t; int leaf; int3 vox; };
+
+// SHADE_VOXEL: per-voxel DDA inside the brick                           cuda_gvdb_raycast.cuh:227-265
+template <class S>
+__device__ __forceinline__ void gx_brick_voxel(const GxParams& P, S& smp, int nodeid, float3 t, float3 pos, float3 dir,
+                                               GxHit& h, GxCount& cnt)
+{
+    const GxLeafRec L = P.leaf[nodeid];
+    cnt.n_desc++;
+    smp.enter(L);
+    float3 vmin = make_float3(float(L.px), float(L.py), float(L.pz));
+    float3 o = make_float3(float(L.vx), float(L.vy), float(L.vz));
+    const int res0 = P.res[0];
+
+    GxDDA dda;
+    dda.set_ray(pos, dir, t);
+    dda.prepare_leaf(vmin);
+
+    for (int iter = 0; iter < GX_MAX_ITER && dda.p.x >= 0 && dda.p.y >= 0 && dda.p.z >= 0
+                       && dda.p.x < res0 && dda.p.y < res0 && dda.p.z < res0; iter++) {
+        cnt.s_pt++;
+        if (smp.point(dda.p.x + o.x + .5, dda.p.y + o.y + .5, dda.p.z + o.z + .5) > P.thresh.x) {
+            vmin += gx_f3(dda.p);
+            dda.t = gx_ray_box(pos, dir, vmin, vmin + 1);
+            if (dda.t.z == GX_NOHIT) {      // reference quirk: no step, vmin keeps accumulating (raycast.cuh:244-247)
+                h.hit.z = GX_NOHIT;
+                continue;
+            }
+            h.hit = pos + dda.t.x * dir;
+            float3 fromVoxelCenter = (h.hit - vmin) - 0.5f;
+            fromVoxelCenter -= 0.01 * dir;
+            const float maxCoordinate = fmaxf(fmaxf(fabsf(fromVoxelCenter.x), fabsf(fromVoxelCenter.y)), fabsf(fromVoxelCenter.z));
+            h.norm.x = (fabsf(fromVoxelCenter.x) == maxCoordinate ? copysignf(1.0f, fromVoxelCenter.x) : 0.0f);
+            h.norm.y = (fabsf(fromVoxelCenter.y) == maxCoordinate ? copysignf(1.0f, fromVoxelCenter.y) : 0.0f);
+            h.norm.z = (fabsf(fromVoxelCenter.z) == maxCoordinate ? copysignf(1.0f, fromVoxelCenter.z) : 0.0f);
+            h.t = dda.t.x; h.leaf = nodeid; h.vox = gx_i3(vmin);
+            return;
+        }
+        dda.next();
+        dda.step();
+    }
+}
+
+// SHADE_TRILINEAR: fixed-step march, first sample >= THRESH             cuda_gvdb_raycast.cuh:281-300
+template <class S>
+__device__ __forceinline__ void gx_brick_trilinear(const GxParams& P, S& smp, int nodeid, float3 t, float3 pos, float3 dir,
+                                                   GxHit& h, GxCount& cnt)
+{
+    const GxLeafRec L = P.leaf[nodeid];
+    cnt.n_desc++;
+    smp.enter(L);
+    float3 vmin = make_float3(float(L.px), float(L.py), float(L.pz));
+    float3 o = make_float3(float(L.vx), float(L.vy), float(L.vz));
+    const float res0 = float(P.res[0]);
+    t.x = P.steps.x * ceilf(t.x / P.steps.x);
+    float3 p = pos + t.x * dir - vmin;
+
+    for (int iter = 0; iter < GX_MAX_ITER && p.x >= 0 && p.y >= 0 && p.z >= 0 && p.x < res0 && p.y < res0 && p.z < res0; iter++) {
+        cnt.s_tri++;
+        if (smp.tri(p.x + o.x, p.y + o.y, p.z + o.z) >= P.thresh.x) {
+            h.hit = p + vmin;
+            h.norm = gx_gradient(smp, p + o, cnt, false);
+            h.t = t.x; h.leaf = nodeid; h.vox = gx_i3(gx_floor(h.hit));
+            return;
+        }
+        p += P.steps.x * dir;
+        t.x += P.steps.x;
+    }
+}
+
+// SHADE_LEVELSET: first sample < THRESH                                 cuda_gvdb_raycast.cuh:389-410, :186-197
+// (p is taken from the UNSNAPPED t.x; the fine march re-tests the same point and returns at i = 0; bounds inclusive)
+template <class S>
+__device__ __forceinline__ void gx_brick_levelset(const GxParams& P, S& smp, int nodeid, float3 t, float3 pos, float3 dir,
+                                                  GxHit& h, GxCount& cnt)
+{
+    const GxLeafRec L = P.leaf[nodeid];
+    cnt.n_desc++;
+    smp.enter(L);
+    float3 vmin = make_float3(float(L.px), float(L.py), float(L.pz));
+    float3 o = make_float3(float(L.vx), float(L.vy), float(L.vz));
+    const float res0 = float(P.res[0]);
+    float3 p = pos + t.x * dir - vmin;
+
+    for (int iter = 0; iter < GX_MAX_ITER && p.x >= 0 && p.y >= 0 && p.z >= 0 && p.x <= res0 && p.y <= res0 && p.z <= res0; iter++) {
+        cnt.s_tri++;
+        if (smp.tri(p.x + o.x, p.y + o.y, p.z + o.z) < P.thresh.x) {
+            // rayLevelSet(): the first fine sample is this very point, so it returns immediately with p unchanged
+            cnt.s_tri++;
+            h.hit = p + vmin;
+            if (h.hit.z != GX_NOHIT) {
+                h.norm = gx_gradient(smp, p + o, cnt, true);
+                h.t = t.x; h.leaf = nodeid; h.vox = gx_i3(gx_floor(h.hit));
+                return;
+            }
+        }
+        p += P.steps.x * dir;
+    }
+}
+
+// SHADE_VOLUME: emission / absorption through the transfer function    cuda_gvdb_raycast.cuh:485-533
+template <class S>
+__device__ __forceinline__ void gx_brick_deep(const GxParams& P, S& smp, int nodeid, float3 t, float3 pos, float3 dir,
+                                              GxHit& h, GxCount& cnt, float tDepth)
+{
+    const GxLeafRec L = P.leaf[nodeid];
+    cnt.n_desc++;
+    smp.enter(L);
+    float3 vmin = make_float3(float(L.px), float(L.py), float(L.pz));
+    t.x = P.steps.x * ceilf(t.x / P.steps.x);
+    float3 o = make_float3(float(L.vx), float(L.vy), float(L.vz));
+    float3 wp = pos + t.x * dir;
+    float3 p = wp - vmin;
+    const float3 wpt = P.steps.x * dir;
+    const float dt = sqrtf(gx_dot(wpt, wpt));
+    const float res0 = float(P.res[0]);
+    float4& clr = h.clr;
+
+    if (h.hit.x == 0) h.hit.x = t.x;
+
+    for (int iter = 0; clr.w > P.cutoff.y && iter < GX_MAX_ITER && p.x >= 0 && p.y >= 0 && p.z >= 0
+                       && p.x < res0 && p.y < res0 && p.z < res0; iter++) {
+        if (t.x > tDepth) {
+            float3 d = wp - pos;
+            h.hit.y = sqrtf(gx_dot(d, d));
+            h.hit.z = 1;
+            clr = make_float4(fminf(clr.x, 1.f), fminf(clr.y, 1.f), fminf(clr.z, 1.f), fmaxf(clr.w, 0.f));
+            return;
+        }
+        cnt.s_tri++;
+        const float rawSample = smp.tri(p.x + o.x, p.y + o.y, p.z + o.z);
+        if (rawSample >= P.cutoff.x) {
+            cnt.s_lut++;
+            float4 val = gx_transfer(P, rawSample);
+            val.w = exp(P.extinct.x * val.w * P.steps.x);
+            const float4 hclr = make_float4(1, 1, 1, 1);    // no colour channel on this path (clr_chan == CHAN_UNDEF)
+            clr.x += val.x * clr.w * (1 - val.w) * P.extinct.y * hclr.x;
+            clr.y += val.y * clr.w * (1 - val.w) * P.extinct.y * hclr.y;
+            clr.z += val.z * clr.w * (1 - val.w) * P.extinct.y * hclr.z;
+            clr.w *= val.w;
+        }
+        p += wpt;
+        wp += wpt;
+        t.x += dt;
+    }
+    h.hit.y = t.x;
+    clr = make_float4(fminf(clr.x, 1.f), fminf(clr.y, 1.f), fminf(clr.z, 1.f), fmaxf(clr.w, 0.f));
+}
+
+// ------------------------------------------------------------------------------------------------ master ray cast
+// Iterative hierarchical 3-D DDA over the compact tables.               cuda_gvdb_raycast.cuh:543-611
+// The per-level stack (node id, tMax) is kept in registers: only levels 1..4 can hold state.
+struct GxStack {
+    int   n1, n2, n3, n4;
+    float m1, m2, m3, m4;
+    __device__ __forceinline__ void set(int lev, int n, float m)
+    {
+        if (lev == 1) { n1 = n; m1 = m; } else if (lev == 2) { n2 = n; m2 = m; }
+        else if (lev == 3) { n3 = n; m3 = m; } else { n4 = n; m4 = m; }
+    }
+    __device__ __forceinline__ int   node(int lev) const { return lev == 1 ? n1 : (lev == 2 ? n2 : (lev == 3 ? n3 : n4)); }
+    __device__ __forceinline__ float tmax(int lev) const { return lev == 1 ? m1 : (lev == 2 ? m2 : (lev == 3 ? m3 : m4)); }
+};
+
+template <int MODE, class S>
+__device__ __forceinline__ void gx_raycast(const GxParams& P, S& smp, float3 pos, float3 dir, GxHit& h, GxCount& cnt,
+                                           int px, int py)
+{
+    GxStack st;
+    st.n1 = st.n2 = st.n3 = st.n4 = 0; st.m1 = st.m2 = st.m3 = st.m4 = 0.f;
+    int lev = P.top_lev;
+    cnt.rays++;
+    float3 tStart = gx_ray_box(pos, dir, P.bmin, P.bmax);
+    if (tStart.z == GX_NOHIT) return;
+    if (lev < 1 || lev >= GX_MAXLEV) return;        // single-brick volume: the reference loop never runs either
+    int4 np = __ldg(&P.npos[lev][0]);
+    cnt.n_desc++;
+    float3 vmin = make_float3(float(np.x), float(np.y), float(np.z));
+
+    tStart.x += P.epsilon;
+    st.set(lev, 0, tStart.y - P.epsilon);
+
+    GxDDA dda;
+    dda.set_ray(pos, dir, tStart);
+    dda.prepare(vmin, P.vdel[lev]);
+    const float tDepth = gx_depth_max(P, dir, px, py);
+
+    for (int iter = 0; iter < GX_MAX_ITER && lev > 0 && lev <= P.top_lev && dda.p.x >= 0 && dda.p.y >= 0 && dda.p.z >= 0
+                       && dda.p.x <= P.res[lev] && dda.p.y <= P.res[lev] && dda.p.z <= P.res[lev]; iter++) {
+        dda.next();
+        if (dda.t.x > tDepth) { h.hit.z = 0; return; }
+
+        const int dm = P.dim[lev];
+        const int b = (((int(dda.p.z) << dm) + int(dda.p.y)) << dm) + int(dda.p.x);
+        // cells outside [0,res) can only be reached through the reference's inclusive loop bound; they hold no child
+        int c = -1;
+        if ((dda.p.x | dda.p.y | dda.p.z) >= 0 && dda.p.x < P.res[lev] && dda.p.y < P.res[lev] && dda.p.z < P.res[lev])
+            c = __ldg(&P.child[lev][(size_t(st.node(lev)) << (3 * dm)) + b]);
+        cnt.n_dda++;
+        if (c != -1) {
+            if (lev == 1) {
+                dda.t.x += P.epsilon;
+                if (MODE == GX_MODE_VOXEL)          gx_brick_voxel(P, smp, c, dda.t, pos, dir, h, cnt);
+                else if (MODE == GX_MODE_TRILINEAR) gx_brick_trilinear(P, smp, c, dda.t, pos, dir, h, cnt);
+                else if (MODE == GX_MODE_LEVELSET)  gx_brick_levelset(P, smp, c, dda.t, pos, dir, h, cnt);
+                else                                gx_brick_deep(P, smp, c, dda.t, pos, dir, h, cnt, tDepth);
+                if (h.clr.w <= 0) { h.clr.w = 0; return; }
+                if (h.hit.z != GX_NOHIT) return;
+                // deep mode: once transmittance is at or below ALPHACUT no later brick can change the colour
+                // (their sample loops do not run and the exit clamp is idempotent), so stop here.
+                if (MODE == GX_MODE_DEEP && h.clr.w <= P.cutoff.y) return;
+                dda.step();
+            } else {
+                lev--;
+                np = __ldg(&P.npos[lev][c]);
+                cnt.n_desc++;
+                vmin = make_float3(float(np.x), float(np.y), float(np.z));
+                dda.t.x += P.epsilon;
+                st.set(lev, c, dda.t.y - P.epsilon);
+                dda.prepare(vmin, P.vdel[lev]);
+            }
+        } else {
+            dda.step();
+        }
+        while (dda.t.x > st.tmax(lev) && lev <= P.top_lev) {
+            lev++;
+            if (lev <= P.top_lev) {
+                np = __ldg(&P.npos[lev][st.node(lev)]);
+                cnt.n_desc++;
+                vmin = make_float3(float(np.x), float(np.y), float(np.z));
+                dda.prepare(vmin, P.vdel[lev]);
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ shading
+// Phong + optional shadow ray with the same brick function              cuda_gvdb_module.cu:38-57
+template <int MODE, class S>
+__device__ __forceinline__ float4 gx_phong(const GxParams& P, S& smp, float3 shit, float3 snorm, float4 sclr, GxCount& cnt,
+                                           int px, int py)
+{
+    if (shit.z == GX_NOHIT) return P.backclr;
+    float3 lightdir = gx_normalize(P.light_pos - shit);
+    float diff = 0.9 * fmaxf(0.0f, gx_dot(snorm, lightdir));
+    float amb = 0.1f;
+    if (P.shadow_params.x > 0) {
+        GxHit h2;
+        h2.hit = make_float3(0, 0, GX_NOHIT);
+        h2.clr = make_float4(0, 0, 0, 1);
+        h2.norm = make_float3(0, 0, 0); h2.t = 0; h2.leaf = -1; h2.vox = make_int3(0, 0, 0);
+        gx_raycast<MODE>(P, smp, shit + snorm * P.shadow_params.y, lightdir, h2, cnt, px, py);
+        diff = (h2.hit.z == GX_NOHIT ? diff : diff * (1.0 - P.shadow_params.x));
+    }
+    return make_float4(sclr.x * (diff + amb), sclr.y * (diff + amb), sclr.z * (diff + amb), 1.0);
+}
+
+// ------------------------------------------------------------------------------------------------ kernels
+#define GX_FLAG_DEBUG 1
+#define GX_FLAG_COUNT 2
+#define GX_FLAG_TILES 4
+
+template <int MODE, int SAMPLER, int FLAGS>
+__global__ void __launch_bounds__(256) gx_render_kernel(const __grid_constant__ GxParams P)
+{
+    int x, y;
+    size_t opix;
+    if (FLAGS & GX_FLAG_TILES) {
+        // blockIdx.y = tile slot of this rank, blockIdx.x = sub-block inside the tile
+        const int ts = P.tile_size;
+        const int sub_x = ts / blockDim.x;
+        const int tile = blockIdx.y * P.nranks + P.rank;
+        if (tile >= P.ntiles) return;
+        const int lx = (blockIdx.x % sub_x) * blockDim.x + threadIdx.x;
+        const int ly = (blockIdx.x / sub_x) * blockDim.y + threadIdx.y;
+        x = (tile % P.tiles_x) * ts + lx;
+        y = (tile / P.tiles_x) * ts + ly;
+        opix = (size_t(blockIdx.y) * ts + ly) * ts + lx;
+        if (x >= P.width || y >= P.height) return;
+    } else {
+        x = P.x0 + blockIdx.x * blockDim.x + threadIdx.x;
+        y = P.y0 + blockIdx.y * blockDim.y + threadIdx.y;
+        if (x >= P.x1 || y >= P.y1) return;
+        opix = size_t(y) * P.out_stride + x;
+    }
+
+    GxSampler<SAMPLER> smp(P);
+    GxCount cnt = {0, 0, 0, 0, 0, 0};
+    GxHit h;
+    h.norm = make_float3(0, 0, 0); h.t = 0; h.leaf = -1; h.vox = make_int3(0, 0, 0);
+
+    // cuda_gvdb_geom.cuh:48-63
+    float3 rpos = gx_mmult(P.invxform, P.campos);
+    float u = float(x + 0.5f) / float(P.width), v = float(y + 0.5f) / float(P.height);
+    float3 vv = u * P.camu + v * P.camv + P.cams;
+    float3 rdir = gx_normalize(gx_mmult(P.invxrot, vv));
+
+    float4 clr;
+    float4 raw = make_float4(0, 0, 0, 0);
+    if (MODE == GX_MODE_DEEP) {
+        h.clr = make_float4(0, 0, 0, 1);
+        h.hit = make_float3(0, 0, GX_NOHIT);
+        gx_raycast<MODE>(P, smp, rpos, rdir, h, cnt, x, y);
+        raw = h.clr;
+        clr = h.clr;
+        float a = 1.0 - clr.w;
+        clr = make_float4(P.backclr.x + a * (clr.x - P.backclr.x), P.backclr.y + a * (clr.y - P.backclr.y),
+                          P.backclr.z + a * (clr.z - P.backclr.z), 1.0 - clr.w);
+    } else {
+        h.clr = make_float4(1, 1, 1, 1);
+        h.hit = (MODE == GX_MODE_LEVELSET) ? make_float3(0, 0, GX_NOHIT) : make_float3(GX_NOHIT, GX_NOHIT, GX_NOHIT);
+        gx_raycast<MODE>(P, smp, rpos, rdir, h, cnt, x, y);
+        clr = gx_phong<MODE>(P, smp, h.hit, h.norm, h.clr, cnt, x, y);
+    }
+    P.out[opix] = make_uchar4(clr.x * 255, clr.y * 255, clr.z * 255, clr.w * 255);
+
+    if (FLAGS & GX_FLAG_DEBUG) {
+        float4* d = P.dbg + 3 * (size_t(y) * P.width + x);
+        if (MODE == GX_MODE_DEEP) {
+            d[0] = raw;
+            d[1] = make_float4(h.hit.x, h.hit.y, h.hit.z, 0.f);
+            d[2] = make_float4(0, 0, 0, 0);
+        } else {
+            bool miss = (h.hit.z == GX_NOHIT);
+            d[0] = make_float4(h.hit.x, h.hit.y, h.hit.z, miss ? 0.f : h.t);
+            d[1] = miss ? make_float4(0, 0, 0, __int_as_float(-1)) : make_float4(h.norm.x, h.norm.y, h.norm.z, __int_as_float(h.leaf));
+            d[2] = miss ? make_float4(0, 0, 0, 0)
+                        : make_float4(__int_as_float(h.vox.x), __int_as_float(h.vox.y), __int_as_float(h.vox.z), 0.f);
+        }
+    }
+    if (FLAGS & GX_FLAG_COUNT) {
+        unsigned int v6[6] = {cnt.s_tri, cnt.s_pt, cnt.n_dda, cnt.n_desc, cnt.s_lut, cnt.rays};
+        #pragma unroll
+        for (int i = 0; i < 6; i++) {
+            unsigned int s = v6[i];
+            // threads that returned early are not in the mask: use the active mask
+            unsigned m = __activemask();
+            for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(m, s, o);
+            if ((threadIdx.y * blockDim.x + threadIdx.x) % 32 == 0) atomicAdd(&P.counters[i], (unsigned long long)s);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ import kernels
+// pool-0 / pool-1 (reference layout) -> compact tables.  One thread per child cell.
+//   child list entry = Elem(0, lev-1, ndx) = grp | lev << 8 | ndx << 16, or 0xFFFFFFFFFFFFFFFF (src/gvdb_allocator.h:59-62,
+//   gvdb_volume_gvdb.cpp:3015-3023); node->mChildList = Elem(1, lev, ndx) or ID_UNDEFL.
+__global__ void gx_build_child_table(const char* __restrict__ nodelist, int nodewid, int nodecnt,
+                                     const char* __restrict__ childlist, int childwid, int cells,
+                                     int* __restrict__ child_out, int4* __restrict__ npos_out)
+{
+    size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    size_t total = size_t(nodecnt) * cells;
+    if (i >= total) return;
+    int n = int(i / cells), b = int(i % cells);
+    const GxNode* node = reinterpret_cast<const GxNode*>(nodelist + size_t(n) * nodewid);
+    uint64_t listid = node->mChildList;
+    int c = -1;
+    if (listid != GX_ID_UNDEFL) {
+        uint64_t cndx = listid >> 16;
+        const uint64_t* clist = reinterpret_cast<const uint64_t*>(childlist + cndx * size_t(childwid));
+        c = int(clist[b] >> 16);
+    }
+    child_out[i] = c;
+    if (b == 0) npos_out[n] = make_int4(node->mPos.x, node->mPos.y, node->mPos.z, 0);
+}
+
+__global__ void gx_build_leaf_table(const char* __restrict__ nodelist, int nodewid, int nodecnt, int brick_res,
+                                    int apron, int cnt_x, int cnt_y, GxLeafRec* __restrict__ out)
+{
+    int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= nodecnt) return;
+    const GxNode* node = reinterpret_cast<const GxNode*>(nodelist + size_t(n) * nodewid);
+    GxLeafRec r;
+    r.px = node->mPos.x; r.py = node->mPos.y; r.pz = node->mPos.z;
+    r.vx = node->mValue.x; r.vy = node->mValue.y; r.vz = node->mValue.z;
+    int sx = (r.vx - apron) / brick_res, sy = (r.vy - apron) / brick_res, sz = (r.vz - apron) / brick_res;
+    r.base = (r.vx < 0) ? 0 : ((sz * cnt_y + sy) * cnt_x + sx) * GX_BRICK_STRIDE;
+    r.pad = 0;
+    out[n] = r;
+}
+
+// atlas (x-fastest linear image, as cuMemcpy3D array->linear delivers it) -> brick-major; one CTA per brick slot
+__global__ void gx_repack_atlas(const float* __restrict__ lin, int rx, int ry, int rz, int cnt_x, int cnt_y,
+                                float* __restrict__ bricks)
+{
+    const int slot = blockIdx.x;
+    const int sx = slot % cnt_x, sy = (slot / cnt_x) % cnt_y, sz = slot / (cnt_x * cnt_y);
+    for (int i = threadIdx.x; i < GX_BRICK_STRIDE; i += blockDim.x) {
+        float v = 0.f;
+        if (i < GX_BRICK_DIM * GX_BRICK_DIM * GX_BRICK_DIM) {
+            int x = i % GX_BRICK_DIM, y = (i / GX_BRICK_DIM) % GX_BRICK_DIM, z = i / (GX_BRICK_DIM * GX_BRICK_DIM);
+            size_t ax = size_t(sx) * GX_BRICK_DIM + x, ay = size_t(sy) * GX_BRICK_DIM + y, az = size_t(sz) * GX_BRICK_DIM + z;
+            v = lin[(az * ry + ay) * rx + ax];
+        }
+        bricks[size_t(slot) * GX_BRICK_STRIDE + i] = v;
+    }
+}
+
+// scatter gathered tile buffers [nranks][slots][ts*ts] back into a row-major frame
+__global__ void gx_assemble_tiles(const uchar4* __restrict__ gathered, uchar4* __restrict__ frame, int width, int height,
+                                  int ts, int tiles_x, int ntiles, int nranks, int slots)
+{
+    const int tile = blockIdx.y;
+    if (tile >= ntiles) return;
+    const int r = tile % nranks, k = tile / nranks;
+    const uchar4* src = gathered + (size_t(r) * slots + k) * ts * ts;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < ts * ts; i += gridDim.x * blockDim.x) {
+        int lx = i % ts, ly = i / ts;
+        int x = (tile % tiles_x) * ts + lx, y = (tile / tiles_x) * ts + ly;
+        if (x < width && y < height) frame[size_t(y) * width + x] = src[i];
+    }
+}
+
+// calibration: hardware filter vs software model at arbitrary atlas-space points
+__global__ void gx_sample_points_kernel(GxParams P, const float* __restrict__ xyz, int n, int cnt_x, int cnt_y,
+                                        float* __restrict__ out_tex, float* __restrict__ out_lin)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float x = xyz[3 * i], y = xyz[3 * i + 1], z = xyz[3 * i + 2];
+    out_tex[i] = tex3D<float>(P.tex, x, y, z);
+    GxSampler<GX_SAMPLER_LINEAR> s(P);
+    GxLeafRec L;
+    int sx = int(x) / GX_BRICK_DIM, sy = int(y) / GX_BRICK_DIM, sz = int(z) / GX_BRICK_DIM;
+    L.vx = sx * GX_BRICK_DIM + 1; L.vy = sy * GX_BRICK_DIM + 1; L.vz = sz * GX_BRICK_DIM + 1;
+    L.base = ((sz * cnt_y + sy) * cnt_x + sx) * GX_BRICK_STRIDE;
+    L.px = L.py = L.pz = L.pad = 0;
+    s.enter(L);
+    out_lin[i] = s.tri(x, y, z);
+}

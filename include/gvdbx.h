@@ -1,0 +1,126 @@
+/* gvdbx.h — C ABI of libgvdbx.so: B200-native (sm_100a) ray-cast render path, drop-in for the device side of
+ * VolumeGVDB::Render(shade mode, channel, render buffer) of NVIDIA/gvdb-voxels.
+ *
+ * Boundary replaced (reference, relative to /root/reference/source/gvdb_library):
+ *   src/gvdb_volume_gvdb.cpp:4336-4381  VolumeGVDB::Render      -> gvdbx_render / gvdbx_render_tiles
+ *   src/gvdb_volume_gvdb.cpp:4254-4306  PrepareRender (ScnInfo) -> the 416-byte block passed to gvdbx_render
+ *   src/gvdb_volume_gvdb.cpp:3946-3989  PrepareVDB (VDBInfo)    -> gvdbx_import_topology (1232-byte block)
+ *   src/gvdb_volume_gvdb.cpp:720-803    SetupAtlasAccess        -> gvdbx_import_atlas_array / _host
+ *   src/gvdb_volume_gvdb.cpp:4892-4898  CommitTransferFunc      -> gvdbx_set_transfer
+ *   src/gvdb_volume_gvdb.cpp:4241-4251  ReadRenderBuf           -> gvdbx_read_buffer
+ *   kernels/cuda_gvdb_module.cu:60-181  gvdbRayDeep / gvdbRaySurfaceVoxel / gvdbRaySurfaceTrilinear / gvdbRayLevelSet
+ *
+ * Conventions: plain pointers and sizes only; every function returns 0 or a negative GVDBX_E_* code and never
+ * exits the process (the reference prints and exit(-1)s: src/gvdb_types.cpp:86-90); gvdbx_last_error() gives text.
+ * All work is enqueued on the stream given at creation (NULL = legacy default stream, what the reference launches
+ * on: gvdb_volume_gvdb.cpp:4375) with no hidden synchronisation unless stated.  There is NO CPU fallback: without
+ * a CUDA device every entry point that touches the device fails with GVDBX_E_CUDA.
+ */
+#ifndef GVDBX_H
+#define GVDBX_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GVDBX_VDBINFO_BYTES 1232   /* sizeof(VDBInfo), kernels/cuda_gvdb_nodes.cuh:42-67 */
+#define GVDBX_SCNINFO_BYTES 416    /* sizeof(ScnInfo), kernels/cuda_gvdb_scene.cuh:35-64 */
+#define GVDBX_NODE_BYTES    64     /* sizeof(VDBNode), kernels/cuda_gvdb_nodes.cuh:24-35 */
+#define GVDBX_TRANSFER_ENTRIES 16384 /* src/gvdb_scene.cpp:70 */
+
+/* shade modes: numeric values of the reference's SHADE_* (src/gvdb_types.h:73-81) */
+#define GVDBX_SHADE_VOXEL      0
+#define GVDBX_SHADE_TRILINEAR  4
+#define GVDBX_SHADE_LEVELSET   6
+#define GVDBX_SHADE_VOLUME     7
+#define GVDBX_SHADE_OFF        100
+
+/* error codes */
+#define GVDBX_OK            0
+#define GVDBX_E_ARG        -1   /* bad argument / unsupported value */
+#define GVDBX_E_CUDA       -2   /* CUDA runtime error (see gvdbx_last_error) */
+#define GVDBX_E_STATE      -3   /* call order (e.g. render before import) */
+#define GVDBX_E_UNSUPPORTED -4  /* feature of the reference outside this path (e.g. colour channel) */
+
+/* options for gvdbx_set_option */
+#define GVDBX_OPT_SAMPLER   1   /* 0 = hardware texture fetch (bit-exact vs reference), 1 = linear brick-major loads */
+#define GVDBX_OPT_BLOCK_W   2   /* CTA pixel tile width  (default 8)  */
+#define GVDBX_OPT_BLOCK_H   3   /* CTA pixel tile height (default 8)  */
+#define GVDBX_OPT_COUNTERS  4   /* 1 = accumulate work counters during render (slower; for roofline accounting) */
+
+typedef struct gvdbx_ctx gvdbx_t;
+
+/* work counters of the last counted render (SURVEY.md §8d units) */
+typedef struct gvdbx_counters {
+    uint64_t s_tri;    /* trilinear samples (brick march + gradient taps)            32 B each */
+    uint64_t s_pt;     /* point samples (SHADE_VOXEL brick DDA steps)                 4 B each */
+    uint64_t n_dda;    /* DDA steps at levels >= 1 (child-table reads)                8 B each */
+    uint64_t n_desc;   /* node-record reads on descent / brick entry                 64 B each */
+    uint64_t s_lut;    /* transfer-function reads (deep)                             16 B each (not in HBM figure) */
+    uint64_t rays;     /* primary + shadow rays cast */
+} gvdbx_counters;
+
+int  gvdbx_create(gvdbx_t** h, int cuda_device, void* cuda_stream);
+int  gvdbx_destroy(gvdbx_t* h);
+const char* gvdbx_last_error(const gvdbx_t* h);
+int  gvdbx_set_option(gvdbx_t* h, int option, int value);
+
+/* Topology.  `vdbinfo` is a HOST copy of the reference's 1232-byte VDBInfo as PrepareVDB fills it
+ * (VolumeGVDB::getVDBInfo(), gvdb_volume_gvdb.h:519): nodelist[] / childlist[] hold DEVICE pointers to the caller's
+ * pool-0 node records and pool-1 child lists.  The library builds its own compact traversal tables from them (device
+ * side) and keeps no reference to the caller's pools afterwards.  Call again whenever the reference would set
+ * mVDBInfo.update (FinishTopology / UpdateAtlas / SetEpsilon). */
+int  gvdbx_import_topology(gvdbx_t* h, const void* vdbinfo);
+/* Same, but pool contents come from HOST memory (e.g. Allocator::getPoolCPU or a VBX file): pool0[l] / pool1[l] point
+ * at nodecnt[l]*nodewid[l] and <lists>*childwid[l] bytes; pool1_bytes[l] gives the size of each child-list pool. */
+int  gvdbx_import_topology_host(gvdbx_t* h, const void* vdbinfo, const void* const* pool0, const void* const* pool1,
+                                const uint64_t* pool1_bytes);
+
+/* Brick atlas of channel `chan` (T_FLOAT only).  `cuarray` is the reference's 3-D CUarray (DataPtr::garray,
+ * gvdb_allocator.cpp:392-408); it is sampled in place by the texture path and re-laid out brick-major for the linear
+ * path.  Call again after the atlas content changed (there is no dirty notification in the reference). */
+int  gvdbx_import_atlas_array(gvdbx_t* h, int chan, void* cuarray, int res_x, int res_y, int res_z);
+/* Same from a HOST image of the atlas, x fastest (the layout of Allocator::AtlasCommitFromCPU, gvdb_allocator.cpp:797). */
+int  gvdbx_import_atlas_host(gvdbx_t* h, int chan, const float* texels, int res_x, int res_y, int res_z);
+
+/* Transfer function: 16384 float4 (Scene::getTransferFunc()).  Alternatively leave unset and pass a device pointer in
+ * ScnInfo.transfer exactly like the reference does. */
+int  gvdbx_set_transfer(gvdbx_t* h, const float* rgba_host);
+
+/* Render one frame (or a sub-rectangle) into a caller-owned DEVICE buffer of width*height RGBA8 pixels, row-major,
+ * y = 0 the top-left corner ray — the bytes VolumeGVDB::ReadRenderBuf returns.  `scninfo` is a HOST copy of the
+ * 416-byte ScnInfo that PrepareRender fills (VolumeGVDB::getScnInfo()).  tile_w/tile_h <= 0 means the full frame.
+ * Asynchronous on the context's stream. */
+int  gvdbx_render(gvdbx_t* h, const void* scninfo, int shade_mode, int chan, uint64_t outbuf_d,
+                  int tile_x0, int tile_y0, int tile_w, int tile_h);
+
+/* Image-space tiling for multi-GPU: the frame is cut into tile_size x tile_size tiles, numbered row-major; this call
+ * renders the tiles with (tile_id % nranks) == rank into `packed_d`, tile after tile (each tile_size*tile_size RGBA8,
+ * edge tiles padded), i.e. ceil(ntiles/nranks) tile slots per rank.  gvdbx_assemble_tiles scatters the gathered
+ * [nranks][slots][tile] buffer back into a row-major frame. */
+int  gvdbx_render_tiles(gvdbx_t* h, const void* scninfo, int shade_mode, int chan, uint64_t packed_d,
+                        int tile_size, int rank, int nranks);
+int  gvdbx_tiles_per_rank(int width, int height, int tile_size, int nranks);
+int  gvdbx_assemble_tiles(gvdbx_t* h, uint64_t gathered_d, uint64_t frame_d, int width, int height, int tile_size, int nranks);
+
+/* Debug / parity outputs: same traversal, additionally writes 48 B per pixel into dbg_d:
+ *   float4 {hit.x, hit.y, hit.z, t_hit}   float4 {norm.x, norm.y, norm.z, as_float(leaf id)}   int4 {voxel.x, voxel.y, voxel.z, iterations}
+ * (deep mode: float4 raw colour before compositing, float4 {hit.x, hit.y, hit.z, 0}, int4 0). */
+int  gvdbx_render_debug(gvdbx_t* h, const void* scninfo, int shade_mode, int chan, uint64_t outbuf_d, uint64_t dbg_d);
+
+/* ReadRenderBuf: device -> host copy of `bytes`, synchronises the stream. */
+int  gvdbx_read_buffer(gvdbx_t* h, uint64_t buf_d, void* host, size_t bytes);
+int  gvdbx_sync(gvdbx_t* h);
+int  gvdbx_get_counters(gvdbx_t* h, gvdbx_counters* out);
+
+/* Calibration aid: samples channel `chan` at n atlas-space points (xyz triples, device pointer) with the hardware
+ * texture path and with the linear-load emulation; writes n floats each. */
+int  gvdbx_sample_points(gvdbx_t* h, int chan, uint64_t xyz_d, int n, uint64_t out_tex_d, uint64_t out_lin_d);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GVDBX_H */

@@ -1,0 +1,233 @@
+// ref_harness.cpp — TEST INFRASTRUCTURE (oracle/_ref), not product.
+//
+// Drives the UNMODIFIED reference (oracle/_ref/libgvdb.so + its own cubin) through its own public API,
+// the way source/gRenderToFile/main_rendertofile.cpp:17-83 does, on the synthetic scenes of oracle/scenes.h:
+//
+//   Initialize -> Configure(3,3,3,3,3) -> AddChannel(0,T_FLOAT,1) -> ActivateSpace per brick -> FinishTopology ->
+//   UpdateAtlas -> atlas upload (mPool->AtlasCommitFromCPU) -> UpdateApron -> scene params -> AddRenderBuf ->
+//   Render(mode,0,0) -> ReadRenderBuf
+//
+// and dumps, into <outdir>/ :
+//   vdbinfo.bin (1232 B)  scninfo_<mode>.bin (416 B)  pool<g>_L<l>.bin  atlas.bin (+ meta.txt)  transfer.bin
+//   out_<mode>.rgba       hit_<mode>.f32 (32 B/pixel via the RenderKernel wrappers of oracle_kernels.cu)
+//   timing.json           (CPU topology-build seconds, render ms/frame by CUDA-event-free cuCtxSynchronize bracketing)
+//
+// These dumps are (a) the byte-identical inputs both renderers consume in the parity tests and (b) the golden outputs.
+//
+// usage: ref_harness <preset> <outdir> [--modes voxel,trilinear,levelset,deep] [--size WxH] [--frames N] [--warmup W]
+//                    [--nodump] [--shadow 0|1] [--hits 0|1]
+#include "gvdb.h"
+#include <cuda.h>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+#include <algorithm>
+#include <sys/stat.h>
+
+#include "scenes.h"
+
+using namespace nvdb;
+
+static double now_s()
+{
+    return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+static void dump(const std::string& path, const void* p, size_t n)
+{
+    FILE* f = fopen(path.c_str(), "wb");
+    if (!f) { fprintf(stderr, "cannot write %s\n", path.c_str()); exit(2); }
+    fwrite(p, 1, n, f); fclose(f);
+}
+struct Mode { const char* name; int shade; const char* hitkernel; };
+static const Mode kModes[] = {
+    {"voxel", SHADE_VOXEL, "oracleHitVoxel"}, {"trilinear", SHADE_TRILINEAR, "oracleHitTrilinear"},
+    {"levelset", SHADE_LEVELSET, "oracleHitLevelSet"}, {"deep", SHADE_VOLUME, "oracleDeepRaw"},
+};
+
+int main(int argc, char** argv)
+{
+    if (argc < 3) { fprintf(stderr, "usage: ref_harness <preset> <outdir> [opts]\n"); return 1; }
+    std::string preset = argv[1], outdir = argv[2], modes = "";
+    int W = 0, H = 0, frames = 1, warmup = 0, nodump = 0, shadow = -1, hits = 1;
+    for (int i = 3; i < argc; i++) {
+        std::string a = argv[i];
+        if (a == "--modes" && i + 1 < argc) modes = argv[++i];
+        else if (a == "--size" && i + 1 < argc) sscanf(argv[++i], "%dx%d", &W, &H);
+        else if (a == "--frames" && i + 1 < argc) frames = atoi(argv[++i]);
+        else if (a == "--warmup" && i + 1 < argc) warmup = atoi(argv[++i]);
+        else if (a == "--nodump") nodump = 1;
+        else if (a == "--shadow" && i + 1 < argc) shadow = atoi(argv[++i]);
+        else if (a == "--hits" && i + 1 < argc) hits = atoi(argv[++i]);
+    }
+    scene_preset P;
+    if (scene_get_preset(preset.c_str(), &P)) { fprintf(stderr, "unknown preset %s\n", preset.c_str()); return 1; }
+    if (W > 0) { P.width = W; P.height = H; }
+    if (shadow == 0) { P.shadow[0] = 0; P.shadow[1] = 0; P.shadow[2] = 0; }
+    mkdir(outdir.c_str(), 0777);
+
+    // ---- synthetic volume (CPU, shared generator)
+    scene_data S;
+    double t0 = now_s();
+    scene_generate(&P, &S);
+    double t_gen = now_s() - t0;
+    fprintf(stderr, "[ref] preset %s: %d bricks (gen %.2fs)\n", P.name, S.nbricks, t_gen);
+
+    // ---- reference library
+    VolumeGVDB gvdb;
+    gvdb.SetDebug(false);
+    gvdb.SetVerbose(false);
+    gvdb.SetCudaDevice(0);          // explicit device: never GVDB_DEV_FIRST (cuGLGetDevices)
+    gvdb.Initialize();
+
+    // ---- CPU topology build (timed: the reference's host-side baseline)
+    t0 = now_s();
+    gvdb.Configure(3, 3, 3, 3, 3);
+    gvdb.SetChannelDefault(16, 16, 1);
+    gvdb.AddChannel(0, T_FLOAT, 1);
+    double t_cfg = now_s() - t0;
+    t0 = now_s();
+    for (int n = 0; n < S.nbricks; n++)
+        gvdb.ActivateSpace(Vector3DF((float)S.brick_pos[3 * n], (float)S.brick_pos[3 * n + 1], (float)S.brick_pos[3 * n + 2]));
+    double t_act = now_s() - t0;
+    t0 = now_s();
+    gvdb.FinishTopology();
+    gvdb.UpdateAtlas();
+    cuCtxSynchronize();
+    double t_fin = now_s() - t0;
+    gvdb.SetEpsilon(P.epsilon, 256);
+
+    // ---- atlas upload: brick n (activation order) == leaf n (PoolAlloc hands out consecutive indices)
+    Vector3DI ares = gvdb.mPool->getAtlasRes(0);
+    size_t atexels = (size_t)ares.x * ares.y * ares.z;
+    std::vector<float> atlas(atexels, 0.0f);
+    int nleaf = (int)gvdb.mPool->getPoolTotalCnt(0, 0);
+    if (nleaf != S.nbricks) { fprintf(stderr, "leaf count %d != bricks %d\n", nleaf, S.nbricks); return 3; }
+    for (int n = 0; n < nleaf; n++) {
+        Node* nd = gvdb.getNode(0, 0, n);
+        if (nd->mPos.x != S.brick_pos[3 * n] || nd->mPos.y != S.brick_pos[3 * n + 1] || nd->mPos.z != S.brick_pos[3 * n + 2]) {
+            fprintf(stderr, "leaf %d pos mismatch\n", n); return 3;
+        }
+        const float* v = S.values + 512 * (size_t)n;
+        for (int k = 0; k < 8; k++) for (int j = 0; j < 8; j++) {
+            float* dst = &atlas[((size_t)(nd->mValue.z + k) * ares.y + (nd->mValue.y + j)) * ares.x + nd->mValue.x];
+            memcpy(dst, v + (k * 8 + j) * 8, 8 * sizeof(float));
+        }
+    }
+    gvdb.mPool->AtlasCommitFromCPU(0, (uchar*)atlas.data());
+    gvdb.UpdateApron(0, 0.0f);
+    cuCtxSynchronize();
+
+    // ---- scene
+    Scene* scn = gvdb.getScene();
+    scn->SetSteps(P.steps[0], P.steps[1], P.steps[2]);
+    scn->SetExtinct(P.extinct[0], P.extinct[1], P.extinct[2]);
+    scn->SetVolumeRange(P.thresh[0], P.thresh[1], P.thresh[2]);
+    scn->SetCutoff(P.cutoff[0], P.cutoff[1], P.cutoff[2]);
+    scn->SetBackgroundClr(P.backclr[0], P.backclr[1], P.backclr[2], P.backclr[3]);
+    scn->SetShadowParams(P.shadow[0], P.shadow[1], P.shadow[2]);
+    if (P.transfer == 1) {
+        scn->LinearTransferFunc(0.00f, 0.25f, Vector4DF(0, 0, 0, 0), Vector4DF(1, 1, 0, 0.1f));
+        scn->LinearTransferFunc(0.25f, 0.50f, Vector4DF(1, 1, 0, 0.4f), Vector4DF(1, 0, 0, 0.3f));
+        scn->LinearTransferFunc(0.50f, 0.75f, Vector4DF(1, 0, 0, 0.3f), Vector4DF(.2f, .2f, 0.2f, 0.1f));
+        scn->LinearTransferFunc(0.75f, 1.00f, Vector4DF(.2f, .2f, 0.2f, 0.1f), Vector4DF(0, 0, 0, 0.0));
+        gvdb.CommitTransferFunc();
+    }
+    Camera3D* cam = new Camera3D;
+    cam->setFov(P.fov);
+    cam->setOrbit(Vector3DF(P.cam_angs[0], P.cam_angs[1], P.cam_angs[2]),
+                  Vector3DF(P.cam_target[0], P.cam_target[1], P.cam_target[2]), P.cam_dist, 1.0f);
+    scn->SetCamera(cam);
+    scn->SetRes(P.width, P.height);
+    Light* lgt = new Light;
+    lgt->setOrbit(Vector3DF(P.light_angs[0], P.light_angs[1], P.light_angs[2]),
+                  Vector3DF(P.light_target[0], P.light_target[1], P.light_target[2]), P.light_dist, 1.0f);
+    scn->SetLight(0, lgt);
+
+    const int w = P.width, h = P.height;
+    gvdb.AddRenderBuf(0, w, h, 4);
+    gvdb.AddRenderBuf(1, w, h, 32);
+
+    // ---- static dumps
+    if (!nodump) {
+        gvdb.PrepareVDB();
+        dump(outdir + "/vdbinfo.bin", gvdb.getVDBInfo(), 1232);
+        gvdb.FetchPoolCPU();
+        int levs = gvdb.mPool->getNumLevels();
+        FILE* mf = fopen((outdir + "/meta.txt").c_str(), "w");
+        fprintf(mf, "preset %s\nbricks %d\nlevels %d\natlas_res %d %d %d\nwidth %d\nheight %d\n", P.name, S.nbricks, levs, ares.x, ares.y, ares.z, w, h);
+        for (int g = 0; g < 2; g++) for (int l = 0; l < levs; l++) {
+            uint64 cnt = gvdb.mPool->getPoolTotalCnt(g, l), wid = gvdb.mPool->getPoolWidth(g, l);
+            fprintf(mf, "pool %d %d %llu %llu\n", g, l, (unsigned long long)cnt, (unsigned long long)wid);
+            char nm[64]; snprintf(nm, sizeof nm, "/pool%d_L%d.bin", g, l);
+            dump(outdir + nm, cnt * wid ? gvdb.mPool->getPoolCPU(g, l) : "", cnt * wid);
+        }
+        fclose(mf);
+        // atlas after the reference's own UpdateApron
+        std::vector<float> back(atexels);
+        for (int z = 0; z < ares.z; z++)
+            gvdb.mPool->AtlasRetrieveSlice(0, z, 0, 0, (uchar*)(back.data() + (size_t)z * ares.x * ares.y));
+        dump(outdir + "/atlas.bin", back.data(), atexels * sizeof(float));
+        dump(outdir + "/transfer.bin", scn->getTransferFunc(), 16384 * 16);
+        dump(outdir + "/brick_pos.bin", S.brick_pos, sizeof(int32_t) * 3 * (size_t)S.nbricks);
+    }
+
+    // ---- oracle wrapper kernels via the RenderKernel plugin API
+    CUmodule omod = 0;
+    if (hits) {
+        if (cuModuleLoad(&omod, "oracle_kernels.cubin") != CUDA_SUCCESS) { fprintf(stderr, "cannot load oracle_kernels.cubin\n"); hits = 0; }
+    }
+
+    std::string timing = "{\"preset\":\"" + preset + "\",\"bricks\":" + std::to_string(S.nbricks) +
+        ",\"width\":" + std::to_string(w) + ",\"height\":" + std::to_string(h) +
+        ",\"topology_build_s\":{\"configure\":" + std::to_string(t_cfg) + ",\"activate\":" + std::to_string(t_act) +
+        ",\"finish_update_atlas\":" + std::to_string(t_fin) + ",\"threads\":1},\"scene_gen_s\":" + std::to_string(t_gen) + ",\"render\":{";
+    bool first = true;
+    std::vector<unsigned char> img((size_t)w * h * 4);
+    std::vector<float> hitbuf((size_t)w * h * 8);
+    for (const Mode& m : kModes) {
+        bool want = modes.empty() ? (m.shade == P.shade) : (("," + modes + ",").find(std::string(",") + m.name + ",") != std::string::npos);
+        if (!want) continue;
+        for (int i = 0; i < warmup; i++) gvdb.Render(m.shade, 0, 0);
+        cuCtxSynchronize();
+        std::vector<double> ms;
+        for (int i = 0; i < frames; i++) {
+            double a = now_s();
+            gvdb.Render(m.shade, 0, 0);
+            cuCtxSynchronize();
+            ms.push_back((now_s() - a) * 1e3);
+        }
+        double a = now_s();
+        gvdb.ReadRenderBuf(0, img.data());
+        double read_ms = (now_s() - a) * 1e3;
+        std::sort(ms.begin(), ms.end());
+        double med = ms[ms.size() / 2], mn = ms[0];
+        if (!nodump) {
+            dump(outdir + "/out_" + m.name + ".rgba", img.data(), img.size());
+            dump(outdir + "/scninfo_" + m.name + ".bin", gvdb.getScnInfo(), 416);
+        }
+        if (hits) {
+            CUfunction fn;
+            if (cuModuleGetFunction(&fn, omod, m.hitkernel) == CUDA_SUCCESS) {
+                gvdb.SetModule(omod);               // scn symbol of the wrapper module
+                scn->SetShading(m.shade);
+                gvdb.RenderKernel(fn, 0, 1);
+                cuCtxSynchronize();
+                gvdb.ReadRenderBuf(1, (unsigned char*)hitbuf.data());
+                gvdb.SetModule();                   // back to the native module
+                if (!nodump) dump(outdir + "/hit_" + m.name + ".f32", hitbuf.data(), hitbuf.size() * sizeof(float));
+            }
+        }
+        char buf[256];
+        snprintf(buf, sizeof buf, "%s\"%s\":{\"ms_median\":%.4f,\"ms_min\":%.4f,\"read_ms\":%.4f,\"frames\":%d}", first ? "" : ",", m.name, med, mn, read_ms, frames);
+        timing += buf; first = false;
+        fprintf(stderr, "[ref] %s: %.3f ms/frame (min %.3f), %.2f Mrays/s\n", m.name, med, mn, w * (double)h / med * 1e-3);
+    }
+    timing += "}}";
+    dump(outdir + "/timing.json", timing.data(), timing.size());
+    printf("%s\n", timing.c_str());
+    scene_free(&S);
+    return 0;
+}

@@ -1,0 +1,183 @@
+"""refcmp.py — parity harness: UNMODIFIED reference (oracle/_ref) vs libgvdbx on identical bytes.
+
+Test infrastructure (may execute oracle/): runs oracle/_ref/ref_harness as a subprocess (it has its own CUDA
+context), loads its dumps (the reference's own VDBInfo / ScnInfo / pools / atlas-after-UpdateApron / transfer
+table) and renders the same inputs through the C ABI of libgvdbx.so.  Nothing here reads /root/reference.
+
+CLI:  python tests/refcmp.py --presets cfg1_small,cfg3_small --out gpurun_out/refcmp.json
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF_DIR = os.path.join(ROOT, "oracle", "_ref")
+MODES = {"voxel": 0, "trilinear": 4, "levelset": 6, "deep": 7}
+
+
+def have_ref():
+    return all(os.path.exists(os.path.join(REF_DIR, f)) for f in
+               ("ref_harness", "libgvdb.so", "cuda_gvdb_module.cubin", "cuda_gvdb_copydata.ptx"))
+
+
+def run_ref(preset, outdir, modes=None, size=None, frames=1, warmup=0, nodump=False, shadow=None, hits=True, timeout=1800):
+    """Run the reference harness; returns its timing dict."""
+    cmd = ["./ref_harness", preset, os.path.abspath(outdir)]
+    if modes:
+        cmd += ["--modes", ",".join(modes)]
+    if size:
+        cmd += ["--size", f"{size[0]}x{size[1]}"]
+    cmd += ["--frames", str(frames), "--warmup", str(warmup), "--hits", "1" if hits else "0"]
+    if nodump:
+        cmd.append("--nodump")
+    if shadow is not None:
+        cmd += ["--shadow", str(int(shadow))]
+    r = subprocess.run(cmd, cwd=REF_DIR, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=timeout)
+    if r.returncode != 0:
+        raise RuntimeError(f"ref_harness failed ({r.returncode}): {r.stderr[-2000:]}")
+    line = [l for l in r.stdout.splitlines() if l.startswith("{")][-1]
+    return json.loads(line)
+
+
+def load_dump(d):
+    meta = {"pools": {}}
+    for line in open(os.path.join(d, "meta.txt")):
+        t = line.split()
+        if t[0] == "pool":
+            meta["pools"][(int(t[1]), int(t[2]))] = (int(t[3]), int(t[4]))
+        elif t[0] == "atlas_res":
+            meta["atlas_res"] = tuple(int(x) for x in t[1:4])
+        elif t[0] in ("bricks", "levels", "width", "height"):
+            meta[t[0]] = int(t[1])
+        else:
+            meta[t[0]] = t[1]
+    out = {"meta": meta, "dir": d}
+    out["vdbinfo"] = open(os.path.join(d, "vdbinfo.bin"), "rb").read()
+    rx, ry, rz = meta["atlas_res"]
+    out["atlas"] = np.fromfile(os.path.join(d, "atlas.bin"), dtype=np.float32).reshape(rz, ry, rx)
+    out["transfer"] = np.fromfile(os.path.join(d, "transfer.bin"), dtype=np.float32)
+    out["pool0"], out["pool1"] = {}, {}
+    for (g, l), (cnt, wid) in meta["pools"].items():
+        p = os.path.join(d, f"pool{g}_L{l}.bin")
+        b = np.fromfile(p, dtype=np.uint8) if os.path.getsize(p) else np.zeros(0, np.uint8)
+        (out["pool0"] if g == 0 else out["pool1"])[l] = b
+    out["scn"], out["rgba"], out["hit"] = {}, {}, {}
+    w, h = meta["width"], meta["height"]
+    for m in MODES:
+        p = os.path.join(d, f"scninfo_{m}.bin")
+        if os.path.exists(p):
+            out["scn"][m] = open(p, "rb").read()
+            out["rgba"][m] = np.fromfile(os.path.join(d, f"out_{m}.rgba"), dtype=np.uint8).reshape(h, w, 4)
+            hp = os.path.join(d, f"hit_{m}.f32")
+            if os.path.exists(hp):
+                out["hit"][m] = np.fromfile(hp, dtype=np.float32).reshape(h, w, 8)
+    return out
+
+
+def make_renderer(dump, pkg, device=0):
+    r = pkg.Renderer(device)
+    r.import_topology_host(dump["vdbinfo"], dump["pool0"], dump["pool1"])
+    r.import_atlas_host(dump["atlas"])
+    r.set_transfer(dump["transfer"])
+    return r
+
+
+def render_mine(r, dump, mode, sampler, debug=False):
+    import torch
+    w, h = dump["meta"]["width"], dump["meta"]["height"]
+    r.set_sampler(sampler)
+    out = torch.zeros((h, w, 4), dtype=torch.uint8, device="cuda")
+    if debug:
+        dbg = torch.zeros((h, w, 12), dtype=torch.float32, device="cuda")
+        r.render_debug(dump["scn"][mode], MODES[mode], out.data_ptr(), dbg.data_ptr())
+        r.sync()
+        return out.cpu().numpy(), dbg.cpu().numpy(), r.counters()
+    r.render(dump["scn"][mode], MODES[mode], out.data_ptr())
+    r.sync()
+    return out.cpu().numpy(), None, None
+
+
+def psnr(a, b):
+    mse = np.mean((a.astype(np.float64) - b.astype(np.float64)) ** 2)
+    return 99.0 if mse == 0 else float(10 * np.log10(255.0 ** 2 / mse))
+
+
+def compare(dump, pkg, modes=None, device=0, verbose=True):
+    """Returns {mode: {sampler: stats}}."""
+    res = {}
+    r = make_renderer(dump, pkg, device)
+    for m in (modes or dump["scn"].keys()):
+        ref = dump["rgba"][m]
+        res[m] = {}
+        for sname, s in (("tex", 0), ("linear", 1)):
+            mine, dbg, cnt = render_mine(r, dump, m, s, debug=True)
+            plain, _, _ = render_mine(r, dump, m, s, debug=False)
+            diff = np.abs(mine.astype(np.int32) - ref.astype(np.int32))
+            st = {
+                "pixels": int(ref.shape[0] * ref.shape[1]),
+                "rgba_mismatch_pixels": int((diff.max(axis=2) > 0).sum()),
+                "rgba_max_abs": int(diff.max()),
+                "rgba_over1_pixels": int((diff.max(axis=2) > 1).sum()),
+                "psnr": psnr(mine, ref),
+                "plain_equals_debug": bool(np.array_equal(plain, mine)),
+                "counters": cnt,
+            }
+            if m in dump["hit"]:
+                rh = dump["hit"][m]
+                if m == "deep":
+                    a = dbg[:, :, 0:4].view(np.uint32)
+                    b = rh[:, :, 0:4].view(np.uint32)
+                    st["raw_clr_mismatch_pixels"] = int((a != b).any(axis=2).sum())
+                    st["raw_clr_max_abs"] = float(np.abs(dbg[:, :, 0:4] - rh[:, :, 0:4]).max())
+                else:
+                    a = dbg[:, :, 0:3].view(np.uint32)
+                    b = rh[:, :, 0:3].view(np.uint32)
+                    bad_hit = (a != b).any(axis=2)
+                    an = dbg[:, :, 4:7].view(np.uint32)
+                    bn = rh[:, :, 4:7].view(np.uint32)
+                    bad_norm = (an != bn).any(axis=2)
+                    st["hit_mismatch_pixels"] = int(bad_hit.sum())
+                    st["norm_mismatch_pixels"] = int(bad_norm.sum())
+                    st["hit_pixels"] = int((rh[:, :, 2] != np.float32(1.0e10)).sum())
+                    if bad_hit.any():
+                        ys, xs = np.nonzero(bad_hit)
+                        st["hit_examples"] = [
+                            {"x": int(x), "y": int(y), "ref": rh[y, x, 0:3].tolist(), "mine": dbg[y, x, 0:3].tolist()}
+                            for y, x in list(zip(ys, xs))[:5]]
+            res[m][sname] = st
+            if verbose:
+                print(f"[refcmp] {dump['meta'].get('preset')} {m:9s} {sname:6s} " +
+                      json.dumps({k: v for k, v in st.items() if k not in ("counters", "hit_examples")}), flush=True)
+    r.close()
+    return res
+
+
+def main():
+    sys.path.insert(0, ROOT)
+    from __graft_entry__ import load_package
+    pkg = load_package()
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--presets", default="cfg1_tiny,cfg2_tiny,cfg3_tiny,cfg4_tiny")
+    ap.add_argument("--modes", default="voxel,trilinear,levelset,deep")
+    ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "refcmp.json"))
+    ap.add_argument("--keep", default="")
+    a = ap.parse_args()
+    allres = {}
+    for preset in a.presets.split(","):
+        d = os.path.join(a.keep, preset) if a.keep else tempfile.mkdtemp(prefix="refdump_")
+        os.makedirs(d, exist_ok=True)
+        timing = run_ref(preset, d, modes=a.modes.split(","))
+        dump = load_dump(d)
+        allres[preset] = {"ref_timing": timing, "cmp": compare(dump, pkg, a.modes.split(","))}
+    os.makedirs(os.path.dirname(a.out), exist_ok=True)
+    json.dump(allres, open(a.out, "w"), indent=1)
+    print("[refcmp] wrote", a.out)
+
+
+if __name__ == "__main__":
+    main()
