@@ -9,7 +9,7 @@ There is no CPU fallback: every call that needs the device raises GvdbxError whe
 shared library or a CUDA device is missing.
 """
 from .api import (  # noqa: F401
-    GvdbxError, Renderer, lib, lib_path,
+    GvdbxError, Renderer, Volume, lib, lib_path, HOST_SYMBOLS,
     SHADE_VOXEL, SHADE_TRILINEAR, SHADE_LEVELSET, SHADE_VOLUME, SHADE_OFF,
     SAMPLER_TEX, SAMPLER_LINEAR, VDBINFO_BYTES, SCNINFO_BYTES,
     EXPORTED_SYMBOLS,

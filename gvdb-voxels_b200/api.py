@@ -216,3 +216,127 @@ class Renderer:
     def sample_points(self, xyz_ptr, n, out_tex_ptr, out_lin_ptr, chan=0):
         self._ck(self._L.gvdbx_sample_points(self._h, chan, int(xyz_ptr), n, int(out_tex_ptr), int(out_lin_ptr)),
                  "gvdbx_sample_points")
+
+
+# ------------------------------------------------------------------------------------------------ host mirror
+HOST_SYMBOLS = [
+    "gvdbxh_create", "gvdbxh_destroy", "gvdbxh_set_transform", "gvdbxh_camera", "gvdbxh_camera_nearfar", "gvdbxh_light",
+    "gvdbxh_scene_params", "gvdbxh_linear_transfer", "gvdbxh_transfer_table", "gvdbxh_set_res", "gvdbxh_prepare_render",
+    "gvdbxh_import_topology_host", "gvdbxh_import_atlas_host", "gvdbxh_commit_transfer", "gvdbxh_add_render_buf",
+    "gvdbxh_render", "gvdbxh_read_render_buf", "gvdbxh_set_option", "gvdbxh_last_error",
+]
+
+
+def _f(vals):
+    return (C.c_float * len(vals))(*[float(v) for v in vals])
+
+
+class Volume:
+    """Mirror of the render-facing part of the reference's VolumeGVDB (gvdb-voxels_b200/csrc/gvdbx_host.h):
+    Scene / Camera3D / Light state, SetTransform, CommitTransferFunc, AddRenderBuf, Render, ReadRenderBuf.
+
+    device < 0 creates host state only (ScnInfo bytes can be produced without a GPU)."""
+
+    def __init__(self, device=0):
+        L = lib()
+        L.gvdbxh_create.restype = C.c_void_p
+        L.gvdbxh_create.argtypes = [C.c_int]
+        L.gvdbxh_transfer_table.restype = C.POINTER(C.c_float)
+        L.gvdbxh_last_error.restype = C.c_char_p
+        for s in HOST_SYMBOLS:
+            if s not in ("gvdbxh_create", "gvdbxh_transfer_table", "gvdbxh_last_error"):
+                getattr(L, s).restype = C.c_int
+        self._L = L
+        self._h = C.c_void_p(L.gvdbxh_create(int(device)))
+        if not self._h:
+            raise GvdbxError(f"gvdbxh_create(device={device}) failed: no CUDA device / no CPU fallback")
+        self._bufs = {}
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.gvdbxh_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc, what):
+        if rc != 0:
+            msg = self._L.gvdbxh_last_error(self._h)
+            raise GvdbxError(f"{what} failed ({rc}): {msg.decode() if msg else ''}")
+
+    # --- Scene / camera state (reference: gvdb_scene.h, gvdb_camera.h)
+    def SetTransform(self, pretrans=(0, 0, 0), scal=(1, 1, 1), angs=(0, 0, 0), trans=(0, 0, 0)):
+        self._L.gvdbxh_set_transform(self._h, _f(pretrans), _f(scal), _f(angs), _f(trans))
+
+    def SetCamera(self, fov, angs, target, dist, dolly=1.0):
+        self._L.gvdbxh_camera(self._h, C.c_float(fov), _f(angs), _f(target), C.c_float(dist), C.c_float(dolly))
+
+    def SetLight(self, angs, target, dist, dolly=1.0):
+        self._L.gvdbxh_light(self._h, _f(angs), _f(target), C.c_float(dist), C.c_float(dolly))
+
+    def SetSceneParams(self, steps, extinct, thresh, cutoff, backclr, shadow):
+        self._L.gvdbxh_scene_params(self._h, _f(steps), _f(extinct), _f(thresh), _f(cutoff), _f(backclr), _f(shadow))
+
+    def LinearTransferFunc(self, t0, t1, a, b):
+        self._L.gvdbxh_linear_transfer(self._h, C.c_float(t0), C.c_float(t1), _f(a), _f(b))
+
+    def transfer_table(self):
+        p = self._L.gvdbxh_transfer_table(self._h)
+        return np.ctypeslib.as_array(p, shape=(16384 * 4,)).copy()
+
+    def SetRes(self, w, h):
+        self._L.gvdbxh_set_res(self._h, int(w), int(h))
+
+    def PrepareRender(self, w, h, shading):
+        out = (C.c_uint8 * SCNINFO_BYTES)()
+        self._L.gvdbxh_prepare_render(self._h, int(w), int(h), int(shading), out)
+        return bytes(out)
+
+    # --- volume import + render (needs a device)
+    def ImportTopologyHost(self, vdbinfo, pool0, pool1):
+        p, keep = _buf(vdbinfo)
+        a0 = (C.c_void_p * 10)()
+        a1 = (C.c_void_p * 10)()
+        n1 = (C.c_uint64 * 10)()
+        alive = []
+        for lev in range(10):
+            for arr, src in ((a0, pool0), (a1, pool1)):
+                b = src.get(lev)
+                if b is None or len(b) == 0:
+                    arr[lev] = None
+                    continue
+                q, k = _buf(b)
+                alive.append(k)
+                arr[lev] = q
+                if arr is a1:
+                    n1[lev] = k.nbytes
+        self._ck(self._L.gvdbxh_import_topology_host(self._h, p, a0, a1, n1), "ImportTopologyHost")
+
+    def ImportAtlasHost(self, texels, chan=0):
+        a = np.ascontiguousarray(texels, dtype=np.float32)
+        rz, ry, rx = a.shape
+        self._ck(self._L.gvdbxh_import_atlas_host(self._h, chan, a.ctypes.data_as(C.c_void_p), rx, ry, rz), "ImportAtlasHost")
+
+    def CommitTransferFunc(self):
+        self._ck(self._L.gvdbxh_commit_transfer(self._h), "CommitTransferFunc")
+
+    def AddRenderBuf(self, chan, w, h, bpp):
+        self._ck(self._L.gvdbxh_add_render_buf(self._h, chan, w, h, bpp), "AddRenderBuf")
+        self._bufs[chan] = (w, h, bpp)
+
+    def Render(self, shading, chan=0, rbuf=0):
+        self._ck(self._L.gvdbxh_render(self._h, int(shading), int(chan), int(rbuf)), "Render")
+
+    def ReadRenderBuf(self, chan, out=None):
+        w, h, bpp = self._bufs[chan]
+        if out is None:
+            out = np.empty((h, w, bpp), dtype=np.uint8)
+        self._ck(self._L.gvdbxh_read_render_buf(self._h, chan, out.ctypes.data_as(C.c_void_p)), "ReadRenderBuf")
+        return out
+
+    def set_option(self, opt, value):
+        self._ck(self._L.gvdbxh_set_option(self._h, int(opt), int(value)), "set_option")

@@ -500,3 +500,13 @@ extern "C" int gvdbx_sample_points(gvdbx_t* h, int chan, uint64_t xyz_d, int n, 
     GX_CUDA(h, cudaGetLastError());
     return GVDBX_OK;
 }
+
+// device-buffer helpers for the host mirror (gvdbx_host.cpp is plain C++)
+extern "C" int gvdbx_internal_alloc(uint64_t* ptr, size_t bytes)
+{
+    void* d = nullptr;
+    if (!ptr || cudaMalloc(&d, bytes) != cudaSuccess) return GVDBX_E_CUDA;
+    *ptr = (uint64_t)d;
+    return GVDBX_OK;
+}
+extern "C" int gvdbx_internal_free(uint64_t ptr) { return cudaFree((void*)ptr) == cudaSuccess ? GVDBX_OK : GVDBX_E_CUDA; }

@@ -1,0 +1,51 @@
+"""make_golden_ref.py — generates tests/golden/ref_<preset>.npz on the GPU box by running the UNMODIFIED reference
+(oracle/_ref/ref_harness) and condensing its dumps: VDBInfo, ScnInfo per mode, RGBA per mode, hit/normal buffers
+(tiny presets), SHA-256 of every pool and of the atlas after the reference's own UpdateApron.
+
+  python tests/make_golden_ref.py gpurun_out/golden          (then copy *.npz into tests/golden/ and commit)
+"""
+import hashlib
+import os
+import sys
+import tempfile
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import refcmp  # noqa: E402
+
+PRESETS = ["cfg1_tiny", "cfg2_tiny", "cfg3_tiny", "cfg4_tiny", "cfg1_small", "cfg2_small", "cfg3_small", "cfg4_small"]
+
+
+def sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def main(outdir):
+    os.makedirs(outdir, exist_ok=True)
+    for preset in PRESETS:
+        d = tempfile.mkdtemp(prefix="refdump_")
+        timing = refcmp.run_ref(preset, d, modes=list(refcmp.MODES))
+        dump = refcmp.load_dump(d)
+        out = {"vdbinfo": np.frombuffer(dump["vdbinfo"], np.uint8), "bricks": dump["meta"]["bricks"],
+               "atlas_res": np.array(dump["meta"]["atlas_res"]), "atlas_sha": sha(dump["atlas"]),
+               "transfer_sha": sha(dump["transfer"]), "width": dump["meta"]["width"], "height": dump["meta"]["height"],
+               "ms_per_frame": np.array([timing["render"][m]["ms_median"] for m in refcmp.MODES])}
+        for lev, b in dump["pool0"].items():
+            out[f"pool0_L{lev}_sha"] = sha(b)
+            out[f"pool0_L{lev}_bytes"] = len(b)
+        for lev, b in dump["pool1"].items():
+            out[f"pool1_L{lev}_sha"] = sha(b)
+            out[f"pool1_L{lev}_bytes"] = len(b)
+        for m in refcmp.MODES:
+            out[f"scn_{m}"] = np.frombuffer(dump["scn"][m], np.uint8)
+            out[f"rgba_{m}"] = dump["rgba"][m]
+            if "tiny" in preset and m in dump["hit"]:
+                out[f"hit_{m}"] = dump["hit"][m]
+        np.savez_compressed(os.path.join(outdir, f"ref_{preset}.npz"), **out)
+        print("[golden]", preset, "bricks", out["bricks"], "atlas", out["atlas_res"], flush=True)
+
+
+if __name__ == "__main__":
+    main(sys.argv[1] if len(sys.argv) > 1 else os.path.join(ROOT, "gpurun_out", "golden"))
