@@ -16,6 +16,9 @@
 //
 // usage: ref_harness <preset> <outdir> [--modes voxel,trilinear,levelset,deep] [--size WxH] [--frames N] [--warmup W]
 //                    [--nodump] [--shadow 0|1] [--hits 0|1]
+//        ref_harness <preset> <outdir> --bench --orbit F --steps K --warmup W [--mode levelset] [--size WxH]
+//          bench mode: a step = F frames on an orbit (camera yaw + 360*j/F); prints one JSON line with the device-synchronised
+//          time of K steps for Render() alone and for Render()+ReadRenderBuf() (the reference's end-to-end path).
 #include "gvdb.h"
 #include <cuda.h>
 #include <chrono>
@@ -51,7 +54,8 @@ int main(int argc, char** argv)
 {
     if (argc < 3) { fprintf(stderr, "usage: ref_harness <preset> <outdir> [opts]\n"); return 1; }
     std::string preset = argv[1], outdir = argv[2], modes = "";
-    int W = 0, H = 0, frames = 1, warmup = 0, nodump = 0, shadow = -1, hits = 1;
+    int W = 0, H = 0, frames = 1, warmup = 0, nodump = 0, shadow = -1, hits = 1, bench = 0, orbit = 8, steps = 5;
+    std::string bmode = "";
     for (int i = 3; i < argc; i++) {
         std::string a = argv[i];
         if (a == "--modes" && i + 1 < argc) modes = argv[++i];
@@ -61,6 +65,10 @@ int main(int argc, char** argv)
         else if (a == "--nodump") nodump = 1;
         else if (a == "--shadow" && i + 1 < argc) shadow = atoi(argv[++i]);
         else if (a == "--hits" && i + 1 < argc) hits = atoi(argv[++i]);
+        else if (a == "--bench") { bench = 1; nodump = 1; hits = 0; }
+        else if (a == "--orbit" && i + 1 < argc) orbit = atoi(argv[++i]);
+        else if (a == "--steps" && i + 1 < argc) steps = atoi(argv[++i]);
+        else if (a == "--mode" && i + 1 < argc) bmode = argv[++i];
     }
     scene_preset P;
     if (scene_get_preset(preset.c_str(), &P)) { fprintf(stderr, "unknown preset %s\n", preset.c_str()); return 1; }
@@ -149,6 +157,33 @@ int main(int argc, char** argv)
     const int w = P.width, h = P.height;
     gvdb.AddRenderBuf(0, w, h, 4);
     gvdb.AddRenderBuf(1, w, h, 32);
+
+
+    // ---- bench mode (bench.py --impl reference): the reference's own CUDA render through its public API
+    if (bench) {
+        int shade = P.shade;
+        for (const Mode& m : kModes) if (bmode == m.name) shade = m.shade;
+        std::vector<unsigned char> frame((size_t)w * h * 4);
+        auto set_cam = [&](int j) {
+            cam->setOrbit(Vector3DF(P.cam_angs[0] + 360.0f * (float)j / (float)orbit, P.cam_angs[1], P.cam_angs[2]),
+                          Vector3DF(P.cam_target[0], P.cam_target[1], P.cam_target[2]), P.cam_dist, 1.0f);
+        };
+        for (int s = 0; s < warmup; s++) for (int j = 0; j < orbit; j++) { set_cam(j); gvdb.Render(shade, 0, 0); }
+        cuCtxSynchronize();
+        double tk0 = now_s();
+        for (int s = 0; s < steps; s++) { for (int j = 0; j < orbit; j++) { set_cam(j); gvdb.Render(shade, 0, 0); } cuCtxSynchronize(); }
+        double t_kernel = now_s() - tk0;
+        double te0 = now_s();
+        for (int s = 0; s < steps; s++) for (int j = 0; j < orbit; j++) { set_cam(j); gvdb.Render(shade, 0, 0); gvdb.ReadRenderBuf(0, frame.data()); }
+        double t_e2e = now_s() - te0;
+        unsigned long long sum = 0;
+        for (size_t i = 0; i < frame.size(); i += 97) sum += frame[i];
+        printf("{\"preset\":\"%s\",\"bricks\":%d,\"width\":%d,\"height\":%d,\"shade\":%d,\"orbit\":%d,\"steps\":%d,\"warmup\":%d,"
+               "\"render_s\":%.6f,\"e2e_s\":%.6f,\"topology_build_s\":%.6f,\"scene_gen_s\":%.3f,\"checksum\":%llu}\n",
+               preset.c_str(), S.nbricks, w, h, shade, orbit, steps, warmup, t_kernel, t_e2e, t_cfg + t_act + t_fin, t_gen, sum);
+        scene_free(&S);
+        return 0;
+    }
 
     // ---- static dumps
     if (!nodump) {

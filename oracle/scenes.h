@@ -268,10 +268,10 @@ static inline int scene_get_preset(const char* name, scene_preset* p)
         scn_set3(p->cam_angs, 35.f, 25.f, 0.f); scn_set3(p->cam_target, 512.f * s, 512.f * s, 512.f * s); p->cam_dist = 1800.f * s;
         scn_set3(p->light_target, 528.f * s, -80.f * s, 200.f * s); p->light_dist = 800.f * s;
         scn_set3(p->steps, .25f, 16.f, .25f); scn_set3(p->thresh, 0.0f, -3.f, 3.f); p->epsilon = 0.01f;
-    } else if (!strncmp(name, "cfg3", 4)) {     /* random solid balls, SHADE_VOXEL, 3840x2160 */
+    } else if (!strncmp(name, "cfg3", 4)) {     /* 600 random solid balls r in [12,40] (~1 % occupancy, ~170 k bricks), SHADE_VOXEL, 3840x2160 */
         p->kind = SCN_KIND_BALLS; p->N = tiny ? 64 : (small ? 256 : 2048);
         float s = p->N / 2048.f;
-        p->a = tiny ? 6.f : (small ? 48.f : 4096.f); p->b = tiny ? 4.f : (small ? 8.f : 12.f); p->c = tiny ? 9.f : (small ? 20.f : 40.f);
+        p->a = tiny ? 6.f : (small ? 48.f : 600.f); p->b = tiny ? 4.f : (small ? 8.f : 12.f); p->c = tiny ? 9.f : (small ? 20.f : 40.f);
         p->width = tiny ? 96 : (small ? 384 : 3840); p->height = tiny ? 54 : (small ? 216 : 2160);
         p->shade = SCN_SHADE_VOXEL; p->fov = 40.f;
         scn_set3(p->cam_angs, 60.f, 20.f, 0.f); scn_set3(p->cam_target, 1024.f * s, 1024.f * s, 1024.f * s); p->cam_dist = 3600.f * s;
