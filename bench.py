@@ -176,6 +176,7 @@ def main():
     ap.add_argument("--tile", type=int, default=32)
     ap.add_argument("--block", default="8x8")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--traversal", default="default", choices=["default", "literal", "packet"])
     a = ap.parse_args()
     a.size = tuple(int(x) for x in a.size.split("x")) if a.size else None
     a.warmup = max(a.warmup, 3) if a.impl != "reference" else a.warmup
@@ -217,6 +218,7 @@ def main():
     r.set_sampler(0 if a.sampler == "tex" else 1)
     bw, bh = (int(x) for x in a.block.split("x"))
     r.set_block(bw, bh)
+    r.set_option(5, {"default": 0, "literal": 1, "packet": 2}[a.traversal])
 
     # ---------------- algorithmic bytes per frame (counted render, outside the timed region)
     frame = torch.zeros((h, w, 4), dtype=torch.uint8, device=dev)
@@ -300,6 +302,7 @@ def main():
         v.AddRenderBuf(0, w, h, 4)
         v.set_option(1, 0 if a.sampler == "tex" else 1)
         v.set_option(2, bw); v.set_option(3, bh)
+        v.set_option(5, {"default": 0, "literal": 1, "packet": 2}[a.traversal])
 
         def step_e2e():
             for j in range(a.frames):
@@ -315,7 +318,6 @@ def main():
             step_e2e()
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
-        e2e_same = bool(np.array_equal(host_np, frame.cpu().numpy())) if True else None
         e2e = {"value": rays_step * a.steps / dt / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": a.frames * 416,
                "d2h_bytes_per_step": a.frames * w * h * 4, "ms_per_frame": dt / a.steps / a.frames * 1e3,
                "api": "VolumeGVDB mirror: SetCamera + Render + ReadRenderBuf into pinned host memory"}
@@ -390,7 +392,7 @@ def main():
            "ms_per_step": ms_total / a.steps, "ms_per_frame": ms_total / a.steps / a.frames, "higher_is_better": True,
            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
            "config": {"workload": f"{a.workload} {SHADE_NAME[shade]} {w}x{h}", "frames_per_step": a.frames, "bricks": timing["bricks"],
-                      "atlas_mb": vol["atlas"].nbytes / 1e6, "sampler": a.sampler, "block": a.block,
+                      "atlas_mb": vol["atlas"].nbytes / 1e6, "sampler": a.sampler, "block": a.block, "traversal": a.traversal,
                       "parallelism": f"image tiles {a.tile}x{a.tile} round-robin over {world} GPU(s), volume replicated" if world > 1 else "single GPU",
                       "l2_policy": "inputs larger than L2 (atlas %.0f MB vs 126 MB L2); camera changes every frame" % (vol["atlas"].nbytes / 1e6)},
            "e2e": e2e, "gpu_launches": launches_timed, "roofline": roofline, "clocks": clk, "import_s": import_s,

@@ -14,7 +14,7 @@ import numpy as np
 
 SHADE_VOXEL, SHADE_TRILINEAR, SHADE_LEVELSET, SHADE_VOLUME, SHADE_OFF = 0, 4, 6, 7, 100
 SAMPLER_TEX, SAMPLER_LINEAR = 0, 1
-OPT_SAMPLER, OPT_BLOCK_W, OPT_BLOCK_H, OPT_COUNTERS = 1, 2, 3, 4
+OPT_SAMPLER, OPT_BLOCK_W, OPT_BLOCK_H, OPT_COUNTERS, OPT_TRAVERSAL = 1, 2, 3, 4, 5
 VDBINFO_BYTES, SCNINFO_BYTES = 1232, 416
 
 EXPORTED_SYMBOLS = [

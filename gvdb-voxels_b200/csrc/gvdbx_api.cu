@@ -5,6 +5,7 @@
 // caller's current context; everything is stream-ordered on the stream given to gvdbx_create.
 #include "../../include/gvdbx.h"
 #include "gvdbx_device.cuh"
+#include "gvdbx_trace.cuh"
 
 #include <cstdio>
 #include <cstdlib>
@@ -17,7 +18,7 @@ struct gvdbx_ctx {
     cudaStream_t stream = nullptr;
     std::string  err;
     // options
-    int sampler = GX_SAMPLER_TEX, block_w = 8, block_h = 8, count = 0;
+    int sampler = GX_SAMPLER_TEX, block_w = 8, block_h = 8, count = 0, literal = 0;
     // topology
     bool       have_topo = false;
     GxVDBInfo  vdb;
@@ -110,9 +111,13 @@ extern "C" int gvdbx_set_option(gvdbx_t* h, int option, int value)
     case GVDBX_OPT_BLOCK_W:  if (value < 1 || value > 32) return gx_fail(h, GVDBX_E_ARG, "block_w"); h->block_w = value; break;
     case GVDBX_OPT_BLOCK_H:  if (value < 1 || value > 32) return gx_fail(h, GVDBX_E_ARG, "block_h"); h->block_h = value; break;
     case GVDBX_OPT_COUNTERS: h->count = value ? 1 : 0; break;
+    case GVDBX_OPT_TRAVERSAL: if (value < 0 || value > 2) return gx_fail(h, GVDBX_E_ARG, "traversal must be 0, 1 or 2"); h->literal = value; break;
     default: return gx_fail(h, GVDBX_E_ARG, "unknown option");
     }
-    if (h->block_w * h->block_h > 256) { h->block_w = 8; h->block_h = 8; return gx_fail(h, GVDBX_E_ARG, "block larger than 256 threads"); }
+    if (h->block_w * h->block_h > 256 || (h->block_w * h->block_h) % 32 != 0) {
+        const bool pending = (option == GVDBX_OPT_BLOCK_W);     // width is set first, height second: only judge the pair
+        if (!pending) { h->block_w = 8; h->block_h = 8; return gx_fail(h, GVDBX_E_ARG, "CTA tile must be a multiple of 32 and at most 256 threads"); }
+    }
     return GVDBX_OK;
 }
 
@@ -294,6 +299,8 @@ static gx_kernel_t gx_pick_flags(int flags)
     case 0: return gx_render_kernel<MODE, SAMPLER, 0>;
     case GX_FLAG_DEBUG | GX_FLAG_COUNT: return gx_render_kernel<MODE, SAMPLER, GX_FLAG_DEBUG | GX_FLAG_COUNT>;
     case GX_FLAG_TILES: return gx_render_kernel<MODE, SAMPLER, GX_FLAG_TILES>;
+    case GX_FLAG_LITERAL: return gx_render_kernel<MODE, SAMPLER, GX_FLAG_LITERAL>;
+    case GX_FLAG_PACKET: return gx_render_kernel<MODE, SAMPLER, GX_FLAG_PACKET>;
     }
     return nullptr;
 }
@@ -378,7 +385,7 @@ extern "C" int gvdbx_render(gvdbx_t* h, const void* scninfo, int shade_mode, int
         P.x0 = tx0; P.y0 = ty0; P.x1 = tx0 + tw; P.y1 = ty0 + th;
     }
     P.out = (uchar4*)outbuf_d;
-    const int flags = h->count ? (GX_FLAG_DEBUG | GX_FLAG_COUNT) : 0;
+    const int flags = h->count ? (GX_FLAG_DEBUG | GX_FLAG_COUNT) : (h->literal == 1 ? GX_FLAG_LITERAL : (h->literal == 2 ? GX_FLAG_PACKET : 0));
     float4* dbg_tmp = nullptr;
     if (h->count) {     // counted renders reuse the debug variant; give it a scratch debug buffer
         GX_CUDA(h, cudaMalloc(&dbg_tmp, size_t(P.width) * P.height * 48));

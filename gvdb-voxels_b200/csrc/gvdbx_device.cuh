@@ -477,7 +477,12 @@ struct GxStack {
     __device__ __forceinline__ float tmax(int lev) const { return lev == 1 ? m1 : (lev == 2 ? m2 : (lev == 3 ? m3 : m4)); }
 };
 
-template <int MODE, class S>
+// four-samples-per-round brick marchers (gvdbx_trace.cuh)
+template <class S> __device__ __forceinline__ void gx2_brick_trilinear(const GxParams&, S&, int, float3, float3, float3, GxHit&, GxCount&);
+template <class S> __device__ __forceinline__ void gx2_brick_levelset(const GxParams&, S&, int, float3, float3, float3, GxHit&, GxCount&);
+template <class S> __device__ __forceinline__ void gx2_brick_deep(const GxParams&, S&, int, float3, float3, float3, GxHit&, GxCount&, float);
+
+template <int MODE, bool BATCH, class S>
 __device__ __forceinline__ void gx_raycast(const GxParams& P, S& smp, float3 pos, float3 dir, GxHit& h, GxCount& cnt,
                                            int px, int py)
 {
@@ -516,9 +521,12 @@ __device__ __forceinline__ void gx_raycast(const GxParams& P, S& smp, float3 pos
             if (lev == 1) {
                 dda.t.x += P.epsilon;
                 if (MODE == GX_MODE_VOXEL)          gx_brick_voxel(P, smp, c, dda.t, pos, dir, h, cnt);
-                else if (MODE == GX_MODE_TRILINEAR) gx_brick_trilinear(P, smp, c, dda.t, pos, dir, h, cnt);
-                else if (MODE == GX_MODE_LEVELSET)  gx_brick_levelset(P, smp, c, dda.t, pos, dir, h, cnt);
-                else                                gx_brick_deep(P, smp, c, dda.t, pos, dir, h, cnt, tDepth);
+                else if (MODE == GX_MODE_TRILINEAR) { if (BATCH) gx2_brick_trilinear(P, smp, c, dda.t, pos, dir, h, cnt);
+                                                      else       gx_brick_trilinear(P, smp, c, dda.t, pos, dir, h, cnt); }
+                else if (MODE == GX_MODE_LEVELSET)  { if (BATCH) gx2_brick_levelset(P, smp, c, dda.t, pos, dir, h, cnt);
+                                                      else       gx_brick_levelset(P, smp, c, dda.t, pos, dir, h, cnt); }
+                else                                { if (BATCH) gx2_brick_deep(P, smp, c, dda.t, pos, dir, h, cnt, tDepth);
+                                                      else       gx_brick_deep(P, smp, c, dda.t, pos, dir, h, cnt, tDepth); }
                 if (h.clr.w <= 0) { h.clr.w = 0; return; }
                 if (h.hit.z != GX_NOHIT) return;
                 // deep mode: once transmittance is at or below ALPHACUT no later brick can change the colour
@@ -551,7 +559,7 @@ __device__ __forceinline__ void gx_raycast(const GxParams& P, S& smp, float3 pos
 
 // ------------------------------------------------------------------------------------------------ shading
 // Phong + optional shadow ray with the same brick function              cuda_gvdb_module.cu:38-57
-template <int MODE, class S>
+template <int MODE, bool BATCH, class S>
 __device__ __forceinline__ float4 gx_phong(const GxParams& P, S& smp, float3 shit, float3 snorm, float4 sclr, GxCount& cnt,
                                            int px, int py)
 {
@@ -564,22 +572,30 @@ __device__ __forceinline__ float4 gx_phong(const GxParams& P, S& smp, float3 shi
         h2.hit = make_float3(0, 0, GX_NOHIT);
         h2.clr = make_float4(0, 0, 0, 1);
         h2.norm = make_float3(0, 0, 0); h2.t = 0; h2.leaf = -1; h2.vox = make_int3(0, 0, 0);
-        gx_raycast<MODE>(P, smp, shit + snorm * P.shadow_params.y, lightdir, h2, cnt, px, py);
+        gx_raycast<MODE, BATCH>(P, smp, shit + snorm * P.shadow_params.y, lightdir, h2, cnt, px, py);
         diff = (h2.hit.z == GX_NOHIT ? diff : diff * (1.0 - P.shadow_params.x));
     }
     return make_float4(sclr.x * (diff + amb), sclr.y * (diff + amb), sclr.z * (diff + amb), 1.0);
 }
 
 // ------------------------------------------------------------------------------------------------ kernels
-#define GX_FLAG_DEBUG 1
-#define GX_FLAG_COUNT 2
-#define GX_FLAG_TILES 4
+#define GX_FLAG_DEBUG   1
+#define GX_FLAG_COUNT   2
+#define GX_FLAG_TILES   4
+#define GX_FLAG_LITERAL 8      // reference-shaped loops: literal nesting, one sample at a time (A/B baseline)
+#define GX_FLAG_PACKET  16     // vote-converged two-phase traversal of gvdbx_trace.cuh (A/B)
+// default (neither flag): literal nesting of traversal and brick visit, four-samples-per-round brick marchers
+
+template <int MODE, class S>
+__device__ __forceinline__ float4 gx2_trace_pixel(const GxParams& P, S& smp, float3 rpos, float3 rdir, int px, int py,
+                                                  GxCount& cnt, GxHit& prim, float4& raw, bool valid);
 
 template <int MODE, int SAMPLER, int FLAGS>
 __global__ void __launch_bounds__(256) gx_render_kernel(const __grid_constant__ GxParams P)
 {
     int x, y;
     size_t opix;
+    bool valid;
     if (FLAGS & GX_FLAG_TILES) {
         // blockIdx.y = tile slot of this rank, blockIdx.x = sub-block inside the tile
         const int ts = P.tile_size;
@@ -591,13 +607,14 @@ __global__ void __launch_bounds__(256) gx_render_kernel(const __grid_constant__ 
         x = (tile % P.tiles_x) * ts + lx;
         y = (tile / P.tiles_x) * ts + ly;
         opix = (size_t(blockIdx.y) * ts + ly) * ts + lx;
-        if (x >= P.width || y >= P.height) return;
+        valid = (x < P.width && y < P.height);
     } else {
         x = P.x0 + blockIdx.x * blockDim.x + threadIdx.x;
         y = P.y0 + blockIdx.y * blockDim.y + threadIdx.y;
-        if (x >= P.x1 || y >= P.y1) return;
+        valid = (x < P.x1 && y < P.y1);
         opix = size_t(y) * P.out_stride + x;
     }
+    if (!(FLAGS & GX_FLAG_PACKET) && !valid) return;     // the packet traversal keeps whole warps alive for its votes
 
     GxSampler<SAMPLER> smp(P);
     GxCount cnt = {0, 0, 0, 0, 0, 0};
@@ -612,10 +629,14 @@ __global__ void __launch_bounds__(256) gx_render_kernel(const __grid_constant__ 
 
     float4 clr;
     float4 raw = make_float4(0, 0, 0, 0);
-    if (MODE == GX_MODE_DEEP) {
+    constexpr bool BATCH = !(FLAGS & GX_FLAG_LITERAL);
+    if (FLAGS & GX_FLAG_PACKET) {
+        clr = gx2_trace_pixel<MODE>(P, smp, rpos, rdir, x, y, cnt, h, raw, valid);
+        if (!valid) return;
+    } else if (MODE == GX_MODE_DEEP) {
         h.clr = make_float4(0, 0, 0, 1);
         h.hit = make_float3(0, 0, GX_NOHIT);
-        gx_raycast<MODE>(P, smp, rpos, rdir, h, cnt, x, y);
+        gx_raycast<MODE, BATCH>(P, smp, rpos, rdir, h, cnt, x, y);
         raw = h.clr;
         clr = h.clr;
         float a = 1.0 - clr.w;
@@ -624,8 +645,8 @@ __global__ void __launch_bounds__(256) gx_render_kernel(const __grid_constant__ 
     } else {
         h.clr = make_float4(1, 1, 1, 1);
         h.hit = (MODE == GX_MODE_LEVELSET) ? make_float3(0, 0, GX_NOHIT) : make_float3(GX_NOHIT, GX_NOHIT, GX_NOHIT);
-        gx_raycast<MODE>(P, smp, rpos, rdir, h, cnt, x, y);
-        clr = gx_phong<MODE>(P, smp, h.hit, h.norm, h.clr, cnt, x, y);
+        gx_raycast<MODE, BATCH>(P, smp, rpos, rdir, h, cnt, x, y);
+        clr = gx_phong<MODE, BATCH>(P, smp, h.hit, h.norm, h.clr, cnt, x, y);
     }
     P.out[opix] = make_uchar4(clr.x * 255, clr.y * 255, clr.z * 255, clr.w * 255);
 
@@ -646,13 +667,7 @@ __global__ void __launch_bounds__(256) gx_render_kernel(const __grid_constant__ 
     if (FLAGS & GX_FLAG_COUNT) {
         unsigned int v6[6] = {cnt.s_tri, cnt.s_pt, cnt.n_dda, cnt.n_desc, cnt.s_lut, cnt.rays};
         #pragma unroll
-        for (int i = 0; i < 6; i++) {
-            unsigned int s = v6[i];
-            // threads that returned early are not in the mask: use the active mask
-            unsigned m = __activemask();
-            for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(m, s, o);
-            if ((threadIdx.y * blockDim.x + threadIdx.x) % 32 == 0) atomicAdd(&P.counters[i], (unsigned long long)s);
-        }
+        for (int i = 0; i < 6; i++) atomicAdd(&P.counters[i], (unsigned long long)v6[i]);
     }
 }
 

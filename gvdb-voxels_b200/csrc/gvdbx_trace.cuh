@@ -1,0 +1,401 @@
+// gvdbx_trace.cuh — warp-coherent ("while-while") form of the GVDB ray cast for sm_100a.
+//
+// Same per-ray arithmetic as gvdbx_device.cuh's literal form (and therefore as the reference: every lane executes the
+// identical sequence of floating-point operations on its own ray), but the control flow is organised for a warp:
+//
+//   * PHASE A / PHASE B: a lane advances its hierarchical DDA until it stands in front of a brick (or dies); only
+//     then does the warp reconverge and all lanes sample their bricks together.  In the literal nesting
+//     (rayCast -> brickFunc inside the loop body, cuda_gvdb_raycast.cuh:567-610) brick visits of different lanes fall
+//     into different outer iterations and the sample loop runs at ~12/32 active lanes (profiles/r01_*).
+//   * ONE traversal instance serves primary AND shadow rays: a lane whose primary ray is finished turns it into its
+//     shadow ray (performPhongShading, cuda_gvdb_module.cu:38-57) and keeps going instead of idling until the whole
+//     warp has finished the primary pass.
+//   * Inside a brick the fixed-step marchers know how many samples are certainly inside the brick (conservative
+//     bound); those are taken in batches of four with the four texture fetches in flight together and without the
+//     six boundary compares per sample; the remaining samples run the original fully-checked loop.  Sample positions
+//     are still produced by the same chain of roundings (p = fma(step, dir, p) resp. p = p + wpt), so every fetched
+//     value, threshold test and accumulated colour is bit-identical to the one-at-a-time loop.
+#pragma once
+#include "gvdbx_device.cuh"
+
+__device__ __forceinline__ float gx_rcp_approx(float x)
+{
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
+// Number of consecutive fixed-step samples p, p+d, p+2d, ... that are guaranteed to lie strictly inside (0,res0)^3.
+// Conservative by `m` voxels, far above the accumulated rounding of <= 256 steps (<= 256 * 0.5 ulp(8) = 1.2e-4) and
+// the error of the approximate division.
+__device__ __forceinline__ int gx_safe_samples(float3 p, float3 d, float res0)
+{
+    const float m = 4e-3f;
+    float nx = d.x > 0 ? (res0 - m - p.x) / d.x : (d.x < 0 ? (p.x - m) / -d.x : 1e9f);
+    float ny = d.y > 0 ? (res0 - m - p.y) / d.y : (d.y < 0 ? (p.y - m) / -d.y : 1e9f);
+    float nz = d.z > 0 ? (res0 - m - p.z) / d.z : (d.z < 0 ? (p.z - m) / -d.z : 1e9f);
+    const bool inside = p.x > m && p.y > m && p.z > m && p.x < res0 - m && p.y < res0 - m && p.z < res0 - m;
+    float n = fminf(fminf(nx, ny), nz);
+    if (!inside || !(n >= 0.f)) return 0;
+    return int(fminf(n, 1024.f)) + 1;
+}
+
+// ------------------------------------------------------------------------------------------------ brick samplers
+// Fixed-step marchers, four samples per round.  `n` = samples still known to be inside the brick (conservative); while
+// n >= 4 the six boundary compares per sample are skipped, afterwards every sample of a round is checked exactly as the
+// reference loop condition does.  The four fetches of a round are issued before the first result is consumed; results
+// are then consumed strictly in order, so the sample at which the loop ends, the hit position and the accumulated
+// colour are those of the one-at-a-time loop.  Fetches behind the end of the loop are discarded (a fetch just outside
+// the brick reads apron / neighbour texels, never unmapped memory).
+#define GX_INB(q, hi)    ((q).x >= 0 && (q).y >= 0 && (q).z >= 0 && (q).x <  (hi) && (q).y <  (hi) && (q).z <  (hi))
+#define GX_INB_LE(q, hi) ((q).x >= 0 && (q).y >= 0 && (q).z >= 0 && (q).x <= (hi) && (q).y <= (hi) && (q).z <= (hi))
+#define GX_STEP_FMA(dst, src) { (dst).x = __fmaf_rn(st, dir.x, (src).x); (dst).y = __fmaf_rn(st, dir.y, (src).y); (dst).z = __fmaf_rn(st, dir.z, (src).z); }
+#define GX_STEP_ADD(dst, src) { (dst).x = __fadd_rn((src).x, wpt.x); (dst).y = __fadd_rn((src).y, wpt.y); (dst).z = __fadd_rn((src).z, wpt.z); }
+
+// SHADE_TRILINEAR                                                        cuda_gvdb_raycast.cuh:281-300
+template <class S>
+__device__ __forceinline__ void gx2_brick_trilinear(const GxParams& P, S& smp, int nodeid, float3 t, float3 pos, float3 dir,
+                                                    GxHit& h, GxCount& cnt)
+{
+    const GxLeafRec L = P.leaf[nodeid];
+    cnt.n_desc++;
+    smp.enter(L);
+    const float3 vmin = make_float3(float(L.px), float(L.py), float(L.pz));
+    const float3 o = make_float3(float(L.vx), float(L.vy), float(L.vz));
+    const float res0 = float(P.res[0]);
+    const float st = P.steps.x, thr = P.thresh.x;
+    t.x = st * ceilf(t.x / st);
+    float3 p = pos + t.x * dir - vmin;
+    int n = gx_safe_samples(p, st * dir, res0);
+    for (int iter = 0; iter < GX_MAX_ITER; iter += 4) {
+        float3 p1, p2, p3;
+        GX_STEP_FMA(p1, p); GX_STEP_FMA(p2, p1); GX_STEP_FMA(p3, p2);
+        bool k0 = true, k1 = true, k2 = true, k3 = true;
+        if (n >= 4) n -= 4;
+        else { n = 0; k0 = GX_INB(p, res0); k1 = GX_INB(p1, res0); k2 = GX_INB(p2, res0); k3 = GX_INB(p3, res0); }
+        const float v0 = smp.tri(p.x + o.x, p.y + o.y, p.z + o.z);
+        const float v1 = smp.tri(p1.x + o.x, p1.y + o.y, p1.z + o.z);
+        const float v2 = smp.tri(p2.x + o.x, p2.y + o.y, p2.z + o.z);
+        const float v3 = smp.tri(p3.x + o.x, p3.y + o.y, p3.z + o.z);
+        int k = -1;                      // index of the sample that ends the loop, hit = it passed the threshold
+        bool hit = false;
+        if (!k0) k = 0; else if (v0 >= thr) { k = 0; hit = true; }
+        else if (!k1) k = 1; else if (v1 >= thr) { k = 1; hit = true; p = p1; }
+        else if (!k2) k = 2; else if (v2 >= thr) { k = 2; hit = true; p = p2; }
+        else if (!k3) k = 3; else if (v3 >= thr) { k = 3; hit = true; p = p3; }
+        if (k >= 0) {
+            cnt.s_tri += k + (hit ? 1 : 0);
+            if (hit) {
+                h.hit = p + vmin;
+                h.norm = gx_gradient(smp, p + o, cnt, false);
+                h.t = t.x; h.leaf = nodeid; h.vox = gx_i3(gx_floor(h.hit));
+            }
+            return;
+        }
+        cnt.s_tri += 4;
+        GX_STEP_FMA(p, p3);
+    }
+}
+
+// SHADE_LEVELSET                                                         cuda_gvdb_raycast.cuh:389-410, :186-197
+// (p from the UNSNAPPED t.x; inclusive bounds; the fine march re-tests the same point and returns at once)
+template <class S>
+__device__ __forceinline__ void gx2_brick_levelset(const GxParams& P, S& smp, int nodeid, float3 t, float3 pos, float3 dir,
+                                                   GxHit& h, GxCount& cnt)
+{
+    const GxLeafRec L = P.leaf[nodeid];
+    cnt.n_desc++;
+    smp.enter(L);
+    const float3 vmin = make_float3(float(L.px), float(L.py), float(L.pz));
+    const float3 o = make_float3(float(L.vx), float(L.vy), float(L.vz));
+    const float res0 = float(P.res[0]);
+    const float st = P.steps.x, thr = P.thresh.x;
+    float3 p = pos + t.x * dir - vmin;
+    int n = gx_safe_samples(p, st * dir, res0);
+    for (int iter = 0; iter < GX_MAX_ITER; iter += 4) {
+        float3 p1, p2, p3;
+        GX_STEP_FMA(p1, p); GX_STEP_FMA(p2, p1); GX_STEP_FMA(p3, p2);
+        bool k0 = true, k1 = true, k2 = true, k3 = true;
+        if (n >= 4) n -= 4;
+        else { n = 0; k0 = GX_INB_LE(p, res0); k1 = GX_INB_LE(p1, res0); k2 = GX_INB_LE(p2, res0); k3 = GX_INB_LE(p3, res0); }
+        const float v0 = smp.tri(p.x + o.x, p.y + o.y, p.z + o.z);
+        const float v1 = smp.tri(p1.x + o.x, p1.y + o.y, p1.z + o.z);
+        const float v2 = smp.tri(p2.x + o.x, p2.y + o.y, p2.z + o.z);
+        const float v3 = smp.tri(p3.x + o.x, p3.y + o.y, p3.z + o.z);
+        int k = -1;
+        bool hit = false;
+        if (!k0) k = 0; else if (v0 < thr) { k = 0; hit = true; }
+        else if (!k1) k = 1; else if (v1 < thr) { k = 1; hit = true; p = p1; }
+        else if (!k2) k = 2; else if (v2 < thr) { k = 2; hit = true; p = p2; }
+        else if (!k3) k = 3; else if (v3 < thr) { k = 3; hit = true; p = p3; }
+        if (k >= 0) {
+            cnt.s_tri += k + (hit ? 2 : 0);
+            if (hit) {
+                h.hit = p + vmin;       // always != NOHIT for finite coordinates: the reference accepts it and returns
+                h.norm = gx_gradient(smp, p + o, cnt, true);
+                h.t = t.x; h.leaf = nodeid; h.vox = gx_i3(gx_floor(h.hit));
+            }
+            return;
+        }
+        cnt.s_tri += 4;
+        GX_STEP_FMA(p, p3);
+    }
+}
+
+// one emission/absorption update for a sample that passed the MINVAL test     cuda_gvdb_raycast.cuh:514-523
+__device__ __forceinline__ void gx_deep_accumulate(const GxParams& P, float4& clr, float4 val)
+{
+    val.w = exp(P.extinct.x * val.w * P.steps.x);
+    const float om = 1 - val.w;
+    clr.x = __fadd_rn(clr.x, __fmul_rn(__fmul_rn(__fmul_rn(__fmul_rn(val.x, clr.w), om), P.extinct.y), 1.0f));
+    clr.y = __fadd_rn(clr.y, __fmul_rn(__fmul_rn(__fmul_rn(__fmul_rn(val.y, clr.w), om), P.extinct.y), 1.0f));
+    clr.z = __fadd_rn(clr.z, __fmul_rn(__fmul_rn(__fmul_rn(__fmul_rn(val.z, clr.w), om), P.extinct.y), 1.0f));
+    clr.w *= val.w;
+}
+// transfer-function index (cuda_gvdb_dda.cuh:20-23): float divide (= multiply by the approximate reciprocal, which is
+// what div.approx lowers to), then clamp and scale in double, truncate.
+__device__ __forceinline__ int gx_transfer_index(float v, float thresh, float inv_range)
+{
+    return int(min(1.0, max(0.0, (v - thresh) * inv_range)) * 16300.0f);
+}
+
+// SHADE_VOLUME                                                           cuda_gvdb_raycast.cuh:485-533
+template <class S>
+__device__ __forceinline__ void gx2_brick_deep(const GxParams& P, S& smp, int nodeid, float3 t, float3 pos, float3 dir,
+                                               GxHit& h, GxCount& cnt, float tDepth)
+{
+    const GxLeafRec L = P.leaf[nodeid];
+    cnt.n_desc++;
+    smp.enter(L);
+    const float3 vmin = make_float3(float(L.px), float(L.py), float(L.pz));
+    const float st = P.steps.x;
+    t.x = st * ceilf(t.x / st);
+    const float3 o = make_float3(float(L.vx), float(L.vy), float(L.vz));
+    float3 wp = pos + t.x * dir;
+    float3 p = wp - vmin;
+    const float3 wpt = make_float3(__fmul_rn(st, dir.x), __fmul_rn(st, dir.y), __fmul_rn(st, dir.z));
+    const float dt = sqrtf(gx_dot(wpt, wpt));
+    const float res0 = float(P.res[0]);
+    const float minval = P.cutoff.x, acut = P.cutoff.y, thresh = P.thresh.x;
+    const float inv_range = gx_rcp_approx(P.thresh.z - P.thresh.y);
+    float4& clr = h.clr;
+    if (h.hit.x == 0) h.hit.x = t.x;
+
+    if (P.dbuf != nullptr) {            // depth-buffer compositing: one sample at a time, as written in the reference
+        for (int iter = 0; clr.w > acut && iter < GX_MAX_ITER && GX_INB(p, res0); iter++) {
+            if (t.x > tDepth) {
+                float3 d = wp - pos;
+                h.hit.y = sqrtf(gx_dot(d, d));
+                h.hit.z = 1;
+                clr = make_float4(fminf(clr.x, 1.f), fminf(clr.y, 1.f), fminf(clr.z, 1.f), fmaxf(clr.w, 0.f));
+                return;
+            }
+            cnt.s_tri++;
+            const float raw = smp.tri(p.x + o.x, p.y + o.y, p.z + o.z);
+            if (raw >= minval) { cnt.s_lut++; gx_deep_accumulate(P, clr, __ldg(&P.transfer[gx_transfer_index(raw, thresh, inv_range)])); }
+            GX_STEP_ADD(p, p); GX_STEP_ADD(wp, wp);
+            t.x += dt;
+        }
+    } else {
+        int n = gx_safe_samples(p, wpt, res0);
+        for (int iter = 0; iter < GX_MAX_ITER && clr.w > acut; iter += 4) {
+            float3 p1, p2, p3;
+            GX_STEP_ADD(p1, p); GX_STEP_ADD(p2, p1); GX_STEP_ADD(p3, p2);
+            bool k0 = true, k1 = true, k2 = true, k3 = true;
+            if (n >= 4) n -= 4;
+            else { n = 0; k0 = GX_INB(p, res0); k1 = GX_INB(p1, res0); k2 = GX_INB(p2, res0); k3 = GX_INB(p3, res0); }
+            const float v0 = smp.tri(p.x + o.x, p.y + o.y, p.z + o.z);
+            const float v1 = smp.tri(p1.x + o.x, p1.y + o.y, p1.z + o.z);
+            const float v2 = smp.tri(p2.x + o.x, p2.y + o.y, p2.z + o.z);
+            const float v3 = smp.tri(p3.x + o.x, p3.y + o.y, p3.z + o.z);
+            const bool a0 = v0 >= minval, a1 = v1 >= minval, a2 = v2 >= minval, a3 = v3 >= minval;
+            // transfer-function reads of the whole round in flight together (entry 0 for rejected samples, unused)
+            const float4 c0 = __ldg(&P.transfer[a0 ? gx_transfer_index(v0, thresh, inv_range) : 0]);
+            const float4 c1 = __ldg(&P.transfer[a1 ? gx_transfer_index(v1, thresh, inv_range) : 0]);
+            const float4 c2 = __ldg(&P.transfer[a2 ? gx_transfer_index(v2, thresh, inv_range) : 0]);
+            const float4 c3 = __ldg(&P.transfer[a3 ? gx_transfer_index(v3, thresh, inv_range) : 0]);
+            // consume in order; `done` = samples processed (each is followed by one position / t step in the reference)
+            int done = 0;
+            bool more = k0;             // loop condition for sample 0 (alpha was checked by the for statement)
+            if (more) { done = 1; cnt.s_tri++; if (a0) { cnt.s_lut++; gx_deep_accumulate(P, clr, c0); } more = k1 && clr.w > acut; }
+            if (more) { done = 2; cnt.s_tri++; if (a1) { cnt.s_lut++; gx_deep_accumulate(P, clr, c1); } more = k2 && clr.w > acut; }
+            if (more) { done = 3; cnt.s_tri++; if (a2) { cnt.s_lut++; gx_deep_accumulate(P, clr, c2); } more = k3 && clr.w > acut; }
+            if (more) { done = 4; cnt.s_tri++; if (a3) { cnt.s_lut++; gx_deep_accumulate(P, clr, c3); } }
+            for (int q = 0; q < done; q++) t.x += dt;
+            if (done < 4) break;        // left the brick or fell below ALPHACUT inside this round
+            GX_STEP_ADD(p, p3);
+        }
+    }
+    h.hit.y = t.x;
+    clr = make_float4(fminf(clr.x, 1.f), fminf(clr.y, 1.f), fminf(clr.z, 1.f), fmaxf(clr.w, 0.f));
+}
+
+// ------------------------------------------------------------------------------------------------ traversal state
+struct GxTrav {
+    GxDDA   dda;
+    GxStack st;
+    int     lev, iter;
+    float   tDepth;
+    bool    alive;
+};
+
+// entry of rayCast: slab test, root, first Prepare                      cuda_gvdb_raycast.cuh:551-565
+__device__ __forceinline__ void gx2_start(const GxParams& P, GxTrav& T, float3 pos, float3 dir, GxCount& cnt, int px, int py)
+{
+    T.alive = false; T.iter = 0;
+    T.lev = P.top_lev;
+    T.st.n1 = T.st.n2 = T.st.n3 = T.st.n4 = 0; T.st.m1 = T.st.m2 = T.st.m3 = T.st.m4 = 0.f;
+    cnt.rays++;
+    float3 tStart = gx_ray_box(pos, dir, P.bmin, P.bmax);
+    if (tStart.z == GX_NOHIT) return;
+    if (T.lev < 1 || T.lev >= GX_MAXLEV) return;
+    const int4 np = __ldg(&P.npos[T.lev][0]);
+    cnt.n_desc++;
+    const float3 vmin = make_float3(float(np.x), float(np.y), float(np.z));
+    tStart.x += P.epsilon;
+    T.st.set(T.lev, 0, tStart.y - P.epsilon);
+    T.dda.set_ray(pos, dir, tStart);
+    T.dda.prepare(vmin, P.vdel[T.lev]);
+    T.tDepth = gx_depth_max(P, dir, px, py);
+    T.alive = true;
+}
+
+// pop levels whose exit has been passed                                  cuda_gvdb_raycast.cuh:603-609
+__device__ __forceinline__ void gx2_ascend(const GxParams& P, GxTrav& T, GxCount& cnt)
+{
+    while (T.dda.t.x > T.st.tmax(T.lev) && T.lev <= P.top_lev) {
+        T.lev++;
+        if (T.lev <= P.top_lev) {
+            const int4 np = __ldg(&P.npos[T.lev][T.st.node(T.lev)]);
+            cnt.n_desc++;
+            T.dda.prepare(make_float3(float(np.x), float(np.y), float(np.z)), P.vdel[T.lev]);
+        }
+    }
+}
+
+// PHASE A, one iteration: one pass of the reference loop body (cuda_gvdb_raycast.cuh:567-602) minus the brick call.
+// Returns the leaf index when the ray now stands in front of a brick (dda.t.x already moved inside by epsilon; the
+// iteration is completed later by gx2_leave_brick), otherwise -1 (T.alive cleared when the ray is finished).
+__device__ __forceinline__ int gx2_dda_iteration(const GxParams& P, GxTrav& T, GxHit& h, GxCount& cnt)
+{
+    GxDDA& d = T.dda;
+    const int lev = T.lev;
+    if (!(T.iter < GX_MAX_ITER && lev > 0 && lev <= P.top_lev && d.p.x >= 0 && d.p.y >= 0 && d.p.z >= 0
+          && d.p.x <= P.res[lev] && d.p.y <= P.res[lev] && d.p.z <= P.res[lev])) { T.alive = false; return -1; }
+    d.next();
+    if (d.t.x > T.tDepth) { h.hit.z = 0; T.alive = false; return -1; }
+    const int dm = P.dim[lev];
+    const int b = (((int(d.p.z) << dm) + int(d.p.y)) << dm) + int(d.p.x);
+    int c = -1;
+    if (d.p.x < P.res[lev] && d.p.y < P.res[lev] && d.p.z < P.res[lev])
+        c = __ldg(&P.child[lev][(size_t(T.st.node(lev)) << (3 * dm)) + b]);
+    cnt.n_dda++;
+    if (c != -1) {
+        d.t.x += P.epsilon;
+        if (lev == 1) return c;
+        T.lev = lev - 1;
+        const int4 np = __ldg(&P.npos[lev - 1][c]);
+        cnt.n_desc++;
+        T.st.set(lev - 1, c, d.t.y - P.epsilon);
+        d.prepare(make_float3(float(np.x), float(np.y), float(np.z)), P.vdel[lev - 1]);
+    } else {
+        d.step();
+    }
+    gx2_ascend(P, T, cnt);
+    T.iter++;
+    return -1;
+}
+
+// second half of the reference iteration that visited a brick: termination tests, Step, ascend    :584-609
+template <int MODE>
+__device__ __forceinline__ void gx2_leave_brick(const GxParams& P, GxTrav& T, GxHit& h, GxCount& cnt)
+{
+    if (h.clr.w <= 0) { h.clr.w = 0; T.alive = false; return; }
+    if (h.hit.z != GX_NOHIT) { T.alive = false; return; }
+    if (MODE == GX_MODE_DEEP && h.clr.w <= P.cutoff.y) { T.alive = false; return; }   // later bricks cannot change the colour
+    T.dda.step();
+    gx2_ascend(P, T, cnt);
+    T.iter++;
+}
+
+// ------------------------------------------------------------------------------------------------ per-pixel driver
+// All 32 lanes of the warp call this together (`valid` = lane owns a pixel); convergence is forced with warp votes at
+// the head of every DDA iteration and every ray-state transition, so that PHASE B really runs with all lanes that
+// have a brick pending.  Returns the final float colour of the pixel (before 8-bit packing); `prim` receives the
+// primary ray's hit record.
+template <int MODE, class S>
+__device__ __forceinline__ float4 gx2_trace_pixel(const GxParams& P, S& smp, float3 rpos, float3 rdir, int px, int py,
+                                                  GxCount& cnt, GxHit& prim, float4& raw, bool valid)
+{
+    const unsigned FULL = 0xffffffffu;
+    GxTrav T;
+    GxHit h;
+    h.norm = make_float3(0, 0, 0); h.t = 0; h.leaf = -1; h.vox = make_int3(0, 0, 0);
+    if (MODE == GX_MODE_DEEP) { h.clr = make_float4(0, 0, 0, 1); h.hit = make_float3(0, 0, GX_NOHIT); }
+    else { h.clr = make_float4(1, 1, 1, 1);
+           h.hit = (MODE == GX_MODE_LEVELSET) ? make_float3(0, 0, GX_NOHIT) : make_float3(GX_NOHIT, GX_NOHIT, GX_NOHIT); }
+    prim = h;
+    float3 pos = rpos, dir = rdir;
+    int phase = 0;                      // 0 = primary ray, 1 = shadow ray
+    float diff = 0.f;
+    float4 result = make_float4(0, 0, 0, 0);
+    bool done = !valid;
+    T.alive = false; T.iter = 0; T.lev = 0; T.tDepth = 0;
+    if (valid) gx2_start(P, T, pos, dir, cnt, px, py);
+
+    while (!__all_sync(FULL, done)) {
+        // ---- PHASE A: every live lane walks its DDA until it stands in front of a brick or its ray ends
+        int brick = -1;
+        while (__any_sync(FULL, !done && T.alive && brick < 0)) {
+            if (!done && T.alive && brick < 0) brick = gx2_dda_iteration(P, T, h, cnt);
+        }
+        // ---- PHASE B: the warp samples its pending bricks together
+        if (brick >= 0) {
+            if (MODE == GX_MODE_VOXEL)          gx_brick_voxel(P, smp, brick, T.dda.t, pos, dir, h, cnt);
+            else if (MODE == GX_MODE_TRILINEAR) gx2_brick_trilinear(P, smp, brick, T.dda.t, pos, dir, h, cnt);
+            else if (MODE == GX_MODE_LEVELSET)  gx2_brick_levelset(P, smp, brick, T.dda.t, pos, dir, h, cnt);
+            else                                gx2_brick_deep(P, smp, brick, T.dda.t, pos, dir, h, cnt, T.tDepth);
+            gx2_leave_brick<MODE>(P, T, h, cnt);
+        }
+        __syncwarp();
+        if (done || T.alive) continue;
+
+        // ---- the current ray of this lane is finished
+        if (MODE == GX_MODE_DEEP) {
+            raw = h.clr;
+            prim = h;
+            const float a = 1.0 - h.clr.w;
+            result = make_float4(P.backclr.x + a * (h.clr.x - P.backclr.x), P.backclr.y + a * (h.clr.y - P.backclr.y),
+                                 P.backclr.z + a * (h.clr.z - P.backclr.z), 1.0 - h.clr.w);
+            done = true;
+        } else if (phase == 0) {                                 // performPhongShading, cuda_gvdb_module.cu:38-57
+            prim = h;
+            if (h.hit.z == GX_NOHIT) { result = P.backclr; done = true; }
+            else {
+                const float3 lightdir = gx_normalize(P.light_pos - h.hit);
+                diff = 0.9 * fmaxf(0.0f, gx_dot(h.norm, lightdir));
+                if (P.shadow_params.x > 0) {
+                    pos = h.hit + h.norm * P.shadow_params.y;
+                    dir = lightdir;
+                    result = h.clr;                              // surface colour, kept while the shadow ray runs
+                    h.hit = make_float3(0, 0, GX_NOHIT);
+                    h.clr = make_float4(0, 0, 0, 1);
+                    phase = 1;
+                    gx2_start(P, T, pos, dir, cnt, px, py);
+                    if (!T.alive) {                              // shadow ray misses the volume box entirely
+                        result = make_float4(result.x * (diff + 0.1f), result.y * (diff + 0.1f), result.z * (diff + 0.1f), 1.0);
+                        done = true;
+                    }
+                } else {
+                    result = make_float4(h.clr.x * (diff + 0.1f), h.clr.y * (diff + 0.1f), h.clr.z * (diff + 0.1f), 1.0);
+                    done = true;
+                }
+            }
+        } else {                                                 // shadow ray finished
+            diff = (h.hit.z == GX_NOHIT ? diff : diff * (1.0 - P.shadow_params.x));
+            result = make_float4(result.x * (diff + 0.1f), result.y * (diff + 0.1f), result.z * (diff + 0.1f), 1.0);
+            done = true;
+        }
+    }
+    return result;
+}

@@ -306,6 +306,11 @@ int64_t ora_activate_space(ora_tree* t, int x, int y, int z)
     if (id == ID_UNDEFL) return -1;
     return (int64_t)ElemNdx(id);
 }
+/* the activation loop of a volume build: ActivateSpace for n brick corners (xyz triples), in order */
+void ora_activate_bricks(ora_tree* t, const int32_t* pos, int n)
+{
+    for (int i = 0; i < n; i++) ora_activate_space(t, pos[3 * i], pos[3 * i + 1], pos[3 * i + 2]);
+}
 /* ComputeBounds, :1792-1816 (called by FinishTopology :1579-1593) */
 void ora_finish_topology(ora_tree* t)
 {

@@ -26,6 +26,7 @@ typedef struct ora_tree ora_tree;
 ora_tree* ora_tree_create(int levs, const int* logdim, const int* initcnt, int atlas_cx, int atlas_cy, int atlas_cz, int apron);
 void      ora_tree_destroy(ora_tree* t);
 int64_t   ora_activate_space(ora_tree* t, int x, int y, int z);   /* returns leaf index or -1 */
+void      ora_activate_bricks(ora_tree* t, const int32_t* pos, int n);
 void      ora_finish_topology(ora_tree* t);                        /* ComputeBounds */
 void      ora_update_atlas(ora_tree* t);                           /* slot assignment + atlas map */
 void      ora_set_epsilon(ora_tree* t, float eps, int maxiter);

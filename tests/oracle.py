@@ -43,6 +43,7 @@ def lib():
     L.ora_tree_destroy.argtypes = [C.c_void_p]
     L.ora_activate_space.restype = C.c_int64
     L.ora_activate_space.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
+    L.ora_activate_bricks.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
     L.ora_finish_topology.argtypes = [C.c_void_p]
     L.ora_update_atlas.argtypes = [C.c_void_p]
     L.ora_set_epsilon.argtypes = [C.c_void_p, C.c_float, C.c_int]
@@ -96,8 +97,8 @@ def build_volume(brick_pos, values, epsilon=0.001, transfer=None, timing=None):
     initcnt = (C.c_int * 5)(4, 4, 2, 1, 1)          # Configure(q4..q0), gvdb_volume_gvdb.cpp:2364-2377
     t0 = time.perf_counter()
     t = L.ora_tree_create(5, logdim, initcnt, 16, 16, 1, 1)
-    for x, y, z in brick_pos.tolist():
-        L.ora_activate_space(t, x, y, z)
+    bp = np.ascontiguousarray(brick_pos, np.int32)
+    L.ora_activate_bricks(t, bp.ctypes.data_as(C.c_void_p), len(bp))
     L.ora_finish_topology(t)
     L.ora_update_atlas(t)
     if timing is not None:
