@@ -241,10 +241,8 @@ def main():
                 r.render(scn, shade, frame.data_ptr())
                 launches += 1
         else:
-            for scn in scns:
-                tiled.render(scn, shade)
-                tiled.gather()
-                launches += 2 if rank == 0 else 1
+            tiled.render_frames(scns, shade)
+            launches += len(scns) * (2 if rank == 0 else 1)
 
     tiled = mg.TiledFrame(r, w, h, a.tile, rank, world, dev) if world > 1 else None
 
@@ -323,13 +321,12 @@ def main():
                "api": "VolumeGVDB mirror: SetCamera + Render + ReadRenderBuf into pinned host memory"}
         v.close()
     else:
+        def to_host(j, fr):
+            host.copy_(fr, non_blocking=True)                   # D2H of the assembled frame, stream-ordered
+            torch.cuda.current_stream().synchronize()           # the caller owns the host frame now
+
         def step_e2e():
-            for scn in scns:
-                tiled.render(scn, shade)
-                fr = tiled.gather()
-                if rank == 0:
-                    host.copy_(fr, non_blocking=True)
-                    torch.cuda.current_stream().synchronize()
+            tiled.render_frames(scns, shade, on_frame=to_host)
         for _ in range(2):
             step_e2e()
         sync_all()

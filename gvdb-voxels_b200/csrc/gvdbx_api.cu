@@ -20,7 +20,7 @@ struct gvdbx_ctx {
     // options
     int sampler = GX_SAMPLER_TEX, block_w = 8, block_h = 8, count = 0, literal = 0;
     // topology
-    bool       have_topo = false;
+    bool       have_topo = false, uniform3 = false;
     GxVDBInfo  vdb;
     int*       d_child[GX_MAXLEV] = {};
     int4*      d_npos[GX_MAXLEV] = {};
@@ -158,6 +158,8 @@ extern "C" int gvdbx_import_topology(gvdbx_t* h, const void* vdbinfo)
     GX_CUDA(h, cudaGetLastError());
     h->vdb = v;
     h->have_topo = true;
+    h->uniform3 = true;
+    for (int l = 0; l <= v.top_lev; l++) if (v.dim[l] != 3 || v.vdel[l].x != float(1 << (3 * l)) || v.vdel[l].y != v.vdel[l].x || v.vdel[l].z != v.vdel[l].x) h->uniform3 = false;
     return GVDBX_OK;
 }
 
@@ -292,30 +294,31 @@ extern "C" int gvdbx_set_transfer(gvdbx_t* h, const float* rgba_host)
 // ------------------------------------------------------------------------------------------------ render
 typedef void (*gx_kernel_t)(const GxParams);
 
-template <int MODE, int SAMPLER>
+template <int MODE, int SAMPLER, bool UNI>
 static gx_kernel_t gx_pick_flags(int flags)
 {
     switch (flags) {
-    case 0: return gx_render_kernel<MODE, SAMPLER, 0>;
-    case GX_FLAG_DEBUG | GX_FLAG_COUNT: return gx_render_kernel<MODE, SAMPLER, GX_FLAG_DEBUG | GX_FLAG_COUNT>;
-    case GX_FLAG_TILES: return gx_render_kernel<MODE, SAMPLER, GX_FLAG_TILES>;
-    case GX_FLAG_LITERAL: return gx_render_kernel<MODE, SAMPLER, GX_FLAG_LITERAL>;
-    case GX_FLAG_PACKET: return gx_render_kernel<MODE, SAMPLER, GX_FLAG_PACKET>;
+    case 0: return gx_render_kernel<MODE, SAMPLER, 0, UNI>;
+    case GX_FLAG_DEBUG | GX_FLAG_COUNT: return gx_render_kernel<MODE, SAMPLER, GX_FLAG_DEBUG | GX_FLAG_COUNT, UNI>;
+    case GX_FLAG_TILES: return gx_render_kernel<MODE, SAMPLER, GX_FLAG_TILES, UNI>;
+    case GX_FLAG_LITERAL: return gx_render_kernel<MODE, SAMPLER, GX_FLAG_LITERAL, false>;      // A/B variants: generic tree only
+    case GX_FLAG_PACKET: return gx_render_kernel<MODE, SAMPLER, GX_FLAG_PACKET, false>;
     }
     return nullptr;
 }
 template <int MODE>
-static gx_kernel_t gx_pick_sampler(int sampler, int flags)
+static gx_kernel_t gx_pick_sampler(int sampler, int flags, bool uni)
 {
-    return sampler == GX_SAMPLER_TEX ? gx_pick_flags<MODE, GX_SAMPLER_TEX>(flags) : gx_pick_flags<MODE, GX_SAMPLER_LINEAR>(flags);
+    if (sampler == GX_SAMPLER_TEX) return uni ? gx_pick_flags<MODE, GX_SAMPLER_TEX, true>(flags) : gx_pick_flags<MODE, GX_SAMPLER_TEX, false>(flags);
+    return uni ? gx_pick_flags<MODE, GX_SAMPLER_LINEAR, true>(flags) : gx_pick_flags<MODE, GX_SAMPLER_LINEAR, false>(flags);
 }
-static gx_kernel_t gx_pick(int mode, int sampler, int flags)
+static gx_kernel_t gx_pick(int mode, int sampler, int flags, bool uni)
 {
     switch (mode) {
-    case GX_MODE_VOXEL:     return gx_pick_sampler<GX_MODE_VOXEL>(sampler, flags);
-    case GX_MODE_TRILINEAR: return gx_pick_sampler<GX_MODE_TRILINEAR>(sampler, flags);
-    case GX_MODE_LEVELSET:  return gx_pick_sampler<GX_MODE_LEVELSET>(sampler, flags);
-    case GX_MODE_DEEP:      return gx_pick_sampler<GX_MODE_DEEP>(sampler, flags);
+    case GX_MODE_VOXEL:     return gx_pick_sampler<GX_MODE_VOXEL>(sampler, flags, uni);
+    case GX_MODE_TRILINEAR: return gx_pick_sampler<GX_MODE_TRILINEAR>(sampler, flags, uni);
+    case GX_MODE_LEVELSET:  return gx_pick_sampler<GX_MODE_LEVELSET>(sampler, flags, uni);
+    case GX_MODE_DEEP:      return gx_pick_sampler<GX_MODE_DEEP>(sampler, flags, uni);
     }
     return nullptr;
 }
@@ -392,7 +395,7 @@ extern "C" int gvdbx_render(gvdbx_t* h, const void* scninfo, int shade_mode, int
         P.dbg = dbg_tmp;
         GX_CUDA(h, cudaMemsetAsync(h->d_counters, 0, 8 * sizeof(unsigned long long), h->stream));
     }
-    gx_kernel_t k = gx_pick(mode, h->sampler, flags);
+    gx_kernel_t k = gx_pick(mode, h->sampler, flags, h->uniform3);
     dim3 block(h->block_w, h->block_h, 1);
     dim3 grid((P.x1 - P.x0 + block.x - 1) / block.x, (P.y1 - P.y0 + block.y - 1) / block.y, 1);
     k<<<grid, block, 0, h->stream>>>(P);
@@ -412,7 +415,7 @@ extern "C" int gvdbx_render_debug(gvdbx_t* h, const void* scninfo, int shade_mod
     P.out = (uchar4*)outbuf_d;
     P.dbg = (float4*)dbg_d;
     GX_CUDA(h, cudaMemsetAsync(h->d_counters, 0, 8 * sizeof(unsigned long long), h->stream));
-    gx_kernel_t k = gx_pick(mode, h->sampler, GX_FLAG_DEBUG | GX_FLAG_COUNT);
+    gx_kernel_t k = gx_pick(mode, h->sampler, GX_FLAG_DEBUG | GX_FLAG_COUNT, h->uniform3);
     dim3 block(h->block_w, h->block_h, 1);
     dim3 grid((P.width + block.x - 1) / block.x, (P.height + block.y - 1) / block.y, 1);
     k<<<grid, block, 0, h->stream>>>(P);
@@ -444,7 +447,7 @@ extern "C" int gvdbx_render_tiles(gvdbx_t* h, const void* scninfo, int shade_mod
     P.ntiles = P.tiles_x * ((P.height + tile_size - 1) / tile_size);
     P.rank = rank; P.nranks = nranks;
     const int slots = (P.ntiles + nranks - 1) / nranks;
-    gx_kernel_t k = gx_pick(mode, h->sampler, GX_FLAG_TILES);
+    gx_kernel_t k = gx_pick(mode, h->sampler, GX_FLAG_TILES, h->uniform3);
     dim3 block(h->block_w, h->block_h, 1);
     dim3 grid((tile_size / h->block_w) * (tile_size / h->block_h), slots, 1);
     k<<<grid, block, 0, h->stream>>>(P);

@@ -117,14 +117,26 @@ __device__ __forceinline__ float3 gx_mmult(const float* m, float3 v)
     return p;
 }
 
+// MUFU.RCP — what div.approx.ftz lowers to on sm_100a (x / d == x * rcp(d) bit for bit under --use_fast_math), so a
+// reciprocal that is reused many times per ray can be taken once without changing any result.
+__device__ __forceinline__ float gx_rcp_approx(float x)
+{
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
 // ------------------------------------------------------------------------------------------------ work counters
 struct GxCount { unsigned int s_tri, s_pt, n_dda, n_desc, s_lut, rays; };
 
 // ------------------------------------------------------------------------------------------------ samplers
 // Both take ATLAS-space coordinates exactly as the reference passes them to tex3D (p + o).
-template <int SAMPLER> struct GxSampler;
+// UNI = every level of the tree has log2dim 3 (Configure(3,3,3,3,3), the reference's default and all its samples):
+// res = 8, dim = 3, vdel[lev] = 8^lev become compile-time constants.
+template <int SAMPLER, bool UNI_> struct GxSampler;
 
-template <> struct GxSampler<GX_SAMPLER_TEX> {
+template <bool UNI_> struct GxSampler<GX_SAMPLER_TEX, UNI_> {
+    static constexpr bool UNI = UNI_;
     cudaTextureObject_t tex;
     __device__ __forceinline__ GxSampler(const GxParams& P) : tex(P.tex) {}
     __device__ __forceinline__ void enter(const GxLeafRec&) {}
@@ -147,7 +159,8 @@ template <> struct GxSampler<GX_SAMPLER_TEX> {
 // at most 1 ulp-of-result (the unit accumulates wider than fp32).
 // The two x-neighbours of a sample are adjacent floats; a brick is one contiguous 4 KB block, so a warp marching
 // through one brick touches at most 32 consecutive 128-B lines.
-template <> struct GxSampler<GX_SAMPLER_LINEAR> {
+template <bool UNI_> struct GxSampler<GX_SAMPLER_LINEAR, UNI_> {
+    static constexpr bool UNI = UNI_;
     const float* bricks;
     const float* b;      // current brick
     int ox, oy, oz;      // atlas texel index of the brick's texel (0,0,0) = mValue - apron
@@ -206,6 +219,15 @@ template <> struct GxSampler<GX_SAMPLER_LINEAR> {
     }
 };
 
+// ------------------------------------------------------------------------------------------------ tree geometry accessors
+template <class S> __device__ __forceinline__ int gx_res(const GxParams& P, int lev) { return S::UNI ? 8 : P.res[lev]; }
+template <class S> __device__ __forceinline__ int gx_dim(const GxParams& P, int lev) { return S::UNI ? 3 : P.dim[lev]; }
+template <class S> __device__ __forceinline__ float3 gx_vdel(const GxParams& P, int lev)
+{
+    if (S::UNI) { const float v = float(1 << (3 * lev)); return make_float3(v, v, v); }     // 8^lev, exact
+    return P.vdel[lev];
+}
+
 // ------------------------------------------------------------------------------------------------ geometry
 // slab test: (tnear clamped to >= 0, tfar, 0 | NOHIT)                       cuda_gvdb_geom.cuh:85-98
 __device__ __forceinline__ float3 gx_ray_box(float3 rpos, float3 rdir, float3 vmin, float3 vmax)
@@ -225,6 +247,7 @@ __device__ __forceinline__ float3 gx_ray_box(float3 rpos, float3 rdir, float3 vm
 // ------------------------------------------------------------------------------------------------ hierarchical DDA
 struct GxDDA {
     float3 pos, dir;
+    float3 inv;     // MUFU.RCP of dir, taken once per ray
     int3   pStep;
     float3 tDel;
     float3 t;
@@ -235,13 +258,14 @@ struct GxDDA {
     __device__ __forceinline__ void set_ray(float3 startPos, float3 startDir, float3 startT)
     {
         pos = startPos; dir = startDir;
+        inv = make_float3(gx_rcp_approx(dir.x), gx_rcp_approx(dir.y), gx_rcp_approx(dir.z));
         pStep = make_int3((dir.x > 0) ? 1 : -1, (dir.y > 0) ? 1 : -1, (dir.z > 0) ? 1 : -1);
         t = startT;
     }
     // cuda_gvdb_dda.cuh:61-66
     __device__ __forceinline__ void prepare(float3 vmin, float3 vdel)
     {
-        tDel = gx_fabs(vdel / dir);
+        tDel = gx_fabs(vdel * inv);                 // vdel / dir
         float3 pFlt = (pos + t.x * dir - vmin) / vdel;
         tSide = ((gx_floor(pFlt) - pFlt + 0.5f) * gx_f3(pStep) + 0.5) * tDel + t.x;
         p = gx_i3(gx_floor(pFlt));
@@ -249,7 +273,7 @@ struct GxDDA {
     // cuda_gvdb_dda.cuh:70-75 (brick: child size 1, no "+ t.x")
     __device__ __forceinline__ void prepare_leaf(float3 vmin)
     {
-        tDel = gx_fabs(1.0f / dir);
+        tDel = gx_fabs(inv);                        // 1.0f / dir
         float3 pFlt = pos + t.x * dir - vmin;
         tSide = ((gx_floor(pFlt) - pFlt + 0.5f) * gx_f3(pStep) + 0.5) * tDel;
         p = gx_i3(gx_floor(pFlt));
@@ -322,7 +346,7 @@ __device__ __forceinline__ void gx_brick_voxel(const GxParams& P, S& smp, int no
     smp.enter(L);
     float3 vmin = make_float3(float(L.px), float(L.py), float(L.pz));
     float3 o = make_float3(float(L.vx), float(L.vy), float(L.vz));
-    const int res0 = P.res[0];
+    const int res0 = gx_res<S>(P, 0);
 
     GxDDA dda;
     dda.set_ray(pos, dir, t);
@@ -363,7 +387,7 @@ __device__ __forceinline__ void gx_brick_trilinear(const GxParams& P, S& smp, in
     smp.enter(L);
     float3 vmin = make_float3(float(L.px), float(L.py), float(L.pz));
     float3 o = make_float3(float(L.vx), float(L.vy), float(L.vz));
-    const float res0 = float(P.res[0]);
+    const float res0 = float(gx_res<S>(P, 0));
     t.x = P.steps.x * ceilf(t.x / P.steps.x);
     float3 p = pos + t.x * dir - vmin;
 
@@ -391,7 +415,7 @@ __device__ __forceinline__ void gx_brick_levelset(const GxParams& P, S& smp, int
     smp.enter(L);
     float3 vmin = make_float3(float(L.px), float(L.py), float(L.pz));
     float3 o = make_float3(float(L.vx), float(L.vy), float(L.vz));
-    const float res0 = float(P.res[0]);
+    const float res0 = float(gx_res<S>(P, 0));
     float3 p = pos + t.x * dir - vmin;
 
     for (int iter = 0; iter < GX_MAX_ITER && p.x >= 0 && p.y >= 0 && p.z >= 0 && p.x <= res0 && p.y <= res0 && p.z <= res0; iter++) {
@@ -425,7 +449,7 @@ __device__ __forceinline__ void gx_brick_deep(const GxParams& P, S& smp, int nod
     float3 p = wp - vmin;
     const float3 wpt = P.steps.x * dir;
     const float dt = sqrtf(gx_dot(wpt, wpt));
-    const float res0 = float(P.res[0]);
+    const float res0 = float(gx_res<S>(P, 0));
     float4& clr = h.clr;
 
     if (h.hit.x == 0) h.hit.x = t.x;
@@ -502,19 +526,19 @@ __device__ __forceinline__ void gx_raycast(const GxParams& P, S& smp, float3 pos
 
     GxDDA dda;
     dda.set_ray(pos, dir, tStart);
-    dda.prepare(vmin, P.vdel[lev]);
+    dda.prepare(vmin, gx_vdel<S>(P, lev));
     const float tDepth = gx_depth_max(P, dir, px, py);
 
     for (int iter = 0; iter < GX_MAX_ITER && lev > 0 && lev <= P.top_lev && dda.p.x >= 0 && dda.p.y >= 0 && dda.p.z >= 0
-                       && dda.p.x <= P.res[lev] && dda.p.y <= P.res[lev] && dda.p.z <= P.res[lev]; iter++) {
+                       && dda.p.x <= gx_res<S>(P, lev) && dda.p.y <= gx_res<S>(P, lev) && dda.p.z <= gx_res<S>(P, lev); iter++) {
         dda.next();
         if (dda.t.x > tDepth) { h.hit.z = 0; return; }
 
-        const int dm = P.dim[lev];
+        const int dm = gx_dim<S>(P, lev);
         const int b = (((int(dda.p.z) << dm) + int(dda.p.y)) << dm) + int(dda.p.x);
         // cells outside [0,res) can only be reached through the reference's inclusive loop bound; they hold no child
         int c = -1;
-        if ((dda.p.x | dda.p.y | dda.p.z) >= 0 && dda.p.x < P.res[lev] && dda.p.y < P.res[lev] && dda.p.z < P.res[lev])
+        if ((dda.p.x | dda.p.y | dda.p.z) >= 0 && dda.p.x < gx_res<S>(P, lev) && dda.p.y < gx_res<S>(P, lev) && dda.p.z < gx_res<S>(P, lev))
             c = __ldg(&P.child[lev][(size_t(st.node(lev)) << (3 * dm)) + b]);
         cnt.n_dda++;
         if (c != -1) {
@@ -540,7 +564,7 @@ __device__ __forceinline__ void gx_raycast(const GxParams& P, S& smp, float3 pos
                 vmin = make_float3(float(np.x), float(np.y), float(np.z));
                 dda.t.x += P.epsilon;
                 st.set(lev, c, dda.t.y - P.epsilon);
-                dda.prepare(vmin, P.vdel[lev]);
+                dda.prepare(vmin, gx_vdel<S>(P, lev));
             }
         } else {
             dda.step();
@@ -551,7 +575,7 @@ __device__ __forceinline__ void gx_raycast(const GxParams& P, S& smp, float3 pos
                 np = __ldg(&P.npos[lev][st.node(lev)]);
                 cnt.n_desc++;
                 vmin = make_float3(float(np.x), float(np.y), float(np.z));
-                dda.prepare(vmin, P.vdel[lev]);
+                dda.prepare(vmin, gx_vdel<S>(P, lev));
             }
         }
     }
@@ -590,7 +614,7 @@ template <int MODE, class S>
 __device__ __forceinline__ float4 gx2_trace_pixel(const GxParams& P, S& smp, float3 rpos, float3 rdir, int px, int py,
                                                   GxCount& cnt, GxHit& prim, float4& raw, bool valid);
 
-template <int MODE, int SAMPLER, int FLAGS>
+template <int MODE, int SAMPLER, int FLAGS, bool UNI>
 __global__ void __launch_bounds__(256) gx_render_kernel(const __grid_constant__ GxParams P)
 {
     int x, y;
@@ -616,7 +640,7 @@ __global__ void __launch_bounds__(256) gx_render_kernel(const __grid_constant__ 
     }
     if (!(FLAGS & GX_FLAG_PACKET) && !valid) return;     // the packet traversal keeps whole warps alive for its votes
 
-    GxSampler<SAMPLER> smp(P);
+    GxSampler<SAMPLER, UNI> smp(P);
     GxCount cnt = {0, 0, 0, 0, 0, 0};
     GxHit h;
     h.norm = make_float3(0, 0, 0); h.t = 0; h.leaf = -1; h.vox = make_int3(0, 0, 0);
@@ -750,7 +774,7 @@ __global__ void gx_sample_points_kernel(GxParams P, const float* __restrict__ xy
     if (i >= n) return;
     float x = xyz[3 * i], y = xyz[3 * i + 1], z = xyz[3 * i + 2];
     out_tex[i] = tex3D<float>(P.tex, x, y, z);
-    GxSampler<GX_SAMPLER_LINEAR> s(P);
+    GxSampler<GX_SAMPLER_LINEAR, false> s(P);
     GxLeafRec L;
     int sx = int(x) / GX_BRICK_DIM, sy = int(y) / GX_BRICK_DIM, sz = int(z) / GX_BRICK_DIM;
     L.vx = sx * GX_BRICK_DIM + 1; L.vy = sy * GX_BRICK_DIM + 1; L.vz = sz * GX_BRICK_DIM + 1;

@@ -18,13 +18,6 @@
 #pragma once
 #include "gvdbx_device.cuh"
 
-__device__ __forceinline__ float gx_rcp_approx(float x)
-{
-    float r;
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
-    return r;
-}
-
 // Number of consecutive fixed-step samples p, p+d, p+2d, ... that are guaranteed to lie strictly inside (0,res0)^3.
 // Conservative by `m` voxels, far above the accumulated rounding of <= 256 steps (<= 256 * 0.5 ulp(8) = 1.2e-4) and
 // the error of the approximate division.
@@ -62,7 +55,7 @@ __device__ __forceinline__ void gx2_brick_trilinear(const GxParams& P, S& smp, i
     smp.enter(L);
     const float3 vmin = make_float3(float(L.px), float(L.py), float(L.pz));
     const float3 o = make_float3(float(L.vx), float(L.vy), float(L.vz));
-    const float res0 = float(P.res[0]);
+    const float res0 = float(gx_res<S>(P, 0));
     const float st = P.steps.x, thr = P.thresh.x;
     t.x = st * ceilf(t.x / st);
     float3 p = pos + t.x * dir - vmin;
@@ -108,7 +101,7 @@ __device__ __forceinline__ void gx2_brick_levelset(const GxParams& P, S& smp, in
     smp.enter(L);
     const float3 vmin = make_float3(float(L.px), float(L.py), float(L.pz));
     const float3 o = make_float3(float(L.vx), float(L.vy), float(L.vz));
-    const float res0 = float(P.res[0]);
+    const float res0 = float(gx_res<S>(P, 0));
     const float st = P.steps.x, thr = P.thresh.x;
     float3 p = pos + t.x * dir - vmin;
     int n = gx_safe_samples(p, st * dir, res0);
@@ -175,7 +168,7 @@ __device__ __forceinline__ void gx2_brick_deep(const GxParams& P, S& smp, int no
     float3 p = wp - vmin;
     const float3 wpt = make_float3(__fmul_rn(st, dir.x), __fmul_rn(st, dir.y), __fmul_rn(st, dir.z));
     const float dt = sqrtf(gx_dot(wpt, wpt));
-    const float res0 = float(P.res[0]);
+    const float res0 = float(gx_res<S>(P, 0));
     const float minval = P.cutoff.x, acut = P.cutoff.y, thresh = P.thresh.x;
     const float inv_range = gx_rcp_approx(P.thresh.z - P.thresh.y);
     float4& clr = h.clr;
@@ -240,6 +233,7 @@ struct GxTrav {
 };
 
 // entry of rayCast: slab test, root, first Prepare                      cuda_gvdb_raycast.cuh:551-565
+template <class S>
 __device__ __forceinline__ void gx2_start(const GxParams& P, GxTrav& T, float3 pos, float3 dir, GxCount& cnt, int px, int py)
 {
     T.alive = false; T.iter = 0;
@@ -255,12 +249,13 @@ __device__ __forceinline__ void gx2_start(const GxParams& P, GxTrav& T, float3 p
     tStart.x += P.epsilon;
     T.st.set(T.lev, 0, tStart.y - P.epsilon);
     T.dda.set_ray(pos, dir, tStart);
-    T.dda.prepare(vmin, P.vdel[T.lev]);
+    T.dda.prepare(vmin, gx_vdel<S>(P, T.lev));
     T.tDepth = gx_depth_max(P, dir, px, py);
     T.alive = true;
 }
 
 // pop levels whose exit has been passed                                  cuda_gvdb_raycast.cuh:603-609
+template <class S>
 __device__ __forceinline__ void gx2_ascend(const GxParams& P, GxTrav& T, GxCount& cnt)
 {
     while (T.dda.t.x > T.st.tmax(T.lev) && T.lev <= P.top_lev) {
@@ -268,7 +263,7 @@ __device__ __forceinline__ void gx2_ascend(const GxParams& P, GxTrav& T, GxCount
         if (T.lev <= P.top_lev) {
             const int4 np = __ldg(&P.npos[T.lev][T.st.node(T.lev)]);
             cnt.n_desc++;
-            T.dda.prepare(make_float3(float(np.x), float(np.y), float(np.z)), P.vdel[T.lev]);
+            T.dda.prepare(make_float3(float(np.x), float(np.y), float(np.z)), gx_vdel<S>(P, T.lev));
         }
     }
 }
@@ -276,18 +271,19 @@ __device__ __forceinline__ void gx2_ascend(const GxParams& P, GxTrav& T, GxCount
 // PHASE A, one iteration: one pass of the reference loop body (cuda_gvdb_raycast.cuh:567-602) minus the brick call.
 // Returns the leaf index when the ray now stands in front of a brick (dda.t.x already moved inside by epsilon; the
 // iteration is completed later by gx2_leave_brick), otherwise -1 (T.alive cleared when the ray is finished).
+template <class S>
 __device__ __forceinline__ int gx2_dda_iteration(const GxParams& P, GxTrav& T, GxHit& h, GxCount& cnt)
 {
     GxDDA& d = T.dda;
     const int lev = T.lev;
     if (!(T.iter < GX_MAX_ITER && lev > 0 && lev <= P.top_lev && d.p.x >= 0 && d.p.y >= 0 && d.p.z >= 0
-          && d.p.x <= P.res[lev] && d.p.y <= P.res[lev] && d.p.z <= P.res[lev])) { T.alive = false; return -1; }
+          && d.p.x <= gx_res<S>(P, lev) && d.p.y <= gx_res<S>(P, lev) && d.p.z <= gx_res<S>(P, lev))) { T.alive = false; return -1; }
     d.next();
     if (d.t.x > T.tDepth) { h.hit.z = 0; T.alive = false; return -1; }
-    const int dm = P.dim[lev];
+    const int dm = gx_dim<S>(P, lev);
     const int b = (((int(d.p.z) << dm) + int(d.p.y)) << dm) + int(d.p.x);
     int c = -1;
-    if (d.p.x < P.res[lev] && d.p.y < P.res[lev] && d.p.z < P.res[lev])
+    if (d.p.x < gx_res<S>(P, lev) && d.p.y < gx_res<S>(P, lev) && d.p.z < gx_res<S>(P, lev))
         c = __ldg(&P.child[lev][(size_t(T.st.node(lev)) << (3 * dm)) + b]);
     cnt.n_dda++;
     if (c != -1) {
@@ -297,24 +293,24 @@ __device__ __forceinline__ int gx2_dda_iteration(const GxParams& P, GxTrav& T, G
         const int4 np = __ldg(&P.npos[lev - 1][c]);
         cnt.n_desc++;
         T.st.set(lev - 1, c, d.t.y - P.epsilon);
-        d.prepare(make_float3(float(np.x), float(np.y), float(np.z)), P.vdel[lev - 1]);
+        d.prepare(make_float3(float(np.x), float(np.y), float(np.z)), gx_vdel<S>(P, lev - 1));
     } else {
         d.step();
     }
-    gx2_ascend(P, T, cnt);
+    gx2_ascend<S>(P, T, cnt);
     T.iter++;
     return -1;
 }
 
 // second half of the reference iteration that visited a brick: termination tests, Step, ascend    :584-609
-template <int MODE>
+template <int MODE, class S>
 __device__ __forceinline__ void gx2_leave_brick(const GxParams& P, GxTrav& T, GxHit& h, GxCount& cnt)
 {
     if (h.clr.w <= 0) { h.clr.w = 0; T.alive = false; return; }
     if (h.hit.z != GX_NOHIT) { T.alive = false; return; }
     if (MODE == GX_MODE_DEEP && h.clr.w <= P.cutoff.y) { T.alive = false; return; }   // later bricks cannot change the colour
     T.dda.step();
-    gx2_ascend(P, T, cnt);
+    gx2_ascend<S>(P, T, cnt);
     T.iter++;
 }
 
@@ -341,13 +337,13 @@ __device__ __forceinline__ float4 gx2_trace_pixel(const GxParams& P, S& smp, flo
     float4 result = make_float4(0, 0, 0, 0);
     bool done = !valid;
     T.alive = false; T.iter = 0; T.lev = 0; T.tDepth = 0;
-    if (valid) gx2_start(P, T, pos, dir, cnt, px, py);
+    if (valid) gx2_start<S>(P, T, pos, dir, cnt, px, py);
 
     while (!__all_sync(FULL, done)) {
         // ---- PHASE A: every live lane walks its DDA until it stands in front of a brick or its ray ends
         int brick = -1;
         while (__any_sync(FULL, !done && T.alive && brick < 0)) {
-            if (!done && T.alive && brick < 0) brick = gx2_dda_iteration(P, T, h, cnt);
+            if (!done && T.alive && brick < 0) brick = gx2_dda_iteration<S>(P, T, h, cnt);
         }
         // ---- PHASE B: the warp samples its pending bricks together
         if (brick >= 0) {
@@ -355,7 +351,7 @@ __device__ __forceinline__ float4 gx2_trace_pixel(const GxParams& P, S& smp, flo
             else if (MODE == GX_MODE_TRILINEAR) gx2_brick_trilinear(P, smp, brick, T.dda.t, pos, dir, h, cnt);
             else if (MODE == GX_MODE_LEVELSET)  gx2_brick_levelset(P, smp, brick, T.dda.t, pos, dir, h, cnt);
             else                                gx2_brick_deep(P, smp, brick, T.dda.t, pos, dir, h, cnt, T.tDepth);
-            gx2_leave_brick<MODE>(P, T, h, cnt);
+            gx2_leave_brick<MODE, S>(P, T, h, cnt);
         }
         __syncwarp();
         if (done || T.alive) continue;
@@ -381,7 +377,7 @@ __device__ __forceinline__ float4 gx2_trace_pixel(const GxParams& P, S& smp, flo
                     h.hit = make_float3(0, 0, GX_NOHIT);
                     h.clr = make_float4(0, 0, 0, 1);
                     phase = 1;
-                    gx2_start(P, T, pos, dir, cnt, px, py);
+                    gx2_start<S>(P, T, pos, dir, cnt, px, py);
                     if (!T.alive) {                              // shadow ray misses the volume box entirely
                         result = make_float4(result.x * (diff + 0.1f), result.y * (diff + 0.1f), result.z * (diff + 0.1f), 1.0);
                         done = true;

@@ -52,30 +52,59 @@ def assemble_tiles_host(gathered, width, height, tile_size, world):
 
 
 class TiledFrame:
-    """Per-rank state for rendering one frame size across `world` ranks."""
+    """Per-rank state for rendering frames of one size across `world` ranks.
+
+    Frames are pipelined: the tile gather of frame j (NCCL stream) overlaps the render of frame j+1 (render stream);
+    packed / gathered buffers are double-buffered so that a buffer is never rewritten while its gather is in flight."""
 
     def __init__(self, renderer, width, height, tile_size, rank, world, device):
         import torch
         self.r, self.w, self.h, self.ts, self.rank, self.world = renderer, width, height, tile_size, rank, world
         self.slots = slots_per_rank(width, height, tile_size, world)
-        self.packed = torch.zeros((self.slots, tile_size, tile_size, 4), dtype=torch.uint8, device=device)
-        self.gathered = None
+        self.packed = [torch.zeros((self.slots, tile_size, tile_size, 4), dtype=torch.uint8, device=device) for _ in range(2)]
+        self.gathered = [None, None]
         self.frame = None
         if rank == 0:
-            self.gathered = torch.zeros((world, self.slots, tile_size, tile_size, 4), dtype=torch.uint8, device=device)
+            self.gathered = [torch.zeros((world, self.slots, tile_size, tile_size, 4), dtype=torch.uint8, device=device)
+                             for _ in range(2)]
             self.frame = torch.zeros((height, width, 4), dtype=torch.uint8, device=device)
+        self._pending = None          # (buffer index, work handle) of the gather in flight
 
-    def render(self, scninfo, shade):
-        self.r.render_tiles(scninfo, shade, self.packed.data_ptr(), self.ts, self.rank, self.world)
+    def _assemble(self, b):
+        src = self.packed[b] if self.world == 1 else self.gathered[b]
+        self.r.assemble_tiles(src.data_ptr(), self.frame.data_ptr(), self.w, self.h, self.ts, self.world)
 
-    def gather(self):
-        """tiles -> rank 0 (NCCL gather on the current stream), then un-permute on rank 0."""
+    def _finish_pending(self):
+        if self._pending is not None:
+            b, work = self._pending
+            if work is not None:
+                work.wait()           # render stream waits for the collective (stream-ordered, no host sync)
+            if self.rank == 0:
+                self._assemble(b)
+            self._pending = None
+
+    def render_frames(self, scninfos, shade, on_frame=None):
+        """Render a sequence of frames; on rank 0 `on_frame(j, frame_tensor)` is called when frame j is assembled
+        (stream-ordered: consume it on the current stream)."""
         import torch.distributed as dist
-        if self.world == 1:
-            src = self.packed
-        else:
-            dist.gather(self.packed, list(self.gathered.unbind(0)) if self.rank == 0 else None, dst=0)
-            src = self.gathered
-        if self.rank == 0:
-            self.r.assemble_tiles(src.data_ptr(), self.frame.data_ptr(), self.w, self.h, self.ts, self.world)
+        for j, scn in enumerate(scninfos):
+            b = j & 1
+            self.r.render_tiles(scn, shade, self.packed[b].data_ptr(), self.ts, self.rank, self.world)
+            work = None
+            if self.world > 1:
+                work = dist.gather(self.packed[b], list(self.gathered[b].unbind(0)) if self.rank == 0 else None, dst=0, async_op=True)
+            prev = self._pending
+            if prev is not None:      # finish frame j-1 while frame j's gather runs
+                self._finish_pending()
+                if on_frame is not None and self.rank == 0:
+                    on_frame(j - 1, self.frame)
+            self._pending = (b, work)
+        self._finish_pending()
+        if on_frame is not None and self.rank == 0 and len(scninfos):
+            on_frame(len(scninfos) - 1, self.frame)
+        return self.frame
+
+    # single-frame convenience (no overlap)
+    def render(self, scninfo, shade):
+        self.render_frames([scninfo], shade)
         return self.frame
