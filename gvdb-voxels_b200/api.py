@@ -22,7 +22,7 @@ EXPORTED_SYMBOLS = [
     "gvdbx_import_topology", "gvdbx_import_topology_host",
     "gvdbx_import_atlas_array", "gvdbx_import_atlas_host", "gvdbx_set_transfer",
     "gvdbx_render", "gvdbx_render_tiles", "gvdbx_tiles_per_rank", "gvdbx_assemble_tiles",
-    "gvdbx_render_debug", "gvdbx_read_buffer", "gvdbx_sync", "gvdbx_get_counters",
+    "gvdbx_render_debug", "gvdbx_raytrace", "gvdbx_read_buffer", "gvdbx_sync", "gvdbx_get_counters",
     "gvdbx_sample_points",
 ]
 
@@ -71,6 +71,7 @@ def lib():
     L.gvdbx_tiles_per_rank.argtypes = [i32, i32, i32, i32]
     L.gvdbx_assemble_tiles.argtypes = [vp, u64, u64, i32, i32, i32, i32]
     L.gvdbx_render_debug.argtypes = [vp, vp, i32, i32, u64, u64]
+    L.gvdbx_raytrace.argtypes = [vp, vp, i32, u64, i32, C.c_float]
     L.gvdbx_read_buffer.argtypes = [vp, u64, vp, C.c_size_t]
     L.gvdbx_sync.argtypes = [vp]
     L.gvdbx_get_counters.argtypes = [vp, C.POINTER(Counters)]
@@ -195,6 +196,11 @@ class Renderer:
     def assemble_tiles(self, gathered_ptr, frame_ptr, width, height, tile_size, nranks):
         self._ck(self._L.gvdbx_assemble_tiles(self._h, int(gathered_ptr), int(frame_ptr), width, height, tile_size, nranks),
                  "gvdbx_assemble_tiles")
+
+    def raytrace(self, scninfo, rays_ptr, num_rays, bias, chan=0):
+        """VolumeGVDB::Raytrace on a device array of 64-byte ScnRay records (in place)."""
+        p, keep = _buf(scninfo)
+        self._ck(self._L.gvdbx_raytrace(self._h, p, chan, int(rays_ptr), int(num_rays), C.c_float(bias)), "gvdbx_raytrace")
 
     def read_buffer(self, buf_ptr, nbytes):
         out = np.empty(nbytes, dtype=np.uint8)

@@ -468,6 +468,29 @@ extern "C" int gvdbx_assemble_tiles(gvdbx_t* h, uint64_t gathered_d, uint64_t fr
     return GVDBX_OK;
 }
 
+// VolumeGVDB::Raytrace (gvdb_volume_gvdb.cpp:4384-4408): `rays_d` = device array of n 64-byte ScnRay records, updated in
+// place (hit, normal).  ScnInfo supplies steps / thresholds exactly like PrepareRender(1,1,0) does for the reference.
+extern "C" int gvdbx_raytrace(gvdbx_t* h, const void* scninfo, int chan, uint64_t rays_d, int num_rays, float bias)
+{
+    if (!h) return GVDBX_E_ARG;
+    GX_CUDA(h, cudaSetDevice(h->device));
+    GxParams P; int mode = 0;
+    int rc = gx_fill_params(h, scninfo, GVDBX_SHADE_TRILINEAR, chan, P, mode);
+    if (rc) return rc;
+    if (!rays_d || num_rays <= 0) return gx_fail(h, GVDBX_E_ARG, "rays/num_rays");
+    P.dbuf = nullptr;                                   // per-pixel depth buffers do not apply to ray bundles
+    const unsigned blocks = (num_rays + 63) / 64;       // 64-thread CTAs like the reference launch
+    if (h->sampler == GX_SAMPLER_TEX) {
+        if (h->uniform3) gx_raytrace_kernel<GX_SAMPLER_TEX, true><<<blocks, 64, 0, h->stream>>>(P, (float*)rays_d, num_rays, bias);
+        else             gx_raytrace_kernel<GX_SAMPLER_TEX, false><<<blocks, 64, 0, h->stream>>>(P, (float*)rays_d, num_rays, bias);
+    } else {
+        if (h->uniform3) gx_raytrace_kernel<GX_SAMPLER_LINEAR, true><<<blocks, 64, 0, h->stream>>>(P, (float*)rays_d, num_rays, bias);
+        else             gx_raytrace_kernel<GX_SAMPLER_LINEAR, false><<<blocks, 64, 0, h->stream>>>(P, (float*)rays_d, num_rays, bias);
+    }
+    GX_CUDA(h, cudaGetLastError());
+    return GVDBX_OK;
+}
+
 extern "C" int gvdbx_read_buffer(gvdbx_t* h, uint64_t buf_d, void* host, size_t bytes)
 {
     if (!h || !buf_d || !host) return GVDBX_E_ARG;

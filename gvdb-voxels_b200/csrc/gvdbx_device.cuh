@@ -695,6 +695,29 @@ __global__ void __launch_bounds__(256) gx_render_kernel(const __grid_constant__ 
     }
 }
 
+// ------------------------------------------------------------------------------------------------ explicit ray bundles
+// gvdbRaytrace (cuda_gvdb_module.cu:211-222): one thread per 64-byte ScnRay record {hit@0, normal@12, orig@24, dir@36,
+// clr@48, pnode@52, pndx@56}; surface hit with the trilinear brick function, hit pulled back by `bias` along the ray.
+template <int SAMPLER, bool UNI>
+__global__ void __launch_bounds__(64) gx_raytrace_kernel(const __grid_constant__ GxParams P, float* __restrict__ rays, int num_rays, float bias)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= num_rays) return;
+    float* r = rays + 16 * size_t(i);
+    GxSampler<SAMPLER, UNI> smp(P);
+    GxCount cnt = {0, 0, 0, 0, 0, 0};
+    GxHit h;
+    h.hit = make_float3(GX_NOHIT, GX_NOHIT, GX_NOHIT);
+    h.norm = make_float3(r[3], r[4], r[5]);                 // left as it was when nothing is hit
+    h.clr = make_float4(1, 1, 1, 1);
+    h.t = 0; h.leaf = -1; h.vox = make_int3(0, 0, 0);
+    const float3 orig = make_float3(r[6], r[7], r[8]), dir = make_float3(r[9], r[10], r[11]);
+    gx_raycast<GX_MODE_TRILINEAR, true>(P, smp, orig, dir, h, cnt, 0, 0);
+    if (h.hit.z != GX_NOHIT) h.hit -= dir * bias;
+    r[0] = h.hit.x; r[1] = h.hit.y; r[2] = h.hit.z;
+    r[3] = h.norm.x; r[4] = h.norm.y; r[5] = h.norm.z;
+}
+
 // ------------------------------------------------------------------------------------------------ import kernels
 // pool-0 / pool-1 (reference layout) -> compact tables.  One thread per child cell.
 //   child list entry = Elem(0, lev-1, ndx) = grp | lev << 8 | ndx << 16, or 0xFFFFFFFFFFFFFFFF (src/gvdb_allocator.h:59-62,

@@ -113,6 +113,12 @@ int  gvdbx_assemble_tiles(gvdbx_t* h, uint64_t gathered_d, uint64_t frame_d, int
  * (deep mode: float4 raw colour before compositing, float4 {hit.x, hit.y, hit.z, 0}, int4 0). */
 int  gvdbx_render_debug(gvdbx_t* h, const void* scninfo, int shade_mode, int chan, uint64_t outbuf_d, uint64_t dbg_d);
 
+/* VolumeGVDB::Raytrace (src/gvdb_volume_gvdb.cpp:4384-4408, kernel gvdbRaytrace kernels/cuda_gvdb_module.cu:211-222):
+ * traces `num_rays` explicit rays given as 64-byte ScnRay records (hit@0, normal@12, orig@24, dir@36, clr@48, pnode@52,
+ * pndx@56; src/gvdb_volume_gvdb.h:300-308) in DEVICE memory with the trilinear surface brick function; writes hit
+ * (pulled back by `bias` along the ray) and normal in place, hit = (NOHIT,NOHIT,NOHIT) on a miss. */
+int  gvdbx_raytrace(gvdbx_t* h, const void* scninfo, int chan, uint64_t rays_d, int num_rays, float bias);
+
 /* ReadRenderBuf: device -> host copy of `bytes`, synchronises the stream. */
 int  gvdbx_read_buffer(gvdbx_t* h, uint64_t buf_d, void* host, size_t bytes);
 int  gvdbx_sync(gvdbx_t* h);

@@ -56,6 +56,8 @@ int main(int argc, char** argv)
     std::string preset = argv[1], outdir = argv[2], modes = "";
     int W = 0, H = 0, frames = 1, warmup = 0, nodump = 0, shadow = -1, hits = 1, bench = 0, orbit = 8, steps = 5;
     std::string bmode = "";
+    float xf[12] = {0, 0, 0, 1, 1, 1, 0, 0, 0, 0, 0, 0};
+    int have_xf = 0, use_dbuf = 0, nrays = 0;
     for (int i = 3; i < argc; i++) {
         std::string a = argv[i];
         if (a == "--modes" && i + 1 < argc) modes = argv[++i];
@@ -69,6 +71,9 @@ int main(int argc, char** argv)
         else if (a == "--orbit" && i + 1 < argc) orbit = atoi(argv[++i]);
         else if (a == "--steps" && i + 1 < argc) steps = atoi(argv[++i]);
         else if (a == "--mode" && i + 1 < argc) bmode = argv[++i];
+        else if (a == "--xform" && i + 1 < argc) { have_xf = 1; sscanf(argv[++i], "%f,%f,%f,%f,%f,%f,%f,%f,%f,%f,%f,%f", xf, xf + 1, xf + 2, xf + 3, xf + 4, xf + 5, xf + 6, xf + 7, xf + 8, xf + 9, xf + 10, xf + 11); }
+        else if (a == "--dbuf") use_dbuf = 1;
+        else if (a == "--raytrace" && i + 1 < argc) nrays = atoi(argv[++i]);
     }
     scene_preset P;
     if (scene_get_preset(preset.c_str(), &P)) { fprintf(stderr, "unknown preset %s\n", preset.c_str()); return 1; }
@@ -157,6 +162,38 @@ int main(int argc, char** argv)
     const int w = P.width, h = P.height;
     gvdb.AddRenderBuf(0, w, h, 4);
     gvdb.AddRenderBuf(1, w, h, 32);
+    // --xform: VolumeGVDB::SetTransform(pretrans, scale, angles, trans)   (gvdb_volume_gvdb.cpp:5770)
+    if (have_xf) gvdb.SetTransform(Vector3DF(xf[0], xf[1], xf[2]), Vector3DF(xf[3], xf[4], xf[5]), Vector3DF(xf[6], xf[7], xf[8]), Vector3DF(xf[9], xf[10], xf[11]));
+    // --dbuf: a synthetic depth buffer in a plain render buffer (AddDepthBuf itself needs GL): NDC depth of a slanted
+    // plane between 0.8 and 1.2 camera distances, bound with Scene::SetDepthBuf (consumed at gvdb_volume_gvdb.cpp:4300)
+    if (use_dbuf) {
+        gvdb.AddRenderBuf(2, w, h, 4);
+        std::vector<float> z((size_t)w * h);
+        const double n = cam->getNear(), f = cam->getFar();
+        for (int y = 0; y < h; y++) for (int x = 0; x < w; x++) {
+            double lin = P.cam_dist * (0.8 + 0.4 * (double)x / w);
+            z[(size_t)y * w + x] = (float)(f / (f - n) - (n * f / (f - n)) / lin);
+        }
+        cuMemcpyHtoD(gvdb.mRenderBuf[2].gpu, z.data(), z.size() * sizeof(float));
+        scn->SetDepthBuf(2);
+        if (!nodump) dump(outdir + "/dbuf.bin", z.data(), z.size() * sizeof(float));
+    }
+    // --raytrace N: VolumeGVDB::Raytrace on an explicit ray bundle (gvdb_volume_gvdb.cpp:4384-4408, gSprayDeposit usage)
+    if (nrays > 0) {
+        DataPtr rays;
+        gvdb.AllocData(rays, nrays, sizeof(ScnRay));
+        scene_make_rays(&P, nrays, rays.cpu);
+        if (!nodump) dump(outdir + "/rays_in.bin", rays.cpu, (size_t)nrays * 64);
+        gvdb.CommitData(rays);
+        const float bias = -0.0001f;
+        gvdb.Raytrace(rays, 0, SHADE_TRILINEAR, 0, bias);
+        cuCtxSynchronize();
+        gvdb.RetrieveData(rays);
+        if (!nodump) {
+            dump(outdir + "/rays_out.bin", rays.cpu, (size_t)nrays * 64);
+            dump(outdir + "/scninfo_raytrace.bin", gvdb.getScnInfo(), 416);
+        }
+    }
 
 
     // ---- bench mode (bench.py --impl reference): the reference's own CUDA render through its public API

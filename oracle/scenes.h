@@ -294,6 +294,30 @@ static inline int scene_get_preset(const char* name, scene_preset* p)
     return 0;
 }
 
+/* ------------------------------------------------------------------ explicit ray bundles (VolumeGVDB::Raytrace)
+ * n ScnRay records of 64 bytes (src/gvdb_volume_gvdb.h:300-308): hit@0 normal@12 orig@24 dir@36 clr@48 pnode@52 pndx@56.
+ * Origins on a shell of radius 0.9 N around the volume centre, directions towards random points of the central half. */
+static inline void scene_make_rays(const scene_preset* p, int n, void* out)
+{
+    uint64_t s = 0xA5A5A5A55A5A5A5AULL;
+    float c = 0.5f * (float)p->N, R = 0.9f * (float)p->N;
+    for (int i = 0; i < n; i++) {
+        float* r = (float*)((char*)out + 64 * (size_t)i);
+        memset(r, 0, 64);
+        float u = 2.f * scn_u01(&s) - 1.f, ph = 6.2831853f * scn_u01(&s);
+        float q = sqrtf(1.f - u * u);
+        float ox = c + R * q * cosf(ph), oy = c + R * u, oz = c + R * q * sinf(ph);
+        float tx = c + 0.5f * (float)p->N * (scn_u01(&s) - 0.5f), ty = c + 0.5f * (float)p->N * (scn_u01(&s) - 0.5f),
+              tz = c + 0.5f * (float)p->N * (scn_u01(&s) - 0.5f);
+        float dx = tx - ox, dy = ty - oy, dz = tz - oz;
+        float il = 1.0f / sqrtf(dx * dx + dy * dy + dz * dz);
+        r[3] = 7.f; r[4] = 8.f; r[5] = 9.f;               /* normal: left untouched by the kernel on a miss */
+        r[6] = ox; r[7] = oy; r[8] = oz;
+        r[9] = dx * il; r[10] = dy * il; r[11] = dz * il;
+        ((uint32_t*)r)[12] = 0xFF00FF00u + (uint32_t)i;
+    }
+}
+
 #ifdef __cplusplus
 }
 #endif

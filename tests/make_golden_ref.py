@@ -47,5 +47,36 @@ def main(outdir):
         print("[golden]", preset, "bricks", out["bricks"], "atlas", out["atlas_res"], flush=True)
 
 
+def extras(outdir):
+    """golden cases beyond the plain presets: SetTransform, depth-buffer compositing, explicit ray bundles"""
+    xf = (3.0, -2.0, 1.5, 1.25, 0.8, 1.1, 20.0, -35.0, 10.0, 5.0, 7.0, -4.0)
+    for tag, preset, kw in (("xform", "cfg1_small", {"xform": xf}), ("dbuf", "cfg4_small", {"dbuf": True}),
+                            ("rays", "cfg1_small", {"raytrace": 20000})):
+        d = tempfile.mkdtemp(prefix="refdump_")
+        refcmp.run_ref(preset, d, modes=list(refcmp.MODES), hits=(tag != "rays"), **kw)
+        dump = refcmp.load_dump(d)
+        out = {"preset": preset, "width": dump["meta"]["width"], "height": dump["meta"]["height"],
+               "vdbinfo": np.frombuffer(dump["vdbinfo"], np.uint8)}
+        if tag == "xform":
+            out["xform"] = np.array(xf, np.float32)
+        for m in refcmp.MODES:
+            out[f"scn_{m}"] = np.frombuffer(dump["scn"][m], np.uint8)
+            out[f"rgba_{m}"] = dump["rgba"][m]
+        if tag == "dbuf":
+            out["dbuf"] = dump["dbuf"]
+        if tag == "rays":
+            out["rays_in"] = dump["rays_in"]
+            out["rays_out"] = dump["rays_out"]
+            out["scn_raytrace"] = np.frombuffer(dump["scn_raytrace"], np.uint8)
+            for m in refcmp.MODES:
+                del out[f"rgba_{m}"]
+        np.savez_compressed(os.path.join(outdir, f"ref_extra_{tag}.npz"), **out)
+        print("[golden] extra", tag, preset, flush=True)
+
+
 if __name__ == "__main__":
-    main(sys.argv[1] if len(sys.argv) > 1 else os.path.join(ROOT, "gpurun_out", "golden"))
+    out = sys.argv[1] if len(sys.argv) > 1 else os.path.join(ROOT, "gpurun_out", "golden")
+    if "--extras-only" not in sys.argv:
+        main(out)
+    os.makedirs(out, exist_ok=True)
+    extras(out)

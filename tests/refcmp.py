@@ -25,7 +25,8 @@ def have_ref():
                ("ref_harness", "libgvdb.so", "cuda_gvdb_module.cubin", "cuda_gvdb_copydata.ptx"))
 
 
-def run_ref(preset, outdir, modes=None, size=None, frames=1, warmup=0, nodump=False, shadow=None, hits=True, timeout=1800):
+def run_ref(preset, outdir, modes=None, size=None, frames=1, warmup=0, nodump=False, shadow=None, hits=True, timeout=1800,
+            xform=None, dbuf=False, raytrace=0):
     """Run the reference harness; returns its timing dict."""
     cmd = ["./ref_harness", preset, os.path.abspath(outdir)]
     if modes:
@@ -37,6 +38,12 @@ def run_ref(preset, outdir, modes=None, size=None, frames=1, warmup=0, nodump=Fa
         cmd.append("--nodump")
     if shadow is not None:
         cmd += ["--shadow", str(int(shadow))]
+    if xform is not None:
+        cmd += ["--xform", ",".join(repr(float(v)) for v in xform)]
+    if dbuf:
+        cmd.append("--dbuf")
+    if raytrace:
+        cmd += ["--raytrace", str(int(raytrace))]
     r = subprocess.run(cmd, cwd=REF_DIR, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=timeout)
     if r.returncode != 0:
         raise RuntimeError(f"ref_harness failed ({r.returncode}): {r.stderr[-2000:]}")
@@ -76,6 +83,13 @@ def load_dump(d):
             hp = os.path.join(d, f"hit_{m}.f32")
             if os.path.exists(hp):
                 out["hit"][m] = np.fromfile(hp, dtype=np.float32).reshape(h, w, 8)
+    for name in ("dbuf", "rays_in", "rays_out"):
+        q = os.path.join(d, name + ".bin")
+        if os.path.exists(q):
+            out[name] = np.fromfile(q, dtype=np.float32)
+    q = os.path.join(d, "scninfo_raytrace.bin")
+    if os.path.exists(q):
+        out["scn_raytrace"] = open(q, "rb").read()
     return out
 
 
@@ -87,10 +101,22 @@ def make_renderer(dump, pkg, device=0):
     return r
 
 
+def patch_dbuf(scninfo, ptr):
+    """ScnInfo.dbuf (offset 400) holds a device pointer of the reference process: replace it with ours."""
+    b = bytearray(scninfo)
+    b[400:408] = int(ptr).to_bytes(8, "little")
+    return bytes(b)
+
+
 def render_mine(r, dump, mode, sampler, debug=False):
     import torch
     w, h = dump["meta"]["width"], dump["meta"]["height"]
     r.set_sampler(sampler)
+    if "dbuf" in dump:
+        if "_dbuf_dev" not in dump:
+            dump["_dbuf_dev"] = torch.from_numpy(dump["dbuf"]).cuda()
+        dump = dict(dump)
+        dump["scn"] = {m: patch_dbuf(s, dump["_dbuf_dev"].data_ptr()) for m, s in dump["scn"].items()}
     out = torch.zeros((h, w, 4), dtype=torch.uint8, device="cuda")
     if debug:
         dbg = torch.zeros((h, w, 12), dtype=torch.float32, device="cuda")

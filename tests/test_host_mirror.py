@@ -57,3 +57,20 @@ def test_default_and_rendertofile_transfer_tables(ora, pkg):
     for preset in ("cfg1_tiny", "cfg4_tiny"):
         _, table = ora.scninfo_for(pkg, ora.preset(preset))
         assert sha(table) == str(golden(preset)["transfer_sha"])
+
+
+def test_scninfo_with_set_transform_equals_reference(ora, pkg):
+    """PrepareRender after SetTransform: xform / invxform / invxrot and the light position transformed by mInvXform."""
+    g = np.load(os.path.join(GOLDEN, "ref_extra_xform.npz"))
+    p = ora.preset(str(g["preset"]))
+    xf = [float(v) for v in g["xform"]]
+    v = pkg.Volume(-1)
+    v.SetTransform(xf[0:3], xf[3:6], xf[6:9], xf[9:12])
+    v.SetSceneParams(list(p.steps), list(p.extinct), list(p.thresh), list(p.cutoff), list(p.backclr), list(p.shadow))
+    v.SetCamera(p.fov, list(p.cam_angs), list(p.cam_target), p.cam_dist)
+    v.SetRes(p.width, p.height)
+    v.SetLight(list(p.light_angs), list(p.light_target), p.light_dist)
+    for m, sh in MODES.items():
+        scn = v.PrepareRender(p.width, p.height, sh)
+        assert np.array_equal(mask_scninfo(scn), mask_scninfo(g[f"scn_{m}"].tobytes())), m
+    v.close()
