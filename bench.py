@@ -224,7 +224,7 @@ def main():
     frame = torch.zeros((h, w, 4), dtype=torch.uint8, device=dev)
     bytes_alg = []
     counters = []
-    if rank == 0:
+    if rank == 0:          # counted with the reference's own semantics (no brick culling): units of the ALGORITHM
         r.set_counters(True)
         for scn in scns:
             r.render(scn, shade, frame.data_ptr())

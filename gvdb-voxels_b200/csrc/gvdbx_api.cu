@@ -30,6 +30,8 @@ struct gvdbx_ctx {
     cudaArray_t         own_array = nullptr;
     cudaTextureObject_t tex = 0;
     float*              d_bricks = nullptr;
+    GxRange*            d_range = nullptr;
+    int                 cull = 1;
     int                 ares[3] = {0, 0, 0};
     // transfer function
     float4* d_transfer = nullptr;
@@ -85,7 +87,8 @@ static void gx_free_atlas(gvdbx_t* h)
     if (h->tex) cudaDestroyTextureObject(h->tex);
     if (h->own_array) cudaFreeArray(h->own_array);
     if (h->d_bricks) cudaFree(h->d_bricks);
-    h->tex = 0; h->own_array = nullptr; h->d_bricks = nullptr; h->have_atlas = false;
+    if (h->d_range) cudaFree(h->d_range);
+    h->tex = 0; h->own_array = nullptr; h->d_bricks = nullptr; h->d_range = nullptr; h->have_atlas = false;
 }
 
 extern "C" int gvdbx_destroy(gvdbx_t* h)
@@ -111,6 +114,7 @@ extern "C" int gvdbx_set_option(gvdbx_t* h, int option, int value)
     case GVDBX_OPT_BLOCK_W:  if (value < 1 || value > 32) return gx_fail(h, GVDBX_E_ARG, "block_w"); h->block_w = value; break;
     case GVDBX_OPT_BLOCK_H:  if (value < 1 || value > 32) return gx_fail(h, GVDBX_E_ARG, "block_h"); h->block_h = value; break;
     case GVDBX_OPT_COUNTERS: h->count = value ? 1 : 0; break;
+    case GVDBX_OPT_CULL: h->cull = value ? 1 : 0; break;
     case GVDBX_OPT_TRAVERSAL: if (value < 0 || value > 2) return gx_fail(h, GVDBX_E_ARG, "traversal must be 0, 1 or 2"); h->literal = value; break;
     default: return gx_fail(h, GVDBX_E_ARG, "unknown option");
     }
@@ -219,7 +223,8 @@ static int gx_repack(gvdbx_t* h, const float* d_linear, int rx, int ry, int rz)
     const int cx = rx / GX_BRICK_DIM, cy = ry / GX_BRICK_DIM, cz = rz / GX_BRICK_DIM;
     const size_t slots = size_t(cx) * cy * cz;
     GX_CUDA(h, cudaMalloc(&h->d_bricks, slots * GX_BRICK_STRIDE * sizeof(float)));
-    gx_repack_atlas<<<(unsigned)slots, 256, 0, h->stream>>>(d_linear, rx, ry, rz, cx, cy, h->d_bricks);
+    GX_CUDA(h, cudaMalloc(&h->d_range, slots * sizeof(GxRange)));
+    gx_repack_atlas<<<(unsigned)slots, 256, 0, h->stream>>>(d_linear, rx, ry, rz, cx, cy, h->d_bricks, h->d_range);
     GX_CUDA(h, cudaGetLastError());
     h->ares[0] = rx; h->ares[1] = ry; h->ares[2] = rz;
     return GVDBX_OK;
@@ -362,6 +367,7 @@ static int gx_fill_params(gvdbx_t* h, const void* scninfo, int shade_mode, int c
     P.top_lev = v.top_lev; P.epsilon = v.epsilon; P.bmin = f3(v.bmin); P.bmax = f3(v.bmax);
     P.leaf = h->d_leaf;
     P.tex = h->tex; P.bricks = h->d_bricks;
+    P.range = h->cull ? h->d_range : nullptr;
     P.counters = h->d_counters;
     P.out_stride = s.width;
     P.x0 = 0; P.y0 = 0; P.x1 = s.width; P.y1 = s.height;
@@ -389,6 +395,7 @@ extern "C" int gvdbx_render(gvdbx_t* h, const void* scninfo, int shade_mode, int
     }
     P.out = (uchar4*)outbuf_d;
     const int flags = h->count ? (GX_FLAG_DEBUG | GX_FLAG_COUNT) : (h->literal == 1 ? GX_FLAG_LITERAL : (h->literal == 2 ? GX_FLAG_PACKET : 0));
+    if (flags & (GX_FLAG_COUNT | GX_FLAG_LITERAL)) P.range = nullptr;     // counters / A-B baseline follow the reference's own work
     float4* dbg_tmp = nullptr;
     if (h->count) {     // counted renders reuse the debug variant; give it a scratch debug buffer
         GX_CUDA(h, cudaMalloc(&dbg_tmp, size_t(P.width) * P.height * 48));
@@ -414,6 +421,7 @@ extern "C" int gvdbx_render_debug(gvdbx_t* h, const void* scninfo, int shade_mod
     if (!outbuf_d || !dbg_d) return gx_fail(h, GVDBX_E_ARG, "null output buffer");
     P.out = (uchar4*)outbuf_d;
     P.dbg = (float4*)dbg_d;
+    P.range = nullptr;                                  // debug + counters follow the reference's own work (no brick culling)
     GX_CUDA(h, cudaMemsetAsync(h->d_counters, 0, 8 * sizeof(unsigned long long), h->stream));
     gx_kernel_t k = gx_pick(mode, h->sampler, GX_FLAG_DEBUG | GX_FLAG_COUNT, h->uniform3);
     dim3 block(h->block_w, h->block_h, 1);

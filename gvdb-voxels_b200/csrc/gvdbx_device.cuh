@@ -47,6 +47,12 @@ struct alignas(16) GxLeafRec {     // 32 B, one per level-0 node
     int vx, vy, vz;                // mValue : atlas texel of the first interior voxel
     int pad;
 };
+// Value range of every brick slot over all 10^3 texels (interior + apron), built when the atlas is imported.  Hardware
+// and software trilinear filtering are convex combinations of texels (non-negative 8-bit weights summing to 256), so no
+// sample taken inside the brick can leave [lo, hi]: a brick whose range cannot satisfy the mode's acceptance test is
+// skipped without changing any result.  (The reference keeps an unused mVRange field in every node for this purpose,
+// src/gvdb_node.h:34.)
+struct GxRange { float lo, hi; };
 
 struct GxParams {
     // ---- scene (ScnInfo fields the path reads)
@@ -77,6 +83,7 @@ struct GxParams {
     // ---- atlas
     cudaTextureObject_t tex;             // caller's 3-D array, linear filter, unnormalised, clamp
     const float*        bricks;          // brick-major copy
+    const GxRange*      range;           // per brick slot (index = GxLeafRec::base / GX_BRICK_STRIDE); may be null
     // ---- output
     uchar4*  out;
     float4*  dbg;                        // 3 x 16 B per pixel (debug variant only)
@@ -343,6 +350,7 @@ __device__ __forceinline__ void gx_brick_voxel(const GxParams& P, S& smp, int no
 {
     const GxLeafRec L = P.leaf[nodeid];
     cnt.n_desc++;
+    if (P.range != nullptr && !(P.range[L.base / GX_BRICK_STRIDE].hi > P.thresh.x)) return;  // no voxel above THRESH
     smp.enter(L);
     float3 vmin = make_float3(float(L.px), float(L.py), float(L.pz));
     float3 o = make_float3(float(L.vx), float(L.vy), float(L.vz));
@@ -757,20 +765,31 @@ __global__ void gx_build_leaf_table(const char* __restrict__ nodelist, int nodew
     out[n] = r;
 }
 
-// atlas (x-fastest linear image, as cuMemcpy3D array->linear delivers it) -> brick-major; one CTA per brick slot
+// atlas (x-fastest linear image, as cuMemcpy3D array->linear delivers it) -> brick-major; one CTA per brick slot.
+// Also reduces the slot's value range (NaN-ignoring min / max over the 10^3 texels).
 __global__ void gx_repack_atlas(const float* __restrict__ lin, int rx, int ry, int rz, int cnt_x, int cnt_y,
-                                float* __restrict__ bricks)
+                                float* __restrict__ bricks, GxRange* __restrict__ range)
 {
     const int slot = blockIdx.x;
     const int sx = slot % cnt_x, sy = (slot / cnt_x) % cnt_y, sz = slot / (cnt_x * cnt_y);
+    float lo = INFINITY, hi = -INFINITY;
     for (int i = threadIdx.x; i < GX_BRICK_STRIDE; i += blockDim.x) {
         float v = 0.f;
         if (i < GX_BRICK_DIM * GX_BRICK_DIM * GX_BRICK_DIM) {
             int x = i % GX_BRICK_DIM, y = (i / GX_BRICK_DIM) % GX_BRICK_DIM, z = i / (GX_BRICK_DIM * GX_BRICK_DIM);
             size_t ax = size_t(sx) * GX_BRICK_DIM + x, ay = size_t(sy) * GX_BRICK_DIM + y, az = size_t(sz) * GX_BRICK_DIM + z;
             v = lin[(az * ry + ay) * rx + ax];
+            lo = fminf(lo, v); hi = fmaxf(hi, v);
         }
         bricks[size_t(slot) * GX_BRICK_STRIDE + i] = v;
+    }
+    __shared__ float slo[8], shi[8];
+    for (int o = 16; o > 0; o >>= 1) { lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, o)); hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, o)); }
+    if ((threadIdx.x & 31) == 0) { slo[threadIdx.x >> 5] = lo; shi[threadIdx.x >> 5] = hi; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < (blockDim.x >> 5); w++) { lo = fminf(lo, slo[w]); hi = fmaxf(hi, shi[w]); }
+        range[slot].lo = lo; range[slot].hi = hi;
     }
 }
 

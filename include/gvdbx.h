@@ -50,6 +50,7 @@ extern "C" {
 #define GVDBX_OPT_BLOCK_W   2   /* CTA pixel tile width  (default 8)  */
 #define GVDBX_OPT_BLOCK_H   3   /* CTA pixel tile height (default 8)  */
 #define GVDBX_OPT_COUNTERS  4   /* 1 = accumulate work counters during render (slower; for roofline accounting) */
+#define GVDBX_OPT_CULL      6   /* 1 (default) = skip bricks whose value range cannot satisfy the mode's acceptance test (exact) */
 #define GVDBX_OPT_TRAVERSAL 5   /* 0 = default (four-samples-per-round brick marchers), 1 = reference-shaped loops, one sample at a time (A/B),
                                    2 = vote-converged two-phase packet traversal (A/B) */
 

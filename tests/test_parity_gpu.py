@@ -63,6 +63,12 @@ def test_texture_path_bit_exact_vs_reference(scenes, torch_cuda, preset, mode):
     w, h = int(g["width"]), int(g["height"])
     img, dbg = _render(torch_cuda, r, g[f"scn_{mode}"].tobytes(), MODES[mode], w, h, 0, debug=True)
     assert np.array_equal(img, g[f"rgba_{mode}"]), f"{(img != g[f'rgba_{mode}']).any(axis=2).sum()} pixels differ"
+    # production variant (brick range culling on) and the A/B traversals: same bytes
+    for trav in (0, 1, 2):
+        r.set_option(5, trav)
+        plain = _render(torch_cuda, r, g[f"scn_{mode}"].tobytes(), MODES[mode], w, h, 0)
+        assert np.array_equal(plain, g[f"rgba_{mode}"]), (trav, int((plain != g[f"rgba_{mode}"]).any(axis=2).sum()))
+    r.set_option(5, 0)
     key = f"hit_{mode}"
     if key in g.files:
         ref = g[key]
