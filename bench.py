@@ -273,6 +273,21 @@ def main():
     clk = clocks.stop() if rank == 0 else None
     launches_timed = launches
 
+    # per-rank render-only time of one step (no gather): shows the load balance of the static tile partition
+    rank_render_ms = None
+    if world > 1:
+        sync_all()
+        r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        r0.record()
+        for scn in scns:
+            r.render_tiles(scn, shade, tiled.packed[0].data_ptr(), a.tile, rank, world)
+        r1.record()
+        torch.cuda.synchronize()
+        mine = torch.tensor([r0.elapsed_time(r1)], dtype=torch.float64, device=dev)
+        allms = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allms, mine)
+        rank_render_ms = [round(float(x.item()), 3) for x in allms]
+
     # multi-GPU determinism check: the gathered frame equals a single-GPU render of the same camera
     frame_ok = None
     if world > 1 and rank == 0:
@@ -398,6 +413,7 @@ def main():
         out["cpu_baseline"] = cpu
     if frame_ok is not None:
         out["multi_gpu_frame_matches_single_gpu"] = frame_ok
+        out["rank_render_ms_per_step"] = rank_render_ms
     print(json.dumps(out))
     if world > 1:
         dist.barrier()

@@ -531,23 +531,28 @@ __device__ __forceinline__ void gx_raycast(const GxParams& P, S& smp, float3 pos
 
     tStart.x += P.epsilon;
     st.set(lev, 0, tStart.y - P.epsilon);
+    // the state of the CURRENT level is mirrored in plain registers so that the per-step code has no select chains:
+    float      cur_tmax = tStart.y - P.epsilon;       // exit parameter of the current node
+    const int* ctab = P.child[lev];                   // child table of the current node (node 0 of the top level)
+    unsigned   res = unsigned(gx_res<S>(P, lev));
 
     GxDDA dda;
     dda.set_ray(pos, dir, tStart);
     dda.prepare(vmin, gx_vdel<S>(P, lev));
     const float tDepth = gx_depth_max(P, dir, px, py);
 
-    for (int iter = 0; iter < GX_MAX_ITER && lev > 0 && lev <= P.top_lev && dda.p.x >= 0 && dda.p.y >= 0 && dda.p.z >= 0
-                       && dda.p.x <= gx_res<S>(P, lev) && dda.p.y <= gx_res<S>(P, lev) && dda.p.z <= gx_res<S>(P, lev); iter++) {
+    // loop guard of the reference (cuda_gvdb_raycast.cuh:567): 0 <= p <= res on every axis == unsigned(p) <= res
+    for (int iter = 0; iter < GX_MAX_ITER && lev > 0 && lev <= P.top_lev
+                       && unsigned(dda.p.x) <= res && unsigned(dda.p.y) <= res && unsigned(dda.p.z) <= res; iter++) {
         dda.next();
         if (dda.t.x > tDepth) { h.hit.z = 0; return; }
 
         const int dm = gx_dim<S>(P, lev);
         const int b = (((int(dda.p.z) << dm) + int(dda.p.y)) << dm) + int(dda.p.x);
-        // cells outside [0,res) can only be reached through the reference's inclusive loop bound; they hold no child
+        // cells with a coordinate == res can only be reached through the reference's inclusive loop bound; they hold no
+        // child.  res is a power of two, so "all three coordinates < res" is one compare on their OR.
         int c = -1;
-        if ((dda.p.x | dda.p.y | dda.p.z) >= 0 && dda.p.x < gx_res<S>(P, lev) && dda.p.y < gx_res<S>(P, lev) && dda.p.z < gx_res<S>(P, lev))
-            c = __ldg(&P.child[lev][(size_t(st.node(lev)) << (3 * dm)) + b]);
+        if (unsigned(dda.p.x | dda.p.y | dda.p.z) < res) c = __ldg(ctab + b);
         cnt.n_dda++;
         if (c != -1) {
             if (lev == 1) {
@@ -571,16 +576,23 @@ __device__ __forceinline__ void gx_raycast(const GxParams& P, S& smp, float3 pos
                 cnt.n_desc++;
                 vmin = make_float3(float(np.x), float(np.y), float(np.z));
                 dda.t.x += P.epsilon;
-                st.set(lev, c, dda.t.y - P.epsilon);
+                cur_tmax = dda.t.y - P.epsilon;
+                st.set(lev, c, cur_tmax);
+                ctab = P.child[lev] + (size_t(c) << (3 * gx_dim<S>(P, lev)));
+                res = unsigned(gx_res<S>(P, lev));
                 dda.prepare(vmin, gx_vdel<S>(P, lev));
             }
         } else {
             dda.step();
         }
-        while (dda.t.x > st.tmax(lev) && lev <= P.top_lev) {
+        while (dda.t.x > cur_tmax && lev <= P.top_lev) {
             lev++;
             if (lev <= P.top_lev) {
-                np = __ldg(&P.npos[lev][st.node(lev)]);
+                const int n = st.node(lev);
+                cur_tmax = st.tmax(lev);
+                ctab = P.child[lev] + (size_t(n) << (3 * gx_dim<S>(P, lev)));
+                res = unsigned(gx_res<S>(P, lev));
+                np = __ldg(&P.npos[lev][n]);
                 cnt.n_desc++;
                 vmin = make_float3(float(np.x), float(np.y), float(np.z));
                 dda.prepare(vmin, gx_vdel<S>(P, lev));

@@ -138,20 +138,26 @@ __device__ __forceinline__ void gx2_brick_levelset(const GxParams& P, S& smp, in
 }
 
 // one emission/absorption update for a sample that passed the MINVAL test     cuda_gvdb_raycast.cuh:514-523
+// (the reference multiplies by hclr = 1 last; x * 1 is exact, so only the five separately rounded products remain)
 __device__ __forceinline__ void gx_deep_accumulate(const GxParams& P, float4& clr, float4 val)
 {
     val.w = exp(P.extinct.x * val.w * P.steps.x);
     const float om = 1 - val.w;
-    clr.x = __fadd_rn(clr.x, __fmul_rn(__fmul_rn(__fmul_rn(__fmul_rn(val.x, clr.w), om), P.extinct.y), 1.0f));
-    clr.y = __fadd_rn(clr.y, __fmul_rn(__fmul_rn(__fmul_rn(__fmul_rn(val.y, clr.w), om), P.extinct.y), 1.0f));
-    clr.z = __fadd_rn(clr.z, __fmul_rn(__fmul_rn(__fmul_rn(__fmul_rn(val.z, clr.w), om), P.extinct.y), 1.0f));
+    clr.x = __fadd_rn(clr.x, __fmul_rn(__fmul_rn(__fmul_rn(val.x, clr.w), om), P.extinct.y));
+    clr.y = __fadd_rn(clr.y, __fmul_rn(__fmul_rn(__fmul_rn(val.y, clr.w), om), P.extinct.y));
+    clr.z = __fadd_rn(clr.z, __fmul_rn(__fmul_rn(__fmul_rn(val.z, clr.w), om), P.extinct.y));
     clr.w *= val.w;
 }
-// transfer-function index (cuda_gvdb_dda.cuh:20-23): float divide (= multiply by the approximate reciprocal, which is
-// what div.approx lowers to), then clamp and scale in double, truncate.
+// transfer-function index (cuda_gvdb_dda.cuh:20-23): int(min(1.0, max(0.0, u)) * 16300.0f) with u = (v - THRESH) /
+// (VMAX - VMIN) a float (divide = multiply by the approximate reciprocal) and the clamp / scale / truncation in DOUBLE,
+// i.e. floor of the EXACT product clamp(u) * 16300.  Same integer without the FP64 pipe: round the product in fp32, take
+// its floor f, and step back by one when the exact product (sign of a single fma) lies below f — rounding to nearest can
+// lift the product onto the next integer but never drop it below one.
 __device__ __forceinline__ int gx_transfer_index(float v, float thresh, float inv_range)
 {
-    return int(min(1.0, max(0.0, (v - thresh) * inv_range)) * 16300.0f);
+    const float u = fminf(fmaxf((v - thresh) * inv_range, 0.0f), 1.0f);      // NaN -> 0 like max(0.0, NaN)
+    const float f = floorf(__fmul_rn(u, 16300.0f));
+    return int(f) - (__fmaf_rn(u, 16300.0f, -f) < 0.0f ? 1 : 0);
 }
 
 // SHADE_VOLUME                                                           cuda_gvdb_raycast.cuh:485-533
