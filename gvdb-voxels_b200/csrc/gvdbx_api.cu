@@ -30,7 +30,9 @@ struct gvdbx_ctx {
     cudaArray_t         own_array = nullptr;
     cudaTextureObject_t tex = 0;
     float*              d_bricks = nullptr;
-    GxRange*            d_range = nullptr;
+    GxRange*            d_range = nullptr;      // per brick slot
+    GxRange*            d_leaf_range = nullptr; // per leaf (valid when topology and atlas are both imported)
+    size_t              nslots = 0;
     int                 cull = 1;
     int                 ares[3] = {0, 0, 0};
     // transfer function
@@ -73,6 +75,8 @@ extern "C" int gvdbx_create(gvdbx_t** out, int cuda_device, void* cuda_stream)
 
 static void gx_free_topology(gvdbx_t* h)
 {
+    if (h->d_leaf_range) cudaFree(h->d_leaf_range);
+    h->d_leaf_range = nullptr;
     for (int l = 0; l < GX_MAXLEV; l++) {
         if (h->d_child[l]) cudaFree(h->d_child[l]);
         if (h->d_npos[l]) cudaFree(h->d_npos[l]);
@@ -88,6 +92,8 @@ static void gx_free_atlas(gvdbx_t* h)
     if (h->own_array) cudaFreeArray(h->own_array);
     if (h->d_bricks) cudaFree(h->d_bricks);
     if (h->d_range) cudaFree(h->d_range);
+    if (h->d_leaf_range) cudaFree(h->d_leaf_range);
+    h->d_leaf_range = nullptr;
     h->tex = 0; h->own_array = nullptr; h->d_bricks = nullptr; h->d_range = nullptr; h->have_atlas = false;
 }
 
@@ -122,6 +128,18 @@ extern "C" int gvdbx_set_option(gvdbx_t* h, int option, int value)
         const bool pending = (option == GVDBX_OPT_BLOCK_W);     // width is set first, height second: only judge the pair
         if (!pending) { h->block_w = 8; h->block_h = 8; return gx_fail(h, GVDBX_E_ARG, "CTA tile must be a multiple of 32 and at most 256 threads"); }
     }
+    return GVDBX_OK;
+}
+
+// per-leaf value ranges need both the leaf table (topology) and the slot ranges (atlas): built by whichever comes last
+static int gx_update_leaf_ranges(gvdbx_t* h)
+{
+    if (h->d_leaf_range) { cudaFree(h->d_leaf_range); h->d_leaf_range = nullptr; }
+    if (!h->have_topo || !h->d_range || !h->d_leaf) return GVDBX_OK;
+    const int n = h->vdb.nodecnt[0];
+    GX_CUDA(h, cudaMalloc(&h->d_leaf_range, size_t(n) * sizeof(GxRange)));
+    gx_leaf_ranges<<<(n + 255) / 256, 256, 0, h->stream>>>(h->d_leaf, n, h->d_range, (int)h->nslots, h->d_leaf_range);
+    GX_CUDA(h, cudaGetLastError());
     return GVDBX_OK;
 }
 
@@ -164,7 +182,7 @@ extern "C" int gvdbx_import_topology(gvdbx_t* h, const void* vdbinfo)
     h->have_topo = true;
     h->uniform3 = true;
     for (int l = 0; l <= v.top_lev; l++) if (v.dim[l] != 3 || v.vdel[l].x != float(1 << (3 * l)) || v.vdel[l].y != v.vdel[l].x || v.vdel[l].z != v.vdel[l].x) h->uniform3 = false;
-    return GVDBX_OK;
+    return gx_update_leaf_ranges(h);
 }
 
 extern "C" int gvdbx_import_topology_host(gvdbx_t* h, const void* vdbinfo, const void* const* pool0, const void* const* pool1,
@@ -227,7 +245,8 @@ static int gx_repack(gvdbx_t* h, const float* d_linear, int rx, int ry, int rz)
     gx_repack_atlas<<<(unsigned)slots, 256, 0, h->stream>>>(d_linear, rx, ry, rz, cx, cy, h->d_bricks, h->d_range);
     GX_CUDA(h, cudaGetLastError());
     h->ares[0] = rx; h->ares[1] = ry; h->ares[2] = rz;
-    return GVDBX_OK;
+    h->nslots = slots;
+    return gx_update_leaf_ranges(h);
 }
 
 extern "C" int gvdbx_import_atlas_array(gvdbx_t* h, int chan, void* cuarray, int rx, int ry, int rz)
@@ -367,7 +386,7 @@ static int gx_fill_params(gvdbx_t* h, const void* scninfo, int shade_mode, int c
     P.top_lev = v.top_lev; P.epsilon = v.epsilon; P.bmin = f3(v.bmin); P.bmax = f3(v.bmax);
     P.leaf = h->d_leaf;
     P.tex = h->tex; P.bricks = h->d_bricks;
-    P.range = h->cull ? h->d_range : nullptr;
+    P.range = h->cull ? h->d_leaf_range : nullptr;
     P.counters = h->d_counters;
     P.out_stride = s.width;
     P.x0 = 0; P.y0 = 0; P.x1 = s.width; P.y1 = s.height;

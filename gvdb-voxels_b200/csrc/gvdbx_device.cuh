@@ -83,7 +83,7 @@ struct GxParams {
     // ---- atlas
     cudaTextureObject_t tex;             // caller's 3-D array, linear filter, unnormalised, clamp
     const float*        bricks;          // brick-major copy
-    const GxRange*      range;           // per brick slot (index = GxLeafRec::base / GX_BRICK_STRIDE); may be null
+    const GxRange*      range;           // value range per LEAF (same index as `leaf`); null = no culling
     // ---- output
     uchar4*  out;
     float4*  dbg;                        // 3 x 16 B per pixel (debug variant only)
@@ -350,7 +350,7 @@ __device__ __forceinline__ void gx_brick_voxel(const GxParams& P, S& smp, int no
 {
     const GxLeafRec L = P.leaf[nodeid];
     cnt.n_desc++;
-    if (P.range != nullptr && !(P.range[L.base / GX_BRICK_STRIDE].hi > P.thresh.x)) return;  // no voxel above THRESH
+    if (P.range != nullptr && !(__ldg(&P.range[nodeid].hi) > P.thresh.x)) return;             // no voxel above THRESH
     smp.enter(L);
     float3 vmin = make_float3(float(L.px), float(L.py), float(L.pz));
     float3 o = make_float3(float(L.vx), float(L.vy), float(L.vz));
@@ -360,8 +360,8 @@ __device__ __forceinline__ void gx_brick_voxel(const GxParams& P, S& smp, int no
     dda.set_ray(pos, dir, t);
     dda.prepare_leaf(vmin);
 
-    for (int iter = 0; iter < GX_MAX_ITER && dda.p.x >= 0 && dda.p.y >= 0 && dda.p.z >= 0
-                       && dda.p.x < res0 && dda.p.y < res0 && dda.p.z < res0; iter++) {
+    // 0 <= p < res0 on every axis (res0 is a power of two) == one unsigned compare on the OR of the coordinates
+    for (int iter = 0; iter < GX_MAX_ITER && unsigned(dda.p.x | dda.p.y | dda.p.z) < unsigned(res0); iter++) {
         cnt.s_pt++;
         if (smp.point(dda.p.x + o.x + .5, dda.p.y + o.y + .5, dda.p.z + o.z + .5) > P.thresh.x) {
             vmin += gx_f3(dda.p);
@@ -803,6 +803,19 @@ __global__ void gx_repack_atlas(const float* __restrict__ lin, int rx, int ry, i
         for (int w = 1; w < (blockDim.x >> 5); w++) { lo = fminf(lo, slo[w]); hi = fmaxf(hi, shi[w]); }
         range[slot].lo = lo; range[slot].hi = hi;
     }
+}
+
+// value range per leaf = range of the brick slot the leaf's mValue points at (run when both topology and atlas are in)
+__global__ void gx_leaf_ranges(const GxLeafRec* __restrict__ leaf, int nleaf, const GxRange* __restrict__ slot_range,
+                               int nslots, GxRange* __restrict__ out)
+{
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= nleaf) return;
+    const int slot = leaf[n].base / GX_BRICK_STRIDE;
+    GxRange r;
+    r.lo = -INFINITY; r.hi = INFINITY;                     // unknown slot: never culled
+    if (leaf[n].vx >= 0 && slot >= 0 && slot < nslots) r = slot_range[slot];
+    out[n] = r;
 }
 
 // scatter gathered tile buffers [nranks][slots][ts*ts] back into a row-major frame

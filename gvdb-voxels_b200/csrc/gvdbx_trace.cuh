@@ -53,7 +53,7 @@ __device__ __forceinline__ void gx2_brick_trilinear(const GxParams& P, S& smp, i
     const GxLeafRec L = P.leaf[nodeid];
     cnt.n_desc++;
     const float st = P.steps.x, thr = P.thresh.x;
-    if (P.range != nullptr && !(P.range[L.base / GX_BRICK_STRIDE].hi >= thr)) return;     // no sample can reach THRESH
+    if (P.range != nullptr && !(__ldg(&P.range[nodeid].hi) >= thr)) return;                // no sample can reach THRESH
     smp.enter(L);
     const float3 vmin = make_float3(float(L.px), float(L.py), float(L.pz));
     const float3 o = make_float3(float(L.vx), float(L.vy), float(L.vz));
@@ -100,7 +100,7 @@ __device__ __forceinline__ void gx2_brick_levelset(const GxParams& P, S& smp, in
     const GxLeafRec L = P.leaf[nodeid];
     cnt.n_desc++;
     const float st = P.steps.x, thr = P.thresh.x;
-    if (P.range != nullptr && !(P.range[L.base / GX_BRICK_STRIDE].lo < thr)) return;      // no sample can fall below THRESH
+    if (P.range != nullptr && !(__ldg(&P.range[nodeid].lo) < thr)) return;                 // no sample can fall below THRESH
     smp.enter(L);
     const float3 vmin = make_float3(float(L.px), float(L.py), float(L.pz));
     const float3 o = make_float3(float(L.vx), float(L.vy), float(L.vz));
@@ -169,7 +169,7 @@ __device__ __forceinline__ void gx2_brick_deep(const GxParams& P, S& smp, int no
     cnt.n_desc++;
     // every sample below MINVAL is skipped by the reference: such a brick only refreshes hit.x / hit.y (not part of the
     // image) and re-applies an idempotent clamp.  Not taken when a depth buffer is bound (hit.z bookkeeping).
-    if (P.range != nullptr && P.dbuf == nullptr && !(P.range[L.base / GX_BRICK_STRIDE].hi >= P.cutoff.x)) return;
+    if (P.range != nullptr && P.dbuf == nullptr && !(__ldg(&P.range[nodeid].hi) >= P.cutoff.x)) return;
     smp.enter(L);
     const float3 vmin = make_float3(float(L.px), float(L.py), float(L.pz));
     const float st = P.steps.x;
