@@ -635,7 +635,7 @@ __device__ __forceinline__ float4 gx2_trace_pixel(const GxParams& P, S& smp, flo
                                                   GxCount& cnt, GxHit& prim, float4& raw, bool valid);
 
 template <int MODE, int SAMPLER, int FLAGS, bool UNI>
-__global__ void __launch_bounds__(256) gx_render_kernel(const __grid_constant__ GxParams P)
+__global__ void __launch_bounds__(256, 4) gx_render_kernel(const __grid_constant__ GxParams P)
 {
     int x, y;
     size_t opix;
