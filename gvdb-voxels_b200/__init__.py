@@ -11,6 +11,8 @@ shared library or a CUDA device is missing.
 from .api import (  # noqa: F401
     GvdbxError, Renderer, Volume, lib, lib_path, HOST_SYMBOLS,
     SHADE_VOXEL, SHADE_TRILINEAR, SHADE_LEVELSET, SHADE_VOLUME, SHADE_OFF,
+    SHADE_SECTION2D, SHADE_SECTION3D, SHADE_EMPTYSKIP, SHADE_TRICUBIC,
+    OPT_SAMPLER, OPT_BLOCK_W, OPT_BLOCK_H, OPT_COUNTERS, OPT_TRAVERSAL, OPT_CULL, OPT_SPP, OPT_DEEP_SHADOW,
     SAMPLER_TEX, SAMPLER_LINEAR, VDBINFO_BYTES, SCNINFO_BYTES,
     EXPORTED_SYMBOLS,
 )

@@ -13,8 +13,9 @@ import os
 import numpy as np
 
 SHADE_VOXEL, SHADE_TRILINEAR, SHADE_LEVELSET, SHADE_VOLUME, SHADE_OFF = 0, 4, 6, 7, 100
+SHADE_SECTION2D, SHADE_SECTION3D, SHADE_EMPTYSKIP, SHADE_TRICUBIC = 1, 2, 3, 5
 SAMPLER_TEX, SAMPLER_LINEAR = 0, 1
-OPT_SAMPLER, OPT_BLOCK_W, OPT_BLOCK_H, OPT_COUNTERS, OPT_TRAVERSAL = 1, 2, 3, 4, 5
+OPT_SAMPLER, OPT_BLOCK_W, OPT_BLOCK_H, OPT_COUNTERS, OPT_TRAVERSAL, OPT_CULL, OPT_SPP, OPT_DEEP_SHADOW = 1, 2, 3, 4, 5, 6, 7, 8
 VDBINFO_BYTES, SCNINFO_BYTES = 1232, 416
 
 EXPORTED_SYMBOLS = [
@@ -130,6 +131,14 @@ class Renderer:
         self.set_option(OPT_BLOCK_W, w)
         self.set_option(OPT_BLOCK_H, h)
 
+    def set_spp(self, n):
+        """rays per pixel (1 = the reference's pixel-centre ray)"""
+        self.set_option(OPT_SPP, n)
+
+    def set_deep_shadow(self, on):
+        """SHADE_VOLUME + one shadow march towards the light (BASELINE.json config 4)"""
+        self.set_option(OPT_DEEP_SHADOW, 1 if on else 0)
+
     def set_counters(self, on):
         self.set_option(OPT_COUNTERS, 1 if on else 0)
 
@@ -227,7 +236,7 @@ class Renderer:
 # ------------------------------------------------------------------------------------------------ host mirror
 HOST_SYMBOLS = [
     "gvdbxh_create", "gvdbxh_destroy", "gvdbxh_set_transform", "gvdbxh_camera", "gvdbxh_camera_nearfar", "gvdbxh_light",
-    "gvdbxh_scene_params", "gvdbxh_linear_transfer", "gvdbxh_transfer_table", "gvdbxh_set_res", "gvdbxh_prepare_render",
+    "gvdbxh_scene_params", "gvdbxh_cross_section", "gvdbxh_linear_transfer", "gvdbxh_transfer_table", "gvdbxh_set_res", "gvdbxh_prepare_render",
     "gvdbxh_import_topology_host", "gvdbxh_import_atlas_host", "gvdbxh_commit_transfer", "gvdbxh_add_render_buf",
     "gvdbxh_render", "gvdbxh_read_render_buf", "gvdbxh_set_option", "gvdbxh_last_error",
 ]
@@ -286,6 +295,10 @@ class Volume:
 
     def SetSceneParams(self, steps, extinct, thresh, cutoff, backclr, shadow):
         self._L.gvdbxh_scene_params(self._h, _f(steps), _f(extinct), _f(thresh), _f(cutoff), _f(backclr), _f(shadow))
+
+    def SetCrossSection(self, pnt, norm):
+        """Scene::SetCrossSection (gvdb_scene.h:147): plane of SHADE_SECTION3D / origin + per-axis extent of SHADE_SECTION2D"""
+        self._L.gvdbxh_cross_section(self._h, _f(pnt), _f(norm))
 
     def LinearTransferFunc(self, t0, t1, a, b):
         self._L.gvdbxh_linear_transfer(self._h, C.c_float(t0), C.c_float(t1), _f(a), _f(b))

@@ -4,8 +4,7 @@
 // (src/gvdb_volume_gvdb.cpp:3946-3989, 4254-4306, 4336-4381, 4241-4251).  CUDA runtime API only; works under the
 // caller's current context; everything is stream-ordered on the stream given to gvdbx_create.
 #include "../../include/gvdbx.h"
-#include "gvdbx_device.cuh"
-#include "gvdbx_trace.cuh"
+#include "gvdbx_import.cuh"
 
 #include <cstdio>
 #include <cstdlib>
@@ -18,7 +17,7 @@ struct gvdbx_ctx {
     cudaStream_t stream = nullptr;
     std::string  err;
     // options
-    int sampler = GX_SAMPLER_TEX, block_w = 8, block_h = 8, count = 0, literal = 0;
+    int sampler = GX_SAMPLER_TEX, block_w = 8, block_h = 8, count = 0, literal = 0, spp = 1, deep_shadow = 0;
     // topology
     bool       have_topo = false, uniform3 = false;
     GxVDBInfo  vdb;
@@ -121,6 +120,8 @@ extern "C" int gvdbx_set_option(gvdbx_t* h, int option, int value)
     case GVDBX_OPT_BLOCK_H:  if (value < 1 || value > 32) return gx_fail(h, GVDBX_E_ARG, "block_h"); h->block_h = value; break;
     case GVDBX_OPT_COUNTERS: h->count = value ? 1 : 0; break;
     case GVDBX_OPT_CULL: h->cull = value ? 1 : 0; break;
+    case GVDBX_OPT_SPP: if (value < 1 || value > 64) return gx_fail(h, GVDBX_E_ARG, "spp must be 1..64"); h->spp = value; break;
+    case GVDBX_OPT_DEEP_SHADOW: h->deep_shadow = value ? 1 : 0; break;
     case GVDBX_OPT_TRAVERSAL: if (value < 0 || value > 2) return gx_fail(h, GVDBX_E_ARG, "traversal must be 0, 1 or 2"); h->literal = value; break;
     default: return gx_fail(h, GVDBX_E_ARG, "unknown option");
     }
@@ -317,32 +318,29 @@ extern "C" int gvdbx_set_transfer(gvdbx_t* h, const float* rgba_host)
 
 // ------------------------------------------------------------------------------------------------ render
 typedef void (*gx_kernel_t)(const GxParams);
+// one translation unit per shade mode (gvdbx_k_*.cu, gvdbx_pick.cuh)
+gx_kernel_t gx_pick_voxel(int sampler, int flags, bool uni);
+gx_kernel_t gx_pick_trilinear(int sampler, int flags, bool uni);
+gx_kernel_t gx_pick_levelset(int sampler, int flags, bool uni);
+gx_kernel_t gx_pick_deep(int sampler, int flags, bool uni);
+gx_kernel_t gx_pick_deepshadow(int sampler, int flags, bool uni);
+gx_kernel_t gx_pick_tricubic(int sampler, int flags, bool uni);
+gx_kernel_t gx_pick_emptyskip(int sampler, int flags, bool uni);
+gx_kernel_t gx_pick_section2d(int sampler, int flags, bool uni);
+gx_kernel_t gx_pick_section3d(int sampler, int flags, bool uni);
 
-template <int MODE, int SAMPLER, bool UNI>
-static gx_kernel_t gx_pick_flags(int flags)
-{
-    switch (flags) {
-    case 0: return gx_render_kernel<MODE, SAMPLER, 0, UNI>;
-    case GX_FLAG_DEBUG | GX_FLAG_COUNT: return gx_render_kernel<MODE, SAMPLER, GX_FLAG_DEBUG | GX_FLAG_COUNT, UNI>;
-    case GX_FLAG_TILES: return gx_render_kernel<MODE, SAMPLER, GX_FLAG_TILES, UNI>;
-    case GX_FLAG_LITERAL: return gx_render_kernel<MODE, SAMPLER, GX_FLAG_LITERAL, false>;      // A/B variants: generic tree only
-    case GX_FLAG_PACKET: return gx_render_kernel<MODE, SAMPLER, GX_FLAG_PACKET, false>;
-    }
-    return nullptr;
-}
-template <int MODE>
-static gx_kernel_t gx_pick_sampler(int sampler, int flags, bool uni)
-{
-    if (sampler == GX_SAMPLER_TEX) return uni ? gx_pick_flags<MODE, GX_SAMPLER_TEX, true>(flags) : gx_pick_flags<MODE, GX_SAMPLER_TEX, false>(flags);
-    return uni ? gx_pick_flags<MODE, GX_SAMPLER_LINEAR, true>(flags) : gx_pick_flags<MODE, GX_SAMPLER_LINEAR, false>(flags);
-}
 static gx_kernel_t gx_pick(int mode, int sampler, int flags, bool uni)
 {
     switch (mode) {
-    case GX_MODE_VOXEL:     return gx_pick_sampler<GX_MODE_VOXEL>(sampler, flags, uni);
-    case GX_MODE_TRILINEAR: return gx_pick_sampler<GX_MODE_TRILINEAR>(sampler, flags, uni);
-    case GX_MODE_LEVELSET:  return gx_pick_sampler<GX_MODE_LEVELSET>(sampler, flags, uni);
-    case GX_MODE_DEEP:      return gx_pick_sampler<GX_MODE_DEEP>(sampler, flags, uni);
+    case GX_MODE_VOXEL:      return gx_pick_voxel(sampler, flags, uni);
+    case GX_MODE_TRILINEAR:  return gx_pick_trilinear(sampler, flags, uni);
+    case GX_MODE_LEVELSET:   return gx_pick_levelset(sampler, flags, uni);
+    case GX_MODE_DEEP:       return gx_pick_deep(sampler, flags, uni);
+    case GX_MODE_DEEPSHADOW: return gx_pick_deepshadow(sampler, flags, uni);
+    case GX_MODE_TRICUBIC:   return gx_pick_tricubic(sampler, flags, uni);
+    case GX_MODE_EMPTYSKIP:  return gx_pick_emptyskip(sampler, flags, uni);
+    case GX_MODE_SECTION2D:  return gx_pick_section2d(sampler, flags, uni);
+    case GX_MODE_SECTION3D:  return gx_pick_section3d(sampler, flags, uni);
     }
     return nullptr;
 }
@@ -359,9 +357,15 @@ static int gx_fill_params(gvdbx_t* h, const void* scninfo, int shade_mode, int c
     case GVDBX_SHADE_VOXEL:     mode = GX_MODE_VOXEL; break;
     case GVDBX_SHADE_TRILINEAR: mode = GX_MODE_TRILINEAR; break;
     case GVDBX_SHADE_LEVELSET:  mode = GX_MODE_LEVELSET; break;
-    case GVDBX_SHADE_VOLUME:    mode = GX_MODE_DEEP; break;
-    default: return gx_fail(h, GVDBX_E_UNSUPPORTED, "shade mode outside the hot path (supported: VOXEL 0, TRILINEAR 4, LEVELSET 6, VOLUME 7)");
+    case GVDBX_SHADE_VOLUME:    mode = h->deep_shadow ? GX_MODE_DEEPSHADOW : GX_MODE_DEEP; break;
+    case GVDBX_SHADE_TRICUBIC:  mode = GX_MODE_TRICUBIC; break;
+    case GVDBX_SHADE_EMPTYSKIP: mode = GX_MODE_EMPTYSKIP; break;
+    case GVDBX_SHADE_SECTION2D: mode = GX_MODE_SECTION2D; break;
+    case GVDBX_SHADE_SECTION3D: mode = GX_MODE_SECTION3D; break;
+    default: return gx_fail(h, GVDBX_E_UNSUPPORTED, "unknown shade mode (the reference's Render switch handles 0..7, gvdb_volume_gvdb.cpp:4363-4372)");
     }
+    if (h->sampler != GX_SAMPLER_TEX && (mode == GX_MODE_TRICUBIC || mode == GX_MODE_EMPTYSKIP || mode == GX_MODE_SECTION2D || mode == GX_MODE_SECTION3D))
+        return gx_fail(h, GVDBX_E_UNSUPPORTED, "this shade mode needs the texture sampler (tricubic taps reach beyond the brick apron)");
     GxScnInfo s;
     memcpy(&s, scninfo, sizeof s);
     if (s.width <= 0 || s.height <= 0) return gx_fail(h, GVDBX_E_ARG, "ScnInfo width/height");
@@ -369,18 +373,20 @@ static int gx_fill_params(gvdbx_t* h, const void* scninfo, int shade_mode, int c
     P.width = s.width; P.height = s.height; P.camnear = s.camnear; P.camfar = s.camfar;
     P.campos = f3(s.campos); P.cams = f3(s.cams); P.camu = f3(s.camu); P.camv = f3(s.camv);
     P.light_pos = f3(s.light_pos); P.shadow_params = f3(s.shadow_params);
+    P.slice_pnt = f3(s.slice_pnt); P.slice_norm = f3(s.slice_norm);
     P.backclr = make_float4(s.backclr.x, s.backclr.y, s.backclr.z, s.backclr.w);
     memcpy(P.xform, s.xform, sizeof P.xform);
     memcpy(P.invxform, s.invxform, sizeof P.invxform);
     memcpy(P.invxrot, s.invxrot, sizeof P.invxrot);
     P.extinct = f3(s.extinct); P.steps = f3(s.steps); P.cutoff = f3(s.cutoff); P.thresh = f3(s.thresh);
     P.transfer = h->d_transfer ? h->d_transfer : (const float4*)s.transfer;
-    if (mode == GX_MODE_DEEP && !P.transfer)
+    if ((mode == GX_MODE_DEEP || mode == GX_MODE_DEEPSHADOW || mode == GX_MODE_SECTION2D || mode == GX_MODE_SECTION3D) && !P.transfer)
         return gx_fail(h, GVDBX_E_STATE, "transfer function not on GPU (reference: 'Must call CommitTransferFunc')");
     P.dbuf = (const float*)s.dbuf;
     const GxVDBInfo& v = h->vdb;
     for (int l = 0; l < GX_MAXLEV; l++) {
         P.dim[l] = v.dim[l]; P.res[l] = v.res[l]; P.vdel[l] = f3(v.vdel[l]);
+        P.noderange[l] = make_int3(v.noderange[l].x, v.noderange[l].y, v.noderange[l].z);
         P.child[l] = h->d_child[l]; P.npos[l] = h->d_npos[l];
     }
     P.top_lev = v.top_lev; P.epsilon = v.epsilon; P.bmin = f3(v.bmin); P.bmax = f3(v.bmax);
@@ -390,6 +396,10 @@ static int gx_fill_params(gvdbx_t* h, const void* scninfo, int shade_mode, int c
     P.counters = h->d_counters;
     P.out_stride = s.width;
     P.x0 = 0; P.y0 = 0; P.x1 = s.width; P.y1 = s.height;
+    // sub-pixel pattern: g x g grid with g = ceil(sqrt(spp)); sample s at ((s % g) + .5) / g, ((s / g) + .5) / g
+    int g = 1;
+    while (g * g < h->spp) g++;
+    P.spp = h->spp; P.spp_grid = g; P.spp_inv_grid = 1.0f / float(g); P.spp_inv = 1.0f / float(h->spp);
     return GVDBX_OK;
 }
 
@@ -413,7 +423,10 @@ extern "C" int gvdbx_render(gvdbx_t* h, const void* scninfo, int shade_mode, int
         P.x0 = tx0; P.y0 = ty0; P.x1 = tx0 + tw; P.y1 = ty0 + th;
     }
     P.out = (uchar4*)outbuf_d;
-    const int flags = h->count ? (GX_FLAG_DEBUG | GX_FLAG_COUNT) : (h->literal == 1 ? GX_FLAG_LITERAL : (h->literal == 2 ? GX_FLAG_PACKET : 0));
+    const bool core = (mode <= GX_MODE_DEEP);          // the A/B traversal variants exist for the four core modes only
+    const int flags = h->count ? (GX_FLAG_DEBUG | GX_FLAG_COUNT)
+                    : (h->spp > 1 ? GX_FLAG_SPP
+                    : (core && h->literal == 1 ? GX_FLAG_LITERAL : (core && h->literal == 2 ? GX_FLAG_PACKET : 0)));
     if (flags & (GX_FLAG_COUNT | GX_FLAG_LITERAL)) P.range = nullptr;     // counters / A-B baseline follow the reference's own work
     float4* dbg_tmp = nullptr;
     if (h->count) {     // counted renders reuse the debug variant; give it a scratch debug buffer
@@ -422,6 +435,7 @@ extern "C" int gvdbx_render(gvdbx_t* h, const void* scninfo, int shade_mode, int
         GX_CUDA(h, cudaMemsetAsync(h->d_counters, 0, 8 * sizeof(unsigned long long), h->stream));
     }
     gx_kernel_t k = gx_pick(mode, h->sampler, flags, h->uniform3);
+    if (!k) return gx_fail(h, GVDBX_E_UNSUPPORTED, "no kernel variant for this mode / sampler / option combination");
     dim3 block(h->block_w, h->block_h, 1);
     dim3 grid((P.x1 - P.x0 + block.x - 1) / block.x, (P.y1 - P.y0 + block.y - 1) / block.y, 1);
     k<<<grid, block, 0, h->stream>>>(P);
@@ -443,6 +457,7 @@ extern "C" int gvdbx_render_debug(gvdbx_t* h, const void* scninfo, int shade_mod
     P.range = nullptr;                                  // debug + counters follow the reference's own work (no brick culling)
     GX_CUDA(h, cudaMemsetAsync(h->d_counters, 0, 8 * sizeof(unsigned long long), h->stream));
     gx_kernel_t k = gx_pick(mode, h->sampler, GX_FLAG_DEBUG | GX_FLAG_COUNT, h->uniform3);
+    if (!k) return gx_fail(h, GVDBX_E_UNSUPPORTED, "no kernel variant for this mode / sampler combination");
     dim3 block(h->block_w, h->block_h, 1);
     dim3 grid((P.width + block.x - 1) / block.x, (P.height + block.y - 1) / block.y, 1);
     k<<<grid, block, 0, h->stream>>>(P);
@@ -469,12 +484,14 @@ extern "C" int gvdbx_render_tiles(gvdbx_t* h, const void* scninfo, int shade_mod
     if (tile_size <= 0 || tile_size % h->block_w || tile_size % h->block_h)
         return gx_fail(h, GVDBX_E_ARG, "tile_size must be a multiple of the CTA tile");
     P.out = (uchar4*)packed_d;
+    P.out_stride = 0;                                   // packed tile slots
     P.tile_size = tile_size;
     P.tiles_x = (P.width + tile_size - 1) / tile_size;
     P.ntiles = P.tiles_x * ((P.height + tile_size - 1) / tile_size);
     P.rank = rank; P.nranks = nranks;
     const int slots = (P.ntiles + nranks - 1) / nranks;
-    gx_kernel_t k = gx_pick(mode, h->sampler, GX_FLAG_TILES, h->uniform3);
+    gx_kernel_t k = gx_pick(mode, h->sampler, GX_FLAG_TILES | (h->spp > 1 ? GX_FLAG_SPP : 0), h->uniform3);
+    if (!k) return gx_fail(h, GVDBX_E_UNSUPPORTED, "no kernel variant for this mode / sampler combination");
     dim3 block(h->block_w, h->block_h, 1);
     dim3 grid((tile_size / h->block_w) * (tile_size / h->block_h), slots, 1);
     k<<<grid, block, 0, h->stream>>>(P);

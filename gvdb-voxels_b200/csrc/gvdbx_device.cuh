@@ -33,6 +33,12 @@
 #define GX_MODE_TRILINEAR 1
 #define GX_MODE_LEVELSET  2
 #define GX_MODE_DEEP      3
+#define GX_MODE_TRICUBIC  4      // SHADE_TRICUBIC  (brick function + pixel mode)
+#define GX_MODE_EMPTYSKIP 5      // SHADE_EMPTYSKIP (brick function + pixel mode)
+#define GX_MODE_SHADOW    6      // rayShadowBrick: brick function only (secondary ray of GX_MODE_DEEPSHADOW)
+#define GX_MODE_SECTION2D 7      // SHADE_SECTION2D (pixel mode, no ray cast)
+#define GX_MODE_SECTION3D 8      // SHADE_SECTION3D (pixel mode: section plane + trilinear surface)
+#define GX_MODE_DEEPSHADOW 9     // deep march + shadow march towards the light (BASELINE.json config 4)
 
 #define GX_SAMPLER_TEX    0
 #define GX_SAMPLER_LINEAR 1
@@ -60,6 +66,7 @@ struct GxParams {
     float    camnear, camfar;
     float3   campos, cams, camu, camv;
     float3   light_pos;
+    float3   slice_pnt, slice_norm; // SCN_SLICE_PNT / SCN_SLICE_NORM (section modes)
     float3   shadow_params;        // x = SHADOWAMT, y = SHADOWBIAS
     float4   backclr;
     float    xform[16], invxform[16], invxrot[16];
@@ -73,6 +80,7 @@ struct GxParams {
     int      dim[GX_MAXLEV];
     int      res[GX_MAXLEV];
     float3   vdel[GX_MAXLEV];
+    int3     noderange[GX_MAXLEV];
     int      top_lev;
     float    epsilon;
     float3   bmin, bmax;
@@ -90,6 +98,9 @@ struct GxParams {
     unsigned long long* counters;        // 6 x u64 (count variant only)
     int      out_stride;                 // pixels per output row
     int      x0, y0, x1, y1;             // pixel rectangle [x0,x1) x [y0,y1)
+    // ---- sub-pixel sampling (GX_FLAG_SPP): spp rays per pixel on a spp_grid x spp_grid pattern, averaged before packing
+    int      spp, spp_grid;
+    float    spp_inv_grid, spp_inv;
     // ---- tile-list mode (multi-GPU): tiles with id % nranks == rank, packed tile after tile
     int      tile_size, tiles_x, ntiles, rank, nranks;
 };
@@ -106,6 +117,7 @@ __device__ __forceinline__ float3 operator-(float3 a, float b)  { return make_fl
 __device__ __forceinline__ float3 operator*(float3 a, float b)  { return make_float3(a.x * b, a.y * b, a.z * b); }
 __device__ __forceinline__ float3 operator*(float b, float3 a)  { return make_float3(b * a.x, b * a.y, b * a.z); }
 __device__ __forceinline__ float3 operator/(float b, float3 a)  { return make_float3(b / a.x, b / a.y, b / a.z); }
+__device__ __forceinline__ float3 operator-(float b, float3 a)  { return make_float3(b - a.x, b - a.y, b - a.z); }
 __device__ __forceinline__ void   operator+=(float3& a, float3 b) { a.x += b.x; a.y += b.y; a.z += b.z; }
 __device__ __forceinline__ void   operator-=(float3& a, float3 b) { a.x -= b.x; a.y -= b.y; a.z -= b.z; }
 __device__ __forceinline__ float  gx_dot(float3 a, float3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
@@ -514,6 +526,10 @@ template <class S> __device__ __forceinline__ void gx2_brick_trilinear(const GxP
 template <class S> __device__ __forceinline__ void gx2_brick_levelset(const GxParams&, S&, int, float3, float3, float3, GxHit&, GxCount&);
 template <class S> __device__ __forceinline__ void gx2_brick_deep(const GxParams&, S&, int, float3, float3, float3, GxHit&, GxCount&, float);
 
+// brick functions of the remaining shade modes (gvdbx_extra.cuh)
+template <class S> __device__ __forceinline__ void gx_brick_tricubic(const GxParams&, S&, int, float3, float3, float3, GxHit&, GxCount&);
+template <class S> __device__ __forceinline__ void gx_brick_shadow(const GxParams&, S&, int, float3, float3, float3, GxHit&, GxCount&);
+
 template <int MODE, bool BATCH, class S>
 __device__ __forceinline__ void gx_raycast(const GxParams& P, S& smp, float3 pos, float3 dir, GxHit& h, GxCount& cnt,
                                            int px, int py)
@@ -557,13 +573,16 @@ __device__ __forceinline__ void gx_raycast(const GxParams& P, S& smp, float3 pos
         if (c != -1) {
             if (lev == 1) {
                 dda.t.x += P.epsilon;
-                if (MODE == GX_MODE_VOXEL)          gx_brick_voxel(P, smp, c, dda.t, pos, dir, h, cnt);
-                else if (MODE == GX_MODE_TRILINEAR) { if (BATCH) gx2_brick_trilinear(P, smp, c, dda.t, pos, dir, h, cnt);
+                if constexpr (MODE == GX_MODE_VOXEL)          gx_brick_voxel(P, smp, c, dda.t, pos, dir, h, cnt);
+                else if constexpr (MODE == GX_MODE_TRILINEAR) { if (BATCH) gx2_brick_trilinear(P, smp, c, dda.t, pos, dir, h, cnt);
                                                       else       gx_brick_trilinear(P, smp, c, dda.t, pos, dir, h, cnt); }
-                else if (MODE == GX_MODE_LEVELSET)  { if (BATCH) gx2_brick_levelset(P, smp, c, dda.t, pos, dir, h, cnt);
+                else if constexpr (MODE == GX_MODE_LEVELSET)  { if (BATCH) gx2_brick_levelset(P, smp, c, dda.t, pos, dir, h, cnt);
                                                       else       gx_brick_levelset(P, smp, c, dda.t, pos, dir, h, cnt); }
-                else                                { if (BATCH) gx2_brick_deep(P, smp, c, dda.t, pos, dir, h, cnt, tDepth);
+                else if constexpr (MODE == GX_MODE_DEEP)      { if (BATCH) gx2_brick_deep(P, smp, c, dda.t, pos, dir, h, cnt, tDepth);
                                                       else       gx_brick_deep(P, smp, c, dda.t, pos, dir, h, cnt, tDepth); }
+                else if constexpr (MODE == GX_MODE_TRICUBIC)  gx_brick_tricubic(P, smp, c, dda.t, pos, dir, h, cnt);
+                else if constexpr (MODE == GX_MODE_EMPTYSKIP) h.hit = pos + dda.t.x * dir;       // rayEmptySkipBrick, cuda_gvdb_raycast.cuh:425-428
+                else                                gx_brick_shadow(P, smp, c, dda.t, pos, dir, h, cnt);
                 if (h.clr.w <= 0) { h.clr.w = 0; return; }
                 if (h.hit.z != GX_NOHIT) return;
                 // deep mode: once transmittance is at or below ALPHACUT no later brick can change the colour
@@ -634,6 +653,57 @@ template <int MODE, class S>
 __device__ __forceinline__ float4 gx2_trace_pixel(const GxParams& P, S& smp, float3 rpos, float3 rdir, int px, int py,
                                                   GxCount& cnt, GxHit& prim, float4& raw, bool valid);
 
+// section / deep-shadow pixel functions (gvdbx_extra.cuh)
+template <class S> __device__ __forceinline__ float4 gx_pixel_section2d(const GxParams&, S&, int, int, GxCount&);
+template <bool BATCH, class S> __device__ __forceinline__ float4 gx_pixel_section3d(const GxParams&, S&, float3, float3, int, int, GxCount&, GxHit&);
+template <bool BATCH, class S> __device__ __forceinline__ float4 gx_pixel_deepshadow(const GxParams&, S&, float3, float3, int, int, GxCount&, GxHit&, float4&);
+
+// One camera ray through pixel (x,y) at sub-pixel offset (ox,oy) — the reference kernels use (0.5, 0.5) — shaded to the
+// float colour the reference packs with make_uchar4(clr*255).           cuda_gvdb_module.cu:60-181, :184-207, :225-298
+template <int MODE, bool BATCH, class S>
+__device__ __forceinline__ float4 gx_shade_pixel(const GxParams& P, S& smp, int x, int y, float ox, float oy,
+                                                 GxCount& cnt, GxHit& h, float4& raw)
+{
+    if constexpr (MODE == GX_MODE_SECTION2D) { return gx_pixel_section2d(P, smp, x, y, cnt); } else {
+    // cuda_gvdb_geom.cuh:48-63
+    float3 rpos = gx_mmult(P.invxform, P.campos);
+    float u = float(x + ox) / float(P.width), v = float(y + oy) / float(P.height);
+    float3 vv = u * P.camu + v * P.camv + P.cams;
+    float3 rdir = gx_normalize(gx_mmult(P.invxrot, vv));
+    float4 clr;
+    if constexpr (MODE == GX_MODE_DEEP) {
+        h.clr = make_float4(0, 0, 0, 1);
+        h.hit = make_float3(0, 0, GX_NOHIT);
+        gx_raycast<GX_MODE_DEEP, BATCH>(P, smp, rpos, rdir, h, cnt, x, y);
+        raw = h.clr;
+        clr = h.clr;
+        float a = 1.0 - clr.w;
+        clr = make_float4(P.backclr.x + a * (clr.x - P.backclr.x), P.backclr.y + a * (clr.y - P.backclr.y),
+                          P.backclr.z + a * (clr.z - P.backclr.z), 1.0 - clr.w);
+    } else if constexpr (MODE == GX_MODE_DEEPSHADOW) {
+        clr = gx_pixel_deepshadow<BATCH>(P, smp, rpos, rdir, x, y, cnt, h, raw);
+    } else if constexpr (MODE == GX_MODE_SECTION3D) {
+        clr = gx_pixel_section3d<BATCH>(P, smp, rpos, rdir, x, y, cnt, h);
+    } else if constexpr (MODE == GX_MODE_EMPTYSKIP) {                               // cuda_gvdb_module.cu:184-207
+        h.clr = make_float4(1, 1, 1, 1);
+        h.hit = make_float3(GX_NOHIT, GX_NOHIT, GX_NOHIT);
+        gx_raycast<GX_MODE_EMPTYSKIP, BATCH>(P, smp, rpos, rdir, h, cnt, x, y);
+        if (h.hit.z != GX_NOHIT) { const float3 c = h.hit * 0.01; clr = make_float4(c.x, c.y, c.z, 1); }
+        else clr = P.backclr;
+        clr.w = 1.0f;                                                     // the kernel packs alpha as the literal 255
+    } else {
+        h.clr = make_float4(1, 1, 1, 1);
+        h.hit = (MODE == GX_MODE_LEVELSET) ? make_float3(0, 0, GX_NOHIT) : make_float3(GX_NOHIT, GX_NOHIT, GX_NOHIT);
+        gx_raycast<MODE, BATCH>(P, smp, rpos, rdir, h, cnt, x, y);
+        // the tricubic kernel shades its shadow ray with the trilinear brick function (cuda_gvdb_module.cu:136)
+        clr = gx_phong<(MODE == GX_MODE_TRICUBIC ? GX_MODE_TRILINEAR : MODE), BATCH>(P, smp, h.hit, h.norm, h.clr, cnt, x, y);
+    }
+    return clr;
+    }
+}
+
+#define GX_FLAG_SPP     32     // P.spp sub-pixel samples per pixel, averaged in float before packing
+
 template <int MODE, int SAMPLER, int FLAGS, bool UNI>
 __global__ void __launch_bounds__(256, 4) gx_render_kernel(const __grid_constant__ GxParams P)
 {
@@ -650,7 +720,9 @@ __global__ void __launch_bounds__(256, 4) gx_render_kernel(const __grid_constant
         const int ly = (blockIdx.x / sub_x) * blockDim.y + threadIdx.y;
         x = (tile % P.tiles_x) * ts + lx;
         y = (tile / P.tiles_x) * ts + ly;
-        opix = (size_t(blockIdx.y) * ts + ly) * ts + lx;
+        // direct mode (out_stride > 0): pixels go straight into a row-major frame (possibly a peer GPU's, over NVLink);
+        // packed mode: tile after tile into this rank's own buffer
+        opix = P.out_stride > 0 ? size_t(y) * P.out_stride + x : (size_t(blockIdx.y) * ts + ly) * ts + lx;
         valid = (x < P.width && y < P.height);
     } else {
         x = P.x0 + blockIdx.x * blockDim.x + threadIdx.x;
@@ -664,42 +736,44 @@ __global__ void __launch_bounds__(256, 4) gx_render_kernel(const __grid_constant
     GxCount cnt = {0, 0, 0, 0, 0, 0};
     GxHit h;
     h.norm = make_float3(0, 0, 0); h.t = 0; h.leaf = -1; h.vox = make_int3(0, 0, 0);
-
-    // cuda_gvdb_geom.cuh:48-63
-    float3 rpos = gx_mmult(P.invxform, P.campos);
-    float u = float(x + 0.5f) / float(P.width), v = float(y + 0.5f) / float(P.height);
-    float3 vv = u * P.camu + v * P.camv + P.cams;
-    float3 rdir = gx_normalize(gx_mmult(P.invxrot, vv));
+    h.hit = make_float3(0, 0, GX_NOHIT); h.clr = make_float4(0, 0, 0, 0);
 
     float4 clr;
     float4 raw = make_float4(0, 0, 0, 0);
     constexpr bool BATCH = !(FLAGS & GX_FLAG_LITERAL);
-    if (FLAGS & GX_FLAG_PACKET) {
+    if constexpr ((FLAGS & GX_FLAG_PACKET) != 0) {
+        float3 rpos = gx_mmult(P.invxform, P.campos);
+        float u = float(x + 0.5f) / float(P.width), v = float(y + 0.5f) / float(P.height);
+        float3 vv = u * P.camu + v * P.camv + P.cams;
+        float3 rdir = gx_normalize(gx_mmult(P.invxrot, vv));
         clr = gx2_trace_pixel<MODE>(P, smp, rpos, rdir, x, y, cnt, h, raw, valid);
         if (!valid) return;
-    } else if (MODE == GX_MODE_DEEP) {
-        h.clr = make_float4(0, 0, 0, 1);
-        h.hit = make_float3(0, 0, GX_NOHIT);
-        gx_raycast<MODE, BATCH>(P, smp, rpos, rdir, h, cnt, x, y);
-        raw = h.clr;
-        clr = h.clr;
-        float a = 1.0 - clr.w;
-        clr = make_float4(P.backclr.x + a * (clr.x - P.backclr.x), P.backclr.y + a * (clr.y - P.backclr.y),
-                          P.backclr.z + a * (clr.z - P.backclr.z), 1.0 - clr.w);
+    } else if constexpr ((FLAGS & GX_FLAG_SPP) != 0) {
+        // sample s sits at ((s % g) + 0.5) / g, ((s / g) + 0.5) / g inside the pixel; colours are summed in sample order
+        float4 sum = make_float4(0, 0, 0, 0);
+        for (int s = 0; s < P.spp; s++) {
+            const float ox = __fmul_rn(float(s % P.spp_grid) + 0.5f, P.spp_inv_grid);
+            const float oy = __fmul_rn(float(s / P.spp_grid) + 0.5f, P.spp_inv_grid);
+            const float4 c = gx_shade_pixel<MODE, BATCH>(P, smp, x, y, ox, oy, cnt, h, raw);
+            sum.x = __fadd_rn(sum.x, c.x); sum.y = __fadd_rn(sum.y, c.y); sum.z = __fadd_rn(sum.z, c.z); sum.w = __fadd_rn(sum.w, c.w);
+        }
+        clr = make_float4(__fmul_rn(sum.x, P.spp_inv), __fmul_rn(sum.y, P.spp_inv), __fmul_rn(sum.z, P.spp_inv), __fmul_rn(sum.w, P.spp_inv));
     } else {
-        h.clr = make_float4(1, 1, 1, 1);
-        h.hit = (MODE == GX_MODE_LEVELSET) ? make_float3(0, 0, GX_NOHIT) : make_float3(GX_NOHIT, GX_NOHIT, GX_NOHIT);
-        gx_raycast<MODE, BATCH>(P, smp, rpos, rdir, h, cnt, x, y);
-        clr = gx_phong<MODE, BATCH>(P, smp, h.hit, h.norm, h.clr, cnt, x, y);
+        clr = gx_shade_pixel<MODE, BATCH>(P, smp, x, y, 0.5f, 0.5f, cnt, h, raw);
     }
-    P.out[opix] = make_uchar4(clr.x * 255, clr.y * 255, clr.z * 255, clr.w * 255);
+    if (MODE == GX_MODE_EMPTYSKIP || MODE == GX_MODE_SECTION2D || MODE == GX_MODE_SECTION3D)
+        P.out[opix] = make_uchar4(clr.x * 255, clr.y * 255, clr.z * 255, 255);
+    else
+        P.out[opix] = make_uchar4(clr.x * 255, clr.y * 255, clr.z * 255, clr.w * 255);
 
     if (FLAGS & GX_FLAG_DEBUG) {
         float4* d = P.dbg + 3 * (size_t(y) * P.width + x);
-        if (MODE == GX_MODE_DEEP) {
+        if (MODE == GX_MODE_DEEP || MODE == GX_MODE_DEEPSHADOW) {
             d[0] = raw;
             d[1] = make_float4(h.hit.x, h.hit.y, h.hit.z, 0.f);
             d[2] = make_float4(0, 0, 0, 0);
+        } else if (MODE == GX_MODE_SECTION2D) {
+            d[0] = clr; d[1] = make_float4(0, 0, 0, 0); d[2] = make_float4(0, 0, 0, 0);
         } else {
             bool miss = (h.hit.z == GX_NOHIT);
             d[0] = make_float4(h.hit.x, h.hit.y, h.hit.z, miss ? 0.f : h.t);
@@ -738,115 +812,3 @@ __global__ void __launch_bounds__(64) gx_raytrace_kernel(const __grid_constant__
     r[3] = h.norm.x; r[4] = h.norm.y; r[5] = h.norm.z;
 }
 
-// ------------------------------------------------------------------------------------------------ import kernels
-// pool-0 / pool-1 (reference layout) -> compact tables.  One thread per child cell.
-//   child list entry = Elem(0, lev-1, ndx) = grp | lev << 8 | ndx << 16, or 0xFFFFFFFFFFFFFFFF (src/gvdb_allocator.h:59-62,
-//   gvdb_volume_gvdb.cpp:3015-3023); node->mChildList = Elem(1, lev, ndx) or ID_UNDEFL.
-__global__ void gx_build_child_table(const char* __restrict__ nodelist, int nodewid, int nodecnt,
-                                     const char* __restrict__ childlist, int childwid, int cells,
-                                     int* __restrict__ child_out, int4* __restrict__ npos_out)
-{
-    size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
-    size_t total = size_t(nodecnt) * cells;
-    if (i >= total) return;
-    int n = int(i / cells), b = int(i % cells);
-    const GxNode* node = reinterpret_cast<const GxNode*>(nodelist + size_t(n) * nodewid);
-    uint64_t listid = node->mChildList;
-    int c = -1;
-    if (listid != GX_ID_UNDEFL) {
-        uint64_t cndx = listid >> 16;
-        const uint64_t* clist = reinterpret_cast<const uint64_t*>(childlist + cndx * size_t(childwid));
-        c = int(clist[b] >> 16);
-    }
-    child_out[i] = c;
-    if (b == 0) npos_out[n] = make_int4(node->mPos.x, node->mPos.y, node->mPos.z, 0);
-}
-
-__global__ void gx_build_leaf_table(const char* __restrict__ nodelist, int nodewid, int nodecnt, int brick_res,
-                                    int apron, int cnt_x, int cnt_y, GxLeafRec* __restrict__ out)
-{
-    int n = blockIdx.x * blockDim.x + threadIdx.x;
-    if (n >= nodecnt) return;
-    const GxNode* node = reinterpret_cast<const GxNode*>(nodelist + size_t(n) * nodewid);
-    GxLeafRec r;
-    r.px = node->mPos.x; r.py = node->mPos.y; r.pz = node->mPos.z;
-    r.vx = node->mValue.x; r.vy = node->mValue.y; r.vz = node->mValue.z;
-    int sx = (r.vx - apron) / brick_res, sy = (r.vy - apron) / brick_res, sz = (r.vz - apron) / brick_res;
-    r.base = (r.vx < 0) ? 0 : ((sz * cnt_y + sy) * cnt_x + sx) * GX_BRICK_STRIDE;
-    r.pad = 0;
-    out[n] = r;
-}
-
-// atlas (x-fastest linear image, as cuMemcpy3D array->linear delivers it) -> brick-major; one CTA per brick slot.
-// Also reduces the slot's value range (NaN-ignoring min / max over the 10^3 texels).
-__global__ void gx_repack_atlas(const float* __restrict__ lin, int rx, int ry, int rz, int cnt_x, int cnt_y,
-                                float* __restrict__ bricks, GxRange* __restrict__ range)
-{
-    const int slot = blockIdx.x;
-    const int sx = slot % cnt_x, sy = (slot / cnt_x) % cnt_y, sz = slot / (cnt_x * cnt_y);
-    float lo = INFINITY, hi = -INFINITY;
-    for (int i = threadIdx.x; i < GX_BRICK_STRIDE; i += blockDim.x) {
-        float v = 0.f;
-        if (i < GX_BRICK_DIM * GX_BRICK_DIM * GX_BRICK_DIM) {
-            int x = i % GX_BRICK_DIM, y = (i / GX_BRICK_DIM) % GX_BRICK_DIM, z = i / (GX_BRICK_DIM * GX_BRICK_DIM);
-            size_t ax = size_t(sx) * GX_BRICK_DIM + x, ay = size_t(sy) * GX_BRICK_DIM + y, az = size_t(sz) * GX_BRICK_DIM + z;
-            v = lin[(az * ry + ay) * rx + ax];
-            lo = fminf(lo, v); hi = fmaxf(hi, v);
-        }
-        bricks[size_t(slot) * GX_BRICK_STRIDE + i] = v;
-    }
-    __shared__ float slo[8], shi[8];
-    for (int o = 16; o > 0; o >>= 1) { lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, o)); hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, o)); }
-    if ((threadIdx.x & 31) == 0) { slo[threadIdx.x >> 5] = lo; shi[threadIdx.x >> 5] = hi; }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        for (int w = 1; w < (blockDim.x >> 5); w++) { lo = fminf(lo, slo[w]); hi = fmaxf(hi, shi[w]); }
-        range[slot].lo = lo; range[slot].hi = hi;
-    }
-}
-
-// value range per leaf = range of the brick slot the leaf's mValue points at (run when both topology and atlas are in)
-__global__ void gx_leaf_ranges(const GxLeafRec* __restrict__ leaf, int nleaf, const GxRange* __restrict__ slot_range,
-                               int nslots, GxRange* __restrict__ out)
-{
-    const int n = blockIdx.x * blockDim.x + threadIdx.x;
-    if (n >= nleaf) return;
-    const int slot = leaf[n].base / GX_BRICK_STRIDE;
-    GxRange r;
-    r.lo = -INFINITY; r.hi = INFINITY;                     // unknown slot: never culled
-    if (leaf[n].vx >= 0 && slot >= 0 && slot < nslots) r = slot_range[slot];
-    out[n] = r;
-}
-
-// scatter gathered tile buffers [nranks][slots][ts*ts] back into a row-major frame
-__global__ void gx_assemble_tiles(const uchar4* __restrict__ gathered, uchar4* __restrict__ frame, int width, int height,
-                                  int ts, int tiles_x, int ntiles, int nranks, int slots)
-{
-    const int tile = blockIdx.y;
-    if (tile >= ntiles) return;
-    const int r = tile % nranks, k = tile / nranks;
-    const uchar4* src = gathered + (size_t(r) * slots + k) * ts * ts;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < ts * ts; i += gridDim.x * blockDim.x) {
-        int lx = i % ts, ly = i / ts;
-        int x = (tile % tiles_x) * ts + lx, y = (tile / tiles_x) * ts + ly;
-        if (x < width && y < height) frame[size_t(y) * width + x] = src[i];
-    }
-}
-
-// calibration: hardware filter vs software model at arbitrary atlas-space points
-__global__ void gx_sample_points_kernel(GxParams P, const float* __restrict__ xyz, int n, int cnt_x, int cnt_y,
-                                        float* __restrict__ out_tex, float* __restrict__ out_lin)
-{
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    float x = xyz[3 * i], y = xyz[3 * i + 1], z = xyz[3 * i + 2];
-    out_tex[i] = tex3D<float>(P.tex, x, y, z);
-    GxSampler<GX_SAMPLER_LINEAR, false> s(P);
-    GxLeafRec L;
-    int sx = int(x) / GX_BRICK_DIM, sy = int(y) / GX_BRICK_DIM, sz = int(z) / GX_BRICK_DIM;
-    L.vx = sx * GX_BRICK_DIM + 1; L.vy = sy * GX_BRICK_DIM + 1; L.vz = sz * GX_BRICK_DIM + 1;
-    L.base = ((sz * cnt_y + sy) * cnt_x + sx) * GX_BRICK_STRIDE;
-    L.px = L.py = L.pz = L.pad = 0;
-    s.enter(L);
-    out_lin[i] = s.tri(x, y, z);
-}

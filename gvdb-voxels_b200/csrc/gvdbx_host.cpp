@@ -400,6 +400,10 @@ void gvdbxh_linear_transfer(gvdbxh_volume* h, float t0, float t1, const float a[
 {
     h->v.getScene()->LinearTransferFunc(t0, t1, Vec4(a[0], a[1], a[2], a[3]), Vec4(b[0], b[1], b[2], b[3]));
 }
+void gvdbxh_cross_section(gvdbxh_volume* h, const float pnt[3], const float norm[3])
+{
+    h->v.getScene()->SetCrossSection({pnt[0], pnt[1], pnt[2]}, {norm[0], norm[1], norm[2]});
+}
 const float* gvdbxh_transfer_table(gvdbxh_volume* h) { return h->v.getScene()->getTransferFunc(); }
 void gvdbxh_set_res(gvdbxh_volume* h, int w, int hh) { h->v.getScene()->SetRes(w, hh); }
 void gvdbxh_prepare_render(gvdbxh_volume* h, int w, int hh, int shading, void* out)

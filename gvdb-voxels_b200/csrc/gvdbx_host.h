@@ -136,6 +136,7 @@ void  gvdbxh_camera_nearfar(gvdbxh_volume*, float n, float f);
 void  gvdbxh_light(gvdbxh_volume*, const float angs[3], const float target[3], float dist, float dolly);
 void  gvdbxh_scene_params(gvdbxh_volume*, const float steps[3], const float extinct[3], const float thresh[3],
                           const float cutoff[3], const float backclr[4], const float shadow[3]);
+void  gvdbxh_cross_section(gvdbxh_volume*, const float pnt[3], const float norm[3]);   // Scene::SetCrossSection, src/gvdb_scene.h:147
 void  gvdbxh_linear_transfer(gvdbxh_volume*, float t0, float t1, const float a[4], const float b[4]);
 const float* gvdbxh_transfer_table(gvdbxh_volume*);
 void  gvdbxh_set_res(gvdbxh_volume*, int w, int h);

@@ -1,0 +1,3 @@
+// gx_render_kernel instantiations for one shade mode (see gvdbx_pick.cuh)
+#include "gvdbx_pick.cuh"
+GX_DEFINE_PICK(trilinear, GX_MODE_TRILINEAR, true, true)

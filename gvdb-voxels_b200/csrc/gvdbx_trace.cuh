@@ -167,13 +167,14 @@ __device__ __forceinline__ void gx2_brick_deep(const GxParams& P, S& smp, int no
 {
     const GxLeafRec L = P.leaf[nodeid];
     cnt.n_desc++;
-    // every sample below MINVAL is skipped by the reference: such a brick only refreshes hit.x / hit.y (not part of the
-    // image) and re-applies an idempotent clamp.  Not taken when a depth buffer is bound (hit.z bookkeeping).
+    const float st = P.steps.x;
+    t.x = st * ceilf(t.x / st);
+    if (h.hit.x == 0) h.hit.x = t.x;    // parameter of the first sample of the first brick entered (deep + shadow starts there)
+    // every sample below MINVAL is skipped by the reference: such a brick only refreshes hit.y (not part of the image)
+    // and re-applies an idempotent clamp.  Not taken when a depth buffer is bound (hit.z bookkeeping).
     if (P.range != nullptr && P.dbuf == nullptr && !(__ldg(&P.range[nodeid].hi) >= P.cutoff.x)) return;
     smp.enter(L);
     const float3 vmin = make_float3(float(L.px), float(L.py), float(L.pz));
-    const float st = P.steps.x;
-    t.x = st * ceilf(t.x / st);
     const float3 o = make_float3(float(L.vx), float(L.vy), float(L.vz));
     float3 wp = pos + t.x * dir;
     float3 p = wp - vmin;
@@ -183,7 +184,6 @@ __device__ __forceinline__ void gx2_brick_deep(const GxParams& P, S& smp, int no
     const float minval = P.cutoff.x, acut = P.cutoff.y, thresh = P.thresh.x;
     const float inv_range = gx_rcp_approx(P.thresh.z - P.thresh.y);
     float4& clr = h.clr;
-    if (h.hit.x == 0) h.hit.x = t.x;
 
     if (P.dbuf != nullptr) {            // depth-buffer compositing: one sample at a time, as written in the reference
         for (int iter = 0; clr.w > acut && iter < GX_MAX_ITER && GX_INB(p, res0); iter++) {

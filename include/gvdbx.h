@@ -33,7 +33,11 @@ extern "C" {
 
 /* shade modes: numeric values of the reference's SHADE_* (src/gvdb_types.h:73-81) */
 #define GVDBX_SHADE_VOXEL      0
+#define GVDBX_SHADE_SECTION2D  1   /* kernels/cuda_gvdb_module.cu:272-298 (texture sampler only) */
+#define GVDBX_SHADE_SECTION3D  2   /* kernels/cuda_gvdb_module.cu:225-269 (texture sampler only) */
+#define GVDBX_SHADE_EMPTYSKIP  3   /* kernels/cuda_gvdb_module.cu:184-207 */
 #define GVDBX_SHADE_TRILINEAR  4
+#define GVDBX_SHADE_TRICUBIC   5   /* kernels/cuda_gvdb_module.cu:122-139 (texture sampler only) */
 #define GVDBX_SHADE_LEVELSET   6
 #define GVDBX_SHADE_VOLUME     7
 #define GVDBX_SHADE_OFF        100
@@ -51,6 +55,11 @@ extern "C" {
 #define GVDBX_OPT_BLOCK_H   3   /* CTA pixel tile height (default 8)  */
 #define GVDBX_OPT_COUNTERS  4   /* 1 = accumulate work counters during render (slower; for roofline accounting) */
 #define GVDBX_OPT_CULL      6   /* 1 (default) = skip bricks whose value range cannot satisfy the mode's acceptance test (exact) */
+#define GVDBX_OPT_SPP       7   /* rays per pixel (default 1 = the reference's pixel-centre ray).  n > 1: samples on a g x g sub-pixel grid,
+                                   g = ceil(sqrt(n)), sample s at ((s % g) + .5) / g, ((s / g) + .5) / g; float colours summed in sample
+                                   order, scaled by 1/n, packed once (BASELINE.json config 5: 4 spp) */
+#define GVDBX_OPT_DEEP_SHADOW 8 /* 1 = SHADE_VOLUME casts one shadow march (rayShadowBrick, kernels/cuda_gvdb_raycast.cuh:445-463) from
+                                   the first sample towards the light and darkens the accumulated colour (BASELINE.json config 4) */
 #define GVDBX_OPT_TRAVERSAL 5   /* 0 = default (four-samples-per-round brick marchers), 1 = reference-shaped loops, one sample at a time (A/B),
                                    2 = vote-converged two-phase packet traversal (A/B) */
 

@@ -92,3 +92,44 @@ extern "C" __global__ void oracleDeepShadow(VDBInfo* gvdb, uchar chan, uchar4* o
     clr = make_float4(lerp3(SCN_BACKCLR, clr, 1.0 - clr.w), 1.0 - clr.w);
     outBuf[y * scn.width + x] = make_uchar4(clr.x * 255, clr.y * 255, clr.z * 255, clr.w * 255);
 }
+
+// SHADE_TRICUBIC brick function (module.cu:122-139): primary hit point + normal
+extern "C" __global__ void oracleHitTricubic(VDBInfo* gvdb, uchar chan, uchar4* outBuf)
+{
+    ORACLE_PIXEL();
+    float3 hit = make_float3(NOHIT, NOHIT, NOHIT), norm = make_float3(0, 0, 0);
+    float4 clr = make_float4(1, 1, 1, 1);
+    rayCast(gvdb, chan, rpos, rdir, hit, norm, clr, raySurfaceTricubicBrick);
+    oracleStoreHit(outBuf, x, y, hit, norm);
+}
+// SHADE_EMPTYSKIP brick function (module.cu:184-207): first brick entry point
+extern "C" __global__ void oracleHitEmptySkip(VDBInfo* gvdb, uchar chan, uchar4* outBuf)
+{
+    ORACLE_PIXEL();
+    float3 hit = make_float3(NOHIT, NOHIT, NOHIT), norm = make_float3(0, 0, 0);
+    float4 clr = make_float4(1, 1, 1, 1);
+    rayCast(gvdb, chan, rpos, rdir, hit, norm, clr, rayEmptySkipBrick);
+    oracleStoreHit(outBuf, x, y, hit, make_float3(0, 0, 0));
+}
+// BASELINE.json config 5: deep render with several rays per pixel.  One launch per sample: scn.frame = samples per
+// pixel n, scn.samples = index s of this launch (the two ScnInfo fields PrepareRender fills from Scene::SetFrame /
+// SetSample and no native kernel reads).  Sample s sits at ((s % g) + .5) / g, ((s / g) + .5) / g with g = ceil(sqrt(n))
+// instead of the native kernels' (.5, .5); everything else is gvdbRayDeep (module.cu:60-78).  The composited FLOAT
+// colour goes to a 16 B/pixel render buffer; the harness sums the samples in order, scales by 1/n and packs.
+extern "C" __global__ void oracleDeepSample(VDBInfo* gvdb, uchar chan, uchar4* outBuf)
+{
+    int x = blockIdx.x * blockDim.x + threadIdx.x;
+    int y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= scn.width || y >= scn.height) return;
+    int n = scn.frame < 1 ? 1 : scn.frame, s = scn.samples, g = 1;
+    while (g * g < n) g++;
+    const float inv_g = __fdiv_rn(1.0f, float(g));
+    const float ox = __fmul_rn(float(s % g) + 0.5f, inv_g), oy = __fmul_rn(float(s / g) + 0.5f, inv_g);
+    float3 rpos = getViewPos();
+    float3 rdir = getViewRay(float(x + ox) / float(scn.width), float(y + oy) / float(scn.height));
+    float4 clr = make_float4(0, 0, 0, 1);
+    float3 hit = make_float3(0, 0, NOHIT), norm;
+    rayCast(gvdb, chan, rpos, rdir, hit, norm, clr, rayDeepBrick);
+    clr = make_float4(lerp3(SCN_BACKCLR, clr, 1.0 - clr.w), 1.0 - clr.w);
+    ((float4*)outBuf)[y * scn.width + x] = clr;
+}

@@ -44,17 +44,22 @@ static void dump(const std::string& path, const void* p, size_t n)
     if (!f) { fprintf(stderr, "cannot write %s\n", path.c_str()); exit(2); }
     fwrite(p, 1, n, f); fclose(f);
 }
-struct Mode { const char* name; int shade; const char* hitkernel; };
+// kind 0: native Render(shade) [+ hit wrapper]; kind 1: composed RGBA8 kernel through RenderKernel (BASELINE config 4);
+// kind 2: per-sample float colour kernel, `spp` samples averaged on the host (BASELINE config 5)
+struct Mode { const char* name; int shade; const char* hitkernel; int kind; };
 static const Mode kModes[] = {
-    {"voxel", SHADE_VOXEL, "oracleHitVoxel"}, {"trilinear", SHADE_TRILINEAR, "oracleHitTrilinear"},
-    {"levelset", SHADE_LEVELSET, "oracleHitLevelSet"}, {"deep", SHADE_VOLUME, "oracleDeepRaw"},
+    {"voxel", SHADE_VOXEL, "oracleHitVoxel", 0}, {"trilinear", SHADE_TRILINEAR, "oracleHitTrilinear", 0},
+    {"levelset", SHADE_LEVELSET, "oracleHitLevelSet", 0}, {"deep", SHADE_VOLUME, "oracleDeepRaw", 0},
+    {"tricubic", SHADE_TRICUBIC, "oracleHitTricubic", 0}, {"emptyskip", SHADE_EMPTYSKIP, "oracleHitEmptySkip", 0},
+    {"section2d", SHADE_SECTION2D, "", 0}, {"section3d", SHADE_SECTION3D, "", 0},
+    {"deepshadow", SHADE_VOLUME, "oracleDeepShadow", 1}, {"deepspp", SHADE_VOLUME, "oracleDeepSample", 2},
 };
 
 int main(int argc, char** argv)
 {
     if (argc < 3) { fprintf(stderr, "usage: ref_harness <preset> <outdir> [opts]\n"); return 1; }
     std::string preset = argv[1], outdir = argv[2], modes = "";
-    int W = 0, H = 0, frames = 1, warmup = 0, nodump = 0, shadow = -1, hits = 1, bench = 0, orbit = 8, steps = 5;
+    int W = 0, H = 0, frames = 1, warmup = 0, nodump = 0, shadow = -1, hits = 1, bench = 0, orbit = 8, steps = 5, spp = 4;
     std::string bmode = "";
     float xf[12] = {0, 0, 0, 1, 1, 1, 0, 0, 0, 0, 0, 0};
     int have_xf = 0, use_dbuf = 0, nrays = 0;
@@ -73,6 +78,7 @@ int main(int argc, char** argv)
         else if (a == "--mode" && i + 1 < argc) bmode = argv[++i];
         else if (a == "--xform" && i + 1 < argc) { have_xf = 1; sscanf(argv[++i], "%f,%f,%f,%f,%f,%f,%f,%f,%f,%f,%f,%f", xf, xf + 1, xf + 2, xf + 3, xf + 4, xf + 5, xf + 6, xf + 7, xf + 8, xf + 9, xf + 10, xf + 11); }
         else if (a == "--dbuf") use_dbuf = 1;
+        else if (a == "--spp" && i + 1 < argc) spp = atoi(argv[++i]);
         else if (a == "--raytrace" && i + 1 < argc) nrays = atoi(argv[++i]);
     }
     scene_preset P;
@@ -162,6 +168,7 @@ int main(int argc, char** argv)
     const int w = P.width, h = P.height;
     gvdb.AddRenderBuf(0, w, h, 4);
     gvdb.AddRenderBuf(1, w, h, 32);
+    gvdb.AddRenderBuf(3, w, h, 16);
     // --xform: VolumeGVDB::SetTransform(pretrans, scale, angles, trans)   (gvdb_volume_gvdb.cpp:5770)
     if (have_xf) gvdb.SetTransform(Vector3DF(xf[0], xf[1], xf[2]), Vector3DF(xf[3], xf[4], xf[5]), Vector3DF(xf[6], xf[7], xf[8]), Vector3DF(xf[9], xf[10], xf[11]));
     // --dbuf: a synthetic depth buffer in a plain render buffer (AddDepthBuf itself needs GL): NDC depth of a slanted
@@ -198,20 +205,36 @@ int main(int argc, char** argv)
 
     // ---- bench mode (bench.py --impl reference): the reference's own CUDA render through its public API
     if (bench) {
-        int shade = P.shade;
-        for (const Mode& m : kModes) if (bmode == m.name) shade = m.shade;
+        int shade = P.shade, kind = 0;
+        const char* kname = "";
+        for (const Mode& m : kModes) if (bmode == m.name) { shade = m.shade; kind = m.kind; kname = m.hitkernel; }
+        CUmodule bmod = 0; CUfunction bfn = 0;
+        if (kind != 0) {
+            if (cuModuleLoad(&bmod, "oracle_kernels.cubin") != CUDA_SUCCESS || cuModuleGetFunction(&bfn, bmod, kname) != CUDA_SUCCESS) {
+                fprintf(stderr, "cannot load %s from oracle_kernels.cubin\n", kname); return 4;
+            }
+            gvdb.SetModule(bmod);
+            scn->SetShading(shade);
+        }
         std::vector<unsigned char> frame((size_t)w * h * 4);
         auto set_cam = [&](int j) {
             cam->setOrbit(Vector3DF(P.cam_angs[0] + 360.0f * (float)j / (float)orbit, P.cam_angs[1], P.cam_angs[2]),
                           Vector3DF(P.cam_target[0], P.cam_target[1], P.cam_target[2]), P.cam_dist, 1.0f);
         };
-        for (int s = 0; s < warmup; s++) for (int j = 0; j < orbit; j++) { set_cam(j); gvdb.Render(shade, 0, 0); }
+        // kind 1: the composed kernel writes RGBA8 into buffer 0; kind 2: `spp` per-sample launches into the float buffer
+        // (the host-side average is not part of the timed region: it favours the reference)
+        auto render = [&]() {
+            if (kind == 0) gvdb.Render(shade, 0, 0);
+            else if (kind == 1) gvdb.RenderKernel(bfn, 0, 0);
+            else for (int sidx = 0; sidx < spp; sidx++) { scn->SetSample(sidx); scn->SetFrame(spp); gvdb.RenderKernel(bfn, 0, 3); }
+        };
+        for (int s = 0; s < warmup; s++) for (int j = 0; j < orbit; j++) { set_cam(j); render(); }
         cuCtxSynchronize();
         double tk0 = now_s();
-        for (int s = 0; s < steps; s++) { for (int j = 0; j < orbit; j++) { set_cam(j); gvdb.Render(shade, 0, 0); } cuCtxSynchronize(); }
+        for (int s = 0; s < steps; s++) { for (int j = 0; j < orbit; j++) { set_cam(j); render(); } cuCtxSynchronize(); }
         double t_kernel = now_s() - tk0;
         double te0 = now_s();
-        for (int s = 0; s < steps; s++) for (int j = 0; j < orbit; j++) { set_cam(j); gvdb.Render(shade, 0, 0); gvdb.ReadRenderBuf(0, frame.data()); }
+        for (int s = 0; s < steps; s++) for (int j = 0; j < orbit; j++) { set_cam(j); render(); gvdb.ReadRenderBuf(0, frame.data()); }
         double t_e2e = now_s() - te0;
         unsigned long long sum = 0;
         for (size_t i = 0; i < frame.size(); i += 97) sum += frame[i];
@@ -248,9 +271,7 @@ int main(int argc, char** argv)
 
     // ---- oracle wrapper kernels via the RenderKernel plugin API
     CUmodule omod = 0;
-    if (hits) {
-        if (cuModuleLoad(&omod, "oracle_kernels.cubin") != CUDA_SUCCESS) { fprintf(stderr, "cannot load oracle_kernels.cubin\n"); hits = 0; }
-    }
+    if (cuModuleLoad(&omod, "oracle_kernels.cubin") != CUDA_SUCCESS) { fprintf(stderr, "cannot load oracle_kernels.cubin\n"); hits = 0; omod = 0; }
 
     std::string timing = "{\"preset\":\"" + preset + "\",\"bricks\":" + std::to_string(S.nbricks) +
         ",\"width\":" + std::to_string(w) + ",\"height\":" + std::to_string(h) +
@@ -259,20 +280,52 @@ int main(int argc, char** argv)
     bool first = true;
     std::vector<unsigned char> img((size_t)w * h * 4);
     std::vector<float> hitbuf((size_t)w * h * 8);
+    const float cN = 0.5f * (float)P.N;
+    std::vector<float> sample((size_t)w * h * 4), accum((size_t)w * h * 4);
     for (const Mode& m : kModes) {
-        bool want = modes.empty() ? (m.shade == P.shade) : (("," + modes + ",").find(std::string(",") + m.name + ",") != std::string::npos);
+        bool want = modes.empty() ? (m.shade == P.shade && m.kind == 0)
+                                  : (("," + modes + ",").find(std::string(",") + m.name + ",") != std::string::npos);
         if (!want) continue;
-        for (int i = 0; i < warmup; i++) gvdb.Render(m.shade, 0, 0);
+        // section plane: 2D = centre + (u,0,v) * half extent (slice_norm is a per-axis scale there); 3D = tilted plane
+        if (m.shade == SHADE_SECTION2D) scn->SetCrossSection(Vector3DF(cN, cN * 0.9f, cN), Vector3DF(cN * 0.8f, 1.0f, cN * 0.8f));
+        if (m.shade == SHADE_SECTION3D) scn->SetCrossSection(Vector3DF(cN, cN, cN * 0.85f), Vector3DF(0.3f, 0.2f, 1.0f));
+        CUfunction kfn = 0;
+        if (m.kind != 0) {
+            if (!omod || cuModuleGetFunction(&kfn, omod, m.hitkernel) != CUDA_SUCCESS) { fprintf(stderr, "no kernel %s\n", m.hitkernel); continue; }
+            gvdb.SetModule(omod);
+            scn->SetShading(m.shade);
+        }
+        auto render = [&]() {
+            if (m.kind == 0) gvdb.Render(m.shade, 0, 0);
+            else if (m.kind == 1) gvdb.RenderKernel(kfn, 0, 0);
+            else for (int sidx = 0; sidx < spp; sidx++) { scn->SetSample(sidx); scn->SetFrame(spp); gvdb.RenderKernel(kfn, 0, 3); }
+        };
+        for (int i = 0; i < warmup; i++) render();
         cuCtxSynchronize();
         std::vector<double> ms;
         for (int i = 0; i < frames; i++) {
             double a = now_s();
-            gvdb.Render(m.shade, 0, 0);
+            render();
             cuCtxSynchronize();
             ms.push_back((now_s() - a) * 1e3);
         }
         double a = now_s();
-        gvdb.ReadRenderBuf(0, img.data());
+        if (m.kind == 2) {
+            // sample colours summed in sample order, scaled by 1/spp, packed like make_uchar4(clr*255)
+            std::fill(accum.begin(), accum.end(), 0.0f);
+            for (int sidx = 0; sidx < spp; sidx++) {
+                scn->SetSample(sidx); scn->SetFrame(spp);
+                gvdb.RenderKernel(kfn, 0, 3);
+                cuCtxSynchronize();
+                gvdb.ReadRenderBuf(3, (unsigned char*)sample.data());
+                for (size_t i = 0; i < accum.size(); i++) accum[i] = accum[i] + sample[i];
+            }
+            const float inv = 1.0f / (float)spp;
+            for (size_t i = 0; i < accum.size(); i++) { volatile float c = accum[i] * inv; volatile float q = c * 255.0f; img[i] = (unsigned char)(int)q; }
+            scn->SetSample(0); scn->SetFrame(0);
+        } else {
+            gvdb.ReadRenderBuf(0, img.data());
+        }
         double read_ms = (now_s() - a) * 1e3;
         std::sort(ms.begin(), ms.end());
         double med = ms[ms.size() / 2], mn = ms[0];
@@ -280,7 +333,8 @@ int main(int argc, char** argv)
             dump(outdir + "/out_" + m.name + ".rgba", img.data(), img.size());
             dump(outdir + "/scninfo_" + m.name + ".bin", gvdb.getScnInfo(), 416);
         }
-        if (hits) {
+        if (m.kind != 0) gvdb.SetModule();
+        if (hits && m.kind == 0 && m.hitkernel[0]) {
             CUfunction fn;
             if (cuModuleGetFunction(&fn, omod, m.hitkernel) == CUDA_SUCCESS) {
                 gvdb.SetModule(omod);               // scn symbol of the wrapper module

@@ -74,9 +74,31 @@ def extras(outdir):
         print("[golden] extra", tag, preset, flush=True)
 
 
+def modes2(outdir):
+    """the rest of Render()'s switch (tricubic, empty skip, sections) and the two composed BASELINE modes (deep + shadow,
+    deep at 4 rays per pixel): ScnInfo + RGBA per mode, hit / normal buffers for the tiny presets"""
+    for preset in ("cfg1_tiny", "cfg4_tiny", "cfg1_small", "cfg4_small"):
+        d = tempfile.mkdtemp(prefix="refdump_")
+        refcmp.run_ref(preset, d, modes=["deep"] + list(refcmp.MODES2))
+        dump = refcmp.load_dump(d)
+        out = {"preset": preset, "width": dump["meta"]["width"], "height": dump["meta"]["height"], "spp": 4,
+               "vdbinfo": np.frombuffer(dump["vdbinfo"], np.uint8)}
+        for m in refcmp.MODES2:
+            out[f"scn_{m}"] = np.frombuffer(dump["scn"][m], np.uint8)
+            out[f"rgba_{m}"] = dump["rgba"][m]
+            if "tiny" in preset and m in dump["hit"]:
+                out[f"hit_{m}"] = dump["hit"][m]
+        np.savez_compressed(os.path.join(outdir, f"ref_modes2_{preset}.npz"), **out)
+        print("[golden] modes2", preset, flush=True)
+
+
 if __name__ == "__main__":
     out = sys.argv[1] if len(sys.argv) > 1 else os.path.join(ROOT, "gpurun_out", "golden")
+    os.makedirs(out, exist_ok=True)
+    if "--modes2-only" in sys.argv:
+        modes2(out)
+        sys.exit(0)
     if "--extras-only" not in sys.argv:
         main(out)
-    os.makedirs(out, exist_ok=True)
     extras(out)
+    modes2(out)

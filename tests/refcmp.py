@@ -18,6 +18,10 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 REF_DIR = os.path.join(ROOT, "oracle", "_ref")
 MODES = {"voxel": 0, "trilinear": 4, "levelset": 6, "deep": 7}
+# the rest of Render()'s switch + the two composed BASELINE modes: name -> (shade, deep_shadow option, spp option)
+MODES2 = {"tricubic": (5, 0, 1), "emptyskip": (3, 0, 1), "section2d": (1, 0, 1), "section3d": (2, 0, 1),
+          "deepshadow": (7, 1, 1), "deepspp": (7, 0, 4)}
+ALL_SHADE = dict(MODES, **{k: v[0] for k, v in MODES2.items()})
 
 
 def have_ref():
@@ -75,7 +79,7 @@ def load_dump(d):
         (out["pool0"] if g == 0 else out["pool1"])[l] = b
     out["scn"], out["rgba"], out["hit"] = {}, {}, {}
     w, h = meta["width"], meta["height"]
-    for m in MODES:
+    for m in list(MODES) + list(MODES2):
         p = os.path.join(d, f"scninfo_{m}.bin")
         if os.path.exists(p):
             out["scn"][m] = open(p, "rb").read()
@@ -118,14 +122,21 @@ def render_mine(r, dump, mode, sampler, debug=False):
         dump = dict(dump)
         dump["scn"] = {m: patch_dbuf(s, dump["_dbuf_dev"].data_ptr()) for m, s in dump["scn"].items()}
     out = torch.zeros((h, w, 4), dtype=torch.uint8, device="cuda")
-    if debug:
-        dbg = torch.zeros((h, w, 12), dtype=torch.float32, device="cuda")
-        r.render_debug(dump["scn"][mode], MODES[mode], out.data_ptr(), dbg.data_ptr())
+    _, dshadow, spp = MODES2.get(mode, (0, 0, 1))
+    r.set_deep_shadow(dshadow)
+    r.set_spp(spp)
+    try:
+        if debug:
+            dbg = torch.zeros((h, w, 12), dtype=torch.float32, device="cuda")
+            r.render_debug(dump["scn"][mode], ALL_SHADE[mode], out.data_ptr(), dbg.data_ptr())
+            r.sync()
+            return out.cpu().numpy(), dbg.cpu().numpy(), r.counters()
+        r.render(dump["scn"][mode], ALL_SHADE[mode], out.data_ptr())
         r.sync()
-        return out.cpu().numpy(), dbg.cpu().numpy(), r.counters()
-    r.render(dump["scn"][mode], MODES[mode], out.data_ptr())
-    r.sync()
-    return out.cpu().numpy(), None, None
+        return out.cpu().numpy(), None, None
+    finally:
+        r.set_deep_shadow(0)
+        r.set_spp(1)
 
 
 def psnr(a, b):
@@ -183,6 +194,37 @@ def compare(dump, pkg, modes=None, device=0, verbose=True):
     return res
 
 
+def compare2(dump, pkg, modes=None, device=0, verbose=True):
+    """The rest of Render()'s switch + the composed modes (texture sampler; deep variants also with linear loads)."""
+    res = {}
+    r = make_renderer(dump, pkg, device)
+    for m in (modes or [k for k in MODES2 if k in dump["scn"]]):
+        ref = dump["rgba"][m]
+        res[m] = {}
+        for sname, s in (("tex", 0), ("linear", 1)):
+            if s == 1 and not m.startswith("deep"):
+                continue
+            mine, dbg, cnt = render_mine(r, dump, m, s, debug=(m != "deepspp"))
+            plain, _, _ = render_mine(r, dump, m, s, debug=False)
+            diff = np.abs(plain.astype(np.int32) - ref.astype(np.int32))
+            st = {"pixels": int(ref.shape[0] * ref.shape[1]),
+                  "rgba_mismatch_pixels": int((diff.max(axis=2) > 0).sum()), "rgba_max_abs": int(diff.max()),
+                  "rgba_over1_pixels": int((diff.max(axis=2) > 1).sum()), "psnr": psnr(plain, ref),
+                  "plain_equals_debug": bool(np.array_equal(plain, mine)), "nonbackground": int((ref != ref[0, 0]).any(axis=2).sum())}
+            if m in dump["hit"] and dbg is not None:
+                rh = dump["hit"][m]
+                bad_hit = (dbg[:, :, 0:3].view(np.uint32) != rh[:, :, 0:3].view(np.uint32)).any(axis=2)
+                st["hit_mismatch_pixels"] = int(bad_hit.sum())
+                if m == "tricubic":
+                    st["norm_mismatch_pixels"] = int((dbg[:, :, 4:7].view(np.uint32) != rh[:, :, 4:7].view(np.uint32)).any(axis=2).sum())
+                st["hit_pixels"] = int((rh[:, :, 2] != np.float32(1.0e10)).sum())
+            res[m][sname] = st
+            if verbose:
+                print(f"[refcmp2] {dump['meta'].get('preset')} {m:10s} {sname:6s} " + json.dumps(st), flush=True)
+    r.close()
+    return res
+
+
 def main():
     sys.path.insert(0, ROOT)
     from __graft_entry__ import load_package
@@ -192,14 +234,18 @@ def main():
     ap.add_argument("--modes", default="voxel,trilinear,levelset,deep")
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "refcmp.json"))
     ap.add_argument("--keep", default="")
+    ap.add_argument("--modes2", default="", help="comma list out of " + ",".join(MODES2) + " or 'all'")
     a = ap.parse_args()
+    m2 = list(MODES2) if a.modes2 == "all" else [m for m in a.modes2.split(",") if m]
     allres = {}
     for preset in a.presets.split(","):
         d = os.path.join(a.keep, preset) if a.keep else tempfile.mkdtemp(prefix="refdump_")
         os.makedirs(d, exist_ok=True)
-        timing = run_ref(preset, d, modes=a.modes.split(","))
+        timing = run_ref(preset, d, modes=a.modes.split(",") + m2)
         dump = load_dump(d)
         allres[preset] = {"ref_timing": timing, "cmp": compare(dump, pkg, a.modes.split(","))}
+        if m2:
+            allres[preset]["cmp2"] = compare2(dump, pkg, m2)
     os.makedirs(os.path.dirname(a.out), exist_ok=True)
     json.dump(allres, open(a.out, "w"), indent=1)
     print("[refcmp] wrote", a.out)

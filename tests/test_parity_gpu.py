@@ -227,7 +227,7 @@ def test_edge_cases(ora, pkg, torch_cuda):
     assert (out.cpu().numpy() == bg).all()
     # unsupported shade mode, SHADE_OFF clears
     with pytest.raises(pkg.GvdbxError):
-        r.render(scn, 5, out.data_ptr())            # SHADE_TRICUBIC: outside the path
+        r.render(scn, 9, out.data_ptr())            # not a shade mode of the reference's Render switch
     out.fill_(7)
     r.render(scn, pkg.SHADE_OFF, out.data_ptr())
     r.sync()
@@ -361,3 +361,100 @@ def test_full_size_cfg2_levelset_properties(scenes, torch_cuda, ora, pkg):
     r.set_option(5, 0)
     assert np.array_equal(_render(torch, r, scn, 6, w, h, 0), tex)
     assert (tex != tex[0, 0]).any()
+
+
+# ------------------------------------------------------------------------------------------------ rest of Render()'s switch
+def _modes2(preset):
+    import os
+    from common import GOLDEN
+    return np.load(os.path.join(GOLDEN, f"ref_modes2_{preset}.npz"))
+
+
+def _render2(torch, r, g, mode, debug=False):
+    shade, dshadow, spp = refcmp.MODES2[mode]
+    r.set_sampler(0)
+    r.set_deep_shadow(dshadow)
+    r.set_spp(spp)
+    try:
+        return _render(torch, r, g[f"scn_{mode}"].tobytes(), shade, int(g["width"]), int(g["height"]), 0, debug=debug)
+    finally:
+        r.set_deep_shadow(0)
+        r.set_spp(1)
+
+
+@pytest.mark.parametrize("preset", ["cfg1_tiny", "cfg4_tiny", "cfg1_small", "cfg4_small"])
+@pytest.mark.parametrize("mode", list(refcmp.MODES2))
+def test_remaining_modes_bit_exact_vs_reference(scenes, torch_cuda, preset, mode):
+    """SHADE_TRICUBIC / EMPTYSKIP / SECTION2D / SECTION3D against the reference's native kernels, deep + shadow and
+    deep at 4 rays per pixel against kernels composed from the reference's own device functions: RGBA bit for bit,
+    hit point (+ normal for tricubic) bit for bit on the tiny presets."""
+    g = _modes2(preset)
+    p, vol, r = scenes(preset)
+    ref = g[f"rgba_{mode}"]
+    if mode == "deepspp":
+        img = _render2(torch_cuda, r, g, mode)
+    else:
+        img, dbg = _render2(torch_cuda, r, g, mode, debug=True)
+        assert np.array_equal(_render2(torch_cuda, r, g, mode), img)            # plain variant == debug variant
+        key = f"hit_{mode}"
+        if key in g.files:
+            assert np.array_equal(dbg[:, :, 0:3].view(np.uint32), g[key][:, :, 0:3].view(np.uint32))
+            if mode == "tricubic":
+                assert np.array_equal(dbg[:, :, 4:7].view(np.uint32), g[key][:, :, 4:7].view(np.uint32))
+    assert np.array_equal(img, ref), f"{(img != ref).any(axis=2).sum()} pixels differ"
+    assert (ref != ref[0, 0]).any()                                             # something is in view
+
+
+def test_composed_modes_properties(scenes, torch_cuda):
+    """deep + shadow really darkens; 1 ray per pixel == the plain kernel; the tile-list variant of a 4-spp render and
+    the linear-load sampler agree with the full-frame texture render; texture-only modes refuse the linear sampler."""
+    torch = torch_cuda
+    preset = "cfg4_small"
+    g, g0 = _modes2(preset), golden(preset)
+    p, vol, r = scenes(preset)
+    w, h = int(g["width"]), int(g["height"])
+    assert not np.array_equal(g["rgba_deepshadow"], g0["rgba_deep"])
+    assert g["rgba_deepshadow"][:, :, :3].astype(int).sum() < g0["rgba_deep"][:, :, :3].astype(int).sum()
+    assert not np.array_equal(g["rgba_deepspp"], g0["rgba_deep"])
+    scn = g0["scn_deep"].tobytes()
+    r.set_spp(1)
+    assert np.array_equal(_render(torch, r, scn, 7, w, h, 0), g0["rgba_deep"])
+    # 4 spp through the tile-list kernels (the multi-GPU path of BASELINE config 5)
+    r.set_spp(4)
+    world, ts = 3, 32
+    slots = r.tiles_per_rank(w, h, ts, world)
+    gathered = torch.zeros((world, slots, ts, ts, 4), dtype=torch.uint8, device="cuda")
+    for rank in range(world):
+        r.render_tiles(g["scn_deepspp"].tobytes(), 7, gathered[rank].data_ptr(), ts, rank, world)
+    frame = torch.zeros((h, w, 4), dtype=torch.uint8, device="cuda")
+    r.assemble_tiles(gathered.data_ptr(), frame.data_ptr(), w, h, ts, world)
+    r.sync()
+    assert np.array_equal(frame.cpu().numpy(), g["rgba_deepspp"])
+    lin = _render(torch, r, g["scn_deepspp"].tobytes(), 7, w, h, 1)
+    assert tolerance_ok(lin, g["rgba_deepspp"])[0]
+    # 4 spp in a surface mode: averaged colour stays within the per-sample extremes, silhouette pixels change
+    r.set_sampler(0)
+    s4 = _render(torch, r, g0["scn_trilinear"].tobytes(), 4, w, h, 0)
+    r.set_spp(1)
+    s1 = _render(torch, r, g0["scn_trilinear"].tobytes(), 4, w, h, 0)
+    assert np.array_equal(s1, g0["rgba_trilinear"]) and not np.array_equal(s4, s1)
+    assert (np.abs(s4.astype(int) - s1.astype(int)).max(axis=2) > 0).mean() < 0.5
+    # texture-only modes refuse the linear sampler instead of silently rendering something else
+    r.set_sampler(1)
+    out = torch.zeros((h, w, 4), dtype=torch.uint8, device="cuda")
+    for shade in (1, 2, 3, 5):
+        with pytest.raises(Exception):
+            r.render(g["scn_tricubic"].tobytes(), shade, out.data_ptr())
+    r.set_sampler(0)
+
+
+@pytest.mark.skipif(not refcmp.have_ref(), reason="oracle/_ref not built")
+def test_live_reference_remaining_modes(pkg, torch_cuda, tmp_path):
+    """the unmodified reference run now at a size / preset that is not in the goldens: every remaining mode bit-exact"""
+    d = str(tmp_path / "dump")
+    refcmp.run_ref("cfg2_small", d, modes=["deep"] + list(refcmp.MODES2), size=(231, 157))
+    dump = refcmp.load_dump(d)
+    res = refcmp.compare2(dump, pkg, verbose=False)
+    for m in refcmp.MODES2:
+        assert res[m]["tex"]["rgba_mismatch_pixels"] == 0, (m, res[m]["tex"])
+        assert res[m]["tex"].get("hit_mismatch_pixels", 0) == 0 and res[m]["tex"].get("norm_mismatch_pixels", 0) == 0
