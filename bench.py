@@ -22,6 +22,10 @@ import sys
 import threading
 import time
 
+# render and consumer streams should not share a hardware queue (the default of 8 connections is spread over torch's
+# pool of 32 streams): must be set before the CUDA context exists
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -114,14 +118,19 @@ def run_reference(a):
     p = oracle.preset(a.workload)
     w, h = a.size if a.size else (p.width, p.height)
     shade = MODES[a.mode] if a.mode else p.shade
-    rays = a.frames * w * h
+    rays = a.frames * w * h * a.spp
+    mode_name = SHADE_NAME[shade]
+    if shade == 7 and a.deep_shadow:
+        mode_name = "deepshadow"        # composed from the reference's own device functions through RenderKernel
+    elif shade == 7 and a.spp > 1:
+        mode_name = "deepspp"
     base = {"metric": "Mrays/s", "unit": "Mrays/s", "impl": "reference", "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"{a.workload} {SHADE_NAME[shade]} {w}x{h}", "frames_per_step": a.frames}}
+            "config": {"workload": f"{a.workload} {mode_name} {w}x{h}", "frames_per_step": a.frames, "spp": a.spp}}
     refdir = os.path.join(ROOT, "oracle", "_ref")
     if os.path.exists(os.path.join(refdir, "ref_harness")):
         cmd = ["./ref_harness", a.workload, "/tmp/ref_bench", "--bench", "--orbit", str(a.frames), "--steps", str(a.steps),
-               "--warmup", str(a.warmup), "--mode", SHADE_NAME[shade], "--size", f"{w}x{h}"]
+               "--warmup", str(a.warmup), "--mode", mode_name, "--size", f"{w}x{h}", "--spp", str(a.spp)]
         r = subprocess.run(cmd, cwd=refdir, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
         if r.returncode == 0:
             j = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
@@ -177,6 +186,11 @@ def main():
     ap.add_argument("--block", default="8x8")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--traversal", default="default", choices=["default", "literal", "packet"])
+    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
+                    help="N>1: peer = render kernels store straight into rank 0's frame over NVLink (default); nccl = packed tiles + gather + assemble")
+    ap.add_argument("--slots", type=int, default=4, help="frames in flight in the peer ring")
+    ap.add_argument("--spp", type=int, default=1)
+    ap.add_argument("--deep-shadow", action="store_true")
     a = ap.parse_args()
     a.size = tuple(int(x) for x in a.size.split("x")) if a.size else None
     a.warmup = max(a.warmup, 3) if a.impl != "reference" else a.warmup
@@ -219,6 +233,7 @@ def main():
     bw, bh = (int(x) for x in a.block.split("x"))
     r.set_block(bw, bh)
     r.set_option(5, {"default": 0, "literal": 1, "packet": 2}[a.traversal])
+    r.set_deep_shadow(a.deep_shadow)
 
     # ---------------- algorithmic bytes per frame (counted render, outside the timed region)
     frame = torch.zeros((h, w, 4), dtype=torch.uint8, device=dev)
@@ -232,19 +247,42 @@ def main():
             counters.append(c)
             bytes_alg.append(B_TRI * c["s_tri"] + B_PT * c["s_pt"] + B_DDA * c["n_dda"] + B_DESC * c["n_desc"] + B_PIX * w * h)
         r.set_counters(False)
+    r.set_spp(a.spp)
+    rays_step *= a.spp
+    bytes_alg = [b * a.spp for b in bytes_alg]
     launches = 0
 
-    def step_resident():
+    ring, consumer = None, None
+    if world > 1 and a.exchange == "peer":
+        ring = mg.PeerFrameRing(r, w, h, a.tile, rank, world, nslots=a.slots)
+        consumer = torch.cuda.Stream(device=dev) if rank == 0 else None
+    tiled = mg.TiledFrame(r, w, h, a.tile, rank, world, dev) if (world > 1 and ring is None) else None
+
+    def step_resident(on_frame=None):
+        """one step = all frames of the orbit; N>1: every rank renders its tiles of every frame.
+        peer exchange: 2 launches per frame and rank (render + done flag), +1 on rank 0 (release flags)."""
         nonlocal launches
         if world == 1:
             for scn in scns:
                 r.render(scn, shade, frame.data_ptr())
                 launches += 1
+        elif ring is not None:
+            for scn in scns:
+                q = ring.submit(scn, shade)
+                launches += 2
+                if rank == 0:
+                    ring.acquire(q, consumer.cuda_stream)
+                    if on_frame is not None:
+                        on_frame(q)
+                    ring.release(q, consumer.cuda_stream)
+                    launches += 1
         else:
             tiled.render_frames(scns, shade)
             launches += len(scns) * (2 if rank == 0 else 1)
 
-    tiled = mg.TiledFrame(r, w, h, a.tile, rank, world, dev) if world > 1 else None
+    def join_consumer():
+        if consumer is not None:
+            torch.cuda.current_stream().wait_stream(consumer)
 
     def sync_all():
         torch.cuda.synchronize()
@@ -254,6 +292,7 @@ def main():
 
     for _ in range(a.warmup):
         step_resident()
+    join_consumer()
     sync_all()
     clocks = ClockSampler(local)
     if rank == 0:
@@ -264,6 +303,7 @@ def main():
     e0.record()
     for _ in range(a.steps):
         step_resident()
+    join_consumer()
     e1.record()
     sync_all()
     ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
@@ -279,8 +319,9 @@ def main():
         sync_all()
         r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         r0.record()
+        scratch = torch.zeros((mg.slots_per_rank(w, h, a.tile, world), a.tile, a.tile, 4), dtype=torch.uint8, device=dev)
         for scn in scns:
-            r.render_tiles(scn, shade, tiled.packed[0].data_ptr(), a.tile, rank, world)
+            r.render_tiles(scn, shade, scratch.data_ptr(), a.tile, rank, world)
         r1.record()
         torch.cuda.synchronize()
         mine = torch.tensor([r0.elapsed_time(r1)], dtype=torch.float64, device=dev)
@@ -294,7 +335,8 @@ def main():
         ref = torch.zeros_like(frame)
         r.render(scns[-1], shade, ref.data_ptr())
         r.sync()
-        frame_ok = bool(torch.equal(ref, tiled.frame))
+        last = ring.frame_tensor(ring.seq, torch, dev) if ring is not None else tiled.frame
+        frame_ok = bool(torch.equal(ref, last))
 
     # ---------------- e2e through the reference-facing API with host buffers (rank-local at N=1; tiled at N>1)
     e2e = None
@@ -316,6 +358,8 @@ def main():
         v.set_option(1, 0 if a.sampler == "tex" else 1)
         v.set_option(2, bw); v.set_option(3, bh)
         v.set_option(5, {"default": 0, "literal": 1, "packet": 2}[a.traversal])
+        v.set_option(7, a.spp)
+        v.set_option(8, 1 if a.deep_shadow else 0)
 
         def step_e2e():
             for j in range(a.frames):
@@ -336,12 +380,22 @@ def main():
                "api": "VolumeGVDB mirror: SetCamera + Render + ReadRenderBuf into pinned host memory"}
         v.close()
     else:
-        def to_host(j, fr):
-            host.copy_(fr, non_blocking=True)                   # D2H of the assembled frame, stream-ordered
-            torch.cuda.current_stream().synchronize()           # the caller owns the host frame now
+        if ring is not None:
+            def to_host(q):
+                with torch.cuda.stream(consumer):               # D2H of the finished frame behind the acquire, on the consumer stream
+                    host.copy_(ring.frame_tensor(q, torch, dev), non_blocking=True)
 
-        def step_e2e():
-            tiled.render_frames(scns, shade, on_frame=to_host)
+            def step_e2e():
+                step_resident(on_frame=to_host if rank == 0 else None)
+                if rank == 0:
+                    consumer.synchronize()                      # the caller owns the host frames of this step now
+        else:
+            def to_host(j, fr):
+                host.copy_(fr, non_blocking=True)                   # D2H of the assembled frame, stream-ordered
+                torch.cuda.current_stream().synchronize()           # the caller owns the host frame now
+
+            def step_e2e():
+                tiled.render_frames(scns, shade, on_frame=to_host)
         for _ in range(2):
             step_e2e()
         sync_all()
@@ -354,7 +408,8 @@ def main():
         dt = float(dt.item())
         e2e = {"value": rays_step * a.steps / dt / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": a.frames * 416 * world,
                "d2h_bytes_per_step": a.frames * w * h * 4, "ms_per_frame": dt / a.steps / a.frames * 1e3,
-               "api": "gvdbx_render_tiles per rank + NCCL gather + gvdbx_assemble_tiles + D2H to pinned host on rank 0"}
+               "api": ("gvdbx_render_tiles_direct per rank into rank 0's frame ring over NVLink + D2H to pinned host on rank 0" if ring is not None
+                       else "gvdbx_render_tiles per rank + NCCL gather + gvdbx_assemble_tiles + D2H to pinned host on rank 0")}
 
     if rank != 0:
         if world > 1:
@@ -403,9 +458,10 @@ def main():
     out = {"metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
            "ms_per_step": ms_total / a.steps, "ms_per_frame": ms_total / a.steps / a.frames, "higher_is_better": True,
            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-           "config": {"workload": f"{a.workload} {SHADE_NAME[shade]} {w}x{h}", "frames_per_step": a.frames, "bricks": timing["bricks"],
+           "config": {"workload": f"{a.workload} {SHADE_NAME[shade]}{'+shadow' if a.deep_shadow else ''} {w}x{h}", "frames_per_step": a.frames, "bricks": timing["bricks"],
                       "atlas_mb": vol["atlas"].nbytes / 1e6, "sampler": a.sampler, "block": a.block, "traversal": a.traversal,
-                      "parallelism": f"image tiles {a.tile}x{a.tile} round-robin over {world} GPU(s), volume replicated" if world > 1 else "single GPU",
+                      "parallelism": (f"image tiles {a.tile}x{a.tile} round-robin over {world} GPU(s), volume replicated, exchange={a.exchange}"
+                                      if world > 1 else "single GPU"), "spp": a.spp, "deep_shadow": bool(a.deep_shadow),
                       "l2_policy": "inputs larger than L2 (atlas %.0f MB vs 126 MB L2); camera changes every frame" % (vol["atlas"].nbytes / 1e6)},
            "e2e": e2e, "gpu_launches": launches_timed, "roofline": roofline, "clocks": clk, "import_s": import_s,
            "scene_gen_s": timing["scene_gen_s"]}

@@ -24,7 +24,8 @@ EXPORTED_SYMBOLS = [
     "gvdbx_import_atlas_array", "gvdbx_import_atlas_host", "gvdbx_set_transfer",
     "gvdbx_render", "gvdbx_render_tiles", "gvdbx_tiles_per_rank", "gvdbx_assemble_tiles",
     "gvdbx_render_debug", "gvdbx_raytrace", "gvdbx_read_buffer", "gvdbx_sync", "gvdbx_get_counters",
-    "gvdbx_sample_points",
+    "gvdbx_sample_points", "gvdbx_render_tiles_direct", "gvdbx_peer_alloc", "gvdbx_peer_free", "gvdbx_peer_open",
+    "gvdbx_peer_close", "gvdbx_stream_signal", "gvdbx_stream_signal_add", "gvdbx_stream_signal_many", "gvdbx_stream_wait", "gvdbx_set_stream",
 ]
 
 
@@ -77,6 +78,16 @@ def lib():
     L.gvdbx_sync.argtypes = [vp]
     L.gvdbx_get_counters.argtypes = [vp, C.POINTER(Counters)]
     L.gvdbx_sample_points.argtypes = [vp, i32, u64, i32, u64, u64]
+    L.gvdbx_render_tiles_direct.argtypes = [vp, vp, i32, i32, u64, i32, i32, i32]
+    L.gvdbx_peer_alloc.argtypes = [vp, C.c_size_t, C.POINTER(u64), vp]
+    L.gvdbx_peer_free.argtypes = [vp, u64]
+    L.gvdbx_peer_open.argtypes = [vp, vp, C.POINTER(u64)]
+    L.gvdbx_peer_close.argtypes = [vp, u64]
+    L.gvdbx_stream_signal.argtypes = [vp, vp, u64, C.c_uint32]
+    L.gvdbx_stream_wait.argtypes = [vp, vp, u64, C.c_uint32]
+    L.gvdbx_stream_signal_add.argtypes = [vp, vp, u64, C.c_uint32]
+    L.gvdbx_stream_signal_many.argtypes = [vp, vp, C.POINTER(u64), i32, C.c_uint32]
+    L.gvdbx_set_stream.argtypes = [vp, vp]
     for s in EXPORTED_SYMBOLS:
         if s != "gvdbx_last_error":
             getattr(L, s).restype = i32
@@ -198,6 +209,48 @@ class Renderer:
         p, keep = _buf(scninfo)
         self._ck(self._L.gvdbx_render_tiles(self._h, p, shade, chan, int(packed_ptr), tile_size, rank, nranks),
                  "gvdbx_render_tiles")
+
+    def render_tiles_direct(self, scninfo, shade, frame_ptr, tile_size, rank, nranks, chan=0):
+        """this rank's tiles straight into a row-major frame (local or peer-mapped)"""
+        p, keep = _buf(scninfo)
+        self._ck(self._L.gvdbx_render_tiles_direct(self._h, p, shade, chan, int(frame_ptr), tile_size, rank, nranks),
+                 "gvdbx_render_tiles_direct")
+
+    # --- peer memory + stream-ordered flags (multi-GPU without a gather)
+    def peer_alloc(self, nbytes):
+        d = C.c_uint64()
+        hd = (C.c_uint8 * 64)()
+        self._ck(self._L.gvdbx_peer_alloc(self._h, nbytes, C.byref(d), hd), "gvdbx_peer_alloc")
+        return int(d.value), bytes(hd)
+
+    def peer_free(self, dptr):
+        self._ck(self._L.gvdbx_peer_free(self._h, int(dptr)), "gvdbx_peer_free")
+
+    def peer_open(self, handle):
+        d = C.c_uint64()
+        p, keep = _buf(handle)
+        self._ck(self._L.gvdbx_peer_open(self._h, p, C.byref(d)), "gvdbx_peer_open")
+        return int(d.value)
+
+    def peer_close(self, dptr):
+        self._ck(self._L.gvdbx_peer_close(self._h, int(dptr)), "gvdbx_peer_close")
+
+    def stream_signal(self, flag_ptr, value, stream=None):
+        self._ck(self._L.gvdbx_stream_signal(self._h, C.c_void_p(stream or 0), int(flag_ptr), int(value) & 0xFFFFFFFF), "gvdbx_stream_signal")
+
+    def stream_signal_add(self, flag_ptr, inc, stream=None):
+        self._ck(self._L.gvdbx_stream_signal_add(self._h, C.c_void_p(stream or 0), int(flag_ptr), int(inc)), "gvdbx_stream_signal_add")
+
+    def stream_signal_many(self, flag_ptrs, value, stream=None):
+        a = (C.c_uint64 * len(flag_ptrs))(*[int(p) for p in flag_ptrs])
+        self._ck(self._L.gvdbx_stream_signal_many(self._h, C.c_void_p(stream or 0), a, len(flag_ptrs), int(value) & 0xFFFFFFFF),
+                 "gvdbx_stream_signal_many")
+
+    def stream_wait(self, flag_ptr, value, stream=None):
+        self._ck(self._L.gvdbx_stream_wait(self._h, C.c_void_p(stream or 0), int(flag_ptr), int(value) & 0xFFFFFFFF), "gvdbx_stream_wait")
+
+    def set_stream(self, stream):
+        self._ck(self._L.gvdbx_set_stream(self._h, C.c_void_p(stream or 0)), "gvdbx_set_stream")
 
     def tiles_per_rank(self, width, height, tile_size, nranks):
         return self._L.gvdbx_tiles_per_rank(width, height, tile_size, nranks)

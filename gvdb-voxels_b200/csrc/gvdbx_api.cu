@@ -17,7 +17,7 @@ struct gvdbx_ctx {
     cudaStream_t stream = nullptr;
     std::string  err;
     // options
-    int sampler = GX_SAMPLER_TEX, block_w = 8, block_h = 8, count = 0, literal = 0, spp = 1, deep_shadow = 0;
+    int sampler = GX_SAMPLER_TEX, block_w = 8, block_h = 8, count = 0, literal = 0, spp = 1, deep_shadow = 0, memops = 0;
     // topology
     bool       have_topo = false, uniform3 = false;
     GxVDBInfo  vdb;
@@ -122,6 +122,7 @@ extern "C" int gvdbx_set_option(gvdbx_t* h, int option, int value)
     case GVDBX_OPT_CULL: h->cull = value ? 1 : 0; break;
     case GVDBX_OPT_SPP: if (value < 1 || value > 64) return gx_fail(h, GVDBX_E_ARG, "spp must be 1..64"); h->spp = value; break;
     case GVDBX_OPT_DEEP_SHADOW: h->deep_shadow = value ? 1 : 0; break;
+    case GVDBX_OPT_STREAM_MEMOPS: h->memops = value ? 1 : 0; break;
     case GVDBX_OPT_TRAVERSAL: if (value < 0 || value > 2) return gx_fail(h, GVDBX_E_ARG, "traversal must be 0, 1 or 2"); h->literal = value; break;
     default: return gx_fail(h, GVDBX_E_ARG, "unknown option");
     }
@@ -495,6 +496,149 @@ extern "C" int gvdbx_render_tiles(gvdbx_t* h, const void* scninfo, int shade_mod
     dim3 block(h->block_w, h->block_h, 1);
     dim3 grid((tile_size / h->block_w) * (tile_size / h->block_h), slots, 1);
     k<<<grid, block, 0, h->stream>>>(P);
+    GX_CUDA(h, cudaGetLastError());
+    return GVDBX_OK;
+}
+
+// Direct mode: the same tile list, but every pixel goes straight to its place in a row-major frame.  `frame_d` may be a
+// peer GPU's buffer opened with gvdbx_peer_open: the stores then travel over NVLink from inside the render kernel and no
+// gather / assemble step exists.
+extern "C" int gvdbx_render_tiles_direct(gvdbx_t* h, const void* scninfo, int shade_mode, int chan, uint64_t frame_d,
+                                         int tile_size, int rank, int nranks)
+{
+    if (!h) return GVDBX_E_ARG;
+    GX_CUDA(h, cudaSetDevice(h->device));
+    GxParams P; int mode = 0;
+    int rc = gx_fill_params(h, scninfo, shade_mode, chan, P, mode);
+    if (rc) return rc;
+    if (!frame_d || nranks <= 0 || rank < 0 || rank >= nranks) return gx_fail(h, GVDBX_E_ARG, "rank/nranks/buffer");
+    if (tile_size <= 0 || tile_size % h->block_w || tile_size % h->block_h)
+        return gx_fail(h, GVDBX_E_ARG, "tile_size must be a multiple of the CTA tile");
+    P.out = (uchar4*)frame_d;
+    P.out_stride = P.width;                             // > 0 selects direct addressing in the tile-list kernels
+    P.tile_size = tile_size;
+    P.tiles_x = (P.width + tile_size - 1) / tile_size;
+    P.ntiles = P.tiles_x * ((P.height + tile_size - 1) / tile_size);
+    P.rank = rank; P.nranks = nranks;
+    const int slots = (P.ntiles + nranks - 1) / nranks;
+    gx_kernel_t k = gx_pick(mode, h->sampler, GX_FLAG_TILES | (h->spp > 1 ? GX_FLAG_SPP : 0), h->uniform3);
+    if (!k) return gx_fail(h, GVDBX_E_UNSUPPORTED, "no kernel variant for this mode / sampler combination");
+    dim3 block(h->block_w, h->block_h, 1);
+    dim3 grid((tile_size / h->block_w) * (tile_size / h->block_h), slots, 1);
+    k<<<grid, block, 0, h->stream>>>(P);
+    GX_CUDA(h, cudaGetLastError());
+    return GVDBX_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ peer memory + flags
+extern "C" int gvdbx_peer_alloc(gvdbx_t* h, size_t bytes, uint64_t* dptr, void* handle64)
+{
+    if (!h || !dptr || !handle64 || bytes == 0) return GVDBX_E_ARG;
+    static_assert(sizeof(cudaIpcMemHandle_t) == GVDBX_IPC_HANDLE_BYTES, "IPC handle size");
+    GX_CUDA(h, cudaSetDevice(h->device));
+    void* p = nullptr;
+    GX_CUDA(h, cudaMalloc(&p, bytes));
+    GX_CUDA(h, cudaMemset(p, 0, bytes));
+    cudaIpcMemHandle_t hd;
+    cudaError_t e = cudaIpcGetMemHandle(&hd, p);
+    if (e != cudaSuccess) { cudaFree(p); h->err = std::string("cudaIpcGetMemHandle: ") + cudaGetErrorString(e); return GVDBX_E_CUDA; }
+    memcpy(handle64, &hd, sizeof hd);
+    *dptr = (uint64_t)p;
+    return GVDBX_OK;
+}
+extern "C" int gvdbx_peer_free(gvdbx_t* h, uint64_t dptr)
+{
+    if (!h || !dptr) return GVDBX_E_ARG;
+    GX_CUDA(h, cudaSetDevice(h->device));
+    GX_CUDA(h, cudaFree((void*)dptr));
+    return GVDBX_OK;
+}
+extern "C" int gvdbx_peer_open(gvdbx_t* h, const void* handle64, uint64_t* dptr)
+{
+    if (!h || !dptr || !handle64) return GVDBX_E_ARG;
+    GX_CUDA(h, cudaSetDevice(h->device));
+    cudaIpcMemHandle_t hd;
+    memcpy(&hd, handle64, sizeof hd);
+    void* p = nullptr;
+    GX_CUDA(h, cudaIpcOpenMemHandle(&p, hd, cudaIpcMemLazyEnablePeerAccess));
+    *dptr = (uint64_t)p;
+    return GVDBX_OK;
+}
+extern "C" int gvdbx_peer_close(gvdbx_t* h, uint64_t dptr)
+{
+    if (!h || !dptr) return GVDBX_E_ARG;
+    GX_CUDA(h, cudaSetDevice(h->device));
+    GX_CUDA(h, cudaIpcCloseMemHandle((void*)dptr));
+    return GVDBX_OK;
+}
+
+extern "C" int gvdbx_set_stream(gvdbx_t* h, void* cuda_stream)
+{
+    if (!h) return GVDBX_E_ARG;
+    h->stream = (cudaStream_t)cuda_stream;
+    return GVDBX_OK;
+}
+
+// stream-ordered flag write: everything enqueued before it on `stream` (incl. stores to peer memory) is complete and
+// visible system-wide before the flag changes
+extern "C" int gvdbx_stream_signal(gvdbx_t* h, void* cuda_stream, uint64_t flag_d, uint32_t value)
+{
+    if (!h || !flag_d) return GVDBX_E_ARG;
+    GX_CUDA(h, cudaSetDevice(h->device));
+    cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : h->stream;
+    gx_signal_kernel<<<1, 1, 0, st>>>((unsigned int*)flag_d, value);
+    GX_CUDA(h, cudaGetLastError());
+    return GVDBX_OK;
+}
+
+// same, but adds `inc` to a counter (several producers share one counter: the waiter targets producers * uses)
+extern "C" int gvdbx_stream_signal_add(gvdbx_t* h, void* cuda_stream, uint64_t flag_d, uint32_t inc)
+{
+    if (!h || !flag_d) return GVDBX_E_ARG;
+    GX_CUDA(h, cudaSetDevice(h->device));
+    cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : h->stream;
+    gx_signal_add_kernel<<<1, 1, 0, st>>>((unsigned int*)flag_d, inc);
+    GX_CUDA(h, cudaGetLastError());
+    return GVDBX_OK;
+}
+// same value to up to 16 flags (one per peer) with one launch
+extern "C" int gvdbx_stream_signal_many(gvdbx_t* h, void* cuda_stream, const uint64_t* flags_d, int n, uint32_t value)
+{
+    if (!h || !flags_d || n <= 0 || n > 16) return GVDBX_E_ARG;
+    GX_CUDA(h, cudaSetDevice(h->device));
+    cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : h->stream;
+    GxFlagList L;
+    for (int i = 0; i < 16; i++) L.p[i] = i < n ? (unsigned int*)flags_d[i] : nullptr;
+    gx_signal_many_kernel<<<1, 16, 0, st>>>(L, n, value);
+    GX_CUDA(h, cudaGetLastError());
+    return GVDBX_OK;
+}
+
+// stream-ordered wait until *flag >= value (flag in LOCAL device memory).  Default: a one-thread polling kernel that gives
+// up after ~20 s (flag[1] = 0xDEAD) so that a lost peer or a mis-ordered submission cannot wedge the GPU.  With
+// GVDBX_OPT_STREAM_MEMOPS the driver's cuStreamWaitValue32 is used instead (no SM involved, but unbounded).
+// Submission-order rule either way: when waiter and signaller are streams of the SAME process, enqueue the signal first —
+// streams can share a hardware queue, where a wait enqueued ahead of its signal would never be passed.
+typedef int (*gx_cuStreamWaitValue32_t)(cudaStream_t, unsigned long long, unsigned int, unsigned int);
+extern "C" int gvdbx_stream_wait(gvdbx_t* h, void* cuda_stream, uint64_t flag_d, uint32_t value)
+{
+    if (!h || !flag_d) return GVDBX_E_ARG;
+    GX_CUDA(h, cudaSetDevice(h->device));
+    cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : h->stream;
+    if (h->memops) {
+        static gx_cuStreamWaitValue32_t fn = nullptr;
+        static bool looked = false;
+        if (!looked) {
+            looked = true;
+            void* p = nullptr;
+            cudaDriverEntryPointQueryResult qr;
+            if (cudaGetDriverEntryPoint("cuStreamWaitValue32", &p, cudaEnableDefault, &qr) == cudaSuccess && qr == cudaDriverEntryPointSuccess)
+                fn = (gx_cuStreamWaitValue32_t)p;
+            cudaGetLastError();
+        }
+        if (fn && fn(st, (unsigned long long)flag_d, value, 0x0 /* CU_STREAM_WAIT_VALUE_GEQ */) == 0) return GVDBX_OK;
+    }
+    gx_wait_kernel<<<1, 1, 0, st>>>((unsigned int*)flag_d, value);
     GX_CUDA(h, cudaGetLastError());
     return GVDBX_OK;
 }

@@ -115,3 +115,35 @@ __global__ void gx_sample_points_kernel(GxParams P, const float* __restrict__ xy
     s.enter(L);
     out_lin[i] = s.tri(x, y, z);
 }
+
+// ------------------------------------------------------------------------------------------------ cross-GPU flags
+// one thread: release-store of a sequence number (the frame's pixels were stored by kernels earlier in the stream)
+__global__ void gx_signal_kernel(unsigned int* flag, unsigned int value)
+{
+    __threadfence_system();
+    asm volatile("st.release.sys.global.u32 [%0], %1;" :: "l"(flag), "r"(value) : "memory");
+}
+__global__ void gx_signal_add_kernel(unsigned int* flag, unsigned int inc)
+{
+    __threadfence_system();
+    asm volatile("red.release.sys.global.add.u32 [%0], %1;" :: "l"(flag), "r"(inc) : "memory");
+}
+struct GxFlagList { unsigned int* p[16]; };
+__global__ void gx_signal_many_kernel(GxFlagList L, int n, unsigned int value)
+{
+    __threadfence_system();
+    if (threadIdx.x < n) asm volatile("st.release.sys.global.u32 [%0], %1;" :: "l"(L.p[threadIdx.x]), "r"(value) : "memory");
+}
+// one thread: polls a LOCAL flag until it reaches `value`; bounded (~20 s) so that a lost peer cannot wedge the GPU —
+// on timeout flag[1] is set to 0xDEAD and the stream continues
+__global__ void gx_wait_kernel(unsigned int* flag, unsigned int value)
+{
+    const long long t0 = clock64();
+    for (;;) {
+        unsigned int v;
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+        if (int(v - value) >= 0) return;
+        __nanosleep(256);
+        if (clock64() - t0 > 40000000000ll) { flag[1] = 0xDEADu; return; }
+    }
+}

@@ -60,6 +60,7 @@ extern "C" {
                                    order, scaled by 1/n, packed once (BASELINE.json config 5: 4 spp) */
 #define GVDBX_OPT_DEEP_SHADOW 8 /* 1 = SHADE_VOLUME casts one shadow march (rayShadowBrick, kernels/cuda_gvdb_raycast.cuh:445-463) from
                                    the first sample towards the light and darkens the accumulated colour (BASELINE.json config 4) */
+#define GVDBX_OPT_STREAM_MEMOPS 9 /* 1 = gvdbx_stream_wait uses cuStreamWaitValue32 (front-end wait, unbounded) instead of the bounded polling kernel */
 #define GVDBX_OPT_TRAVERSAL 5   /* 0 = default (four-samples-per-round brick marchers), 1 = reference-shaped loops, one sample at a time (A/B),
                                    2 = vote-converged two-phase packet traversal (A/B) */
 
@@ -115,6 +116,11 @@ int  gvdbx_render(gvdbx_t* h, const void* scninfo, int shade_mode, int chan, uin
  * [nranks][slots][tile] buffer back into a row-major frame. */
 int  gvdbx_render_tiles(gvdbx_t* h, const void* scninfo, int shade_mode, int chan, uint64_t packed_d,
                         int tile_size, int rank, int nranks);
+/* Direct variant: the same tile list, but each pixel is stored at its place in the row-major frame `frame_d`
+ * (width*height RGBA8).  `frame_d` may be a buffer of ANOTHER GPU opened with gvdbx_peer_open: the stores then go over
+ * NVLink from inside the render kernel — render and "gather" are one kernel, nothing is packed or assembled. */
+int  gvdbx_render_tiles_direct(gvdbx_t* h, const void* scninfo, int shade_mode, int chan, uint64_t frame_d,
+                               int tile_size, int rank, int nranks);
 int  gvdbx_tiles_per_rank(int width, int height, int tile_size, int nranks);
 int  gvdbx_assemble_tiles(gvdbx_t* h, uint64_t gathered_d, uint64_t frame_d, int width, int height, int tile_size, int nranks);
 
@@ -128,6 +134,26 @@ int  gvdbx_render_debug(gvdbx_t* h, const void* scninfo, int shade_mode, int cha
  * pndx@56; src/gvdb_volume_gvdb.h:300-308) in DEVICE memory with the trilinear surface brick function; writes hit
  * (pulled back by `bias` along the ray) and normal in place, hit = (NOHIT,NOHIT,NOHIT) on a miss. */
 int  gvdbx_raytrace(gvdbx_t* h, const void* scninfo, int chan, uint64_t rays_d, int num_rays, float bias);
+
+/* Peer memory for one-process-per-GPU rendering into a frame owned by one rank (CUDA IPC; both GPUs in one NVLink /
+ * NVSwitch domain).  gvdbx_peer_alloc: zero-filled device buffer + 64-byte handle to ship to the other processes;
+ * gvdbx_peer_open: map another process's buffer (peer access is enabled on first use). */
+#define GVDBX_IPC_HANDLE_BYTES 64
+int  gvdbx_peer_alloc(gvdbx_t* h, size_t bytes, uint64_t* dptr, void* handle64);
+int  gvdbx_peer_free(gvdbx_t* h, uint64_t dptr);
+int  gvdbx_peer_open(gvdbx_t* h, const void* handle64, uint64_t* dptr);
+int  gvdbx_peer_close(gvdbx_t* h, uint64_t dptr);
+/* Stream-ordered 32-bit sequence flags (cuda_stream NULL = the context's stream).  signal: after everything enqueued
+ * before it has completed, store `value` to *flag_d (local or peer memory) with system-scope release.  wait: hold back
+ * everything enqueued after it until *flag_d >= value (flag in LOCAL memory; 8 bytes: [0] sequence, [1] timeout mark:
+ * the default polling kernel gives up after ~20 s and stores 0xDEAD there).  When waiter and signaller are streams of
+ * the same process, enqueue the signal before the wait (streams may share a hardware queue). */
+int  gvdbx_stream_signal(gvdbx_t* h, void* cuda_stream, uint64_t flag_d, uint32_t value);
+int  gvdbx_stream_signal_add(gvdbx_t* h, void* cuda_stream, uint64_t flag_d, uint32_t inc);      /* *flag_d += inc (atomic, release) */
+int  gvdbx_stream_signal_many(gvdbx_t* h, void* cuda_stream, const uint64_t* flags_d, int n, uint32_t value); /* n <= 16 flags, one launch */
+int  gvdbx_stream_wait(gvdbx_t* h, void* cuda_stream, uint64_t flag_d, uint32_t value);
+/* Switch the stream all later calls of this context enqueue on (e.g. to alternate frames between two streams). */
+int  gvdbx_set_stream(gvdbx_t* h, void* cuda_stream);
 
 /* ReadRenderBuf: device -> host copy of `bytes`, synchronises the stream. */
 int  gvdbx_read_buffer(gvdbx_t* h, uint64_t buf_d, void* host, size_t bytes);

@@ -458,3 +458,92 @@ def test_live_reference_remaining_modes(pkg, torch_cuda, tmp_path):
     for m in refcmp.MODES2:
         assert res[m]["tex"]["rgba_mismatch_pixels"] == 0, (m, res[m]["tex"])
         assert res[m]["tex"].get("hit_mismatch_pixels", 0) == 0 and res[m]["tex"].get("norm_mismatch_pixels", 0) == 0
+
+
+# ------------------------------------------------------------------------------------------------ peer frame ring (one GPU)
+def test_direct_tiles_and_peer_ring_single_process(scenes, torch_cuda, pkg, ora):
+    """Three "ranks" in one process on one GPU (raw pointers instead of IPC handles): every rank's tile-list kernel stores
+    straight into the ring slot, flags order producers and consumer, a slot is reused only after its release.  Every
+    delivered frame equals the single-kernel render of the same camera."""
+    torch = torch_cuda
+    from gvdb_voxels_b200 import multigpu as mg
+    g = golden("cfg3_small")
+    p, vol, r = scenes("cfg3_small")
+    w, h = int(g["width"]), int(g["height"])
+    r.set_sampler(0)
+    world, ts, nslots, nframes = 3, 32, 2, 7
+    scns = [ora.scninfo_for(pkg, p, shade=0, cam_angs=(p.cam_angs[0] + 40.0 * j, p.cam_angs[1], p.cam_angs[2]))[0] for j in range(nframes)]
+    want = [_render(torch, r, s, 0, w, h, 0) for s in scns]
+    assert np.array_equal(want[0], g["rgba_voxel"])
+    # direct mode alone: all ranks into one local frame
+    frame = torch.zeros((h, w, 4), dtype=torch.uint8, device="cuda")
+    for rank in range(world):
+        r.render_tiles_direct(scns[0], 0, frame.data_ptr(), ts, rank, world)
+    r.sync()
+    assert np.array_equal(frame.cpu().numpy(), want[0])
+    # the ring: the "ranks" share one process, so the bootstrap exchange is a list
+    box = []
+
+    def make(rank):
+        def exchange(obj):
+            box.append(obj)
+            return box if rank == 0 else None
+        return exchange
+    # rank 0 must be built last here (it needs everybody's released flag); others resolve rank 0's ring lazily below
+    rings = {}
+    pending = []
+    for rank in (1, 2):
+        rel_ptr, rel_handle = r.peer_alloc(256)
+        pending.append({"rank": rank, "pid": __import__("os").getpid(), "released": rel_handle, "released_ptr": rel_ptr, "ring": None, "ring_ptr": None})
+    rings[0] = mg.PeerFrameRing(r, w, h, ts, 0, world, nslots=nslots, exchange=lambda obj: [obj] + pending)
+    entry0 = {"rank": 0, "pid": __import__("os").getpid(), "released": None, "released_ptr": rings[0].released_local, "ring": None, "ring_ptr": rings[0].ring_base}
+    for rank in (1, 2):
+        rings[rank] = mg.PeerFrameRing(r, w, h, ts, rank, world, nslots=nslots, exchange=lambda obj: [entry0] + pending)
+        rings[rank].released_local = pending[rank - 1]["released_ptr"]      # the flag rank 0 was told about
+    consumer = torch.cuda.Stream()
+    got = []
+    for j in range(nframes):
+        for rank in (2, 0, 1):                       # any submission order within a frame
+            q = rings[rank].submit(scns[j], 0)
+        rings[0].acquire(q, consumer.cuda_stream)
+        with torch.cuda.stream(consumer):
+            got.append(rings[0].frame_tensor(q, torch, "cuda").clone())
+        rings[0].release(q, consumer.cuda_stream)
+    consumer.synchronize()
+    r.sync()
+    for j in range(nframes):
+        assert np.array_equal(got[j].cpu().numpy(), want[j]), j
+    # no wait ran into its timeout
+    flags = torch.as_tensor(mg.CudaBuffer(rings[0].done_ptr[0], (2,), "<u4"), device="cuda").cpu().numpy()
+    assert flags[1] != 0xDEAD
+    for k in (1, 2, 0):
+        rings[k].close()
+    for e in pending:
+        r.peer_free(e["released_ptr"])
+
+
+def test_stream_flags_order_two_streams(scenes, torch_cuda, pkg):
+    """gvdbx_stream_wait holds a stream until another stream's gvdbx_stream_signal / _signal_add reaches the value.
+    (Signals are enqueued first: two streams of one process may share a hardware queue.)"""
+    torch = torch_cuda
+    p, vol, r = scenes("cfg1_tiny")
+    ptr, _ = r.peer_alloc(256)
+    a, b = torch.cuda.Stream(), torch.cuda.Stream()
+    x = torch.zeros(1 << 20, device="cuda")
+    m = torch.randn(2048, 2048, device="cuda")
+    torch.cuda.synchronize()
+    with torch.cuda.stream(b):
+        for _ in range(20):                          # keeps stream b busy for a while before the fill
+            m = (m @ m).clamp_(-1, 1)
+        x.fill_(41.0)
+    r.stream_signal(ptr, 2, b.cuda_stream)
+    r.stream_signal_add(ptr, 1, b.cuda_stream)       # 2 + 1 = 3 releases stream a
+    r.stream_wait(ptr, 3, a.cuda_stream)
+    with torch.cuda.stream(a):
+        y = x + 1                                    # must see b's fill
+    a.synchronize()
+    assert float(y.min()) == 42.0 and float(y.max()) == 42.0
+    flags = torch.as_tensor(__import__("gvdb_voxels_b200").multigpu.CudaBuffer(ptr, (2,), "<u4"), device="cuda").cpu().numpy()
+    assert flags[0] == 3 and flags[1] == 0
+    b.synchronize()
+    r.peer_free(ptr)
