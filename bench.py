@@ -189,6 +189,7 @@ def main():
     ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
                     help="N>1: peer = render kernels store straight into rank 0's frame over NVLink (default); nccl = packed tiles + gather + assemble")
     ap.add_argument("--slots", type=int, default=4, help="frames in flight in the peer ring")
+    ap.add_argument("--lanes", type=int, default=4, help="frame lanes: consecutive frames alternate between this many internal streams (0 = one stream)")
     ap.add_argument("--spp", type=int, default=1)
     ap.add_argument("--deep-shadow", action="store_true")
     a = ap.parse_args()
@@ -236,7 +237,9 @@ def main():
     r.set_deep_shadow(a.deep_shadow)
 
     # ---------------- algorithmic bytes per frame (counted render, outside the timed region)
-    frame = torch.zeros((h, w, 4), dtype=torch.uint8, device=dev)
+    nbuf = max(1, a.lanes)
+    frames_d = [torch.zeros((h, w, 4), dtype=torch.uint8, device=dev) for _ in range(nbuf)]     # one output frame per lane
+    frame = frames_d[0]
     bytes_alg = []
     counters = []
     if rank == 0:          # counted with the reference's own semantics (no brick culling): units of the ALGORITHM
@@ -248,6 +251,7 @@ def main():
             bytes_alg.append(B_TRI * c["s_tri"] + B_PT * c["s_pt"] + B_DDA * c["n_dda"] + B_DESC * c["n_desc"] + B_PIX * w * h)
         r.set_counters(False)
     r.set_spp(a.spp)
+    r.lanes(a.lanes)
     rays_step *= a.spp
     bytes_alg = [b * a.spp for b in bytes_alg]
     launches = 0
@@ -262,9 +266,11 @@ def main():
         """one step = all frames of the orbit; N>1: every rank renders its tiles of every frame.
         peer exchange: 2 launches per frame and rank (render + done flag), +1 on rank 0 (release flags)."""
         nonlocal launches
+        r.lanes_fork()
         if world == 1:
-            for scn in scns:
-                r.render(scn, shade, frame.data_ptr())
+            for j, scn in enumerate(scns):
+                r.lane_select(j % nbuf if a.lanes else -1)
+                r.render(scn, shade, frames_d[j % nbuf].data_ptr())
                 launches += 1
         elif ring is not None:
             for scn in scns:
@@ -279,6 +285,7 @@ def main():
         else:
             tiled.render_frames(scns, shade)
             launches += len(scns) * (2 if rank == 0 else 1)
+        r.lanes_join()
 
     def join_consumer():
         if consumer is not None:
@@ -333,6 +340,7 @@ def main():
     frame_ok = None
     if world > 1 and rank == 0:
         ref = torch.zeros_like(frame)
+        r.lane_select(-1)
         r.render(scns[-1], shade, ref.data_ptr())
         r.sync()
         last = ring.frame_tensor(ring.seq, torch, dev) if ring is not None else tiled.frame
@@ -354,7 +362,11 @@ def main():
             v.LinearTransferFunc(0.75, 1.00, (.2, .2, 0.2, 0.1), (0, 0, 0, 0.0))
         v.CommitTransferFunc()
         v.SetLight(list(p.light_angs), list(p.light_target), p.light_dist)
-        v.AddRenderBuf(0, w, h, 4)
+        hosts = [host] + [torch.empty((h, w, 4), dtype=torch.uint8).pin_memory() for _ in range(nbuf - 1)]
+        hosts_np = [t.numpy() for t in hosts]
+        for k in range(nbuf):
+            v.AddRenderBuf(k, w, h, 4)
+        v.SetRenderLanes(a.lanes)
         v.set_option(1, 0 if a.sampler == "tex" else 1)
         v.set_option(2, bw); v.set_option(3, bh)
         v.set_option(5, {"default": 0, "literal": 1, "packet": 2}[a.traversal])
@@ -362,11 +374,18 @@ def main():
         v.set_option(8, 1 if a.deep_shadow else 0)
 
         def step_e2e():
+            # render buffer k = frame lane k: frame j renders into buffer j % nbuf while earlier frames are still being
+            # rendered / copied; a host frame is handed to the caller (SyncRenderBuf) before its buffer is reused
             for j in range(a.frames):
+                k = j % nbuf
+                if j >= nbuf:
+                    v.SyncRenderBuf(k)
                 v.SetCamera(p.fov, (p.cam_angs[0] + 360.0 * j / a.frames, p.cam_angs[1], p.cam_angs[2]), list(p.cam_target), p.cam_dist)
                 v.SetRes(w, h)
-                v.Render(shade, 0, 0)               # PrepareRender: 416-byte ScnInfo host -> device with the launch
-                v.ReadRenderBuf(0, host_np)         # device -> pinned host, synchronises
+                v.Render(shade, 0, k)                       # PrepareRender: 416-byte ScnInfo host -> device with the launch
+                v.ReadRenderBufAsync(k, hosts_np[k])        # device -> pinned host behind the kernel, on the buffer's lane
+            for k in range(min(nbuf, a.frames)):
+                v.SyncRenderBuf(k)
         for _ in range(2):
             step_e2e()
         torch.cuda.synchronize()
@@ -377,13 +396,15 @@ def main():
         dt = time.perf_counter() - t0
         e2e = {"value": rays_step * a.steps / dt / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": a.frames * 416,
                "d2h_bytes_per_step": a.frames * w * h * 4, "ms_per_frame": dt / a.steps / a.frames * 1e3,
-               "api": "VolumeGVDB mirror: SetCamera + Render + ReadRenderBuf into pinned host memory"}
+               "api": f"VolumeGVDB mirror: SetCamera + Render(rbuf = frame % {nbuf}) + ReadRenderBufAsync into pinned host memory + SyncRenderBuf"}
         v.close()
     else:
         if ring is not None:
+            host_ring = [host] + [torch.empty((h, w, 4), dtype=torch.uint8).pin_memory() for _ in range(a.slots - 1)] if rank == 0 else []
+
             def to_host(q):
                 with torch.cuda.stream(consumer):               # D2H of the finished frame behind the acquire, on the consumer stream
-                    host.copy_(ring.frame_tensor(q, torch, dev), non_blocking=True)
+                    host_ring[(q - 1) % a.slots].copy_(ring.frame_tensor(q, torch, dev), non_blocking=True)
 
             def step_e2e():
                 step_resident(on_frame=to_host if rank == 0 else None)
@@ -459,7 +480,7 @@ def main():
            "ms_per_step": ms_total / a.steps, "ms_per_frame": ms_total / a.steps / a.frames, "higher_is_better": True,
            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
            "config": {"workload": f"{a.workload} {SHADE_NAME[shade]}{'+shadow' if a.deep_shadow else ''} {w}x{h}", "frames_per_step": a.frames, "bricks": timing["bricks"],
-                      "atlas_mb": vol["atlas"].nbytes / 1e6, "sampler": a.sampler, "block": a.block, "traversal": a.traversal,
+                      "atlas_mb": vol["atlas"].nbytes / 1e6, "sampler": a.sampler, "block": a.block, "traversal": a.traversal, "frame_lanes": a.lanes,
                       "parallelism": (f"image tiles {a.tile}x{a.tile} round-robin over {world} GPU(s), volume replicated, exchange={a.exchange}"
                                       if world > 1 else "single GPU"), "spp": a.spp, "deep_shadow": bool(a.deep_shadow),
                       "l2_policy": "inputs larger than L2 (atlas %.0f MB vs 126 MB L2); camera changes every frame" % (vol["atlas"].nbytes / 1e6)},

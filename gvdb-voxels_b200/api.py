@@ -26,6 +26,7 @@ EXPORTED_SYMBOLS = [
     "gvdbx_render_debug", "gvdbx_raytrace", "gvdbx_read_buffer", "gvdbx_sync", "gvdbx_get_counters",
     "gvdbx_sample_points", "gvdbx_render_tiles_direct", "gvdbx_peer_alloc", "gvdbx_peer_free", "gvdbx_peer_open",
     "gvdbx_peer_close", "gvdbx_stream_signal", "gvdbx_stream_signal_add", "gvdbx_stream_signal_many", "gvdbx_stream_wait", "gvdbx_set_stream",
+    "gvdbx_read_buffer_async", "gvdbx_lanes", "gvdbx_lane_select", "gvdbx_lane_stream", "gvdbx_lanes_fork", "gvdbx_lanes_join",
 ]
 
 
@@ -88,9 +89,16 @@ def lib():
     L.gvdbx_stream_signal_add.argtypes = [vp, vp, u64, C.c_uint32]
     L.gvdbx_stream_signal_many.argtypes = [vp, vp, C.POINTER(u64), i32, C.c_uint32]
     L.gvdbx_set_stream.argtypes = [vp, vp]
+    L.gvdbx_read_buffer_async.argtypes = [vp, u64, vp, C.c_size_t]
+    L.gvdbx_lanes.argtypes = [vp, i32]
+    L.gvdbx_lane_select.argtypes = [vp, i32]
+    L.gvdbx_lane_stream.argtypes = [vp, i32]
+    L.gvdbx_lanes_fork.argtypes = [vp]
+    L.gvdbx_lanes_join.argtypes = [vp]
     for s in EXPORTED_SYMBOLS:
-        if s != "gvdbx_last_error":
+        if s not in ("gvdbx_last_error", "gvdbx_lane_stream"):
             getattr(L, s).restype = i32
+    L.gvdbx_lane_stream.restype = vp
     _LIB = L
     return L
 
@@ -252,6 +260,27 @@ class Renderer:
     def set_stream(self, stream):
         self._ck(self._L.gvdbx_set_stream(self._h, C.c_void_p(stream or 0)), "gvdbx_set_stream")
 
+    # --- frame lanes (consecutive frames on alternating internal streams)
+    def lanes(self, n):
+        self._ck(self._L.gvdbx_lanes(self._h, int(n)), "gvdbx_lanes")
+        self.nlanes = int(n)
+
+    def lane_select(self, lane):
+        self._ck(self._L.gvdbx_lane_select(self._h, int(lane)), "gvdbx_lane_select")
+
+    def lane_stream(self, lane):
+        return int(self._L.gvdbx_lane_stream(self._h, int(lane)) or 0)
+
+    def lanes_fork(self):
+        self._ck(self._L.gvdbx_lanes_fork(self._h), "gvdbx_lanes_fork")
+
+    def lanes_join(self):
+        self._ck(self._L.gvdbx_lanes_join(self._h), "gvdbx_lanes_join")
+
+    def read_into_async(self, buf_ptr, host_array):
+        self._ck(self._L.gvdbx_read_buffer_async(self._h, int(buf_ptr), host_array.ctypes.data_as(C.c_void_p), host_array.nbytes),
+                 "gvdbx_read_buffer_async")
+
     def tiles_per_rank(self, width, height, tile_size, nranks):
         return self._L.gvdbx_tiles_per_rank(width, height, tile_size, nranks)
 
@@ -291,7 +320,7 @@ HOST_SYMBOLS = [
     "gvdbxh_create", "gvdbxh_destroy", "gvdbxh_set_transform", "gvdbxh_camera", "gvdbxh_camera_nearfar", "gvdbxh_light",
     "gvdbxh_scene_params", "gvdbxh_cross_section", "gvdbxh_linear_transfer", "gvdbxh_transfer_table", "gvdbxh_set_res", "gvdbxh_prepare_render",
     "gvdbxh_import_topology_host", "gvdbxh_import_atlas_host", "gvdbxh_commit_transfer", "gvdbxh_add_render_buf",
-    "gvdbxh_render", "gvdbxh_read_render_buf", "gvdbxh_set_option", "gvdbxh_last_error",
+    "gvdbxh_render", "gvdbxh_read_render_buf", "gvdbxh_set_render_lanes", "gvdbxh_read_render_buf_async", "gvdbxh_sync_render_buf", "gvdbxh_set_option", "gvdbxh_last_error",
 ]
 
 
@@ -409,6 +438,16 @@ class Volume:
             out = np.empty((h, w, bpp), dtype=np.uint8)
         self._ck(self._L.gvdbxh_read_render_buf(self._h, chan, out.ctypes.data_as(C.c_void_p)), "ReadRenderBuf")
         return out
+
+    def SetRenderLanes(self, n):
+        """extension: render buffer j lives on frame lane j % n, so frames in different render buffers overlap"""
+        self._ck(self._L.gvdbxh_set_render_lanes(self._h, int(n)), "SetRenderLanes")
+
+    def ReadRenderBufAsync(self, chan, out):
+        self._ck(self._L.gvdbxh_read_render_buf_async(self._h, chan, out.ctypes.data_as(C.c_void_p)), "ReadRenderBufAsync")
+
+    def SyncRenderBuf(self, chan):
+        self._ck(self._L.gvdbxh_sync_render_buf(self._h, chan), "SyncRenderBuf")
 
     def set_option(self, opt, value):
         self._ck(self._L.gvdbxh_set_option(self._h, int(opt), int(value)), "set_option")

@@ -38,6 +38,11 @@ struct gvdbx_ctx {
     float4* d_transfer = nullptr;
     // counters
     unsigned long long* d_counters = nullptr;
+    // frame lanes: internal streams that consecutive frames alternate between (the tail of frame j overlaps frame j + 1)
+    cudaStream_t base_stream = nullptr;
+    std::vector<cudaStream_t> lanes;
+    std::vector<cudaEvent_t>  lane_ev;
+    cudaEvent_t  base_ev = nullptr;
 };
 
 #define GX_CUDA(h, call)                                                                              \
@@ -66,6 +71,7 @@ extern "C" int gvdbx_create(gvdbx_t** out, int cuda_device, void* cuda_stream)
     gvdbx_t* h = new gvdbx_ctx;
     h->device = cuda_device;
     h->stream = (cudaStream_t)cuda_stream;
+    h->base_stream = h->stream;
     if (cudaMalloc(&h->d_counters, 8 * sizeof(unsigned long long)) != cudaSuccess) { delete h; return GVDBX_E_CUDA; }
     cudaMemset(h->d_counters, 0, 8 * sizeof(unsigned long long));
     *out = h;
@@ -101,6 +107,7 @@ extern "C" int gvdbx_destroy(gvdbx_t* h)
     if (!h) return GVDBX_E_ARG;
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
+    gvdbx_lanes(h, 0);
     gx_free_topology(h);
     gx_free_atlas(h);
     if (h->d_transfer) cudaFree(h->d_transfer);
@@ -576,6 +583,65 @@ extern "C" int gvdbx_set_stream(gvdbx_t* h, void* cuda_stream)
 {
     if (!h) return GVDBX_E_ARG;
     h->stream = (cudaStream_t)cuda_stream;
+    h->base_stream = h->stream;
+    return GVDBX_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ frame lanes
+// A frame's kernel ends with a tail of a few long rays during which most SMs idle (1080p: ~15 % of the frame; a rank of
+// an 8-GPU run renders 1/8 of the rays and is ALL tail).  Rendering consecutive frames on alternating streams lets the
+// next frame fill those SMs.  The library owns the streams; the caller owns one output buffer per lane.
+extern "C" int gvdbx_lanes(gvdbx_t* h, int n)
+{
+    if (!h || n < 0 || n > 16) return GVDBX_E_ARG;
+    GX_CUDA(h, cudaSetDevice(h->device));
+    for (cudaStream_t s : h->lanes) { cudaStreamSynchronize(s); cudaStreamDestroy(s); }
+    for (cudaEvent_t e : h->lane_ev) cudaEventDestroy(e);
+    if (h->base_ev) { cudaEventDestroy(h->base_ev); h->base_ev = nullptr; }
+    h->lanes.clear(); h->lane_ev.clear();
+    h->stream = h->base_stream;
+    for (int i = 0; i < n; i++) {
+        cudaStream_t s; cudaEvent_t e;
+        GX_CUDA(h, cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+        GX_CUDA(h, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        h->lanes.push_back(s); h->lane_ev.push_back(e);
+    }
+    if (n) GX_CUDA(h, cudaEventCreateWithFlags(&h->base_ev, cudaEventDisableTiming));
+    return GVDBX_OK;
+}
+extern "C" int gvdbx_lane_select(gvdbx_t* h, int lane)
+{
+    if (!h) return GVDBX_E_ARG;
+    if (lane < 0 || h->lanes.empty()) { h->stream = h->base_stream; return GVDBX_OK; }
+    h->stream = h->lanes[lane % (int)h->lanes.size()];
+    return GVDBX_OK;
+}
+extern "C" void* gvdbx_lane_stream(gvdbx_t* h, int lane)
+{
+    if (!h || lane < 0 || h->lanes.empty()) return h ? (void*)h->base_stream : nullptr;
+    return (void*)h->lanes[lane % (int)h->lanes.size()];
+}
+// every lane waits for what the creation stream has enqueued so far (inputs ready); stream-ordered, no host sync
+extern "C" int gvdbx_lanes_fork(gvdbx_t* h)
+{
+    if (!h) return GVDBX_E_ARG;
+    if (h->lanes.empty()) return GVDBX_OK;
+    GX_CUDA(h, cudaSetDevice(h->device));
+    GX_CUDA(h, cudaEventRecord(h->base_ev, h->base_stream));
+    for (cudaStream_t s : h->lanes) GX_CUDA(h, cudaStreamWaitEvent(s, h->base_ev, 0));
+    return GVDBX_OK;
+}
+// the creation stream waits for everything enqueued on the lanes so far; selects the creation stream again
+extern "C" int gvdbx_lanes_join(gvdbx_t* h)
+{
+    if (!h) return GVDBX_E_ARG;
+    h->stream = h->base_stream;
+    if (h->lanes.empty()) return GVDBX_OK;
+    GX_CUDA(h, cudaSetDevice(h->device));
+    for (size_t i = 0; i < h->lanes.size(); i++) {
+        GX_CUDA(h, cudaEventRecord(h->lane_ev[i], h->lanes[i]));
+        GX_CUDA(h, cudaStreamWaitEvent(h->base_stream, h->lane_ev[i], 0));
+    }
     return GVDBX_OK;
 }
 
@@ -685,6 +751,16 @@ extern "C" int gvdbx_read_buffer(gvdbx_t* h, uint64_t buf_d, void* host, size_t 
     GX_CUDA(h, cudaSetDevice(h->device));
     GX_CUDA(h, cudaMemcpyAsync(host, (const void*)buf_d, bytes, cudaMemcpyDeviceToHost, h->stream));
     GX_CUDA(h, cudaStreamSynchronize(h->stream));
+    return GVDBX_OK;
+}
+
+// same copy without the synchronisation: the host buffer (pinned, for a truly asynchronous copy) is valid once the stream
+// the context currently uses has passed this point (gvdbx_sync, or an event of the caller's)
+extern "C" int gvdbx_read_buffer_async(gvdbx_t* h, uint64_t buf_d, void* host, size_t bytes)
+{
+    if (!h || !buf_d || !host) return GVDBX_E_ARG;
+    GX_CUDA(h, cudaSetDevice(h->device));
+    GX_CUDA(h, cudaMemcpyAsync(host, (const void*)buf_d, bytes, cudaMemcpyDeviceToHost, h->stream));
     return GVDBX_OK;
 }
 

@@ -310,7 +310,27 @@ int VolumeGVDB::ResizeRenderBuf(int chan, int w, int h, int bpp)
 int VolumeGVDB::ReadRenderBuf(int chan, unsigned char* out)
 {
     if (chan < 0 || chan >= (int)mRenderBuf.size() || !mRenderBuf[chan].gpu || !out) return GVDBX_E_ARG;
+    if (mLanes) gvdbx_lane_select(mCtx, chan);
     return gvdbx_read_buffer(mCtx, mRenderBuf[chan].gpu, out, mRenderBuf[chan].size);
+}
+int VolumeGVDB::SetRenderLanes(int n)
+{
+    if (!mCtx) return GVDBX_E_STATE;
+    int rc = gvdbx_lanes(mCtx, n);
+    if (rc == GVDBX_OK) mLanes = n;
+    return rc;
+}
+int VolumeGVDB::ReadRenderBufAsync(int chan, unsigned char* out)
+{
+    if (chan < 0 || chan >= (int)mRenderBuf.size() || !mRenderBuf[chan].gpu || !out) return GVDBX_E_ARG;
+    if (mLanes) gvdbx_lane_select(mCtx, chan);
+    return gvdbx_read_buffer_async(mCtx, mRenderBuf[chan].gpu, out, mRenderBuf[chan].size);
+}
+int VolumeGVDB::SyncRenderBuf(int chan)
+{
+    if (!mCtx) return GVDBX_E_STATE;
+    if (mLanes) gvdbx_lane_select(mCtx, chan);
+    return gvdbx_sync(mCtx);
 }
 void VolumeGVDB::PrepareRender(int w, int h, char shading)
 {
@@ -354,6 +374,7 @@ int VolumeGVDB::Render(char shading, uint8_t chan, uint8_t rbuf)
     const int width = (int)mRenderBuf[rbuf].stride;
     const int height = (int)(mRenderBuf[rbuf].max / mRenderBuf[rbuf].stride);
     PrepareRender(width, height, shading);
+    if (mLanes) gvdbx_lane_select(mCtx, rbuf);
     return gvdbx_render(mCtx, &mScnInfo, shading, chan, mRenderBuf[rbuf].gpu, 0, 0, 0, 0);
 }
 }  // namespace gvdbx
@@ -420,6 +441,9 @@ int gvdbxh_commit_transfer(gvdbxh_volume* h) { return h->v.CommitTransferFunc();
 int gvdbxh_add_render_buf(gvdbxh_volume* h, int chan, int w, int hh, int bpp) { return h->v.AddRenderBuf(chan, w, hh, bpp); }
 int gvdbxh_render(gvdbxh_volume* h, int shading, int chan, int rbuf) { return h->v.Render((char)shading, (uint8_t)chan, (uint8_t)rbuf); }
 int gvdbxh_read_render_buf(gvdbxh_volume* h, int chan, void* out) { return h->v.ReadRenderBuf(chan, (unsigned char*)out); }
+int gvdbxh_set_render_lanes(gvdbxh_volume* h, int n) { return h->v.SetRenderLanes(n); }
+int gvdbxh_read_render_buf_async(gvdbxh_volume* h, int chan, void* out) { return h->v.ReadRenderBufAsync(chan, (unsigned char*)out); }
+int gvdbxh_sync_render_buf(gvdbxh_volume* h, int chan) { return h->v.SyncRenderBuf(chan); }
 int gvdbxh_set_option(gvdbxh_volume* h, int option, int value) { return h->v.handle() ? gvdbx_set_option(h->v.handle(), option, value) : GVDBX_E_STATE; }
 const char* gvdbxh_last_error(gvdbxh_volume* h) { return h->v.lastError(); }
 }

@@ -106,6 +106,12 @@ public:
     int  AddRenderBuf(int chan, int width, int height, int byteperpix);      // :4164-4178
     int  ResizeRenderBuf(int chan, int width, int height, int byteperpix);   // :4211-4238
     int  ReadRenderBuf(int chan, unsigned char* outptr);                     // :4241-4251
+    // extension: render buffer j lives on frame lane j % n (gvdbx_lanes): Render(.., rbuf) and the reads of rbuf are
+    // enqueued there, so frames in different render buffers overlap.  ReadRenderBufAsync returns at once; the host
+    // buffer (pinned) is valid after SyncRenderBuf(chan).
+    int  SetRenderLanes(int n);
+    int  ReadRenderBufAsync(int chan, unsigned char* outptr);
+    int  SyncRenderBuf(int chan);
     void PrepareRender(int w, int h, char shading);                          // :4254-4306 (fills mScnInfo)
     int  Render(char shading, uint8_t chan, uint8_t rbuf);                   // :4336-4381
     const char* getScnInfo() const { return (const char*)&mScnInfo; }
@@ -121,6 +127,7 @@ private:
     GxScnInfo mScnInfo;
     std::vector<RenderBuf> mRenderBuf;
     bool      mTransferCommitted = false;
+    int       mLanes = 0;
 };
 
 }  // namespace gvdbx
@@ -147,6 +154,9 @@ int   gvdbxh_commit_transfer(gvdbxh_volume*);
 int   gvdbxh_add_render_buf(gvdbxh_volume*, int chan, int w, int h, int bpp);
 int   gvdbxh_render(gvdbxh_volume*, int shading, int chan, int rbuf);
 int   gvdbxh_read_render_buf(gvdbxh_volume*, int chan, void* out);
+int   gvdbxh_set_render_lanes(gvdbxh_volume*, int n);
+int   gvdbxh_read_render_buf_async(gvdbxh_volume*, int chan, void* out);
+int   gvdbxh_sync_render_buf(gvdbxh_volume*, int chan);
 int   gvdbxh_set_option(gvdbxh_volume*, int option, int value);
 const char* gvdbxh_last_error(gvdbxh_volume*);
 }

