@@ -345,6 +345,20 @@ def main():
         r.sync()
         last = ring.frame_tensor(ring.seq, torch, dev) if ring is not None else tiled.frame
         frame_ok = bool(torch.equal(ref, last))
+        if not frame_ok:        # which rank's tiles differ
+            bad = (ref != last).any(dim=2).cpu().numpy()
+            tx = (w + a.tile - 1) // a.tile
+            ys, xs = np.nonzero(bad)
+            owner = ((ys // a.tile) * tx + xs // a.tile) % world
+            sys.stderr.write(f"[bench] frame mismatch: {int(bad.sum())} pixels, by owning rank {np.bincount(owner, minlength=world).tolist()}, "
+                             f"nonzero in ring frame {int((last != 0).any(dim=2).sum())} of {w * h}\n")
+            for k in range(len(scns)):
+                r.render(scns[k], shade, ref.data_ptr())
+                r.sync()
+                sys.stderr.write(f"[bench]   vs camera {k}: {int((ref != last).any(dim=2).sum())} pixels differ\n")
+
+    if world > 1:
+        dist.barrier()      # the other ranks must not start the e2e frames (which reuse the ring slots) while rank 0 still compares
 
     # ---------------- e2e through the reference-facing API with host buffers (rank-local at N=1; tiled at N>1)
     e2e = None
