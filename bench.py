@@ -266,7 +266,6 @@ def main():
         """one step = all frames of the orbit; N>1: every rank renders its tiles of every frame.
         peer exchange: 2 launches per frame and rank (render + done flag), +1 on rank 0 (release flags)."""
         nonlocal launches
-        r.lanes_fork()
         if world == 1:
             for j, scn in enumerate(scns):
                 r.lane_select(j % nbuf if a.lanes else -1)
@@ -285,9 +284,10 @@ def main():
         else:
             tiled.render_frames(scns, shade)
             launches += len(scns) * (2 if rank == 0 else 1)
-        r.lanes_join()
 
     def join_consumer():
+        """the measuring stream waits for the frame lanes and (rank 0) the consumer stream: stream-ordered, no host sync"""
+        r.lanes_join()
         if consumer is not None:
             torch.cuda.current_stream().wait_stream(consumer)
 
@@ -297,6 +297,7 @@ def main():
             dist.barrier()
             torch.cuda.synchronize()
 
+    r.lanes_fork()
     for _ in range(a.warmup):
         step_resident()
     join_consumer()
@@ -308,6 +309,7 @@ def main():
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sync_all()
     e0.record()
+    r.lanes_fork()
     for _ in range(a.steps):
         step_resident()
     join_consumer()
@@ -424,6 +426,7 @@ def main():
                 step_resident(on_frame=to_host if rank == 0 else None)
                 if rank == 0:
                     consumer.synchronize()                      # the caller owns the host frames of this step now
+                r.lane_select(-1)
         else:
             def to_host(j, fr):
                 host.copy_(fr, non_blocking=True)                   # D2H of the assembled frame, stream-ordered

@@ -24,7 +24,7 @@ EXPORTED_SYMBOLS = [
     "gvdbx_import_atlas_array", "gvdbx_import_atlas_host", "gvdbx_set_transfer",
     "gvdbx_render", "gvdbx_render_tiles", "gvdbx_tiles_per_rank", "gvdbx_assemble_tiles",
     "gvdbx_render_debug", "gvdbx_raytrace", "gvdbx_read_buffer", "gvdbx_sync", "gvdbx_get_counters",
-    "gvdbx_sample_points", "gvdbx_render_tiles_direct", "gvdbx_peer_alloc", "gvdbx_peer_free", "gvdbx_peer_open",
+    "gvdbx_sample_points", "gvdbx_render_tiles_direct", "gvdbx_render_tiles_ring", "gvdbx_peer_alloc", "gvdbx_peer_free", "gvdbx_peer_open",
     "gvdbx_peer_close", "gvdbx_stream_signal", "gvdbx_stream_signal_add", "gvdbx_stream_signal_many", "gvdbx_stream_wait", "gvdbx_set_stream",
     "gvdbx_read_buffer_async", "gvdbx_lanes", "gvdbx_lane_select", "gvdbx_lane_stream", "gvdbx_lanes_fork", "gvdbx_lanes_join",
 ]
@@ -80,6 +80,7 @@ def lib():
     L.gvdbx_get_counters.argtypes = [vp, C.POINTER(Counters)]
     L.gvdbx_sample_points.argtypes = [vp, i32, u64, i32, u64, u64]
     L.gvdbx_render_tiles_direct.argtypes = [vp, vp, i32, i32, u64, i32, i32, i32]
+    L.gvdbx_render_tiles_ring.argtypes = [vp, vp, i32, i32, u64, i32, i32, i32, u64, C.c_uint32, u64]
     L.gvdbx_peer_alloc.argtypes = [vp, C.c_size_t, C.POINTER(u64), vp]
     L.gvdbx_peer_free.argtypes = [vp, u64]
     L.gvdbx_peer_open.argtypes = [vp, vp, C.POINTER(u64)]
@@ -223,6 +224,12 @@ class Renderer:
         p, keep = _buf(scninfo)
         self._ck(self._L.gvdbx_render_tiles_direct(self._h, p, shade, chan, int(frame_ptr), tile_size, rank, nranks),
                  "gvdbx_render_tiles_direct")
+
+    def render_tiles_ring(self, scninfo, shade, frame_ptr, tile_size, rank, nranks, wait_flag, wait_value, done_flag, chan=0):
+        """[wait] + this rank's tiles + done += 1 in one call (the per-frame step of PeerFrameRing)"""
+        p, keep = _buf(scninfo)
+        self._ck(self._L.gvdbx_render_tiles_ring(self._h, p, shade, chan, int(frame_ptr), tile_size, rank, nranks,
+                                                 int(wait_flag), int(wait_value) & 0xFFFFFFFF, int(done_flag)), "gvdbx_render_tiles_ring")
 
     # --- peer memory + stream-ordered flags (multi-GPU without a gather)
     def peer_alloc(self, nbytes):

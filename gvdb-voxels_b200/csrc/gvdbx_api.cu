@@ -537,6 +537,20 @@ extern "C" int gvdbx_render_tiles_direct(gvdbx_t* h, const void* scninfo, int sh
     return GVDBX_OK;
 }
 
+// One call per frame and rank for the peer frame ring: [wait until *wait_flag_d >= wait_value] -> this rank's tiles into
+// frame_d -> *done_flag_d += 1, all on the context's current stream / lane (wait_flag_d == 0: no wait).
+extern "C" int gvdbx_render_tiles_ring(gvdbx_t* h, const void* scninfo, int shade_mode, int chan, uint64_t frame_d,
+                                       int tile_size, int rank, int nranks, uint64_t wait_flag_d, uint32_t wait_value,
+                                       uint64_t done_flag_d)
+{
+    if (!h || !done_flag_d) return GVDBX_E_ARG;
+    int rc = GVDBX_OK;
+    if (wait_flag_d) rc = gvdbx_stream_wait(h, nullptr, wait_flag_d, wait_value);
+    if (rc == GVDBX_OK) rc = gvdbx_render_tiles_direct(h, scninfo, shade_mode, chan, frame_d, tile_size, rank, nranks);
+    if (rc == GVDBX_OK) rc = gvdbx_stream_signal_add(h, nullptr, done_flag_d, 1);
+    return rc;
+}
+
 // ------------------------------------------------------------------------------------------------ peer memory + flags
 extern "C" int gvdbx_peer_alloc(gvdbx_t* h, size_t bytes, uint64_t* dptr, void* handle64)
 {

@@ -194,10 +194,15 @@ class PeerFrameRing:
         slot, _ = ring_slot(q, self.nslots)
         if getattr(self.r, "nlanes", 0):                      # consecutive frames on alternating internal streams
             self.r.lane_select((q - 1) % self.r.nlanes)
-        if q > self.nslots:                                   # the slot's previous frame must have been consumed
-            self.r.stream_wait(self.released_local, q - self.nslots)
-        self.r.render_tiles_direct(scninfo, shade, self.frame_ptr[slot], self.ts, self.rank, self.world)
-        self.r.stream_signal_add(self.done_ptr[slot], 1)
+        # the slot's previous frame (q - nslots) must have been consumed before its pixels are overwritten
+        wait = (self.released_local, q - self.nslots) if q > self.nslots else (0, 0)
+        if hasattr(self.r, "render_tiles_ring"):
+            self.r.render_tiles_ring(scninfo, shade, self.frame_ptr[slot], self.ts, self.rank, self.world, wait[0], wait[1], self.done_ptr[slot])
+        else:
+            if wait[0]:
+                self.r.stream_wait(*wait)
+            self.r.render_tiles_direct(scninfo, shade, self.frame_ptr[slot], self.ts, self.rank, self.world)
+            self.r.stream_signal_add(self.done_ptr[slot], 1)
         return q
 
     # ---- rank 0 (consumer)

@@ -121,6 +121,11 @@ int  gvdbx_render_tiles(gvdbx_t* h, const void* scninfo, int shade_mode, int cha
  * NVLink from inside the render kernel — render and "gather" are one kernel, nothing is packed or assembled. */
 int  gvdbx_render_tiles_direct(gvdbx_t* h, const void* scninfo, int shade_mode, int chan, uint64_t frame_d,
                                int tile_size, int rank, int nranks);
+/* The per-frame call of the peer frame ring (multigpu.py::PeerFrameRing): optional back-pressure wait, this rank's
+ * tiles into frame_d, then *done_flag_d += 1 — three stream-ordered operations on the current stream / lane. */
+int  gvdbx_render_tiles_ring(gvdbx_t* h, const void* scninfo, int shade_mode, int chan, uint64_t frame_d,
+                             int tile_size, int rank, int nranks, uint64_t wait_flag_d, uint32_t wait_value,
+                             uint64_t done_flag_d);
 int  gvdbx_tiles_per_rank(int width, int height, int tile_size, int nranks);
 int  gvdbx_assemble_tiles(gvdbx_t* h, uint64_t gathered_d, uint64_t frame_d, int width, int height, int tile_size, int nranks);
 
