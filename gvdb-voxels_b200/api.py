@@ -24,7 +24,7 @@ EXPORTED_SYMBOLS = [
     "gvdbx_import_atlas_array", "gvdbx_import_atlas_host", "gvdbx_set_transfer",
     "gvdbx_render", "gvdbx_render_tiles", "gvdbx_tiles_per_rank", "gvdbx_assemble_tiles",
     "gvdbx_render_debug", "gvdbx_raytrace", "gvdbx_read_buffer", "gvdbx_sync", "gvdbx_get_counters",
-    "gvdbx_sample_points", "gvdbx_render_tiles_direct", "gvdbx_render_tiles_ring", "gvdbx_peer_alloc", "gvdbx_peer_free", "gvdbx_peer_open",
+    "gvdbx_sample_points", "gvdbx_update_apron", "gvdbx_export_atlas_host", "gvdbx_render_tiles_direct", "gvdbx_render_tiles_ring", "gvdbx_peer_alloc", "gvdbx_peer_free", "gvdbx_peer_open",
     "gvdbx_peer_close", "gvdbx_stream_signal", "gvdbx_stream_signal_add", "gvdbx_stream_signal_many", "gvdbx_stream_wait", "gvdbx_set_stream",
     "gvdbx_read_buffer_async", "gvdbx_lanes", "gvdbx_lane_select", "gvdbx_lane_stream", "gvdbx_lanes_fork", "gvdbx_lanes_join",
 ]
@@ -80,6 +80,8 @@ def lib():
     L.gvdbx_get_counters.argtypes = [vp, C.POINTER(Counters)]
     L.gvdbx_sample_points.argtypes = [vp, i32, u64, i32, u64, u64]
     L.gvdbx_render_tiles_direct.argtypes = [vp, vp, i32, i32, u64, i32, i32, i32]
+    L.gvdbx_update_apron.argtypes = [vp, i32, C.c_float]
+    L.gvdbx_export_atlas_host.argtypes = [vp, i32, vp, i32, i32, i32]
     L.gvdbx_render_tiles_ring.argtypes = [vp, vp, i32, i32, u64, i32, i32, i32, u64, C.c_uint32, u64]
     L.gvdbx_peer_alloc.argtypes = [vp, C.c_size_t, C.POINTER(u64), vp]
     L.gvdbx_peer_free.argtypes = [vp, u64]
@@ -198,6 +200,16 @@ class Renderer:
     def import_atlas_array(self, cuarray, res_xyz, chan=0):
         self._ck(self._L.gvdbx_import_atlas_array(self._h, chan, C.c_void_p(cuarray), *map(int, res_xyz)),
                  "gvdbx_import_atlas_array")
+
+    def update_apron(self, boundval=0.0, chan=0):
+        """VolumeGVDB::UpdateApron(chan, boundval) on the imported atlas"""
+        self._ck(self._L.gvdbx_update_apron(self._h, chan, C.c_float(boundval)), "gvdbx_update_apron")
+
+    def export_atlas_host(self, shape_zyx, chan=0):
+        rz, ry, rx = shape_zyx
+        out = np.empty((rz, ry, rx), dtype=np.float32)
+        self._ck(self._L.gvdbx_export_atlas_host(self._h, chan, out.ctypes.data_as(C.c_void_p), rx, ry, rz), "gvdbx_export_atlas_host")
+        return out
 
     def set_transfer(self, rgba):
         a = np.ascontiguousarray(rgba, dtype=np.float32).reshape(-1)

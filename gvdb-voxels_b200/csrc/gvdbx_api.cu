@@ -28,6 +28,8 @@ struct gvdbx_ctx {
     bool                have_atlas = false;
     cudaArray_t         own_array = nullptr;
     cudaTextureObject_t tex = 0;
+    cudaSurfaceObject_t surf = 0;       // same array, for UpdateApron (needs CUDA_ARRAY3D_SURFACE_LDST like the reference's volOut)
+    cudaArray_t         array = nullptr; // the array both objects sit on (caller's or own_array)
     float*              d_bricks = nullptr;
     GxRange*            d_range = nullptr;      // per brick slot
     GxRange*            d_leaf_range = nullptr; // per leaf (valid when topology and atlas are both imported)
@@ -94,6 +96,8 @@ static void gx_free_topology(gvdbx_t* h)
 static void gx_free_atlas(gvdbx_t* h)
 {
     if (h->tex) cudaDestroyTextureObject(h->tex);
+    if (h->surf) cudaDestroySurfaceObject(h->surf);
+    h->surf = 0; h->array = nullptr;
     if (h->own_array) cudaFreeArray(h->own_array);
     if (h->d_bricks) cudaFree(h->d_bricks);
     if (h->d_range) cudaFree(h->d_range);
@@ -240,6 +244,8 @@ static int gx_make_texture(gvdbx_t* h, cudaArray_t arr)
     td.addressMode[0] = td.addressMode[1] = td.addressMode[2] = cudaAddressModeClamp;
     td.normalizedCoords = 0;
     GX_CUDA(h, cudaCreateTextureObject(&h->tex, &rd, &td, nullptr));
+    h->array = arr;
+    if (cudaCreateSurfaceObject(&h->surf, &rd) != cudaSuccess) { h->surf = 0; cudaGetLastError(); }   // array without the surface flag: no UpdateApron
     return GVDBX_OK;
 }
 
@@ -311,6 +317,57 @@ extern "C" int gvdbx_import_atlas_host(gvdbx_t* h, int chan, const float* texels
     if (e != cudaSuccess) { h->err = std::string("cudaMemcpyAsync: ") + cudaGetErrorString(e); return GVDBX_E_CUDA; }
     if (rc) return rc;
     h->have_atlas = true;
+    return GVDBX_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ UpdateApron / atlas read-back
+static void gx_tree_params(gvdbx_t* h, GxParams& P)
+{
+    memset(&P, 0, sizeof P);
+    const GxVDBInfo& v = h->vdb;
+    for (int l = 0; l < GX_MAXLEV; l++) {
+        P.dim[l] = v.dim[l]; P.res[l] = v.res[l]; P.vdel[l] = make_float3(v.vdel[l].x, v.vdel[l].y, v.vdel[l].z);
+        P.noderange[l] = make_int3(v.noderange[l].x, v.noderange[l].y, v.noderange[l].z);
+        P.child[l] = h->d_child[l]; P.npos[l] = h->d_npos[l];
+    }
+    P.top_lev = v.top_lev; P.epsilon = v.epsilon;
+    P.leaf = h->d_leaf;
+    P.tex = h->tex; P.bricks = h->d_bricks;
+}
+
+extern "C" int gvdbx_update_apron(gvdbx_t* h, int chan, float boundval)
+{
+    if (!h) return GVDBX_E_ARG;
+    if (chan != 0) return gx_fail(h, GVDBX_E_UNSUPPORTED, "only channel 0 (T_FLOAT) is supported");
+    if (!h->have_topo || !h->have_atlas) return gx_fail(h, GVDBX_E_STATE, "UpdateApron needs topology and atlas");
+    if (!h->surf) return gx_fail(h, GVDBX_E_UNSUPPORTED, "the atlas array was created without surface load/store");
+    GX_CUDA(h, cudaSetDevice(h->device));
+    GxParams P;
+    gx_tree_params(h, P);
+    const int n = h->vdb.nodecnt[0];
+    gx_update_apron_kernel<<<n, 128, 0, h->stream>>>(P, h->surf, h->d_bricks, n, boundval);
+    GX_CUDA(h, cudaGetLastError());
+    gx_brick_ranges<<<(unsigned)h->nslots, 256, 0, h->stream>>>(h->d_bricks, h->d_range);
+    GX_CUDA(h, cudaGetLastError());
+    return gx_update_leaf_ranges(h);
+}
+
+// host image of the atlas array, x fastest (the inverse of gvdbx_import_atlas_host; Allocator::AtlasRetrieveSlice per slice)
+extern "C" int gvdbx_export_atlas_host(gvdbx_t* h, int chan, float* texels, int rx, int ry, int rz)
+{
+    if (!h || !texels) return GVDBX_E_ARG;
+    if (chan != 0) return gx_fail(h, GVDBX_E_UNSUPPORTED, "only channel 0 (T_FLOAT) is supported");
+    if (!h->have_atlas || !h->array) return gx_fail(h, GVDBX_E_STATE, "no atlas imported");
+    if (rx != h->ares[0] || ry != h->ares[1] || rz != h->ares[2]) return gx_fail(h, GVDBX_E_ARG, "atlas resolution mismatch");
+    GX_CUDA(h, cudaSetDevice(h->device));
+    cudaMemcpy3DParms cp;
+    memset(&cp, 0, sizeof cp);
+    cp.srcArray = h->array;
+    cp.dstPtr = make_cudaPitchedPtr(texels, size_t(rx) * sizeof(float), rx, ry);
+    cp.extent = make_cudaExtent(rx, ry, rz);
+    cp.kind = cudaMemcpyDeviceToHost;
+    GX_CUDA(h, cudaMemcpy3DAsync(&cp, h->stream));
+    GX_CUDA(h, cudaStreamSynchronize(h->stream));
     return GVDBX_OK;
 }
 

@@ -116,6 +116,61 @@ __global__ void gx_sample_points_kernel(GxParams P, const float* __restrict__ xy
     out_lin[i] = s.tri(x, y, z);
 }
 
+// ------------------------------------------------------------------------------------------------ apron update
+// VolumeGVDB::UpdateApron for a float channel with apron 1 (gvdb_volume_gvdb.cpp:4418-4453, kernel
+// cuda_gvdb_operators.cuh:72-126): every texel of the six 10x10 faces of every brick takes the value of the voxel that
+// occupies its index-space position in whichever leaf contains it (top-down point query), else `boundval`.  One CTA per
+// leaf; reads only interior voxels and writes only apron texels, so the pass is race-free.  Both copies of the atlas
+// are kept coherent: the 3-D array (through a surface object) and the brick-major layout.
+__global__ void gx_update_apron_kernel(const __grid_constant__ GxParams P, cudaSurfaceObject_t surf, float* __restrict__ bricks,
+                                       int nleaf, float boundval)
+{
+    const int leaf = blockIdx.x;
+    if (leaf >= nleaf) return;
+    const GxLeafRec L = P.leaf[leaf];
+    if (L.vx < 0) return;
+    GxCount cnt = {0, 0, 0, 0, 0, 0};
+    for (int i = threadIdx.x; i < 6 * GX_BRICK_DIM * GX_BRICK_DIM; i += blockDim.x) {
+        const int side = i / (GX_BRICK_DIM * GX_BRICK_DIM), u = (i / GX_BRICK_DIM) % GX_BRICK_DIM, v = i % GX_BRICK_DIM;
+        int bx, by, bz;                                   // texel inside the 10^3 brick
+        switch (side) {
+        case 0:  bx = 0; by = u; bz = v; break;
+        case 1:  bx = u; by = 0; bz = v; break;
+        case 2:  bx = u; by = v; bz = 0; break;
+        case 3:  bx = GX_BRICK_DIM - 1; by = u; bz = v; break;
+        case 4:  bx = u; by = GX_BRICK_DIM - 1; bz = v; break;
+        default: bx = u; by = v; bz = GX_BRICK_DIM - 1; break;
+        }
+        // index-space centre of the texel (getAtlasToWorld, cuda_gvdb_nodes.cuh:145-153)
+        const float3 wpos = make_float3(float(L.px) + float(bx - 1) + 0.5f, float(L.py) + float(by - 1) + 0.5f, float(L.pz) + float(bz - 1) + 0.5f);
+        float value = boundval;
+        const int n = gx_node_at_point<GxSampler<GX_SAMPLER_TEX, false>>(P, wpos, cnt);
+        if (n >= 0) {
+            const GxLeafRec N = P.leaf[n];
+            const float3 offs = make_float3(float(N.vx), float(N.vy), float(N.vz)) + (wpos - make_float3(float(N.px), float(N.py), float(N.pz)));
+            value = surf3Dread<float>(surf, int(unsigned(offs.x)) * int(sizeof(float)), int(unsigned(offs.y)), int(unsigned(offs.z)));
+        }
+        surf3Dwrite(value, surf, (L.vx - 1 + bx) * int(sizeof(float)), L.vy - 1 + by, L.vz - 1 + bz);
+        bricks[size_t(L.base) + (bz * GX_BRICK_DIM + by) * GX_BRICK_DIM + bx] = value;
+    }
+}
+
+// value range per brick slot from the brick-major layout (after the aprons changed)
+__global__ void gx_brick_ranges(const float* __restrict__ bricks, GxRange* __restrict__ range)
+{
+    const float* b = bricks + size_t(blockIdx.x) * GX_BRICK_STRIDE;
+    float lo = INFINITY, hi = -INFINITY;
+    for (int i = threadIdx.x; i < GX_BRICK_DIM * GX_BRICK_DIM * GX_BRICK_DIM; i += blockDim.x) { const float v = b[i]; lo = fminf(lo, v); hi = fmaxf(hi, v); }
+    __shared__ float slo[8], shi[8];
+    for (int o = 16; o > 0; o >>= 1) { lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, o)); hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, o)); }
+    if ((threadIdx.x & 31) == 0) { slo[threadIdx.x >> 5] = lo; shi[threadIdx.x >> 5] = hi; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < (blockDim.x >> 5); w++) { lo = fminf(lo, slo[w]); hi = fmaxf(hi, shi[w]); }
+        range[blockIdx.x].lo = lo; range[blockIdx.x].hi = hi;
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ cross-GPU flags
 // one thread: release-store of a sequence number (the frame's pixels were stored by kernels earlier in the stream)
 __global__ void gx_signal_kernel(unsigned int* flag, unsigned int value)

@@ -99,6 +99,14 @@ int  gvdbx_import_atlas_array(gvdbx_t* h, int chan, void* cuarray, int res_x, in
 /* Same from a HOST image of the atlas, x fastest (the layout of Allocator::AtlasCommitFromCPU, gvdb_allocator.cpp:797). */
 int  gvdbx_import_atlas_host(gvdbx_t* h, int chan, const float* texels, int res_x, int res_y, int res_z);
 
+/* VolumeGVDB::UpdateApron(chan, boundval) (src/gvdb_volume_gvdb.cpp:4418-4453, kernels/cuda_gvdb_operators.cuh:72-126)
+ * on the imported atlas: every apron texel takes the value of the voxel at its index-space position in whichever brick
+ * contains it, else `boundval`.  Writes the 3-D array (the caller's, when imported with gvdbx_import_atlas_array —
+ * exactly what the reference's kernel does) and keeps the library's brick-major copy and value ranges coherent. */
+int  gvdbx_update_apron(gvdbx_t* h, int chan, float boundval);
+/* Read the atlas array back into a host image, x fastest (Allocator::AtlasRetrieveSlice for every slice). */
+int  gvdbx_export_atlas_host(gvdbx_t* h, int chan, float* texels, int res_x, int res_y, int res_z);
+
 /* Transfer function: 16384 float4 (Scene::getTransferFunc()).  Alternatively leave unset and pass a device pointer in
  * ScnInfo.transfer exactly like the reference does. */
 int  gvdbx_set_transfer(gvdbx_t* h, const float* rgba_host);

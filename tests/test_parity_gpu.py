@@ -547,3 +547,46 @@ def test_stream_flags_order_two_streams(scenes, torch_cuda, pkg):
     assert flags[0] == 3 and flags[1] == 0
     b.synchronize()
     r.peer_free(ptr)
+
+
+# ------------------------------------------------------------------------------------------------ UpdateApron
+@pytest.mark.parametrize("preset", ["cfg1_tiny", "cfg3_tiny", "cfg2_small", "cfg4_small"])
+def test_update_apron_matches_reference_atlas(ora, pkg, torch_cuda, preset):
+    """gvdbx_update_apron on an atlas whose aprons were wiped reproduces, byte for byte, the atlas the UNMODIFIED
+    reference holds after its own UpdateApron (SHA-256 in the golden file), keeps the brick-major copy coherent
+    (linear-sampler render unchanged) and the render equal to the golden image."""
+    from common import sha
+    g = golden(preset)
+    p, vol = ora.scene_volume(preset)
+    atlas = vol["atlas"]
+    assert sha(atlas) == str(g["atlas_sha"])
+    # wipe every apron texel: keep only the 8^3 interiors (mValue = atlas texel of the first interior voxel)
+    recs = np.frombuffer(vol["pool0"][0].tobytes(), np.int32).reshape(-1, 16)
+    wiped = np.full_like(atlas, 777.0)
+    for vx, vy, vz in recs[:, 4:7]:
+        wiped[vz:vz + 8, vy:vy + 8, vx:vx + 8] = atlas[vz:vz + 8, vy:vy + 8, vx:vx + 8]
+        # texels of unused slots stay as they are in the reference atlas (zero)
+    used = np.zeros(atlas.shape, bool)
+    for vx, vy, vz in recs[:, 4:7]:
+        used[vz - 1:vz + 9, vy - 1:vy + 9, vx - 1:vx + 9] = True
+    wiped[~used] = atlas[~used]
+    assert not np.array_equal(wiped, atlas)
+    _, table = ora.scninfo_for(pkg, p)
+    r = pkg.Renderer(0)
+    r.import_topology_host(vol["vdbinfo"], vol["pool0"], vol["pool1"])
+    r.import_atlas_host(wiped)
+    r.set_transfer(table)
+    r.update_apron(0.0)
+    back = r.export_atlas_host(atlas.shape)
+    assert np.array_equal(back.view(np.uint32), atlas.view(np.uint32)), f"{(back != atlas).sum()} texels differ"
+    assert sha(back) == str(g["atlas_sha"])
+    w, h = int(g["width"]), int(g["height"])
+    for mode in ("trilinear", "deep"):
+        assert np.array_equal(_render(torch_cuda, r, g[f"scn_{mode}"].tobytes(), MODES[mode], w, h, 0), g[f"rgba_{mode}"])
+        assert tolerance_ok(_render(torch_cuda, r, g[f"scn_{mode}"].tobytes(), MODES[mode], w, h, 1), g[f"rgba_{mode}"])[0]
+    # a different boundary value only changes texels whose position lies in no brick
+    r.update_apron(5.0)
+    b5 = r.export_atlas_host(atlas.shape)
+    changed = b5 != atlas
+    assert changed.any() and (b5[changed] == 5.0).all() and (atlas[changed] == 0.0).all()
+    r.close()
