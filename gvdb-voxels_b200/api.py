@@ -338,7 +338,8 @@ class Renderer:
 HOST_SYMBOLS = [
     "gvdbxh_create", "gvdbxh_destroy", "gvdbxh_set_transform", "gvdbxh_camera", "gvdbxh_camera_nearfar", "gvdbxh_light",
     "gvdbxh_scene_params", "gvdbxh_cross_section", "gvdbxh_linear_transfer", "gvdbxh_transfer_table", "gvdbxh_set_res", "gvdbxh_prepare_render",
-    "gvdbxh_import_topology_host", "gvdbxh_import_atlas_host", "gvdbxh_commit_transfer", "gvdbxh_add_render_buf",
+    "gvdbxh_import_topology_host", "gvdbxh_import_atlas_host", "gvdbxh_commit_transfer",
+    "gvdbxh_load_vbx", "gvdbxh_save_vbx", "gvdbxh_vdbinfo", "gvdbxh_set_epsilon", "gvdbxh_add_render_buf",
     "gvdbxh_render", "gvdbxh_read_render_buf", "gvdbxh_set_render_lanes", "gvdbxh_read_render_buf_async", "gvdbxh_sync_render_buf", "gvdbxh_set_option", "gvdbxh_last_error",
 ]
 
@@ -360,7 +361,7 @@ class Volume:
         L.gvdbxh_transfer_table.restype = C.POINTER(C.c_float)
         L.gvdbxh_last_error.restype = C.c_char_p
         for s in HOST_SYMBOLS:
-            if s not in ("gvdbxh_create", "gvdbxh_transfer_table", "gvdbxh_last_error"):
+            if s not in ("gvdbxh_create", "gvdbxh_transfer_table", "gvdbxh_last_error", "gvdbxh_vdbinfo", "gvdbxh_set_epsilon"):
                 getattr(L, s).restype = C.c_int
         self._L = L
         self._h = C.c_void_p(L.gvdbxh_create(int(device)))
@@ -440,6 +441,21 @@ class Volume:
         a = np.ascontiguousarray(texels, dtype=np.float32)
         rz, ry, rx = a.shape
         self._ck(self._L.gvdbxh_import_atlas_host(self._h, chan, a.ctypes.data_as(C.c_void_p), rx, ry, rz), "ImportAtlasHost")
+
+    def LoadVBX(self, fname, parse_only=False):
+        """VolumeGVDB::LoadVBX (gvdb_volume_gvdb.cpp:507-683): transform, pools and channel-0 atlas of a .vbx file"""
+        self._ck(self._L.gvdbxh_load_vbx(self._h, str(fname).encode(), 1 if parse_only else 0), "LoadVBX")
+
+    def SaveVBX(self, fname):
+        self._ck(self._L.gvdbxh_save_vbx(self._h, str(fname).encode()), "SaveVBX")
+
+    def SetEpsilon(self, eps, maxiter=256):
+        self._L.gvdbxh_set_epsilon(self._h, C.c_float(eps), int(maxiter))
+
+    def vdbinfo(self):
+        out = (C.c_uint8 * VDBINFO_BYTES)()
+        self._L.gvdbxh_vdbinfo(self._h, out)
+        return bytes(out)
 
     def CommitTransferFunc(self):
         self._ck(self._L.gvdbxh_commit_transfer(self._h), "CommitTransferFunc")

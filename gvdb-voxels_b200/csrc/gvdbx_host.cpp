@@ -4,6 +4,7 @@
 #include <math.h>
 #include <stdlib.h>
 #include <string.h>
+#include <stdio.h>
 
 namespace gvdbx {
 
@@ -226,6 +227,7 @@ void Scene::LinearTransferFunc(float t0, float t1, Vec4 a, Vec4 b)
 VolumeGVDB::VolumeGVDB()
 {
     memset(&mScnInfo, 0, sizeof mScnInfo);
+    memset(&mVDBHost, 0, sizeof mVDBHost);
     SetTransform(Vec3(0, 0, 0), Vec3(1, 1, 1), Vec3(0, 0, 0), Vec3(0, 0, 0));   // gvdb_volume_gvdb.cpp:77
 }
 VolumeGVDB::~VolumeGVDB()
@@ -233,7 +235,11 @@ VolumeGVDB::~VolumeGVDB()
     if (mCtx) gvdbx_destroy(mCtx);
     delete mScene;
 }
-const char* VolumeGVDB::lastError() const { return mCtx ? gvdbx_last_error(mCtx) : "no device context"; }
+const char* VolumeGVDB::lastError() const
+{
+    if (!mErr.empty()) return mErr.c_str();
+    return mCtx ? gvdbx_last_error(mCtx) : "no device context";
+}
 int VolumeGVDB::SetCudaDevice(int devid, void* stream)
 {
     if (mCtx) { gvdbx_destroy(mCtx); mCtx = nullptr; }
@@ -265,7 +271,199 @@ void VolumeGVDB::SetTransform(Vec3 pretrans, Vec3 scal, Vec3 angs, Vec3 trans)
 }
 int VolumeGVDB::ImportTopologyHost(const void* v, const void* const* p0, const void* const* p1, const uint64_t* n1)
 {
+    // host copies of what was imported, so that SaveVBX can write them back out
+    memcpy(&mVDBHost, v, sizeof mVDBHost);
+    mLevels = 0;                                        // levels the tree was configured with (upper ones may be empty)
+    while (mLevels < GX_MAXLEV && mVDBHost.nodewid[mLevels] > 0) mLevels++;
+    mPool0.assign(mLevels, {}); mPool1.assign(mLevels, {});
+    for (int l = 0; l < mLevels; l++) {
+        const size_t b0 = size_t(mVDBHost.nodecnt[l]) * mVDBHost.nodewid[l];
+        if (p0[l] && b0) mPool0[l].assign((const unsigned char*)p0[l], (const unsigned char*)p0[l] + b0);
+        if (p1[l] && n1[l]) mPool1[l].assign((const unsigned char*)p1[l], (const unsigned char*)p1[l] + n1[l]);
+    }
+    mRoot = uint64_t(mVDBHost.top_lev) << 8;            // Elem(0, top_lev, 0): group | level << 8 | index << 16
+    mAtlasRes[0] = mVDBHost.atlas_res.x; mAtlasRes[1] = mVDBHost.atlas_res.y; mAtlasRes[2] = mVDBHost.atlas_res.z;
+    mAtlasCnt[0] = mVDBHost.atlas_cnt.x; mAtlasCnt[1] = mVDBHost.atlas_cnt.y; mAtlasCnt[2] = mVDBHost.atlas_cnt.z;
     return mCtx ? gvdbx_import_topology_host(mCtx, v, p0, p1, n1) : GVDBX_E_STATE;
+}
+
+// ------------------------------------------------------------------------------------------------ VBX
+namespace {
+struct Reader {
+    FILE* fp; bool ok = true;
+    template <class T> void get(T* dst, size_t n = 1) { if (ok && fread(dst, sizeof(T), n, fp) != n) ok = false; }
+};
+}
+
+int VolumeGVDB::LoadVBX(const char* fname, bool parse_only)
+{
+    mErr.clear();
+    FILE* fp = fopen(fname, "rb");
+    if (!fp) { mErr = std::string("LoadVBX: unable to open ") + fname; return GVDBX_E_ARG; }
+    Reader rd{fp};
+    auto fail = [&](int code, const std::string& m) { fclose(fp); mErr = "LoadVBX: " + m; return code; };
+
+    //--- file header (gvdb_volume_gvdb.cpp:549-590)
+    unsigned char major = 0, minor = 0;
+    rd.get(&major); rd.get(&minor);
+    if ((major == 1 && minor >= 11) || major > 1) {     // 1.11+ stores the grid transform
+        rd.get(&mPretrans.x, 3); rd.get(&mAngs.x, 3); rd.get(&mScale.x, 3); rd.get(&mTrans.x, 3);
+        SetTransform(mPretrans, mScale, mAngs, mTrans);
+    }
+    int num_grids = 0;
+    rd.get(&num_grids);
+    unsigned char read_masks = 0;
+    if (major >= 2) rd.get(&read_masks);
+    else if (major == 1 && minor == 0) read_masks = 1;  // GVDB 1.0 always used bitmasks
+    if (!rd.ok || num_grids < 1 || num_grids > 1024) return fail(GVDBX_E_ARG, "bad header");
+    if (read_masks) return fail(GVDBX_E_UNSUPPORTED, "bitmask child lists (GVDB 1.0 files) are not supported");
+    std::vector<uint64_t> grid_offs(num_grids);
+    rd.get(grid_offs.data(), num_grids);
+
+    //--- grid header of the first grid (the reference loads every grid over the previous one; files it writes hold one)
+    char grid_name[256];
+    unsigned char dtype = 0, components = 0, compress = 0, topotype = 0, layout = 0;
+    float voxelsize[3];
+    int leafcnt = 0, leafdim[3], apron = 0, num_chan = 0, reuse = 0, axiscnt[3], axisres[3], levels = 0;
+    uint64_t atlas_sz = 0, root = 0;
+    rd.get(grid_name, 256); rd.get(&dtype); rd.get(&components); rd.get(&compress); rd.get(voxelsize, 3);
+    rd.get(&leafcnt); rd.get(leafdim, 3); rd.get(&apron); rd.get(&num_chan); rd.get(&atlas_sz);
+    rd.get(&topotype); rd.get(&reuse); rd.get(&layout); rd.get(axiscnt, 3); rd.get(axisres, 3);
+    //--- topology section
+    rd.get(&levels); rd.get(&root);
+    if (!rd.ok || levels < 1 || levels > GX_MAXLEV) return fail(GVDBX_E_ARG, "bad grid header / level count");
+    if (compress != 0) return fail(GVDBX_E_UNSUPPORTED, "compressed grids");
+    int ld[GX_MAXLEV], res[GX_MAXLEV], range[GX_MAXLEV][3], cnt0[GX_MAXLEV], width0[GX_MAXLEV], cnt1[GX_MAXLEV], width1[GX_MAXLEV];
+    for (int n = 0; n < levels; n++) {
+        rd.get(&ld[n]); rd.get(&res[n]); rd.get(range[n], 3); rd.get(&cnt0[n]); rd.get(&width0[n]); rd.get(&cnt1[n]); rd.get(&width1[n]);
+    }
+    if (!rd.ok) return fail(GVDBX_E_ARG, "truncated topology header");
+    if (width0[0] != (int)sizeof(GxNode)) return fail(GVDBX_E_UNSUPPORTED, "node records of another library version (width != 64)");
+    std::vector<std::vector<unsigned char>> pool0(levels), pool1(levels);
+    for (int n = 0; n < levels; n++) {
+        if (cnt0[n] < 0 || width0[n] < 0) return fail(GVDBX_E_ARG, "bad pool size");
+        pool0[n].resize(size_t(cnt0[n]) * width0[n]);
+        if (!pool0[n].empty()) rd.get(pool0[n].data(), pool0[n].size());
+    }
+    for (int n = 0; n < levels; n++) {
+        if (cnt1[n] < 0 || width1[n] < 0) return fail(GVDBX_E_ARG, "bad pool size");
+        pool1[n].resize(size_t(cnt1[n]) * width1[n]);
+        if (!pool1[n].empty()) rd.get(pool1[n].data(), pool1[n].size());
+    }
+    if (!rd.ok) return fail(GVDBX_E_ARG, "truncated pools");
+
+    //--- VDBInfo as FinishTopology + PrepareVDB produce it (:1579-1593, :1792-1816, :3946-3989)
+    GxVDBInfo v;
+    memset(&v, 0, sizeof v);
+    int tlev = 1;
+    for (int n = levels - 1; n >= 0; n--) {
+        v.dim[n] = ld[n];
+        v.res[n] = 1 << ld[n];
+        v.noderange[n] = {range[n][0], range[n][1], range[n][2]};
+        v.vdel[n] = {float(range[n][0]) / float(v.res[n]), float(range[n][1]) / float(v.res[n]), float(range[n][2]) / float(v.res[n])};
+        v.nodecnt[n] = cnt0[n]; v.nodewid[n] = width0[n]; v.childwid[n] = width1[n];
+        if (cnt0[n] == 1) tlev = n;
+    }
+    v.atlas_apron = apron;
+    v.atlas_cnt = {axiscnt[0], axiscnt[1], axiscnt[2]};
+    v.atlas_res = {axisres[0], axisres[1], axisres[2]};
+    v.brick_res = axiscnt[0] > 0 ? axisres[0] / axiscnt[0] : 0;
+    for (int n = 0; n < apron && n < 4; n++) { v.apron_table[n] = n; v.apron_table[(apron * 2 - 1) - n] = (v.brick_res - 1) - n; }
+    v.top_lev = tlev; v.epsilon = mEpsilon; v.max_iter = mMaxIter;
+    v.clr_chan = GX_CHAN_UNDEF;
+    // ComputeBounds: union of the active leaves' boxes
+    if (cnt0[0] > 0) {
+        const GxNode* nd = (const GxNode*)pool0[0].data();
+        float mn[3] = {float(nd->mPos.x), float(nd->mPos.y), float(nd->mPos.z)}, mx[3] = {mn[0], mn[1], mn[2]};
+        for (int i = 0; i < cnt0[0]; i++) {
+            const GxNode* c = (const GxNode*)(pool0[0].data() + size_t(i) * width0[0]);
+            if (!c->mFlags) continue;
+            const int p[3] = {c->mPos.x, c->mPos.y, c->mPos.z};
+            for (int a = 0; a < 3; a++) {
+                if (p[a] < mn[a]) mn[a] = float(p[a]);
+                if (p[a] + range[0][a] > mx[a]) mx[a] = float(p[a] + range[0][a]);
+            }
+        }
+        v.bmin = {mn[0], mn[1], mn[2]}; v.bmax = {mx[0], mx[1], mx[2]};
+    }
+    mVDBHost = v;
+    mLevels = levels; mRoot = root;
+    for (int a = 0; a < 3; a++) { mAtlasRes[a] = axisres[a]; mAtlasCnt[a] = axiscnt[a]; }
+
+    //--- atlas section: channel 0 must be T_FLOAT (3); further channels are skipped
+    std::vector<float> atlas;
+    for (int chan = 0; chan < num_chan; chan++) {
+        int chan_type = 0, chan_stride = 0;
+        rd.get(&chan_type); rd.get(&chan_stride);
+        const size_t bytes = size_t(chan_stride) * axisres[0] * axisres[1] * axisres[2];
+        if (!rd.ok || chan_stride <= 0) return fail(GVDBX_E_ARG, "truncated atlas header");
+        if (chan == 0) {
+            if (chan_type != 3 || chan_stride != 4) return fail(GVDBX_E_UNSUPPORTED, "channel 0 is not T_FLOAT");
+            atlas.resize(bytes / 4);
+            rd.get(atlas.data(), atlas.size());
+        } else if (fseek(fp, (long)bytes, SEEK_CUR) != 0) rd.ok = false;
+    }
+    if (!rd.ok) return fail(GVDBX_E_ARG, "truncated atlas");
+    fclose(fp);
+    if (parse_only) { mPool0 = pool0; mPool1 = pool1; return GVDBX_OK; }
+    if (!mCtx) { mErr = "LoadVBX: no device context"; return GVDBX_E_STATE; }
+
+    const void* p0[10] = {}; const void* p1[10] = {}; uint64_t n1[10] = {};
+    for (int n = 0; n < levels; n++) { p0[n] = pool0[n].empty() ? nullptr : pool0[n].data(); p1[n] = pool1[n].empty() ? nullptr : pool1[n].data(); n1[n] = pool1[n].size(); }
+    int rc = ImportTopologyHost(&v, p0, p1, n1);
+    mRoot = root;
+    if (rc == GVDBX_OK && !atlas.empty()) rc = gvdbx_import_atlas_host(mCtx, 0, atlas.data(), axisres[0], axisres[1], axisres[2]);
+    return rc;
+}
+
+int VolumeGVDB::SaveVBX(const char* fname)
+{
+    mErr.clear();
+    if (!mCtx || mLevels < 1 || mPool0.empty()) { mErr = "SaveVBX: nothing imported from host pools / LoadVBX"; return GVDBX_E_STATE; }
+    const size_t texels = size_t(mAtlasRes[0]) * mAtlasRes[1] * mAtlasRes[2];
+    std::vector<float> atlas(texels);
+    int rc = gvdbx_export_atlas_host(mCtx, 0, atlas.data(), mAtlasRes[0], mAtlasRes[1], mAtlasRes[2]);
+    if (rc) return rc;
+    FILE* fp = fopen(fname, "wb");
+    if (!fp) { mErr = std::string("SaveVBX: unable to open ") + fname; return GVDBX_E_ARG; }
+    auto put = [&](const void* p, size_t bytes) { fwrite(p, 1, bytes, fp); };
+    const unsigned char major = 1, minor = 11;             // MAJOR_VERSION / MINOR_VERSION, gvdb_volume_gvdb.cpp:31-32
+    put(&major, 1); put(&minor, 1);
+    put(&mPretrans.x, 12); put(&mAngs.x, 12); put(&mScale.x, 12); put(&mTrans.x, 12);
+    const int num_grids = 1;
+    put(&num_grids, 4);
+    uint64_t grid_off = 0;
+    const long grid_table = ftell(fp);
+    put(&grid_off, 8);
+    grid_off = (uint64_t)ftell(fp);
+    char grid_name[256];
+    memset(grid_name, 0, sizeof grid_name);                // (the reference writes this field uninitialised)
+    const unsigned char dtype = 'f', components = 1, compress = 0, topotype = 2, layout = 0;
+    const float voxelsize[3] = {1, 1, 1};
+    const int leafcnt = mVDBHost.nodecnt[0], leafdim[3] = {mVDBHost.res[0], mVDBHost.res[0], mVDBHost.res[0]};
+    const int apron = mVDBHost.atlas_apron, num_chan = 1, reuse = 0;
+    const uint64_t atlas_sz = uint64_t(texels) * 4;
+    put(grid_name, 256); put(&dtype, 1); put(&components, 1); put(&compress, 1); put(voxelsize, 12);
+    put(&leafcnt, 4); put(leafdim, 12); put(&apron, 4); put(&num_chan, 4); put(&atlas_sz, 8);
+    put(&topotype, 1); put(&reuse, 4); put(&layout, 1); put(mAtlasCnt, 12); put(mAtlasRes, 12);
+    put(&mLevels, 4); put(&mRoot, 8);
+    for (int n = 0; n < mLevels; n++) {
+        const int res = mVDBHost.res[n], range[3] = {mVDBHost.noderange[n].x, mVDBHost.noderange[n].y, mVDBHost.noderange[n].z};
+        const int cnt0 = mVDBHost.nodecnt[n], width0 = mVDBHost.nodewid[n], width1 = mVDBHost.childwid[n];
+        const int cnt1 = width1 > 0 ? int(mPool1[n].size() / size_t(width1)) : 0;
+        put(&mVDBHost.dim[n], 4); put(&res, 4); put(range, 12); put(&cnt0, 4); put(&width0, 4); put(&cnt1, 4); put(&width1, 4);
+    }
+    for (int n = 0; n < mLevels; n++) put(mPool0[n].data(), mPool0[n].size());
+    for (int n = 0; n < mLevels; n++) put(mPool1[n].data(), mPool1[n].size());
+    const int chan_type = 3, chan_stride = 4;              // T_FLOAT
+    put(&chan_type, 4); put(&chan_stride, 4);
+    put(atlas.data(), atlas.size() * 4);
+    fseek(fp, grid_table, SEEK_SET);
+    put(&grid_off, 8);
+    const bool bad = ferror(fp) != 0;
+    fclose(fp);
+    if (bad) { mErr = "SaveVBX: write error"; return GVDBX_E_ARG; }
+    return GVDBX_OK;
 }
 int VolumeGVDB::ImportTopologyDevice(const void* v) { return mCtx ? gvdbx_import_topology(mCtx, v) : GVDBX_E_STATE; }
 int VolumeGVDB::ImportAtlasHost(int chan, const float* t, int rx, int ry, int rz)
@@ -437,6 +635,10 @@ int gvdbxh_import_topology_host(gvdbxh_volume* h, const void* v, const void* con
     return h->v.ImportTopologyHost(v, p0, p1, n1);
 }
 int gvdbxh_import_atlas_host(gvdbxh_volume* h, int chan, const float* t, int rx, int ry, int rz) { return h->v.ImportAtlasHost(chan, t, rx, ry, rz); }
+int gvdbxh_load_vbx(gvdbxh_volume* h, const char* fname, int parse_only) { return h->v.LoadVBX(fname, parse_only != 0); }
+int gvdbxh_save_vbx(gvdbxh_volume* h, const char* fname) { return h->v.SaveVBX(fname); }
+void gvdbxh_vdbinfo(gvdbxh_volume* h, void* out) { memcpy(out, h->v.getVDBInfoHost(), 1232); }
+void gvdbxh_set_epsilon(gvdbxh_volume* h, float eps, int maxiter) { h->v.SetEpsilon(eps, maxiter); }
 int gvdbxh_commit_transfer(gvdbxh_volume* h) { return h->v.CommitTransferFunc(); }
 int gvdbxh_add_render_buf(gvdbxh_volume* h, int chan, int w, int hh, int bpp) { return h->v.AddRenderBuf(chan, w, hh, bpp); }
 int gvdbxh_render(gvdbxh_volume* h, int shading, int chan, int rbuf) { return h->v.Render((char)shading, (uint8_t)chan, (uint8_t)rbuf); }

@@ -12,6 +12,7 @@
 // reference's own Camera3D / Matrix4F (oracle/_ref/ref_hostdump, tests/golden/hoststate_*.bin).
 #pragma once
 #include <stdint.h>
+#include <string>
 #include <vector>
 #include "gvdbx_types.h"
 #include "../../include/gvdbx.h"
@@ -102,6 +103,14 @@ public:
     int  ImportTopologyDevice(const void* vdbinfo);
     int  ImportAtlasHost(int chan, const float* texels, int rx, int ry, int rz);
     int  ImportAtlasArray(int chan, void* cuarray, int rx, int ry, int rz);
+    // VBX files (GVDB_FILESPEC.txt; LoadVBX gvdb_volume_gvdb.cpp:507-683, SaveVBX :1626-1767).  LoadVBX parses the file on
+    // the host (transform, per-level pools, channel-0 float atlas), derives the VDBInfo block the way FinishTopology /
+    // ComputeBounds / PrepareVDB do (:1579-1593, :1792-1816, :3946-3989) and imports everything (device needed unless
+    // parse_only).  SaveVBX writes the pools kept from the last host import / LoadVBX plus the atlas read back from the GPU.
+    int  LoadVBX(const char* fname, bool parse_only = false);
+    int  SaveVBX(const char* fname);
+    void SetEpsilon(float eps, int maxiter) { mEpsilon = eps; mMaxIter = maxiter; }   // gvdb_volume_gvdb.h:334
+    const char* getVDBInfoHost() const { return (const char*)&mVDBHost; }             // as derived by LoadVBX / given to ImportTopologyHost
     int  CommitTransferFunc();                                               // :4892-4898
     int  AddRenderBuf(int chan, int width, int height, int byteperpix);      // :4164-4178
     int  ResizeRenderBuf(int chan, int width, int height, int byteperpix);   // :4211-4238
@@ -127,6 +136,15 @@ private:
     GxScnInfo mScnInfo;
     std::vector<RenderBuf> mRenderBuf;
     bool      mTransferCommitted = false;
+    // host copies for SaveVBX
+    GxVDBInfo mVDBHost;
+    std::vector<std::vector<unsigned char>> mPool0, mPool1;
+    uint64_t  mRoot = 0;
+    int       mLevels = 0, mAtlasRes[3] = {0, 0, 0}, mAtlasCnt[3] = {0, 0, 0};
+    Vec3      mPretrans, mAngs, mScale = Vec3(1, 1, 1), mTrans;
+    float     mEpsilon = 0.001f;                                             // gvdb_volume_gvdb.cpp:71-72
+    int       mMaxIter = 256;
+    std::string mErr;
     int       mLanes = 0;
 };
 
@@ -150,6 +168,10 @@ void  gvdbxh_set_res(gvdbxh_volume*, int w, int h);
 void  gvdbxh_prepare_render(gvdbxh_volume*, int w, int h, int shading, void* scninfo_out416);
 int   gvdbxh_import_topology_host(gvdbxh_volume*, const void* vdbinfo, const void* const* pool0, const void* const* pool1, const uint64_t* pool1_bytes);
 int   gvdbxh_import_atlas_host(gvdbxh_volume*, int chan, const float* texels, int rx, int ry, int rz);
+int   gvdbxh_load_vbx(gvdbxh_volume*, const char* fname, int parse_only);
+int   gvdbxh_save_vbx(gvdbxh_volume*, const char* fname);
+void  gvdbxh_vdbinfo(gvdbxh_volume*, void* out1232);
+void  gvdbxh_set_epsilon(gvdbxh_volume*, float eps, int maxiter);
 int   gvdbxh_commit_transfer(gvdbxh_volume*);
 int   gvdbxh_add_render_buf(gvdbxh_volume*, int chan, int w, int h, int bpp);
 int   gvdbxh_render(gvdbxh_volume*, int shading, int chan, int rbuf);

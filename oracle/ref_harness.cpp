@@ -63,6 +63,7 @@ int main(int argc, char** argv)
     std::string bmode = "";
     float xf[12] = {0, 0, 0, 1, 1, 1, 0, 0, 0, 0, 0, 0};
     int have_xf = 0, use_dbuf = 0, nrays = 0;
+    std::string savevbx = "";
     for (int i = 3; i < argc; i++) {
         std::string a = argv[i];
         if (a == "--modes" && i + 1 < argc) modes = argv[++i];
@@ -78,6 +79,7 @@ int main(int argc, char** argv)
         else if (a == "--mode" && i + 1 < argc) bmode = argv[++i];
         else if (a == "--xform" && i + 1 < argc) { have_xf = 1; sscanf(argv[++i], "%f,%f,%f,%f,%f,%f,%f,%f,%f,%f,%f,%f", xf, xf + 1, xf + 2, xf + 3, xf + 4, xf + 5, xf + 6, xf + 7, xf + 8, xf + 9, xf + 10, xf + 11); }
         else if (a == "--dbuf") use_dbuf = 1;
+        else if (a == "--savevbx" && i + 1 < argc) savevbx = argv[++i];
         else if (a == "--spp" && i + 1 < argc) spp = atoi(argv[++i]);
         else if (a == "--raytrace" && i + 1 < argc) nrays = atoi(argv[++i]);
     }
@@ -202,6 +204,9 @@ int main(int argc, char** argv)
         }
     }
 
+
+    // --savevbx: the reference's own VBX writer (gvdb_volume_gvdb.cpp:1626-1767) on the finished volume (transform included)
+    if (!savevbx.empty()) gvdb.SaveVBX(savevbx);
 
     // ---- bench mode (bench.py --impl reference): the reference's own CUDA render through its public API
     if (bench) {

@@ -92,9 +92,29 @@ def modes2(outdir):
         print("[golden] modes2", preset, flush=True)
 
 
+def vbx(outdir):
+    """a VBX file written by the reference's own SaveVBX (with a grid transform), + the images it renders from it"""
+    xf = (3.0, -2.0, 1.5, 1.25, 0.8, 1.1, 20.0, -35.0, 10.0, 5.0, 7.0, -4.0)
+    preset = "cfg1_tiny"
+    d = tempfile.mkdtemp(prefix="refdump_")
+    path = os.path.join(d, "ref.vbx")
+    refcmp.run_ref(preset, d, modes=list(refcmp.MODES), xform=xf, savevbx=path)
+    dump = refcmp.load_dump(d)
+    out = {"preset": preset, "width": dump["meta"]["width"], "height": dump["meta"]["height"], "xform": np.array(xf, np.float32),
+           "vbx": np.fromfile(path, dtype=np.uint8), "vdbinfo": np.frombuffer(dump["vdbinfo"], np.uint8)}
+    for m in refcmp.MODES:
+        out[f"scn_{m}"] = np.frombuffer(dump["scn"][m], np.uint8)
+        out[f"rgba_{m}"] = dump["rgba"][m]
+    np.savez_compressed(os.path.join(outdir, "ref_vbx_cfg1_tiny.npz"), **out)
+    print("[golden] vbx", preset, out["vbx"].size, "bytes", flush=True)
+
+
 if __name__ == "__main__":
     out = sys.argv[1] if len(sys.argv) > 1 else os.path.join(ROOT, "gpurun_out", "golden")
     os.makedirs(out, exist_ok=True)
+    if "--vbx-only" in sys.argv:
+        vbx(out)
+        sys.exit(0)
     if "--modes2-only" in sys.argv:
         modes2(out)
         sys.exit(0)
@@ -102,3 +122,4 @@ if __name__ == "__main__":
         main(out)
     extras(out)
     modes2(out)
+    vbx(out)
