@@ -40,8 +40,18 @@ __device__ __forceinline__ int gx_safe_samples(float3 p, float3 d, float res0)
 // are then consumed strictly in order, so the sample at which the loop ends, the hit position and the accumulated
 // colour are those of the one-at-a-time loop.  Fetches behind the end of the loop are discarded (a fetch just outside
 // the brick reads apron / neighbour texels, never unmapped memory).
-#define GX_INB(q, hi)    ((q).x >= 0 && (q).y >= 0 && (q).z >= 0 && (q).x <  (hi) && (q).y <  (hi) && (q).z <  (hi))
-#define GX_INB_LE(q, hi) ((q).x >= 0 && (q).y >= 0 && (q).z >= 0 && (q).x <= (hi) && (q).y <= (hi) && (q).z <= (hi))
+// Exact in-brick tests in three integer instructions.  Non-negative floats order like their bit patterns, and every
+// negative number or NaN has a larger pattern than any non-negative finite one, so for hi > 0
+//     0 <= x && x < hi   <=>   bits(x) < bits(hi)        (likewise <=),
+// and the three axes fold into one unsigned maximum.  The only float the pattern test gets wrong is -0.0 (>= 0 is true,
+// its pattern is huge): the marchers therefore replace a -0.0 in the brick-entry point by +0.0 (gx_poszero) — no later
+// point of the march can be -0.0 then (x + y is -0.0 only if both are), and +-0.0 are interchangeable in every
+// comparison, sum and texture coordinate the march evaluates, so the samples taken are the reference's.
+__device__ __forceinline__ float gx_poszero1(float x) { const unsigned u = __float_as_uint(x); return __uint_as_float(u == 0x80000000u ? 0u : u); }
+__device__ __forceinline__ float3 gx_poszero(float3 p) { return make_float3(gx_poszero1(p.x), gx_poszero1(p.y), gx_poszero1(p.z)); }
+__device__ __forceinline__ unsigned gx_maxbits(float3 q) { return max(max(__float_as_uint(q.x), __float_as_uint(q.y)), __float_as_uint(q.z)); }
+#define GX_INB(q, hi)    (gx_maxbits(q) <  __float_as_uint(hi))
+#define GX_INB_LE(q, hi) (gx_maxbits(q) <= __float_as_uint(hi))
 #define GX_STEP_FMA(dst, src) { (dst).x = __fmaf_rn(st, dir.x, (src).x); (dst).y = __fmaf_rn(st, dir.y, (src).y); (dst).z = __fmaf_rn(st, dir.z, (src).z); }
 #define GX_STEP_ADD(dst, src) { (dst).x = __fadd_rn((src).x, wpt.x); (dst).y = __fadd_rn((src).y, wpt.y); (dst).z = __fadd_rn((src).z, wpt.z); }
 
@@ -59,14 +69,11 @@ __device__ __forceinline__ void gx2_brick_trilinear(const GxParams& P, S& smp, i
     const float3 o = make_float3(float(L.vx), float(L.vy), float(L.vz));
     const float res0 = float(gx_res<S>(P, 0));
     t.x = st * ceilf(t.x / st);
-    float3 p = pos + t.x * dir - vmin;
-    int n = gx_safe_samples(p, st * dir, res0);
+    float3 p = gx_poszero(pos + t.x * dir - vmin);
     for (int iter = 0; iter < GX_MAX_ITER; iter += 4) {
         float3 p1, p2, p3;
         GX_STEP_FMA(p1, p); GX_STEP_FMA(p2, p1); GX_STEP_FMA(p3, p2);
-        bool k0 = true, k1 = true, k2 = true, k3 = true;
-        if (n >= 4) n -= 4;
-        else { n = 0; k0 = GX_INB(p, res0); k1 = GX_INB(p1, res0); k2 = GX_INB(p2, res0); k3 = GX_INB(p3, res0); }
+        const bool k0 = GX_INB(p, res0), k1 = GX_INB(p1, res0), k2 = GX_INB(p2, res0), k3 = GX_INB(p3, res0);
         const float v0 = smp.tri(p.x + o.x, p.y + o.y, p.z + o.z);
         const float v1 = smp.tri(p1.x + o.x, p1.y + o.y, p1.z + o.z);
         const float v2 = smp.tri(p2.x + o.x, p2.y + o.y, p2.z + o.z);
@@ -105,14 +112,11 @@ __device__ __forceinline__ void gx2_brick_levelset(const GxParams& P, S& smp, in
     const float3 vmin = make_float3(float(L.px), float(L.py), float(L.pz));
     const float3 o = make_float3(float(L.vx), float(L.vy), float(L.vz));
     const float res0 = float(gx_res<S>(P, 0));
-    float3 p = pos + t.x * dir - vmin;
-    int n = gx_safe_samples(p, st * dir, res0);
+    float3 p = gx_poszero(pos + t.x * dir - vmin);
     for (int iter = 0; iter < GX_MAX_ITER; iter += 4) {
         float3 p1, p2, p3;
         GX_STEP_FMA(p1, p); GX_STEP_FMA(p2, p1); GX_STEP_FMA(p3, p2);
-        bool k0 = true, k1 = true, k2 = true, k3 = true;
-        if (n >= 4) n -= 4;
-        else { n = 0; k0 = GX_INB_LE(p, res0); k1 = GX_INB_LE(p1, res0); k2 = GX_INB_LE(p2, res0); k3 = GX_INB_LE(p3, res0); }
+        const bool k0 = GX_INB_LE(p, res0), k1 = GX_INB_LE(p1, res0), k2 = GX_INB_LE(p2, res0), k3 = GX_INB_LE(p3, res0);
         const float v0 = smp.tri(p.x + o.x, p.y + o.y, p.z + o.z);
         const float v1 = smp.tri(p1.x + o.x, p1.y + o.y, p1.z + o.z);
         const float v2 = smp.tri(p2.x + o.x, p2.y + o.y, p2.z + o.z);
@@ -177,7 +181,7 @@ __device__ __forceinline__ void gx2_brick_deep(const GxParams& P, S& smp, int no
     const float3 vmin = make_float3(float(L.px), float(L.py), float(L.pz));
     const float3 o = make_float3(float(L.vx), float(L.vy), float(L.vz));
     float3 wp = pos + t.x * dir;
-    float3 p = wp - vmin;
+    float3 p = gx_poszero(wp - vmin);
     const float3 wpt = make_float3(__fmul_rn(st, dir.x), __fmul_rn(st, dir.y), __fmul_rn(st, dir.z));
     const float dt = sqrtf(gx_dot(wpt, wpt));
     const float res0 = float(gx_res<S>(P, 0));
@@ -201,13 +205,10 @@ __device__ __forceinline__ void gx2_brick_deep(const GxParams& P, S& smp, int no
             t.x += dt;
         }
     } else {
-        int n = gx_safe_samples(p, wpt, res0);
         for (int iter = 0; iter < GX_MAX_ITER && clr.w > acut; iter += 4) {
             float3 p1, p2, p3;
             GX_STEP_ADD(p1, p); GX_STEP_ADD(p2, p1); GX_STEP_ADD(p3, p2);
-            bool k0 = true, k1 = true, k2 = true, k3 = true;
-            if (n >= 4) n -= 4;
-            else { n = 0; k0 = GX_INB(p, res0); k1 = GX_INB(p1, res0); k2 = GX_INB(p2, res0); k3 = GX_INB(p3, res0); }
+            const bool k0 = GX_INB(p, res0), k1 = GX_INB(p1, res0), k2 = GX_INB(p2, res0), k3 = GX_INB(p3, res0);
             const float v0 = smp.tri(p.x + o.x, p.y + o.y, p.z + o.z);
             const float v1 = smp.tri(p1.x + o.x, p1.y + o.y, p1.z + o.z);
             const float v2 = smp.tri(p2.x + o.x, p2.y + o.y, p2.z + o.z);
