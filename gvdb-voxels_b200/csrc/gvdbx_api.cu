@@ -503,7 +503,7 @@ extern "C" int gvdbx_render(gvdbx_t* h, const void* scninfo, int shade_mode, int
     if (!k) return gx_fail(h, GVDBX_E_UNSUPPORTED, "no kernel variant for this mode / sampler / option combination");
     dim3 block(h->block_w, h->block_h, 1);
     dim3 grid((P.x1 - P.x0 + block.x - 1) / block.x, (P.y1 - P.y0 + block.y - 1) / block.y, 1);
-    k<<<grid, block, 0, h->stream>>>(P);
+    k<<<grid, block, size_t(block.x) * block.y * GX_STACK_BYTES_PER_THREAD, h->stream>>>(P);
     GX_CUDA(h, cudaGetLastError());
     if (dbg_tmp) { cudaStreamSynchronize(h->stream); cudaFree(dbg_tmp); }
     return GVDBX_OK;
@@ -525,7 +525,7 @@ extern "C" int gvdbx_render_debug(gvdbx_t* h, const void* scninfo, int shade_mod
     if (!k) return gx_fail(h, GVDBX_E_UNSUPPORTED, "no kernel variant for this mode / sampler combination");
     dim3 block(h->block_w, h->block_h, 1);
     dim3 grid((P.width + block.x - 1) / block.x, (P.height + block.y - 1) / block.y, 1);
-    k<<<grid, block, 0, h->stream>>>(P);
+    k<<<grid, block, size_t(block.x) * block.y * GX_STACK_BYTES_PER_THREAD, h->stream>>>(P);
     GX_CUDA(h, cudaGetLastError());
     return GVDBX_OK;
 }
@@ -559,7 +559,7 @@ extern "C" int gvdbx_render_tiles(gvdbx_t* h, const void* scninfo, int shade_mod
     if (!k) return gx_fail(h, GVDBX_E_UNSUPPORTED, "no kernel variant for this mode / sampler combination");
     dim3 block(h->block_w, h->block_h, 1);
     dim3 grid((tile_size / h->block_w) * (tile_size / h->block_h), slots, 1);
-    k<<<grid, block, 0, h->stream>>>(P);
+    k<<<grid, block, size_t(block.x) * block.y * GX_STACK_BYTES_PER_THREAD, h->stream>>>(P);
     GX_CUDA(h, cudaGetLastError());
     return GVDBX_OK;
 }
@@ -589,7 +589,7 @@ extern "C" int gvdbx_render_tiles_direct(gvdbx_t* h, const void* scninfo, int sh
     if (!k) return gx_fail(h, GVDBX_E_UNSUPPORTED, "no kernel variant for this mode / sampler combination");
     dim3 block(h->block_w, h->block_h, 1);
     dim3 grid((tile_size / h->block_w) * (tile_size / h->block_h), slots, 1);
-    k<<<grid, block, 0, h->stream>>>(P);
+    k<<<grid, block, size_t(block.x) * block.y * GX_STACK_BYTES_PER_THREAD, h->stream>>>(P);
     GX_CUDA(h, cudaGetLastError());
     return GVDBX_OK;
 }
@@ -806,11 +806,11 @@ extern "C" int gvdbx_raytrace(gvdbx_t* h, const void* scninfo, int chan, uint64_
     P.dbuf = nullptr;                                   // per-pixel depth buffers do not apply to ray bundles
     const unsigned blocks = (num_rays + 63) / 64;       // 64-thread CTAs like the reference launch
     if (h->sampler == GX_SAMPLER_TEX) {
-        if (h->uniform3) gx_raytrace_kernel<GX_SAMPLER_TEX, true><<<blocks, 64, 0, h->stream>>>(P, (float*)rays_d, num_rays, bias);
-        else             gx_raytrace_kernel<GX_SAMPLER_TEX, false><<<blocks, 64, 0, h->stream>>>(P, (float*)rays_d, num_rays, bias);
+        if (h->uniform3) gx_raytrace_kernel<GX_SAMPLER_TEX, true><<<blocks, 64, 64 * GX_STACK_BYTES_PER_THREAD, h->stream>>>(P, (float*)rays_d, num_rays, bias);
+        else             gx_raytrace_kernel<GX_SAMPLER_TEX, false><<<blocks, 64, 64 * GX_STACK_BYTES_PER_THREAD, h->stream>>>(P, (float*)rays_d, num_rays, bias);
     } else {
-        if (h->uniform3) gx_raytrace_kernel<GX_SAMPLER_LINEAR, true><<<blocks, 64, 0, h->stream>>>(P, (float*)rays_d, num_rays, bias);
-        else             gx_raytrace_kernel<GX_SAMPLER_LINEAR, false><<<blocks, 64, 0, h->stream>>>(P, (float*)rays_d, num_rays, bias);
+        if (h->uniform3) gx_raytrace_kernel<GX_SAMPLER_LINEAR, true><<<blocks, 64, 64 * GX_STACK_BYTES_PER_THREAD, h->stream>>>(P, (float*)rays_d, num_rays, bias);
+        else             gx_raytrace_kernel<GX_SAMPLER_LINEAR, false><<<blocks, 64, 64 * GX_STACK_BYTES_PER_THREAD, h->stream>>>(P, (float*)rays_d, num_rays, bias);
     }
     GX_CUDA(h, cudaGetLastError());
     return GVDBX_OK;

@@ -267,26 +267,27 @@ __device__ __forceinline__ float3 gx_ray_box(float3 rpos, float3 rdir, float3 vm
 struct GxDDA {
     float3 pos, dir;
     float3 inv;     // MUFU.RCP of dir, taken once per ray
-    int3   pStep;
     float3 tDel;
     float3 t;
     int3   p;
     float3 tSide;
-    int3   mask;
+    bool   mx, my, mz;      // axis mask of the pending step (the reference's int3 mask, kept as predicates)
 
     __device__ __forceinline__ void set_ray(float3 startPos, float3 startDir, float3 startT)
     {
         pos = startPos; dir = startDir;
         inv = make_float3(gx_rcp_approx(dir.x), gx_rcp_approx(dir.y), gx_rcp_approx(dir.z));
-        pStep = make_int3((dir.x > 0) ? 1 : -1, (dir.y > 0) ? 1 : -1, (dir.z > 0) ? 1 : -1);
         t = startT;
     }
+    // pStep = isign3(dir): +1 for dir > 0, else -1 (also for 0)           cuda_math.cuh:1541-1545
+    // (not stored: one compare + select where it is used costs less than three live registers)
+    __device__ __forceinline__ float3 fstep() const { return make_float3((dir.x > 0) ? 1.0f : -1.0f, (dir.y > 0) ? 1.0f : -1.0f, (dir.z > 0) ? 1.0f : -1.0f); }
     // cuda_gvdb_dda.cuh:61-66
     __device__ __forceinline__ void prepare(float3 vmin, float3 vdel)
     {
         tDel = gx_fabs(vdel * inv);                 // vdel / dir
         float3 pFlt = (pos + t.x * dir - vmin) / vdel;
-        tSide = ((gx_floor(pFlt) - pFlt + 0.5f) * gx_f3(pStep) + 0.5) * tDel + t.x;
+        tSide = ((gx_floor(pFlt) - pFlt + 0.5f) * fstep() + 0.5) * tDel + t.x;
         p = gx_i3(gx_floor(pFlt));
     }
     // cuda_gvdb_dda.cuh:70-75 (brick: child size 1, no "+ t.x")
@@ -294,23 +295,29 @@ struct GxDDA {
     {
         tDel = gx_fabs(inv);                        // 1.0f / dir
         float3 pFlt = pos + t.x * dir - vmin;
-        tSide = ((gx_floor(pFlt) - pFlt + 0.5f) * gx_f3(pStep) + 0.5) * tDel;
+        tSide = ((gx_floor(pFlt) - pFlt + 0.5f) * fstep() + 0.5) * tDel;
         p = gx_i3(gx_floor(pFlt));
     }
     // cuda_gvdb_dda.cuh:78-83 (tie rules: x beats z on <=, y beats x, z beats y)
     __device__ __forceinline__ void next()
     {
-        mask.x = int((tSide.x < tSide.y) & (tSide.x <= tSide.z));
-        mask.y = int((tSide.y < tSide.z) & (tSide.y <= tSide.x));
-        mask.z = int((tSide.z < tSide.x) & (tSide.z <= tSide.y));
-        t.y = mask.x ? tSide.x : (mask.y ? tSide.y : tSide.z);
+        mx = (tSide.x < tSide.y) & (tSide.x <= tSide.z);
+        my = (tSide.y < tSide.z) & (tSide.y <= tSide.x);
+        mz = (tSide.z < tSide.x) & (tSide.z <= tSide.y);
+        t.y = mx ? tSide.x : (my ? tSide.y : tSide.z);
     }
-    // cuda_gvdb_dda.cuh:86-90
+    // cuda_gvdb_dda.cuh:86-90: tSide += float(mask) * tDel (a 0 mask still multiplies: 0 * inf = NaN on an axis-parallel
+    // ray, exactly like the reference), p += mask * pStep.  The float mask comes from a select, not an int -> float
+    // conversion (quarter-rate pipe).
     __device__ __forceinline__ void step()
     {
         t.x = t.y;
-        tSide += gx_f3(mask) * tDel;
-        p.x += mask.x * pStep.x; p.y += mask.y * pStep.y; p.z += mask.z * pStep.z;
+        tSide.x = fmaf(mx ? 1.0f : 0.0f, tDel.x, tSide.x);
+        tSide.y = fmaf(my ? 1.0f : 0.0f, tDel.y, tSide.y);
+        tSide.z = fmaf(mz ? 1.0f : 0.0f, tDel.z, tSide.z);
+        p.x += mx ? ((dir.x > 0) ? 1 : -1) : 0;
+        p.y += my ? ((dir.y > 0) ? 1 : -1) : 0;
+        p.z += mz ? ((dir.z > 0) ? 1 : -1) : 0;
     }
 };
 
@@ -509,7 +516,7 @@ __device__ __forceinline__ void gx_brick_deep(const GxParams& P, S& smp, int nod
 // ------------------------------------------------------------------------------------------------ master ray cast
 // Iterative hierarchical 3-D DDA over the compact tables.               cuda_gvdb_raycast.cuh:543-611
 // The per-level stack (node id, tMax) is kept in registers: only levels 1..4 can hold state.
-struct GxStack {
+struct GxStackReg {            // register-resident variant (used by the A/B packet traversal)
     int   n1, n2, n3, n4;
     float m1, m2, m3, m4;
     __device__ __forceinline__ void set(int lev, int n, float m)
@@ -519,6 +526,22 @@ struct GxStack {
     }
     __device__ __forceinline__ int   node(int lev) const { return lev == 1 ? n1 : (lev == 2 ? n2 : (lev == 3 ? n3 : n4)); }
     __device__ __forceinline__ float tmax(int lev) const { return lev == 1 ? m1 : (lev == 2 ? m2 : (lev == 3 ? m3 : m4)); }
+};
+// Default: the (node, tMax) pair of every level 1..4 lives in dynamic shared memory, [level - 1][thread] — one STS / LDS
+// per access, conflict-free, no select chains and eight registers fewer than the register-resident form (the reference:
+// two dynamically indexed local-memory arrays).  GX_STACK_BYTES_PER_THREAD of dynamic shared memory per thread.
+#define GX_STACK_BYTES_PER_THREAD 32
+struct GxStack {
+    static __device__ __forceinline__ int* base() { extern __shared__ int gx_stack_smem[]; return gx_stack_smem; }
+    static __device__ __forceinline__ int  slot(int lev)
+    {
+        const int nt = blockDim.x * blockDim.y;
+        return (lev - 1) * nt + threadIdx.y * blockDim.x + threadIdx.x;
+    }
+    static __device__ __forceinline__ int  half() { return 4 * blockDim.x * blockDim.y; }
+    __device__ __forceinline__ void  set(int lev, int n, float m) const { base()[slot(lev)] = n; base()[half() + slot(lev)] = __float_as_int(m); }
+    __device__ __forceinline__ int   node(int lev) const { return base()[slot(lev)]; }
+    __device__ __forceinline__ float tmax(int lev) const { return __int_as_float(base()[half() + slot(lev)]); }
 };
 
 // four-samples-per-round brick marchers (gvdbx_trace.cuh)
@@ -535,7 +558,6 @@ __device__ __forceinline__ void gx_raycast(const GxParams& P, S& smp, float3 pos
                                            int px, int py)
 {
     GxStack st;
-    st.n1 = st.n2 = st.n3 = st.n4 = 0; st.m1 = st.m2 = st.m3 = st.m4 = 0.f;
     int lev = P.top_lev;
     cnt.rays++;
     float3 tStart = gx_ray_box(pos, dir, P.bmin, P.bmax);

@@ -238,7 +238,7 @@ __device__ __forceinline__ void gx2_brick_deep(const GxParams& P, S& smp, int no
 // ------------------------------------------------------------------------------------------------ traversal state
 struct GxTrav {
     GxDDA   dda;
-    GxStack st;
+    GxStackReg st;
     int     lev, iter;
     float   tDepth;
     bool    alive;
