@@ -33,6 +33,10 @@ struct gvdbx_ctx {
     float*              d_bricks = nullptr;
     GxRange*            d_range = nullptr;      // per brick slot
     GxRange*            d_leaf_range = nullptr; // per leaf (valid when topology and atlas are both imported)
+    unsigned long long* d_vmask = nullptr;      // SHADE_VOXEL occupancy bits per leaf for THRESH == vmask_thresh
+    uint32_t            vmask_thresh_bits = 0;
+    bool                vmask_valid = false;
+    int                 use_vmask = 1;
     size_t              nslots = 0;
     int                 cull = 1;
     int                 ares[3] = {0, 0, 0};
@@ -84,6 +88,8 @@ static void gx_free_topology(gvdbx_t* h)
 {
     if (h->d_leaf_range) cudaFree(h->d_leaf_range);
     h->d_leaf_range = nullptr;
+    if (h->d_vmask) cudaFree(h->d_vmask);
+    h->d_vmask = nullptr; h->vmask_valid = false;
     for (int l = 0; l < GX_MAXLEV; l++) {
         if (h->d_child[l]) cudaFree(h->d_child[l]);
         if (h->d_npos[l]) cudaFree(h->d_npos[l]);
@@ -103,6 +109,7 @@ static void gx_free_atlas(gvdbx_t* h)
     if (h->d_range) cudaFree(h->d_range);
     if (h->d_leaf_range) cudaFree(h->d_leaf_range);
     h->d_leaf_range = nullptr;
+    h->vmask_valid = false;
     h->tex = 0; h->own_array = nullptr; h->d_bricks = nullptr; h->d_range = nullptr; h->have_atlas = false;
 }
 
@@ -134,6 +141,7 @@ extern "C" int gvdbx_set_option(gvdbx_t* h, int option, int value)
     case GVDBX_OPT_SPP: if (value < 1 || value > 64) return gx_fail(h, GVDBX_E_ARG, "spp must be 1..64"); h->spp = value; break;
     case GVDBX_OPT_DEEP_SHADOW: h->deep_shadow = value ? 1 : 0; break;
     case GVDBX_OPT_STREAM_MEMOPS: h->memops = value ? 1 : 0; break;
+    case GVDBX_OPT_VOXEL_MASK: h->use_vmask = value ? 1 : 0; break;
     case GVDBX_OPT_TRAVERSAL: if (value < 0 || value > 2) return gx_fail(h, GVDBX_E_ARG, "traversal must be 0, 1 or 2"); h->literal = value; break;
     default: return gx_fail(h, GVDBX_E_ARG, "unknown option");
     }
@@ -147,12 +155,33 @@ extern "C" int gvdbx_set_option(gvdbx_t* h, int option, int value)
 // per-leaf value ranges need both the leaf table (topology) and the slot ranges (atlas): built by whichever comes last
 static int gx_update_leaf_ranges(gvdbx_t* h)
 {
+    h->vmask_valid = false;                             // topology or atlas changed
+    if (h->d_vmask) { cudaFree(h->d_vmask); h->d_vmask = nullptr; }
     if (h->d_leaf_range) { cudaFree(h->d_leaf_range); h->d_leaf_range = nullptr; }
     if (!h->have_topo || !h->d_range || !h->d_leaf) return GVDBX_OK;
     const int n = h->vdb.nodecnt[0];
     GX_CUDA(h, cudaMalloc(&h->d_leaf_range, size_t(n) * sizeof(GxRange)));
     gx_leaf_ranges<<<(n + 255) / 256, 256, 0, h->stream>>>(h->d_leaf, n, h->d_range, (int)h->nslots, h->d_leaf_range);
     GX_CUDA(h, cudaGetLastError());
+    return GVDBX_OK;
+}
+
+// SHADE_VOXEL occupancy bits for the frame's THRESH: rebuilt (one pass over the brick-major atlas) only when THRESH, the
+// atlas or the topology changed.  Frames in flight on other lanes may still read the old bits: drain them first.
+static int gx_ensure_voxel_mask(gvdbx_t* h, float thresh)
+{
+    uint32_t bits;
+    memcpy(&bits, &thresh, 4);
+    if (h->vmask_valid && bits == h->vmask_thresh_bits) return GVDBX_OK;
+    const int n = h->vdb.nodecnt[0];
+    for (cudaStream_t s : h->lanes) GX_CUDA(h, cudaStreamSynchronize(s));
+    GX_CUDA(h, cudaStreamSynchronize(h->base_stream));
+    if (!h->d_vmask) GX_CUDA(h, cudaMalloc(&h->d_vmask, size_t(n) * 64));
+    gx_build_voxel_mask<<<n, 64, 0, h->stream>>>(h->d_leaf, n, h->d_bricks, thresh, (unsigned char*)h->d_vmask);
+    GX_CUDA(h, cudaGetLastError());
+    GX_CUDA(h, cudaStreamSynchronize(h->stream));
+    h->vmask_thresh_bits = bits;
+    h->vmask_valid = true;
     return GVDBX_OK;
 }
 
@@ -458,6 +487,12 @@ static int gx_fill_params(gvdbx_t* h, const void* scninfo, int shade_mode, int c
     P.leaf = h->d_leaf;
     P.tex = h->tex; P.bricks = h->d_bricks;
     P.range = h->cull ? h->d_leaf_range : nullptr;
+    P.vmask = nullptr;
+    if (mode == GX_MODE_VOXEL && h->use_vmask && v.res[0] == 8) {
+        const int rc = gx_ensure_voxel_mask(h, s.thresh.x);
+        if (rc) return rc;
+        P.vmask = h->d_vmask;
+    }
     P.counters = h->d_counters;
     P.out_stride = s.width;
     P.x0 = 0; P.y0 = 0; P.x1 = s.width; P.y1 = s.height;

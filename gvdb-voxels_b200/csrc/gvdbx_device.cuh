@@ -92,6 +92,7 @@ struct GxParams {
     cudaTextureObject_t tex;             // caller's 3-D array, linear filter, unnormalised, clamp
     const float*        bricks;          // brick-major copy
     const GxRange*      range;           // value range per LEAF (same index as `leaf`); null = no culling
+    const unsigned long long* vmask;     // SHADE_VOXEL: per leaf 8 x 64 bits, bit (z, y * 8 + x) = voxel value > THRESH; null = fetch
     // ---- output
     uchar4*  out;
     float4*  dbg;                        // 3 x 16 B per pixel (debug variant only)
@@ -379,10 +380,36 @@ __device__ __forceinline__ void gx_brick_voxel(const GxParams& P, S& smp, int no
     dda.set_ray(pos, dir, t);
     dda.prepare_leaf(vmin);
 
+    // Occupancy bits instead of one dependent point fetch per voxel step: `value > THRESH` was evaluated once per voxel
+    // when THRESH was set (gx_build_voxel_mask, on the exact texel values a centre fetch returns), so the per-step test is
+    // a bit test on a 64-bit z-slice that is reloaded only when the ray changes slice.
+    const unsigned long long* mk = (P.vmask != nullptr && res0 == 8) ? P.vmask + size_t(nodeid) * 8 : nullptr;
+    unsigned long long slice = 0;
+    int slice_z = -1;
+    // A brick DDA only ever moves away from its entry voxel in the direction of the ray, so every voxel it can visit
+    // lies in the "forward octant" box of the entry voxel.  No occupancy bit in that box = no hit in this brick, whatever
+    // the exact path: skip the voxel walk (the work counters of the reference semantics are kept by the COUNT variant,
+    // which does not take this shortcut: P.range == nullptr there).
+    if (mk != nullptr && P.range != nullptr && unsigned(dda.p.x | dda.p.y | dda.p.z) < 8u) {
+        const unsigned xm = dir.x > 0 ? (0xFFu << dda.p.x) & 0xFFu : 0xFFu >> (7 - dda.p.x);
+        const unsigned long long ym = dir.y > 0 ? ~0ull << (8 * dda.p.y) : ~0ull >> (8 * (7 - dda.p.y));
+        const unsigned long long m2 = (0x0101010101010101ull * xm) & ym;
+        const int z0 = dir.z > 0 ? dda.p.z : 0, z1 = dir.z > 0 ? 7 : dda.p.z;
+        unsigned long long any = 0;
+        for (int z = z0; z <= z1; z++) any |= __ldg(mk + z) & m2;
+        if (any == 0) return;
+    }
     // 0 <= p < res0 on every axis (res0 is a power of two) == one unsigned compare on the OR of the coordinates
     for (int iter = 0; iter < GX_MAX_ITER && unsigned(dda.p.x | dda.p.y | dda.p.z) < unsigned(res0); iter++) {
         cnt.s_pt++;
-        if (smp.point(dda.p.x + o.x + .5, dda.p.y + o.y + .5, dda.p.z + o.z + .5) > P.thresh.x) {
+        bool solid;
+        if (mk != nullptr) {
+            if (dda.p.z != slice_z) { slice_z = dda.p.z; slice = __ldg(mk + slice_z); }
+            solid = (slice >> (dda.p.y * 8 + dda.p.x)) & 1ull;
+        } else {
+            solid = smp.point(dda.p.x + o.x + .5, dda.p.y + o.y + .5, dda.p.z + o.z + .5) > P.thresh.x;
+        }
+        if (solid) {
             vmin += gx_f3(dda.p);
             dda.t = gx_ray_box(pos, dir, vmin, vmin + 1);
             if (dda.t.z == GX_NOHIT) {      // reference quirk: no step, vmin keeps accumulating (raycast.cuh:244-247)

@@ -171,6 +171,24 @@ __global__ void gx_brick_ranges(const float* __restrict__ bricks, GxRange* __res
     }
 }
 
+// SHADE_VOXEL occupancy bits: for every leaf, bit (z, y * 8 + x) of word z = (interior voxel (x, y, z) > thresh).  The
+// comparison is the one raySurfaceVoxelBrick makes per DDA step (cuda_gvdb_raycast.cuh:241) on the value a texel-centre
+// fetch returns, i.e. the stored texel itself.  One 64-thread CTA per leaf, one byte (a row of 8 voxels) per thread.
+__global__ void gx_build_voxel_mask(const GxLeafRec* __restrict__ leaf, int nleaf, const float* __restrict__ bricks, float thresh,
+                                    unsigned char* __restrict__ out)
+{
+    const int n = blockIdx.x;
+    if (n >= nleaf) return;
+    const int z = threadIdx.x >> 3, y = threadIdx.x & 7;
+    unsigned bits = 0;
+    if (leaf[n].vx >= 0) {
+        const float* row = bricks + size_t(leaf[n].base) + ((z + 1) * GX_BRICK_DIM + (y + 1)) * GX_BRICK_DIM + 1;
+        #pragma unroll
+        for (int x = 0; x < 8; x++) bits |= (row[x] > thresh ? 1u : 0u) << x;
+    }
+    out[size_t(n) * 64 + z * 8 + y] = (unsigned char)bits;
+}
+
 // ------------------------------------------------------------------------------------------------ cross-GPU flags
 // one thread: release-store of a sequence number (the frame's pixels were stored by kernels earlier in the stream)
 __global__ void gx_signal_kernel(unsigned int* flag, unsigned int value)

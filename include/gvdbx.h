@@ -61,6 +61,8 @@ extern "C" {
 #define GVDBX_OPT_DEEP_SHADOW 8 /* 1 = SHADE_VOLUME casts one shadow march (rayShadowBrick, kernels/cuda_gvdb_raycast.cuh:445-463) from
                                    the first sample towards the light and darkens the accumulated colour (BASELINE.json config 4) */
 #define GVDBX_OPT_STREAM_MEMOPS 9 /* 1 = gvdbx_stream_wait uses cuStreamWaitValue32 (front-end wait, unbounded) instead of the bounded polling kernel */
+#define GVDBX_OPT_VOXEL_MASK 10 /* 1 (default) = SHADE_VOXEL tests per-brick occupancy bits (value > THRESH, rebuilt when THRESH or the atlas
+                                   changes) instead of one point fetch per voxel step; 0 = fetch (A/B) */
 #define GVDBX_OPT_TRAVERSAL 5   /* 0 = default (four-samples-per-round brick marchers), 1 = reference-shaped loops, one sample at a time (A/B),
                                    2 = vote-converged two-phase packet traversal (A/B) */
 
