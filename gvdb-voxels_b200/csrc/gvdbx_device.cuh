@@ -754,7 +754,10 @@ __device__ __forceinline__ float4 gx_shade_pixel(const GxParams& P, S& smp, int 
 #define GX_FLAG_SPP     32     // P.spp sub-pixel samples per pixel, averaged in float before packing
 
 template <int MODE, int SAMPLER, int FLAGS, bool UNI>
-__global__ void __launch_bounds__(256, 4) gx_render_kernel(const __grid_constant__ GxParams P)
+#ifndef GX_MINBLOCKS
+#define GX_MINBLOCKS 4
+#endif
+__global__ void __launch_bounds__(256, GX_MINBLOCKS) gx_render_kernel(const __grid_constant__ GxParams P)
 {
     int x, y;
     size_t opix;

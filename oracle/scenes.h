@@ -196,7 +196,15 @@ static inline int scene_generate(const scene_preset* p, scene_data* out)
         return 0;
     }
 
-    for (int bz = 0; bz < nb; bz++) for (int by = 0; by < nb; by++) for (int bx = 0; bx < nb; bx++) {
+    /* one z-slab of bricks per task (OpenMP when the including file is compiled with it); slabs are concatenated in z
+     * order afterwards, so the brick order — the ActivateSpace order — does not depend on the thread count */
+    scene_data* slab = (scene_data*)calloc((size_t)nb, sizeof(scene_data));
+    #pragma omp parallel for schedule(dynamic, 1)
+    for (int bz = 0; bz < nb; bz++) {
+        int scap = 0;
+        float v8[512];
+        scene_data* out_s = &slab[bz];
+        for (int by = 0; by < nb; by++) for (int bx = 0; bx < nb; bx++) {
         if (p->kind == SCN_KIND_SPHERE || p->kind == SCN_KIND_CLOUD) {
             /* cheap reject: brick farther than R + brick diagonal from the centre */
             float c = 0.5f * (float)p->N;
@@ -207,10 +215,10 @@ static inline int scene_generate(const scene_preset* p, scene_data* out)
             for (int k = 0; k < 8; k++) for (int j = 0; j < 8; j++) for (int i = 0; i < 8; i++) {
                 float v = (p->kind == SCN_KIND_SPHERE) ? scn_sphere_val(p, bx * 8 + i, by * 8 + j, bz * 8 + k)
                                                        : scn_cloud_val(p, bx * 8 + i, by * 8 + j, bz * 8 + k);
-                vals[(k * 8 + j) * 8 + i] = v;
+                v8[(k * 8 + j) * 8 + i] = v;
                 any |= (v > 0.f);
             }
-            if (any) scn_push_brick(out, &cap, bx * 8, by * 8, bz * 8, vals);
+            if (any) scn_push_brick(out_s, &scap, bx * 8, by * 8, bz * 8, v8);
         } else { /* SCN_KIND_SDF: narrow band, half-width `band` = 12 voxels tested at the brick centre */
             const float band = 12.0f;
             float c = 0.5f * (float)p->N;
@@ -222,11 +230,27 @@ static inline int scene_generate(const scene_preset* p, scene_data* out)
             for (int k = 0; k < 8; k++) for (int j = 0; j < 8; j++) for (int i = 0; i < 8; i++) {
                 float v = scn_sdf_raw(p, bx * 8 + i + 0.5f, by * 8 + j + 0.5f, bz * 8 + k + 0.5f);
                 v = v < -band ? -band : (v > band ? band : v);
-                vals[(k * 8 + j) * 8 + i] = v;
+                v8[(k * 8 + j) * 8 + i] = v;
             }
-            scn_push_brick(out, &cap, bx * 8, by * 8, bz * 8, vals);
+            scn_push_brick(out_s, &scap, bx * 8, by * 8, bz * 8, v8);
+        }
         }
     }
+    size_t total = 0;
+    for (int bz = 0; bz < nb; bz++) total += (size_t)slab[bz].nbricks;
+    out->brick_pos = (int32_t*)malloc(sizeof(int32_t) * 3 * (total ? total : 1));
+    out->values = (float*)malloc(sizeof(float) * 512 * (total ? total : 1));
+    for (int bz = 0; bz < nb; bz++) {
+        size_t n = (size_t)slab[bz].nbricks;
+        if (n) {
+            memcpy(out->brick_pos + 3 * (size_t)out->nbricks, slab[bz].brick_pos, sizeof(int32_t) * 3 * n);
+            memcpy(out->values + 512 * (size_t)out->nbricks, slab[bz].values, sizeof(float) * 512 * n);
+            out->nbricks += (int)n;
+        }
+        free(slab[bz].brick_pos); free(slab[bz].values);
+    }
+    free(slab);
+    (void)cap; (void)vals;
     return 0;
 }
 
@@ -286,6 +310,17 @@ static inline int scene_get_preset(const char* name, scene_preset* p)
         scn_set3(p->cam_angs, 20.f, 30.f, 0.f); scn_set3(p->cam_target, 256.f * s, 256.f * s, 256.f * s); p->cam_dist = 1000.f * s;
         scn_set3(p->light_target, 264.f * s, -40.f * s, 100.f * s); p->light_dist = 400.f * s;
         scn_set3(p->steps, .25f, 16.f, .25f); scn_set3(p->extinct, -1.0f, 1.5f, 0.f);
+        scn_set3(p->thresh, 0.1f, 0.f, 1.f); scn_set3(p->cutoff, .005f, .01f, 0.f);
+        p->transfer = 1;
+    } else if (!strncmp(name, "cfg5", 4)) {     /* large noise cloud (~2.0 M bricks, ~8 GB atlas at full size), deep, 4 rays per pixel, 7680x4320 */
+        p->kind = SCN_KIND_CLOUD; p->N = tiny ? 64 : (small ? 256 : 4096);
+        float s = p->N / 4096.f;
+        p->a = 625.f * s; p->b = 0.6f; p->c = 256.f * (tiny ? 0.0625f : (small ? 0.125f : 1.f));
+        p->width = tiny ? 96 : (small ? 480 : 7680); p->height = tiny ? 54 : (small ? 270 : 4320);
+        p->shade = SCN_SHADE_VOLUME; p->fov = 40.f;
+        scn_set3(p->cam_angs, 30.f, 25.f, 0.f); scn_set3(p->cam_target, 2048.f * s, 2048.f * s, 2048.f * s); p->cam_dist = 7000.f * s;
+        scn_set3(p->light_target, 2112.f * s, -320.f * s, 800.f * s); p->light_dist = 3200.f * s;
+        scn_set3(p->steps, .5f, 16.f, .5f); scn_set3(p->extinct, -1.0f, 1.5f, 0.f);
         scn_set3(p->thresh, 0.1f, 0.f, 1.f); scn_set3(p->cutoff, .005f, .01f, 0.f);
         p->transfer = 1;
     } else {

@@ -460,6 +460,22 @@ def test_live_reference_remaining_modes(pkg, torch_cuda, tmp_path):
         assert res[m]["tex"].get("hit_mismatch_pixels", 0) == 0 and res[m]["tex"].get("norm_mismatch_pixels", 0) == 0
 
 
+@pytest.mark.skipif(not refcmp.have_ref(), reason="oracle/_ref not built")
+def test_live_reference_cfg5_small_deep_4spp(pkg, torch_cuda, tmp_path):
+    """BASELINE config 5 (large noise cloud, deep, 4 rays per pixel) at its small size against the reference run now:
+    plain deep, deep + shadow and the 4-spp average bit-exact."""
+    d = str(tmp_path / "dump")
+    refcmp.run_ref("cfg5_small", d, modes=["deep", "deepshadow", "deepspp"])
+    dump = refcmp.load_dump(d)
+    assert dump["meta"]["bricks"] > 500
+    res = refcmp.compare(dump, pkg, ["deep"], verbose=False)
+    assert res["deep"]["tex"]["rgba_mismatch_pixels"] == 0 and res["deep"]["tex"]["raw_clr_mismatch_pixels"] == 0
+    res2 = refcmp.compare2(dump, pkg, ["deepshadow", "deepspp"], verbose=False)
+    for m in ("deepshadow", "deepspp"):
+        assert res2[m]["tex"]["rgba_mismatch_pixels"] == 0, (m, res2[m]["tex"])
+        assert res2[m]["tex"]["nonbackground"] > 1000
+
+
 # ------------------------------------------------------------------------------------------------ peer frame ring (one GPU)
 def test_direct_tiles_and_peer_ring_single_process(scenes, torch_cuda, pkg, ora):
     """Three "ranks" in one process on one GPU (raw pointers instead of IPC handles): every rank's tile-list kernel stores
