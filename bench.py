@@ -262,6 +262,8 @@ def main():
         consumer = torch.cuda.Stream(device=dev) if rank == 0 else None
     tiled = mg.TiledFrame(r, w, h, a.tile, rank, world, dev) if (world > 1 and ring is None) else None
 
+    kpf = 2 if shade == 7 else 1        # kernels per frame: deep modes build the frame's derived transfer table first
+
     def step_resident(on_frame=None):
         """one step = all frames of the orbit; N>1: every rank renders its tiles of every frame.
         peer exchange: 2 launches per frame and rank (render + done flag), +1 on rank 0 (release flags)."""
@@ -270,11 +272,11 @@ def main():
             for j, scn in enumerate(scns):
                 r.lane_select(j % nbuf if a.lanes else -1)
                 r.render(scn, shade, frames_d[j % nbuf].data_ptr())
-                launches += 1
+                launches += kpf
         elif ring is not None:
             for scn in scns:
                 q = ring.submit(scn, shade)
-                launches += 2
+                launches += 1 + kpf
                 if rank == 0:
                     ring.acquire(q, consumer.cuda_stream)
                     if on_frame is not None:

@@ -42,6 +42,8 @@ struct gvdbx_ctx {
     int                 ares[3] = {0, 0, 0};
     // transfer function
     float4* d_transfer = nullptr;
+    std::vector<float4*> deep_lut;      // per lane (+1 for the creation stream): this frame's {rgb, exp(EXTINCT * alpha * DIRECTSTEP)}
+    int     cur_lane = -1;
     // counters
     unsigned long long* d_counters = nullptr;
     // frame lanes: internal streams that consecutive frames alternate between (the tail of frame j overlaps frame j + 1)
@@ -122,6 +124,7 @@ extern "C" int gvdbx_destroy(gvdbx_t* h)
     gx_free_topology(h);
     gx_free_atlas(h);
     if (h->d_transfer) cudaFree(h->d_transfer);
+    for (float4* p : h->deep_lut) if (p) cudaFree(p);
     if (h->d_counters) cudaFree(h->d_counters);
     delete h;
     return GVDBX_OK;
@@ -477,6 +480,16 @@ static int gx_fill_params(gvdbx_t* h, const void* scninfo, int shade_mode, int c
     if ((mode == GX_MODE_DEEP || mode == GX_MODE_DEEPSHADOW || mode == GX_MODE_SECTION2D || mode == GX_MODE_SECTION3D) && !P.transfer)
         return gx_fail(h, GVDBX_E_STATE, "transfer function not on GPU (reference: 'Must call CommitTransferFunc')");
     P.dbuf = (const float*)s.dbuf;
+    P.transfer_deep = nullptr;
+    if (mode == GX_MODE_DEEP || mode == GX_MODE_DEEPSHADOW) {
+        // this frame's derived table, in the buffer of the stream / lane the frame is enqueued on (stream-ordered, ~2 us)
+        const size_t slot = size_t(h->cur_lane + 1);
+        if (h->deep_lut.size() <= slot) h->deep_lut.resize(slot + 1, nullptr);
+        if (!h->deep_lut[slot]) GX_CUDA(h, cudaMalloc(&h->deep_lut[slot], GVDBX_TRANSFER_ENTRIES * sizeof(float4)));
+        gx_build_deep_lut<<<GVDBX_TRANSFER_ENTRIES / 256, 256, 0, h->stream>>>(P.transfer, h->deep_lut[slot], GVDBX_TRANSFER_ENTRIES, P.extinct.x, P.steps.x);
+        GX_CUDA(h, cudaGetLastError());
+        P.transfer_deep = h->deep_lut[slot];
+    }
     const GxVDBInfo& v = h->vdb;
     for (int l = 0; l < GX_MAXLEV; l++) {
         P.dim[l] = v.dim[l]; P.res[l] = v.res[l]; P.vdel[l] = f3(v.vdel[l]);
@@ -706,6 +719,7 @@ extern "C" int gvdbx_lanes(gvdbx_t* h, int n)
     if (h->base_ev) { cudaEventDestroy(h->base_ev); h->base_ev = nullptr; }
     h->lanes.clear(); h->lane_ev.clear();
     h->stream = h->base_stream;
+    h->cur_lane = -1;
     for (int i = 0; i < n; i++) {
         cudaStream_t s; cudaEvent_t e;
         GX_CUDA(h, cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
@@ -718,8 +732,9 @@ extern "C" int gvdbx_lanes(gvdbx_t* h, int n)
 extern "C" int gvdbx_lane_select(gvdbx_t* h, int lane)
 {
     if (!h) return GVDBX_E_ARG;
-    if (lane < 0 || h->lanes.empty()) { h->stream = h->base_stream; return GVDBX_OK; }
-    h->stream = h->lanes[lane % (int)h->lanes.size()];
+    if (lane < 0 || h->lanes.empty()) { h->stream = h->base_stream; h->cur_lane = -1; return GVDBX_OK; }
+    h->cur_lane = lane % (int)h->lanes.size();
+    h->stream = h->lanes[h->cur_lane];
     return GVDBX_OK;
 }
 extern "C" void* gvdbx_lane_stream(gvdbx_t* h, int lane)
@@ -742,6 +757,7 @@ extern "C" int gvdbx_lanes_join(gvdbx_t* h)
 {
     if (!h) return GVDBX_E_ARG;
     h->stream = h->base_stream;
+    h->cur_lane = -1;
     if (h->lanes.empty()) return GVDBX_OK;
     GX_CUDA(h, cudaSetDevice(h->device));
     for (size_t i = 0; i < h->lanes.size(); i++) {

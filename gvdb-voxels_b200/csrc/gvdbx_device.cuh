@@ -75,6 +75,7 @@ struct GxParams {
     float3   cutoff;               // x = MINVAL, y = ALPHACUT
     float3   thresh;               // x = THRESH, y = VMIN, z = VMAX
     const float4* transfer;
+    const float4* transfer_deep;       // per frame: {rgb, exp(EXTINCT * alpha * DIRECTSTEP)} of every entry (gx_build_deep_lut); null = compute per sample
     const float*  dbuf;
     // ---- tree geometry (VDBInfo fields the path reads)
     int      dim[GX_MAXLEV];

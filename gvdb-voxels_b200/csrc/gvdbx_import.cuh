@@ -116,6 +116,18 @@ __global__ void gx_sample_points_kernel(GxParams P, const float* __restrict__ xy
     out_lin[i] = s.tri(x, y, z);
 }
 
+// ------------------------------------------------------------------------------------------------ deep-mode transfer table
+// {rgb, exp(EXTINCT * alpha * DIRECTSTEP)} for every transfer-function entry: the expression of rayDeepBrick
+// (cuda_gvdb_raycast.cuh:515) evaluated once per entry and frame instead of once per sample (gx_deep_accumulate_pre).
+__global__ void gx_build_deep_lut(const float4* __restrict__ src, float4* __restrict__ dst, int n, float extinct, float step)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float4 val = src[i];
+    val.w = exp(extinct * val.w * step);
+    dst[i] = val;
+}
+
 // ------------------------------------------------------------------------------------------------ apron update
 // VolumeGVDB::UpdateApron for a float channel with apron 1 (gvdb_volume_gvdb.cpp:4418-4453, kernel
 // cuda_gvdb_operators.cuh:72-126): every texel of the six 10x10 faces of every brick takes the value of the voxel that

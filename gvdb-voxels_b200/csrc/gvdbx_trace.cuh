@@ -152,6 +152,17 @@ __device__ __forceinline__ void gx_deep_accumulate(const GxParams& P, float4& cl
     clr.z = __fadd_rn(clr.z, __fmul_rn(__fmul_rn(__fmul_rn(val.z, clr.w), om), P.extinct.y));
     clr.w *= val.w;
 }
+// The same update with the per-sample transparency exp(EXTINCT * alpha * DIRECTSTEP) already in val.w: it depends only on
+// the table entry and two frame constants, so gx_build_deep_lut evaluates it once per entry and frame with the very
+// expression above (same instruction sequence, same bits) instead of once per sample.
+__device__ __forceinline__ void gx_deep_accumulate_pre(const GxParams& P, float4& clr, float4 val)
+{
+    const float om = 1 - val.w;
+    clr.x = __fadd_rn(clr.x, __fmul_rn(__fmul_rn(__fmul_rn(val.x, clr.w), om), P.extinct.y));
+    clr.y = __fadd_rn(clr.y, __fmul_rn(__fmul_rn(__fmul_rn(val.y, clr.w), om), P.extinct.y));
+    clr.z = __fadd_rn(clr.z, __fmul_rn(__fmul_rn(__fmul_rn(val.z, clr.w), om), P.extinct.y));
+    clr.w *= val.w;
+}
 // transfer-function index (cuda_gvdb_dda.cuh:20-23): int(min(1.0, max(0.0, u)) * 16300.0f) with u = (v - THRESH) /
 // (VMAX - VMIN) a float (divide = multiply by the approximate reciprocal) and the clamp / scale / truncation in DOUBLE,
 // i.e. floor of the EXACT product clamp(u) * 16300.  Same integer without the FP64 pipe: round the product in fp32, take
@@ -215,17 +226,18 @@ __device__ __forceinline__ void gx2_brick_deep(const GxParams& P, S& smp, int no
             const float v3 = smp.tri(p3.x + o.x, p3.y + o.y, p3.z + o.z);
             const bool a0 = v0 >= minval, a1 = v1 >= minval, a2 = v2 >= minval, a3 = v3 >= minval;
             // transfer-function reads of the whole round in flight together (entry 0 for rejected samples, unused)
-            const float4 c0 = __ldg(&P.transfer[a0 ? gx_transfer_index(v0, thresh, inv_range) : 0]);
-            const float4 c1 = __ldg(&P.transfer[a1 ? gx_transfer_index(v1, thresh, inv_range) : 0]);
-            const float4 c2 = __ldg(&P.transfer[a2 ? gx_transfer_index(v2, thresh, inv_range) : 0]);
-            const float4 c3 = __ldg(&P.transfer[a3 ? gx_transfer_index(v3, thresh, inv_range) : 0]);
+            const float4* lut = P.transfer_deep;        // {rgb, exp(EXTINCT * alpha * DIRECTSTEP)}: built for this frame by the host side
+            const float4 c0 = __ldg(&lut[a0 ? gx_transfer_index(v0, thresh, inv_range) : 0]);
+            const float4 c1 = __ldg(&lut[a1 ? gx_transfer_index(v1, thresh, inv_range) : 0]);
+            const float4 c2 = __ldg(&lut[a2 ? gx_transfer_index(v2, thresh, inv_range) : 0]);
+            const float4 c3 = __ldg(&lut[a3 ? gx_transfer_index(v3, thresh, inv_range) : 0]);
             // consume in order; `done` = samples processed (each is followed by one position / t step in the reference)
             int done = 0;
             bool more = k0;             // loop condition for sample 0 (alpha was checked by the for statement)
-            if (more) { done = 1; cnt.s_tri++; if (a0) { cnt.s_lut++; gx_deep_accumulate(P, clr, c0); } more = k1 && clr.w > acut; }
-            if (more) { done = 2; cnt.s_tri++; if (a1) { cnt.s_lut++; gx_deep_accumulate(P, clr, c1); } more = k2 && clr.w > acut; }
-            if (more) { done = 3; cnt.s_tri++; if (a2) { cnt.s_lut++; gx_deep_accumulate(P, clr, c2); } more = k3 && clr.w > acut; }
-            if (more) { done = 4; cnt.s_tri++; if (a3) { cnt.s_lut++; gx_deep_accumulate(P, clr, c3); } }
+            if (more) { done = 1; cnt.s_tri++; if (a0) { cnt.s_lut++; gx_deep_accumulate_pre(P, clr, c0); } more = k1 && clr.w > acut; }
+            if (more) { done = 2; cnt.s_tri++; if (a1) { cnt.s_lut++; gx_deep_accumulate_pre(P, clr, c1); } more = k2 && clr.w > acut; }
+            if (more) { done = 3; cnt.s_tri++; if (a2) { cnt.s_lut++; gx_deep_accumulate_pre(P, clr, c2); } more = k3 && clr.w > acut; }
+            if (more) { done = 4; cnt.s_tri++; if (a3) { cnt.s_lut++; gx_deep_accumulate_pre(P, clr, c3); } }
             for (int q = 0; q < done; q++) t.x += dt;
             if (done < 4) break;        // left the brick or fell below ALPHACUT inside this round
             GX_STEP_ADD(p, p3);
