@@ -10,35 +10,18 @@
 //   * ONE traversal instance serves primary AND shadow rays: a lane whose primary ray is finished turns it into its
 //     shadow ray (performPhongShading, cuda_gvdb_module.cu:38-57) and keeps going instead of idling until the whole
 //     warp has finished the primary pass.
-//   * Inside a brick the fixed-step marchers know how many samples are certainly inside the brick (conservative
-//     bound); those are taken in batches of four with the four texture fetches in flight together and without the
-//     six boundary compares per sample; the remaining samples run the original fully-checked loop.  Sample positions
-//     are still produced by the same chain of roundings (p = fma(step, dir, p) resp. p = p + wpt), so every fetched
+//   * Inside a brick the fixed-step marchers take four samples per round with the four texture fetches in flight
+//     together; every sample's in-brick test is exact (three integer instructions on the float bit patterns).  Sample
+//     positions are produced by the same chain of roundings (p = fma(step, dir, p) resp. p = p + wpt), so every fetched
 //     value, threshold test and accumulated colour is bit-identical to the one-at-a-time loop.
 #pragma once
 #include "gvdbx_device.cuh"
 
-// Number of consecutive fixed-step samples p, p+d, p+2d, ... that are guaranteed to lie strictly inside (0,res0)^3.
-// Conservative by `m` voxels, far above the accumulated rounding of <= 256 steps (<= 256 * 0.5 ulp(8) = 1.2e-4) and
-// the error of the approximate division.
-__device__ __forceinline__ int gx_safe_samples(float3 p, float3 d, float res0)
-{
-    const float m = 4e-3f;
-    float nx = d.x > 0 ? (res0 - m - p.x) / d.x : (d.x < 0 ? (p.x - m) / -d.x : 1e9f);
-    float ny = d.y > 0 ? (res0 - m - p.y) / d.y : (d.y < 0 ? (p.y - m) / -d.y : 1e9f);
-    float nz = d.z > 0 ? (res0 - m - p.z) / d.z : (d.z < 0 ? (p.z - m) / -d.z : 1e9f);
-    const bool inside = p.x > m && p.y > m && p.z > m && p.x < res0 - m && p.y < res0 - m && p.z < res0 - m;
-    float n = fminf(fminf(nx, ny), nz);
-    if (!inside || !(n >= 0.f)) return 0;
-    return int(fminf(n, 1024.f)) + 1;
-}
-
 // ------------------------------------------------------------------------------------------------ brick samplers
-// Fixed-step marchers, four samples per round.  `n` = samples still known to be inside the brick (conservative); while
-// n >= 4 the six boundary compares per sample are skipped, afterwards every sample of a round is checked exactly as the
-// reference loop condition does.  The four fetches of a round are issued before the first result is consumed; results
-// are then consumed strictly in order, so the sample at which the loop ends, the hit position and the accumulated
-// colour are those of the one-at-a-time loop.  Fetches behind the end of the loop are discarded (a fetch just outside
+// Fixed-step marchers, four samples per round.  Every sample of a round is checked exactly as the reference loop
+// condition does (GX_INB / GX_INB_LE below).  The four fetches of a round are issued before the first result is consumed;
+// results are then consumed strictly in order, so the sample at which the loop ends, the hit position and the
+// accumulated colour are those of the one-at-a-time loop.  Fetches behind the end of the loop are discarded (a fetch just outside
 // the brick reads apron / neighbour texels, never unmapped memory).
 // Exact in-brick tests in three integer instructions.  Non-negative floats order like their bit patterns, and every
 // negative number or NaN has a larger pattern than any non-negative finite one, so for hi > 0
