@@ -472,6 +472,11 @@ def main():
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                 "peak_source": peak_src, "kernel": f"gx_render_kernel<{SHADE_NAME[shade]},{a.sampler}>",
                 "algorithmic_bytes_per_frame": alg_step / a.frames,
+                "dram_achieved": (traffic * a.frames * a.steps * a.spp / (ms_total * 1e-3) / 1e9) if traffic else None,
+                "note": "achieved = SURVEY 8(d) algorithmic bytes (32 B per trilinear sample, 8 B per DDA step, 64 B per node record, 4 B per pixel) / time: "
+                        "an EFFECTIVE bandwidth - neighbouring rays share bricks, 99 % of the sectors hit in L1 and ~78 % of the rest in L2, so measured "
+                        "DRAM traffic (`traffic`, bytes per launch; `dram_achieved`, GB/s) is ~2.5 % of it and frac exceeds 1; the kernel is bound by "
+                        "instruction issue (IPC 2.8-3.1 of 4 at 14-16 of 32 lanes, profiles/r01_ncu_summary.md), not by HBM",
                 "units_per_step": tot, "bytes_per_unit": {"s_tri": B_TRI, "s_pt": B_PT, "n_dda": B_DDA, "n_desc": B_DESC, "pixel": B_PIX}}
 
     # ---------------- CPU baselines (rank 0, N=1 only): oracle port on a bounded sample
