@@ -64,6 +64,7 @@ int main(int argc, char** argv)
     float xf[12] = {0, 0, 0, 1, 1, 1, 0, 0, 0, 0, 0, 0};
     int have_xf = 0, use_dbuf = 0, nrays = 0;
     std::string savevbx = "";
+    int lightdump = 0;
     for (int i = 3; i < argc; i++) {
         std::string a = argv[i];
         if (a == "--modes" && i + 1 < argc) modes = argv[++i];
@@ -71,6 +72,7 @@ int main(int argc, char** argv)
         else if (a == "--frames" && i + 1 < argc) frames = atoi(argv[++i]);
         else if (a == "--warmup" && i + 1 < argc) warmup = atoi(argv[++i]);
         else if (a == "--nodump") nodump = 1;
+        else if (a == "--lightdump") lightdump = 1;        // images + ScnInfo + VDBInfo only (no pools / atlas: large volumes)
         else if (a == "--shadow" && i + 1 < argc) shadow = atoi(argv[++i]);
         else if (a == "--hits" && i + 1 < argc) hits = atoi(argv[++i]);
         else if (a == "--bench") { bench = 1; nodump = 1; hits = 0; }
@@ -106,7 +108,10 @@ int main(int argc, char** argv)
     // ---- CPU topology build (timed: the reference's host-side baseline)
     t0 = now_s();
     gvdb.Configure(3, 3, 3, 3, 3);
-    gvdb.SetChannelDefault(16, 16, 1);
+    {   // 16 x 16 x N brick slots like the reference samples; 128 x 128 x N for the large volume (3-D array limit of 16384 along z)
+        const int cxy = S.nbricks > 400000 ? 128 : 16;
+        gvdb.SetChannelDefault(cxy, cxy, 1);
+    }
     gvdb.AddChannel(0, T_FLOAT, 1);
     double t_cfg = now_s() - t0;
     t0 = now_s();
@@ -251,7 +256,14 @@ int main(int argc, char** argv)
     }
 
     // ---- static dumps
-    if (!nodump) {
+    if (!nodump && lightdump) {
+        gvdb.PrepareVDB();
+        dump(outdir + "/vdbinfo.bin", gvdb.getVDBInfo(), 1232);
+        FILE* mf = fopen((outdir + "/meta.txt").c_str(), "w");
+        fprintf(mf, "preset %s\nbricks %d\nlevels %d\natlas_res %d %d %d\nwidth %d\nheight %d\n", P.name, S.nbricks, gvdb.mPool->getNumLevels(), ares.x, ares.y, ares.z, w, h);
+        fclose(mf);
+    }
+    if (!nodump && !lightdump) {
         gvdb.PrepareVDB();
         dump(outdir + "/vdbinfo.bin", gvdb.getVDBInfo(), 1232);
         gvdb.FetchPoolCPU();

@@ -96,7 +96,10 @@ def build_volume(brick_pos, values, epsilon=0.001, transfer=None, timing=None):
     logdim = (C.c_int * 5)(3, 3, 3, 3, 3)
     initcnt = (C.c_int * 5)(4, 4, 2, 1, 1)          # Configure(q4..q0), gvdb_volume_gvdb.cpp:2364-2377
     t0 = time.perf_counter()
-    t = L.ora_tree_create(5, logdim, initcnt, 16, 16, 1, 1)
+    # SetChannelDefault(16, 16, 1) like the reference samples; above ~400 k bricks the 16 x 16 x N slot grid would exceed the
+    # 16384-texel limit of a 3-D array along z, so the large volume uses 128 x 128 x N (cfg 5)
+    cxy = 128 if len(brick_pos) > 400000 else 16
+    t = L.ora_tree_create(5, logdim, initcnt, cxy, cxy, 1, 1)
     bp = np.ascontiguousarray(brick_pos, np.int32)
     L.ora_activate_bricks(t, bp.ctypes.data_as(C.c_void_p), len(bp))
     L.ora_finish_topology(t)
