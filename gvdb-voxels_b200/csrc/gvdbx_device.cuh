@@ -581,10 +581,22 @@ template <class S> __device__ __forceinline__ void gx2_brick_deep(const GxParams
 template <class S> __device__ __forceinline__ void gx_brick_tricubic(const GxParams&, S&, int, float3, float3, float3, GxHit&, GxCount&);
 template <class S> __device__ __forceinline__ void gx_brick_shadow(const GxParams&, S&, int, float3, float3, float3, GxHit&, GxCount&);
 
+// lane-state-machine form of the ray cast for the fixed-step marchers (gvdbx_trace.cuh).  Bit-identical output, but
+// MEASURED SLOWER than the literal nesting on every workload (cfg1 3102 vs 3862, cfg2 2099 vs 2499, cfg4 411 vs 496
+// Mrays/s, profiles/r01_ncu_summary.md): compiled only with -DGX_STATE_MACHINE=1.
+#ifndef GX_STATE_MACHINE
+#define GX_STATE_MACHINE 0
+#endif
+template <int MODE, class S>
+__device__ __forceinline__ void gx_raycast_sm(const GxParams& P, S& smp, float3 pos, float3 dir, GxHit& h, GxCount& cnt, int px, int py);
+
 template <int MODE, bool BATCH, class S>
 __device__ __forceinline__ void gx_raycast(const GxParams& P, S& smp, float3 pos, float3 dir, GxHit& h, GxCount& cnt,
                                            int px, int py)
 {
+    if constexpr (GX_STATE_MACHINE && BATCH && (MODE == GX_MODE_TRILINEAR || MODE == GX_MODE_LEVELSET || MODE == GX_MODE_DEEP)) {
+        if (MODE != GX_MODE_DEEP || P.dbuf == nullptr) { gx_raycast_sm<MODE>(P, smp, pos, dir, h, cnt, px, py); return; }
+    }
     GxStack st;
     int lev = P.top_lev;
     cnt.rays++;

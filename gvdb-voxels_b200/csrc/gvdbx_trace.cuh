@@ -230,6 +230,231 @@ __device__ __forceinline__ void gx2_brick_deep(const GxParams& P, S& smp, int no
     clr = make_float4(fminf(clr.x, 1.f), fminf(clr.y, 1.f), fminf(clr.z, 1.f), fmaxf(clr.w, 0.f));
 }
 
+// ------------------------------------------------------------------------------------------------ lane state machine
+// The literal nesting (rayCast -> brickFunc inside the loop body) makes a warp pay, for every brick visit, as many
+// sample rounds as its LONGEST chord needs: lanes with a short chord (or none) idle, and ncu shows the marchers at 10-15
+// of 32 lanes.  Here a lane is either TRAVERSING (one hierarchical-DDA iteration per turn) or MARCHING (one round of four
+// samples per turn); the warp loops over turns and a lane that finishes its brick goes back to traversing while its
+// neighbours keep marching theirs — nobody waits for anybody.  Every lane still executes exactly the reference's
+// sequence of floating-point operations on its own ray (same roundings, same order), only the interleaving across lanes
+// differs, so the output is unchanged (all parity tests pass with it).
+// RESULT: slower by 17-20 % (A/B, -DGX_STATE_MACHINE=1).  With 8^3 bricks and a quarter-voxel step a brick visit is only
+// ~5 rounds; the traversal turn + brick entry + post-brick bookkeeping (~150 instructions) now runs in nearly every warp
+// turn for the few lanes that need it instead of once per brick visit for all lanes, which costs more than the marcher
+// lanes it recovers.  Kept as the measured alternative to the literal nesting, not compiled by default.
+struct GxMarch {
+    float3 p;           // current sample, brick-local
+    float3 o;           // mValue: atlas texel of the first interior voxel
+    float  tx, dt;      // ray parameter of the current sample (deep) / of the brick entry (surface), parameter step (deep)
+    int    node, it;    // leaf index, samples taken so far in this brick
+};
+
+// brick entry: everything the brick functions do before their sample loop.  Returns false when there is nothing to
+// march (culled brick, or deep mode already below ALPHACUT): the visit is complete.
+template <int MODE, class S>
+__device__ __forceinline__ bool gx3_begin(const GxParams& P, S& smp, int nodeid, float3 t, float3 pos, float3 dir, GxHit& h,
+                                          GxCount& cnt, GxMarch& M)
+{
+    const GxLeafRec L = P.leaf[nodeid];
+    cnt.n_desc++;
+    const float st = P.steps.x;
+    if constexpr (MODE == GX_MODE_TRILINEAR) {
+        if (P.range != nullptr && !(__ldg(&P.range[nodeid].hi) >= P.thresh.x)) return false;
+        t.x = st * ceilf(t.x / st);
+    } else if constexpr (MODE == GX_MODE_LEVELSET) {
+        if (P.range != nullptr && !(__ldg(&P.range[nodeid].lo) < P.thresh.x)) return false;
+    } else {
+        t.x = st * ceilf(t.x / st);
+        if (h.hit.x == 0) h.hit.x = t.x;
+        if (P.range != nullptr && !(__ldg(&P.range[nodeid].hi) >= P.cutoff.x)) return false;
+    }
+    smp.enter(L);
+    const float3 vmin = make_float3(float(L.px), float(L.py), float(L.pz));
+    M.o = make_float3(float(L.vx), float(L.vy), float(L.vz));
+    M.node = nodeid; M.it = 0; M.tx = t.x; M.dt = 0.f;
+    if constexpr (MODE == GX_MODE_DEEP) {
+        const float3 wp = pos + t.x * dir;
+        M.p = gx_poszero(wp - vmin);
+        const float3 wpt = make_float3(__fmul_rn(st, dir.x), __fmul_rn(st, dir.y), __fmul_rn(st, dir.z));
+        M.dt = sqrtf(gx_dot(wpt, wpt));
+        if (!(h.clr.w > P.cutoff.y)) {          // the sample loop would not run: exit bookkeeping of rayDeepBrick only
+            h.hit.y = t.x;
+            h.clr = make_float4(fminf(h.clr.x, 1.f), fminf(h.clr.y, 1.f), fminf(h.clr.z, 1.f), fmaxf(h.clr.w, 0.f));
+            return false;
+        }
+    } else {
+        M.p = gx_poszero(pos + t.x * dir - vmin);
+    }
+    return true;
+}
+
+// one round of four samples; returns true when the brick visit is complete (hit, left the brick, sample budget spent)
+template <int MODE, class S>
+__device__ __forceinline__ bool gx3_round(const GxParams& P, S& smp, float3 pos, float3 dir, GxHit& h, GxCount& cnt, GxMarch& M)
+{
+    const float res0 = float(gx_res<S>(P, 0));
+    const float st = P.steps.x;
+    const float3 o = M.o;
+    float3 p = M.p, p1, p2, p3;
+    if constexpr (MODE == GX_MODE_DEEP) {
+        const float3 wpt = make_float3(__fmul_rn(st, dir.x), __fmul_rn(st, dir.y), __fmul_rn(st, dir.z));
+        const float minval = P.cutoff.x, acut = P.cutoff.y, thresh = P.thresh.x;
+        const float inv_range = gx_rcp_approx(P.thresh.z - P.thresh.y);
+        float4& clr = h.clr;
+        GX_STEP_ADD(p1, p); GX_STEP_ADD(p2, p1); GX_STEP_ADD(p3, p2);
+        const bool k0 = GX_INB(p, res0), k1 = GX_INB(p1, res0), k2 = GX_INB(p2, res0), k3 = GX_INB(p3, res0);
+        const float v0 = smp.tri(p.x + o.x, p.y + o.y, p.z + o.z);
+        const float v1 = smp.tri(p1.x + o.x, p1.y + o.y, p1.z + o.z);
+        const float v2 = smp.tri(p2.x + o.x, p2.y + o.y, p2.z + o.z);
+        const float v3 = smp.tri(p3.x + o.x, p3.y + o.y, p3.z + o.z);
+        const bool a0 = v0 >= minval, a1 = v1 >= minval, a2 = v2 >= minval, a3 = v3 >= minval;
+        const float4* lut = P.transfer_deep;
+        const float4 c0 = __ldg(&lut[a0 ? gx_transfer_index(v0, thresh, inv_range) : 0]);
+        const float4 c1 = __ldg(&lut[a1 ? gx_transfer_index(v1, thresh, inv_range) : 0]);
+        const float4 c2 = __ldg(&lut[a2 ? gx_transfer_index(v2, thresh, inv_range) : 0]);
+        const float4 c3 = __ldg(&lut[a3 ? gx_transfer_index(v3, thresh, inv_range) : 0]);
+        int done = 0;
+        bool more = k0;
+        if (more) { done = 1; cnt.s_tri++; if (a0) { cnt.s_lut++; gx_deep_accumulate_pre(P, clr, c0); } more = k1 && clr.w > acut; }
+        if (more) { done = 2; cnt.s_tri++; if (a1) { cnt.s_lut++; gx_deep_accumulate_pre(P, clr, c1); } more = k2 && clr.w > acut; }
+        if (more) { done = 3; cnt.s_tri++; if (a2) { cnt.s_lut++; gx_deep_accumulate_pre(P, clr, c2); } more = k3 && clr.w > acut; }
+        if (more) { done = 4; cnt.s_tri++; if (a3) { cnt.s_lut++; gx_deep_accumulate_pre(P, clr, c3); } }
+        for (int q = 0; q < done; q++) M.tx += M.dt;
+        M.it += 4;
+        if (done == 4 && M.it < GX_MAX_ITER && clr.w > acut) { GX_STEP_ADD(M.p, p3); return false; }
+        h.hit.y = M.tx;
+        clr = make_float4(fminf(clr.x, 1.f), fminf(clr.y, 1.f), fminf(clr.z, 1.f), fmaxf(clr.w, 0.f));
+        return true;
+    } else {
+        const float thr = P.thresh.x;
+        GX_STEP_FMA(p1, p); GX_STEP_FMA(p2, p1); GX_STEP_FMA(p3, p2);
+        bool k0, k1, k2, k3;
+        if constexpr (MODE == GX_MODE_TRILINEAR) { k0 = GX_INB(p, res0); k1 = GX_INB(p1, res0); k2 = GX_INB(p2, res0); k3 = GX_INB(p3, res0); }
+        else                                     { k0 = GX_INB_LE(p, res0); k1 = GX_INB_LE(p1, res0); k2 = GX_INB_LE(p2, res0); k3 = GX_INB_LE(p3, res0); }
+        const float v0 = smp.tri(p.x + o.x, p.y + o.y, p.z + o.z);
+        const float v1 = smp.tri(p1.x + o.x, p1.y + o.y, p1.z + o.z);
+        const float v2 = smp.tri(p2.x + o.x, p2.y + o.y, p2.z + o.z);
+        const float v3 = smp.tri(p3.x + o.x, p3.y + o.y, p3.z + o.z);
+        const bool ls = (MODE == GX_MODE_LEVELSET);
+        const bool t0 = ls ? v0 < thr : v0 >= thr, t1 = ls ? v1 < thr : v1 >= thr, t2 = ls ? v2 < thr : v2 >= thr, t3 = ls ? v3 < thr : v3 >= thr;
+        int k = -1;
+        bool hit = false;
+        if (!k0) k = 0; else if (t0) { k = 0; hit = true; }
+        else if (!k1) k = 1; else if (t1) { k = 1; hit = true; p = p1; }
+        else if (!k2) k = 2; else if (t2) { k = 2; hit = true; p = p2; }
+        else if (!k3) k = 3; else if (t3) { k = 3; hit = true; p = p3; }
+        if (k >= 0) {
+            cnt.s_tri += k + (hit ? (ls ? 2 : 1) : 0);
+            if (hit) {
+                const GxLeafRec L = P.leaf[M.node];
+                h.hit = p + make_float3(float(L.px), float(L.py), float(L.pz));
+                h.norm = gx_gradient(smp, p + o, cnt, ls);
+                h.t = M.tx; h.leaf = M.node; h.vox = gx_i3(gx_floor(h.hit));
+            }
+            return true;
+        }
+        cnt.s_tri += 4;
+        M.it += 4;
+        GX_STEP_FMA(M.p, p3);
+        return M.it >= GX_MAX_ITER;
+    }
+}
+
+template <int MODE, class S>
+__device__ __forceinline__ void gx_raycast_sm(const GxParams& P, S& smp, float3 pos, float3 dir, GxHit& h, GxCount& cnt, int px, int py)
+{
+    GxStack st;
+    int lev = P.top_lev;
+    cnt.rays++;
+    float3 tStart = gx_ray_box(pos, dir, P.bmin, P.bmax);
+    if (tStart.z == GX_NOHIT) return;
+    if (lev < 1 || lev >= GX_MAXLEV) return;
+    int4 np = __ldg(&P.npos[lev][0]);
+    cnt.n_desc++;
+    float3 vmin = make_float3(float(np.x), float(np.y), float(np.z));
+    tStart.x += P.epsilon;
+    st.set(lev, 0, tStart.y - P.epsilon);
+    float      cur_tmax = tStart.y - P.epsilon;
+    const int* ctab = P.child[lev];
+    unsigned   res = unsigned(gx_res<S>(P, lev));
+    GxDDA dda;
+    dda.set_ray(pos, dir, tStart);
+    dda.prepare(vmin, gx_vdel<S>(P, lev));
+    const float tDepth = gx_depth_max(P, dir, px, py);
+
+    // tail of a reference loop iteration: pop the levels whose exit has been passed (cuda_gvdb_raycast.cuh:603-609)
+    auto ascend = [&]() {
+        while (dda.t.x > cur_tmax && lev <= P.top_lev) {
+            lev++;
+            if (lev <= P.top_lev) {
+                const int n = st.node(lev);
+                cur_tmax = st.tmax(lev);
+                ctab = P.child[lev] + (size_t(n) << (3 * gx_dim<S>(P, lev)));
+                res = unsigned(gx_res<S>(P, lev));
+                const int4 q = __ldg(&P.npos[lev][n]);
+                cnt.n_desc++;
+                dda.prepare(make_float3(float(q.x), float(q.y), float(q.z)), gx_vdel<S>(P, lev));
+            }
+        }
+    };
+    // what rayCast does after a brick function returns (:584-602); false = the ray is finished
+    auto after_brick = [&]() -> bool {
+        if (h.clr.w <= 0) { h.clr.w = 0; return false; }
+        if (h.hit.z != GX_NOHIT) return false;
+        if (MODE == GX_MODE_DEEP && h.clr.w <= P.cutoff.y) return false;
+        dda.step();
+        return true;
+    };
+
+    enum { TRAVERSE = 0, MARCH = 1, DONE = 2 };
+    int state = TRAVERSE, iter = 0;
+    GxMarch M;
+    while (state != DONE) {
+        if (state == TRAVERSE) {
+            if (!(iter < GX_MAX_ITER && lev > 0 && lev <= P.top_lev
+                  && unsigned(dda.p.x) <= res && unsigned(dda.p.y) <= res && unsigned(dda.p.z) <= res)) { state = DONE; }
+            else {
+                dda.next();
+                if (dda.t.x > tDepth) { h.hit.z = 0; state = DONE; }
+                else {
+                    const int dm = gx_dim<S>(P, lev);
+                    const int b = (((int(dda.p.z) << dm) + int(dda.p.y)) << dm) + int(dda.p.x);
+                    int c = -1;
+                    if (unsigned(dda.p.x | dda.p.y | dda.p.z) < res) c = __ldg(ctab + b);
+                    cnt.n_dda++;
+                    bool tail = true;                   // finish the reference iteration now (ascend, iter++)
+                    if (c != -1) {
+                        if (lev == 1) {
+                            dda.t.x += P.epsilon;
+                            if (gx3_begin<MODE>(P, smp, c, dda.t, pos, dir, h, cnt, M)) { state = MARCH; tail = false; }
+                            else if (!after_brick()) { state = DONE; tail = false; }
+                        } else {
+                            lev--;
+                            np = __ldg(&P.npos[lev][c]);
+                            cnt.n_desc++;
+                            dda.t.x += P.epsilon;
+                            cur_tmax = dda.t.y - P.epsilon;
+                            st.set(lev, c, cur_tmax);
+                            ctab = P.child[lev] + (size_t(c) << (3 * gx_dim<S>(P, lev)));
+                            res = unsigned(gx_res<S>(P, lev));
+                            dda.prepare(make_float3(float(np.x), float(np.y), float(np.z)), gx_vdel<S>(P, lev));
+                        }
+                    } else {
+                        dda.step();
+                    }
+                    if (tail) { ascend(); iter++; }
+                }
+            }
+        }
+        if (state == MARCH) {
+            if (gx3_round<MODE>(P, smp, pos, dir, h, cnt, M)) {
+                if (after_brick()) { ascend(); iter++; state = TRAVERSE; }
+                else state = DONE;
+            }
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ traversal state
 struct GxTrav {
     GxDDA   dda;
