@@ -24,7 +24,7 @@ EXPORTED_SYMBOLS = [
     "gvdbx_import_atlas_array", "gvdbx_import_atlas_host", "gvdbx_set_transfer",
     "gvdbx_render", "gvdbx_render_tiles", "gvdbx_tiles_per_rank", "gvdbx_assemble_tiles",
     "gvdbx_render_debug", "gvdbx_raytrace", "gvdbx_read_buffer", "gvdbx_sync", "gvdbx_get_counters",
-    "gvdbx_sample_points", "gvdbx_update_apron", "gvdbx_export_atlas_host", "gvdbx_render_tiles_direct", "gvdbx_render_tiles_ring", "gvdbx_peer_alloc", "gvdbx_peer_free", "gvdbx_peer_open",
+    "gvdbx_sample_points", "gvdbx_kernel_params", "gvdbx_update_apron", "gvdbx_export_atlas_host", "gvdbx_render_tiles_direct", "gvdbx_render_tiles_ring", "gvdbx_peer_alloc", "gvdbx_peer_free", "gvdbx_peer_open",
     "gvdbx_peer_close", "gvdbx_stream_signal", "gvdbx_stream_signal_add", "gvdbx_stream_signal_many", "gvdbx_stream_wait", "gvdbx_set_stream",
     "gvdbx_read_buffer_async", "gvdbx_lanes", "gvdbx_lane_select", "gvdbx_lane_stream", "gvdbx_lanes_fork", "gvdbx_lanes_join",
 ]
@@ -80,6 +80,7 @@ def lib():
     L.gvdbx_get_counters.argtypes = [vp, C.POINTER(Counters)]
     L.gvdbx_sample_points.argtypes = [vp, i32, u64, i32, u64, u64]
     L.gvdbx_render_tiles_direct.argtypes = [vp, vp, i32, i32, u64, i32, i32, i32]
+    L.gvdbx_kernel_params.argtypes = [vp, vp, i32, i32, u64, vp, C.c_size_t]
     L.gvdbx_update_apron.argtypes = [vp, i32, C.c_float]
     L.gvdbx_export_atlas_host.argtypes = [vp, i32, vp, i32, i32, i32]
     L.gvdbx_render_tiles_ring.argtypes = [vp, vp, i32, i32, u64, i32, i32, i32, u64, C.c_uint32, u64]
@@ -278,6 +279,17 @@ class Renderer:
 
     def set_stream(self, stream):
         self._ck(self._L.gvdbx_set_stream(self._h, C.c_void_p(stream or 0)), "gvdbx_set_stream")
+
+    def render_custom_example(self, scninfo, out_ptr, chan=0):
+        """the reference's gRenderKernel sample kernel built against csrc/gvdbx_plugin.cuh (libgvdbx_custom_example.so)"""
+        path = os.path.join(os.path.dirname(lib_path()), "libgvdbx_custom_example.so")
+        if not os.path.exists(path):
+            raise GvdbxError(f"{path} is missing: build it with `make -C gvdb-voxels_b200`")
+        ex = C.CDLL(path)
+        ex.gvdbx_example_render_custom.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_uint64, C.c_void_p]
+        ex.gvdbx_example_render_custom.restype = C.c_int
+        p, keep = _buf(scninfo)
+        self._ck(ex.gvdbx_example_render_custom(self._h, p, chan, int(out_ptr), None), "gvdbx_example_render_custom")
 
     # --- frame lanes (consecutive frames on alternating internal streams)
     def lanes(self, n):

@@ -557,6 +557,21 @@ extern "C" int gvdbx_render(gvdbx_t* h, const void* scninfo, int shade_mode, int
     return GVDBX_OK;
 }
 
+// RenderKernel plugin point: the parameter block of this frame for a user kernel built against csrc/gvdbx_plugin.cuh
+extern "C" int gvdbx_kernel_params(gvdbx_t* h, const void* scninfo, int shade_mode, int chan, uint64_t outbuf_d, void* params_out,
+                                   size_t params_bytes)
+{
+    if (!h || !params_out) return GVDBX_E_ARG;
+    if (params_bytes != sizeof(GxParams)) return gx_fail(h, GVDBX_E_ARG, "params_bytes != sizeof(GxParams): plugin built against other headers");
+    GX_CUDA(h, cudaSetDevice(h->device));
+    GxParams P; int mode = 0;
+    int rc = gx_fill_params(h, scninfo, shade_mode, chan, P, mode);
+    if (rc) return rc;
+    P.out = (uchar4*)outbuf_d;
+    memcpy(params_out, &P, sizeof P);
+    return GVDBX_OK;
+}
+
 extern "C" int gvdbx_render_debug(gvdbx_t* h, const void* scninfo, int shade_mode, int chan, uint64_t outbuf_d, uint64_t dbg_d)
 {
     if (!h) return GVDBX_E_ARG;

@@ -139,6 +139,14 @@ int  gvdbx_render_tiles_ring(gvdbx_t* h, const void* scninfo, int shade_mode, in
 int  gvdbx_tiles_per_rank(int width, int height, int tile_size, int nranks);
 int  gvdbx_assemble_tiles(gvdbx_t* h, uint64_t gathered_d, uint64_t frame_d, int width, int height, int tile_size, int nranks);
 
+/* VolumeGVDB::RenderKernel plugin point (src/gvdb_volume_gvdb.cpp:4309-4333): user kernels built against
+ * gvdb-voxels_b200/csrc/gvdbx_plugin.cuh take the frame's parameter block (GxParams, by value, __grid_constant__) instead
+ * of the reference's (VDBInfo*, chan, outBuf).  This call fills it for `scninfo` (shade_mode selects the per-frame tables
+ * that are prepared: occupancy bits for SHADE_VOXEL, derived transfer table for SHADE_VOLUME); params_bytes must equal
+ * sizeof(GxParams) of the headers the kernel was built with.  Launch with 32 bytes of dynamic shared memory per thread. */
+int  gvdbx_kernel_params(gvdbx_t* h, const void* scninfo, int shade_mode, int chan, uint64_t outbuf_d, void* params_out,
+                         size_t params_bytes);
+
 /* Debug / parity outputs: same traversal, additionally writes 48 B per pixel into dbg_d:
  *   float4 {hit.x, hit.y, hit.z, t_hit}   float4 {norm.x, norm.y, norm.z, as_float(leaf id)}   int4 {voxel.x, voxel.y, voxel.z, iterations}
  * (deep mode: float4 raw colour before compositing, float4 {hit.x, hit.y, hit.z, 0}, int4 0). */

@@ -44,6 +44,7 @@ static void dump(const std::string& path, const void* p, size_t n)
     if (!f) { fprintf(stderr, "cannot write %s\n", path.c_str()); exit(2); }
     fwrite(p, 1, n, f); fclose(f);
 }
+// kind 3: user kernel of the reference's own sample (source/gRenderKernel/render_custom.cu) through RenderKernel;
 // kind 0: native Render(shade) [+ hit wrapper]; kind 1: composed RGBA8 kernel through RenderKernel (BASELINE config 4);
 // kind 2: per-sample float colour kernel, `spp` samples averaged on the host (BASELINE config 5)
 struct Mode { const char* name; int shade; const char* hitkernel; int kind; };
@@ -53,6 +54,7 @@ static const Mode kModes[] = {
     {"tricubic", SHADE_TRICUBIC, "oracleHitTricubic", 0}, {"emptyskip", SHADE_EMPTYSKIP, "oracleHitEmptySkip", 0},
     {"section2d", SHADE_SECTION2D, "", 0}, {"section3d", SHADE_SECTION3D, "", 0},
     {"deepshadow", SHADE_VOLUME, "oracleDeepShadow", 1}, {"deepspp", SHADE_VOLUME, "oracleDeepSample", 2},
+    {"custom", SHADE_TRILINEAR, "raycast_kernel", 3},     // the reference's gRenderKernel sample (render_custom.cubin) through RenderKernel
 };
 
 int main(int argc, char** argv)
@@ -308,13 +310,19 @@ int main(int argc, char** argv)
         if (m.shade == SHADE_SECTION3D) scn->SetCrossSection(Vector3DF(cN, cN, cN * 0.85f), Vector3DF(0.3f, 0.2f, 1.0f));
         CUfunction kfn = 0;
         if (m.kind != 0) {
-            if (!omod || cuModuleGetFunction(&kfn, omod, m.hitkernel) != CUDA_SUCCESS) { fprintf(stderr, "no kernel %s\n", m.hitkernel); continue; }
-            gvdb.SetModule(omod);
+            CUmodule use = omod;
+            if (m.kind == 3) {
+                static CUmodule cmod = 0;
+                if (!cmod && cuModuleLoad(&cmod, "render_custom.cubin") != CUDA_SUCCESS) { fprintf(stderr, "cannot load render_custom.cubin\n"); continue; }
+                use = cmod;
+            }
+            if (!use || cuModuleGetFunction(&kfn, use, m.hitkernel) != CUDA_SUCCESS) { fprintf(stderr, "no kernel %s\n", m.hitkernel); continue; }
+            gvdb.SetModule(use);
             scn->SetShading(m.shade);
         }
         auto render = [&]() {
             if (m.kind == 0) gvdb.Render(m.shade, 0, 0);
-            else if (m.kind == 1) gvdb.RenderKernel(kfn, 0, 0);
+            else if (m.kind == 1 || m.kind == 3) gvdb.RenderKernel(kfn, 0, 0);
             else for (int sidx = 0; sidx < spp; sidx++) { scn->SetSample(sidx); scn->SetFrame(spp); gvdb.RenderKernel(kfn, 0, 3); }
         };
         for (int i = 0; i < warmup; i++) render();

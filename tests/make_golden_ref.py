@@ -79,11 +79,11 @@ def modes2(outdir):
     deep at 4 rays per pixel): ScnInfo + RGBA per mode, hit / normal buffers for the tiny presets"""
     for preset in ("cfg1_tiny", "cfg4_tiny", "cfg1_small", "cfg4_small"):
         d = tempfile.mkdtemp(prefix="refdump_")
-        refcmp.run_ref(preset, d, modes=["deep"] + list(refcmp.MODES2))
+        refcmp.run_ref(preset, d, modes=["deep", refcmp.CUSTOM] + list(refcmp.MODES2))
         dump = refcmp.load_dump(d)
         out = {"preset": preset, "width": dump["meta"]["width"], "height": dump["meta"]["height"], "spp": 4,
                "vdbinfo": np.frombuffer(dump["vdbinfo"], np.uint8)}
-        for m in refcmp.MODES2:
+        for m in list(refcmp.MODES2) + [refcmp.CUSTOM]:
             out[f"scn_{m}"] = np.frombuffer(dump["scn"][m], np.uint8)
             out[f"rgba_{m}"] = dump["rgba"][m]
             if "tiny" in preset and m in dump["hit"]:

@@ -21,6 +21,7 @@ MODES = {"voxel": 0, "trilinear": 4, "levelset": 6, "deep": 7}
 # the rest of Render()'s switch + the two composed BASELINE modes: name -> (shade, deep_shadow option, spp option)
 MODES2 = {"tricubic": (5, 0, 1), "emptyskip": (3, 0, 1), "section2d": (1, 0, 1), "section3d": (2, 0, 1),
           "deepshadow": (7, 1, 1), "deepspp": (7, 0, 4)}
+CUSTOM = "custom"          # the reference's gRenderKernel sample kernel (user kernel through RenderKernel)
 ALL_SHADE = dict(MODES, **{k: v[0] for k, v in MODES2.items()})
 
 
@@ -81,7 +82,7 @@ def load_dump(d):
         (out["pool0"] if g == 0 else out["pool1"])[l] = b
     out["scn"], out["rgba"], out["hit"] = {}, {}, {}
     w, h = meta["width"], meta["height"]
-    for m in list(MODES) + list(MODES2):
+    for m in list(MODES) + list(MODES2) + [CUSTOM]:
         p = os.path.join(d, f"scninfo_{m}.bin")
         if os.path.exists(p):
             out["scn"][m] = open(p, "rb").read()

@@ -606,3 +606,24 @@ def test_update_apron_matches_reference_atlas(ora, pkg, torch_cuda, preset):
     changed = b5 != atlas
     assert changed.any() and (b5[changed] == 5.0).all() and (atlas[changed] == 0.0).all()
     r.close()
+
+
+# ------------------------------------------------------------------------------------------------ RenderKernel plugin point
+@pytest.mark.parametrize("preset", ["cfg1_tiny", "cfg4_tiny", "cfg1_small", "cfg4_small"])
+def test_custom_kernel_plugin_bit_exact_vs_reference_sample(scenes, torch_cuda, preset):
+    """The reference's own custom-kernel sample (source/gRenderKernel/render_custom.cu, launched through
+    VolumeGVDB::RenderKernel) against the same kernel written on the product's plugin API (csrc/gvdbx_plugin.cuh,
+    gvdbx_kernel_params): RGBA bit for bit."""
+    g = _modes2(preset)
+    if "rgba_custom" not in g.files:
+        pytest.skip("golden without the custom-kernel image")
+    p, vol, r = scenes(preset)
+    w, h = int(g["width"]), int(g["height"])
+    r.set_sampler(0)
+    out = torch_cuda.zeros((h, w, 4), dtype=torch_cuda.uint8, device="cuda")
+    r.render_custom_example(g["scn_custom"].tobytes(), out.data_ptr())
+    r.sync()
+    img = out.cpu().numpy()
+    ref = g["rgba_custom"]
+    assert np.array_equal(img, ref), f"{(img != ref).any(axis=2).sum()} pixels differ"
+    assert (ref != ref[0, 0]).any()
