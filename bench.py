@@ -259,7 +259,11 @@ def main():
     ring, consumer = None, None
     if world > 1 and a.exchange == "peer":
         ring = mg.PeerFrameRing(r, w, h, a.tile, rank, world, nslots=a.slots)
-        consumer = torch.cuda.Stream(device=dev) if rank == 0 else None
+        # rank 0 consumes finished frames on two streams in turn (the wait for frame q+1 overlaps the D2H copy of frame q);
+        # slots are released in frame order: the release of q waits for the release of q-1 (event)
+        consumers = [torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)] if rank == 0 else None
+        released_ev = [torch.cuda.Event(), torch.cuda.Event()] if rank == 0 else None
+        consumer = consumers[0] if rank == 0 else None
     tiled = mg.TiledFrame(r, w, h, a.tile, rank, world, dev) if (world > 1 and ring is None) else None
 
     kpf = 2 if shade == 7 else 1        # kernels per frame: deep modes build the frame's derived transfer table first
@@ -278,10 +282,14 @@ def main():
                 q = ring.submit(scn, shade)
                 launches += 1 + kpf
                 if rank == 0:
-                    ring.acquire(q, consumer.cuda_stream)
+                    cs = consumers[q & 1]
+                    ring.acquire(q, cs.cuda_stream)
                     if on_frame is not None:
-                        on_frame(q)
-                    ring.release(q, consumer.cuda_stream)
+                        on_frame(q, cs)
+                    if q > 1:
+                        cs.wait_event(released_ev[(q - 1) & 1])
+                    ring.release(q, cs.cuda_stream)
+                    released_ev[q & 1].record(cs)
                     launches += 1
         else:
             tiled.render_frames(scns, shade)
@@ -291,7 +299,8 @@ def main():
         """the measuring stream waits for the frame lanes and (rank 0) the consumer stream: stream-ordered, no host sync"""
         r.lanes_join()
         if consumer is not None:
-            torch.cuda.current_stream().wait_stream(consumer)
+            for cs in consumers:
+                torch.cuda.current_stream().wait_stream(cs)
 
     def sync_all():
         torch.cuda.synchronize()
@@ -420,14 +429,15 @@ def main():
         if ring is not None:
             host_ring = [host] + [torch.empty((h, w, 4), dtype=torch.uint8).pin_memory() for _ in range(a.slots - 1)] if rank == 0 else []
 
-            def to_host(q):
-                with torch.cuda.stream(consumer):               # D2H of the finished frame behind the acquire, on the consumer stream
+            def to_host(q, cs):
+                with torch.cuda.stream(cs):                     # D2H of the finished frame behind the acquire, on its consumer stream
                     host_ring[(q - 1) % a.slots].copy_(ring.frame_tensor(q, torch, dev), non_blocking=True)
 
             def step_e2e():
                 step_resident(on_frame=to_host if rank == 0 else None)
                 if rank == 0:
-                    consumer.synchronize()                      # the caller owns the host frames of this step now
+                    for cs in consumers:
+                        cs.synchronize()                        # the caller owns the host frames of this step now
                 r.lane_select(-1)
         else:
             def to_host(j, fr):
