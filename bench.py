@@ -62,14 +62,21 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append([time.time()] + [c.strip() for c in line.split(",")][1:])
 
-    def stop(self):
+    def stop(self, t0=None, t1=None):
+        """summary of the samples taken between host times t0 and t1 (the timed region); when the region is shorter than
+        the 100 ms sampling period, of the samples within half a second around it (same load: warm-up / e2e steps)"""
         if self.proc:
             time.sleep(0.15)
             self.proc.terminate()
+        rows, window = self.rows, "all"
+        if t0 is not None:
+            inside = [r for r in self.rows if t0 <= r[0] <= t1]
+            near = [r for r in self.rows if t0 - 0.5 <= r[0] <= t1 + 0.5]
+            rows, window = (inside, "timed region") if len(inside) >= 2 else (near, "timed region +- 0.5 s")
         sm, mx, reasons = [], [], set()
-        for r in self.rows:
+        for r in rows:
             try:
                 sm.append(float(r[1])); mx.append(float(r[2]))
                 for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
@@ -79,7 +86,7 @@ class ClockSampler:
                 pass
         sm.sort()
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "window": window}
 
 
 def build_workload(name, size=None, timing=None):
@@ -308,17 +315,18 @@ def main():
             dist.barrier()
             torch.cuda.synchronize()
 
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()              # before the warm-up: nvidia-smi needs ~0.1 s to deliver its first sample
     r.lanes_fork()
     for _ in range(a.warmup):
         step_resident()
     join_consumer()
     sync_all()
-    clocks = ClockSampler(local)
-    if rank == 0:
-        clocks.start()
     launches = 0
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sync_all()
+    t_region0 = time.time()
     e0.record()
     r.lanes_fork()
     for _ in range(a.steps):
@@ -330,7 +338,8 @@ def main():
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms_total = float(ms.item())
-    clk = clocks.stop() if rank == 0 else None
+    t_region1 = time.time()
+    clk = clocks.stop(t_region0, t_region1) if rank == 0 else None
     launches_timed = launches
 
     # per-rank render-only time of one step (no gather): shows the load balance of the static tile partition
