@@ -66,6 +66,7 @@ int main(int argc, char** argv)
     float xf[12] = {0, 0, 0, 1, 1, 1, 0, 0, 0, 0, 0, 0};
     int have_xf = 0, use_dbuf = 0, nrays = 0;
     std::string savevbx = "";
+    int cfg[5] = {3, 3, 3, 3, 3};                  // Configure(q4..q0): log2 dims from the top level down to the brick
     int lightdump = 0;
     for (int i = 3; i < argc; i++) {
         std::string a = argv[i];
@@ -84,6 +85,7 @@ int main(int argc, char** argv)
         else if (a == "--xform" && i + 1 < argc) { have_xf = 1; sscanf(argv[++i], "%f,%f,%f,%f,%f,%f,%f,%f,%f,%f,%f,%f", xf, xf + 1, xf + 2, xf + 3, xf + 4, xf + 5, xf + 6, xf + 7, xf + 8, xf + 9, xf + 10, xf + 11); }
         else if (a == "--dbuf") use_dbuf = 1;
         else if (a == "--savevbx" && i + 1 < argc) savevbx = argv[++i];
+        else if (a == "--config" && i + 1 < argc) sscanf(argv[++i], "%d,%d,%d,%d,%d", cfg, cfg + 1, cfg + 2, cfg + 3, cfg + 4);
         else if (a == "--spp" && i + 1 < argc) spp = atoi(argv[++i]);
         else if (a == "--raytrace" && i + 1 < argc) nrays = atoi(argv[++i]);
     }
@@ -109,7 +111,7 @@ int main(int argc, char** argv)
 
     // ---- CPU topology build (timed: the reference's host-side baseline)
     t0 = now_s();
-    gvdb.Configure(3, 3, 3, 3, 3);
+    gvdb.Configure(cfg[0], cfg[1], cfg[2], cfg[3], cfg[4]);
     {   // 16 x 16 x N brick slots like the reference samples; 128 x 128 x N for the large volume (3-D array limit of 16384 along z)
         const int cxy = S.nbricks > 400000 ? 128 : 16;
         gvdb.SetChannelDefault(cxy, cxy, 1);

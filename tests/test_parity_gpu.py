@@ -627,3 +627,27 @@ def test_custom_kernel_plugin_bit_exact_vs_reference_sample(scenes, torch_cuda, 
     ref = g["rgba_custom"]
     assert np.array_equal(img, ref), f"{(img != ref).any(axis=2).sum()} pixels differ"
     assert (ref != ref[0, 0]).any()
+
+
+# ------------------------------------------------------------------------------------------------ non-uniform trees
+@pytest.mark.skipif(not refcmp.have_ref(), reason="oracle/_ref not built")
+@pytest.mark.parametrize("config", [(3, 3, 4, 4, 3), (2, 3, 5, 2, 3)])
+def test_live_reference_non_uniform_tree(pkg, torch_cuda, tmp_path, config):
+    """Trees whose levels are not all log2dim 3 (Configure(q4, q3, q2, q1, 3): 16^3 / 32^3 / 4^3 children per node) take
+    the generic kernel variants (res / dim / vdel from the parameter block).  The unmodified reference builds and renders
+    such a tree now; its pools, atlas, VDBInfo and ScnInfo are imported and every mode must match bit for bit."""
+    d = str(tmp_path / "dump")
+    refcmp.run_ref("cfg4_small", d, modes=list(MODES) + list(refcmp.MODES2), size=(222, 148), config=config)
+    dump = refcmp.load_dump(d)
+    vdb = np.frombuffer(dump["vdbinfo"], np.int32)
+    assert list(vdb[0:5]) == [3, config[3], config[2], config[1], config[0]]          # dim[] per level, brick first
+    res = refcmp.compare(dump, pkg, list(MODES), verbose=False)
+    for m in MODES:
+        assert res[m]["tex"]["rgba_mismatch_pixels"] == 0, (m, res[m]["tex"])
+        assert res[m]["tex"].get("hit_mismatch_pixels", 0) == 0 and res[m]["tex"].get("raw_clr_mismatch_pixels", 0) == 0
+        assert res[m]["linear"]["rgba_over1_pixels"] <= 2e-3 * res[m]["linear"]["pixels"]
+    assert res["voxel"]["linear"]["rgba_mismatch_pixels"] == 0
+    res2 = refcmp.compare2(dump, pkg, verbose=False)
+    for m in refcmp.MODES2:
+        assert res2[m]["tex"]["rgba_mismatch_pixels"] == 0, (m, res2[m]["tex"])
+        assert res2[m]["tex"].get("hit_mismatch_pixels", 0) == 0
