@@ -196,6 +196,9 @@ def main():
     ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
                     help="N>1: peer = render kernels store straight into rank 0's frame over NVLink (default); nccl = packed tiles + gather + assemble")
     ap.add_argument("--slots", type=int, default=4, help="frames in flight in the peer ring")
+    ap.add_argument("--replicate", default="broadcast", choices=["broadcast", "local"],
+                    help="N>1: broadcast = rank 0 builds the volume, pools and atlas travel GPU to GPU (NCCL over NVLink); "
+                         "local = every rank builds and uploads its own copy")
     ap.add_argument("--lanes", type=int, default=4, help="frame lanes: consecutive frames alternate between this many internal streams (0 = one stream)")
     ap.add_argument("--spp", type=int, default=1)
     ap.add_argument("--deep-shadow", action="store_true")
@@ -223,17 +226,31 @@ def main():
 
     # ---------------- workload (CPU: scene synthesis + reference-style topology build = reported CPU baseline #1)
     timing = {}
-    p, vol = build_workload(a.workload, a.size, timing)
+    bcast = world > 1 and a.replicate == "broadcast"
+    if bcast and rank != 0:
+        p, vol = oracle.preset(a.workload), None          # the volume arrives over NVLink below
+        if a.size:
+            p.width, p.height = a.size
+    else:
+        if world > 1:
+            oracle.lib().ora_set_num_threads(max(1, (os.cpu_count() or 1) // (1 if bcast else world)))   # torchrun exports OMP_NUM_THREADS=1
+        p, vol = build_workload(a.workload, a.size, timing)
     w, h = p.width, p.height
     shade = MODES[a.mode] if a.mode else p.shade
     scns, table = frame_scninfos(pkg, p, shade, a.frames)
-    vol["transfer"] = table
+    if vol is not None:
+        vol["transfer"] = table
     rays_step = a.frames * w * h
 
     t0 = time.perf_counter()
     r = pkg.Renderer(local)
-    r.import_topology_host(vol["vdbinfo"], vol["pool0"], vol["pool1"])
-    r.import_atlas_host(vol["atlas"])
+    if bcast:
+        meta = mg.replicate_volume(r, vol, rank, world, dev)
+        atlas_bytes = int(np.prod(meta["atlas_shape"])) * 4
+    else:
+        r.import_topology_host(vol["vdbinfo"], vol["pool0"], vol["pool1"])
+        r.import_atlas_host(vol["atlas"])
+        atlas_bytes = vol["atlas"].nbytes
     r.set_transfer(table)
     r.sync()
     import_s = time.perf_counter() - t0
@@ -523,10 +540,10 @@ def main():
            "ms_per_step": ms_total / a.steps, "ms_per_frame": ms_total / a.steps / a.frames, "higher_is_better": True,
            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
            "config": {"workload": f"{a.workload} {SHADE_NAME[shade]}{'+shadow' if a.deep_shadow else ''} {w}x{h}", "frames_per_step": a.frames, "bricks": timing["bricks"],
-                      "atlas_mb": vol["atlas"].nbytes / 1e6, "sampler": a.sampler, "block": a.block, "traversal": a.traversal, "frame_lanes": a.lanes,
+                      "atlas_mb": atlas_bytes / 1e6, "replicate": a.replicate if world > 1 else None, "sampler": a.sampler, "block": a.block, "traversal": a.traversal, "frame_lanes": a.lanes,
                       "parallelism": (f"image tiles {a.tile}x{a.tile} round-robin over {world} GPU(s), volume replicated, exchange={a.exchange}"
                                       if world > 1 else "single GPU"), "spp": a.spp, "deep_shadow": bool(a.deep_shadow),
-                      "l2_policy": "inputs larger than L2 (atlas %.0f MB vs 126 MB L2); camera changes every frame" % (vol["atlas"].nbytes / 1e6)},
+                      "l2_policy": "inputs larger than L2 (atlas %.0f MB vs 126 MB L2); camera changes every frame" % (atlas_bytes / 1e6)},
            "e2e": e2e, "gpu_launches": launches_timed, "roofline": roofline, "clocks": clk, "import_s": import_s,
            "scene_gen_s": timing["scene_gen_s"]}
     if cpu:

@@ -21,7 +21,7 @@ VDBINFO_BYTES, SCNINFO_BYTES = 1232, 416
 EXPORTED_SYMBOLS = [
     "gvdbx_create", "gvdbx_destroy", "gvdbx_last_error", "gvdbx_set_option",
     "gvdbx_import_topology", "gvdbx_import_topology_host",
-    "gvdbx_import_atlas_array", "gvdbx_import_atlas_host", "gvdbx_set_transfer",
+    "gvdbx_import_atlas_array", "gvdbx_import_atlas_host", "gvdbx_import_atlas_device", "gvdbx_set_transfer",
     "gvdbx_render", "gvdbx_render_tiles", "gvdbx_tiles_per_rank", "gvdbx_assemble_tiles",
     "gvdbx_render_debug", "gvdbx_raytrace", "gvdbx_read_buffer", "gvdbx_sync", "gvdbx_get_counters",
     "gvdbx_sample_points", "gvdbx_kernel_params", "gvdbx_update_apron", "gvdbx_export_atlas_host", "gvdbx_render_tiles_direct", "gvdbx_render_tiles_ring", "gvdbx_peer_alloc", "gvdbx_peer_free", "gvdbx_peer_open",
@@ -68,6 +68,7 @@ def lib():
     L.gvdbx_import_topology_host.argtypes = [vp, vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(u64)]
     L.gvdbx_import_atlas_array.argtypes = [vp, i32, vp, i32, i32, i32]
     L.gvdbx_import_atlas_host.argtypes = [vp, i32, vp, i32, i32, i32]
+    L.gvdbx_import_atlas_device.argtypes = [vp, i32, u64, i32, i32, i32]
     L.gvdbx_set_transfer.argtypes = [vp, vp]
     L.gvdbx_render.argtypes = [vp, vp, i32, i32, u64, i32, i32, i32, i32]
     L.gvdbx_render_tiles.argtypes = [vp, vp, i32, i32, u64, i32, i32, i32]
@@ -197,6 +198,10 @@ class Renderer:
         rz, ry, rx = a.shape
         self._ck(self._L.gvdbx_import_atlas_host(self._h, chan, a.ctypes.data_as(C.c_void_p), rx, ry, rz),
                  "gvdbx_import_atlas_host")
+
+    def import_atlas_device(self, texels_ptr, res_xyz, chan=0):
+        """atlas from a device image [z][y][x] float32 (e.g. received by a broadcast)"""
+        self._ck(self._L.gvdbx_import_atlas_device(self._h, chan, int(texels_ptr), *map(int, res_xyz)), "gvdbx_import_atlas_device")
 
     def import_atlas_array(self, cuarray, res_xyz, chan=0):
         self._ck(self._L.gvdbx_import_atlas_array(self._h, chan, C.c_void_p(cuarray), *map(int, res_xyz)),

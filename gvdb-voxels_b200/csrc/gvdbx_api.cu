@@ -403,6 +403,32 @@ extern "C" int gvdbx_export_atlas_host(gvdbx_t* h, int chan, float* texels, int 
     return GVDBX_OK;
 }
 
+// Same from a DEVICE image of the atlas (x fastest): what a rank receives when the volume is replicated with a
+// broadcast over NVLink instead of being rebuilt / re-uploaded by every process.
+extern "C" int gvdbx_import_atlas_device(gvdbx_t* h, int chan, uint64_t texels_d, int rx, int ry, int rz)
+{
+    if (!h || !texels_d || rx <= 0 || ry <= 0 || rz <= 0) return GVDBX_E_ARG;
+    if (chan != 0) return gx_fail(h, GVDBX_E_UNSUPPORTED, "only channel 0 (T_FLOAT) is supported");
+    GX_CUDA(h, cudaSetDevice(h->device));
+    gx_free_atlas(h);
+    cudaChannelFormatDesc fd = cudaCreateChannelDesc<float>();
+    GX_CUDA(h, cudaMalloc3DArray(&h->own_array, &fd, make_cudaExtent(rx, ry, rz), cudaArraySurfaceLoadStore));
+    cudaMemcpy3DParms cp;
+    memset(&cp, 0, sizeof cp);
+    cp.srcPtr = make_cudaPitchedPtr((void*)texels_d, size_t(rx) * sizeof(float), rx, ry);
+    cp.dstArray = h->own_array;
+    cp.extent = make_cudaExtent(rx, ry, rz);
+    cp.kind = cudaMemcpyDeviceToDevice;
+    GX_CUDA(h, cudaMemcpy3DAsync(&cp, h->stream));
+    int rc = gx_make_texture(h, h->own_array);
+    if (rc) return rc;
+    rc = gx_repack(h, (const float*)texels_d, rx, ry, rz);
+    GX_CUDA(h, cudaStreamSynchronize(h->stream));       // the caller may free / reuse its image now
+    if (rc) return rc;
+    h->have_atlas = true;
+    return GVDBX_OK;
+}
+
 extern "C" int gvdbx_set_transfer(gvdbx_t* h, const float* rgba_host)
 {
     if (!h || !rgba_host) return GVDBX_E_ARG;

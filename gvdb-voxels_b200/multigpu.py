@@ -219,3 +219,49 @@ class PeerFrameRing:
     def frame_tensor(self, q, torch, device):
         slot, _ = ring_slot(q, self.nslots)
         return torch.as_tensor(CudaBuffer(self.frame_ptr[slot], (self.h, self.w, 4)), device=device)
+
+
+# ------------------------------------------------------------------------------------------------ volume replication
+def replicate_volume(renderer, vol, rank, world, device, src=0):
+    """Replicate the volume of rank `src` on every rank: pools and atlas travel GPU to GPU (torch.distributed broadcast,
+    NCCL over NVLink) and are imported from device memory (gvdbx_import_topology with the VDBInfo pointers patched to the
+    received pools, gvdbx_import_atlas_device) — instead of every process rebuilding the topology and pushing the atlas
+    through its own PCIe link.  `vol` = {"vdbinfo", "pool0", "pool1", "atlas"} on rank `src`, ignored elsewhere.
+    Returns the metadata dict {"atlas_shape", "bricks", ...} on every rank."""
+    import torch
+    import torch.distributed as dist
+    meta = [None]
+    if rank == src:
+        meta[0] = {"vdbinfo": bytes(vol["vdbinfo"]), "atlas_shape": tuple(vol["atlas"].shape),
+                   "pool0": {int(l): int(len(b)) for l, b in vol["pool0"].items() if len(b)},
+                   "pool1": {int(l): int(len(b)) for l, b in vol["pool1"].items() if len(b)}}
+    if world > 1:
+        dist.broadcast_object_list(meta, src=src)
+    m = meta[0]
+
+    def bcast(host_array, nbytes, dtype):
+        if rank == src:
+            t = torch.from_numpy(np.ascontiguousarray(host_array)).view(dtype).to(device)
+        else:
+            t = torch.empty(nbytes // torch.empty(0, dtype=dtype).element_size(), dtype=dtype, device=device)
+        if world > 1:
+            dist.broadcast(t, src=src)
+        return t
+    pools = {}
+    for grp in ("pool0", "pool1"):
+        for lev, n in m[grp].items():
+            pools[(grp, lev)] = bcast(vol[grp][lev] if rank == src else None, n, torch.uint8)
+    # VDBInfo: nodelist[] at byte 440, childlist[] at byte 520 (8 bytes per level) hold the DEVICE pointers of the pools
+    vb = bytearray(m["vdbinfo"])
+    for lev in range(10):
+        p0 = pools.get(("pool0", lev))
+        p1 = pools.get(("pool1", lev))
+        vb[440 + 8 * lev: 448 + 8 * lev] = int(p0.data_ptr() if p0 is not None else 0).to_bytes(8, "little")
+        vb[520 + 8 * lev: 528 + 8 * lev] = int(p1.data_ptr() if p1 is not None else 0).to_bytes(8, "little")
+    renderer.import_topology(bytes(vb))
+    rz, ry, rx = m["atlas_shape"]
+    atlas = bcast(vol["atlas"].reshape(-1) if rank == src else None, rz * ry * rx * 4, torch.float32)
+    renderer.import_atlas_device(atlas.data_ptr(), (rx, ry, rz))
+    renderer.sync()
+    del atlas, pools
+    return m

@@ -101,6 +101,9 @@ int  gvdbx_import_atlas_array(gvdbx_t* h, int chan, void* cuarray, int res_x, in
 /* Same from a HOST image of the atlas, x fastest (the layout of Allocator::AtlasCommitFromCPU, gvdb_allocator.cpp:797). */
 int  gvdbx_import_atlas_host(gvdbx_t* h, int chan, const float* texels, int res_x, int res_y, int res_z);
 
+/* Same from a DEVICE image (x fastest), e.g. one received by a broadcast from the rank that built the volume. */
+int  gvdbx_import_atlas_device(gvdbx_t* h, int chan, uint64_t texels_d, int res_x, int res_y, int res_z);
+
 /* VolumeGVDB::UpdateApron(chan, boundval) (src/gvdb_volume_gvdb.cpp:4418-4453, kernels/cuda_gvdb_operators.cuh:72-126)
  * on the imported atlas: every apron texel takes the value of the voxel at its index-space position in whichever brick
  * contains it, else `boundval`.  Writes the 3-D array (the caller's, when imported with gvdbx_import_atlas_array —

@@ -839,6 +839,16 @@ int ora_max_threads(void)
 #endif
 }
 
+/* launchers such as torchrun export OMP_NUM_THREADS=1: let the caller ask for the host's cores explicitly */
+void ora_set_num_threads(int n)
+{
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 /* ============================================================================================ scenes */
 int ora_scene_preset(const char* name, void* out, size_t bytes)
 {

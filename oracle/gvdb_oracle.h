@@ -63,6 +63,7 @@ int       ora_render(const ora_volume* v, const void* scninfo416, int shade, int
 /* software model of the texture unit: trilinear fetch at atlas coordinate (x,y,z) */
 float     ora_tex3d(const ora_volume* v, float x, float y, float z);
 int       ora_max_threads(void);
+void      ora_set_num_threads(int n);
 
 /* ---- scenes (oracle/scenes.h) */
 int       ora_scene_preset(const char* name, void* preset_out, size_t preset_bytes);

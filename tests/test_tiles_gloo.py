@@ -70,3 +70,76 @@ def test_tile_ids_cover_frame_exactly_once():
         ids = sorted(t for r in range(world) for t in mg.tile_ids_for_rank(w, h, ts, r, world))
         assert ids == list(range(mg.tile_grid(w, h, ts)[2]))
         assert max(len(mg.tile_ids_for_rank(w, h, ts, r, world)) for r in range(world)) == mg.slots_per_rank(w, h, ts, world)
+
+
+# ------------------------------------------------------------------------------------------------ volume replication
+class _FakeImportRenderer:
+    """records what multigpu.replicate_volume hands to the import calls (CPU tensors: the 'device pointers' are host
+    addresses, read back with ctypes)"""
+
+    def __init__(self):
+        self.pools, self.atlas = {}, None
+
+    def import_topology(self, vdbinfo):
+        import ctypes
+        vb = np.frombuffer(vdbinfo, np.uint8)
+        assert vb.size == 1232
+        cnt, wid, cw = vb[320:360].view(np.int32), vb[360:400].view(np.int32), vb[400:440].view(np.int32)
+        nl, cl = vb[440:520].view(np.uint64), vb[520:600].view(np.uint64)
+        for lev in range(5):
+            if nl[lev]:
+                self.pools[("pool0", lev)] = ctypes.string_at(int(nl[lev]), int(cnt[lev]) * int(wid[lev]))
+            if cl[lev]:
+                self.pools[("pool1", lev)] = ctypes.string_at(int(cl[lev]), int(self.n1[lev]))
+        self.vdbinfo_masked = bytes(vb[:440]) + bytes(vb[600:])
+
+    def import_atlas_device(self, ptr, res_xyz):
+        import ctypes
+        rx, ry, rz = res_xyz
+        self.atlas = np.frombuffer(ctypes.string_at(int(ptr), rx * ry * rz * 4), np.float32).reshape(rz, ry, rx).copy()
+
+    def sync(self):
+        pass
+
+
+def _replicate_worker(rank, world, port, q):
+    import hashlib
+    import torch
+    import torch.distributed as dist
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from __graft_entry__ import load_package
+    load_package()
+    from gvdb_voxels_b200 import multigpu as mg
+    import oracle
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    p, vol = oracle.scene_volume("cfg3_tiny")          # every rank can build it: the received copy is compared with it
+    r = _FakeImportRenderer()
+    r.n1 = {lev: len(b) for lev, b in vol["pool1"].items()}
+    meta = mg.replicate_volume(r, vol if rank == 0 else None, rank, world, torch.device("cpu"))
+    ok = tuple(meta["atlas_shape"]) == vol["atlas"].shape and np.array_equal(r.atlas, vol["atlas"])
+    for (grp, lev), b in r.pools.items():
+        ok &= b == bytes(np.ascontiguousarray(vol[grp][lev]).tobytes())
+    ok &= len(r.pools) == sum(1 for g in ("pool0", "pool1") for b in vol[g].values() if len(b))
+    vb = np.frombuffer(vol["vdbinfo"], np.uint8)
+    ok &= r.vdbinfo_masked == bytes(vb[:440]) + bytes(vb[600:])
+    dist.barrier()
+    dist.destroy_process_group()
+    q.put((rank, bool(ok)))
+
+
+def test_replicate_volume_two_ranks():
+    """rank 0's pools / atlas / VDBInfo arrive bit-identical on rank 1 and are handed to the import calls by pointer"""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_replicate_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=180) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert all(ok for _, ok in res), res
