@@ -55,3 +55,17 @@ def test_product_does_not_reference_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h", "Makefile")):
                 text = open(os.path.join(dirpath, f), errors="ignore").read()
                 assert "liboracle" not in text and "gvdb_oracle" not in text and "oracle/" not in text.replace("oracle/_ref/ref_hostdump", ""), f
+
+
+def test_python_constants_match_header(pkg):
+    """shade modes / options / sizes of the ctypes front end are the header's"""
+    hdr = open(os.path.join(ROOT, "include", "gvdbx.h")).read()
+    defs = {k: int(v) for k, v in re.findall(r"#define\s+(GVDBX_[A-Z_0-9]+)\s+(-?\d+)\b", hdr)}
+    for name in ("VOXEL", "SECTION2D", "SECTION3D", "EMPTYSKIP", "TRILINEAR", "TRICUBIC", "LEVELSET", "VOLUME", "OFF"):
+        assert getattr(pkg, f"SHADE_{name}") == defs[f"GVDBX_SHADE_{name}"], name
+    for name in ("SAMPLER", "BLOCK_W", "BLOCK_H", "COUNTERS", "TRAVERSAL", "CULL", "SPP", "DEEP_SHADOW"):
+        assert getattr(pkg, f"OPT_{name}") == defs[f"GVDBX_OPT_{name}"], name
+    assert pkg.VDBINFO_BYTES == defs["GVDBX_VDBINFO_BYTES"] and pkg.SCNINFO_BYTES == defs["GVDBX_SCNINFO_BYTES"]
+    # every option number is unique
+    opts = [v for k, v in defs.items() if k.startswith("GVDBX_OPT_")]
+    assert len(opts) == len(set(opts))
