@@ -89,6 +89,10 @@ struct GxParams {
     const int*       child[GX_MAXLEV];   // child[lev][node * cells(lev) + b] = index at lev-1, or -1
     const int4*      npos[GX_MAXLEV];    // npos[lev][node] = {mPos, 0}            (lev >= 1)
     const GxLeafRec* leaf;               // leaf[node]                              (lev == 0)
+    // ---- the reference's own pools (GX_REF_LAYOUT builds only): VDBInfo::nodelist / nodewid / childlist / childwid
+    const char* ref_nodes[GX_MAXLEV];
+    const char* ref_clist[GX_MAXLEV];
+    int         ref_nodewid[GX_MAXLEV], ref_childwid[GX_MAXLEV];
     // ---- atlas
     cudaTextureObject_t tex;             // caller's 3-D array, linear filter, unnormalised, clamp
     const float*        bricks;          // brick-major copy
@@ -249,6 +253,45 @@ template <class S> __device__ __forceinline__ float3 gx_vdel(const GxParams& P, 
     return P.vdel[lev];
 }
 
+// ------------------------------------------------------------------------------------------------ tree tables
+// Two layouts behind four accessors.  Default: the compact tables built at import (§2 of DESIGN.md).  GX_REF_LAYOUT (the
+// module-level drop-in, csrc/gvdbx_module.cu): the reference's own pools as VDBInfo points at them — 64-byte node
+// records (mPos@4, mValue@16, mChildList@48) and per-node lists of 64-bit child entries (index = entry >> 16, all ones =
+// no child), kernels/cuda_gvdb_nodes.cuh:24-35, :115-129, :184-196.
+#ifdef GX_REF_LAYOUT
+typedef const unsigned long long* gx_ctab_t;
+__device__ __forceinline__ const GxNode* gx_ref_node(const GxParams& P, int lev, int node)
+{
+    return reinterpret_cast<const GxNode*>(P.ref_nodes[lev] + size_t(node) * P.ref_nodewid[lev]);
+}
+__device__ __forceinline__ gx_ctab_t gx_table(const GxParams& P, int lev, int node, int /*dim*/)
+{
+    const unsigned long long listid = gx_ref_node(P, lev, node)->mChildList;
+    if (listid == GX_ID_UNDEFL) return nullptr;
+    return reinterpret_cast<gx_ctab_t>(P.ref_clist[lev] + size_t(listid >> 16) * P.ref_childwid[lev]);
+}
+__device__ __forceinline__ int gx_child(gx_ctab_t t, int b) { return t ? int(__ldg(t + b) >> 16) : -1; }
+__device__ __forceinline__ int4 gx_node_pos(const GxParams& P, int lev, int node)
+{
+    const GxNode* n = gx_ref_node(P, lev, node);
+    return make_int4(n->mPos.x, n->mPos.y, n->mPos.z, 0);
+}
+__device__ __forceinline__ GxLeafRec gx_leaf(const GxParams& P, int node)
+{
+    const GxNode* n = gx_ref_node(P, 0, node);
+    GxLeafRec r;
+    r.px = n->mPos.x; r.py = n->mPos.y; r.pz = n->mPos.z; r.base = 0;
+    r.vx = n->mValue.x; r.vy = n->mValue.y; r.vz = n->mValue.z; r.pad = 0;
+    return r;
+}
+#else
+typedef const int* gx_ctab_t;
+__device__ __forceinline__ gx_ctab_t gx_table(const GxParams& P, int lev, int node, int dim) { return P.child[lev] + (size_t(node) << (3 * dim)); }
+__device__ __forceinline__ int gx_child(gx_ctab_t t, int b) { return __ldg(t + b); }
+__device__ __forceinline__ int4 gx_node_pos(const GxParams& P, int lev, int node) { return __ldg(&P.npos[lev][node]); }
+__device__ __forceinline__ GxLeafRec gx_leaf(const GxParams& P, int node) { return P.leaf[node]; }
+#endif
+
 // ------------------------------------------------------------------------------------------------ geometry
 // slab test: (tnear clamped to >= 0, tfar, 0 | NOHIT)                       cuda_gvdb_geom.cuh:85-98
 __device__ __forceinline__ float3 gx_ray_box(float3 rpos, float3 rdir, float3 vmin, float3 vmax)
@@ -369,7 +412,7 @@ template <class S>
 __device__ __forceinline__ void gx_brick_voxel(const GxParams& P, S& smp, int nodeid, float3 t, float3 pos, float3 dir,
                                                GxHit& h, GxCount& cnt)
 {
-    const GxLeafRec L = P.leaf[nodeid];
+    const GxLeafRec L = gx_leaf(P, nodeid);
     cnt.n_desc++;
     if (P.range != nullptr && !(__ldg(&P.range[nodeid].hi) > P.thresh.x)) return;             // no voxel above THRESH
     smp.enter(L);
@@ -437,7 +480,7 @@ template <class S>
 __device__ __forceinline__ void gx_brick_trilinear(const GxParams& P, S& smp, int nodeid, float3 t, float3 pos, float3 dir,
                                                    GxHit& h, GxCount& cnt)
 {
-    const GxLeafRec L = P.leaf[nodeid];
+    const GxLeafRec L = gx_leaf(P, nodeid);
     cnt.n_desc++;
     smp.enter(L);
     float3 vmin = make_float3(float(L.px), float(L.py), float(L.pz));
@@ -465,7 +508,7 @@ template <class S>
 __device__ __forceinline__ void gx_brick_levelset(const GxParams& P, S& smp, int nodeid, float3 t, float3 pos, float3 dir,
                                                   GxHit& h, GxCount& cnt)
 {
-    const GxLeafRec L = P.leaf[nodeid];
+    const GxLeafRec L = gx_leaf(P, nodeid);
     cnt.n_desc++;
     smp.enter(L);
     float3 vmin = make_float3(float(L.px), float(L.py), float(L.pz));
@@ -494,7 +537,7 @@ template <class S>
 __device__ __forceinline__ void gx_brick_deep(const GxParams& P, S& smp, int nodeid, float3 t, float3 pos, float3 dir,
                                               GxHit& h, GxCount& cnt, float tDepth)
 {
-    const GxLeafRec L = P.leaf[nodeid];
+    const GxLeafRec L = gx_leaf(P, nodeid);
     cnt.n_desc++;
     smp.enter(L);
     float3 vmin = make_float3(float(L.px), float(L.py), float(L.pz));
@@ -560,7 +603,11 @@ struct GxStackReg {            // register-resident variant (used by the A/B pac
 // two dynamically indexed local-memory arrays).  GX_STACK_BYTES_PER_THREAD of dynamic shared memory per thread.
 #define GX_STACK_BYTES_PER_THREAD 32
 struct GxStack {
+#ifdef GX_REF_LAYOUT    // launched by the reference's own RenderKernel / Render (no dynamic shared memory): room for 16 x 16 CTAs
+    static __device__ __forceinline__ int* base() { __shared__ int gx_stack_static[8 * 256]; return gx_stack_static; }
+#else
     static __device__ __forceinline__ int* base() { extern __shared__ int gx_stack_smem[]; return gx_stack_smem; }
+#endif
     static __device__ __forceinline__ int  slot(int lev)
     {
         const int nt = blockDim.x * blockDim.y;
@@ -603,7 +650,7 @@ __device__ __forceinline__ void gx_raycast(const GxParams& P, S& smp, float3 pos
     float3 tStart = gx_ray_box(pos, dir, P.bmin, P.bmax);
     if (tStart.z == GX_NOHIT) return;
     if (lev < 1 || lev >= GX_MAXLEV) return;        // single-brick volume: the reference loop never runs either
-    int4 np = __ldg(&P.npos[lev][0]);
+    int4 np = gx_node_pos(P, lev, 0);
     cnt.n_desc++;
     float3 vmin = make_float3(float(np.x), float(np.y), float(np.z));
 
@@ -611,7 +658,7 @@ __device__ __forceinline__ void gx_raycast(const GxParams& P, S& smp, float3 pos
     st.set(lev, 0, tStart.y - P.epsilon);
     // the state of the CURRENT level is mirrored in plain registers so that the per-step code has no select chains:
     float      cur_tmax = tStart.y - P.epsilon;       // exit parameter of the current node
-    const int* ctab = P.child[lev];                   // child table of the current node (node 0 of the top level)
+    gx_ctab_t  ctab = gx_table(P, lev, 0, gx_dim<S>(P, lev));   // child table of the current node (node 0 of the top level)
     unsigned   res = unsigned(gx_res<S>(P, lev));
 
     GxDDA dda;
@@ -630,7 +677,7 @@ __device__ __forceinline__ void gx_raycast(const GxParams& P, S& smp, float3 pos
         // cells with a coordinate == res can only be reached through the reference's inclusive loop bound; they hold no
         // child.  res is a power of two, so "all three coordinates < res" is one compare on their OR.
         int c = -1;
-        if (unsigned(dda.p.x | dda.p.y | dda.p.z) < res) c = __ldg(ctab + b);
+        if (unsigned(dda.p.x | dda.p.y | dda.p.z) < res) c = gx_child(ctab, b);
         cnt.n_dda++;
         if (c != -1) {
             if (lev == 1) {
@@ -653,13 +700,13 @@ __device__ __forceinline__ void gx_raycast(const GxParams& P, S& smp, float3 pos
                 dda.step();
             } else {
                 lev--;
-                np = __ldg(&P.npos[lev][c]);
+                np = gx_node_pos(P, lev, c);
                 cnt.n_desc++;
                 vmin = make_float3(float(np.x), float(np.y), float(np.z));
                 dda.t.x += P.epsilon;
                 cur_tmax = dda.t.y - P.epsilon;
                 st.set(lev, c, cur_tmax);
-                ctab = P.child[lev] + (size_t(c) << (3 * gx_dim<S>(P, lev)));
+                ctab = gx_table(P, lev, c, gx_dim<S>(P, lev));
                 res = unsigned(gx_res<S>(P, lev));
                 dda.prepare(vmin, gx_vdel<S>(P, lev));
             }
@@ -671,9 +718,9 @@ __device__ __forceinline__ void gx_raycast(const GxParams& P, S& smp, float3 pos
             if (lev <= P.top_lev) {
                 const int n = st.node(lev);
                 cur_tmax = st.tmax(lev);
-                ctab = P.child[lev] + (size_t(n) << (3 * gx_dim<S>(P, lev)));
+                ctab = gx_table(P, lev, n, gx_dim<S>(P, lev));
                 res = unsigned(gx_res<S>(P, lev));
-                np = __ldg(&P.npos[lev][n]);
+                np = gx_node_pos(P, lev, n);
                 cnt.n_desc++;
                 vmin = make_float3(float(np.x), float(np.y), float(np.z));
                 dda.prepare(vmin, gx_vdel<S>(P, lev));

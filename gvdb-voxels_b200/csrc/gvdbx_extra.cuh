@@ -23,7 +23,7 @@ __device__ __forceinline__ int gx_node_at_point(const GxParams& P, float3 pos, G
     if (lev < 0 || lev >= GX_MAXLEV) return -1;
     int n = 0;
     if (lev == 0) return 0;
-    int4 np = __ldg(&P.npos[lev][0]);
+    int4 np = gx_node_pos(P, lev, 0);
     cnt.n_desc++;
     float3 vmin = make_float3(float(np.x), float(np.y), float(np.z));
     while (lev > 0) {
@@ -37,13 +37,13 @@ __device__ __forceinline__ int gx_node_at_point(const GxParams& P, float3 pos, G
         // the approximate division can round a coordinate just below the upper face up to res: the reference then reads a
         // neighbouring cell (or past the list); such a point is treated as outside here
         if (unsigned(b) >= (1u << (3 * dm))) return -1;
-        const int c = __ldg(P.child[lev] + (size_t(n) << (3 * dm)) + b);
+        const int c = gx_child(gx_table(P, lev, n, dm), b);
         cnt.n_dda++;
         lev--;
         if (c == -1) return -1;
         n = c;
         if (lev > 0) {
-            np = __ldg(&P.npos[lev][n]);
+            np = gx_node_pos(P, lev, n);
             cnt.n_desc++;
             vmin = make_float3(float(np.x), float(np.y), float(np.z));
         }
@@ -127,7 +127,7 @@ template <class S>
 __device__ __forceinline__ void gx_brick_tricubic(const GxParams& P, S& smp, int nodeid, float3 t, float3 pos, float3 dir,
                                                   GxHit& h, GxCount& cnt)
 {
-    const GxLeafRec L = P.leaf[nodeid];
+    const GxLeafRec L = gx_leaf(P, nodeid);
     cnt.n_desc++;
     smp.enter(L);
     float3 vmin = make_float3(float(L.px), float(L.py), float(L.pz));
@@ -159,7 +159,7 @@ template <class S>
 __device__ __forceinline__ void gx_brick_shadow(const GxParams& P, S& smp, int nodeid, float3 t, float3 pos, float3 dir,
                                                 GxHit& h, GxCount& cnt)
 {
-    const GxLeafRec L = P.leaf[nodeid];
+    const GxLeafRec L = gx_leaf(P, nodeid);
     cnt.n_desc++;
     smp.enter(L);
     float3 vmin = make_float3(float(L.px), float(L.py), float(L.pz));
@@ -224,7 +224,7 @@ __device__ __forceinline__ float4 gx_pixel_section2d(const GxParams& P, S& smp, 
     float3 wpos = P.slice_pnt + spnt * P.slice_norm;
     const int n = gx_node_at_point<S>(P, wpos, cnt);
     if (n < 0) return make_float4(bgclr.x, bgclr.y, bgclr.z, 1);
-    const GxLeafRec L = P.leaf[n];
+    const GxLeafRec L = gx_leaf(P, n);
     cnt.n_desc++;
     smp.enter(L);
     const float3 vmin = make_float3(float(L.px), float(L.py), float(L.pz));
@@ -252,7 +252,7 @@ __device__ __forceinline__ float4 gx_pixel_section3d(const GxParams& P, S& smp, 
         wpos += t * rdir;
         const int n = gx_node_at_point<S>(P, wpos, cnt);
         if (n >= 0) {
-            const GxLeafRec L = P.leaf[n];
+            const GxLeafRec L = gx_leaf(P, n);
             cnt.n_desc++;
             smp.enter(L);
             const float3 vmin = make_float3(float(L.px), float(L.py), float(L.pz));

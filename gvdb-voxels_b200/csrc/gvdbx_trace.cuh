@@ -43,7 +43,7 @@ template <class S>
 __device__ __forceinline__ void gx2_brick_trilinear(const GxParams& P, S& smp, int nodeid, float3 t, float3 pos, float3 dir,
                                                     GxHit& h, GxCount& cnt)
 {
-    const GxLeafRec L = P.leaf[nodeid];
+    const GxLeafRec L = gx_leaf(P, nodeid);
     cnt.n_desc++;
     const float st = P.steps.x, thr = P.thresh.x;
     if (P.range != nullptr && !(__ldg(&P.range[nodeid].hi) >= thr)) return;                // no sample can reach THRESH
@@ -87,7 +87,7 @@ template <class S>
 __device__ __forceinline__ void gx2_brick_levelset(const GxParams& P, S& smp, int nodeid, float3 t, float3 pos, float3 dir,
                                                    GxHit& h, GxCount& cnt)
 {
-    const GxLeafRec L = P.leaf[nodeid];
+    const GxLeafRec L = gx_leaf(P, nodeid);
     cnt.n_desc++;
     const float st = P.steps.x, thr = P.thresh.x;
     if (P.range != nullptr && !(__ldg(&P.range[nodeid].lo) < thr)) return;                 // no sample can fall below THRESH
@@ -135,6 +135,11 @@ __device__ __forceinline__ void gx_deep_accumulate(const GxParams& P, float4& cl
     clr.z = __fadd_rn(clr.z, __fmul_rn(__fmul_rn(__fmul_rn(val.z, clr.w), om), P.extinct.y));
     clr.w *= val.w;
 }
+#ifdef GX_REF_LAYOUT
+#define GX_DEEP_LUT false
+#else
+#define GX_DEEP_LUT true
+#endif
 // The same update with the per-sample transparency exp(EXTINCT * alpha * DIRECTSTEP) already in val.w: it depends only on
 // the table entry and two frame constants, so gx_build_deep_lut evaluates it once per entry and frame with the very
 // expression above (same instruction sequence, same bits) instead of once per sample.
@@ -163,7 +168,7 @@ template <class S>
 __device__ __forceinline__ void gx2_brick_deep(const GxParams& P, S& smp, int nodeid, float3 t, float3 pos, float3 dir,
                                                GxHit& h, GxCount& cnt, float tDepth)
 {
-    const GxLeafRec L = P.leaf[nodeid];
+    const GxLeafRec L = gx_leaf(P, nodeid);
     cnt.n_desc++;
     const float st = P.steps.x;
     t.x = st * ceilf(t.x / st);
@@ -209,7 +214,10 @@ __device__ __forceinline__ void gx2_brick_deep(const GxParams& P, S& smp, int no
             const float v3 = smp.tri(p3.x + o.x, p3.y + o.y, p3.z + o.z);
             const bool a0 = v0 >= minval, a1 = v1 >= minval, a2 = v2 >= minval, a3 = v3 >= minval;
             // transfer-function reads of the whole round in flight together (entry 0 for rejected samples, unused)
-            const float4* lut = P.transfer_deep;        // {rgb, exp(EXTINCT * alpha * DIRECTSTEP)}: built for this frame by the host side
+            // {rgb, exp(EXTINCT * alpha * DIRECTSTEP)} built for this frame by the host side; the module-level drop-in has no
+            // host side: plain table, exp per sample
+            constexpr bool pre = GX_DEEP_LUT;
+            const float4* lut = pre ? P.transfer_deep : P.transfer;
             const float4 c0 = __ldg(&lut[a0 ? gx_transfer_index(v0, thresh, inv_range) : 0]);
             const float4 c1 = __ldg(&lut[a1 ? gx_transfer_index(v1, thresh, inv_range) : 0]);
             const float4 c2 = __ldg(&lut[a2 ? gx_transfer_index(v2, thresh, inv_range) : 0]);
@@ -217,10 +225,10 @@ __device__ __forceinline__ void gx2_brick_deep(const GxParams& P, S& smp, int no
             // consume in order; `done` = samples processed (each is followed by one position / t step in the reference)
             int done = 0;
             bool more = k0;             // loop condition for sample 0 (alpha was checked by the for statement)
-            if (more) { done = 1; cnt.s_tri++; if (a0) { cnt.s_lut++; gx_deep_accumulate_pre(P, clr, c0); } more = k1 && clr.w > acut; }
-            if (more) { done = 2; cnt.s_tri++; if (a1) { cnt.s_lut++; gx_deep_accumulate_pre(P, clr, c1); } more = k2 && clr.w > acut; }
-            if (more) { done = 3; cnt.s_tri++; if (a2) { cnt.s_lut++; gx_deep_accumulate_pre(P, clr, c2); } more = k3 && clr.w > acut; }
-            if (more) { done = 4; cnt.s_tri++; if (a3) { cnt.s_lut++; gx_deep_accumulate_pre(P, clr, c3); } }
+            if (more) { done = 1; cnt.s_tri++; if (a0) { cnt.s_lut++; if (pre) gx_deep_accumulate_pre(P, clr, c0); else gx_deep_accumulate(P, clr, c0); } more = k1 && clr.w > acut; }
+            if (more) { done = 2; cnt.s_tri++; if (a1) { cnt.s_lut++; if (pre) gx_deep_accumulate_pre(P, clr, c1); else gx_deep_accumulate(P, clr, c1); } more = k2 && clr.w > acut; }
+            if (more) { done = 3; cnt.s_tri++; if (a2) { cnt.s_lut++; if (pre) gx_deep_accumulate_pre(P, clr, c2); else gx_deep_accumulate(P, clr, c2); } more = k3 && clr.w > acut; }
+            if (more) { done = 4; cnt.s_tri++; if (a3) { cnt.s_lut++; if (pre) gx_deep_accumulate_pre(P, clr, c3); else gx_deep_accumulate(P, clr, c3); } }
             for (int q = 0; q < done; q++) t.x += dt;
             if (done < 4) break;        // left the brick or fell below ALPHACUT inside this round
             GX_STEP_ADD(p, p3);
@@ -255,7 +263,7 @@ template <int MODE, class S>
 __device__ __forceinline__ bool gx3_begin(const GxParams& P, S& smp, int nodeid, float3 t, float3 pos, float3 dir, GxHit& h,
                                           GxCount& cnt, GxMarch& M)
 {
-    const GxLeafRec L = P.leaf[nodeid];
+    const GxLeafRec L = gx_leaf(P, nodeid);
     cnt.n_desc++;
     const float st = P.steps.x;
     if constexpr (MODE == GX_MODE_TRILINEAR) {
@@ -308,17 +316,18 @@ __device__ __forceinline__ bool gx3_round(const GxParams& P, S& smp, float3 pos,
         const float v2 = smp.tri(p2.x + o.x, p2.y + o.y, p2.z + o.z);
         const float v3 = smp.tri(p3.x + o.x, p3.y + o.y, p3.z + o.z);
         const bool a0 = v0 >= minval, a1 = v1 >= minval, a2 = v2 >= minval, a3 = v3 >= minval;
-        const float4* lut = P.transfer_deep;
+        constexpr bool pre = GX_DEEP_LUT;
+        const float4* lut = pre ? P.transfer_deep : P.transfer;
         const float4 c0 = __ldg(&lut[a0 ? gx_transfer_index(v0, thresh, inv_range) : 0]);
         const float4 c1 = __ldg(&lut[a1 ? gx_transfer_index(v1, thresh, inv_range) : 0]);
         const float4 c2 = __ldg(&lut[a2 ? gx_transfer_index(v2, thresh, inv_range) : 0]);
         const float4 c3 = __ldg(&lut[a3 ? gx_transfer_index(v3, thresh, inv_range) : 0]);
         int done = 0;
         bool more = k0;
-        if (more) { done = 1; cnt.s_tri++; if (a0) { cnt.s_lut++; gx_deep_accumulate_pre(P, clr, c0); } more = k1 && clr.w > acut; }
-        if (more) { done = 2; cnt.s_tri++; if (a1) { cnt.s_lut++; gx_deep_accumulate_pre(P, clr, c1); } more = k2 && clr.w > acut; }
-        if (more) { done = 3; cnt.s_tri++; if (a2) { cnt.s_lut++; gx_deep_accumulate_pre(P, clr, c2); } more = k3 && clr.w > acut; }
-        if (more) { done = 4; cnt.s_tri++; if (a3) { cnt.s_lut++; gx_deep_accumulate_pre(P, clr, c3); } }
+        if (more) { done = 1; cnt.s_tri++; if (a0) { cnt.s_lut++; if (pre) gx_deep_accumulate_pre(P, clr, c0); else gx_deep_accumulate(P, clr, c0); } more = k1 && clr.w > acut; }
+        if (more) { done = 2; cnt.s_tri++; if (a1) { cnt.s_lut++; if (pre) gx_deep_accumulate_pre(P, clr, c1); else gx_deep_accumulate(P, clr, c1); } more = k2 && clr.w > acut; }
+        if (more) { done = 3; cnt.s_tri++; if (a2) { cnt.s_lut++; if (pre) gx_deep_accumulate_pre(P, clr, c2); else gx_deep_accumulate(P, clr, c2); } more = k3 && clr.w > acut; }
+        if (more) { done = 4; cnt.s_tri++; if (a3) { cnt.s_lut++; if (pre) gx_deep_accumulate_pre(P, clr, c3); else gx_deep_accumulate(P, clr, c3); } }
         for (int q = 0; q < done; q++) M.tx += M.dt;
         M.it += 4;
         if (done == 4 && M.it < GX_MAX_ITER && clr.w > acut) { GX_STEP_ADD(M.p, p3); return false; }
@@ -346,7 +355,7 @@ __device__ __forceinline__ bool gx3_round(const GxParams& P, S& smp, float3 pos,
         if (k >= 0) {
             cnt.s_tri += k + (hit ? (ls ? 2 : 1) : 0);
             if (hit) {
-                const GxLeafRec L = P.leaf[M.node];
+                const GxLeafRec L = gx_leaf(P, M.node);
                 h.hit = p + make_float3(float(L.px), float(L.py), float(L.pz));
                 h.norm = gx_gradient(smp, p + o, cnt, ls);
                 h.t = M.tx; h.leaf = M.node; h.vox = gx_i3(gx_floor(h.hit));
@@ -369,13 +378,13 @@ __device__ __forceinline__ void gx_raycast_sm(const GxParams& P, S& smp, float3 
     float3 tStart = gx_ray_box(pos, dir, P.bmin, P.bmax);
     if (tStart.z == GX_NOHIT) return;
     if (lev < 1 || lev >= GX_MAXLEV) return;
-    int4 np = __ldg(&P.npos[lev][0]);
+    int4 np = gx_node_pos(P, lev, 0);
     cnt.n_desc++;
     float3 vmin = make_float3(float(np.x), float(np.y), float(np.z));
     tStart.x += P.epsilon;
     st.set(lev, 0, tStart.y - P.epsilon);
     float      cur_tmax = tStart.y - P.epsilon;
-    const int* ctab = P.child[lev];
+    gx_ctab_t  ctab = gx_table(P, lev, 0, gx_dim<S>(P, lev));
     unsigned   res = unsigned(gx_res<S>(P, lev));
     GxDDA dda;
     dda.set_ray(pos, dir, tStart);
@@ -389,9 +398,9 @@ __device__ __forceinline__ void gx_raycast_sm(const GxParams& P, S& smp, float3 
             if (lev <= P.top_lev) {
                 const int n = st.node(lev);
                 cur_tmax = st.tmax(lev);
-                ctab = P.child[lev] + (size_t(n) << (3 * gx_dim<S>(P, lev)));
+                ctab = gx_table(P, lev, n, gx_dim<S>(P, lev));
                 res = unsigned(gx_res<S>(P, lev));
-                const int4 q = __ldg(&P.npos[lev][n]);
+                const int4 q = gx_node_pos(P, lev, n);
                 cnt.n_desc++;
                 dda.prepare(make_float3(float(q.x), float(q.y), float(q.z)), gx_vdel<S>(P, lev));
             }
@@ -420,7 +429,7 @@ __device__ __forceinline__ void gx_raycast_sm(const GxParams& P, S& smp, float3 
                     const int dm = gx_dim<S>(P, lev);
                     const int b = (((int(dda.p.z) << dm) + int(dda.p.y)) << dm) + int(dda.p.x);
                     int c = -1;
-                    if (unsigned(dda.p.x | dda.p.y | dda.p.z) < res) c = __ldg(ctab + b);
+                    if (unsigned(dda.p.x | dda.p.y | dda.p.z) < res) c = gx_child(ctab, b);
                     cnt.n_dda++;
                     bool tail = true;                   // finish the reference iteration now (ascend, iter++)
                     if (c != -1) {
@@ -430,12 +439,12 @@ __device__ __forceinline__ void gx_raycast_sm(const GxParams& P, S& smp, float3 
                             else if (!after_brick()) { state = DONE; tail = false; }
                         } else {
                             lev--;
-                            np = __ldg(&P.npos[lev][c]);
+                            np = gx_node_pos(P, lev, c);
                             cnt.n_desc++;
                             dda.t.x += P.epsilon;
                             cur_tmax = dda.t.y - P.epsilon;
                             st.set(lev, c, cur_tmax);
-                            ctab = P.child[lev] + (size_t(c) << (3 * gx_dim<S>(P, lev)));
+                            ctab = gx_table(P, lev, c, gx_dim<S>(P, lev));
                             res = unsigned(gx_res<S>(P, lev));
                             dda.prepare(make_float3(float(np.x), float(np.y), float(np.z)), gx_vdel<S>(P, lev));
                         }
@@ -475,7 +484,7 @@ __device__ __forceinline__ void gx2_start(const GxParams& P, GxTrav& T, float3 p
     float3 tStart = gx_ray_box(pos, dir, P.bmin, P.bmax);
     if (tStart.z == GX_NOHIT) return;
     if (T.lev < 1 || T.lev >= GX_MAXLEV) return;
-    const int4 np = __ldg(&P.npos[T.lev][0]);
+    const int4 np = gx_node_pos(P, T.lev, 0);
     cnt.n_desc++;
     const float3 vmin = make_float3(float(np.x), float(np.y), float(np.z));
     tStart.x += P.epsilon;
@@ -493,7 +502,7 @@ __device__ __forceinline__ void gx2_ascend(const GxParams& P, GxTrav& T, GxCount
     while (T.dda.t.x > T.st.tmax(T.lev) && T.lev <= P.top_lev) {
         T.lev++;
         if (T.lev <= P.top_lev) {
-            const int4 np = __ldg(&P.npos[T.lev][T.st.node(T.lev)]);
+            const int4 np = gx_node_pos(P, T.lev, T.st.node(T.lev));
             cnt.n_desc++;
             T.dda.prepare(make_float3(float(np.x), float(np.y), float(np.z)), gx_vdel<S>(P, T.lev));
         }
@@ -516,13 +525,13 @@ __device__ __forceinline__ int gx2_dda_iteration(const GxParams& P, GxTrav& T, G
     const int b = (((int(d.p.z) << dm) + int(d.p.y)) << dm) + int(d.p.x);
     int c = -1;
     if (d.p.x < gx_res<S>(P, lev) && d.p.y < gx_res<S>(P, lev) && d.p.z < gx_res<S>(P, lev))
-        c = __ldg(&P.child[lev][(size_t(T.st.node(lev)) << (3 * dm)) + b]);
+        c = gx_child(gx_table(P, lev, T.st.node(lev), dm), b);
     cnt.n_dda++;
     if (c != -1) {
         d.t.x += P.epsilon;
         if (lev == 1) return c;
         T.lev = lev - 1;
-        const int4 np = __ldg(&P.npos[lev - 1][c]);
+        const int4 np = gx_node_pos(P, lev - 1, c);
         cnt.n_desc++;
         T.st.set(lev - 1, c, d.t.y - P.epsilon);
         d.prepare(make_float3(float(np.x), float(np.y), float(np.z)), gx_vdel<S>(P, lev - 1));

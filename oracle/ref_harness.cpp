@@ -68,6 +68,7 @@ int main(int argc, char** argv)
     std::string savevbx = "";
     int cfg[5] = {3, 3, 3, 3, 3};                  // Configure(q4..q0): log2 dims from the top level down to the brick
     int lightdump = 0;
+    std::string usermodule = "";                   // --module: render the native modes with the kernels of this cubin (RenderKernel)
     for (int i = 3; i < argc; i++) {
         std::string a = argv[i];
         if (a == "--modes" && i + 1 < argc) modes = argv[++i];
@@ -75,7 +76,8 @@ int main(int argc, char** argv)
         else if (a == "--frames" && i + 1 < argc) frames = atoi(argv[++i]);
         else if (a == "--warmup" && i + 1 < argc) warmup = atoi(argv[++i]);
         else if (a == "--nodump") nodump = 1;
-        else if (a == "--lightdump") lightdump = 1;        // images + ScnInfo + VDBInfo only (no pools / atlas: large volumes)
+        else if (a == "--lightdump") lightdump = 1;
+        else if (a == "--module" && i + 1 < argc) { usermodule = argv[++i]; hits = 0; }        // images + ScnInfo + VDBInfo only (no pools / atlas: large volumes)
         else if (a == "--shadow" && i + 1 < argc) shadow = atoi(argv[++i]);
         else if (a == "--hits" && i + 1 < argc) hits = atoi(argv[++i]);
         else if (a == "--bench") { bench = 1; nodump = 1; hits = 0; }
@@ -311,6 +313,20 @@ int main(int argc, char** argv)
         if (m.shade == SHADE_SECTION2D) scn->SetCrossSection(Vector3DF(cN, cN * 0.9f, cN), Vector3DF(cN * 0.8f, 1.0f, cN * 0.8f));
         if (m.shade == SHADE_SECTION3D) scn->SetCrossSection(Vector3DF(cN, cN, cN * 0.85f), Vector3DF(0.3f, 0.2f, 1.0f));
         CUfunction kfn = 0;
+        static CUmodule umod = 0;
+        if (m.kind == 0 && !usermodule.empty()) {
+            // module-level drop-in: same kernel NAME as the native one, taken from the user's cubin, launched through the
+            // reference's own plugin seam (SetModule + RenderKernel, 8 x 8 CTAs)
+            static const char* names[][2] = {{"voxel", "gvdbRaySurfaceVoxel"}, {"trilinear", "gvdbRaySurfaceTrilinear"}, {"tricubic", "gvdbRaySurfaceTricubic"},
+                                             {"levelset", "gvdbRayLevelSet"}, {"deep", "gvdbRayDeep"}, {"emptyskip", "gvdbRayEmptySkip"},
+                                             {"section2d", "gvdbSection2D"}, {"section3d", "gvdbSection3D"}};
+            const char* kname = "";
+            for (auto& n : names) if (std::string(n[0]) == m.name) kname = n[1];
+            if (!umod && cuModuleLoad(&umod, usermodule.c_str()) != CUDA_SUCCESS) { fprintf(stderr, "cannot load %s\n", usermodule.c_str()); return 5; }
+            if (cuModuleGetFunction(&kfn, umod, kname) != CUDA_SUCCESS) { fprintf(stderr, "no kernel %s in %s\n", kname, usermodule.c_str()); return 5; }
+            gvdb.SetModule(umod);
+            scn->SetShading(m.shade);
+        }
         if (m.kind != 0) {
             CUmodule use = omod;
             if (m.kind == 3) {
@@ -323,7 +339,8 @@ int main(int argc, char** argv)
             scn->SetShading(m.shade);
         }
         auto render = [&]() {
-            if (m.kind == 0) gvdb.Render(m.shade, 0, 0);
+            if (m.kind == 0 && kfn) gvdb.RenderKernel(kfn, 0, 0);
+            else if (m.kind == 0) gvdb.Render(m.shade, 0, 0);
             else if (m.kind == 1 || m.kind == 3) gvdb.RenderKernel(kfn, 0, 0);
             else for (int sidx = 0; sidx < spp; sidx++) { scn->SetSample(sidx); scn->SetFrame(spp); gvdb.RenderKernel(kfn, 0, 3); }
         };
@@ -360,7 +377,7 @@ int main(int argc, char** argv)
             dump(outdir + "/out_" + m.name + ".rgba", img.data(), img.size());
             dump(outdir + "/scninfo_" + m.name + ".bin", gvdb.getScnInfo(), 416);
         }
-        if (m.kind != 0) gvdb.SetModule();
+        if (m.kind != 0 || kfn) gvdb.SetModule();
         if (hits && m.kind == 0 && m.hitkernel[0]) {
             CUfunction fn;
             if (cuModuleGetFunction(&fn, omod, m.hitkernel) == CUDA_SUCCESS) {

@@ -31,7 +31,7 @@ def have_ref():
 
 
 def run_ref(preset, outdir, modes=None, size=None, frames=1, warmup=0, nodump=False, shadow=None, hits=True, timeout=1800,
-            xform=None, dbuf=False, raytrace=0, savevbx=None, config=None):
+            xform=None, dbuf=False, raytrace=0, savevbx=None, config=None, module=None):
     """Run the reference harness; returns its timing dict."""
     cmd = ["./ref_harness", preset, os.path.abspath(outdir)]
     if modes:
@@ -53,6 +53,8 @@ def run_ref(preset, outdir, modes=None, size=None, frames=1, warmup=0, nodump=Fa
         cmd += ["--savevbx", os.path.abspath(savevbx)]
     if config:
         cmd += ["--config", ",".join(str(int(c)) for c in config)]
+    if module:
+        cmd += ["--module", os.path.abspath(module)]
     r = subprocess.run(cmd, cwd=REF_DIR, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=timeout)
     if r.returncode != 0:
         raise RuntimeError(f"ref_harness failed ({r.returncode}): {r.stderr[-2000:]}")

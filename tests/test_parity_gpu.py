@@ -651,3 +651,25 @@ def test_live_reference_non_uniform_tree(pkg, torch_cuda, tmp_path, config):
     for m in refcmp.MODES2:
         assert res2[m]["tex"]["rgba_mismatch_pixels"] == 0, (m, res2[m]["tex"])
         assert res2[m]["tex"].get("hit_mismatch_pixels", 0) == 0
+
+
+# ------------------------------------------------------------------------------------------------ module-level drop-in
+@pytest.mark.skipif(not refcmp.have_ref(), reason="oracle/_ref not built")
+@pytest.mark.parametrize("preset", ["cfg1_small", "cfg4_small"])
+def test_module_dropin_inside_unmodified_reference(pkg, preset):
+    """SURVEY 8b level B: gvdbx_module.cubin (the reference's kernel names, signature and globals; the library's
+    traversal walking the reference's OWN pools) loaded by the UNMODIFIED reference through SetModule + RenderKernel.
+    Every native mode must produce the bytes of the reference's own kernels (goldens)."""
+    import os
+    import tempfile
+    cubin = os.path.join(os.path.dirname(pkg.lib_path()), "gvdbx_module.cubin")
+    assert os.path.exists(cubin), "build it with make -C gvdb-voxels_b200"
+    g, g2 = golden(preset), _modes2(preset)
+    d = tempfile.mkdtemp(prefix="refdump_")
+    modes = list(MODES) + ["tricubic", "emptyskip", "section2d", "section3d"]
+    refcmp.run_ref(preset, d, modes=modes, module=cubin, nodump=False, hits=False)
+    w, h = int(g["width"]), int(g["height"])
+    for m in modes:
+        img = np.fromfile(os.path.join(d, f"out_{m}.rgba"), dtype=np.uint8).reshape(h, w, 4)
+        ref = g[f"rgba_{m}"] if m in MODES else g2[f"rgba_{m}"]
+        assert np.array_equal(img, ref), (m, int((img != ref).any(axis=2).sum()))
