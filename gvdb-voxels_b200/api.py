@@ -21,7 +21,7 @@ VDBINFO_BYTES, SCNINFO_BYTES = 1232, 416
 EXPORTED_SYMBOLS = [
     "gvdbx_create", "gvdbx_destroy", "gvdbx_last_error", "gvdbx_set_option",
     "gvdbx_import_topology", "gvdbx_import_topology_host",
-    "gvdbx_import_atlas_array", "gvdbx_import_atlas_host", "gvdbx_import_atlas_device", "gvdbx_set_transfer",
+    "gvdbx_import_atlas_array", "gvdbx_import_atlas_host", "gvdbx_import_atlas_device", "gvdbx_import_color_array", "gvdbx_import_color_host", "gvdbx_clear_color", "gvdbx_set_transfer",
     "gvdbx_render", "gvdbx_render_tiles", "gvdbx_tiles_per_rank", "gvdbx_assemble_tiles",
     "gvdbx_render_debug", "gvdbx_raytrace", "gvdbx_read_buffer", "gvdbx_sync", "gvdbx_get_counters",
     "gvdbx_sample_points", "gvdbx_kernel_params", "gvdbx_update_apron", "gvdbx_export_atlas_host", "gvdbx_render_tiles_direct", "gvdbx_render_tiles_ring", "gvdbx_peer_alloc", "gvdbx_peer_free", "gvdbx_peer_open",
@@ -69,6 +69,9 @@ def lib():
     L.gvdbx_import_atlas_array.argtypes = [vp, i32, vp, i32, i32, i32]
     L.gvdbx_import_atlas_host.argtypes = [vp, i32, vp, i32, i32, i32]
     L.gvdbx_import_atlas_device.argtypes = [vp, i32, u64, i32, i32, i32]
+    L.gvdbx_import_color_array.argtypes = [vp, vp, i32]
+    L.gvdbx_import_color_host.argtypes = [vp, vp, i32, i32, i32, i32]
+    L.gvdbx_clear_color.argtypes = [vp]
     L.gvdbx_set_transfer.argtypes = [vp, vp]
     L.gvdbx_render.argtypes = [vp, vp, i32, i32, u64, i32, i32, i32, i32]
     L.gvdbx_render_tiles.argtypes = [vp, vp, i32, i32, u64, i32, i32, i32]
@@ -202,6 +205,17 @@ class Renderer:
     def import_atlas_device(self, texels_ptr, res_xyz, chan=0):
         """atlas from a device image [z][y][x] float32 (e.g. received by a broadcast)"""
         self._ck(self._L.gvdbx_import_atlas_device(self._h, chan, int(texels_ptr), *map(int, res_xyz)), "gvdbx_import_atlas_device")
+
+    def import_color_host(self, rgba8, linear=True):
+        """colour channel: uint8 [z][y][x][4] atlas image with the slot layout of channel 0; linear = AddChannel's filter"""
+        a = np.ascontiguousarray(rgba8, dtype=np.uint8)
+        assert a.ndim == 4 and a.shape[3] == 4
+        rz, ry, rx, _ = a.shape
+        self._ck(self._L.gvdbx_import_color_host(self._h, a.ctypes.data_as(C.c_void_p), rx, ry, rz, 1 if linear else 0),
+                 "gvdbx_import_color_host")
+
+    def clear_color(self):
+        self._ck(self._L.gvdbx_clear_color(self._h), "gvdbx_clear_color")
 
     def import_atlas_array(self, cuarray, res_xyz, chan=0):
         self._ck(self._L.gvdbx_import_atlas_array(self._h, chan, C.c_void_p(cuarray), *map(int, res_xyz)),

@@ -40,6 +40,9 @@ struct gvdbx_ctx {
     size_t              nslots = 0;
     int                 cull = 1;
     int                 ares[3] = {0, 0, 0};
+    // colour channel (VDBInfo::clr_chan): uchar4 atlas with the slot layout of channel 0
+    cudaTextureObject_t clr_tex = 0;
+    cudaArray_t         clr_own = nullptr;
     // transfer function
     float4* d_transfer = nullptr;
     std::vector<float4*> deep_lut;      // per lane (+1 for the creation stream): this frame's {rgb, exp(EXTINCT * alpha * DIRECTSTEP)}
@@ -123,6 +126,8 @@ extern "C" int gvdbx_destroy(gvdbx_t* h)
     gvdbx_lanes(h, 0);
     gx_free_topology(h);
     gx_free_atlas(h);
+    if (h->clr_tex) cudaDestroyTextureObject(h->clr_tex);
+    if (h->clr_own) cudaFreeArray(h->clr_own);
     if (h->d_transfer) cudaFree(h->d_transfer);
     for (float4* p : h->deep_lut) if (p) cudaFree(p);
     if (h->d_counters) cudaFree(h->d_counters);
@@ -196,7 +201,6 @@ extern "C" int gvdbx_import_topology(gvdbx_t* h, const void* vdbinfo)
     GxVDBInfo v;
     memcpy(&v, vdbinfo, sizeof v);
     if (v.top_lev < 0 || v.top_lev >= GX_MAXLEV) return gx_fail(h, GVDBX_E_ARG, "top_lev out of range (0..4)");
-    if (v.clr_chan != GX_CHAN_UNDEF) return gx_fail(h, GVDBX_E_UNSUPPORTED, "colour channel (clr_chan) is not supported on this path");
     if (v.atlas_apron != 1 || v.brick_res != GX_BRICK_DIM || v.res[0] != GX_BRICK_DIM - 2)
         return gx_fail(h, GVDBX_E_UNSUPPORTED, "only 8^3 bricks with apron 1 are supported (brick_res 10)");
     for (int l = 0; l <= v.top_lev; l++) {
@@ -429,6 +433,63 @@ extern "C" int gvdbx_import_atlas_device(gvdbx_t* h, int chan, uint64_t texels_d
     return GVDBX_OK;
 }
 
+// ------------------------------------------------------------------------------------------------ colour channel
+static void gx_free_color(gvdbx_t* h)
+{
+    if (h->clr_tex) cudaDestroyTextureObject(h->clr_tex);
+    if (h->clr_own) cudaFreeArray(h->clr_own);
+    h->clr_tex = 0; h->clr_own = nullptr;
+}
+static int gx_make_color_texture(gvdbx_t* h, cudaArray_t arr, int filter)
+{
+    // same descriptor as SetupAtlasAccess builds for a T_UCHAR4 channel (gvdb_volume_gvdb.cpp:753-783): integer reads,
+    // unnormalised coordinates, the channel's filter mode (F_POINT for a usable colour channel: CUDA rejects linear
+    // filtering of integer reads, for the reference's cuTexObjectCreate as for this call)
+    cudaResourceDesc rd;
+    memset(&rd, 0, sizeof rd);
+    rd.resType = cudaResourceTypeArray;
+    rd.res.array.array = arr;
+    cudaTextureDesc td;
+    memset(&td, 0, sizeof td);
+    td.filterMode = filter ? cudaFilterModeLinear : cudaFilterModePoint;
+    td.readMode = cudaReadModeElementType;
+    td.addressMode[0] = td.addressMode[1] = td.addressMode[2] = cudaAddressModeClamp;
+    td.normalizedCoords = 0;
+    GX_CUDA(h, cudaCreateTextureObject(&h->clr_tex, &rd, &td, nullptr));
+    return GVDBX_OK;
+}
+extern "C" int gvdbx_import_color_array(gvdbx_t* h, void* cuarray, int filter)
+{
+    if (!h || !cuarray) return GVDBX_E_ARG;
+    GX_CUDA(h, cudaSetDevice(h->device));
+    gx_free_color(h);
+    return gx_make_color_texture(h, (cudaArray_t)cuarray, filter);
+}
+extern "C" int gvdbx_import_color_host(gvdbx_t* h, const void* rgba8_texels, int rx, int ry, int rz, int filter)
+{
+    if (!h || !rgba8_texels || rx <= 0 || ry <= 0 || rz <= 0) return GVDBX_E_ARG;
+    GX_CUDA(h, cudaSetDevice(h->device));
+    gx_free_color(h);
+    cudaChannelFormatDesc fd = cudaCreateChannelDesc<uchar4>();
+    GX_CUDA(h, cudaMalloc3DArray(&h->clr_own, &fd, make_cudaExtent(rx, ry, rz), 0));
+    cudaMemcpy3DParms cp;
+    memset(&cp, 0, sizeof cp);
+    cp.srcPtr = make_cudaPitchedPtr((void*)rgba8_texels, size_t(rx) * 4, rx, ry);
+    cp.dstArray = h->clr_own;
+    cp.extent = make_cudaExtent(rx, ry, rz);
+    cp.kind = cudaMemcpyHostToDevice;
+    GX_CUDA(h, cudaMemcpy3DAsync(&cp, h->stream));
+    GX_CUDA(h, cudaStreamSynchronize(h->stream));
+    return gx_make_color_texture(h, h->clr_own, filter);
+}
+extern "C" int gvdbx_clear_color(gvdbx_t* h)
+{
+    if (!h) return GVDBX_E_ARG;
+    GX_CUDA(h, cudaSetDevice(h->device));
+    gx_free_color(h);
+    return GVDBX_OK;
+}
+
 extern "C" int gvdbx_set_transfer(gvdbx_t* h, const float* rgba_host)
 {
     if (!h || !rgba_host) return GVDBX_E_ARG;
@@ -525,6 +586,12 @@ static int gx_fill_params(gvdbx_t* h, const void* scninfo, int shade_mode, int c
     P.top_lev = v.top_lev; P.epsilon = v.epsilon; P.bmin = f3(v.bmin); P.bmax = f3(v.bmax);
     P.leaf = h->d_leaf;
     P.tex = h->tex; P.bricks = h->d_bricks;
+    // the colour channel is used exactly when the reference would: VDBInfo::clr_chan set (SetColorChannel)
+    P.clr_tex = 0;
+    if (v.clr_chan != GX_CHAN_UNDEF) {
+        if (!h->clr_tex) return gx_fail(h, GVDBX_E_STATE, "VDBInfo.clr_chan is set but no colour atlas was imported (gvdbx_import_color_*)");
+        P.clr_tex = h->clr_tex;
+    }
     P.range = h->cull ? h->d_leaf_range : nullptr;
     P.vmask = nullptr;
     if (mode == GX_MODE_VOXEL && h->use_vmask && v.res[0] == 8) {

@@ -95,6 +95,7 @@ struct GxParams {
     int         ref_nodewid[GX_MAXLEV], ref_childwid[GX_MAXLEV];
     // ---- atlas
     cudaTextureObject_t tex;             // caller's 3-D array, linear filter, unnormalised, clamp
+    cudaTextureObject_t clr_tex;         // colour channel (uchar4 atlas, VDBInfo::clr_chan); 0 = CHAN_UNDEF
     const float*        bricks;          // brick-major copy
     const GxRange*      range;           // value range per LEAF (same index as `leaf`); null = no culling
     const unsigned long long* vmask;     // SHADE_VOXEL: per leaf 8 x 64 bits, bit (z, y * 8 + x) = voxel value > THRESH; null = fetch
@@ -373,6 +374,14 @@ __device__ __forceinline__ float4 gx_transfer(const GxParams& P, float v)
     return __ldg(&P.transfer[int(min(1.0, max(0.0, (v - P.thresh.x) / (P.thresh.z - P.thresh.y))) * 16300.0f)]);
 }
 
+// colour channel fetch at atlas position p (truncated to the texel): getColorF, cuda_gvdb_raycast.cuh:206-209 +
+// make_float4(uchar4), cuda_math.cuh:221-224
+__device__ __forceinline__ float4 gx_color(const GxParams& P, float3 p)
+{
+    const uchar4 a = tex3D<uchar4>(P.clr_tex, (int)p.x, (int)p.y, (int)p.z);
+    return make_float4(float(a.x) / 255.0f, float(a.y) / 255.0f, float(a.z) / 255.0f, float(a.w) / 255.0f);
+}
+
 // depth-buffer clip: cuda_gvdb_raycast.cuh:343-370
 __device__ __forceinline__ float gx_depth_max(const GxParams& P, float3 rayDir, int px, int py)
 {
@@ -468,6 +477,7 @@ __device__ __forceinline__ void gx_brick_voxel(const GxParams& P, S& smp, int no
             h.norm.y = (fabsf(fromVoxelCenter.y) == maxCoordinate ? copysignf(1.0f, fromVoxelCenter.y) : 0.0f);
             h.norm.z = (fabsf(fromVoxelCenter.z) == maxCoordinate ? copysignf(1.0f, fromVoxelCenter.z) : 0.0f);
             h.t = dda.t.x; h.leaf = nodeid; h.vox = gx_i3(vmin);
+            if (P.clr_tex) h.clr = gx_color(P, gx_f3(dda.p) + o);
             return;
         }
         dda.next();
@@ -495,6 +505,7 @@ __device__ __forceinline__ void gx_brick_trilinear(const GxParams& P, S& smp, in
             h.hit = p + vmin;
             h.norm = gx_gradient(smp, p + o, cnt, false);
             h.t = t.x; h.leaf = nodeid; h.vox = gx_i3(gx_floor(h.hit));
+            if (P.clr_tex) h.clr = gx_color(P, p + o);
             return;
         }
         p += P.steps.x * dir;
@@ -525,6 +536,7 @@ __device__ __forceinline__ void gx_brick_levelset(const GxParams& P, S& smp, int
             if (h.hit.z != GX_NOHIT) {
                 h.norm = gx_gradient(smp, p + o, cnt, true);
                 h.t = t.x; h.leaf = nodeid; h.vox = gx_i3(gx_floor(h.hit));
+                if (P.clr_tex) h.clr = gx_color(P, p + o);
                 return;
             }
         }
@@ -567,7 +579,7 @@ __device__ __forceinline__ void gx_brick_deep(const GxParams& P, S& smp, int nod
             cnt.s_lut++;
             float4 val = gx_transfer(P, rawSample);
             val.w = exp(P.extinct.x * val.w * P.steps.x);
-            const float4 hclr = make_float4(1, 1, 1, 1);    // no colour channel on this path (clr_chan == CHAN_UNDEF)
+            const float4 hclr = P.clr_tex ? gx_color(P, p + o) : make_float4(1, 1, 1, 1);
             // reference: clr.x += val.x * clr.w * (1 - val.w) * ALBEDO * hclr.x with hclr a run-time select, so the
             // final add pairs with "* hclr.x" (= 1): every product is rounded on its own.  Pinned with _rn intrinsics.
             const float om = 1 - val.w;
@@ -642,7 +654,7 @@ __device__ __forceinline__ void gx_raycast(const GxParams& P, S& smp, float3 pos
                                            int px, int py)
 {
     if constexpr (GX_STATE_MACHINE && BATCH && (MODE == GX_MODE_TRILINEAR || MODE == GX_MODE_LEVELSET || MODE == GX_MODE_DEEP)) {
-        if (MODE != GX_MODE_DEEP || P.dbuf == nullptr) { gx_raycast_sm<MODE>(P, smp, pos, dir, h, cnt, px, py); return; }
+        if (MODE != GX_MODE_DEEP || (P.dbuf == nullptr && !P.clr_tex)) { gx_raycast_sm<MODE>(P, smp, pos, dir, h, cnt, px, py); return; }
     }
     GxStack st;
     int lev = P.top_lev;
@@ -687,7 +699,7 @@ __device__ __forceinline__ void gx_raycast(const GxParams& P, S& smp, float3 pos
                                                       else       gx_brick_trilinear(P, smp, c, dda.t, pos, dir, h, cnt); }
                 else if constexpr (MODE == GX_MODE_LEVELSET)  { if (BATCH) gx2_brick_levelset(P, smp, c, dda.t, pos, dir, h, cnt);
                                                       else       gx_brick_levelset(P, smp, c, dda.t, pos, dir, h, cnt); }
-                else if constexpr (MODE == GX_MODE_DEEP)      { if (BATCH) gx2_brick_deep(P, smp, c, dda.t, pos, dir, h, cnt, tDepth);
+                else if constexpr (MODE == GX_MODE_DEEP)      { if (BATCH && !P.clr_tex) gx2_brick_deep(P, smp, c, dda.t, pos, dir, h, cnt, tDepth);   // per-sample colour: literal marcher
                                                       else       gx_brick_deep(P, smp, c, dda.t, pos, dir, h, cnt, tDepth); }
                 else if constexpr (MODE == GX_MODE_TRICUBIC)  gx_brick_tricubic(P, smp, c, dda.t, pos, dir, h, cnt);
                 else if constexpr (MODE == GX_MODE_EMPTYSKIP) h.hit = pos + dda.t.x * dir;       // rayEmptySkipBrick, cuda_gvdb_raycast.cuh:425-428

@@ -145,6 +145,7 @@ __device__ __forceinline__ void gx_brick_tricubic(const GxParams& P, S& smp, int
             h.hit = p + vmin;
             h.norm = gx_gradient_tricubic(smp, p, o, cnt);
             h.t = t.x; h.leaf = nodeid; h.vox = gx_i3(gx_floor(h.hit));
+            if (P.clr_tex) h.clr = gx_color(P, p + o);
             return;
         }
         p += P.steps.x * dir;

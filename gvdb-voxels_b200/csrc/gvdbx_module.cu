@@ -44,6 +44,7 @@ static __device__ __forceinline__ void gx_module_params(GxParams& P, const GxVDB
     P.top_lev = gvdb->top_lev; P.epsilon = gvdb->epsilon; P.bmin = f3(gvdb->bmin); P.bmax = f3(gvdb->bmax);
     P.leaf = nullptr;
     P.tex = (cudaTextureObject_t)gvdb->volIn[chan];
+    P.clr_tex = gvdb->clr_chan != GX_CHAN_UNDEF ? (cudaTextureObject_t)gvdb->volIn[gvdb->clr_chan] : 0;
     P.bricks = nullptr; P.range = nullptr; P.vmask = nullptr;
     P.out = outBuf; P.dbg = nullptr; P.counters = nullptr;
     P.out_stride = s.width; P.x0 = 0; P.y0 = 0; P.x1 = s.width; P.y1 = s.height;

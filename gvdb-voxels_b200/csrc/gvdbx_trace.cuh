@@ -73,6 +73,7 @@ __device__ __forceinline__ void gx2_brick_trilinear(const GxParams& P, S& smp, i
                 h.hit = p + vmin;
                 h.norm = gx_gradient(smp, p + o, cnt, false);
                 h.t = t.x; h.leaf = nodeid; h.vox = gx_i3(gx_floor(h.hit));
+                if (P.clr_tex) h.clr = gx_color(P, p + o);
             }
             return;
         }
@@ -116,6 +117,7 @@ __device__ __forceinline__ void gx2_brick_levelset(const GxParams& P, S& smp, in
                 h.hit = p + vmin;       // always != NOHIT for finite coordinates: the reference accepts it and returns
                 h.norm = gx_gradient(smp, p + o, cnt, true);
                 h.t = t.x; h.leaf = nodeid; h.vox = gx_i3(gx_floor(h.hit));
+                if (P.clr_tex) h.clr = gx_color(P, p + o);
             }
             return;
         }
@@ -359,6 +361,7 @@ __device__ __forceinline__ bool gx3_round(const GxParams& P, S& smp, float3 pos,
                 h.hit = p + make_float3(float(L.px), float(L.py), float(L.pz));
                 h.norm = gx_gradient(smp, p + o, cnt, ls);
                 h.t = M.tx; h.leaf = M.node; h.vox = gx_i3(gx_floor(h.hit));
+                if (P.clr_tex) h.clr = gx_color(P, p + o);
             }
             return true;
         }

@@ -112,6 +112,17 @@ int  gvdbx_update_apron(gvdbx_t* h, int chan, float boundval);
 /* Read the atlas array back into a host image, x fastest (Allocator::AtlasRetrieveSlice for every slice). */
 int  gvdbx_export_atlas_host(gvdbx_t* h, int chan, float* texels, int res_x, int res_y, int res_z);
 
+/* Colour channel (VolumeGVDB::SetColorChannel, src/gvdb_volume_gvdb.cpp:686-690; getColorF, kernels/cuda_gvdb_raycast.cuh:
+ * 200-209): a uchar4 atlas with the brick-slot layout of channel 0, fetched at the hit voxel (surface modes) / at every
+ * sample (deep).  It is used exactly when the imported VDBInfo has clr_chan set; rendering such a volume without a colour
+ * atlas is GVDBX_E_STATE.  `cuarray` = the reference's 3-D CUarray of that channel (sampled in place); `filter` = the
+ * channel's filter mode as given to AddChannel: 0 = F_POINT (gPointFusion).  1 = F_LINEAR, AddChannel's default, is
+ * passed on to CUDA unchanged and rejected there for an integer-read texture (cudaErrorInvalidFilterSetting ->
+ * GVDBX_E_CUDA) — the reference's own cuTexObjectCreate fails the same way for such a channel. */
+int  gvdbx_import_color_array(gvdbx_t* h, void* cuarray, int filter);
+int  gvdbx_import_color_host(gvdbx_t* h, const void* rgba8_texels, int res_x, int res_y, int res_z, int filter);
+int  gvdbx_clear_color(gvdbx_t* h);
+
 /* Transfer function: 16384 float4 (Scene::getTransferFunc()).  Alternatively leave unset and pass a device pointer in
  * ScnInfo.transfer exactly like the reference does. */
 int  gvdbx_set_transfer(gvdbx_t* h, const float* rgba_host);

@@ -67,7 +67,7 @@ int main(int argc, char** argv)
     int have_xf = 0, use_dbuf = 0, nrays = 0;
     std::string savevbx = "";
     int cfg[5] = {3, 3, 3, 3, 3};                  // Configure(q4..q0): log2 dims from the top level down to the brick
-    int lightdump = 0;
+    int lightdump = 0, use_color = 0;               // --color: second channel T_UCHAR4 + SetColorChannel (gFluidSurface / gSprayDeposit usage)
     std::string usermodule = "";                   // --module: render the native modes with the kernels of this cubin (RenderKernel)
     for (int i = 3; i < argc; i++) {
         std::string a = argv[i];
@@ -77,6 +77,7 @@ int main(int argc, char** argv)
         else if (a == "--warmup" && i + 1 < argc) warmup = atoi(argv[++i]);
         else if (a == "--nodump") nodump = 1;
         else if (a == "--lightdump") lightdump = 1;
+        else if (a == "--color") use_color = 1;
         else if (a == "--module" && i + 1 < argc) { usermodule = argv[++i]; hits = 0; }        // images + ScnInfo + VDBInfo only (no pools / atlas: large volumes)
         else if (a == "--shadow" && i + 1 < argc) shadow = atoi(argv[++i]);
         else if (a == "--hits" && i + 1 < argc) hits = atoi(argv[++i]);
@@ -119,6 +120,8 @@ int main(int argc, char** argv)
         gvdb.SetChannelDefault(cxy, cxy, 1);
     }
     gvdb.AddChannel(0, T_FLOAT, 1);
+    if (use_color) gvdb.AddChannel(1, T_UCHAR4, 1, F_POINT);    // as gPointFusion does (main_point_fusion.cpp:430); AddChannel's default
+                                                                // F_LINEAR is rejected by CUDA for an integer-read texture
     double t_cfg = now_s() - t0;
     t0 = now_s();
     for (int n = 0; n < S.nbricks; n++)
@@ -151,6 +154,23 @@ int main(int argc, char** argv)
     gvdb.mPool->AtlasCommitFromCPU(0, (uchar*)atlas.data());
     gvdb.UpdateApron(0, 0.0f);
     cuCtxSynchronize();
+    // --color: a colour per interior voxel from its index-space position, same slot layout as channel 0
+    std::vector<unsigned char> color;
+    if (use_color) {
+        color.assign(atexels * 4, 0);
+        for (int n = 0; n < nleaf; n++) {
+            Node* nd = gvdb.getNode(0, 0, n);
+            for (int k = 0; k < 8; k++) for (int j = 0; j < 8; j++) for (int i = 0; i < 8; i++) {
+                const int wx = nd->mPos.x + i, wy = nd->mPos.y + j, wz = nd->mPos.z + k;
+                unsigned char* c = &color[4 * (((size_t)(nd->mValue.z + k) * ares.y + (nd->mValue.y + j)) * ares.x + nd->mValue.x + i)];
+                c[0] = (unsigned char)(40 + (wx * 37 + wy * 11) % 216); c[1] = (unsigned char)(40 + (wy * 29 + wz * 7) % 216);
+                c[2] = (unsigned char)(40 + (wz * 41 + wx * 3) % 216);  c[3] = (unsigned char)(128 + (wx + wy + wz) % 128);
+            }
+        }
+        gvdb.mPool->AtlasCommitFromCPU(1, color.data());
+        gvdb.SetColorChannel(1);
+        cuCtxSynchronize();
+    }
 
     // ---- scene
     Scene* scn = gvdb.getScene();
@@ -289,6 +309,7 @@ int main(int argc, char** argv)
             gvdb.mPool->AtlasRetrieveSlice(0, z, 0, 0, (uchar*)(back.data() + (size_t)z * ares.x * ares.y));
         dump(outdir + "/atlas.bin", back.data(), atexels * sizeof(float));
         dump(outdir + "/transfer.bin", scn->getTransferFunc(), 16384 * 16);
+        if (use_color) dump(outdir + "/color.bin", color.data(), color.size());
         dump(outdir + "/brick_pos.bin", S.brick_pos, sizeof(int32_t) * 3 * (size_t)S.nbricks);
     }
 

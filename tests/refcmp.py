@@ -31,7 +31,7 @@ def have_ref():
 
 
 def run_ref(preset, outdir, modes=None, size=None, frames=1, warmup=0, nodump=False, shadow=None, hits=True, timeout=1800,
-            xform=None, dbuf=False, raytrace=0, savevbx=None, config=None, module=None):
+            xform=None, dbuf=False, raytrace=0, savevbx=None, config=None, module=None, color=False):
     """Run the reference harness; returns its timing dict."""
     cmd = ["./ref_harness", preset, os.path.abspath(outdir)]
     if modes:
@@ -55,6 +55,8 @@ def run_ref(preset, outdir, modes=None, size=None, frames=1, warmup=0, nodump=Fa
         cmd += ["--config", ",".join(str(int(c)) for c in config)]
     if module:
         cmd += ["--module", os.path.abspath(module)]
+    if color:
+        cmd.append("--color")
     r = subprocess.run(cmd, cwd=REF_DIR, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=timeout)
     if r.returncode != 0:
         raise RuntimeError(f"ref_harness failed ({r.returncode}): {r.stderr[-2000:]}")
@@ -94,6 +96,9 @@ def load_dump(d):
             hp = os.path.join(d, f"hit_{m}.f32")
             if os.path.exists(hp):
                 out["hit"][m] = np.fromfile(hp, dtype=np.float32).reshape(h, w, 8)
+    q = os.path.join(d, "color.bin")
+    if os.path.exists(q):
+        out["color"] = np.fromfile(q, dtype=np.uint8).reshape(rz, ry, rx, 4)
     for name in ("dbuf", "rays_in", "rays_out"):
         q = os.path.join(d, name + ".bin")
         if os.path.exists(q):
@@ -108,6 +113,8 @@ def make_renderer(dump, pkg, device=0):
     r = pkg.Renderer(device)
     r.import_topology_host(dump["vdbinfo"], dump["pool0"], dump["pool1"])
     r.import_atlas_host(dump["atlas"])
+    if "color" in dump:
+        r.import_color_host(dump["color"], linear=False)       # the harness creates the channel with F_POINT
     r.set_transfer(dump["transfer"])
     return r
 

@@ -673,3 +673,40 @@ def test_module_dropin_inside_unmodified_reference(pkg, preset):
         img = np.fromfile(os.path.join(d, f"out_{m}.rgba"), dtype=np.uint8).reshape(h, w, 4)
         ref = g[f"rgba_{m}"] if m in MODES else g2[f"rgba_{m}"]
         assert np.array_equal(img, ref), (m, int((img != ref).any(axis=2).sum()))
+
+
+# ------------------------------------------------------------------------------------------------ colour channel
+@pytest.mark.skipif(not refcmp.have_ref(), reason="oracle/_ref not built")
+def test_live_reference_color_channel(pkg, torch_cuda, tmp_path):
+    """Second channel T_UCHAR4 (F_POINT, as gPointFusion creates it) + SetColorChannel: the hit voxel's colour tints the
+    surface modes, every deep sample is multiplied by its voxel's colour.  The unmodified reference renders such a
+    volume now; with its colour atlas imported every mode must match bit for bit, and differ from the uncoloured image."""
+    d = str(tmp_path / "dump")
+    refcmp.run_ref("cfg4_small", d, modes=list(MODES) + ["tricubic"], size=(240, 160), color=True)
+    dump = refcmp.load_dump(d)
+    assert "color" in dump and np.frombuffer(dump["vdbinfo"], np.uint8)[685] == 1          # VDBInfo.clr_chan
+    res = refcmp.compare(dump, pkg, list(MODES), verbose=False)
+    for m in MODES:
+        assert res[m]["tex"]["rgba_mismatch_pixels"] == 0, (m, res[m]["tex"])          # the native kernels' bytes
+        assert res[m]["tex"].get("hit_mismatch_pixels", 0) == 0
+        # raw (float) deep colour comes from the oracle WRAPPER kernel, a different compilation context than the native
+        # gvdbRayDeep whose 8-bit output is matched exactly above: with a run-time colour factor its last product / add
+        # may contract differently, so the float comparison is a tolerance here
+        assert res[m]["tex"].get("raw_clr_max_abs", 0.0) < 1e-5, (m, res[m]["tex"])
+        assert res[m]["linear"]["rgba_over1_pixels"] <= 2e-3 * res[m]["linear"]["pixels"]
+    res2 = refcmp.compare2(dump, pkg, ["tricubic"], verbose=False)
+    assert res2["tricubic"]["tex"]["rgba_mismatch_pixels"] == 0
+    # the colour really changes the picture, and a volume that announces a colour channel cannot be rendered without it
+    d0 = str(tmp_path / "plain")
+    refcmp.run_ref("cfg4_small", d0, modes=["trilinear", "deep"], size=(240, 160), hits=False)
+    plain = refcmp.load_dump(d0)
+    assert not np.array_equal(plain["rgba"]["trilinear"], dump["rgba"]["trilinear"])
+    assert not np.array_equal(plain["rgba"]["deep"], dump["rgba"]["deep"])
+    r = pkg.Renderer(0)
+    r.import_topology_host(dump["vdbinfo"], dump["pool0"], dump["pool1"])
+    r.import_atlas_host(dump["atlas"])
+    r.set_transfer(dump["transfer"])
+    out = torch_cuda.zeros((160, 240, 4), dtype=torch_cuda.uint8, device="cuda")
+    with pytest.raises(pkg.GvdbxError):
+        r.render(dump["scn"]["trilinear"], 4, out.data_ptr())
+    r.close()
