@@ -414,7 +414,10 @@ __device__ __forceinline__ float3 gx_gradient(const S& smp, float3 p, GxCount& c
 }
 
 // ------------------------------------------------------------------------------------------------ brick functions
-struct GxHit { float3 hit, norm; float4 clr; float t; int leaf; int3 vox; };
+// cpos = atlas position of a surface hit (p + o exactly as the brick function holds it): the colour channel is fetched
+// there AFTER the ray cast returns (gx_hit_color), so that the constant surface colour (1,1,1,1) does not have to live in
+// registers through the whole traversal
+struct GxHit { float3 hit, norm; float4 clr; float t; int leaf; int3 vox; float3 cpos; };
 
 // SHADE_VOXEL: per-voxel DDA inside the brick                           cuda_gvdb_raycast.cuh:227-265
 template <class S>
@@ -477,7 +480,7 @@ __device__ __forceinline__ void gx_brick_voxel(const GxParams& P, S& smp, int no
             h.norm.y = (fabsf(fromVoxelCenter.y) == maxCoordinate ? copysignf(1.0f, fromVoxelCenter.y) : 0.0f);
             h.norm.z = (fabsf(fromVoxelCenter.z) == maxCoordinate ? copysignf(1.0f, fromVoxelCenter.z) : 0.0f);
             h.t = dda.t.x; h.leaf = nodeid; h.vox = gx_i3(vmin);
-            if (P.clr_tex) h.clr = gx_color(P, gx_f3(dda.p) + o);
+            h.cpos = gx_f3(dda.p) + o;
             return;
         }
         dda.next();
@@ -505,7 +508,7 @@ __device__ __forceinline__ void gx_brick_trilinear(const GxParams& P, S& smp, in
             h.hit = p + vmin;
             h.norm = gx_gradient(smp, p + o, cnt, false);
             h.t = t.x; h.leaf = nodeid; h.vox = gx_i3(gx_floor(h.hit));
-            if (P.clr_tex) h.clr = gx_color(P, p + o);
+            h.cpos = p + o;
             return;
         }
         p += P.steps.x * dir;
@@ -536,7 +539,7 @@ __device__ __forceinline__ void gx_brick_levelset(const GxParams& P, S& smp, int
             if (h.hit.z != GX_NOHIT) {
                 h.norm = gx_gradient(smp, p + o, cnt, true);
                 h.t = t.x; h.leaf = nodeid; h.vox = gx_i3(gx_floor(h.hit));
-                if (P.clr_tex) h.clr = gx_color(P, p + o);
+                h.cpos = p + o;
                 return;
             }
         }
@@ -741,6 +744,14 @@ __device__ __forceinline__ void gx_raycast(const GxParams& P, S& smp, float3 pos
     }
 }
 
+// hclr of the surface brick functions (`if (gvdb->clr_chan != CHAN_UNDEF) hclr = getColorF(gvdb, gvdb->clr_chan, p + o)`,
+// cuda_gvdb_raycast.cuh:259, :294, :333, :403), applied after the ray cast: a hit ends the ray, so nothing reads hclr in
+// between except rayCast's `clr.w <= 0` test, which can only confirm the return the hit causes anyway
+__device__ __forceinline__ void gx_hit_color(const GxParams& P, GxHit& h)
+{
+    if (P.clr_tex && h.hit.z != GX_NOHIT) h.clr = gx_color(P, h.cpos);
+}
+
 // ------------------------------------------------------------------------------------------------ shading
 // Phong + optional shadow ray with the same brick function              cuda_gvdb_module.cu:38-57
 template <int MODE, bool BATCH, class S>
@@ -816,8 +827,17 @@ __device__ __forceinline__ float4 gx_shade_pixel(const GxParams& P, S& smp, int 
         h.clr = make_float4(1, 1, 1, 1);
         h.hit = (MODE == GX_MODE_LEVELSET) ? make_float3(0, 0, GX_NOHIT) : make_float3(GX_NOHIT, GX_NOHIT, GX_NOHIT);
         gx_raycast<MODE, BATCH>(P, smp, rpos, rdir, h, cnt, x, y);
+        // colour channel: the hit voxel's colour is fetched now but kept as its four BYTES (one register) while the shadow
+        // ray runs; performPhongShading's sclr.rgb * (diff + amb) is then (diff + amb) — what the call returns for the
+        // constant colour 1 — times the colour: the same single rounding per channel
+        const bool tint = P.clr_tex && h.hit.z != GX_NOHIT;
+        uchar4 cb = make_uchar4(255, 255, 255, 255);
+        if (tint) cb = tex3D<uchar4>(P.clr_tex, (int)h.cpos.x, (int)h.cpos.y, (int)h.cpos.z);
         // the tricubic kernel shades its shadow ray with the trilinear brick function (cuda_gvdb_module.cu:136)
         clr = gx_phong<(MODE == GX_MODE_TRICUBIC ? GX_MODE_TRILINEAR : MODE), BATCH>(P, smp, h.hit, h.norm, h.clr, cnt, x, y);
+        if (tint) {
+            clr.x = (float(cb.x) / 255.0f) * clr.x; clr.y = (float(cb.y) / 255.0f) * clr.y; clr.z = (float(cb.z) / 255.0f) * clr.z;
+        }
     }
     return clr;
     }

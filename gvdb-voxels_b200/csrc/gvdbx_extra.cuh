@@ -145,7 +145,7 @@ __device__ __forceinline__ void gx_brick_tricubic(const GxParams& P, S& smp, int
             h.hit = p + vmin;
             h.norm = gx_gradient_tricubic(smp, p, o, cnt);
             h.t = t.x; h.leaf = nodeid; h.vox = gx_i3(gx_floor(h.hit));
-            if (P.clr_tex) h.clr = gx_color(P, p + o);
+            h.cpos = p + o;
             return;
         }
         p += P.steps.x * dir;
@@ -269,6 +269,7 @@ __device__ __forceinline__ float4 gx_pixel_section3d(const GxParams& P, S& smp, 
     h.hit = make_float3(GX_NOHIT, GX_NOHIT, GX_NOHIT);
     h.clr = make_float4(1, 1, 1, 1);
     gx_raycast<GX_MODE_TRILINEAR, BATCH>(P, smp, wpos, rdir, h, cnt, x, y);
+    gx_hit_color(P, h);
     if (h.hit.z != GX_NOHIT) {
         float3 lightdir = gx_normalize(P.light_pos - h.hit);
         float ds = (t > P.thresh.x) ? 1 : 0.8 * fmaxf(0.0f, gx_dot(h.norm, lightdir));

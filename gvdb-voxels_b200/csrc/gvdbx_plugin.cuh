@@ -33,6 +33,8 @@ __device__ __forceinline__ void gvdbx_ray_cast(const GxParams& P, float3 pos, fl
     GxHit h;
     h.hit = hit; h.norm = norm; h.clr = clr;
     h.t = 0; h.leaf = -1; h.vox = make_int3(0, 0, 0);
+    h.cpos = make_float3(0, 0, 0);
     gx_raycast<MODE, true>(P, smp, pos, dir, h, cnt, px, py);
+    if (MODE == GX_MODE_VOXEL || MODE == GX_MODE_TRILINEAR || MODE == GX_MODE_LEVELSET || MODE == GX_MODE_TRICUBIC) gx_hit_color(P, h);
     hit = h.hit; norm = h.norm; clr = h.clr;
 }

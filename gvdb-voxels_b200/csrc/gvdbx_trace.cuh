@@ -73,7 +73,7 @@ __device__ __forceinline__ void gx2_brick_trilinear(const GxParams& P, S& smp, i
                 h.hit = p + vmin;
                 h.norm = gx_gradient(smp, p + o, cnt, false);
                 h.t = t.x; h.leaf = nodeid; h.vox = gx_i3(gx_floor(h.hit));
-                if (P.clr_tex) h.clr = gx_color(P, p + o);
+                h.cpos = p + o;
             }
             return;
         }
@@ -117,7 +117,7 @@ __device__ __forceinline__ void gx2_brick_levelset(const GxParams& P, S& smp, in
                 h.hit = p + vmin;       // always != NOHIT for finite coordinates: the reference accepts it and returns
                 h.norm = gx_gradient(smp, p + o, cnt, true);
                 h.t = t.x; h.leaf = nodeid; h.vox = gx_i3(gx_floor(h.hit));
-                if (P.clr_tex) h.clr = gx_color(P, p + o);
+                h.cpos = p + o;
             }
             return;
         }
@@ -361,7 +361,7 @@ __device__ __forceinline__ bool gx3_round(const GxParams& P, S& smp, float3 pos,
                 h.hit = p + make_float3(float(L.px), float(L.py), float(L.pz));
                 h.norm = gx_gradient(smp, p + o, cnt, ls);
                 h.t = M.tx; h.leaf = M.node; h.vox = gx_i3(gx_floor(h.hit));
-                if (P.clr_tex) h.clr = gx_color(P, p + o);
+                h.cpos = p + o;
             }
             return true;
         }
@@ -609,6 +609,7 @@ __device__ __forceinline__ float4 gx2_trace_pixel(const GxParams& P, S& smp, flo
                                  P.backclr.z + a * (h.clr.z - P.backclr.z), 1.0 - h.clr.w);
             done = true;
         } else if (phase == 0) {                                 // performPhongShading, cuda_gvdb_module.cu:38-57
+            gx_hit_color(P, h);
             prim = h;
             if (h.hit.z == GX_NOHIT) { result = P.backclr; done = true; }
             else {
