@@ -521,12 +521,12 @@ def main():
         nthreads = oracle.lib().ora_max_threads()
         # bounded sample of the same workload: whole frames of the orbit (1 spp), sized from one timed frame to ~15 s of CPU work
         t0 = time.perf_counter()
-        oracle.render(vol, scns[0], shade)
+        oracle.render(vol, scns[0], shade, deep_shadow=a.deep_shadow)
         dt1 = time.perf_counter() - t0
         nfr = int(max(1, min(64, round(15.0 / max(dt1, 1e-3)))))
         t0 = time.perf_counter()
         for j in range(nfr):
-            oracle.render(vol, scns[j % len(scns)], shade)
+            oracle.render(vol, scns[j % len(scns)], shade, deep_shadow=a.deep_shadow)
         dt = time.perf_counter() - t0
         cpu = {"value": nfr * w * h / dt / 1e6, "unit": "Mrays/s", "cores": nthreads, "kind": "port",
                "sample": f"{nfr} full frames of the orbit ({nfr * w * h} primary rays, 1 ray per pixel), CPU restatement oracle/gvdb_oracle.c, "

@@ -7,6 +7,12 @@
 #include "gvdb_oracle.h"
 #include "scenes.h"
 
+/* the remaining values of the reference's SHADE_* enum (src/gvdb_types.h:105-112) */
+#define ORA_SHADE_SECTION2D 1
+#define ORA_SHADE_SECTION3D 2
+#define ORA_SHADE_EMPTYSKIP 3
+#define ORA_SHADE_TRICUBIC  5
+
 #include <math.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -700,6 +706,98 @@ static void brick_deep(const rc_ctx* c, int nodeid, f3 t, f3 pos, f3 dir, rc_out
     k->x = fminf(k->x, 1.f); k->y = fminf(k->y, 1.f); k->z = fminf(k->z, 1.f); k->w = fmaxf(k->w, 0.f);
 }
 
+/* getTricubic, kernels/cuda_gvdb_raycast.cuh:32-96: 27 fetches at texel corners, quadratic B-spline weights */
+static float tricubic(const rc_ctx* c, f3 p, f3 offs)
+{
+    f3 q = sub3(flr3(add3(p, offs)), F3(1, 1, 1));
+    f3 fr = sub3(p, flr3(p));
+    f3 tb = F3(fr.x * 0.5f + 0.25f, fr.y * 0.5f + 0.25f, fr.z * 0.5f + 0.25f);
+    f3 ta = F3(1.0f - tb.x, 1.0f - tb.y, 1.0f - tb.z);
+    f3 ta2 = mul3(ta, ta), tb2 = mul3(tb, tb), tab = scl3(mul3(ta, tb), 2.0f);
+    float plane[3][3];
+    for (int k = 0; k < 3; k++) for (int j = 0; j < 3; j++) {
+        float t0 = fetch(c, q.x, q.y + (float)j, q.z + (float)k), t1 = fetch(c, q.x + 1, q.y + (float)j, q.z + (float)k),
+              t2 = fetch(c, q.x + 2, q.y + (float)j, q.z + (float)k);
+        plane[k][j] = t0 * ta2.x + t1 * tab.x + t2 * tb2.x;
+    }
+    float col[3];
+    for (int k = 0; k < 3; k++) col[k] = plane[k][0] * ta2.y + plane[k][1] * tab.y + plane[k][2] * tb2.y;
+    return col[0] * ta2.z + col[1] * tab.z + col[2] * tb2.z;
+}
+/* getGradientTricubic, :159-169 */
+static f3 gradient_tricubic(const rc_ctx* c, f3 p, f3 offs)
+{
+    const float vs = 0.5f;
+    f3 g;
+    g.x = (tricubic(c, add3(p, F3(-vs, 0, 0)), offs) - tricubic(c, add3(p, F3(vs, 0, 0)), offs)) / (2 * vs);
+    g.y = (tricubic(c, add3(p, F3(0, -vs, 0)), offs) - tricubic(c, add3(p, F3(0, vs, 0)), offs)) / (2 * vs);
+    g.z = (tricubic(c, add3(p, F3(0, 0, -vs)), offs) - tricubic(c, add3(p, F3(0, 0, vs)), offs)) / (2 * vs);
+    return nrm3(g);
+}
+/* raySurfaceTricubicBrick, :316-339 */
+static void brick_tricubic(const rc_ctx* c, int nodeid, f3 t, f3 pos, f3 dir, rc_out* o)
+{
+    const ora_node* node = get_node(c, 0, nodeid);
+    f3 vmin = F3((float)node->mPos.x, (float)node->mPos.y, (float)node->mPos.z);
+    f3 a = F3((float)node->mValue.x, (float)node->mValue.y, (float)node->mValue.z);
+    float res0 = (float)c->g->res[0];
+    f3 p = sub3(add3(pos, scl3(dir, t.x)), vmin);
+    for (int it = 0; it < 256 && p.x >= 0 && p.y >= 0 && p.z >= 0 && p.x < res0 && p.y < res0 && p.z < res0; it++) {
+        float vz = tricubic(c, p, a);
+        if (vz >= c->s->thresh.x) {
+            float vx = tricubic(c, sub3(p, scl3(dir, c->s->steps.z)), a);
+            float vy = (vz - c->s->thresh.x) / (vz - vx);
+            p = add3(p, scl3(dir, -vy * c->s->steps.z));
+            o->hit = add3(p, vmin);
+            o->norm = gradient_tricubic(c, p, a);
+            return;
+        }
+        p = add3(p, scl3(dir, c->s->steps.x));
+        t.x += c->s->steps.x;
+    }
+}
+/* rayShadowBrick, :445-463: opacity accumulates in clr.w; the attenuation is evaluated in double like the literals make it */
+static void brick_shadow(const rc_ctx* c, int nodeid, f3 t, f3 pos, f3 dir, rc_out* o)
+{
+    const ora_node* node = get_node(c, 0, nodeid);
+    f3 vmin = F3((float)node->mPos.x, (float)node->mPos.y, (float)node->mPos.z);
+    t.x += c->g->epsilon;
+    t.y -= c->g->epsilon;
+    f3 a = F3((float)node->mValue.x, (float)node->mValue.y, (float)node->mValue.z);
+    f3 p = sub3(add3(pos, scl3(dir, t.x)), vmin);
+    f3 pt = scl3(dir, c->s->steps.x);
+    float res0 = (float)c->g->res[0];
+    for (; o->clr.w < 1 && p.x >= 0 && p.y >= 0 && p.z >= 0 && p.x < res0 && p.y < res0 && p.z < res0;) {
+        f4 T = transfer(c, fetch(c, p.x + a.x, p.y + a.y, p.z + a.z));
+        float val = (float)exp((double)(c->s->extinct.x * T.w * c->s->steps.y) / (1.0 + (double)t.x * 0.4));
+        o->clr.w = (float)(1.0 - (1.0 - (double)o->clr.w) * (double)val);
+        p = add3(p, pt);
+        t.x += c->s->steps.y;
+    }
+}
+/* getNode(lev, start, pos) / getNodeAtPoint, kernels/cuda_gvdb_nodes.cuh:199-253: leaf index at an index-space point or -1 */
+static int node_at_point(const rc_ctx* c, f3 pos)
+{
+    const ora_vdbinfo* g = c->g;
+    int lev = g->top_lev, id = 0;
+    const ora_node* node = get_node(c, lev, 0);
+    while (lev > 0) {
+        f3 vmin = F3((float)node->mPos.x, (float)node->mPos.y, (float)node->mPos.z);
+        f3 vmax = add3(vmin, F3((float)g->noderange[lev].x, (float)g->noderange[lev].y, (float)g->noderange[lev].z));
+        if (pos.x < vmin.x || pos.y < vmin.y || pos.z < vmin.z || pos.x >= vmax.x || pos.y >= vmax.y || pos.z >= vmax.z) return -1;
+        f3 q = div3(sub3(pos, vmin), g->vdel[lev]);
+        int px = (int)q.x, py = (int)q.y, pz = (int)q.z;
+        int b = (((pz << g->dim[lev]) + py) << g->dim[lev]) + px;
+        lev--;
+        id = get_child(c, node, b);
+        if (id == -1) return -1;
+        node = get_node(c, lev, id);
+    }
+    return id;
+}
+
+#define ORA_BRICK_SHADOW 100    /* brick function selector for rayShadowBrick (not a shade mode) */
+
 /* rayCast, kernels/cuda_gvdb_raycast.cuh:543-611 */
 static void ray_cast(const rc_ctx* c, int shade, f3 pos, f3 dir, rc_out* o)
 {
@@ -730,6 +828,9 @@ static void ray_cast(const rc_ctx* c, int shade, f3 pos, f3 dir, rc_out* o)
                 case SCN_SHADE_VOXEL:     brick_voxel(c, child, d.t, pos, dir, o); break;
                 case SCN_SHADE_TRILINEAR: brick_trilinear(c, child, d.t, pos, dir, o); break;
                 case SCN_SHADE_LEVELSET:  brick_levelset(c, child, d.t, pos, dir, o); break;
+                case ORA_SHADE_TRICUBIC:  brick_tricubic(c, child, d.t, pos, dir, o); break;
+                case ORA_SHADE_EMPTYSKIP: o->hit = add3(pos, scl3(dir, d.t.x)); break;          /* rayEmptySkipBrick, :425-428 */
+                case ORA_BRICK_SHADOW:    brick_shadow(c, child, d.t, pos, dir, o); break;
                 default:                  brick_deep(c, child, d.t, pos, dir, o); break;
                 }
                 if (o->clr.w <= 0) { o->clr.w = 0; return; }
@@ -775,17 +876,114 @@ static f4 phong(const rc_ctx* c, int shade, f3 shit, f3 snorm, f4 sclr)
     return r;
 }
 
-/* gvdbRayDeep / gvdbRaySurfaceVoxel / gvdbRaySurfaceTrilinear / gvdbRayLevelSet, kernels/cuda_gvdb_module.cu:60-181 */
-int ora_render(const ora_volume* v, const void* scninfo, int shade, int y0, int y1, uint8_t* out, float* hit_norm, int threads)
+/* one camera ray through pixel (x, y) at sub-pixel offset (ox, oy), shaded to the float colour the kernels pack:
+ * gvdbRayDeep / gvdbRaySurfaceVoxel / ...Trilinear / ...Tricubic / gvdbRayLevelSet / gvdbRayEmptySkip / gvdbSection2D /
+ * gvdbSection3D, kernels/cuda_gvdb_module.cu:60-298; deep_shadow = the composition of SURVEY.md 8c (ii) */
+static f4 shade_pixel(const rc_ctx* c, int shade, int deep_shadow, int x, int y, float ox, float oy, rc_out* o)
+{
+    const ora_scninfo* s = c->s;
+    const int W = s->width, H = s->height;
+    f4 clr;
+    if (shade == ORA_SHADE_SECTION2D) {                                                /* module.cu:272-298 */
+        f3 spnt = F3((float)((double)(float)x * 2.0 / W - 1.0), 0, (float)((double)(float)y * 2.0 / H - 1.0));
+        f3 wpos = add3(s->slice_pnt, mul3(spnt, s->slice_norm));
+        f4 r = {0, 0, 0, 1};
+        int n = node_at_point(c, wpos);
+        if (n < 0) return r;
+        const ora_node* node = get_node(c, 0, n);
+        f3 p = add3(F3((float)node->mValue.x, (float)node->mValue.y, (float)node->mValue.z),
+                    sub3(wpos, F3((float)node->mPos.x, (float)node->mPos.y, (float)node->mPos.z)));
+        f4 t = transfer(c, fetch(c, p.x, p.y, p.z));
+        r.x = t.w * t.x; r.y = t.w * t.y; r.z = t.w * t.z;
+        return r;
+    }
+    f3 rpos = mmult(s->invxform, s->campos);                                       /* geom.cuh:48-51 */
+    float u = (float)(x + ox) / (float)W, w = (float)(y + oy) / (float)H;
+    f3 vv = add3(add3(scl3(s->camu, u), scl3(s->camv, w)), s->cams);               /* geom.cuh:55-63 */
+    f3 rdir = nrm3(mmult(s->invxrot, vv));
+    o->norm = F3(0, 0, 0);
+    if (shade == SCN_SHADE_VOLUME) {
+        o->clr.x = o->clr.y = o->clr.z = 0; o->clr.w = 1;
+        o->hit = F3(0, 0, NOHIT);
+        ray_cast(c, shade, rpos, rdir, o);
+        if (deep_shadow && o->hit.x != 0.f) {
+            f3 spos = add3(rpos, scl3(rdir, o->hit.x));
+            f3 ldir = nrm3(sub3(s->light_pos, spos));
+            rc_out o2;
+            o2.hit = F3(0, 0, NOHIT); o2.norm = F3(0, 0, 0);
+            o2.clr.x = o2.clr.y = o2.clr.z = o2.clr.w = 0;
+            ray_cast(c, ORA_BRICK_SHADOW, spos, ldir, &o2);
+            float lit = 1.0f - o2.clr.w;
+            o->clr.x *= lit; o->clr.y *= lit; o->clr.z *= lit;
+        }
+        float a = (float)(1.0 - (double)o->clr.w);
+        clr.x = s->backclr.x + a * (o->clr.x - s->backclr.x);
+        clr.y = s->backclr.y + a * (o->clr.y - s->backclr.y);
+        clr.z = s->backclr.z + a * (o->clr.z - s->backclr.z);
+        clr.w = a;
+    } else if (shade == ORA_SHADE_EMPTYSKIP) {                                          /* module.cu:184-207 */
+        o->clr.x = o->clr.y = o->clr.z = o->clr.w = 1;
+        o->hit = F3(NOHIT, NOHIT, NOHIT);
+        ray_cast(c, shade, rpos, rdir, o);
+        if (o->hit.z != NOHIT) { clr.x = o->hit.x * 0.01f; clr.y = o->hit.y * 0.01f; clr.z = o->hit.z * 0.01f; }
+        else clr = s->backclr;
+        clr.w = 1.0f;
+    } else if (shade == ORA_SHADE_SECTION3D) {                                          /* module.cu:225-269 */
+        f4 k = {1, 1, 1, 0};
+        f3 wpos = rpos;
+        const f3 pn = s->slice_norm, pp = s->slice_pnt;                               /* rayPlaneIntersect, geom.cuh:67-71 */
+        float t = ((pp.x - wpos.x) * pn.x + (pp.y - wpos.y) * pn.y + (pp.z - wpos.z) * pn.z) / (rdir.x * pn.x + rdir.y * pn.y + rdir.z * pn.z);
+        t = t > 0 ? t : NOHIT;
+        if (t > 0) {
+            wpos = add3(wpos, scl3(rdir, t));
+            int n = node_at_point(c, wpos);
+            if (n >= 0) {
+                const ora_node* node = get_node(c, 0, n);
+                f3 p = add3(F3((float)node->mValue.x, (float)node->mValue.y, (float)node->mValue.z),
+                            sub3(wpos, F3((float)node->mPos.x, (float)node->mPos.y, (float)node->mPos.z)));
+                t = fetch(c, p.x, p.y, p.z);
+                k = transfer(c, t);
+            } else t = 0;
+        }
+        o->hit = F3(NOHIT, NOHIT, NOHIT);
+        o->clr.x = o->clr.y = o->clr.z = o->clr.w = 1;
+        ray_cast(c, SCN_SHADE_TRILINEAR, wpos, rdir, o);
+        f4 a4;
+        if (o->hit.z != NOHIT) {
+            f3 ld = nrm3(sub3(s->light_pos, o->hit));
+            float ds = (t > s->thresh.x) ? 1.0f : (float)(0.8 * (double)fmaxf(0.0f, dot3(o->norm, ld)));
+            a4.x = o->clr.x * ds; a4.y = o->clr.y * ds; a4.z = o->clr.z * ds; a4.w = o->clr.w * ds;
+        } else a4 = s->backclr;
+        clr.x = a4.x + k.w * (k.x - a4.x); clr.y = a4.y + k.w * (k.y - a4.y); clr.z = a4.z + k.w * (k.z - a4.z);
+        clr.w = 1.0f;
+    } else {
+        o->clr.x = o->clr.y = o->clr.z = o->clr.w = 1;
+        o->hit = shade == SCN_SHADE_LEVELSET ? F3(0, 0, NOHIT) : F3(NOHIT, NOHIT, NOHIT);
+        ray_cast(c, shade, rpos, rdir, o);
+        /* the tricubic kernel shades its shadow ray with the trilinear brick function (module.cu:136) */
+        clr = phong(c, shade == ORA_SHADE_TRICUBIC ? SCN_SHADE_TRILINEAR : shade, o->hit, o->norm, o->clr);
+    }
+    return clr;
+}
+
+/* Render(shade) for every mode of the reference's switch (gvdb_volume_gvdb.cpp:4363-4372); deep_shadow and spp are the
+ * compositions of BASELINE.json configs 4 and 5 (spp rays per pixel on a g x g sub-pixel grid, colours summed in sample
+ * order, scaled by 1/spp, packed once) */
+int ora_render_ex(const ora_volume* v, const void* scninfo, int shade, int y0, int y1, uint8_t* out, float* hit_norm, int threads,
+                  int deep_shadow, int spp)
 {
     const ora_scninfo* s = (const ora_scninfo*)scninfo;
     const ora_vdbinfo* g = (const ora_vdbinfo*)v->vdbinfo;
-    if (shade != SCN_SHADE_VOXEL && shade != SCN_SHADE_TRILINEAR && shade != SCN_SHADE_LEVELSET && shade != SCN_SHADE_VOLUME) return -1;
+    if (shade < 0 || shade > SCN_SHADE_VOLUME) return -1;
     if (g->top_lev < 1 || g->top_lev >= 5) return -1;
+    if (spp < 1) spp = 1;
     rc_ctx c = { v, g, s };
     const int W = s->width, H = s->height;
     if (y0 < 0) y0 = 0;
     if (y1 > H) y1 = H;
+    int grid = 1;
+    while (grid * grid < spp) grid++;
+    const float inv_grid = 1.0f / (float)grid, inv_spp = 1.0f / (float)spp;
 #ifdef _OPENMP
     if (threads > 0) omp_set_num_threads(threads);
 #else
@@ -794,31 +992,21 @@ int ora_render(const ora_volume* v, const void* scninfo, int shade, int y0, int 
     #pragma omp parallel for schedule(dynamic, 1)
     for (int y = y0; y < y1; y++) {
         for (int x = 0; x < W; x++) {
-            f3 rpos = mmult(s->invxform, s->campos);                                       /* geom.cuh:48-51 */
-            float u = (float)(x + 0.5f) / (float)W, w = (float)(y + 0.5f) / (float)H;
-            f3 vv = add3(add3(scl3(s->camu, u), scl3(s->camv, w)), s->cams);               /* geom.cuh:55-63 */
-            f3 rdir = nrm3(mmult(s->invxrot, vv));
             rc_out o;
-            o.norm = F3(0, 0, 0);
-            f4 clr;
-            if (shade == SCN_SHADE_VOLUME) {
-                o.clr.x = o.clr.y = o.clr.z = 0; o.clr.w = 1;
-                o.hit = F3(0, 0, NOHIT);
-                ray_cast(&c, shade, rpos, rdir, &o);
-                float a = (float)(1.0 - (double)o.clr.w);
-                clr.x = s->backclr.x + a * (o.clr.x - s->backclr.x);
-                clr.y = s->backclr.y + a * (o.clr.y - s->backclr.y);
-                clr.z = s->backclr.z + a * (o.clr.z - s->backclr.z);
-                clr.w = a;
-            } else {
-                o.clr.x = o.clr.y = o.clr.z = o.clr.w = 1;
-                o.hit = shade == SCN_SHADE_LEVELSET ? F3(0, 0, NOHIT) : F3(NOHIT, NOHIT, NOHIT);
-                ray_cast(&c, shade, rpos, rdir, &o);
-                clr = phong(&c, shade, o.hit, o.norm, o.clr);
+            o.hit = F3(0, 0, NOHIT); o.norm = F3(0, 0, 0);
+            f4 clr = {0, 0, 0, 0};
+            if (spp == 1) clr = shade_pixel(&c, shade, deep_shadow, x, y, 0.5f, 0.5f, &o);
+            else {
+                for (int k = 0; k < spp; k++) {
+                    f4 q = shade_pixel(&c, shade, deep_shadow, x, y, ((float)(k % grid) + 0.5f) * inv_grid, ((float)(k / grid) + 0.5f) * inv_grid, &o);
+                    clr.x += q.x; clr.y += q.y; clr.z += q.z; clr.w += q.w;
+                }
+                clr.x *= inv_spp; clr.y *= inv_spp; clr.z *= inv_spp; clr.w *= inv_spp;
             }
             uint8_t* px = out + 4 * ((size_t)y * W + x);
             px[0] = (uint8_t)(unsigned)(clr.x * 255); px[1] = (uint8_t)(unsigned)(clr.y * 255);
-            px[2] = (uint8_t)(unsigned)(clr.z * 255); px[3] = (uint8_t)(unsigned)(clr.w * 255);
+            px[2] = (uint8_t)(unsigned)(clr.z * 255);
+            px[3] = (shade == ORA_SHADE_EMPTYSKIP || shade == ORA_SHADE_SECTION2D || shade == ORA_SHADE_SECTION3D) ? 255 : (uint8_t)(unsigned)(clr.w * 255);
             if (hit_norm) {
                 float* hn = hit_norm + 8 * ((size_t)y * W + x);
                 int miss = (o.hit.z == NOHIT);
@@ -828,6 +1016,10 @@ int ora_render(const ora_volume* v, const void* scninfo, int shade, int y0, int 
         }
     }
     return 0;
+}
+int ora_render(const ora_volume* v, const void* scninfo, int shade, int y0, int y1, uint8_t* out, float* hit_norm, int threads)
+{
+    return ora_render_ex(v, scninfo, shade, y0, y1, out, hit_norm, threads, 0, 1);
 }
 
 int ora_max_threads(void)

@@ -60,6 +60,10 @@ typedef struct ora_volume {
  * threads <= 0: all OpenMP threads.  Returns 0 or -1 on unsupported input. */
 int       ora_render(const ora_volume* v, const void* scninfo416, int shade, int y0, int y1,
                      uint8_t* out_rgba, float* hit_norm, int threads);
+/* every shade mode of Render()'s switch (0 voxel, 1 section 2-D, 2 section 3-D, 3 empty skip, 4 trilinear, 5 tricubic,
+ * 6 level set, 7 deep) + the compositions of BASELINE.json configs 4 / 5 (deep_shadow, spp rays per pixel) */
+int       ora_render_ex(const ora_volume* v, const void* scninfo416, int shade, int y0, int y1,
+                        uint8_t* rgba_out, float* hit_norm_out, int threads, int deep_shadow, int spp);
 /* software model of the texture unit: trilinear fetch at atlas coordinate (x,y,z) */
 float     ora_tex3d(const ora_volume* v, float x, float y, float z);
 int       ora_max_threads(void);

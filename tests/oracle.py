@@ -58,6 +58,7 @@ def lib():
     L.ora_fill_vdbinfo.argtypes = [C.c_void_p, C.c_void_p]
     L.ora_fill_atlas.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_float]
     L.ora_render.argtypes = [C.POINTER(OraVolume), C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
+    L.ora_render_ex.argtypes = [C.POINTER(OraVolume), C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int]
     L.ora_tex3d.restype = C.c_float
     L.ora_tex3d.argtypes = [C.POINTER(OraVolume), C.c_float, C.c_float, C.c_float]
     L.ora_scene_preset.argtypes = [C.c_char_p, C.c_void_p, C.c_size_t]
@@ -156,16 +157,17 @@ def _ora_volume(vol):
     return v, keep
 
 
-def render(vol, scninfo, shade, rows=None, threads=0, want_hits=False):
-    """CPU ray caster.  Returns rgba [h,w,4] (+ hit/norm [h,w,8])."""
+def render(vol, scninfo, shade, rows=None, threads=0, want_hits=False, deep_shadow=False, spp=1):
+    """CPU ray caster (every shade mode of Render()'s switch; deep_shadow / spp = BASELINE configs 4 / 5).
+    Returns rgba [h,w,4] (+ hit/norm [h,w,8])."""
     s = np.frombuffer(scninfo, np.uint8).copy()
     w, h = int(s[0:4].view(np.int32)[0]), int(s[4:8].view(np.int32)[0])
     v, keep = _ora_volume(vol)
     out = np.zeros((h, w, 4), np.uint8)
     hn = np.zeros((h, w, 8), np.float32) if want_hits else None
     y0, y1 = rows if rows else (0, h)
-    rc = lib().ora_render(C.byref(v), s.ctypes.data_as(C.c_void_p), int(shade), y0, y1, out.ctypes.data_as(C.c_void_p),
-                          hn.ctypes.data_as(C.c_void_p) if want_hits else None, int(threads))
+    rc = lib().ora_render_ex(C.byref(v), s.ctypes.data_as(C.c_void_p), int(shade), y0, y1, out.ctypes.data_as(C.c_void_p),
+                             hn.ctypes.data_as(C.c_void_p) if want_hits else None, int(threads), 1 if deep_shadow else 0, int(spp))
     if rc != 0:
         raise RuntimeError("ora_render: unsupported input")
     return (out, hn) if want_hits else out

@@ -41,6 +41,28 @@ def test_cpu_raycaster_within_tolerance_of_reference(ora, pkg, preset, mode):
     assert (d > 1).mean() < 2e-3
 
 
+@pytest.mark.parametrize("preset", ["cfg1_tiny", "cfg4_tiny", "cfg1_small"])
+@pytest.mark.parametrize("mode", ["tricubic", "emptyskip", "section2d", "section3d", "deepshadow", "deepspp"])
+def test_cpu_remaining_modes_within_tolerance_of_reference(ora, pkg, preset, mode):
+    """The rest of Render()'s switch (tricubic, empty skip, 2-D / 3-D sections incl. the getNodeAtPoint descent) and the two
+    composed BASELINE modes (deep + rayShadowBrick march, 4 rays per pixel) restated on the CPU, against the reference's
+    images: PSNR >= 60 dB, at most 0.2 % of the pixels off by more than 1/255."""
+    import os
+    import refcmp
+    from common import GOLDEN
+    g = np.load(os.path.join(GOLDEN, f"ref_modes2_{preset}.npz"))
+    p, vol = ora.scene_volume(preset)
+    _, table = ora.scninfo_for(pkg, p)
+    vol["transfer"] = table
+    shade, dshadow, spp = refcmp.MODES2[mode]
+    img = ora.render(vol, g[f"scn_{mode}"].tobytes(), shade, deep_shadow=bool(dshadow), spp=spp)
+    ref = g[f"rgba_{mode}"]
+    d = np.abs(img.astype(int) - ref.astype(int)).max(axis=2)
+    assert psnr(img, ref) >= 60.0, (psnr(img, ref), int((d > 0).sum()))
+    assert (d > 1).mean() < 2e-3
+    assert (ref != ref[0, 0]).any()
+
+
 def test_cpu_hit_points_close_to_reference(ora, pkg):
     g = golden("cfg3_tiny")
     p, vol = ora.scene_volume("cfg3_tiny")
