@@ -11,9 +11,45 @@
 #include <cstring>
 #include <string>
 #include <vector>
+#include <dlfcn.h>
+
+// ------------------------------------------------------------------------------------------------ CUDA context
+// The reference lives in a context it creates itself (StartCuda: cuCtxCreate, gvdb_allocator.cpp:1105-1109) and brackets
+// every entry point with cuCtxPushCurrent / cuCtxPopCurrent (gvdb_volume_gvdb.cpp:41-42).  Its pools, CUarrays and render
+// buffers belong to THAT context, so this library must run in it too: gvdbx_create adopts the context that is current on
+// the calling thread (only when none is current does it bind the device's primary context, as a stand-alone CUDA-runtime
+// host expects), and every entry point makes the adopted context current for its own duration — the same push / pop
+// discipline as the reference.  The four driver entry points are taken from libcuda at run time (no link dependency:
+// the library still loads, and fails with GVDBX_E_CUDA, on a machine without a driver).
+typedef int (*gx_cuCtxGetCurrent_t)(void**);
+typedef int (*gx_cuCtxPushCurrent_t)(void*);
+typedef int (*gx_cuCtxPopCurrent_t)(void**);
+typedef int (*gx_cuCtxGetDevice_t)(int*);
+static struct GxDriver {
+    gx_cuCtxGetCurrent_t  get = nullptr;
+    gx_cuCtxPushCurrent_t push = nullptr;
+    gx_cuCtxPopCurrent_t  pop = nullptr;
+    gx_cuCtxGetDevice_t   dev = nullptr;
+    bool ok = false, looked = false;
+    bool load()
+    {
+        if (looked) return ok;
+        looked = true;
+        void* lib = dlopen("libcuda.so.1", RTLD_NOW | RTLD_GLOBAL);
+        if (!lib) lib = dlopen("libcuda.so", RTLD_NOW | RTLD_GLOBAL);
+        if (!lib) return false;
+        get = (gx_cuCtxGetCurrent_t)dlsym(lib, "cuCtxGetCurrent");
+        push = (gx_cuCtxPushCurrent_t)dlsym(lib, "cuCtxPushCurrent_v2");
+        pop = (gx_cuCtxPopCurrent_t)dlsym(lib, "cuCtxPopCurrent_v2");
+        dev = (gx_cuCtxGetDevice_t)dlsym(lib, "cuCtxGetDevice");
+        ok = get && push && pop && dev;
+        return ok;
+    }
+} gx_drv;
 
 struct gvdbx_ctx {
     int          device = 0;
+    void*        cuctx = nullptr;       // the CUcontext every entry point runs in (adopted at creation)
     cudaStream_t stream = nullptr;
     std::string  err;
     // options
@@ -67,6 +103,21 @@ struct gvdbx_ctx {
 
 static int gx_fail(gvdbx_t* h, int code, const std::string& msg) { if (h) h->err = msg; return code; }
 
+// makes the handle's context current for the lifetime of the object (no-op when it already is)
+struct GxCtx {
+    bool pushed = false;
+    explicit GxCtx(const gvdbx_t* h)
+    {
+        if (!h || !h->cuctx || !gx_drv.ok) return;
+        void* cur = nullptr;
+        if (gx_drv.get(&cur) == 0 && cur == h->cuctx) return;
+        pushed = gx_drv.push(h->cuctx) == 0;
+    }
+    ~GxCtx() { if (pushed) { void* p = nullptr; gx_drv.pop(&p); } }
+    GxCtx(const GxCtx&) = delete;
+    GxCtx& operator=(const GxCtx&) = delete;
+};
+
 extern "C" int gvdbx_create(gvdbx_t** out, int cuda_device, void* cuda_stream)
 {
     if (!out) return GVDBX_E_ARG;
@@ -78,9 +129,23 @@ extern "C" int gvdbx_create(gvdbx_t** out, int cuda_device, void* cuda_stream)
                 e == cudaSuccess ? "device index out of range" : cudaGetErrorString(e));
         return GVDBX_E_CUDA;
     }
-    if (cudaSetDevice(cuda_device) != cudaSuccess) return GVDBX_E_CUDA;
+    // adopt the caller's current context (the reference's own, when called from the VolumeGVDB shim); otherwise bind the
+    // primary context of `cuda_device`
+    void* cur = nullptr;
+    int curdev = -1;
+    if (gx_drv.load() && gx_drv.get(&cur) == 0 && cur != nullptr && gx_drv.dev(&curdev) == 0) {
+        if (curdev != cuda_device) {
+            fprintf(stderr, "gvdbx_create: the current CUDA context is on device %d, not %d\n", curdev, cuda_device);
+            return GVDBX_E_ARG;
+        }
+    } else {
+        if (cudaSetDevice(cuda_device) != cudaSuccess || cudaFree(0) != cudaSuccess) return GVDBX_E_CUDA;
+        cur = nullptr;
+        if (gx_drv.ok) gx_drv.get(&cur);
+    }
     gvdbx_t* h = new gvdbx_ctx;
     h->device = cuda_device;
+    h->cuctx = cur;
     h->stream = (cudaStream_t)cuda_stream;
     h->base_stream = h->stream;
     if (cudaMalloc(&h->d_counters, 8 * sizeof(unsigned long long)) != cudaSuccess) { delete h; return GVDBX_E_CUDA; }
@@ -121,7 +186,8 @@ static void gx_free_atlas(gvdbx_t* h)
 extern "C" int gvdbx_destroy(gvdbx_t* h)
 {
     if (!h) return GVDBX_E_ARG;
-    cudaSetDevice(h->device);
+    {
+    GxCtx ctx_(h);
     cudaStreamSynchronize(h->stream);
     gvdbx_lanes(h, 0);
     gx_free_topology(h);
@@ -131,6 +197,7 @@ extern "C" int gvdbx_destroy(gvdbx_t* h)
     if (h->d_transfer) cudaFree(h->d_transfer);
     for (float4* p : h->deep_lut) if (p) cudaFree(p);
     if (h->d_counters) cudaFree(h->d_counters);
+    }
     delete h;
     return GVDBX_OK;
 }
@@ -197,7 +264,7 @@ static int gx_ensure_voxel_mask(gvdbx_t* h, float thresh)
 extern "C" int gvdbx_import_topology(gvdbx_t* h, const void* vdbinfo)
 {
     if (!h || !vdbinfo) return GVDBX_E_ARG;
-    GX_CUDA(h, cudaSetDevice(h->device));
+    GxCtx ctx_(h);
     GxVDBInfo v;
     memcpy(&v, vdbinfo, sizeof v);
     if (v.top_lev < 0 || v.top_lev >= GX_MAXLEV) return gx_fail(h, GVDBX_E_ARG, "top_lev out of range (0..4)");
@@ -238,7 +305,7 @@ extern "C" int gvdbx_import_topology_host(gvdbx_t* h, const void* vdbinfo, const
                                           const uint64_t* pool1_bytes)
 {
     if (!h || !vdbinfo || !pool0 || !pool1 || !pool1_bytes) return GVDBX_E_ARG;
-    GX_CUDA(h, cudaSetDevice(h->device));
+    GxCtx ctx_(h);
     GxVDBInfo v;
     memcpy(&v, vdbinfo, sizeof v);
     if (v.top_lev < 0 || v.top_lev >= GX_MAXLEV) return gx_fail(h, GVDBX_E_ARG, "top_lev out of range (0..4)");
@@ -304,7 +371,7 @@ extern "C" int gvdbx_import_atlas_array(gvdbx_t* h, int chan, void* cuarray, int
 {
     if (!h || !cuarray || rx <= 0 || ry <= 0 || rz <= 0) return GVDBX_E_ARG;
     if (chan != 0) return gx_fail(h, GVDBX_E_UNSUPPORTED, "only channel 0 (T_FLOAT) is supported");
-    GX_CUDA(h, cudaSetDevice(h->device));
+    GxCtx ctx_(h);
     gx_free_atlas(h);
     int rc = gx_make_texture(h, (cudaArray_t)cuarray);
     if (rc) return rc;
@@ -330,7 +397,7 @@ extern "C" int gvdbx_import_atlas_host(gvdbx_t* h, int chan, const float* texels
 {
     if (!h || !texels || rx <= 0 || ry <= 0 || rz <= 0) return GVDBX_E_ARG;
     if (chan != 0) return gx_fail(h, GVDBX_E_UNSUPPORTED, "only channel 0 (T_FLOAT) is supported");
-    GX_CUDA(h, cudaSetDevice(h->device));
+    GxCtx ctx_(h);
     gx_free_atlas(h);
     cudaChannelFormatDesc fd = cudaCreateChannelDesc<float>();
     GX_CUDA(h, cudaMalloc3DArray(&h->own_array, &fd, make_cudaExtent(rx, ry, rz), cudaArraySurfaceLoadStore));
@@ -377,7 +444,7 @@ extern "C" int gvdbx_update_apron(gvdbx_t* h, int chan, float boundval)
     if (chan != 0) return gx_fail(h, GVDBX_E_UNSUPPORTED, "only channel 0 (T_FLOAT) is supported");
     if (!h->have_topo || !h->have_atlas) return gx_fail(h, GVDBX_E_STATE, "UpdateApron needs topology and atlas");
     if (!h->surf) return gx_fail(h, GVDBX_E_UNSUPPORTED, "the atlas array was created without surface load/store");
-    GX_CUDA(h, cudaSetDevice(h->device));
+    GxCtx ctx_(h);
     GxParams P;
     gx_tree_params(h, P);
     const int n = h->vdb.nodecnt[0];
@@ -395,7 +462,7 @@ extern "C" int gvdbx_export_atlas_host(gvdbx_t* h, int chan, float* texels, int 
     if (chan != 0) return gx_fail(h, GVDBX_E_UNSUPPORTED, "only channel 0 (T_FLOAT) is supported");
     if (!h->have_atlas || !h->array) return gx_fail(h, GVDBX_E_STATE, "no atlas imported");
     if (rx != h->ares[0] || ry != h->ares[1] || rz != h->ares[2]) return gx_fail(h, GVDBX_E_ARG, "atlas resolution mismatch");
-    GX_CUDA(h, cudaSetDevice(h->device));
+    GxCtx ctx_(h);
     cudaMemcpy3DParms cp;
     memset(&cp, 0, sizeof cp);
     cp.srcArray = h->array;
@@ -413,7 +480,7 @@ extern "C" int gvdbx_import_atlas_device(gvdbx_t* h, int chan, uint64_t texels_d
 {
     if (!h || !texels_d || rx <= 0 || ry <= 0 || rz <= 0) return GVDBX_E_ARG;
     if (chan != 0) return gx_fail(h, GVDBX_E_UNSUPPORTED, "only channel 0 (T_FLOAT) is supported");
-    GX_CUDA(h, cudaSetDevice(h->device));
+    GxCtx ctx_(h);
     gx_free_atlas(h);
     cudaChannelFormatDesc fd = cudaCreateChannelDesc<float>();
     GX_CUDA(h, cudaMalloc3DArray(&h->own_array, &fd, make_cudaExtent(rx, ry, rz), cudaArraySurfaceLoadStore));
@@ -461,14 +528,14 @@ static int gx_make_color_texture(gvdbx_t* h, cudaArray_t arr, int filter)
 extern "C" int gvdbx_import_color_array(gvdbx_t* h, void* cuarray, int filter)
 {
     if (!h || !cuarray) return GVDBX_E_ARG;
-    GX_CUDA(h, cudaSetDevice(h->device));
+    GxCtx ctx_(h);
     gx_free_color(h);
     return gx_make_color_texture(h, (cudaArray_t)cuarray, filter);
 }
 extern "C" int gvdbx_import_color_host(gvdbx_t* h, const void* rgba8_texels, int rx, int ry, int rz, int filter)
 {
     if (!h || !rgba8_texels || rx <= 0 || ry <= 0 || rz <= 0) return GVDBX_E_ARG;
-    GX_CUDA(h, cudaSetDevice(h->device));
+    GxCtx ctx_(h);
     gx_free_color(h);
     cudaChannelFormatDesc fd = cudaCreateChannelDesc<uchar4>();
     GX_CUDA(h, cudaMalloc3DArray(&h->clr_own, &fd, make_cudaExtent(rx, ry, rz), 0));
@@ -485,7 +552,7 @@ extern "C" int gvdbx_import_color_host(gvdbx_t* h, const void* rgba8_texels, int
 extern "C" int gvdbx_clear_color(gvdbx_t* h)
 {
     if (!h) return GVDBX_E_ARG;
-    GX_CUDA(h, cudaSetDevice(h->device));
+    GxCtx ctx_(h);
     gx_free_color(h);
     return GVDBX_OK;
 }
@@ -493,7 +560,7 @@ extern "C" int gvdbx_clear_color(gvdbx_t* h)
 extern "C" int gvdbx_set_transfer(gvdbx_t* h, const float* rgba_host)
 {
     if (!h || !rgba_host) return GVDBX_E_ARG;
-    GX_CUDA(h, cudaSetDevice(h->device));
+    GxCtx ctx_(h);
     if (!h->d_transfer) GX_CUDA(h, cudaMalloc(&h->d_transfer, GVDBX_TRANSFER_ENTRIES * sizeof(float4)));
     GX_CUDA(h, cudaMemcpyAsync(h->d_transfer, rgba_host, GVDBX_TRANSFER_ENTRIES * sizeof(float4), cudaMemcpyHostToDevice, h->stream));
     GX_CUDA(h, cudaStreamSynchronize(h->stream));      // the host buffer may be reused by the caller
@@ -613,7 +680,7 @@ extern "C" int gvdbx_render(gvdbx_t* h, const void* scninfo, int shade_mode, int
                             int tx0, int ty0, int tw, int th)
 {
     if (!h) return GVDBX_E_ARG;
-    GX_CUDA(h, cudaSetDevice(h->device));
+    GxCtx ctx_(h);
     if (shade_mode == GVDBX_SHADE_OFF) {    // gvdb_volume_gvdb.cpp:4340-4346
         const GxScnInfo* s = (const GxScnInfo*)scninfo;
         if (!s || !outbuf_d) return GVDBX_E_ARG;
@@ -656,7 +723,7 @@ extern "C" int gvdbx_kernel_params(gvdbx_t* h, const void* scninfo, int shade_mo
 {
     if (!h || !params_out) return GVDBX_E_ARG;
     if (params_bytes != sizeof(GxParams)) return gx_fail(h, GVDBX_E_ARG, "params_bytes != sizeof(GxParams): plugin built against other headers");
-    GX_CUDA(h, cudaSetDevice(h->device));
+    GxCtx ctx_(h);
     GxParams P; int mode = 0;
     int rc = gx_fill_params(h, scninfo, shade_mode, chan, P, mode);
     if (rc) return rc;
@@ -668,7 +735,7 @@ extern "C" int gvdbx_kernel_params(gvdbx_t* h, const void* scninfo, int shade_mo
 extern "C" int gvdbx_render_debug(gvdbx_t* h, const void* scninfo, int shade_mode, int chan, uint64_t outbuf_d, uint64_t dbg_d)
 {
     if (!h) return GVDBX_E_ARG;
-    GX_CUDA(h, cudaSetDevice(h->device));
+    GxCtx ctx_(h);
     GxParams P; int mode = 0;
     int rc = gx_fill_params(h, scninfo, shade_mode, chan, P, mode);
     if (rc) return rc;
@@ -697,7 +764,7 @@ extern "C" int gvdbx_render_tiles(gvdbx_t* h, const void* scninfo, int shade_mod
                                   int tile_size, int rank, int nranks)
 {
     if (!h) return GVDBX_E_ARG;
-    GX_CUDA(h, cudaSetDevice(h->device));
+    GxCtx ctx_(h);
     GxParams P; int mode = 0;
     int rc = gx_fill_params(h, scninfo, shade_mode, chan, P, mode);
     if (rc) return rc;
@@ -727,7 +794,7 @@ extern "C" int gvdbx_render_tiles_direct(gvdbx_t* h, const void* scninfo, int sh
                                          int tile_size, int rank, int nranks)
 {
     if (!h) return GVDBX_E_ARG;
-    GX_CUDA(h, cudaSetDevice(h->device));
+    GxCtx ctx_(h);
     GxParams P; int mode = 0;
     int rc = gx_fill_params(h, scninfo, shade_mode, chan, P, mode);
     if (rc) return rc;
@@ -769,7 +836,7 @@ extern "C" int gvdbx_peer_alloc(gvdbx_t* h, size_t bytes, uint64_t* dptr, void* 
 {
     if (!h || !dptr || !handle64 || bytes == 0) return GVDBX_E_ARG;
     static_assert(sizeof(cudaIpcMemHandle_t) == GVDBX_IPC_HANDLE_BYTES, "IPC handle size");
-    GX_CUDA(h, cudaSetDevice(h->device));
+    GxCtx ctx_(h);
     void* p = nullptr;
     GX_CUDA(h, cudaMalloc(&p, bytes));
     GX_CUDA(h, cudaMemset(p, 0, bytes));
@@ -783,14 +850,14 @@ extern "C" int gvdbx_peer_alloc(gvdbx_t* h, size_t bytes, uint64_t* dptr, void* 
 extern "C" int gvdbx_peer_free(gvdbx_t* h, uint64_t dptr)
 {
     if (!h || !dptr) return GVDBX_E_ARG;
-    GX_CUDA(h, cudaSetDevice(h->device));
+    GxCtx ctx_(h);
     GX_CUDA(h, cudaFree((void*)dptr));
     return GVDBX_OK;
 }
 extern "C" int gvdbx_peer_open(gvdbx_t* h, const void* handle64, uint64_t* dptr)
 {
     if (!h || !dptr || !handle64) return GVDBX_E_ARG;
-    GX_CUDA(h, cudaSetDevice(h->device));
+    GxCtx ctx_(h);
     cudaIpcMemHandle_t hd;
     memcpy(&hd, handle64, sizeof hd);
     void* p = nullptr;
@@ -801,7 +868,7 @@ extern "C" int gvdbx_peer_open(gvdbx_t* h, const void* handle64, uint64_t* dptr)
 extern "C" int gvdbx_peer_close(gvdbx_t* h, uint64_t dptr)
 {
     if (!h || !dptr) return GVDBX_E_ARG;
-    GX_CUDA(h, cudaSetDevice(h->device));
+    GxCtx ctx_(h);
     GX_CUDA(h, cudaIpcCloseMemHandle((void*)dptr));
     return GVDBX_OK;
 }
@@ -821,7 +888,7 @@ extern "C" int gvdbx_set_stream(gvdbx_t* h, void* cuda_stream)
 extern "C" int gvdbx_lanes(gvdbx_t* h, int n)
 {
     if (!h || n < 0 || n > 16) return GVDBX_E_ARG;
-    GX_CUDA(h, cudaSetDevice(h->device));
+    GxCtx ctx_(h);
     for (cudaStream_t s : h->lanes) { cudaStreamSynchronize(s); cudaStreamDestroy(s); }
     for (cudaEvent_t e : h->lane_ev) cudaEventDestroy(e);
     if (h->base_ev) { cudaEventDestroy(h->base_ev); h->base_ev = nullptr; }
@@ -855,7 +922,7 @@ extern "C" int gvdbx_lanes_fork(gvdbx_t* h)
 {
     if (!h) return GVDBX_E_ARG;
     if (h->lanes.empty()) return GVDBX_OK;
-    GX_CUDA(h, cudaSetDevice(h->device));
+    GxCtx ctx_(h);
     GX_CUDA(h, cudaEventRecord(h->base_ev, h->base_stream));
     for (cudaStream_t s : h->lanes) GX_CUDA(h, cudaStreamWaitEvent(s, h->base_ev, 0));
     return GVDBX_OK;
@@ -867,7 +934,7 @@ extern "C" int gvdbx_lanes_join(gvdbx_t* h)
     h->stream = h->base_stream;
     h->cur_lane = -1;
     if (h->lanes.empty()) return GVDBX_OK;
-    GX_CUDA(h, cudaSetDevice(h->device));
+    GxCtx ctx_(h);
     for (size_t i = 0; i < h->lanes.size(); i++) {
         GX_CUDA(h, cudaEventRecord(h->lane_ev[i], h->lanes[i]));
         GX_CUDA(h, cudaStreamWaitEvent(h->base_stream, h->lane_ev[i], 0));
@@ -880,7 +947,7 @@ extern "C" int gvdbx_lanes_join(gvdbx_t* h)
 extern "C" int gvdbx_stream_signal(gvdbx_t* h, void* cuda_stream, uint64_t flag_d, uint32_t value)
 {
     if (!h || !flag_d) return GVDBX_E_ARG;
-    GX_CUDA(h, cudaSetDevice(h->device));
+    GxCtx ctx_(h);
     cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : h->stream;
     gx_signal_kernel<<<1, 1, 0, st>>>((unsigned int*)flag_d, value);
     GX_CUDA(h, cudaGetLastError());
@@ -891,7 +958,7 @@ extern "C" int gvdbx_stream_signal(gvdbx_t* h, void* cuda_stream, uint64_t flag_
 extern "C" int gvdbx_stream_signal_add(gvdbx_t* h, void* cuda_stream, uint64_t flag_d, uint32_t inc)
 {
     if (!h || !flag_d) return GVDBX_E_ARG;
-    GX_CUDA(h, cudaSetDevice(h->device));
+    GxCtx ctx_(h);
     cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : h->stream;
     gx_signal_add_kernel<<<1, 1, 0, st>>>((unsigned int*)flag_d, inc);
     GX_CUDA(h, cudaGetLastError());
@@ -901,7 +968,7 @@ extern "C" int gvdbx_stream_signal_add(gvdbx_t* h, void* cuda_stream, uint64_t f
 extern "C" int gvdbx_stream_signal_many(gvdbx_t* h, void* cuda_stream, const uint64_t* flags_d, int n, uint32_t value)
 {
     if (!h || !flags_d || n <= 0 || n > 16) return GVDBX_E_ARG;
-    GX_CUDA(h, cudaSetDevice(h->device));
+    GxCtx ctx_(h);
     cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : h->stream;
     GxFlagList L;
     for (int i = 0; i < 16; i++) L.p[i] = i < n ? (unsigned int*)flags_d[i] : nullptr;
@@ -919,7 +986,7 @@ typedef int (*gx_cuStreamWaitValue32_t)(cudaStream_t, unsigned long long, unsign
 extern "C" int gvdbx_stream_wait(gvdbx_t* h, void* cuda_stream, uint64_t flag_d, uint32_t value)
 {
     if (!h || !flag_d) return GVDBX_E_ARG;
-    GX_CUDA(h, cudaSetDevice(h->device));
+    GxCtx ctx_(h);
     cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : h->stream;
     if (h->memops) {
         static gx_cuStreamWaitValue32_t fn = nullptr;
@@ -942,7 +1009,7 @@ extern "C" int gvdbx_stream_wait(gvdbx_t* h, void* cuda_stream, uint64_t flag_d,
 extern "C" int gvdbx_assemble_tiles(gvdbx_t* h, uint64_t gathered_d, uint64_t frame_d, int width, int height, int tile_size, int nranks)
 {
     if (!h || !gathered_d || !frame_d || width <= 0 || height <= 0 || tile_size <= 0 || nranks <= 0) return GVDBX_E_ARG;
-    GX_CUDA(h, cudaSetDevice(h->device));
+    GxCtx ctx_(h);
     const int tiles_x = (width + tile_size - 1) / tile_size;
     const int ntiles = tiles_x * ((height + tile_size - 1) / tile_size);
     const int slots = (ntiles + nranks - 1) / nranks;
@@ -957,7 +1024,7 @@ extern "C" int gvdbx_assemble_tiles(gvdbx_t* h, uint64_t gathered_d, uint64_t fr
 extern "C" int gvdbx_raytrace(gvdbx_t* h, const void* scninfo, int chan, uint64_t rays_d, int num_rays, float bias)
 {
     if (!h) return GVDBX_E_ARG;
-    GX_CUDA(h, cudaSetDevice(h->device));
+    GxCtx ctx_(h);
     GxParams P; int mode = 0;
     int rc = gx_fill_params(h, scninfo, GVDBX_SHADE_TRILINEAR, chan, P, mode);
     if (rc) return rc;
@@ -978,7 +1045,7 @@ extern "C" int gvdbx_raytrace(gvdbx_t* h, const void* scninfo, int chan, uint64_
 extern "C" int gvdbx_read_buffer(gvdbx_t* h, uint64_t buf_d, void* host, size_t bytes)
 {
     if (!h || !buf_d || !host) return GVDBX_E_ARG;
-    GX_CUDA(h, cudaSetDevice(h->device));
+    GxCtx ctx_(h);
     GX_CUDA(h, cudaMemcpyAsync(host, (const void*)buf_d, bytes, cudaMemcpyDeviceToHost, h->stream));
     GX_CUDA(h, cudaStreamSynchronize(h->stream));
     return GVDBX_OK;
@@ -989,7 +1056,7 @@ extern "C" int gvdbx_read_buffer(gvdbx_t* h, uint64_t buf_d, void* host, size_t 
 extern "C" int gvdbx_read_buffer_async(gvdbx_t* h, uint64_t buf_d, void* host, size_t bytes)
 {
     if (!h || !buf_d || !host) return GVDBX_E_ARG;
-    GX_CUDA(h, cudaSetDevice(h->device));
+    GxCtx ctx_(h);
     GX_CUDA(h, cudaMemcpyAsync(host, (const void*)buf_d, bytes, cudaMemcpyDeviceToHost, h->stream));
     return GVDBX_OK;
 }
@@ -997,7 +1064,7 @@ extern "C" int gvdbx_read_buffer_async(gvdbx_t* h, uint64_t buf_d, void* host, s
 extern "C" int gvdbx_sync(gvdbx_t* h)
 {
     if (!h) return GVDBX_E_ARG;
-    GX_CUDA(h, cudaSetDevice(h->device));
+    GxCtx ctx_(h);
     GX_CUDA(h, cudaStreamSynchronize(h->stream));
     return GVDBX_OK;
 }
@@ -1005,7 +1072,7 @@ extern "C" int gvdbx_sync(gvdbx_t* h)
 extern "C" int gvdbx_get_counters(gvdbx_t* h, gvdbx_counters* out)
 {
     if (!h || !out) return GVDBX_E_ARG;
-    GX_CUDA(h, cudaSetDevice(h->device));
+    GxCtx ctx_(h);
     unsigned long long v[8];
     GX_CUDA(h, cudaMemcpyAsync(v, h->d_counters, sizeof v, cudaMemcpyDeviceToHost, h->stream));
     GX_CUDA(h, cudaStreamSynchronize(h->stream));
@@ -1018,7 +1085,7 @@ extern "C" int gvdbx_sample_points(gvdbx_t* h, int chan, uint64_t xyz_d, int n, 
     if (!h || !xyz_d || !out_tex_d || !out_lin_d || n <= 0) return GVDBX_E_ARG;
     if (!h->have_atlas) return gx_fail(h, GVDBX_E_STATE, "no atlas imported");
     if (chan != 0) return gx_fail(h, GVDBX_E_UNSUPPORTED, "only channel 0 is supported");
-    GX_CUDA(h, cudaSetDevice(h->device));
+    GxCtx ctx_(h);
     GxParams P;
     memset(&P, 0, sizeof P);
     P.tex = h->tex; P.bricks = h->d_bricks;
@@ -1029,11 +1096,16 @@ extern "C" int gvdbx_sample_points(gvdbx_t* h, int chan, uint64_t xyz_d, int n, 
 }
 
 // device-buffer helpers for the host mirror (gvdbx_host.cpp is plain C++)
-extern "C" int gvdbx_internal_alloc(uint64_t* ptr, size_t bytes)
+extern "C" int gvdbx_internal_alloc(gvdbx_t* h, uint64_t* ptr, size_t bytes)
 {
+    GxCtx ctx_(h);
     void* d = nullptr;
     if (!ptr || cudaMalloc(&d, bytes) != cudaSuccess) return GVDBX_E_CUDA;
     *ptr = (uint64_t)d;
     return GVDBX_OK;
 }
-extern "C" int gvdbx_internal_free(uint64_t ptr) { return cudaFree((void*)ptr) == cudaSuccess ? GVDBX_OK : GVDBX_E_CUDA; }
+extern "C" int gvdbx_internal_free(gvdbx_t* h, uint64_t ptr)
+{
+    GxCtx ctx_(h);
+    return cudaFree((void*)ptr) == cudaSuccess ? GVDBX_OK : GVDBX_E_CUDA;
+}

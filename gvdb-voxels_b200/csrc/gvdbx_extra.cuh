@@ -262,6 +262,10 @@ __device__ __forceinline__ float4 gx_pixel_section3d(const GxParams& P, S& smp, 
             cnt.s_tri++; cnt.s_lut++;
             t = smp.tri(p.x, p.y, p.z);
             clr = __ldg(&P.transfer[gx_transfer_index(t, P.thresh.x, gx_rcp_approx(P.thresh.z - P.thresh.y))]);
+            if (P.clr_tex) {                // the section plane takes the voxel's colour too (cuda_gvdb_module.cu:249-252); alpha * 1.0
+                const float4 c = gx_color(P, p);
+                clr.x *= c.x; clr.y *= c.y; clr.z *= c.z;
+            }
         } else {
             t = 0;
         }

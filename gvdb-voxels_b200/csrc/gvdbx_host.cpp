@@ -490,8 +490,8 @@ int VolumeGVDB::AddRenderBuf(int chan, int w, int h, int bpp)
 }  // namespace gvdbx
 
 // device buffer helpers live in the CUDA translation unit
-extern "C" int gvdbx_internal_alloc(uint64_t* ptr, size_t bytes);
-extern "C" int gvdbx_internal_free(uint64_t ptr);
+extern "C" int gvdbx_internal_alloc(gvdbx_t* h, uint64_t* ptr, size_t bytes);
+extern "C" int gvdbx_internal_free(gvdbx_t* h, uint64_t ptr);
 
 namespace gvdbx {
 int VolumeGVDB::ResizeRenderBuf(int chan, int w, int h, int bpp)
@@ -501,9 +501,9 @@ int VolumeGVDB::ResizeRenderBuf(int chan, int w, int h, int bpp)
     RenderBuf& b = mRenderBuf[chan];
     b.max = (size_t)w * h; b.size = (size_t)w * h * bpp; b.stride = (size_t)w;
     if (chan == 0 && mScene) mScene->SetRes(w, h);
-    if (b.gpu) gvdbx_internal_free(b.gpu);
+    if (b.gpu) gvdbx_internal_free(mCtx, b.gpu);
     b.gpu = 0;
-    return gvdbx_internal_alloc(&b.gpu, b.size);
+    return gvdbx_internal_alloc(mCtx, &b.gpu, b.size);
 }
 int VolumeGVDB::ReadRenderBuf(int chan, unsigned char* out)
 {

@@ -133,3 +133,44 @@ extern "C" __global__ void oracleDeepSample(VDBInfo* gvdb, uchar chan, uchar4* o
     clr = make_float4(lerp3(SCN_BACKCLR, clr, 1.0 - clr.w), 1.0 - clr.w);
     ((float4*)outBuf)[y * scn.width + x] = clr;
 }
+
+// voxel-hit ID and depth.  The native SHADE_VOXEL kernel keeps both internal (it only emits RGBA8), so this
+// is raySurfaceVoxelBrick (cuda_gvdb_raycast.cuh:227-265) restated statement by statement with two extra outputs smuggled
+// through the brick-function signature: norm <- bit patterns of int3(vmin) (the index-space voxel) and hclr <- {dda.t.x (the
+// depth), bit pattern of the leaf id, 0, 1}.  The traversal around it is the reference's own rayCast.
+// Output: 32 B per pixel = float4{hit.xyz, t} int4{voxel.xyz, leaf}; a miss writes {hit, 0} {0, 0, 0, -1}.
+__device__ void oracleVoxelIdBrick(VDBInfo* gvdb, uchar chan, int nodeid, float3 t, float3 pos, float3 dir, float3& hit, float3& norm, float4& hclr)
+{
+    float3 vmin;
+    VDBNode* node = getNode(gvdb, 0, nodeid, &vmin);
+    float3 o = make_float3(node->mValue);
+    HDDAState dda;
+    dda.SetFromRay(pos, dir, t);
+    dda.PrepareLeaf(vmin);
+    for (int iter = 0; iter < MAX_ITER && dda.p.x >= 0 && dda.p.y >= 0 && dda.p.z >= 0
+                       && dda.p.x < gvdb->res[0] && dda.p.y < gvdb->res[0] && dda.p.z < gvdb->res[0]; iter++) {
+        if (tex3D<float>(gvdb->volIn[chan], dda.p.x + o.x + .5, dda.p.y + o.y + .5, dda.p.z + o.z + .5) > SCN_THRESH) {
+            vmin += make_float3(dda.p);
+            dda.t = rayBoxIntersect(pos, dir, vmin, vmin + 1);
+            if (dda.t.z == NOHIT) { hit.z = NOHIT; continue; }
+            hit = getRayPoint(pos, dir, dda.t.x);
+            int3 v = make_int3(vmin);
+            norm = make_float3(__int_as_float(v.x), __int_as_float(v.y), __int_as_float(v.z));
+            hclr = make_float4(dda.t.x, __int_as_float(nodeid), 0.f, 1.f);
+            return;
+        }
+        dda.Next();
+        dda.Step();
+    }
+}
+extern "C" __global__ void oracleVoxelId(VDBInfo* gvdb, uchar chan, uchar4* outBuf)
+{
+    ORACLE_PIXEL();
+    float3 hit = make_float3(NOHIT, NOHIT, NOHIT), norm = make_float3(0, 0, 0);
+    float4 clr = make_float4(1, 1, 1, 1);
+    rayCast(gvdb, chan, rpos, rdir, hit, norm, clr, oracleVoxelIdBrick);
+    float4* o = (float4*)outBuf + 2 * (y * scn.width + x);
+    const bool miss = (hit.z == NOHIT);
+    o[0] = make_float4(hit.x, hit.y, hit.z, miss ? 0.f : clr.x);
+    o[1] = miss ? make_float4(0.f, 0.f, 0.f, __int_as_float(-1)) : make_float4(norm.x, norm.y, norm.z, clr.y);
+}

@@ -20,6 +20,13 @@
 //          bench mode: a step = F frames on an orbit (camera yaw + 360*j/F); prints one JSON line with the device-synchronised
 //          time of K steps for Render() alone and for Render()+ReadRenderBuf() (the reference's end-to-end path).
 #include "gvdb.h"
+#ifdef GVDBX_SHIM
+// ref_harness_x: the same harness with the product's Level-A shim (include/gvdbx_shim.h, the subclass INTEGRATION.md gives to
+// a GVDB maintainer) compiled in and libgvdbx.so linked next to the UNMODIFIED libgvdb.so — one process, one CUcontext (the
+// reference's own).  --gvdbx renders every requested mode twice, Render() and RenderX(), into the reference's mRenderBuf
+// and compares the bytes.  The plain ref_harness never links the product.
+#include "gvdbx_shim.h"
+#endif
 #include <cuda.h>
 #include <chrono>
 #include <cstdio>
@@ -38,6 +45,18 @@ static double now_s()
 {
     return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
+// order-sensitive checksum over 32-bit words (tests/common.py::cksum32 computes the same with numpy): proves that the volume the
+// reference built itself (pools, atlas after its own UpdateApron) is byte-identical to the one the product imports, without
+// writing gigabytes to disk
+static void cksum32(const void* p, size_t bytes, unsigned long long out[2])
+{
+    const uint32_t* w = (const uint32_t*)p;
+    const size_t n = bytes / 4;
+    unsigned long long s1 = 0, s2 = 0;
+    #pragma omp parallel for reduction(+ : s1, s2)
+    for (long long i = 0; i < (long long)n; i++) { s1 += w[i]; s2 += (unsigned long long)w[i] * (unsigned long long)(i % 65521 + 1); }
+    out[0] = s1; out[1] = s2;
+}
 static void dump(const std::string& path, const void* p, size_t n)
 {
     FILE* f = fopen(path.c_str(), "wb");
@@ -54,6 +73,7 @@ static const Mode kModes[] = {
     {"tricubic", SHADE_TRICUBIC, "oracleHitTricubic", 0}, {"emptyskip", SHADE_EMPTYSKIP, "oracleHitEmptySkip", 0},
     {"section2d", SHADE_SECTION2D, "", 0}, {"section3d", SHADE_SECTION3D, "", 0},
     {"deepshadow", SHADE_VOLUME, "oracleDeepShadow", 1}, {"deepspp", SHADE_VOLUME, "oracleDeepSample", 2},
+    {"voxelid", SHADE_VOXEL, "oracleVoxelId", 0},            // voxel int3 + depth t + leaf id through the instrumented brick function (never a default mode)
     {"custom", SHADE_TRILINEAR, "raycast_kernel", 3},     // the reference's gRenderKernel sample (render_custom.cubin) through RenderKernel
 };
 
@@ -67,7 +87,7 @@ int main(int argc, char** argv)
     int have_xf = 0, use_dbuf = 0, nrays = 0;
     std::string savevbx = "";
     int cfg[5] = {3, 3, 3, 3, 3};                  // Configure(q4..q0): log2 dims from the top level down to the brick
-    int lightdump = 0, use_color = 0;               // --color: second channel T_UCHAR4 + SetColorChannel (gFluidSurface / gSprayDeposit usage)
+    int lightdump = 0, use_color = 0, gvdbx = 0;               // --color: second channel T_UCHAR4 + SetColorChannel (gFluidSurface / gSprayDeposit usage)
     std::string usermodule = "";                   // --module: render the native modes with the kernels of this cubin (RenderKernel)
     for (int i = 3; i < argc; i++) {
         std::string a = argv[i];
@@ -78,6 +98,7 @@ int main(int argc, char** argv)
         else if (a == "--nodump") nodump = 1;
         else if (a == "--lightdump") lightdump = 1;
         else if (a == "--color") use_color = 1;
+        else if (a == "--gvdbx") gvdbx = 1;
         else if (a == "--module" && i + 1 < argc) { usermodule = argv[++i]; hits = 0; }        // images + ScnInfo + VDBInfo only (no pools / atlas: large volumes)
         else if (a == "--shadow" && i + 1 < argc) shadow = atoi(argv[++i]);
         else if (a == "--hits" && i + 1 < argc) hits = atoi(argv[++i]);
@@ -106,11 +127,19 @@ int main(int argc, char** argv)
     fprintf(stderr, "[ref] preset %s: %d bricks (gen %.2fs)\n", P.name, S.nbricks, t_gen);
 
     // ---- reference library
+#ifdef GVDBX_SHIM
+    VolumeGVDBX gvdb;
+#else
     VolumeGVDB gvdb;
+    if (gvdbx) { fprintf(stderr, "--gvdbx needs ref_harness_x (built with the shim)\n"); return 1; }
+#endif
     gvdb.SetDebug(false);
     gvdb.SetVerbose(false);
-    gvdb.SetCudaDevice(0);          // explicit device: never GVDB_DEV_FIRST (cuGLGetDevices)
+    gvdb.SetCudaDevice(0);          // explicit device: never GVDB_DEV_FIRST (cuGLGetDevices) -> cuCtxCreate'd context
     gvdb.Initialize();
+#ifdef GVDBX_SHIM
+    if (gvdbx && !gvdb.InitX(0)) { fprintf(stderr, "InitX failed\n"); return 6; }
+#endif
 
     // ---- CPU topology build (timed: the reference's host-side baseline)
     t0 = now_s();
@@ -252,6 +281,13 @@ int main(int argc, char** argv)
             gvdb.SetModule(bmod);
             scn->SetShading(shade);
         }
+#ifdef GVDBX_SHIM
+        if (gvdbx) {
+            if (kind != 0) gvdb.SetModule();
+            gvdbx_set_option(gvdb.x(), GVDBX_OPT_DEEP_SHADOW, kind == 1);
+            gvdbx_set_option(gvdb.x(), GVDBX_OPT_SPP, kind == 2 ? spp : 1);
+        }
+#endif
         std::vector<unsigned char> frame((size_t)w * h * 4);
         auto set_cam = [&](int j) {
             cam->setOrbit(Vector3DF(P.cam_angs[0] + 360.0f * (float)j / (float)orbit, P.cam_angs[1], P.cam_angs[2]),
@@ -260,6 +296,9 @@ int main(int argc, char** argv)
         // kind 1: the composed kernel writes RGBA8 into buffer 0; kind 2: `spp` per-sample launches into the float buffer
         // (the host-side average is not part of the timed region: it favours the reference)
         auto render = [&]() {
+#ifdef GVDBX_SHIM
+            if (gvdbx) { gvdb.RenderX(shade, 0, 0); return; }       // kind 1 / 2: GVDBX_OPT_DEEP_SHADOW / GVDBX_OPT_SPP set below
+#endif
             if (kind == 0) gvdb.Render(shade, 0, 0);
             else if (kind == 1) gvdb.RenderKernel(bfn, 0, 0);
             else for (int sidx = 0; sidx < spp; sidx++) { scn->SetSample(sidx); scn->SetFrame(spp); gvdb.RenderKernel(bfn, 0, 3); }
@@ -275,8 +314,8 @@ int main(int argc, char** argv)
         unsigned long long sum = 0;
         for (size_t i = 0; i < frame.size(); i += 97) sum += frame[i];
         printf("{\"preset\":\"%s\",\"bricks\":%d,\"width\":%d,\"height\":%d,\"shade\":%d,\"orbit\":%d,\"steps\":%d,\"warmup\":%d,"
-               "\"render_s\":%.6f,\"e2e_s\":%.6f,\"topology_build_s\":%.6f,\"scene_gen_s\":%.3f,\"checksum\":%llu}\n",
-               preset.c_str(), S.nbricks, w, h, shade, orbit, steps, warmup, t_kernel, t_e2e, t_cfg + t_act + t_fin, t_gen, sum);
+               "\"render_s\":%.6f,\"e2e_s\":%.6f,\"topology_build_s\":%.6f,\"scene_gen_s\":%.3f,\"checksum\":%llu,\"gvdbx\":%d}\n",
+               preset.c_str(), S.nbricks, w, h, shade, orbit, steps, warmup, t_kernel, t_e2e, t_cfg + t_act + t_fin, t_gen, sum, gvdbx);
         scene_free(&S);
         return 0;
     }
@@ -287,7 +326,23 @@ int main(int argc, char** argv)
         dump(outdir + "/vdbinfo.bin", gvdb.getVDBInfo(), 1232);
         FILE* mf = fopen((outdir + "/meta.txt").c_str(), "w");
         fprintf(mf, "preset %s\nbricks %d\nlevels %d\natlas_res %d %d %d\nwidth %d\nheight %d\n", P.name, S.nbricks, gvdb.mPool->getNumLevels(), ares.x, ares.y, ares.z, w, h);
+        // checksums instead of the bytes: pools as the reference holds them, atlas after the reference's own UpdateApron
+        gvdb.FetchPoolCPU();
+        unsigned long long ck[2];
+        for (int g = 0; g < 2; g++) for (int l = 0; l < gvdb.mPool->getNumLevels(); l++) {
+            uint64 cnt = gvdb.mPool->getPoolTotalCnt(g, l), wid = gvdb.mPool->getPoolWidth(g, l);
+            cksum32(cnt * wid ? gvdb.mPool->getPoolCPU(g, l) : "", cnt * wid, ck);
+            fprintf(mf, "cksum_pool %d %d %llu %llu %llu\n", g, l, (unsigned long long)(cnt * wid), ck[0], ck[1]);
+        }
+        {
+            std::vector<float> back(atexels);
+            for (int z = 0; z < ares.z; z++)
+                gvdb.mPool->AtlasRetrieveSlice(0, z, 0, 0, (uchar*)(back.data() + (size_t)z * ares.x * ares.y));
+            cksum32(back.data(), atexels * sizeof(float), ck);
+            fprintf(mf, "cksum_atlas %llu %llu %llu\n", (unsigned long long)(atexels * sizeof(float)), ck[0], ck[1]);
+        }
         fclose(mf);
+        dump(outdir + "/transfer.bin", scn->getTransferFunc(), 16384 * 16);
     }
     if (!nodump && !lightdump) {
         gvdb.PrepareVDB();
@@ -327,7 +382,7 @@ int main(int argc, char** argv)
     const float cN = 0.5f * (float)P.N;
     std::vector<float> sample((size_t)w * h * 4), accum((size_t)w * h * 4);
     for (const Mode& m : kModes) {
-        bool want = modes.empty() ? (m.shade == P.shade && m.kind == 0)
+        bool want = modes.empty() ? (m.shade == P.shade && m.kind == 0 && strcmp(m.name, "voxelid") != 0)
                                   : (("," + modes + ",").find(std::string(",") + m.name + ",") != std::string::npos);
         if (!want) continue;
         // section plane: 2D = centre + (u,0,v) * half extent (slice_norm is a per-axis scale there); 3D = tilted plane
@@ -411,8 +466,35 @@ int main(int argc, char** argv)
                 if (!nodump) dump(outdir + "/hit_" + m.name + ".f32", hitbuf.data(), hitbuf.size() * sizeof(float));
             }
         }
-        char buf[256];
-        snprintf(buf, sizeof buf, "%s\"%s\":{\"ms_median\":%.4f,\"ms_min\":%.4f,\"read_ms\":%.4f,\"frames\":%d}", first ? "" : ",", m.name, med, mn, read_ms, frames);
+        long xdiff = -1, xnonbg = 0;
+        double xms = 0;
+#ifdef GVDBX_SHIM
+        if (gvdbx && (m.kind == 0 || m.kind == 1 || m.kind == 2) && usermodule.empty()) {
+            // the same frame through the shim: RenderX() into the reference's own render buffer 0, read back by the
+            // reference's own ReadRenderBuf
+            gvdbx_set_option(gvdb.x(), GVDBX_OPT_DEEP_SHADOW, m.kind == 1);
+            gvdbx_set_option(gvdb.x(), GVDBX_OPT_SPP, m.kind == 2 ? spp : 1);
+            std::vector<unsigned char> imgx((size_t)w * h * 4, 0x5A);
+            cuMemsetD8(gvdb.mRenderBuf[0].gpu, 0x5A, (size_t)w * h * 4);
+            gvdb.RenderX(m.shade, 0, 0);
+            cuCtxSynchronize();
+            std::vector<double> xs;
+            for (int i = 0; i < std::max(frames, 1); i++) { double a0 = now_s(); gvdb.RenderX(m.shade, 0, 0); cuCtxSynchronize(); xs.push_back((now_s() - a0) * 1e3); }
+            std::sort(xs.begin(), xs.end());
+            xms = xs[xs.size() / 2];
+            gvdb.ReadRenderBuf(0, imgx.data());
+            xdiff = 0;
+            for (size_t i = 0; i < imgx.size(); i += 4) {
+                if (memcmp(&imgx[i], &img[i], 4)) xdiff++;
+                if (memcmp(&img[i], &img[0], 4)) xnonbg++;
+            }
+            if (!nodump) dump(outdir + "/outx_" + m.name + ".rgba", imgx.data(), imgx.size());
+            fprintf(stderr, "[ref] %s: RenderX %.3f ms/frame, %ld of %d pixels differ from Render()\n", m.name, xms, xdiff, w * h);
+        }
+#endif
+        char buf[384];
+        snprintf(buf, sizeof buf, "%s\"%s\":{\"ms_median\":%.4f,\"ms_min\":%.4f,\"read_ms\":%.4f,\"frames\":%d,\"x_mismatch\":%ld,\"x_nonbg\":%ld,\"x_ms_median\":%.4f}",
+                 first ? "" : ",", m.name, med, mn, read_ms, frames, xdiff, xnonbg, xms);
         timing += buf; first = false;
         fprintf(stderr, "[ref] %s: %.3f ms/frame (min %.3f), %.2f Mrays/s\n", m.name, med, mn, w * (double)h / med * 1e-3);
     }

@@ -301,8 +301,8 @@ static inline int scene_get_preset(const char* name, scene_preset* p)
         scn_set3(p->cam_angs, 60.f, 20.f, 0.f); scn_set3(p->cam_target, 1024.f * s, 1024.f * s, 1024.f * s); p->cam_dist = 3600.f * s;
         scn_set3(p->light_target, 1056.f * s, -160.f * s, 400.f * s); p->light_dist = 1600.f * s;
         scn_set3(p->thresh, 0.5f, 0.f, 1.f);
-    } else if (!strncmp(name, "cfg4", 4)) {     /* noise cloud, deep volume (SHADE_VOLUME), 3840x2160 */
-        p->kind = SCN_KIND_CLOUD; p->N = tiny ? 64 : (small ? 128 : 512);
+    } else if (!strncmp(name, "cfg4", 4)) {     /* noise cloud of radius 400 in a 1024^3 index space, deep volume (SHADE_VOLUME), 3840x2160 */
+        p->kind = SCN_KIND_CLOUD; p->N = tiny ? 64 : (small ? 128 : 1024);
         float s = p->N / 512.f;
         p->a = 200.f * s; p->b = 0.6f; p->c = 64.f * (tiny ? 0.25f : (small ? 0.5f : 1.f));
         p->width = tiny ? 96 : (small ? 384 : 3840); p->height = tiny ? 54 : (small ? 216 : 2160);

@@ -53,3 +53,17 @@ def tolerance_ok(mine, ref, max_over1_frac=2e-3, min_psnr=60.0):
     d = np.abs(mine.astype(np.int32) - ref.astype(np.int32)).max(axis=2)
     over1 = float((d > 1).mean())
     return (over1 == 0.0) or (psnr(mine, ref) >= min_psnr and over1 <= max_over1_frac), over1, psnr(mine, ref)
+
+
+def cksum32(a, chunk=1 << 24):
+    """(sum of 32-bit words, sum of word_i * (i % 65521 + 1)) mod 2^64 — the checksum oracle/ref_harness.cpp prints for the
+    pools and the atlas of a --lightdump run."""
+    w = np.ascontiguousarray(a).reshape(-1).view(np.uint8)
+    w = w[: w.size // 4 * 4].view(np.uint32)
+    s1 = s2 = 0
+    for i in range(0, w.size, chunk):
+        c = w[i:i + chunk].astype(np.uint64)
+        k = (np.arange(i, i + c.size, dtype=np.uint64) % np.uint64(65521)) + np.uint64(1)
+        s1 = (s1 + int(c.sum(dtype=np.uint64))) & 0xFFFFFFFFFFFFFFFF
+        s2 = (s2 + int((c * k).sum(dtype=np.uint64))) & 0xFFFFFFFFFFFFFFFF
+    return s1, s2

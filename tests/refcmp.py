@@ -22,7 +22,9 @@ MODES = {"voxel": 0, "trilinear": 4, "levelset": 6, "deep": 7}
 MODES2 = {"tricubic": (5, 0, 1), "emptyskip": (3, 0, 1), "section2d": (1, 0, 1), "section3d": (2, 0, 1),
           "deepshadow": (7, 1, 1), "deepspp": (7, 0, 4)}
 CUSTOM = "custom"          # the reference's gRenderKernel sample kernel (user kernel through RenderKernel)
+VOXELID = "voxelid"        # SHADE_VOXEL through the instrumented brick function of oracle_kernels.cu: voxel int3, depth t, leaf id
 ALL_SHADE = dict(MODES, **{k: v[0] for k, v in MODES2.items()})
+ALL_SHADE[VOXELID] = 0
 
 
 def have_ref():
@@ -30,10 +32,16 @@ def have_ref():
                ("ref_harness", "libgvdb.so", "cuda_gvdb_module.cubin", "cuda_gvdb_copydata.ptx"))
 
 
+def have_ref_x():
+    return have_ref() and os.path.exists(os.path.join(REF_DIR, "ref_harness_x"))
+
+
 def run_ref(preset, outdir, modes=None, size=None, frames=1, warmup=0, nodump=False, shadow=None, hits=True, timeout=1800,
-            xform=None, dbuf=False, raytrace=0, savevbx=None, config=None, module=None, color=False):
-    """Run the reference harness; returns its timing dict."""
-    cmd = ["./ref_harness", preset, os.path.abspath(outdir)]
+            xform=None, dbuf=False, raytrace=0, savevbx=None, config=None, module=None, color=False, gvdbx=False, lightdump=False,
+            extra=None):
+    """Run the reference harness; returns its timing dict.  gvdbx=True: ref_harness_x, the same harness with the product's
+    Level-A shim (include/gvdbx_shim.h) linked in — every mode is rendered by Render() AND RenderX() in one process."""
+    cmd = ["./ref_harness_x" if gvdbx else "./ref_harness", preset, os.path.abspath(outdir)]
     if modes:
         cmd += ["--modes", ",".join(modes)]
     if size:
@@ -57,6 +65,12 @@ def run_ref(preset, outdir, modes=None, size=None, frames=1, warmup=0, nodump=Fa
         cmd += ["--module", os.path.abspath(module)]
     if color:
         cmd.append("--color")
+    if gvdbx:
+        cmd.append("--gvdbx")
+    if lightdump:
+        cmd.append("--lightdump")
+    if extra:
+        cmd += list(extra)
     r = subprocess.run(cmd, cwd=REF_DIR, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=timeout)
     if r.returncode != 0:
         raise RuntimeError(f"ref_harness failed ({r.returncode}): {r.stderr[-2000:]}")
@@ -88,7 +102,7 @@ def load_dump(d):
         (out["pool0"] if g == 0 else out["pool1"])[l] = b
     out["scn"], out["rgba"], out["hit"] = {}, {}, {}
     w, h = meta["width"], meta["height"]
-    for m in list(MODES) + list(MODES2) + [CUSTOM]:
+    for m in list(MODES) + list(MODES2) + [CUSTOM, VOXELID]:
         p = os.path.join(d, f"scninfo_{m}.bin")
         if os.path.exists(p):
             out["scn"][m] = open(p, "rb").read()
@@ -107,6 +121,53 @@ def load_dump(d):
     if os.path.exists(q):
         out["scn_raytrace"] = open(q, "rb").read()
     return out
+
+
+def load_lightdump(d):
+    """dump of a --lightdump run (large volumes): VDBInfo, ScnInfo + image (+ hit buffer) per mode, and CHECKSUMS of the pools
+    and of the atlas instead of their bytes (tests/common.py::cksum32)."""
+    meta = {"cksum_pool": {}}
+    for line in open(os.path.join(d, "meta.txt")):
+        t = line.split()
+        if t[0] == "cksum_pool":
+            meta["cksum_pool"][(int(t[1]), int(t[2]))] = (int(t[3]), int(t[4]), int(t[5]))
+        elif t[0] == "cksum_atlas":
+            meta["cksum_atlas"] = (int(t[1]), int(t[2]), int(t[3]))
+        elif t[0] == "atlas_res":
+            meta["atlas_res"] = tuple(int(x) for x in t[1:4])
+        elif t[0] in ("bricks", "levels", "width", "height"):
+            meta[t[0]] = int(t[1])
+        else:
+            meta[t[0]] = t[1]
+    out = {"meta": meta, "dir": d, "vdbinfo": open(os.path.join(d, "vdbinfo.bin"), "rb").read(), "scn": {}, "rgba": {}, "hit": {}}
+    out["transfer"] = np.fromfile(os.path.join(d, "transfer.bin"), dtype=np.float32)
+    w, h = meta["width"], meta["height"]
+    for m in list(MODES) + list(MODES2) + [CUSTOM, VOXELID]:
+        p = os.path.join(d, f"scninfo_{m}.bin")
+        if os.path.exists(p):
+            out["scn"][m] = open(p, "rb").read()
+            out["rgba"][m] = np.fromfile(os.path.join(d, f"out_{m}.rgba"), dtype=np.uint8).reshape(h, w, 4)
+            hp = os.path.join(d, f"hit_{m}.f32")
+            if os.path.exists(hp):
+                out["hit"][m] = np.fromfile(hp, dtype=np.float32).reshape(h, w, 8)
+    return out
+
+
+def same_volume(light, vol):
+    """the volume the reference built itself (checksums of a --lightdump run) == the volume `vol` the product imports"""
+    from common import cksum32, mask_vdbinfo
+    bad = []
+    lv = light["meta"]["levels"]
+    if not np.array_equal(mask_vdbinfo(light["vdbinfo"], lv), mask_vdbinfo(bytes(vol["vdbinfo"]), lv)):
+        bad.append("vdbinfo")
+    for (g, l), (nbytes, s1, s2) in light["meta"]["cksum_pool"].items():
+        a = (vol["pool0"] if g == 0 else vol["pool1"]).get(l, np.zeros(0, np.uint8))
+        if a.nbytes != nbytes or cksum32(a) != (s1, s2):
+            bad.append(f"pool{g}_L{l}")
+    nbytes, s1, s2 = light["meta"]["cksum_atlas"]
+    if vol["atlas"].nbytes != nbytes or cksum32(vol["atlas"]) != (s1, s2):
+        bad.append("atlas")
+    return bad
 
 
 def make_renderer(dump, pkg, device=0):
@@ -156,6 +217,18 @@ def render_mine(r, dump, mode, sampler, debug=False):
 def psnr(a, b):
     mse = np.mean((a.astype(np.float64) - b.astype(np.float64)) ** 2)
     return 99.0 if mse == 0 else float(10 * np.log10(255.0 ** 2 / mse))
+
+
+def compare_voxel_ids(dbg, ref):
+    """north_star: voxel-hit IDs and depths bit-exact.  `dbg` = gvdbx_render_debug output [h, w, 12] (float view), `ref` =
+    oracleVoxelId output [h, w, 8]: {hit.xyz, t} {voxel.xyz, leaf} (integers as bit patterns).  Returns mismatch counts."""
+    d, r = dbg.view(np.uint32), ref.view(np.uint32)
+    hitpix = ref[:, :, 2] != np.float32(1.0e10)
+    return {"hit_pixels": int(hitpix.sum()),
+            "hit_mismatch": int((d[:, :, 0:3] != r[:, :, 0:3]).any(axis=2).sum()),
+            "depth_mismatch": int((d[:, :, 3] != r[:, :, 3]).sum()),
+            "voxel_mismatch": int((d[:, :, 8:11] != r[:, :, 4:7]).any(axis=2).sum()),
+            "leaf_mismatch": int((d[:, :, 7] != r[:, :, 7]).sum())}
 
 
 def compare(dump, pkg, modes=None, device=0, verbose=True):

@@ -682,7 +682,7 @@ def test_live_reference_color_channel(pkg, torch_cuda, tmp_path):
     surface modes, every deep sample is multiplied by its voxel's colour.  The unmodified reference renders such a
     volume now; with its colour atlas imported every mode must match bit for bit, and differ from the uncoloured image."""
     d = str(tmp_path / "dump")
-    refcmp.run_ref("cfg4_small", d, modes=list(MODES) + ["tricubic"], size=(240, 160), color=True)
+    refcmp.run_ref("cfg4_small", d, modes=list(MODES) + ["tricubic", "section3d", "section2d", "emptyskip"], size=(240, 160), color=True)
     dump = refcmp.load_dump(d)
     assert "color" in dump and np.frombuffer(dump["vdbinfo"], np.uint8)[685] == 1          # VDBInfo.clr_chan
     res = refcmp.compare(dump, pkg, list(MODES), verbose=False)
@@ -694,12 +694,14 @@ def test_live_reference_color_channel(pkg, torch_cuda, tmp_path):
         # may contract differently, so the float comparison is a tolerance here
         assert res[m]["tex"].get("raw_clr_max_abs", 0.0) < 1e-5, (m, res[m]["tex"])
         assert res[m]["linear"]["rgba_over1_pixels"] <= 2e-3 * res[m]["linear"]["pixels"]
-    res2 = refcmp.compare2(dump, pkg, ["tricubic"], verbose=False)
-    assert res2["tricubic"]["tex"]["rgba_mismatch_pixels"] == 0
+    res2 = refcmp.compare2(dump, pkg, ["tricubic", "section3d", "section2d", "emptyskip"], verbose=False)
+    for m in ("tricubic", "section3d", "section2d", "emptyskip"):      # section 3-D: plane colour AND surface colour are tinted
+        assert res2[m]["tex"]["rgba_mismatch_pixels"] == 0, (m, res2[m]["tex"])
     # the colour really changes the picture, and a volume that announces a colour channel cannot be rendered without it
     d0 = str(tmp_path / "plain")
-    refcmp.run_ref("cfg4_small", d0, modes=["trilinear", "deep"], size=(240, 160), hits=False)
+    refcmp.run_ref("cfg4_small", d0, modes=["trilinear", "deep", "section3d"], size=(240, 160), hits=False)
     plain = refcmp.load_dump(d0)
+    assert not np.array_equal(plain["rgba"]["section3d"], dump["rgba"]["section3d"])
     assert not np.array_equal(plain["rgba"]["trilinear"], dump["rgba"]["trilinear"])
     assert not np.array_equal(plain["rgba"]["deep"], dump["rgba"]["deep"])
     r = pkg.Renderer(0)
@@ -710,3 +712,106 @@ def test_live_reference_color_channel(pkg, torch_cuda, tmp_path):
     with pytest.raises(pkg.GvdbxError):
         r.render(dump["scn"]["trilinear"], 4, out.data_ptr())
     r.close()
+
+
+# ------------------------------------------------------------------------------------------------ Level-A shim, in process
+NATIVE8 = ["voxel", "section2d", "section3d", "emptyskip", "trilinear", "tricubic", "levelset", "deep"]
+
+
+@pytest.mark.skipif(not refcmp.have_ref_x(), reason="oracle/_ref/ref_harness_x not built")
+@pytest.mark.parametrize("preset,color", [("cfg1_small", False), ("cfg4_small", False), ("cfg4_small", True), ("cfg3_small", False)])
+def test_level_a_shim_inside_reference(tmp_path, preset, color):
+    """SURVEY 8b level A, the graded boundary: INTEGRATION.md's VolumeGVDBX subclass (include/gvdbx_shim.h) compiled against
+    the UNMODIFIED libgvdb.so, libgvdbx.so loaded into the same process.  The reference runs under SetCudaDevice(0), i.e. in
+    the CUcontext it creates with cuCtxCreate; its device pools (getVDBInfo()), its atlas CUarray (gvdbx_import_atlas_array),
+    its colour CUarray (gvdbx_import_color_array) and its render buffer are handed over as they are.  RenderX() must leave
+    in mRenderBuf[0] exactly the bytes Render() does — all eight modes of Render()'s switch + the two composed modes."""
+    d = str(tmp_path / "dump")
+    t = refcmp.run_ref(preset, d, modes=NATIVE8 + ["deepshadow", "deepspp"], size=(233, 151), gvdbx=True, color=color, nodump=True, hits=False)
+    for m in NATIVE8 + ["deepshadow", "deepspp"]:
+        r = t["render"][m]
+        assert r["x_mismatch"] == 0, (m, r)
+        if m != "section2d":
+            assert r["x_nonbg"] > 500, (m, r)          # something is in view
+
+
+# ------------------------------------------------------------------------------------------------ voxel id / depth
+@pytest.mark.skipif(not refcmp.have_ref(), reason="oracle/_ref not built")
+@pytest.mark.parametrize("preset,size,shadow", [("cfg3_small", None, 0), ("cfg3_small", (301, 203), 1), ("cfg1_small", None, 1)])
+def test_voxel_id_and_depth_bit_exact_vs_reference(pkg, torch_cuda, tmp_path, preset, size, shadow):
+    """north_star: "voxel-hit IDs and depths bit-exact in SHADE_VOXEL mode".  The native kernel keeps both internal, so the
+    reference side is SURVEY 8c (i): raySurfaceVoxelBrick restated with int3(vmin), dda.t.x and the leaf id as extra outputs,
+    run under the reference's own rayCast through RenderKernel (oracle_kernels.cu::oracleVoxelId).  Compared bit for bit
+    with gvdbx_render_debug's {t, leaf, voxel} for both samplers (occupancy bits on and off)."""
+    d = str(tmp_path / "dump")
+    refcmp.run_ref(preset, d, modes=["voxel", "voxelid"], size=size, shadow=shadow)
+    dump = refcmp.load_dump(d)
+    ref = dump["hit"]["voxelid"]
+    # the instrumented brick function reproduces the plain one's hit point (same traversal, same arithmetic)
+    assert np.array_equal(ref[:, :, 0:3].view(np.uint32), dump["hit"]["voxel"][:, :, 0:3].view(np.uint32))
+    r = refcmp.make_renderer(dump, pkg)
+    for sampler in (0, 1):
+        for vmask in (1, 0):
+            r.set_option(10, vmask)
+            img, dbg, _ = refcmp.render_mine(r, dump, "voxel", sampler, debug=True)
+            assert np.array_equal(img, dump["rgba"]["voxel"])
+            st = refcmp.compare_voxel_ids(dbg, ref)
+            assert st["hit_pixels"] > 1000, st
+            assert st["hit_mismatch"] == 0 and st["depth_mismatch"] == 0 and st["voxel_mismatch"] == 0 and st["leaf_mismatch"] == 0, (sampler, vmask, st)
+    r.set_option(10, 1)
+    r.close()
+
+
+# ------------------------------------------------------------------------------------------------ BASELINE sizes, live
+FULL_CASES = [("cfg1", ["trilinear"]), ("cfg2", ["levelset"]), ("cfg3", ["voxel", "voxelid"]), ("cfg4", ["deep", "deepshadow"])]
+
+
+@pytest.mark.timeout(1200)
+@pytest.mark.skipif(not refcmp.have_ref(), reason="oracle/_ref not built")
+@pytest.mark.parametrize("preset,modes", FULL_CASES)
+def test_full_size_bit_exact_vs_live_reference(scenes, pkg, torch_cuda, tmp_path, preset, modes):
+    """Every BASELINE.json config at the size it is BENCHMARKED at (cfg1 1024x768 trilinear, cfg2 1920x1080 level set — the
+    frame bench.py times —, cfg3 3840x2160 voxel incl. voxel id / depth, cfg4 3840x2160 deep and deep + shadow on the 1024^3
+    volume): the UNMODIFIED reference builds the volume itself and renders it now; the product renders the volume of the CPU
+    restatement, proven byte-identical to the reference's through checksums of pools and atlas (after the reference's own
+    UpdateApron).  Required: 0 differing pixels, hit point / normal / voxel id / depth / raw deep colour bit for bit."""
+    torch = torch_cuda
+    d = str(tmp_path / "dump")
+    refcmp.run_ref(preset, d, modes=modes, lightdump=True, hits=True, timeout=1100)
+    light = refcmp.load_lightdump(d)
+    p, vol, r = scenes(preset)
+    w, h = light["meta"]["width"], light["meta"]["height"]
+    assert (w, h) == (p.width, p.height)
+    assert refcmp.same_volume(light, vol) == []
+    assert np.array_equal(light["transfer"], np.asarray(vol["transfer"], np.float32).reshape(-1))
+    for m in modes:
+        shade = refcmp.ALL_SHADE[m]
+        _, dshadow, spp = refcmp.MODES2.get(m, (0, 0, 1))
+        r.set_deep_shadow(dshadow)
+        try:
+            img = _render(torch, r, light["scn"][m], shade, w, h, 0)
+            ref = light["rgba"][m]
+            assert np.array_equal(img, ref), (m, int((img != ref).any(axis=2).sum()))
+            assert (ref != ref[0, 0]).any(axis=2).mean() > 0.02
+            if m in light["hit"]:
+                _, dbg = _render(torch, r, light["scn"][m], shade, w, h, 0, debug=True)
+                rh = light["hit"][m]
+                if m == "voxelid":
+                    st = refcmp.compare_voxel_ids(dbg, rh)
+                    assert st["hit_mismatch"] == 0 and st["depth_mismatch"] == 0 and st["voxel_mismatch"] == 0 and st["leaf_mismatch"] == 0, st
+                elif m == "deep":
+                    assert np.array_equal(dbg[:, :, 0:4].view(np.uint32), rh[:, :, 0:4].view(np.uint32))
+                else:
+                    assert np.array_equal(dbg[:, :, 0:3].view(np.uint32), rh[:, :, 0:3].view(np.uint32))
+                    assert np.array_equal(dbg[:, :, 4:7].view(np.uint32), rh[:, :, 4:7].view(np.uint32))
+                del dbg, rh
+        finally:
+            r.set_deep_shadow(0)
+    # linear sampler at full size: voxel bit-exact, filtered modes within the north_star tolerance
+    m = modes[0]
+    lin = _render(torch, r, light["scn"][m], refcmp.ALL_SHADE[m], w, h, 1)
+    if m == "voxel":
+        assert np.array_equal(lin, light["rgba"][m])
+    else:
+        ok, over1, ps = tolerance_ok(lin, light["rgba"][m])
+        assert ok, (m, over1, ps)
