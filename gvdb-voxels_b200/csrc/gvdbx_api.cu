@@ -64,16 +64,18 @@ struct gvdbx_ctx {
     bool                have_atlas = false;
     cudaArray_t         own_array = nullptr;
     cudaTextureObject_t tex = 0;
+    cudaTextureObject_t tex_point = 0;  // same array, point filter: exact texel values for the import kernels
     cudaSurfaceObject_t surf = 0;       // same array, for UpdateApron (needs CUDA_ARRAY3D_SURFACE_LDST like the reference's volOut)
-    cudaArray_t         array = nullptr; // the array both objects sit on (caller's or own_array)
-    float*              d_bricks = nullptr;
-    GxRange*            d_range = nullptr;      // per brick slot
+    cudaArray_t         array = nullptr; // the array the objects sit on (caller's or own_array)
+    float*              d_bricks = nullptr;     // brick-major copy, one block per leaf: built on first use of the linear sampler
+    int                 brick_dim = GX_BRICK_DIM, brick_stride = GX_BRICK_STRIDE;
     GxRange*            d_leaf_range = nullptr; // per leaf (valid when topology and atlas are both imported)
+    int*                d_err = nullptr;        // error bits raised by the import kernels
+    cudaEvent_t         build_ev = nullptr;     // orders lazily built tables (occupancy bits, brick-major copy) against all lanes
     unsigned long long* d_vmask = nullptr;      // SHADE_VOXEL occupancy bits per leaf for THRESH == vmask_thresh
     uint32_t            vmask_thresh_bits = 0;
     bool                vmask_valid = false;
     int                 use_vmask = 1;
-    size_t              nslots = 0;
     int                 cull = 1;
     int                 ares[3] = {0, 0, 0};
     // colour channel (VDBInfo::clr_chan): uchar4 atlas with the slot layout of channel 0
@@ -150,16 +152,23 @@ extern "C" int gvdbx_create(gvdbx_t** out, int cuda_device, void* cuda_stream)
     h->base_stream = h->stream;
     if (cudaMalloc(&h->d_counters, 8 * sizeof(unsigned long long)) != cudaSuccess) { delete h; return GVDBX_E_CUDA; }
     cudaMemset(h->d_counters, 0, 8 * sizeof(unsigned long long));
+    if (cudaMalloc(&h->d_err, sizeof(int)) != cudaSuccess) { cudaFree(h->d_counters); delete h; return GVDBX_E_CUDA; }
+    cudaMemset(h->d_err, 0, sizeof(int));
     *out = h;
     return GVDBX_OK;
 }
 
-static void gx_free_topology(gvdbx_t* h)
+static void gx_free_derived(gvdbx_t* h)       // tables that depend on topology AND atlas
 {
     if (h->d_leaf_range) cudaFree(h->d_leaf_range);
-    h->d_leaf_range = nullptr;
     if (h->d_vmask) cudaFree(h->d_vmask);
-    h->d_vmask = nullptr; h->vmask_valid = false;
+    if (h->d_bricks) cudaFree(h->d_bricks);
+    h->d_leaf_range = nullptr; h->d_vmask = nullptr; h->d_bricks = nullptr;
+    h->vmask_valid = false;
+}
+static void gx_free_topology(gvdbx_t* h)
+{
+    gx_free_derived(h);
     for (int l = 0; l < GX_MAXLEV; l++) {
         if (h->d_child[l]) cudaFree(h->d_child[l]);
         if (h->d_npos[l]) cudaFree(h->d_npos[l]);
@@ -171,16 +180,13 @@ static void gx_free_topology(gvdbx_t* h)
 }
 static void gx_free_atlas(gvdbx_t* h)
 {
+    gx_free_derived(h);
     if (h->tex) cudaDestroyTextureObject(h->tex);
+    if (h->tex_point) cudaDestroyTextureObject(h->tex_point);
     if (h->surf) cudaDestroySurfaceObject(h->surf);
     h->surf = 0; h->array = nullptr;
     if (h->own_array) cudaFreeArray(h->own_array);
-    if (h->d_bricks) cudaFree(h->d_bricks);
-    if (h->d_range) cudaFree(h->d_range);
-    if (h->d_leaf_range) cudaFree(h->d_leaf_range);
-    h->d_leaf_range = nullptr;
-    h->vmask_valid = false;
-    h->tex = 0; h->own_array = nullptr; h->d_bricks = nullptr; h->d_range = nullptr; h->have_atlas = false;
+    h->tex = 0; h->tex_point = 0; h->own_array = nullptr; h->have_atlas = false;
 }
 
 extern "C" int gvdbx_destroy(gvdbx_t* h)
@@ -197,6 +203,8 @@ extern "C" int gvdbx_destroy(gvdbx_t* h)
     if (h->d_transfer) cudaFree(h->d_transfer);
     for (float4* p : h->deep_lut) if (p) cudaFree(p);
     if (h->d_counters) cudaFree(h->d_counters);
+    if (h->d_err) cudaFree(h->d_err);
+    if (h->build_ev) cudaEventDestroy(h->build_ev);
     }
     delete h;
     return GVDBX_OK;
@@ -227,49 +235,113 @@ extern "C" int gvdbx_set_option(gvdbx_t* h, int option, int value)
     return GVDBX_OK;
 }
 
-// per-leaf value ranges need both the leaf table (topology) and the slot ranges (atlas): built by whichever comes last
+// error bits of the import kernels -> return code (synchronises: imports are not the per-frame path)
+static int gx_check_import(gvdbx_t* h)
+{
+    int e = 0;
+    GX_CUDA(h, cudaMemcpyAsync(&e, h->d_err, sizeof e, cudaMemcpyDeviceToHost, h->stream));
+    GX_CUDA(h, cudaStreamSynchronize(h->stream));
+    if (!e) return GVDBX_OK;
+    e &= ~GX_ERR_WAIT_TIMEOUT;
+    if (!e) return GVDBX_OK;
+    gx_clear_import_bits<<<1, 1, 0, h->stream>>>(h->d_err);
+    std::string msg = "malformed pools:";
+    if (e & GX_IMPORT_E_CHILDLIST) msg += " a node's mChildList points past the child-list pool;";
+    if (e & GX_IMPORT_E_CHILD) msg += " a child entry points past the node pool of the level below;";
+    if (e & GX_IMPORT_E_LEAFSLOT) msg += " a leaf's mValue brick lies outside the atlas (VDBInfo.atlas_res);";
+    return gx_fail(h, GVDBX_E_ARG, msg);
+}
+
+// Tables derived from topology AND atlas: built by whichever import comes last.  Per-leaf value ranges are reduced straight
+// from the atlas array (no staging copy of the atlas exists); occupancy bits and the brick-major copy are built on first use.
 static int gx_update_leaf_ranges(gvdbx_t* h)
 {
-    h->vmask_valid = false;                             // topology or atlas changed
-    if (h->d_vmask) { cudaFree(h->d_vmask); h->d_vmask = nullptr; }
-    if (h->d_leaf_range) { cudaFree(h->d_leaf_range); h->d_leaf_range = nullptr; }
-    if (!h->have_topo || !h->d_range || !h->d_leaf) return GVDBX_OK;
-    const int n = h->vdb.nodecnt[0];
+    gx_free_derived(h);
+    if (!h->have_topo || !h->tex_point || !h->d_leaf) return GVDBX_OK;
+    const GxVDBInfo& v = h->vdb;
+    if (v.atlas_res.x != h->ares[0] || v.atlas_res.y != h->ares[1] || v.atlas_res.z != h->ares[2])
+        return gx_fail(h, GVDBX_E_ARG, "VDBInfo.atlas_res does not match the imported atlas (stale VDBInfo, or atlas of another volume)");
+    const int n = v.nodecnt[0];
     GX_CUDA(h, cudaMalloc(&h->d_leaf_range, size_t(n) * sizeof(GxRange)));
-    gx_leaf_ranges<<<(n + 255) / 256, 256, 0, h->stream>>>(h->d_leaf, n, h->d_range, (int)h->nslots, h->d_leaf_range);
+    gx_leaf_ranges_array<<<n, 128, 0, h->stream>>>(h->tex_point, h->d_leaf, n, h->brick_dim, h->d_leaf_range);
     GX_CUDA(h, cudaGetLastError());
     return GVDBX_OK;
 }
 
-// SHADE_VOXEL occupancy bits for the frame's THRESH: rebuilt (one pass over the brick-major atlas) only when THRESH, the
-// atlas or the topology changed.  Frames in flight on other lanes may still read the old bits: drain them first.
+// A table that frames in flight on OTHER lanes may be reading (or are about to read) is (re)built in stream order: the
+// building stream first waits for everything enqueued on every lane and on the creation stream, and afterwards every lane
+// waits for the build — events only, no host synchronisation.
+static int gx_build_begin(gvdbx_t* h)
+{
+    if (!h->build_ev) GX_CUDA(h, cudaEventCreateWithFlags(&h->build_ev, cudaEventDisableTiming));
+    for (size_t i = 0; i < h->lanes.size(); i++) {
+        if (h->lanes[i] == h->stream) continue;
+        GX_CUDA(h, cudaEventRecord(h->lane_ev[i], h->lanes[i]));
+        GX_CUDA(h, cudaStreamWaitEvent(h->stream, h->lane_ev[i], 0));
+    }
+    if (h->base_stream != h->stream && h->base_ev) {
+        GX_CUDA(h, cudaEventRecord(h->base_ev, h->base_stream));
+        GX_CUDA(h, cudaStreamWaitEvent(h->stream, h->base_ev, 0));
+    }
+    return GVDBX_OK;
+}
+static int gx_build_end(gvdbx_t* h)
+{
+    GX_CUDA(h, cudaEventRecord(h->build_ev, h->stream));
+    for (cudaStream_t s : h->lanes) if (s != h->stream) GX_CUDA(h, cudaStreamWaitEvent(s, h->build_ev, 0));
+    if (h->base_stream != h->stream) GX_CUDA(h, cudaStreamWaitEvent(h->base_stream, h->build_ev, 0));
+    return GVDBX_OK;
+}
+
+// SHADE_VOXEL occupancy bits for the frame's THRESH (8^3 bricks): rebuilt — one pass over the interior texels — only when
+// THRESH, the atlas or the topology changed; stream-ordered against the frames of all lanes (gx_build_begin / _end).
 static int gx_ensure_voxel_mask(gvdbx_t* h, float thresh)
 {
     uint32_t bits;
     memcpy(&bits, &thresh, 4);
     if (h->vmask_valid && bits == h->vmask_thresh_bits) return GVDBX_OK;
     const int n = h->vdb.nodecnt[0];
-    for (cudaStream_t s : h->lanes) GX_CUDA(h, cudaStreamSynchronize(s));
-    GX_CUDA(h, cudaStreamSynchronize(h->base_stream));
     if (!h->d_vmask) GX_CUDA(h, cudaMalloc(&h->d_vmask, size_t(n) * 64));
-    gx_build_voxel_mask<<<n, 64, 0, h->stream>>>(h->d_leaf, n, h->d_bricks, thresh, (unsigned char*)h->d_vmask);
+    int rc = gx_build_begin(h);
+    if (rc) return rc;
+    gx_build_voxel_mask<<<n, 64, 0, h->stream>>>(h->tex_point, h->d_leaf, n, thresh, (unsigned char*)h->d_vmask);
     GX_CUDA(h, cudaGetLastError());
-    GX_CUDA(h, cudaStreamSynchronize(h->stream));
+    rc = gx_build_end(h);
+    if (rc) return rc;
     h->vmask_thresh_bits = bits;
     h->vmask_valid = true;
     return GVDBX_OK;
 }
 
+// brick-major copy of the atlas (one block per leaf) for the linear sampler: built when that sampler is first used
+static int gx_ensure_bricks(gvdbx_t* h)
+{
+    if (h->d_bricks) return GVDBX_OK;
+    const int n = h->vdb.nodecnt[0];
+    GX_CUDA(h, cudaMalloc(&h->d_bricks, size_t(n) * size_t(h->brick_stride) * sizeof(float)));
+    int rc = gx_build_begin(h);
+    if (rc) return rc;
+    gx_copy_bricks_array<<<n, 256, 0, h->stream>>>(h->tex_point, h->d_leaf, n, h->brick_dim, h->brick_stride, h->d_bricks);
+    GX_CUDA(h, cudaGetLastError());
+    return gx_build_end(h);
+}
+
 // ------------------------------------------------------------------------------------------------ topology
-extern "C" int gvdbx_import_topology(gvdbx_t* h, const void* vdbinfo)
+// listcnt[l] = number of child lists in pool 1 of level l when known (host import: pool bytes / childwid), else 0 = bounded
+// by the node count of that level (every node owns at most one list)
+static int gx_import_topology(gvdbx_t* h, const void* vdbinfo, const uint64_t* listcnt)
 {
     if (!h || !vdbinfo) return GVDBX_E_ARG;
     GxCtx ctx_(h);
     GxVDBInfo v;
     memcpy(&v, vdbinfo, sizeof v);
     if (v.top_lev < 0 || v.top_lev >= GX_MAXLEV) return gx_fail(h, GVDBX_E_ARG, "top_lev out of range (0..4)");
-    if (v.atlas_apron != 1 || v.brick_res != GX_BRICK_DIM || v.res[0] != GX_BRICK_DIM - 2)
-        return gx_fail(h, GVDBX_E_UNSUPPORTED, "only 8^3 bricks with apron 1 are supported (brick_res 10)");
+    // bricks: Configure(.., q0) with q0 = 2..5 (4^3 .. 32^3 voxels; the reference's samples use 3, 4 and 5), apron 1
+    if (v.atlas_apron != 1) return gx_fail(h, GVDBX_E_UNSUPPORTED, "only apron 1 is supported (the reference's default, gvdb_volume_gvdb.cpp:73)");
+    if (v.dim[0] < 2 || v.dim[0] > 5) return gx_fail(h, GVDBX_E_UNSUPPORTED, "brick log2dim must be 2..5");
+    if (v.brick_res != v.res[0] + 2 * v.atlas_apron) return gx_fail(h, GVDBX_E_ARG, "brick_res != res[0] + 2 * apron");
+    if (v.atlas_res.x <= 0 || v.atlas_res.y <= 0 || v.atlas_res.z <= 0 || v.atlas_res.x % v.brick_res || v.atlas_res.y % v.brick_res || v.atlas_res.z % v.brick_res)
+        return gx_fail(h, GVDBX_E_ARG, "atlas_res must be a positive multiple of brick_res");
     for (int l = 0; l <= v.top_lev; l++) {
         if (v.dim[l] < 1 || v.dim[l] > 8 || v.res[l] != (1 << v.dim[l])) return gx_fail(h, GVDBX_E_ARG, "inconsistent dim/res");
         if (v.nodecnt[l] <= 0 || v.nodelist[l] == 0) return gx_fail(h, GVDBX_E_ARG, "empty node pool below top_lev");
@@ -285,21 +357,31 @@ extern "C" int gvdbx_import_topology(gvdbx_t* h, const void* vdbinfo)
         GX_CUDA(h, cudaMalloc(&h->d_npos[l], size_t(v.nodecnt[l]) * sizeof(int4)));
         const int threads = 256;
         const unsigned blocks = (unsigned)((total + threads - 1) / threads);
+        const unsigned long long lists = (listcnt && listcnt[l]) ? listcnt[l] : (unsigned long long)v.nodecnt[l];
         gx_build_child_table<<<blocks, threads, 0, h->stream>>>((const char*)v.nodelist[l], v.nodewid[l], v.nodecnt[l],
-                                                               (const char*)v.childlist[l], v.childwid[l], cells,
-                                                               h->d_child[l], h->d_npos[l]);
+                                                               (const char*)v.childlist[l], v.childwid[l], cells, lists, v.nodecnt[l - 1],
+                                                               h->d_child[l], h->d_npos[l], h->d_err);
         GX_CUDA(h, cudaGetLastError());
     }
     GX_CUDA(h, cudaMalloc(&h->d_leaf, size_t(v.nodecnt[0]) * sizeof(GxLeafRec)));
-    gx_build_leaf_table<<<(v.nodecnt[0] + 255) / 256, 256, 0, h->stream>>>((const char*)v.nodelist[0], v.nodewid[0], v.nodecnt[0],
-                                                                          v.brick_res, v.atlas_apron, v.atlas_cnt.x, v.atlas_cnt.y, h->d_leaf);
+    gx_build_leaf_table<<<(v.nodecnt[0] + 255) / 256, 256, 0, h->stream>>>((const char*)v.nodelist[0], v.nodewid[0], v.nodecnt[0], v.brick_res,
+                                                                          make_int3(v.atlas_res.x, v.atlas_res.y, v.atlas_res.z), h->d_leaf, h->d_err);
     GX_CUDA(h, cudaGetLastError());
+    int rc = gx_check_import(h);
+    if (rc) { gx_free_topology(h); return rc; }
     h->vdb = v;
     h->have_topo = true;
+    h->brick_dim = v.brick_res;
+    h->brick_stride = (v.brick_res * v.brick_res * v.brick_res + 255) / 256 * 256;
     h->uniform3 = true;
     for (int l = 0; l <= v.top_lev; l++) if (v.dim[l] != 3 || v.vdel[l].x != float(1 << (3 * l)) || v.vdel[l].y != v.vdel[l].x || v.vdel[l].z != v.vdel[l].x) h->uniform3 = false;
+    // VDBInfo is the authority on the atlas geometry: an atlas imported earlier with another resolution is stale (UpdateAtlas
+    // re-allocates the reference's array when the volume grows) and is dropped; import it again
+    if (h->have_atlas && (v.atlas_res.x != h->ares[0] || v.atlas_res.y != h->ares[1] || v.atlas_res.z != h->ares[2])) gx_free_atlas(h);
     return gx_update_leaf_ranges(h);
 }
+
+extern "C" int gvdbx_import_topology(gvdbx_t* h, const void* vdbinfo) { return gx_import_topology(h, vdbinfo, nullptr); }
 
 extern "C" int gvdbx_import_topology_host(gvdbx_t* h, const void* vdbinfo, const void* const* pool0, const void* const* pool1,
                                           const uint64_t* pool1_bytes)
@@ -324,18 +406,21 @@ extern "C" int gvdbx_import_topology_host(gvdbx_t* h, const void* vdbinfo, const
         if (!up(pool0[l], size_t(v.nodecnt[l]) * v.nodewid[l], &v.nodelist[l])) rc = GVDBX_E_CUDA;
         if (l >= 1 && !up(pool1[l], (size_t)pool1_bytes[l], &v.childlist[l])) rc = GVDBX_E_CUDA;
     }
-    if (rc == GVDBX_OK) rc = gvdbx_import_topology(h, &v);
-    else h->err = "pool upload failed";
+    if (rc == GVDBX_OK) {
+        uint64_t listcnt[GX_MAXLEV] = {0, 0, 0, 0, 0};
+        for (int l = 1; l <= v.top_lev; l++) if (v.childwid[l] > 0) listcnt[l] = pool1_bytes[l] / (uint64_t)v.childwid[l];
+        rc = gx_import_topology(h, &v, listcnt);
+    } else h->err = "pool upload failed";
     cudaStreamSynchronize(h->stream);
     for (void* d : tmp) cudaFree(d);
     return rc;
 }
 
 // ------------------------------------------------------------------------------------------------ atlas
-static int gx_make_texture(gvdbx_t* h, cudaArray_t arr)
+static int gx_make_texture(gvdbx_t* h, cudaArray_t arr, int rx, int ry, int rz)
 {
     // same descriptor as SetupAtlasAccess (gvdb_volume_gvdb.cpp:753-783): linear filter, element-type reads,
-    // unnormalised coordinates, clamp addressing
+    // unnormalised coordinates, clamp addressing; plus a point-filter view of the same array for the import kernels
     cudaResourceDesc rd;
     memset(&rd, 0, sizeof rd);
     rd.resType = cudaResourceTypeArray;
@@ -347,57 +432,33 @@ static int gx_make_texture(gvdbx_t* h, cudaArray_t arr)
     td.addressMode[0] = td.addressMode[1] = td.addressMode[2] = cudaAddressModeClamp;
     td.normalizedCoords = 0;
     GX_CUDA(h, cudaCreateTextureObject(&h->tex, &rd, &td, nullptr));
+    td.filterMode = cudaFilterModePoint;
+    GX_CUDA(h, cudaCreateTextureObject(&h->tex_point, &rd, &td, nullptr));
     h->array = arr;
     if (cudaCreateSurfaceObject(&h->surf, &rd) != cudaSuccess) { h->surf = 0; cudaGetLastError(); }   // array without the surface flag: no UpdateApron
+    h->ares[0] = rx; h->ares[1] = ry; h->ares[2] = rz;
     return GVDBX_OK;
 }
 
-static int gx_repack(gvdbx_t* h, const float* d_linear, int rx, int ry, int rz)
-{
-    if (rx % GX_BRICK_DIM || ry % GX_BRICK_DIM || rz % GX_BRICK_DIM)
-        return gx_fail(h, GVDBX_E_UNSUPPORTED, "atlas resolution must be a multiple of the 10^3 brick");
-    const int cx = rx / GX_BRICK_DIM, cy = ry / GX_BRICK_DIM, cz = rz / GX_BRICK_DIM;
-    const size_t slots = size_t(cx) * cy * cz;
-    GX_CUDA(h, cudaMalloc(&h->d_bricks, slots * GX_BRICK_STRIDE * sizeof(float)));
-    GX_CUDA(h, cudaMalloc(&h->d_range, slots * sizeof(GxRange)));
-    gx_repack_atlas<<<(unsigned)slots, 256, 0, h->stream>>>(d_linear, rx, ry, rz, cx, cy, h->d_bricks, h->d_range);
-    GX_CUDA(h, cudaGetLastError());
-    h->ares[0] = rx; h->ares[1] = ry; h->ares[2] = rz;
-    h->nslots = slots;
-    return gx_update_leaf_ranges(h);
-}
-
+// The atlas is sampled where it lies: the caller's array (gvdbx_import_atlas_array) or one array owned by the library
+// (_host / _device).  No second copy is made at import; what is derived from it (value ranges now, occupancy bits and the
+// brick-major copy on first use) is read straight from the array.
 extern "C" int gvdbx_import_atlas_array(gvdbx_t* h, int chan, void* cuarray, int rx, int ry, int rz)
 {
     if (!h || !cuarray || rx <= 0 || ry <= 0 || rz <= 0) return GVDBX_E_ARG;
     if (chan != 0) return gx_fail(h, GVDBX_E_UNSUPPORTED, "only channel 0 (T_FLOAT) is supported");
     GxCtx ctx_(h);
     gx_free_atlas(h);
-    int rc = gx_make_texture(h, (cudaArray_t)cuarray);
-    if (rc) return rc;
-    float* d_lin = nullptr;
-    GX_CUDA(h, cudaMalloc(&d_lin, size_t(rx) * ry * rz * sizeof(float)));
-    cudaMemcpy3DParms cp;
-    memset(&cp, 0, sizeof cp);
-    cp.srcArray = (cudaArray_t)cuarray;
-    cp.dstPtr = make_cudaPitchedPtr(d_lin, size_t(rx) * sizeof(float), rx, ry);
-    cp.extent = make_cudaExtent(rx, ry, rz);
-    cp.kind = cudaMemcpyDeviceToDevice;
-    cudaError_t e = cudaMemcpy3DAsync(&cp, h->stream);
-    if (e == cudaSuccess) rc = gx_repack(h, d_lin, rx, ry, rz);
-    cudaStreamSynchronize(h->stream);
-    cudaFree(d_lin);
-    if (e != cudaSuccess) { h->err = std::string("cudaMemcpy3DAsync: ") + cudaGetErrorString(e); return GVDBX_E_CUDA; }
+    int rc = gx_make_texture(h, (cudaArray_t)cuarray, rx, ry, rz);
     if (rc) return rc;
     h->have_atlas = true;
-    return GVDBX_OK;
+    rc = gx_update_leaf_ranges(h);
+    if (rc) gx_free_atlas(h);                           // an atlas that contradicts the topology is not kept
+    return rc;
 }
 
-extern "C" int gvdbx_import_atlas_host(gvdbx_t* h, int chan, const float* texels, int rx, int ry, int rz)
+static int gx_import_atlas_linear(gvdbx_t* h, const void* texels, int rx, int ry, int rz, cudaMemcpyKind kind)
 {
-    if (!h || !texels || rx <= 0 || ry <= 0 || rz <= 0) return GVDBX_E_ARG;
-    if (chan != 0) return gx_fail(h, GVDBX_E_UNSUPPORTED, "only channel 0 (T_FLOAT) is supported");
-    GxCtx ctx_(h);
     gx_free_atlas(h);
     cudaChannelFormatDesc fd = cudaCreateChannelDesc<float>();
     GX_CUDA(h, cudaMalloc3DArray(&h->own_array, &fd, make_cudaExtent(rx, ry, rz), cudaArraySurfaceLoadStore));
@@ -406,21 +467,23 @@ extern "C" int gvdbx_import_atlas_host(gvdbx_t* h, int chan, const float* texels
     cp.srcPtr = make_cudaPitchedPtr((void*)texels, size_t(rx) * sizeof(float), rx, ry);
     cp.dstArray = h->own_array;
     cp.extent = make_cudaExtent(rx, ry, rz);
-    cp.kind = cudaMemcpyHostToDevice;
+    cp.kind = kind;
     GX_CUDA(h, cudaMemcpy3DAsync(&cp, h->stream));
-    int rc = gx_make_texture(h, h->own_array);
-    if (rc) return rc;
-    float* d_lin = nullptr;
-    const size_t bytes = size_t(rx) * ry * rz * sizeof(float);
-    GX_CUDA(h, cudaMalloc(&d_lin, bytes));
-    cudaError_t e = cudaMemcpyAsync(d_lin, texels, bytes, cudaMemcpyHostToDevice, h->stream);
-    if (e == cudaSuccess) rc = gx_repack(h, d_lin, rx, ry, rz);
-    cudaStreamSynchronize(h->stream);
-    cudaFree(d_lin);
-    if (e != cudaSuccess) { h->err = std::string("cudaMemcpyAsync: ") + cudaGetErrorString(e); return GVDBX_E_CUDA; }
+    GX_CUDA(h, cudaStreamSynchronize(h->stream));       // the caller may free / reuse its image now
+    int rc = gx_make_texture(h, h->own_array, rx, ry, rz);
     if (rc) return rc;
     h->have_atlas = true;
-    return GVDBX_OK;
+    rc = gx_update_leaf_ranges(h);
+    if (rc) gx_free_atlas(h);                           // an atlas that contradicts the topology is not kept
+    return rc;
+}
+
+extern "C" int gvdbx_import_atlas_host(gvdbx_t* h, int chan, const float* texels, int rx, int ry, int rz)
+{
+    if (!h || !texels || rx <= 0 || ry <= 0 || rz <= 0) return GVDBX_E_ARG;
+    if (chan != 0) return gx_fail(h, GVDBX_E_UNSUPPORTED, "only channel 0 (T_FLOAT) is supported");
+    GxCtx ctx_(h);
+    return gx_import_atlas_linear(h, texels, rx, ry, rz, cudaMemcpyHostToDevice);
 }
 
 // ------------------------------------------------------------------------------------------------ UpdateApron / atlas read-back
@@ -436,6 +499,7 @@ static void gx_tree_params(gvdbx_t* h, GxParams& P)
     P.top_lev = v.top_lev; P.epsilon = v.epsilon;
     P.leaf = h->d_leaf;
     P.tex = h->tex; P.bricks = h->d_bricks;
+    P.brick_dim = h->brick_dim; P.brick_stride = h->brick_stride;
 }
 
 extern "C" int gvdbx_update_apron(gvdbx_t* h, int chan, float boundval)
@@ -448,11 +512,14 @@ extern "C" int gvdbx_update_apron(gvdbx_t* h, int chan, float boundval)
     GxParams P;
     gx_tree_params(h, P);
     const int n = h->vdb.nodecnt[0];
+    int rc = gx_build_begin(h);                         // frames in flight on other lanes read the texels this pass rewrites
+    if (rc) return rc;
     gx_update_apron_kernel<<<n, 128, 0, h->stream>>>(P, h->surf, h->d_bricks, n, boundval);
     GX_CUDA(h, cudaGetLastError());
-    gx_brick_ranges<<<(unsigned)h->nslots, 256, 0, h->stream>>>(h->d_bricks, h->d_range);
+    // value ranges over interior + apron change with the aprons; occupancy bits (interior voxels only) do not
+    gx_leaf_ranges_array<<<n, 128, 0, h->stream>>>(h->tex_point, h->d_leaf, n, h->brick_dim, h->d_leaf_range);
     GX_CUDA(h, cudaGetLastError());
-    return gx_update_leaf_ranges(h);
+    return gx_build_end(h);
 }
 
 // host image of the atlas array, x fastest (the inverse of gvdbx_import_atlas_host; Allocator::AtlasRetrieveSlice per slice)
@@ -481,23 +548,7 @@ extern "C" int gvdbx_import_atlas_device(gvdbx_t* h, int chan, uint64_t texels_d
     if (!h || !texels_d || rx <= 0 || ry <= 0 || rz <= 0) return GVDBX_E_ARG;
     if (chan != 0) return gx_fail(h, GVDBX_E_UNSUPPORTED, "only channel 0 (T_FLOAT) is supported");
     GxCtx ctx_(h);
-    gx_free_atlas(h);
-    cudaChannelFormatDesc fd = cudaCreateChannelDesc<float>();
-    GX_CUDA(h, cudaMalloc3DArray(&h->own_array, &fd, make_cudaExtent(rx, ry, rz), cudaArraySurfaceLoadStore));
-    cudaMemcpy3DParms cp;
-    memset(&cp, 0, sizeof cp);
-    cp.srcPtr = make_cudaPitchedPtr((void*)texels_d, size_t(rx) * sizeof(float), rx, ry);
-    cp.dstArray = h->own_array;
-    cp.extent = make_cudaExtent(rx, ry, rz);
-    cp.kind = cudaMemcpyDeviceToDevice;
-    GX_CUDA(h, cudaMemcpy3DAsync(&cp, h->stream));
-    int rc = gx_make_texture(h, h->own_array);
-    if (rc) return rc;
-    rc = gx_repack(h, (const float*)texels_d, rx, ry, rz);
-    GX_CUDA(h, cudaStreamSynchronize(h->stream));       // the caller may free / reuse its image now
-    if (rc) return rc;
-    h->have_atlas = true;
-    return GVDBX_OK;
+    return gx_import_atlas_linear(h, (const void*)texels_d, rx, ry, rz, cudaMemcpyDeviceToDevice);
 }
 
 // ------------------------------------------------------------------------------------------------ colour channel
@@ -598,7 +649,7 @@ static gx_kernel_t gx_pick(int mode, int sampler, int flags, bool uni)
 
 static inline float3 f3(const GxF3& a) { return make_float3(a.x, a.y, a.z); }
 
-static int gx_fill_params(gvdbx_t* h, const void* scninfo, int shade_mode, int chan, GxParams& P, int& mode)
+static int gx_fill_params(gvdbx_t* h, const void* scninfo, int shade_mode, int chan, GxParams& P, int& mode, bool force_deep_lut = false)
 {
     if (!h || !scninfo) return GVDBX_E_ARG;
     if (!h->have_topo) return gx_fail(h, GVDBX_E_STATE, "render before gvdbx_import_topology");
@@ -635,7 +686,7 @@ static int gx_fill_params(gvdbx_t* h, const void* scninfo, int shade_mode, int c
         return gx_fail(h, GVDBX_E_STATE, "transfer function not on GPU (reference: 'Must call CommitTransferFunc')");
     P.dbuf = (const float*)s.dbuf;
     P.transfer_deep = nullptr;
-    if (mode == GX_MODE_DEEP || mode == GX_MODE_DEEPSHADOW) {
+    if (mode == GX_MODE_DEEP || mode == GX_MODE_DEEPSHADOW || (force_deep_lut && P.transfer)) {
         // this frame's derived table, in the buffer of the stream / lane the frame is enqueued on (stream-ordered, ~2 us)
         const size_t slot = size_t(h->cur_lane + 1);
         if (h->deep_lut.size() <= slot) h->deep_lut.resize(slot + 1, nullptr);
@@ -652,7 +703,9 @@ static int gx_fill_params(gvdbx_t* h, const void* scninfo, int shade_mode, int c
     }
     P.top_lev = v.top_lev; P.epsilon = v.epsilon; P.bmin = f3(v.bmin); P.bmax = f3(v.bmax);
     P.leaf = h->d_leaf;
+    if (h->sampler == GX_SAMPLER_LINEAR) { const int rc = gx_ensure_bricks(h); if (rc) return rc; }
     P.tex = h->tex; P.bricks = h->d_bricks;
+    P.brick_dim = h->brick_dim; P.brick_stride = h->brick_stride;
     // the colour channel is used exactly when the reference would: VDBInfo::clr_chan set (SetColorChannel)
     P.clr_tex = 0;
     if (v.clr_chan != GX_CHAN_UNDEF) {
@@ -701,14 +754,15 @@ extern "C" int gvdbx_render(gvdbx_t* h, const void* scninfo, int shade_mode, int
                     : (h->spp > 1 ? GX_FLAG_SPP
                     : (core && h->literal == 1 ? GX_FLAG_LITERAL : (core && h->literal == 2 ? GX_FLAG_PACKET : 0)));
     if (flags & (GX_FLAG_COUNT | GX_FLAG_LITERAL)) P.range = nullptr;     // counters / A-B baseline follow the reference's own work
+    if (h->count && h->spp > 1) return gx_fail(h, GVDBX_E_ARG, "work counters are taken at 1 ray per pixel: set GVDBX_OPT_SPP to 1 for the counted render");
+    gx_kernel_t k = gx_pick(mode, h->sampler, flags, h->uniform3);
+    if (!k) return gx_fail(h, GVDBX_E_UNSUPPORTED, "no kernel variant for this mode / sampler / option combination");
     float4* dbg_tmp = nullptr;
     if (h->count) {     // counted renders reuse the debug variant; give it a scratch debug buffer
         GX_CUDA(h, cudaMalloc(&dbg_tmp, size_t(P.width) * P.height * 48));
         P.dbg = dbg_tmp;
         GX_CUDA(h, cudaMemsetAsync(h->d_counters, 0, 8 * sizeof(unsigned long long), h->stream));
     }
-    gx_kernel_t k = gx_pick(mode, h->sampler, flags, h->uniform3);
-    if (!k) return gx_fail(h, GVDBX_E_UNSUPPORTED, "no kernel variant for this mode / sampler / option combination");
     dim3 block(h->block_w, h->block_h, 1);
     dim3 grid((P.x1 - P.x0 + block.x - 1) / block.x, (P.y1 - P.y0 + block.y - 1) / block.y, 1);
     k<<<grid, block, size_t(block.x) * block.y * GX_STACK_BYTES_PER_THREAD, h->stream>>>(P);
@@ -725,7 +779,8 @@ extern "C" int gvdbx_kernel_params(gvdbx_t* h, const void* scninfo, int shade_mo
     if (params_bytes != sizeof(GxParams)) return gx_fail(h, GVDBX_E_ARG, "params_bytes != sizeof(GxParams): plugin built against other headers");
     GxCtx ctx_(h);
     GxParams P; int mode = 0;
-    int rc = gx_fill_params(h, scninfo, shade_mode, chan, P, mode);
+    // a plugin kernel may march deep bricks whatever `shade_mode` says: the derived table is always prepared
+    int rc = gx_fill_params(h, scninfo, shade_mode, chan, P, mode, true);
     if (rc) return rc;
     P.out = (uchar4*)outbuf_d;
     memcpy(params_out, &P, sizeof P);
@@ -1001,7 +1056,7 @@ extern "C" int gvdbx_stream_wait(gvdbx_t* h, void* cuda_stream, uint64_t flag_d,
         }
         if (fn && fn(st, (unsigned long long)flag_d, value, 0x0 /* CU_STREAM_WAIT_VALUE_GEQ */) == 0) return GVDBX_OK;
     }
-    gx_wait_kernel<<<1, 1, 0, st>>>((unsigned int*)flag_d, value);
+    gx_wait_kernel<<<1, 1, 0, st>>>((unsigned int*)flag_d, value, h->d_err);
     GX_CUDA(h, cudaGetLastError());
     return GVDBX_OK;
 }
@@ -1066,6 +1121,10 @@ extern "C" int gvdbx_sync(gvdbx_t* h)
     if (!h) return GVDBX_E_ARG;
     GxCtx ctx_(h);
     GX_CUDA(h, cudaStreamSynchronize(h->stream));
+    // sticky: a stream-ordered wait that ran into its timeout means frames were rendered / consumed out of order
+    int e = 0;
+    GX_CUDA(h, cudaMemcpy(&e, h->d_err, sizeof e, cudaMemcpyDeviceToHost));
+    if (e & GX_ERR_WAIT_TIMEOUT) return gx_fail(h, GVDBX_E_CUDA, "a gvdbx_stream_wait timed out (lost peer or stalled consumer): frames after it are not trustworthy");
     return GVDBX_OK;
 }
 
@@ -1083,15 +1142,24 @@ extern "C" int gvdbx_get_counters(gvdbx_t* h, gvdbx_counters* out)
 extern "C" int gvdbx_sample_points(gvdbx_t* h, int chan, uint64_t xyz_d, int n, uint64_t out_tex_d, uint64_t out_lin_d)
 {
     if (!h || !xyz_d || !out_tex_d || !out_lin_d || n <= 0) return GVDBX_E_ARG;
-    if (!h->have_atlas) return gx_fail(h, GVDBX_E_STATE, "no atlas imported");
+    if (!h->have_atlas || !h->have_topo) return gx_fail(h, GVDBX_E_STATE, "needs topology and atlas");
     if (chan != 0) return gx_fail(h, GVDBX_E_UNSUPPORTED, "only channel 0 is supported");
     GxCtx ctx_(h);
+    int rc = gx_ensure_bricks(h);
+    if (rc) return rc;
     GxParams P;
-    memset(&P, 0, sizeof P);
-    P.tex = h->tex; P.bricks = h->d_bricks;
-    gx_sample_points_kernel<<<(n + 255) / 256, 256, 0, h->stream>>>(P, (const float*)xyz_d, n, h->ares[0] / GX_BRICK_DIM,
-                                                                   h->ares[1] / GX_BRICK_DIM, (float*)out_tex_d, (float*)out_lin_d);
-    GX_CUDA(h, cudaGetLastError());
+    gx_tree_params(h, P);
+    const int cx = h->ares[0] / h->brick_dim, cy = h->ares[1] / h->brick_dim, cz = h->ares[2] / h->brick_dim;
+    int* slot_leaf = nullptr;
+    GX_CUDA(h, cudaMalloc(&slot_leaf, size_t(cx) * cy * cz * sizeof(int)));
+    GX_CUDA(h, cudaMemsetAsync(slot_leaf, 0xFF, size_t(cx) * cy * cz * sizeof(int), h->stream));
+    const int nl = h->vdb.nodecnt[0];
+    gx_build_slot_map<<<(nl + 255) / 256, 256, 0, h->stream>>>(h->d_leaf, nl, h->brick_dim, cx, cy, slot_leaf);
+    gx_sample_points_kernel<<<(n + 255) / 256, 256, 0, h->stream>>>(P, (const float*)xyz_d, n, cx, cy, slot_leaf, (float*)out_tex_d, (float*)out_lin_d);
+    cudaError_t e = cudaGetLastError();
+    cudaStreamSynchronize(h->stream);
+    cudaFree(slot_leaf);
+    GX_CUDA(h, e);
     return GVDBX_OK;
 }
 

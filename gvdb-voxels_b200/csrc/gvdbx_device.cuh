@@ -43,13 +43,15 @@
 #define GX_SAMPLER_TEX    0
 #define GX_SAMPLER_LINEAR 1
 
-#define GX_BRICK_STRIDE   1024     // floats per brick slot in the brick-major atlas (10^3 used, 4 KB aligned)
-#define GX_BRICK_DIM      10       // brick res incl. apron for the brick-major layout (res0 8 + 2*apron 1)
+// brick-major copy of the atlas (linear sampler): one block of brick_dim^3 floats per LEAF, brick_dim = res0 + 2 (apron 1),
+// padded to a multiple of 256 floats.  8^3 bricks (Configure(.., 3), the UNI kernels): 10^3 in 1024 floats = one 4 KB block.
+#define GX_BRICK_STRIDE   1024
+#define GX_BRICK_DIM      10
 
 // ------------------------------------------------------------------------------------------------ parameters
 struct alignas(16) GxLeafRec {     // 32 B, one per level-0 node
     int px, py, pz;                // mPos   : index-space min corner
-    int base;                      // float offset of the brick in the brick-major atlas
+    int idx;                       // the leaf's own index = its block in the brick-major copy (offset = idx * brick_stride, 64-bit)
     int vx, vy, vz;                // mValue : atlas texel of the first interior voxel
     int pad;
 };
@@ -75,7 +77,8 @@ struct GxParams {
     float3   cutoff;               // x = MINVAL, y = ALPHACUT
     float3   thresh;               // x = THRESH, y = VMIN, z = VMAX
     const float4* transfer;
-    const float4* transfer_deep;       // per frame: {rgb, exp(EXTINCT * alpha * DIRECTSTEP)} of every entry (gx_build_deep_lut); null = compute per sample
+    const float4* transfer_deep;       // per frame: {rgb, exp(EXTINCT * alpha * DIRECTSTEP)} of every entry (gx_build_deep_lut); set whenever `transfer` is, for the
+                                       // deep modes and for every block handed to a plugin kernel (gvdbx_kernel_params); the deep marchers require it
     const float*  dbuf;
     // ---- tree geometry (VDBInfo fields the path reads)
     int      dim[GX_MAXLEV];
@@ -96,7 +99,9 @@ struct GxParams {
     // ---- atlas
     cudaTextureObject_t tex;             // caller's 3-D array, linear filter, unnormalised, clamp
     cudaTextureObject_t clr_tex;         // colour channel (uchar4 atlas, VDBInfo::clr_chan); 0 = CHAN_UNDEF
-    const float*        bricks;          // brick-major copy
+    const float*        bricks;          // brick-major copy, one block per leaf (built on first use of the linear sampler)
+    int                 brick_dim;       // res0 + 2 (texels per brick edge incl. apron)
+    int                 brick_stride;    // floats per block
     const GxRange*      range;           // value range per LEAF (same index as `leaf`); null = no culling
     const unsigned long long* vmask;     // SHADE_VOXEL: per leaf 8 x 64 bits, bit (z, y * 8 + x) = voxel value > THRESH; null = fetch
     // ---- output
@@ -190,10 +195,12 @@ template <bool UNI_> struct GxSampler<GX_SAMPLER_LINEAR, UNI_> {
     const float* bricks;
     const float* b;      // current brick
     int ox, oy, oz;      // atlas texel index of the brick's texel (0,0,0) = mValue - apron
-    __device__ __forceinline__ GxSampler(const GxParams& P) : bricks(P.bricks), b(P.bricks), ox(0), oy(0), oz(0) {}
+    int bd_, stride_;    // brick edge / block size for trees with other brick sizes (compile-time 10 / 1024 when UNI)
+    __device__ __forceinline__ GxSampler(const GxParams& P) : bricks(P.bricks), b(P.bricks), ox(0), oy(0), oz(0), bd_(P.brick_dim), stride_(P.brick_stride) {}
+    __device__ __forceinline__ int bd() const { return UNI ? GX_BRICK_DIM : bd_; }
     __device__ __forceinline__ void enter(const GxLeafRec& L)
     {
-        b = bricks + L.base;
+        b = bricks + size_t(L.idx) * size_t(UNI ? GX_BRICK_STRIDE : stride_);
         ox = L.vx - 1; oy = L.vy - 1; oz = L.vz - 1;
     }
     static __device__ __forceinline__ void split(float c, int o, int& i, int& a)
@@ -208,14 +215,14 @@ template <bool UNI_> struct GxSampler<GX_SAMPLER_LINEAR, UNI_> {
     {
         int ix, iy, iz, ax, ay, az;
         split(x, ox, ix, ax); split(y, oy, iy, ay); split(z, oz, iz, az);
-        // in-brick samples only ever need texels 0..9; clamp so that zero-weight neighbours stay inside the brick
-        const int ix1 = min(max(ix + 1, 0), GX_BRICK_DIM - 1), iy1 = min(max(iy + 1, 0), GX_BRICK_DIM - 1),
-                  iz1 = min(max(iz + 1, 0), GX_BRICK_DIM - 1);
-        ix = min(max(ix, 0), GX_BRICK_DIM - 1); iy = min(max(iy, 0), GX_BRICK_DIM - 1); iz = min(max(iz, 0), GX_BRICK_DIM - 1);
-        const float* r00 = b + (iz * GX_BRICK_DIM + iy) * GX_BRICK_DIM;
-        const float* r10 = b + (iz * GX_BRICK_DIM + iy1) * GX_BRICK_DIM;
-        const float* r01 = b + (iz1 * GX_BRICK_DIM + iy) * GX_BRICK_DIM;
-        const float* r11 = b + (iz1 * GX_BRICK_DIM + iy1) * GX_BRICK_DIM;
+        // in-brick samples only ever need texels 0..bd-1; clamp so that zero-weight neighbours stay inside the brick
+        const int BD = bd();
+        const int ix1 = min(max(ix + 1, 0), BD - 1), iy1 = min(max(iy + 1, 0), BD - 1), iz1 = min(max(iz + 1, 0), BD - 1);
+        ix = min(max(ix, 0), BD - 1); iy = min(max(iy, 0), BD - 1); iz = min(max(iz, 0), BD - 1);
+        const float* r00 = b + (iz * BD + iy) * BD;
+        const float* r10 = b + (iz * BD + iy1) * BD;
+        const float* r01 = b + (iz1 * BD + iy) * BD;
+        const float* r11 = b + (iz1 * BD + iy1) * BD;
         const float c000 = __ldg(r00 + ix), c100 = __ldg(r00 + ix1);
         const float c010 = __ldg(r10 + ix), c110 = __ldg(r10 + ix1);
         const float c001 = __ldg(r01 + ix), c101 = __ldg(r01 + ix1);
@@ -241,7 +248,7 @@ template <bool UNI_> struct GxSampler<GX_SAMPLER_LINEAR, UNI_> {
     __device__ __forceinline__ float point(float x, float y, float z) const
     {
         int ix = int(x) - ox, iy = int(y) - oy, iz = int(z) - oz;    // x = texel + 0.5 -> truncation gives the texel
-        return __ldg(b + (iz * GX_BRICK_DIM + iy) * GX_BRICK_DIM + ix);
+        return __ldg(b + (iz * bd() + iy) * bd() + ix);
     }
 };
 
@@ -281,7 +288,7 @@ __device__ __forceinline__ GxLeafRec gx_leaf(const GxParams& P, int node)
 {
     const GxNode* n = gx_ref_node(P, 0, node);
     GxLeafRec r;
-    r.px = n->mPos.x; r.py = n->mPos.y; r.pz = n->mPos.z; r.base = 0;
+    r.px = n->mPos.x; r.py = n->mPos.y; r.pz = n->mPos.z; r.idx = node;
     r.vx = n->mValue.x; r.vy = n->mValue.y; r.vz = n->mValue.z; r.pad = 0;
     return r;
 }

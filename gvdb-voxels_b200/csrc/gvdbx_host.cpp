@@ -302,6 +302,10 @@ int VolumeGVDB::LoadVBX(const char* fname, bool parse_only)
     if (!fp) { mErr = std::string("LoadVBX: unable to open ") + fname; return GVDBX_E_ARG; }
     Reader rd{fp};
     auto fail = [&](int code, const std::string& m) { fclose(fp); mErr = "LoadVBX: " + m; return code; };
+    // every count / width of the header is checked against the file size before anything is allocated
+    fseeko(fp, 0, SEEK_END);
+    const uint64_t file_bytes = (uint64_t)ftello(fp);
+    fseeko(fp, 0, SEEK_SET);
 
     //--- file header (gvdb_volume_gvdb.cpp:549-590)
     unsigned char major = 0, minor = 0;
@@ -338,6 +342,19 @@ int VolumeGVDB::LoadVBX(const char* fname, bool parse_only)
         rd.get(&ld[n]); rd.get(&res[n]); rd.get(range[n], 3); rd.get(&cnt0[n]); rd.get(&width0[n]); rd.get(&cnt1[n]); rd.get(&width1[n]);
     }
     if (!rd.ok) return fail(GVDBX_E_ARG, "truncated topology header");
+    if (apron < 0 || apron > 4 || num_chan < 1 || num_chan > 32) return fail(GVDBX_E_ARG, "bad apron / channel count");
+    for (int a = 0; a < 3; a++)
+        if (axiscnt[a] <= 0 || axisres[a] <= 0 || axisres[a] > 65536 || axisres[a] % axiscnt[a] != 0) return fail(GVDBX_E_ARG, "bad atlas geometry");
+    {
+        uint64_t need = 0;
+        for (int n = 0; n < levels; n++) {
+            if (ld[n] < 1 || ld[n] > 8 || range[n][0] <= 0 || range[n][1] <= 0 || range[n][2] <= 0) return fail(GVDBX_E_ARG, "bad level geometry (log2dim 1..8, positive range)");
+            if (cnt0[n] < 0 || cnt1[n] < 0 || width0[n] < 0 || width1[n] < 0 || width0[n] > (1 << 20) || width1[n] > (1 << 28)) return fail(GVDBX_E_ARG, "bad pool size");
+            need += uint64_t(cnt0[n]) * uint64_t(width0[n]) + uint64_t(cnt1[n]) * uint64_t(width1[n]);
+        }
+        need += 4ull * uint64_t(axisres[0]) * uint64_t(axisres[1]) * uint64_t(axisres[2]);
+        if (need > file_bytes) return fail(GVDBX_E_ARG, "header announces more data than the file holds");
+    }
     if (width0[0] != (int)sizeof(GxNode)) return fail(GVDBX_E_UNSUPPORTED, "node records of another library version (width != 64)");
     std::vector<std::vector<unsigned char>> pool0(levels), pool1(levels);
     for (int n = 0; n < levels; n++) {
@@ -401,7 +418,7 @@ int VolumeGVDB::LoadVBX(const char* fname, bool parse_only)
             if (chan_type != 3 || chan_stride != 4) return fail(GVDBX_E_UNSUPPORTED, "channel 0 is not T_FLOAT");
             atlas.resize(bytes / 4);
             rd.get(atlas.data(), atlas.size());
-        } else if (fseek(fp, (long)bytes, SEEK_CUR) != 0) rd.ok = false;
+        } else if (fseeko(fp, (off_t)bytes, SEEK_CUR) != 0) rd.ok = false;
     }
     if (!rd.ok) return fail(GVDBX_E_ARG, "truncated atlas");
     fclose(fp);
@@ -635,8 +652,15 @@ int gvdbxh_import_topology_host(gvdbxh_volume* h, const void* v, const void* con
     return h->v.ImportTopologyHost(v, p0, p1, n1);
 }
 int gvdbxh_import_atlas_host(gvdbxh_volume* h, int chan, const float* t, int rx, int ry, int rz) { return h->v.ImportAtlasHost(chan, t, rx, ry, rz); }
-int gvdbxh_load_vbx(gvdbxh_volume* h, const char* fname, int parse_only) { return h->v.LoadVBX(fname, parse_only != 0); }
-int gvdbxh_save_vbx(gvdbxh_volume* h, const char* fname) { return h->v.SaveVBX(fname); }
+// no C++ exception may cross the C boundary (allocation failures on absurd sizes)
+int gvdbxh_load_vbx(gvdbxh_volume* h, const char* fname, int parse_only)
+{
+    try { return h->v.LoadVBX(fname, parse_only != 0); } catch (...) { return GVDBX_E_ARG; }
+}
+int gvdbxh_save_vbx(gvdbxh_volume* h, const char* fname)
+{
+    try { return h->v.SaveVBX(fname); } catch (...) { return GVDBX_E_ARG; }
+}
 void gvdbxh_vdbinfo(gvdbxh_volume* h, void* out) { memcpy(out, h->v.getVDBInfoHost(), 1232); }
 void gvdbxh_set_epsilon(gvdbxh_volume* h, float eps, int maxiter) { h->v.SetEpsilon(eps, maxiter); }
 int gvdbxh_commit_transfer(gvdbxh_volume* h) { return h->v.CommitTransferFunc(); }

@@ -4,12 +4,20 @@
 #include "gvdbx_extra.cuh"
 
 // ------------------------------------------------------------------------------------------------ import kernels
+// Error bits the import kernels raise (checked by the host after the import; a malformed VBX file or a stale VDBInfo must
+// not turn into out-of-bounds reads in the render kernels).
+#define GX_IMPORT_E_CHILDLIST 1      // node->mChildList points past the child-list pool
+#define GX_IMPORT_E_CHILD     2      // a child entry points past the node pool of the level below
+#define GX_IMPORT_E_LEAFSLOT  4      // a leaf's mValue brick does not lie inside the atlas
+
+__global__ void gx_clear_import_bits(int* err) { atomicAnd(err, ~(GX_IMPORT_E_CHILDLIST | GX_IMPORT_E_CHILD | GX_IMPORT_E_LEAFSLOT)); }
+
 // pool-0 / pool-1 (reference layout) -> compact tables.  One thread per child cell.
 //   child list entry = Elem(0, lev-1, ndx) = grp | lev << 8 | ndx << 16, or 0xFFFFFFFFFFFFFFFF (src/gvdb_allocator.h:59-62,
 //   gvdb_volume_gvdb.cpp:3015-3023); node->mChildList = Elem(1, lev, ndx) or ID_UNDEFL.
 __global__ void gx_build_child_table(const char* __restrict__ nodelist, int nodewid, int nodecnt,
-                                     const char* __restrict__ childlist, int childwid, int cells,
-                                     int* __restrict__ child_out, int4* __restrict__ npos_out)
+                                     const char* __restrict__ childlist, int childwid, int cells, unsigned long long listcnt, int childcnt,
+                                     int* __restrict__ child_out, int4* __restrict__ npos_out, int* __restrict__ err)
 {
     size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
     size_t total = size_t(nodecnt) * cells;
@@ -20,15 +28,20 @@ __global__ void gx_build_child_table(const char* __restrict__ nodelist, int node
     int c = -1;
     if (listid != GX_ID_UNDEFL) {
         uint64_t cndx = listid >> 16;
-        const uint64_t* clist = reinterpret_cast<const uint64_t*>(childlist + cndx * size_t(childwid));
-        c = int(clist[b] >> 16);
+        if (cndx >= listcnt) { atomicOr(err, GX_IMPORT_E_CHILDLIST); }
+        else {
+            const uint64_t* clist = reinterpret_cast<const uint64_t*>(childlist + cndx * size_t(childwid));
+            c = int(clist[b] >> 16);
+            if (c < -1 || c >= childcnt) { atomicOr(err, GX_IMPORT_E_CHILD); c = -1; }
+        }
     }
     child_out[i] = c;
     if (b == 0) npos_out[n] = make_int4(node->mPos.x, node->mPos.y, node->mPos.z, 0);
 }
 
-__global__ void gx_build_leaf_table(const char* __restrict__ nodelist, int nodewid, int nodecnt, int brick_res,
-                                    int apron, int cnt_x, int cnt_y, GxLeafRec* __restrict__ out)
+// leaf records; a leaf without a brick (mValue.x < 0) keeps vx < 0 and is never sampled
+__global__ void gx_build_leaf_table(const char* __restrict__ nodelist, int nodewid, int nodecnt, int brick_dim, int3 atlas_res,
+                                    GxLeafRec* __restrict__ out, int* __restrict__ err)
 {
     int n = blockIdx.x * blockDim.x + threadIdx.x;
     if (n >= nodecnt) return;
@@ -36,51 +49,78 @@ __global__ void gx_build_leaf_table(const char* __restrict__ nodelist, int nodew
     GxLeafRec r;
     r.px = node->mPos.x; r.py = node->mPos.y; r.pz = node->mPos.z;
     r.vx = node->mValue.x; r.vy = node->mValue.y; r.vz = node->mValue.z;
-    int sx = (r.vx - apron) / brick_res, sy = (r.vy - apron) / brick_res, sz = (r.vz - apron) / brick_res;
-    r.base = (r.vx < 0) ? 0 : ((sz * cnt_y + sy) * cnt_x + sx) * GX_BRICK_STRIDE;
+    r.idx = n;
     r.pad = 0;
+    if (r.vx >= 0 && (r.vx < 1 || r.vy < 1 || r.vz < 1 || r.vx - 1 + brick_dim > atlas_res.x || r.vy - 1 + brick_dim > atlas_res.y ||
+                      r.vz - 1 + brick_dim > atlas_res.z)) {
+        atomicOr(err, GX_IMPORT_E_LEAFSLOT);
+        r.vx = -1;
+    }
     out[n] = r;
 }
 
-// atlas (x-fastest linear image, as cuMemcpy3D array->linear delivers it) -> brick-major; one CTA per brick slot.
-// Also reduces the slot's value range (NaN-ignoring min / max over the 10^3 texels).
-__global__ void gx_repack_atlas(const float* __restrict__ lin, int rx, int ry, int rz, int cnt_x, int cnt_y,
-                                float* __restrict__ bricks, GxRange* __restrict__ range)
+// CTA-wide NaN-ignoring {min, max}
+__device__ __forceinline__ void gx_block_minmax(float& lo, float& hi)
 {
-    const int slot = blockIdx.x;
-    const int sx = slot % cnt_x, sy = (slot / cnt_x) % cnt_y, sz = slot / (cnt_x * cnt_y);
-    float lo = INFINITY, hi = -INFINITY;
-    for (int i = threadIdx.x; i < GX_BRICK_STRIDE; i += blockDim.x) {
-        float v = 0.f;
-        if (i < GX_BRICK_DIM * GX_BRICK_DIM * GX_BRICK_DIM) {
-            int x = i % GX_BRICK_DIM, y = (i / GX_BRICK_DIM) % GX_BRICK_DIM, z = i / (GX_BRICK_DIM * GX_BRICK_DIM);
-            size_t ax = size_t(sx) * GX_BRICK_DIM + x, ay = size_t(sy) * GX_BRICK_DIM + y, az = size_t(sz) * GX_BRICK_DIM + z;
-            v = lin[(az * ry + ay) * rx + ax];
-            lo = fminf(lo, v); hi = fmaxf(hi, v);
-        }
-        bricks[size_t(slot) * GX_BRICK_STRIDE + i] = v;
-    }
-    __shared__ float slo[8], shi[8];
+    __shared__ float slo[32], shi[32];
     for (int o = 16; o > 0; o >>= 1) { lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, o)); hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, o)); }
     if ((threadIdx.x & 31) == 0) { slo[threadIdx.x >> 5] = lo; shi[threadIdx.x >> 5] = hi; }
     __syncthreads();
+    if (threadIdx.x == 0)
+        for (int w = 1; w < (int)((blockDim.x + 31) >> 5); w++) { lo = fminf(lo, slo[w]); hi = fmaxf(hi, shi[w]); }
+}
+
+// Value range of every LEAF over all brick_dim^3 texels of its brick (interior + apron), read straight from the atlas
+// array through a point-filter texture (exact texel values); one CTA per leaf.  A leaf without a brick is never culled.
+__global__ void gx_leaf_ranges_array(cudaTextureObject_t point_tex, const GxLeafRec* __restrict__ leaf, int nleaf, int brick_dim,
+                                     GxRange* __restrict__ out)
+{
+    const int n = blockIdx.x;
+    if (n >= nleaf) return;
+    const GxLeafRec L = leaf[n];
+    float lo = INFINITY, hi = -INFINITY;
+    if (L.vx >= 0) {
+        const int total = brick_dim * brick_dim * brick_dim;
+        for (int i = threadIdx.x; i < total; i += blockDim.x) {
+            const int x = i % brick_dim, y = (i / brick_dim) % brick_dim, z = i / (brick_dim * brick_dim);
+            const float v = tex3D<float>(point_tex, float(L.vx - 1 + x) + 0.5f, float(L.vy - 1 + y) + 0.5f, float(L.vz - 1 + z) + 0.5f);
+            lo = fminf(lo, v); hi = fmaxf(hi, v);
+        }
+    }
+    gx_block_minmax(lo, hi);
     if (threadIdx.x == 0) {
-        for (int w = 1; w < (blockDim.x >> 5); w++) { lo = fminf(lo, slo[w]); hi = fmaxf(hi, shi[w]); }
-        range[slot].lo = lo; range[slot].hi = hi;
+        GxRange r;
+        r.lo = (L.vx >= 0) ? lo : -INFINITY; r.hi = (L.vx >= 0) ? hi : INFINITY;
+        out[n] = r;
     }
 }
 
-// value range per leaf = range of the brick slot the leaf's mValue points at (run when both topology and atlas are in)
-__global__ void gx_leaf_ranges(const GxLeafRec* __restrict__ leaf, int nleaf, const GxRange* __restrict__ slot_range,
-                               int nslots, GxRange* __restrict__ out)
+// brick-major copy for the linear sampler: block n = the brick_dim^3 texels of leaf n, x fastest; one CTA per leaf
+__global__ void gx_copy_bricks_array(cudaTextureObject_t point_tex, const GxLeafRec* __restrict__ leaf, int nleaf, int brick_dim,
+                                     int brick_stride, float* __restrict__ bricks)
+{
+    const int n = blockIdx.x;
+    if (n >= nleaf) return;
+    const GxLeafRec L = leaf[n];
+    float* dst = bricks + size_t(n) * size_t(brick_stride);
+    const int total = brick_dim * brick_dim * brick_dim;
+    for (int i = threadIdx.x; i < brick_stride; i += blockDim.x) {
+        float v = 0.f;
+        if (i < total && L.vx >= 0) {
+            const int x = i % brick_dim, y = (i / brick_dim) % brick_dim, z = i / (brick_dim * brick_dim);
+            v = tex3D<float>(point_tex, float(L.vx - 1 + x) + 0.5f, float(L.vy - 1 + y) + 0.5f, float(L.vz - 1 + z) + 0.5f);
+        }
+        dst[i] = v;
+    }
+}
+
+// brick slot -> leaf index (calibration aid only: gvdbx_sample_points takes atlas-space points)
+__global__ void gx_build_slot_map(const GxLeafRec* __restrict__ leaf, int nleaf, int brick_dim, int cnt_x, int cnt_y, int* __restrict__ slot_leaf)
 {
     const int n = blockIdx.x * blockDim.x + threadIdx.x;
-    if (n >= nleaf) return;
-    const int slot = leaf[n].base / GX_BRICK_STRIDE;
-    GxRange r;
-    r.lo = -INFINITY; r.hi = INFINITY;                     // unknown slot: never culled
-    if (leaf[n].vx >= 0 && slot >= 0 && slot < nslots) r = slot_range[slot];
-    out[n] = r;
+    if (n >= nleaf || leaf[n].vx < 0) return;
+    const int sx = (leaf[n].vx - 1) / brick_dim, sy = (leaf[n].vy - 1) / brick_dim, sz = (leaf[n].vz - 1) / brick_dim;
+    slot_leaf[(size_t(sz) * cnt_y + sy) * cnt_x + sx] = n;
 }
 
 // scatter gathered tile buffers [nranks][slots][ts*ts] back into a row-major frame
@@ -100,19 +140,18 @@ __global__ void gx_assemble_tiles(const uchar4* __restrict__ gathered, uchar4* _
 
 // calibration: hardware filter vs software model at arbitrary atlas-space points
 __global__ void gx_sample_points_kernel(GxParams P, const float* __restrict__ xyz, int n, int cnt_x, int cnt_y,
-                                        float* __restrict__ out_tex, float* __restrict__ out_lin)
+                                        const int* __restrict__ slot_leaf, float* __restrict__ out_tex, float* __restrict__ out_lin)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     float x = xyz[3 * i], y = xyz[3 * i + 1], z = xyz[3 * i + 2];
     out_tex[i] = tex3D<float>(P.tex, x, y, z);
     GxSampler<GX_SAMPLER_LINEAR, false> s(P);
-    GxLeafRec L;
-    int sx = int(x) / GX_BRICK_DIM, sy = int(y) / GX_BRICK_DIM, sz = int(z) / GX_BRICK_DIM;
-    L.vx = sx * GX_BRICK_DIM + 1; L.vy = sy * GX_BRICK_DIM + 1; L.vz = sz * GX_BRICK_DIM + 1;
-    L.base = ((sz * cnt_y + sy) * cnt_x + sx) * GX_BRICK_STRIDE;
-    L.px = L.py = L.pz = L.pad = 0;
-    s.enter(L);
+    const int bd = P.brick_dim;
+    int sx = int(x) / bd, sy = int(y) / bd, sz = int(z) / bd;
+    const int lf = slot_leaf[(size_t(sz) * cnt_y + sy) * cnt_x + sx];
+    if (lf < 0) { out_lin[i] = 0.f; return; }
+    s.enter(P.leaf[lf]);
     out_lin[i] = s.tri(x, y, z);
 }
 
@@ -130,10 +169,10 @@ __global__ void gx_build_deep_lut(const float4* __restrict__ src, float4* __rest
 
 // ------------------------------------------------------------------------------------------------ apron update
 // VolumeGVDB::UpdateApron for a float channel with apron 1 (gvdb_volume_gvdb.cpp:4418-4453, kernel
-// cuda_gvdb_operators.cuh:72-126): every texel of the six 10x10 faces of every brick takes the value of the voxel that
-// occupies its index-space position in whichever leaf contains it (top-down point query), else `boundval`.  One CTA per
-// leaf; reads only interior voxels and writes only apron texels, so the pass is race-free.  Both copies of the atlas
-// are kept coherent: the 3-D array (through a surface object) and the brick-major layout.
+// cuda_gvdb_operators.cuh:72-126): every texel of the six faces of every brick takes the value of the voxel that occupies
+// its index-space position in whichever leaf contains it (top-down point query), else `boundval`.  One CTA per leaf;
+// reads only interior voxels and writes only apron texels, so the pass is race-free.  Both copies of the atlas are kept
+// coherent: the 3-D array (through a surface object) and, if it has been built, the brick-major copy.
 __global__ void gx_update_apron_kernel(const __grid_constant__ GxParams P, cudaSurfaceObject_t surf, float* __restrict__ bricks,
                                        int nleaf, float boundval)
 {
@@ -142,16 +181,17 @@ __global__ void gx_update_apron_kernel(const __grid_constant__ GxParams P, cudaS
     const GxLeafRec L = P.leaf[leaf];
     if (L.vx < 0) return;
     GxCount cnt = {0, 0, 0, 0, 0, 0};
-    for (int i = threadIdx.x; i < 6 * GX_BRICK_DIM * GX_BRICK_DIM; i += blockDim.x) {
-        const int side = i / (GX_BRICK_DIM * GX_BRICK_DIM), u = (i / GX_BRICK_DIM) % GX_BRICK_DIM, v = i % GX_BRICK_DIM;
-        int bx, by, bz;                                   // texel inside the 10^3 brick
+    const int BD = P.brick_dim;
+    for (int i = threadIdx.x; i < 6 * BD * BD; i += blockDim.x) {
+        const int side = i / (BD * BD), u = (i / BD) % BD, v = i % BD;
+        int bx, by, bz;                                   // texel inside the brick
         switch (side) {
         case 0:  bx = 0; by = u; bz = v; break;
         case 1:  bx = u; by = 0; bz = v; break;
         case 2:  bx = u; by = v; bz = 0; break;
-        case 3:  bx = GX_BRICK_DIM - 1; by = u; bz = v; break;
-        case 4:  bx = u; by = GX_BRICK_DIM - 1; bz = v; break;
-        default: bx = u; by = v; bz = GX_BRICK_DIM - 1; break;
+        case 3:  bx = BD - 1; by = u; bz = v; break;
+        case 4:  bx = u; by = BD - 1; bz = v; break;
+        default: bx = u; by = v; bz = BD - 1; break;
         }
         // index-space centre of the texel (getAtlasToWorld, cuda_gvdb_nodes.cuh:145-153)
         const float3 wpos = make_float3(float(L.px) + float(bx - 1) + 0.5f, float(L.py) + float(by - 1) + 0.5f, float(L.pz) + float(bz - 1) + 0.5f);
@@ -163,40 +203,25 @@ __global__ void gx_update_apron_kernel(const __grid_constant__ GxParams P, cudaS
             value = surf3Dread<float>(surf, int(unsigned(offs.x)) * int(sizeof(float)), int(unsigned(offs.y)), int(unsigned(offs.z)));
         }
         surf3Dwrite(value, surf, (L.vx - 1 + bx) * int(sizeof(float)), L.vy - 1 + by, L.vz - 1 + bz);
-        bricks[size_t(L.base) + (bz * GX_BRICK_DIM + by) * GX_BRICK_DIM + bx] = value;
+        if (bricks != nullptr) bricks[size_t(leaf) * size_t(P.brick_stride) + (bz * BD + by) * BD + bx] = value;
     }
 }
 
-// value range per brick slot from the brick-major layout (after the aprons changed)
-__global__ void gx_brick_ranges(const float* __restrict__ bricks, GxRange* __restrict__ range)
-{
-    const float* b = bricks + size_t(blockIdx.x) * GX_BRICK_STRIDE;
-    float lo = INFINITY, hi = -INFINITY;
-    for (int i = threadIdx.x; i < GX_BRICK_DIM * GX_BRICK_DIM * GX_BRICK_DIM; i += blockDim.x) { const float v = b[i]; lo = fminf(lo, v); hi = fmaxf(hi, v); }
-    __shared__ float slo[8], shi[8];
-    for (int o = 16; o > 0; o >>= 1) { lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, o)); hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, o)); }
-    if ((threadIdx.x & 31) == 0) { slo[threadIdx.x >> 5] = lo; shi[threadIdx.x >> 5] = hi; }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        for (int w = 1; w < (blockDim.x >> 5); w++) { lo = fminf(lo, slo[w]); hi = fmaxf(hi, shi[w]); }
-        range[blockIdx.x].lo = lo; range[blockIdx.x].hi = hi;
-    }
-}
-
-// SHADE_VOXEL occupancy bits: for every leaf, bit (z, y * 8 + x) of word z = (interior voxel (x, y, z) > thresh).  The
-// comparison is the one raySurfaceVoxelBrick makes per DDA step (cuda_gvdb_raycast.cuh:241) on the value a texel-centre
+// SHADE_VOXEL occupancy bits (8^3 bricks): for every leaf, bit (y * 8 + x) of word z = (interior voxel (x, y, z) > thresh).
+// The comparison is the one raySurfaceVoxelBrick makes per DDA step (cuda_gvdb_raycast.cuh:241) on the value a texel-centre
 // fetch returns, i.e. the stored texel itself.  One 64-thread CTA per leaf, one byte (a row of 8 voxels) per thread.
-__global__ void gx_build_voxel_mask(const GxLeafRec* __restrict__ leaf, int nleaf, const float* __restrict__ bricks, float thresh,
+__global__ void gx_build_voxel_mask(cudaTextureObject_t point_tex, const GxLeafRec* __restrict__ leaf, int nleaf, float thresh,
                                     unsigned char* __restrict__ out)
 {
     const int n = blockIdx.x;
     if (n >= nleaf) return;
     const int z = threadIdx.x >> 3, y = threadIdx.x & 7;
     unsigned bits = 0;
-    if (leaf[n].vx >= 0) {
-        const float* row = bricks + size_t(leaf[n].base) + ((z + 1) * GX_BRICK_DIM + (y + 1)) * GX_BRICK_DIM + 1;
+    const GxLeafRec L = leaf[n];
+    if (L.vx >= 0) {
         #pragma unroll
-        for (int x = 0; x < 8; x++) bits |= (row[x] > thresh ? 1u : 0u) << x;
+        for (int x = 0; x < 8; x++)
+            bits |= (tex3D<float>(point_tex, float(L.vx + x) + 0.5f, float(L.vy + y) + 0.5f, float(L.vz + z) + 0.5f) > thresh ? 1u : 0u) << x;
     }
     out[size_t(n) * 64 + z * 8 + y] = (unsigned char)bits;
 }
@@ -220,8 +245,9 @@ __global__ void gx_signal_many_kernel(GxFlagList L, int n, unsigned int value)
     if (threadIdx.x < n) asm volatile("st.release.sys.global.u32 [%0], %1;" :: "l"(L.p[threadIdx.x]), "r"(value) : "memory");
 }
 // one thread: polls a LOCAL flag until it reaches `value`; bounded (~20 s) so that a lost peer cannot wedge the GPU —
-// on timeout flag[1] is set to 0xDEAD and the stream continues
-__global__ void gx_wait_kernel(unsigned int* flag, unsigned int value)
+// on timeout flag[1] is set to 0xDEAD, a sticky error bit is raised in the context (gvdbx_sync then fails) and the stream continues
+#define GX_ERR_WAIT_TIMEOUT 0x100
+__global__ void gx_wait_kernel(unsigned int* flag, unsigned int value, int* err)
 {
     const long long t0 = clock64();
     for (;;) {
@@ -229,6 +255,6 @@ __global__ void gx_wait_kernel(unsigned int* flag, unsigned int value)
         asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
         if (int(v - value) >= 0) return;
         __nanosleep(256);
-        if (clock64() - t0 > 40000000000ll) { flag[1] = 0xDEADu; return; }
+        if (clock64() - t0 > 40000000000ll) { flag[1] = 0xDEADu; if (err) atomicOr(err, GX_ERR_WAIT_TIMEOUT); return; }
     }
 }

@@ -179,7 +179,19 @@ class PeerFrameRing:
         self._opened.append(p)
         return p
 
+    def check(self):
+        """raises GvdbxError if any stream-ordered wait of this rank ran into its ~20 s timeout (lost peer, stalled consumer):
+        the polling kernel then lets the stream continue, so frames after it may be incomplete or overwritten — the context
+        keeps a sticky error bit that gvdbx_sync reports"""
+        self.r.sync()
+
     def close(self):
+        try:
+            self.check()
+        finally:
+            self._release_memory()
+
+    def _release_memory(self):
         for p in self._opened:
             self.r.peer_close(p)
         for p in self._own:

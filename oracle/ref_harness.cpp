@@ -35,6 +35,7 @@
 #include <string>
 #include <vector>
 #include <algorithm>
+#include <unordered_map>
 #include <sys/stat.h>
 
 #include "scenes.h"
@@ -153,6 +154,7 @@ int main(int argc, char** argv)
                                                                 // F_LINEAR is rejected by CUDA for an integer-read texture
     double t_cfg = now_s() - t0;
     t0 = now_s();
+    // one ActivateSpace per 8^3 scene brick; with Configure(.., q0 > 3) several scene bricks share one leaf (16^3 / 32^3 voxels)
     for (int n = 0; n < S.nbricks; n++)
         gvdb.ActivateSpace(Vector3DF((float)S.brick_pos[3 * n], (float)S.brick_pos[3 * n + 1], (float)S.brick_pos[3 * n + 2]));
     double t_act = now_s() - t0;
@@ -163,20 +165,36 @@ int main(int argc, char** argv)
     double t_fin = now_s() - t0;
     gvdb.SetEpsilon(P.epsilon, 256);
 
-    // ---- atlas upload: brick n (activation order) == leaf n (PoolAlloc hands out consecutive indices)
+    // ---- atlas upload: every scene brick goes to its place inside its leaf's atlas brick (voxels no scene brick covers
+    // keep the background value: 0 for the densities, +band for the signed distance field)
     Vector3DI ares = gvdb.mPool->getAtlasRes(0);
     size_t atexels = (size_t)ares.x * ares.y * ares.z;
+    const int res0 = 1 << cfg[4];
     std::vector<float> atlas(atexels, 0.0f);
     int nleaf = (int)gvdb.mPool->getPoolTotalCnt(0, 0);
-    if (nleaf != S.nbricks) { fprintf(stderr, "leaf count %d != bricks %d\n", nleaf, S.nbricks); return 3; }
-    for (int n = 0; n < nleaf; n++) {
-        Node* nd = gvdb.getNode(0, 0, n);
-        if (nd->mPos.x != S.brick_pos[3 * n] || nd->mPos.y != S.brick_pos[3 * n + 1] || nd->mPos.z != S.brick_pos[3 * n + 2]) {
-            fprintf(stderr, "leaf %d pos mismatch\n", n); return 3;
+    if (res0 == 8 && nleaf != S.nbricks) { fprintf(stderr, "leaf count %d != bricks %d\n", nleaf, S.nbricks); return 3; }
+    if (res0 != 8 && P.kind == SCN_KIND_SDF) {
+        for (int l = 0; l < nleaf; l++) {
+            Node* nd = gvdb.getNode(0, 0, l);
+            for (int k = 0; k < res0; k++) for (int j = 0; j < res0; j++)
+                std::fill_n(&atlas[((size_t)(nd->mValue.z + k) * ares.y + (nd->mValue.y + j)) * ares.x + nd->mValue.x], res0, 12.0f);
         }
+    }
+    std::unordered_map<unsigned long long, int> leaf_at;          // leaf min corner -> leaf index
+    auto key = [](int x, int y, int z) { return ((unsigned long long)(unsigned)x << 42) ^ ((unsigned long long)(unsigned)y << 21) ^ (unsigned long long)(unsigned)z; };
+    for (int l = 0; l < nleaf; l++) { Node* nd = gvdb.getNode(0, 0, l); leaf_at[key(nd->mPos.x, nd->mPos.y, nd->mPos.z)] = l; }
+    for (int n = 0; n < S.nbricks; n++) {
+        const int bx = S.brick_pos[3 * n], by = S.brick_pos[3 * n + 1], bz = S.brick_pos[3 * n + 2];
+        auto it = leaf_at.find(key(bx / res0 * res0, by / res0 * res0, bz / res0 * res0));
+        if (it == leaf_at.end()) { fprintf(stderr, "no leaf for brick %d\n", n); return 3; }
+        const int lf = it->second;
+        Node* nd = gvdb.getNode(0, 0, lf);
+        const int ox = S.brick_pos[3 * n] - nd->mPos.x, oy = S.brick_pos[3 * n + 1] - nd->mPos.y, oz = S.brick_pos[3 * n + 2] - nd->mPos.z;
+        if (ox < 0 || oy < 0 || oz < 0 || ox + 8 > res0 || oy + 8 > res0 || oz + 8 > res0) { fprintf(stderr, "brick %d outside its leaf\n", n); return 3; }
+        if (res0 == 8 && lf != n) { fprintf(stderr, "leaf %d is not brick %d\n", lf, n); return 3; }
         const float* v = S.values + 512 * (size_t)n;
         for (int k = 0; k < 8; k++) for (int j = 0; j < 8; j++) {
-            float* dst = &atlas[((size_t)(nd->mValue.z + k) * ares.y + (nd->mValue.y + j)) * ares.x + nd->mValue.x];
+            float* dst = &atlas[((size_t)(nd->mValue.z + oz + k) * ares.y + (nd->mValue.y + oy + j)) * ares.x + nd->mValue.x + ox];
             memcpy(dst, v + (k * 8 + j) * 8, 8 * sizeof(float));
         }
     }
@@ -189,7 +207,7 @@ int main(int argc, char** argv)
         color.assign(atexels * 4, 0);
         for (int n = 0; n < nleaf; n++) {
             Node* nd = gvdb.getNode(0, 0, n);
-            for (int k = 0; k < 8; k++) for (int j = 0; j < 8; j++) for (int i = 0; i < 8; i++) {
+            for (int k = 0; k < res0; k++) for (int j = 0; j < res0; j++) for (int i = 0; i < res0; i++) {
                 const int wx = nd->mPos.x + i, wy = nd->mPos.y + j, wz = nd->mPos.z + k;
                 unsigned char* c = &color[4 * (((size_t)(nd->mValue.z + k) * ares.y + (nd->mValue.y + j)) * ares.x + nd->mValue.x + i)];
                 c[0] = (unsigned char)(40 + (wx * 37 + wy * 11) % 216); c[1] = (unsigned char)(40 + (wy * 29 + wz * 7) % 216);

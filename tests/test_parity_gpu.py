@@ -815,3 +815,79 @@ def test_full_size_bit_exact_vs_live_reference(scenes, pkg, torch_cuda, tmp_path
     else:
         ok, over1, ps = tolerance_ok(lin, light["rgba"][m])
         assert ok, (m, over1, ps)
+
+
+# ------------------------------------------------------------------------------------------------ brick sizes
+@pytest.mark.skipif(not refcmp.have_ref(), reason="oracle/_ref not built")
+@pytest.mark.parametrize("preset,config", [("cfg4_small", (3, 3, 3, 3, 4)), ("cfg4_small", (3, 3, 3, 3, 5)), ("cfg1_small", (3, 3, 3, 4, 4)),
+                                           ("cfg3_small", (3, 3, 3, 3, 5)), ("cfg2_small", (3, 3, 3, 3, 4))])
+def test_live_reference_brick_sizes(pkg, torch_cuda, tmp_path, preset, config):
+    """16^3 and 32^3 bricks — Configure(3,3,3,3,4) (gResample, gPointCloud) and Configure(3,3,3,3,5) (gSprayDeposit,
+    gFluidSurface, gPointFusion, gJetsonTX): the unmodified reference builds and renders such a tree now (atlas bricks of
+    18^3 / 34^3 texels); with its pools, atlas, VDBInfo and ScnInfo imported every one of the ten modes must match bit for bit
+    with the texture sampler, voxel id / depth included, and the linear sampler (brick-major blocks of 18^3 / 34^3) must stay
+    within the north_star tolerance."""
+    d = str(tmp_path / "dump")
+    refcmp.run_ref(preset, d, modes=list(MODES) + list(refcmp.MODES2) + ["voxelid"], size=(226, 150), config=config)
+    dump = refcmp.load_dump(d)
+    vdb = np.frombuffer(dump["vdbinfo"], np.int32)
+    assert vdb[0] == config[4] and vdb[10] == (1 << config[4]) and vdb[159] == (1 << config[4]) + 2      # dim[0], res[0], brick_res
+    res = refcmp.compare(dump, pkg, list(MODES), verbose=False)
+    for m in MODES:
+        assert res[m]["tex"]["rgba_mismatch_pixels"] == 0, (m, res[m]["tex"])
+        assert res[m]["tex"].get("hit_mismatch_pixels", 0) == 0 and res[m]["tex"].get("norm_mismatch_pixels", 0) == 0
+        assert res[m]["tex"].get("raw_clr_mismatch_pixels", 0) == 0
+        assert res[m]["tex"]["plain_equals_debug"]
+        assert res[m]["linear"]["rgba_over1_pixels"] <= 2e-3 * res[m]["linear"]["pixels"], (m, res[m]["linear"])
+    assert res["voxel"]["linear"]["rgba_mismatch_pixels"] == 0
+    res2 = refcmp.compare2(dump, pkg, verbose=False)
+    for m in refcmp.MODES2:
+        assert res2[m]["tex"]["rgba_mismatch_pixels"] == 0, (m, res2[m]["tex"])
+        assert res2[m]["tex"].get("hit_mismatch_pixels", 0) == 0
+    r = refcmp.make_renderer(dump, pkg)
+    _, dbg, _ = refcmp.render_mine(r, dump, "voxel", 0, debug=True)
+    st = refcmp.compare_voxel_ids(dbg, dump["hit"]["voxelid"])
+    assert st["hit_mismatch"] == 0 and st["depth_mismatch"] == 0 and st["voxel_mismatch"] == 0 and st["leaf_mismatch"] == 0, st
+    # UpdateApron on these brick sizes: wipe every apron texel, rebuild, compare with the reference's atlas byte for byte
+    bd = (1 << config[4]) + 2
+    atlas = dump["atlas"]
+    recs = np.frombuffer(dump["pool0"][0].tobytes(), np.int32).reshape(-1, 16)
+    wiped = atlas.copy()
+    for vx, vy, vz in recs[:, 4:7]:
+        blk = wiped[vz - 1:vz - 1 + bd, vy - 1:vy - 1 + bd, vx - 1:vx - 1 + bd]
+        keep = blk[1:-1, 1:-1, 1:-1].copy()
+        blk[...] = 777.0
+        blk[1:-1, 1:-1, 1:-1] = keep
+    assert not np.array_equal(wiped, atlas)
+    r.import_atlas_host(wiped)
+    r.update_apron(0.0)
+    back = r.export_atlas_host(atlas.shape)
+    assert np.array_equal(back.view(np.uint32), atlas.view(np.uint32)), f"{(back != atlas).sum()} texels differ"
+    img, _, _ = refcmp.render_mine(r, dump, "trilinear", 0)
+    assert np.array_equal(img, dump["rgba"]["trilinear"])
+    lin, _, _ = refcmp.render_mine(r, dump, "trilinear", 1)          # brick-major copy rebuilt from the updated array
+    assert tolerance_ok(lin, dump["rgba"]["trilinear"])[0]
+    r.close()
+
+
+def test_import_rejects_malformed_pools(ora, pkg, torch_cuda):
+    """a leaf whose mValue lies outside the atlas, a child entry past the node pool, a stale VDBInfo: error codes, no
+    out-of-bounds reads later"""
+    p, vol = ora.scene_volume("cfg1_tiny")
+    r = pkg.Renderer(0)
+    bad = {l: b.copy() for l, b in vol["pool0"].items()}
+    rec = bad[0].view(np.int32).reshape(-1, 16)
+    rec[3, 4] = 100000                                   # mValue.x of leaf 3
+    with pytest.raises(pkg.GvdbxError):
+        r.import_topology_host(vol["vdbinfo"], bad, vol["pool1"])
+    bad1 = {l: b.copy() for l, b in vol["pool1"].items()}
+    lst = bad1[1].view(np.uint64)
+    on = np.nonzero(lst != np.uint64(0xFFFFFFFFFFFFFFFF))[0]
+    lst[on[0]] = np.uint64((1 << 30) << 16)              # child index far past the leaf pool
+    with pytest.raises(pkg.GvdbxError):
+        r.import_topology_host(vol["vdbinfo"], vol["pool0"], bad1)
+    r.import_topology_host(vol["vdbinfo"], vol["pool0"], vol["pool1"])
+    with pytest.raises(pkg.GvdbxError):                  # atlas of another size than VDBInfo.atlas_res announces
+        r.import_atlas_host(np.zeros((20, 160, 160), np.float32))
+    r.import_atlas_host(vol["atlas"])
+    r.close()
