@@ -52,77 +52,74 @@ __device__ __forceinline__ int gx_node_at_point(const GxParams& P, float3 pos, G
 }
 
 // ------------------------------------------------------------------------------------------------ tricubic
-// 27 fetches at texel CORNERS (integer atlas coordinates: each is the mean of 8 texels), quadratic B-spline weights.
-// Reaches one texel beyond the apron for p < 1, so neither the brick-major layout nor value-range culling applies.
+// Quadratic B-spline reconstruction over a 3x3x3 stencil of texel CORNERS (integer atlas coordinates: each corner fetch is
+// the hardware mean of its eight texels).  Separable: weights w(t) = {(1-t)^2, 2 t (1-t), t^2} with t = frac/2 + 1/4 per axis,
+// reduced along x inside a row, along y inside a slice, along z across the three slices.  For p < 1 the stencil reaches one
+// texel beyond the apron, so neither the brick-major layout nor value-range culling applies to this mode.
+// (what is computed: getTricubic, cuda_gvdb_raycast.cuh:32-96; bit-exactness fixes the operand order of every sum)
+struct GxSplineW { float3 lo, mid, hi; };              // per axis: weight of stencil index 0, 1, 2
+
+__device__ __forceinline__ GxSplineW gx_spline_weights(float3 p)
+{
+    const float3 t = (p - gx_floor(p)) * 0.5 + 0.25;
+    const float3 u = (1.0 - t);
+    GxSplineW w;
+    w.lo = u * u; w.hi = t * t; w.mid = u * t * 2.0;
+    return w;
+}
+// one row of three corners along x at (y, z), reduced with the x weights
+template <class S>
+__device__ __forceinline__ float gx_spline_row(const S& smp, float x0, float y, float z, const GxSplineW& w)
+{
+    const float c0 = smp.tri(x0, y, z), c1 = smp.tri(x0 + 1.0f, y, z), c2 = smp.tri(x0 + 2.0f, y, z);
+    return c0 * w.lo.x + c1 * w.mid.x + c2 * w.hi.x;
+}
+// one z slice: three rows, reduced with the y weights
+template <class S>
+__device__ __forceinline__ float gx_spline_slice(const S& smp, float3 q, float z, const GxSplineW& w)
+{
+    const float r0 = gx_spline_row(smp, q.x, q.y, z, w);
+    const float r1 = gx_spline_row(smp, q.x, q.y + 1.0f, z, w);
+    const float r2 = gx_spline_row(smp, q.x, q.y + 2.0f, z, w);
+    return r0 * w.lo.y + r1 * w.mid.y + r2 * w.hi.y;
+}
 template <class S>
 __device__ __forceinline__ float gx_tricubic(const S& smp, float3 p, float3 offs, GxCount& cnt)
 {
-    const float MID = 1.0;
-    const float HI = 2.0;
-    float3 q = gx_floor(p + offs) - MID;
-    float3 tb = (p - gx_floor(p)) * 0.5 + 0.25;
-    float3 ta = (1.0 - tb);
-    float3 ta2 = ta * ta;
-    float3 tb2 = tb * tb;
-    float3 tab = ta * tb * 2.0;
+    const float3 q = gx_floor(p + offs) - 1.0f;        // corner (0,0,0) of the stencil
+    const GxSplineW w = gx_spline_weights(p);
     cnt.s_tri += 27;
-
-    float tv[9];
-    tv[0] = smp.tri(q.x,       q.y,       q.z);
-    tv[1] = smp.tri(q.x + MID, q.y,       q.z);
-    tv[2] = smp.tri(q.x + HI,  q.y,       q.z);
-    tv[3] = smp.tri(q.x,       q.y + MID, q.z);
-    tv[4] = smp.tri(q.x + MID, q.y + MID, q.z);
-    tv[5] = smp.tri(q.x + HI,  q.y + MID, q.z);
-    tv[6] = smp.tri(q.x,       q.y + HI,  q.z);
-    tv[7] = smp.tri(q.x + MID, q.y + HI,  q.z);
-    tv[8] = smp.tri(q.x + HI,  q.y + HI,  q.z);
-    float3 abc = make_float3(tv[0] * ta2.x + tv[1] * tab.x + tv[2] * tb2.x,
-                             tv[3] * ta2.x + tv[4] * tab.x + tv[5] * tb2.x,
-                             tv[6] * ta2.x + tv[7] * tab.x + tv[8] * tb2.x);
-    tv[0] = smp.tri(q.x,       q.y,       q.z + MID);
-    tv[1] = smp.tri(q.x + MID, q.y,       q.z + MID);
-    tv[2] = smp.tri(q.x + HI,  q.y,       q.z + MID);
-    tv[3] = smp.tri(q.x,       q.y + MID, q.z + MID);
-    tv[4] = smp.tri(q.x + MID, q.y + MID, q.z + MID);
-    tv[5] = smp.tri(q.x + HI,  q.y + MID, q.z + MID);
-    tv[6] = smp.tri(q.x,       q.y + HI,  q.z + MID);
-    tv[7] = smp.tri(q.x + MID, q.y + HI,  q.z + MID);
-    tv[8] = smp.tri(q.x + HI,  q.y + HI,  q.z + MID);
-    float3 def = make_float3(tv[0] * ta2.x + tv[1] * tab.x + tv[2] * tb2.x,
-                             tv[3] * ta2.x + tv[4] * tab.x + tv[5] * tb2.x,
-                             tv[6] * ta2.x + tv[7] * tab.x + tv[8] * tb2.x);
-    tv[0] = smp.tri(q.x,       q.y,       q.z + HI);
-    tv[1] = smp.tri(q.x + MID, q.y,       q.z + HI);
-    tv[2] = smp.tri(q.x + HI,  q.y,       q.z + HI);
-    tv[3] = smp.tri(q.x,       q.y + MID, q.z + HI);
-    tv[4] = smp.tri(q.x + MID, q.y + MID, q.z + HI);
-    tv[5] = smp.tri(q.x + HI,  q.y + MID, q.z + HI);
-    tv[6] = smp.tri(q.x,       q.y + HI,  q.z + HI);
-    tv[7] = smp.tri(q.x + MID, q.y + HI,  q.z + HI);
-    tv[8] = smp.tri(q.x + HI,  q.y + HI,  q.z + HI);
-    float3 ghi = make_float3(tv[0] * ta2.x + tv[1] * tab.x + tv[2] * tb2.x,
-                             tv[3] * ta2.x + tv[4] * tab.x + tv[5] * tb2.x,
-                             tv[6] * ta2.x + tv[7] * tab.x + tv[8] * tb2.x);
-    float3 jkl = make_float3(abc.x * ta2.y + abc.y * tab.y + abc.z * tb2.y,
-                             def.x * ta2.y + def.y * tab.y + def.z * tb2.y,
-                             ghi.x * ta2.y + ghi.y * tab.y + ghi.z * tb2.y);
-    return jkl.x * ta2.z + jkl.y * tab.z + jkl.z * tb2.z;
+    const float s0 = gx_spline_slice(smp, q, q.z, w);
+    const float s1 = gx_spline_slice(smp, q, q.z + 1.0f, w);
+    const float s2 = gx_spline_slice(smp, q, q.z + 2.0f, w);
+    return s0 * w.lo.z + s1 * w.mid.z + s2 * w.hi.z;
 }
 
+// central difference of the tricubic field over +-0.5 voxel along one axis (backward minus forward: the surface normal
+// points against the gradient), cuda_gvdb_raycast.cuh:159-169
+template <int AXIS, class S>
+__device__ __forceinline__ float gx_tricubic_slope(const S& smp, float3 p, float3 offs, GxCount& cnt)
+{
+    const float h = 0.5;
+    float3 back = p, fwd = p;
+    if (AXIS == 0) { back.x = p.x + -h; fwd.x = p.x + h; }
+    if (AXIS == 1) { back.y = p.y + -h; fwd.y = p.y + h; }
+    if (AXIS == 2) { back.z = p.z + -h; fwd.z = p.z + h; }
+    return (gx_tricubic(smp, back, offs, cnt) - gx_tricubic(smp, fwd, offs, cnt)) / (2 * h);
+}
 template <class S>
 __device__ __forceinline__ float3 gx_gradient_tricubic(const S& smp, float3 p, float3 offs, GxCount& cnt)
 {
-    const float vs = 0.5;
     float3 g;
-    g.x = (gx_tricubic(smp, p + make_float3(-vs, 0, 0), offs, cnt) - gx_tricubic(smp, p + make_float3(vs, 0, 0), offs, cnt)) / (2 * vs);
-    g.y = (gx_tricubic(smp, p + make_float3(0, -vs, 0), offs, cnt) - gx_tricubic(smp, p + make_float3(0, vs, 0), offs, cnt)) / (2 * vs);
-    g.z = (gx_tricubic(smp, p + make_float3(0, 0, -vs), offs, cnt) - gx_tricubic(smp, p + make_float3(0, 0, vs), offs, cnt)) / (2 * vs);
+    g.x = gx_tricubic_slope<0>(smp, p, offs, cnt);
+    g.y = gx_tricubic_slope<1>(smp, p, offs, cnt);
+    g.z = gx_tricubic_slope<2>(smp, p, offs, cnt);
     return gx_normalize(g);
 }
 
-// SHADE_TRICUBIC brick function: fixed-step march (no start snap), first tricubic sample >= THRESH, one secant
-// refinement step back along the ray.                                    cuda_gvdb_raycast.cuh:316-339
+// SHADE_TRICUBIC brick function (what: raySurfaceTricubicBrick, cuda_gvdb_raycast.cuh:316-339): fixed-step march from the
+// unsnapped entry point; the first sample at or above THRESH is pulled back along the ray by the secant through it and the
+// sample one FINESTEP before it.  In-brick test on the float bit patterns like the other marchers (gvdbx_trace.cuh).
 template <class S>
 __device__ __forceinline__ void gx_brick_tricubic(const GxParams& P, S& smp, int nodeid, float3 t, float3 pos, float3 dir,
                                                   GxHit& h, GxCount& cnt)
@@ -130,18 +127,17 @@ __device__ __forceinline__ void gx_brick_tricubic(const GxParams& P, S& smp, int
     const GxLeafRec L = gx_leaf(P, nodeid);
     cnt.n_desc++;
     smp.enter(L);
-    float3 vmin = make_float3(float(L.px), float(L.py), float(L.pz));
-    float3 o = make_float3(float(L.vx), float(L.vy), float(L.vz));
+    const float3 vmin = make_float3(float(L.px), float(L.py), float(L.pz));
+    const float3 o = make_float3(float(L.vx), float(L.vy), float(L.vz));
     const float res0 = float(gx_res<S>(P, 0));
-    float3 p = pos + t.x * dir - vmin;
-    float3 v;
-
-    for (int iter = 0; iter < GX_MAX_ITER && p.x >= 0 && p.y >= 0 && p.z >= 0 && p.x < res0 && p.y < res0 && p.z < res0; iter++) {
-        v.z = gx_tricubic(smp, p, o, cnt);
-        if (v.z >= P.thresh.x) {
-            v.x = gx_tricubic(smp, p - P.steps.z * dir, o, cnt);
-            v.y = (v.z - P.thresh.x) / (v.z - v.x);
-            p += -v.y * P.steps.z * dir;
+    const float thr = P.thresh.x, fine = P.steps.z;
+    float3 p = gx_poszero(pos + t.x * dir - vmin);
+    for (int iter = 0; iter < GX_MAX_ITER && GX_INB(p, res0); iter++) {
+        const float here = gx_tricubic(smp, p, o, cnt);
+        if (here >= thr) {
+            const float before = gx_tricubic(smp, p - fine * dir, o, cnt);
+            const float back = (here - thr) / (here - before);          // fraction of a fine step to retreat
+            p += -back * fine * dir;
             h.hit = p + vmin;
             h.norm = gx_gradient_tricubic(smp, p, o, cnt);
             h.t = t.x; h.leaf = nodeid; h.vox = gx_i3(gx_floor(h.hit));
@@ -154,8 +150,12 @@ __device__ __forceinline__ void gx_brick_tricubic(const GxParams& P, S& smp, int
 }
 
 // ------------------------------------------------------------------------------------------------ shadow accumulation
-// rayShadowBrick: opacity accumulates in clr.w from 0 towards 1; the ray parameter advances by DIRECTSTEP while the
-// attenuation uses SHADOWSTEP / (1 + 0.4 t) — in DOUBLE, like the reference's literals make it.  No iteration cap.
+// Opacity towards the light (what: rayShadowBrick, cuda_gvdb_raycast.cuh:445-463): every sample is an opaque layer of
+// transparency exp(EXTINCT * alpha(v) * SHADOWSTEP / (1 + 0.4 s)) — evaluated in DOUBLE, as the reference's literals make it —
+// where the attenuation parameter s advances by SHADOWSTEP per sample while the position advances by DIRECTSTEP; opacity
+// accumulates in clr.w from 0 towards 1; no iteration cap.  Four samples per round like the other marchers: positions by
+// the same chain of additions, the four texture fetches and four transfer-table reads in flight before the first layer is
+// applied, layers applied strictly in order, a round cut short exactly where the one-at-a-time loop would stop.
 template <class S>
 __device__ __forceinline__ void gx_brick_shadow(const GxParams& P, S& smp, int nodeid, float3 t, float3 pos, float3 dir,
                                                 GxHit& h, GxCount& cnt)
@@ -163,24 +163,40 @@ __device__ __forceinline__ void gx_brick_shadow(const GxParams& P, S& smp, int n
     const GxLeafRec L = gx_leaf(P, nodeid);
     cnt.n_desc++;
     smp.enter(L);
-    float3 vmin = make_float3(float(L.px), float(L.py), float(L.pz));
-    t.x += P.epsilon;
-    t.y -= P.epsilon;
-    float3 o = make_float3(float(L.vx), float(L.vy), float(L.vz));
-    float3 p = pos + t.x * dir - vmin;
-    float3 pt = P.steps.x * dir;
+    const float3 vmin = make_float3(float(L.px), float(L.py), float(L.pz));
+    const float3 o = make_float3(float(L.vx), float(L.vy), float(L.vz));
     const float res0 = float(gx_res<S>(P, 0));
     const float inv_range = gx_rcp_approx(P.thresh.z - P.thresh.y);
-    float4& clr = h.clr;
-    float val = 0;
+    const float3 wpt = P.steps.x * dir;
+    float s = t.x + P.epsilon;                          // the brick is entered epsilon further in than rayCast handed over
+    float3 p = gx_poszero(pos + s * dir - vmin);
+    float& opacity = h.clr.w;
 
-    for (; clr.w < 1 && p.x >= 0 && p.y >= 0 && p.z >= 0 && p.x < res0 && p.y < res0 && p.z < res0;) {
-        cnt.s_tri++; cnt.s_lut++;
-        const float4 T = __ldg(&P.transfer[gx_transfer_index(smp.tri(p.x + o.x, p.y + o.y, p.z + o.z), P.thresh.x, inv_range)]);
-        val = exp(P.extinct.x * T.w * P.steps.y / (1.0 + t.x * 0.4));
-        clr.w = 1.0 - (1.0 - clr.w) * val;
-        p += pt;
-        t.x += P.steps.y;
+    while (opacity < 1 && GX_INB(p, res0)) {
+        float3 p1, p2, p3;
+        GX_STEP_ADD(p1, p); GX_STEP_ADD(p2, p1); GX_STEP_ADD(p3, p2);
+        const bool k1 = GX_INB(p1, res0), k2 = GX_INB(p2, res0), k3 = GX_INB(p3, res0);
+        const float v0 = smp.tri(p.x + o.x, p.y + o.y, p.z + o.z);
+        const float v1 = smp.tri(p1.x + o.x, p1.y + o.y, p1.z + o.z);
+        const float v2 = smp.tri(p2.x + o.x, p2.y + o.y, p2.z + o.z);
+        const float v3 = smp.tri(p3.x + o.x, p3.y + o.y, p3.z + o.z);
+        const float a0 = __ldg(&P.transfer[gx_transfer_index(v0, P.thresh.x, inv_range)]).w;
+        const float a1 = __ldg(&P.transfer[gx_transfer_index(v1, P.thresh.x, inv_range)]).w;
+        const float a2 = __ldg(&P.transfer[gx_transfer_index(v2, P.thresh.x, inv_range)]).w;
+        const float a3 = __ldg(&P.transfer[gx_transfer_index(v3, P.thresh.x, inv_range)]).w;
+        // one layer: clr.w = 1 - (1 - clr.w) * exp(...), then the parameter step
+        #define GX_SHADOW_LAYER(alpha) { cnt.s_tri++; cnt.s_lut++;                                              \
+            const float val = exp(P.extinct.x * (alpha) * P.steps.y / (1.0 + s * 0.4));                          \
+            opacity = 1.0 - (1.0 - opacity) * val;                                                             \
+            s += P.steps.y; }
+        int done = 1;
+        GX_SHADOW_LAYER(a0);
+        if (opacity < 1 && k1) { GX_SHADOW_LAYER(a1); done = 2;
+            if (opacity < 1 && k2) { GX_SHADOW_LAYER(a2); done = 3;
+                if (opacity < 1 && k3) { GX_SHADOW_LAYER(a3); done = 4; } } }
+        #undef GX_SHADOW_LAYER
+        if (done < 4) break;            // the loop condition failed inside this round
+        GX_STEP_ADD(p, p3);
     }
 }
 
