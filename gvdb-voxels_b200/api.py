@@ -24,7 +24,7 @@ EXPORTED_SYMBOLS = [
     "gvdbx_import_atlas_array", "gvdbx_import_atlas_host", "gvdbx_import_atlas_device", "gvdbx_import_color_array", "gvdbx_import_color_host", "gvdbx_clear_color", "gvdbx_set_transfer",
     "gvdbx_render", "gvdbx_render_tiles", "gvdbx_tiles_per_rank", "gvdbx_assemble_tiles",
     "gvdbx_render_debug", "gvdbx_raytrace", "gvdbx_read_buffer", "gvdbx_sync", "gvdbx_get_counters",
-    "gvdbx_sample_points", "gvdbx_kernel_params", "gvdbx_update_apron", "gvdbx_export_atlas_host", "gvdbx_render_tiles_direct", "gvdbx_render_tiles_ring", "gvdbx_peer_alloc", "gvdbx_peer_free", "gvdbx_peer_open",
+    "gvdbx_sample_points", "gvdbx_kernel_params", "gvdbx_update_apron", "gvdbx_update_apron_faces", "gvdbx_export_atlas_host", "gvdbx_render_tiles_direct", "gvdbx_render_tiles_ring", "gvdbx_peer_alloc", "gvdbx_peer_free", "gvdbx_peer_open",
     "gvdbx_peer_close", "gvdbx_stream_signal", "gvdbx_stream_signal_add", "gvdbx_stream_signal_many", "gvdbx_stream_wait", "gvdbx_set_stream",
     "gvdbx_read_buffer_async", "gvdbx_lanes", "gvdbx_lane_select", "gvdbx_lane_stream", "gvdbx_lanes_fork", "gvdbx_lanes_join",
 ]
@@ -86,6 +86,7 @@ def lib():
     L.gvdbx_render_tiles_direct.argtypes = [vp, vp, i32, i32, u64, i32, i32, i32]
     L.gvdbx_kernel_params.argtypes = [vp, vp, i32, i32, u64, vp, C.c_size_t]
     L.gvdbx_update_apron.argtypes = [vp, i32, C.c_float]
+    L.gvdbx_update_apron_faces.argtypes = [vp, i32]
     L.gvdbx_export_atlas_host.argtypes = [vp, i32, vp, i32, i32, i32]
     L.gvdbx_render_tiles_ring.argtypes = [vp, vp, i32, i32, u64, i32, i32, i32, u64, C.c_uint32, u64]
     L.gvdbx_peer_alloc.argtypes = [vp, C.c_size_t, C.POINTER(u64), vp]
@@ -224,6 +225,10 @@ class Renderer:
     def update_apron(self, boundval=0.0, chan=0):
         """VolumeGVDB::UpdateApron(chan, boundval) on the imported atlas"""
         self._ck(self._L.gvdbx_update_apron(self._h, chan, C.c_float(boundval)), "gvdbx_update_apron")
+
+    def update_apron_faces(self, chan=0):
+        """VolumeGVDB::UpdateApronFaces(chan): face layers swapped between adjacent bricks"""
+        self._ck(self._L.gvdbx_update_apron_faces(self._h, chan), "gvdbx_update_apron_faces")
 
     def export_atlas_host(self, shape_zyx, chan=0):
         rz, ry, rx = shape_zyx

@@ -522,6 +522,25 @@ extern "C" int gvdbx_update_apron(gvdbx_t* h, int chan, float boundval)
     return gx_build_end(h);
 }
 
+extern "C" int gvdbx_update_apron_faces(gvdbx_t* h, int chan)
+{
+    if (!h) return GVDBX_E_ARG;
+    if (chan != 0) return gx_fail(h, GVDBX_E_UNSUPPORTED, "only channel 0 (T_FLOAT) is supported");
+    if (!h->have_topo || !h->have_atlas) return gx_fail(h, GVDBX_E_STATE, "UpdateApronFaces needs topology and atlas");
+    if (!h->surf) return gx_fail(h, GVDBX_E_UNSUPPORTED, "the atlas array was created without surface load/store");
+    GxCtx ctx_(h);
+    GxParams P;
+    gx_tree_params(h, P);
+    const int n = h->vdb.nodecnt[0];
+    int rc = gx_build_begin(h);
+    if (rc) return rc;
+    gx_update_apron_faces_kernel<<<n, 192, 0, h->stream>>>(P, h->surf, h->d_bricks, n);
+    GX_CUDA(h, cudaGetLastError());
+    gx_leaf_ranges_array<<<n, 128, 0, h->stream>>>(h->tex_point, h->d_leaf, n, h->brick_dim, h->d_leaf_range);
+    GX_CUDA(h, cudaGetLastError());
+    return gx_build_end(h);
+}
+
 // host image of the atlas array, x fastest (the inverse of gvdbx_import_atlas_host; Allocator::AtlasRetrieveSlice per slice)
 extern "C" int gvdbx_export_atlas_host(gvdbx_t* h, int chan, float* texels, int rx, int ry, int rz)
 {

@@ -207,6 +207,54 @@ __global__ void gx_update_apron_kernel(const __grid_constant__ GxParams P, cudaS
     }
 }
 
+// VolumeGVDB::UpdateApronFaces (gvdb_volume_gvdb.cpp:4461-4496, kernel gvdbUpdateApronFacesF cuda_gvdb_operators.cuh:27-61):
+// the cheap apron update after a compute pass — face-adjacent bricks swap their boundary layers: for each of the three
+// lower faces (-x, -y, -z) of a brick that has a neighbour there, the brick's first voxel layer goes into the neighbour's
+// upper apron and the neighbour's last voxel layer into the brick's lower apron (res0 x res0 texels per face; edge and corner
+// texels and faces without a neighbour are left alone).  The reference looks the neighbour up in a host-built table
+// (UpdateNeighbors, :2527-2556: leaf at centre - brick width); here the point query does it on the fly.
+// NOTE: the reference's table stores a MISSING neighbour as ElemNdx(ID_UNDEFL) = 0xFFFF while its kernel tests for 0xFFFFFFFF,
+// so the stock kernel reads leaf 65535 for every boundary brick (out of bounds below 65536 leaves); the intended semantics
+// are implemented, and on faces that do have a neighbour the result equals UpdateApron's (tested against the reference atlas).
+__global__ void gx_update_apron_faces_kernel(const __grid_constant__ GxParams P, cudaSurfaceObject_t surf, float* __restrict__ bricks, int nleaf)
+{
+    const int leaf = blockIdx.x;
+    if (leaf >= nleaf) return;
+    const GxLeafRec L = P.leaf[leaf];
+    if (L.vx < 0) return;
+    GxCount cnt = {0, 0, 0, 0, 0, 0};
+    const int R = P.res[0], BD = P.brick_dim;
+    const float d = float(R);
+    const float3 ct = make_float3(float(L.px) + d * 0.5f, float(L.py) + d * 0.5f, float(L.pz) + d * 0.5f);
+    __shared__ int nbr[3];
+    if (threadIdx.x < 3) {
+        const float3 q = make_float3(ct.x - (threadIdx.x == 0 ? d : 0.f), ct.y - (threadIdx.x == 1 ? d : 0.f), ct.z - (threadIdx.x == 2 ? d : 0.f));
+        int n = gx_node_at_point<GxSampler<GX_SAMPLER_TEX, false>>(P, q, cnt);
+        if (n >= 0 && P.leaf[n].vx < 0) n = -1;
+        nbr[threadIdx.x] = n;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 3 * R * R; i += blockDim.x) {
+        const int side = i / (R * R), u = (i / R) % R, v = i % R;
+        const int n = nbr[side];
+        if (n < 0) continue;
+        const GxLeafRec N = P.leaf[n];
+        int3 vox, inc;
+        if (side == 0)      { vox = make_int3(0, u, v); inc = make_int3(1, 0, 0); }
+        else if (side == 1) { vox = make_int3(u, 0, v); inc = make_int3(0, 1, 0); }
+        else                { vox = make_int3(u, v, 0); inc = make_int3(0, 0, 1); }
+        const int3 vn = make_int3(vox.x + inc.x * (R - 1), vox.y + inc.y * (R - 1), vox.z + inc.z * (R - 1));   // neighbour's last layer
+        const float mine = surf3Dread<float>(surf, (L.vx + vox.x) * int(sizeof(float)), L.vy + vox.y, L.vz + vox.z);
+        const float theirs = surf3Dread<float>(surf, (N.vx + vn.x) * int(sizeof(float)), N.vy + vn.y, N.vz + vn.z);
+        surf3Dwrite(mine, surf, (N.vx + vn.x + inc.x) * int(sizeof(float)), N.vy + vn.y + inc.y, N.vz + vn.z + inc.z);      // neighbour's upper apron
+        surf3Dwrite(theirs, surf, (L.vx + vox.x - inc.x) * int(sizeof(float)), L.vy + vox.y - inc.y, L.vz + vox.z - inc.z); // own lower apron
+        if (bricks != nullptr) {        // brick-local texel = interior voxel + 1
+            bricks[size_t(n) * size_t(P.brick_stride) + ((vn.z + inc.z + 1) * BD + (vn.y + inc.y + 1)) * BD + (vn.x + inc.x + 1)] = mine;
+            bricks[size_t(leaf) * size_t(P.brick_stride) + ((vox.z - inc.z + 1) * BD + (vox.y - inc.y + 1)) * BD + (vox.x - inc.x + 1)] = theirs;
+        }
+    }
+}
+
 // SHADE_VOXEL occupancy bits (8^3 bricks): for every leaf, bit (y * 8 + x) of word z = (interior voxel (x, y, z) > thresh).
 // The comparison is the one raySurfaceVoxelBrick makes per DDA step (cuda_gvdb_raycast.cuh:241) on the value a texel-centre
 // fetch returns, i.e. the stored texel itself.  One 64-thread CTA per leaf, one byte (a row of 8 voxels) per thread.

@@ -109,6 +109,11 @@ int  gvdbx_import_atlas_device(gvdbx_t* h, int chan, uint64_t texels_d, int res_
  * contains it, else `boundval`.  Writes the 3-D array (the caller's, when imported with gvdbx_import_atlas_array —
  * exactly what the reference's kernel does) and keeps the library's brick-major copy and value ranges coherent. */
 int  gvdbx_update_apron(gvdbx_t* h, int chan, float boundval);
+/* VolumeGVDB::UpdateApronFaces(chan) (src/gvdb_volume_gvdb.cpp:4461-4496, kernels/cuda_gvdb_operators.cuh:27-61): the cheap
+ * variant — face-adjacent bricks swap their boundary voxel layers into each other's face aprons (edge / corner texels and faces
+ * without a neighbour stay as they are).  Neighbours are found by point query on the imported tree (the reference:
+ * UpdateNeighbors table).  Same coherence guarantees as gvdbx_update_apron. */
+int  gvdbx_update_apron_faces(gvdbx_t* h, int chan);
 /* Read the atlas array back into a host image, x fastest (Allocator::AtlasRetrieveSlice for every slice). */
 int  gvdbx_export_atlas_host(gvdbx_t* h, int chan, float* texels, int res_x, int res_y, int res_z);
 

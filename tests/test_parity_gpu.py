@@ -891,3 +891,63 @@ def test_import_rejects_malformed_pools(ora, pkg, torch_cuda):
         r.import_atlas_host(np.zeros((20, 160, 160), np.float32))
     r.import_atlas_host(vol["atlas"])
     r.close()
+
+
+# ------------------------------------------------------------------------------------------------ UpdateApronFaces
+@pytest.mark.parametrize("preset", ["cfg1_tiny", "cfg4_small"])
+def test_update_apron_faces(ora, pkg, torch_cuda, preset):
+    """gvdbx_update_apron_faces (VolumeGVDB::UpdateApronFaces): on every face shared by two bricks the two face aprons are
+    rebuilt from the other brick's boundary layer — there the result must equal, byte for byte, the atlas the UNMODIFIED
+    reference holds after its UpdateApron (SHA-256 in the golden file); edge / corner texels and faces without a neighbour
+    stay untouched (junk written there beforehand survives)."""
+    from common import sha
+    g = golden(preset)
+    p, vol = ora.scene_volume(preset)
+    atlas = vol["atlas"]
+    assert sha(atlas) == str(g["atlas_sha"])
+    recs = np.frombuffer(vol["pool0"][0].tobytes(), np.int32).reshape(-1, 16)
+    pos, val = recs[:, 1:4], recs[:, 4:7]
+    R = 8
+    index = {tuple(q): i for i, q in enumerate(pos.tolist())}
+    work = atlas.copy()
+    nfaces = 0
+    for i, (q, v) in enumerate(zip(pos.tolist(), val.tolist())):
+        for axis in range(3):
+            nq = list(q); nq[axis] -= R
+            j = index.get(tuple(nq))
+            if j is None:
+                continue
+            nfaces += 1
+            w = val[j].tolist()
+            lo = [slice(v[2], v[2] + R), slice(v[1], v[1] + R), slice(v[0], v[0] + R)]        # [z, y, x] of the interior
+            hi = [slice(w[2], w[2] + R), slice(w[1], w[1] + R), slice(w[0], w[0] + R)]
+            a = 2 - axis                                                                     # array axis of the face normal
+            lo[a] = slice(v[axis] - 1, v[axis])                                              # own lower apron layer
+            hi[a] = slice(w[axis] + R, w[axis] + R + 1)                                      # neighbour's upper apron layer
+            work[tuple(lo)] = 777.0
+            work[tuple(hi)] = 777.0
+    assert nfaces > 10 and not np.array_equal(work, atlas)
+    # junk on an edge texel and on a face without neighbour must survive
+    want = atlas.copy()
+    v0 = val[0].tolist()
+    work[v0[2] - 1, v0[1] - 1, v0[0]] = want[v0[2] - 1, v0[1] - 1, v0[0]] = 555.0          # edge texel of brick 0
+    outer = next(i for i, q in enumerate(pos.tolist()) if tuple([q[0] - R, q[1], q[2]]) not in index)
+    vo = val[outer].tolist()
+    work[vo[2] + 3, vo[1] + 3, vo[0] - 1] = want[vo[2] + 3, vo[1] + 3, vo[0] - 1] = 444.0    # -x face apron, no neighbour
+    _, table = ora.scninfo_for(pkg, p)
+    r = pkg.Renderer(0)
+    r.import_topology_host(vol["vdbinfo"], vol["pool0"], vol["pool1"])
+    r.import_atlas_host(work)
+    r.set_transfer(table)
+    r.set_sampler(1)                                   # builds the brick-major copy first: it must be kept coherent
+    w, h = int(g["width"]), int(g["height"])
+    _render(torch_cuda, r, g["scn_trilinear"].tobytes(), 4, w, h, 1)
+    r.update_apron_faces()
+    back = r.export_atlas_host(atlas.shape)
+    assert np.array_equal(back.view(np.uint32), want.view(np.uint32)), f"{(back != want).sum()} texels differ"
+    # put the two junk texels right: the volume is the reference's again, in both copies of the atlas
+    r.update_apron(0.0)
+    assert sha(r.export_atlas_host(atlas.shape)) == str(g["atlas_sha"])
+    assert np.array_equal(_render(torch_cuda, r, g["scn_trilinear"].tobytes(), 4, w, h, 0), g["rgba_trilinear"])
+    assert tolerance_ok(_render(torch_cuda, r, g["scn_trilinear"].tobytes(), 4, w, h, 1), g["rgba_trilinear"])[0]
+    r.close()
