@@ -168,7 +168,8 @@ class Renderer:
         self.set_option(OPT_DEEP_SHADOW, 1 if on else 0)
 
     def set_counters(self, on):
-        self.set_option(OPT_COUNTERS, 1 if on else 0)
+        """0 = off, 1 / True = count the algorithm's work (no brick culling), 2 = count the production kernel's work"""
+        self.set_option(OPT_COUNTERS, int(on))
 
     def import_topology(self, vdbinfo):
         p, keep = _buf(vdbinfo)

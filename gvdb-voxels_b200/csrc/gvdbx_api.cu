@@ -219,7 +219,7 @@ extern "C" int gvdbx_set_option(gvdbx_t* h, int option, int value)
     case GVDBX_OPT_SAMPLER:  if (value != 0 && value != 1) return gx_fail(h, GVDBX_E_ARG, "sampler must be 0 or 1"); h->sampler = value; break;
     case GVDBX_OPT_BLOCK_W:  if (value < 1 || value > 32) return gx_fail(h, GVDBX_E_ARG, "block_w"); h->block_w = value; break;
     case GVDBX_OPT_BLOCK_H:  if (value < 1 || value > 32) return gx_fail(h, GVDBX_E_ARG, "block_h"); h->block_h = value; break;
-    case GVDBX_OPT_COUNTERS: h->count = value ? 1 : 0; break;
+    case GVDBX_OPT_COUNTERS: if (value < 0 || value > 2) return gx_fail(h, GVDBX_E_ARG, "counters must be 0, 1 or 2"); h->count = value; break;
     case GVDBX_OPT_CULL: h->cull = value ? 1 : 0; break;
     case GVDBX_OPT_SPP: if (value < 1 || value > 64) return gx_fail(h, GVDBX_E_ARG, "spp must be 1..64"); h->spp = value; break;
     case GVDBX_OPT_DEEP_SHADOW: h->deep_shadow = value ? 1 : 0; break;
@@ -772,7 +772,9 @@ extern "C" int gvdbx_render(gvdbx_t* h, const void* scninfo, int shade_mode, int
     const int flags = h->count ? (GX_FLAG_DEBUG | GX_FLAG_COUNT)
                     : (h->spp > 1 ? GX_FLAG_SPP
                     : (core && h->literal == 1 ? GX_FLAG_LITERAL : (core && h->literal == 2 ? GX_FLAG_PACKET : 0)));
-    if (flags & (GX_FLAG_COUNT | GX_FLAG_LITERAL)) P.range = nullptr;     // counters / A-B baseline follow the reference's own work
+    // counters = 1 and the A/B baseline follow the reference's own work (no brick culling); counters = 2 count what the
+    // production kernel really does
+    if ((h->count == 1) || (flags & GX_FLAG_LITERAL)) P.range = nullptr;
     if (h->count && h->spp > 1) return gx_fail(h, GVDBX_E_ARG, "work counters are taken at 1 ray per pixel: set GVDBX_OPT_SPP to 1 for the counted render");
     gx_kernel_t k = gx_pick(mode, h->sampler, flags, h->uniform3);
     if (!k) return gx_fail(h, GVDBX_E_UNSUPPORTED, "no kernel variant for this mode / sampler / option combination");

@@ -53,7 +53,8 @@ extern "C" {
 #define GVDBX_OPT_SAMPLER   1   /* 0 = hardware texture fetch (bit-exact vs reference), 1 = linear brick-major loads */
 #define GVDBX_OPT_BLOCK_W   2   /* CTA pixel tile width  (default 8)  */
 #define GVDBX_OPT_BLOCK_H   3   /* CTA pixel tile height (default 8)  */
-#define GVDBX_OPT_COUNTERS  4   /* 1 = accumulate work counters during render (slower; for roofline accounting) */
+#define GVDBX_OPT_COUNTERS  4   /* accumulate work counters during render (slower; for roofline accounting): 1 = the work of the ALGORITHM as the
+                                   reference does it (no brick culling: SURVEY.md 8d units), 2 = the work the production kernel does (culling on) */
 #define GVDBX_OPT_CULL      6   /* 1 (default) = skip bricks whose value range cannot satisfy the mode's acceptance test (exact) */
 #define GVDBX_OPT_SPP       7   /* rays per pixel (default 1 = the reference's pixel-centre ray).  n > 1: samples on a g x g sub-pixel grid,
                                    g = ceil(sqrt(n)), sample s at ((s % g) + .5) / g, ((s / g) + .5) / g; float colours summed in sample

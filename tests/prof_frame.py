@@ -21,11 +21,14 @@ def main():
     ap.add_argument("--frames", type=int, default=4)
     ap.add_argument("--block", default="8x8")
     ap.add_argument("--size", default="")
+    ap.add_argument("--lanes", type=int, default=0)
+    ap.add_argument("--option", action="append", default=[], help="gvdbx option id=value (repeatable)")
     a = ap.parse_args()
     pkg = bench.load_pkg()
     size = tuple(int(x) for x in a.size.split("x")) if a.size else None
     p, vol = bench.build_workload(a.workload, size)
-    shade = bench.MODES[a.mode] if a.mode else p.shade
+    mode = a.mode or {0: "voxel", 4: "trilinear", 6: "levelset", 7: "deep"}[p.shade]
+    shade, dshadow = bench.MODE[mode]
     scns, table = bench.frame_scninfos(pkg, p, shade, a.frames)
     r = pkg.Renderer(0)
     r.import_topology_host(vol["vdbinfo"], vol["pool0"], vol["pool1"])
@@ -34,6 +37,10 @@ def main():
     r.set_sampler(0 if a.sampler == "tex" else 1)
     bw, bh = (int(x) for x in a.block.split("x"))
     r.set_block(bw, bh)
+    r.set_deep_shadow(dshadow)
+    for o in a.option:
+        k, v = o.split("=")
+        r.set_option(int(k), int(v))
     out = torch.zeros((p.height, p.width, 4), dtype=torch.uint8, device="cuda")
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(a.frames + 1)]
     ev[0].record()
