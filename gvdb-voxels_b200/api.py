@@ -26,6 +26,9 @@ EXPORTED_SYMBOLS = [
     "gvdbx_render_debug", "gvdbx_raytrace", "gvdbx_read_buffer", "gvdbx_sync", "gvdbx_get_counters",
     "gvdbx_sample_points", "gvdbx_kernel_params", "gvdbx_update_apron", "gvdbx_update_apron_faces", "gvdbx_export_atlas_host", "gvdbx_render_tiles_direct", "gvdbx_render_tiles_ring", "gvdbx_peer_alloc", "gvdbx_peer_free", "gvdbx_peer_open",
     "gvdbx_peer_close", "gvdbx_stream_signal", "gvdbx_stream_signal_add", "gvdbx_stream_signal_many", "gvdbx_stream_wait", "gvdbx_set_stream",
+    "gvdbx_render_bands", "gvdbx_render_multi", "gvdbx_ring_create", "gvdbx_ring_connect", "gvdbx_ring_submit", "gvdbx_ring_acquire",
+    "gvdbx_ring_release", "gvdbx_ring_frame", "gvdbx_ring_destroy", "gvdbx_hostring_create", "gvdbx_hostring_submit", "gvdbx_hostring_wait",
+    "gvdbx_hostring_release", "gvdbx_hostring_destroy",
     "gvdbx_read_buffer_async", "gvdbx_lanes", "gvdbx_lane_select", "gvdbx_lane_stream", "gvdbx_lanes_fork", "gvdbx_lanes_join",
 ]
 
@@ -99,6 +102,21 @@ def lib():
     L.gvdbx_stream_signal_many.argtypes = [vp, vp, C.POINTER(u64), i32, C.c_uint32]
     L.gvdbx_set_stream.argtypes = [vp, vp]
     L.gvdbx_read_buffer_async.argtypes = [vp, u64, vp, C.c_size_t]
+    u32 = C.c_uint32
+    L.gvdbx_render_bands.argtypes = [vp, vp, i32, i32, u64, i32, i32, i32]
+    L.gvdbx_render_multi.argtypes = [C.POINTER(vp), i32, vp, i32, i32, u64, i32]
+    L.gvdbx_ring_create.argtypes = [vp, i32, i32, i32, i32, i32, i32, C.POINTER(vp), vp]
+    L.gvdbx_ring_connect.argtypes = [vp, vp]
+    L.gvdbx_ring_submit.argtypes = [vp, vp, i32, i32, C.POINTER(u32)]
+    L.gvdbx_ring_acquire.argtypes = [vp, u32, vp, C.POINTER(u64)]
+    L.gvdbx_ring_release.argtypes = [vp, u32, vp]
+    L.gvdbx_ring_frame.argtypes = [vp, u32, C.POINTER(u64)]
+    L.gvdbx_ring_destroy.argtypes = [vp]
+    L.gvdbx_hostring_create.argtypes = [vp, C.c_char_p, i32, i32, i32, i32, i32, i32, C.POINTER(vp)]
+    L.gvdbx_hostring_submit.argtypes = [vp, vp, i32, i32, C.POINTER(u32)]
+    L.gvdbx_hostring_wait.argtypes = [vp, u32, C.POINTER(vp), i32]
+    L.gvdbx_hostring_release.argtypes = [vp, u32]
+    L.gvdbx_hostring_destroy.argtypes = [vp]
     L.gvdbx_lanes.argtypes = [vp, i32]
     L.gvdbx_lane_select.argtypes = [vp, i32]
     L.gvdbx_lane_stream.argtypes = [vp, i32]
@@ -263,6 +281,11 @@ class Renderer:
         self._ck(self._L.gvdbx_render_tiles_direct(self._h, p, shade, chan, int(frame_ptr), tile_size, rank, nranks),
                  "gvdbx_render_tiles_direct")
 
+    def render_bands(self, scninfo, shade, packed_ptr, band_rows, rank, nranks, chan=0):
+        """full-width bands (band b belongs to rank b % nranks), packed band after band"""
+        p, keep = _buf(scninfo)
+        self._ck(self._L.gvdbx_render_bands(self._h, p, shade, chan, int(packed_ptr), band_rows, rank, nranks), "gvdbx_render_bands")
+
     def render_tiles_ring(self, scninfo, shade, frame_ptr, tile_size, rank, nranks, wait_flag, wait_value, done_flag, chan=0):
         """[wait] + this rank's tiles + done += 1 in one call (the per-frame step of PeerFrameRing)"""
         p, keep = _buf(scninfo)
@@ -369,6 +392,14 @@ class Renderer:
     def sample_points(self, xyz_ptr, n, out_tex_ptr, out_lin_ptr, chan=0):
         self._ck(self._L.gvdbx_sample_points(self._h, chan, int(xyz_ptr), n, int(out_tex_ptr), int(out_lin_ptr)),
                  "gvdbx_sample_points")
+
+
+def render_multi(renderers, scninfo, shade, out_ptr, tile_size=32, chan=0):
+    """gvdbx_render_multi: several contexts of ONE process (one per device) render one frame into renderers[0]'s buffer"""
+    L = lib()
+    hs = (C.c_void_p * len(renderers))(*[r._h for r in renderers])
+    p, keep = _buf(scninfo)
+    renderers[0]._ck(L.gvdbx_render_multi(hs, len(renderers), p, shade, chan, int(out_ptr), tile_size), "gvdbx_render_multi")
 
 
 # ------------------------------------------------------------------------------------------------ host mirror

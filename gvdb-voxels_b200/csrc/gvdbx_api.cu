@@ -3,122 +3,9 @@
 // Host-side counterpart of the reference's PrepareVDB / PrepareRender / Render / ReadRenderBuf
 // (src/gvdb_volume_gvdb.cpp:3946-3989, 4254-4306, 4336-4381, 4241-4251).  CUDA runtime API only; works under the
 // caller's current context; everything is stream-ordered on the stream given to gvdbx_create.
-#include "../../include/gvdbx.h"
+#include "gvdbx_internal.h"
 #include "gvdbx_import.cuh"
 
-#include <cstdio>
-#include <cstdlib>
-#include <cstring>
-#include <string>
-#include <vector>
-#include <dlfcn.h>
-
-// ------------------------------------------------------------------------------------------------ CUDA context
-// The reference lives in a context it creates itself (StartCuda: cuCtxCreate, gvdb_allocator.cpp:1105-1109) and brackets
-// every entry point with cuCtxPushCurrent / cuCtxPopCurrent (gvdb_volume_gvdb.cpp:41-42).  Its pools, CUarrays and render
-// buffers belong to THAT context, so this library must run in it too: gvdbx_create adopts the context that is current on
-// the calling thread (only when none is current does it bind the device's primary context, as a stand-alone CUDA-runtime
-// host expects), and every entry point makes the adopted context current for its own duration — the same push / pop
-// discipline as the reference.  The four driver entry points are taken from libcuda at run time (no link dependency:
-// the library still loads, and fails with GVDBX_E_CUDA, on a machine without a driver).
-typedef int (*gx_cuCtxGetCurrent_t)(void**);
-typedef int (*gx_cuCtxPushCurrent_t)(void*);
-typedef int (*gx_cuCtxPopCurrent_t)(void**);
-typedef int (*gx_cuCtxGetDevice_t)(int*);
-static struct GxDriver {
-    gx_cuCtxGetCurrent_t  get = nullptr;
-    gx_cuCtxPushCurrent_t push = nullptr;
-    gx_cuCtxPopCurrent_t  pop = nullptr;
-    gx_cuCtxGetDevice_t   dev = nullptr;
-    bool ok = false, looked = false;
-    bool load()
-    {
-        if (looked) return ok;
-        looked = true;
-        void* lib = dlopen("libcuda.so.1", RTLD_NOW | RTLD_GLOBAL);
-        if (!lib) lib = dlopen("libcuda.so", RTLD_NOW | RTLD_GLOBAL);
-        if (!lib) return false;
-        get = (gx_cuCtxGetCurrent_t)dlsym(lib, "cuCtxGetCurrent");
-        push = (gx_cuCtxPushCurrent_t)dlsym(lib, "cuCtxPushCurrent_v2");
-        pop = (gx_cuCtxPopCurrent_t)dlsym(lib, "cuCtxPopCurrent_v2");
-        dev = (gx_cuCtxGetDevice_t)dlsym(lib, "cuCtxGetDevice");
-        ok = get && push && pop && dev;
-        return ok;
-    }
-} gx_drv;
-
-struct gvdbx_ctx {
-    int          device = 0;
-    void*        cuctx = nullptr;       // the CUcontext every entry point runs in (adopted at creation)
-    cudaStream_t stream = nullptr;
-    std::string  err;
-    // options
-    int sampler = GX_SAMPLER_TEX, block_w = 8, block_h = 8, count = 0, literal = 0, spp = 1, deep_shadow = 0, memops = 0;
-    // topology
-    bool       have_topo = false, uniform3 = false;
-    GxVDBInfo  vdb;
-    int*       d_child[GX_MAXLEV] = {};
-    int4*      d_npos[GX_MAXLEV] = {};
-    GxLeafRec* d_leaf = nullptr;
-    // atlas
-    bool                have_atlas = false;
-    cudaArray_t         own_array = nullptr;
-    cudaTextureObject_t tex = 0;
-    cudaTextureObject_t tex_point = 0;  // same array, point filter: exact texel values for the import kernels
-    cudaSurfaceObject_t surf = 0;       // same array, for UpdateApron (needs CUDA_ARRAY3D_SURFACE_LDST like the reference's volOut)
-    cudaArray_t         array = nullptr; // the array the objects sit on (caller's or own_array)
-    float*              d_bricks = nullptr;     // brick-major copy, one block per leaf: built on first use of the linear sampler
-    int                 brick_dim = GX_BRICK_DIM, brick_stride = GX_BRICK_STRIDE;
-    GxRange*            d_leaf_range = nullptr; // per leaf (valid when topology and atlas are both imported)
-    int*                d_err = nullptr;        // error bits raised by the import kernels
-    cudaEvent_t         build_ev = nullptr;     // orders lazily built tables (occupancy bits, brick-major copy) against all lanes
-    unsigned long long* d_vmask = nullptr;      // SHADE_VOXEL occupancy bits per leaf for THRESH == vmask_thresh
-    uint32_t            vmask_thresh_bits = 0;
-    bool                vmask_valid = false;
-    int                 use_vmask = 1;
-    int                 cull = 1;
-    int                 ares[3] = {0, 0, 0};
-    // colour channel (VDBInfo::clr_chan): uchar4 atlas with the slot layout of channel 0
-    cudaTextureObject_t clr_tex = 0;
-    cudaArray_t         clr_own = nullptr;
-    // transfer function
-    float4* d_transfer = nullptr;
-    std::vector<float4*> deep_lut;      // per lane (+1 for the creation stream): this frame's {rgb, exp(EXTINCT * alpha * DIRECTSTEP)}
-    int     cur_lane = -1;
-    // counters
-    unsigned long long* d_counters = nullptr;
-    // frame lanes: internal streams that consecutive frames alternate between (the tail of frame j overlaps frame j + 1)
-    cudaStream_t base_stream = nullptr;
-    std::vector<cudaStream_t> lanes;
-    std::vector<cudaEvent_t>  lane_ev;
-    cudaEvent_t  base_ev = nullptr;
-};
-
-#define GX_CUDA(h, call)                                                                              \
-    do {                                                                                              \
-        cudaError_t e_ = (call);                                                                      \
-        if (e_ != cudaSuccess) {                                                                      \
-            (h)->err = std::string(#call) + ": " + cudaGetErrorName(e_) + " - " + cudaGetErrorString(e_); \
-            return GVDBX_E_CUDA;                                                                      \
-        }                                                                                             \
-    } while (0)
-
-static int gx_fail(gvdbx_t* h, int code, const std::string& msg) { if (h) h->err = msg; return code; }
-
-// makes the handle's context current for the lifetime of the object (no-op when it already is)
-struct GxCtx {
-    bool pushed = false;
-    explicit GxCtx(const gvdbx_t* h)
-    {
-        if (!h || !h->cuctx || !gx_drv.ok) return;
-        void* cur = nullptr;
-        if (gx_drv.get(&cur) == 0 && cur == h->cuctx) return;
-        pushed = gx_drv.push(h->cuctx) == 0;
-    }
-    ~GxCtx() { if (pushed) { void* p = nullptr; gx_drv.pop(&p); } }
-    GxCtx(const GxCtx&) = delete;
-    GxCtx& operator=(const GxCtx&) = delete;
-};
 
 extern "C" int gvdbx_create(gvdbx_t** out, int cuda_device, void* cuda_stream)
 {
@@ -836,61 +723,59 @@ extern "C" int gvdbx_tiles_per_rank(int width, int height, int tile_size, int nr
     return (tiles + nranks - 1) / nranks;
 }
 
-extern "C" int gvdbx_render_tiles(gvdbx_t* h, const void* scninfo, int shade_mode, int chan, uint64_t packed_d,
-                                  int tile_size, int rank, int nranks)
+// tile-list launch: the tiles (tile_w x tile_h pixels, numbered row-major) with id % nranks == rank.  direct: every pixel at
+// its place in a row-major frame (possibly a peer GPU's: the stores travel over NVLink from inside the render kernel and no
+// gather / assemble step exists); otherwise packed tile after tile into this rank's own buffer.
+static int gx_render_tile_list(gvdbx_t* h, const void* scninfo, int shade_mode, int chan, uint64_t out_d, int tile_w, int tile_h,
+                               int rank, int nranks, bool direct)
 {
     if (!h) return GVDBX_E_ARG;
     GxCtx ctx_(h);
     GxParams P; int mode = 0;
     int rc = gx_fill_params(h, scninfo, shade_mode, chan, P, mode);
     if (rc) return rc;
-    if (!packed_d || nranks <= 0 || rank < 0 || rank >= nranks) return gx_fail(h, GVDBX_E_ARG, "rank/nranks/buffer");
-    if (tile_size <= 0 || tile_size % h->block_w || tile_size % h->block_h)
-        return gx_fail(h, GVDBX_E_ARG, "tile_size must be a multiple of the CTA tile");
-    P.out = (uchar4*)packed_d;
-    P.out_stride = 0;                                   // packed tile slots
-    P.tile_size = tile_size;
-    P.tiles_x = (P.width + tile_size - 1) / tile_size;
-    P.ntiles = P.tiles_x * ((P.height + tile_size - 1) / tile_size);
+    if (!out_d || nranks <= 0 || rank < 0 || rank >= nranks) return gx_fail(h, GVDBX_E_ARG, "rank/nranks/buffer");
+    if (tile_w <= 0 || tile_h <= 0 || tile_w % h->block_w || tile_h % h->block_h)
+        return gx_fail(h, GVDBX_E_ARG, "tile size must be a multiple of the CTA tile");
+    P.out = (uchar4*)out_d;
+    P.out_stride = direct ? P.width : 0;                // > 0 selects direct addressing in the tile-list kernels
+    P.tile_w = tile_w; P.tile_h = tile_h;
+    P.tiles_x = (P.width + tile_w - 1) / tile_w;
+    P.ntiles = P.tiles_x * ((P.height + tile_h - 1) / tile_h);
     P.rank = rank; P.nranks = nranks;
     const int slots = (P.ntiles + nranks - 1) / nranks;
     gx_kernel_t k = gx_pick(mode, h->sampler, GX_FLAG_TILES | (h->spp > 1 ? GX_FLAG_SPP : 0), h->uniform3);
     if (!k) return gx_fail(h, GVDBX_E_UNSUPPORTED, "no kernel variant for this mode / sampler combination");
     dim3 block(h->block_w, h->block_h, 1);
-    dim3 grid((tile_size / h->block_w) * (tile_size / h->block_h), slots, 1);
+    dim3 grid((tile_w / h->block_w) * (tile_h / h->block_h), slots, 1);
     k<<<grid, block, size_t(block.x) * block.y * GX_STACK_BYTES_PER_THREAD, h->stream>>>(P);
     GX_CUDA(h, cudaGetLastError());
     return GVDBX_OK;
 }
 
-// Direct mode: the same tile list, but every pixel goes straight to its place in a row-major frame.  `frame_d` may be a
-// peer GPU's buffer opened with gvdbx_peer_open: the stores then travel over NVLink from inside the render kernel and no
-// gather / assemble step exists.
+extern "C" int gvdbx_render_tiles(gvdbx_t* h, const void* scninfo, int shade_mode, int chan, uint64_t packed_d,
+                                  int tile_size, int rank, int nranks)
+{
+    return gx_render_tile_list(h, scninfo, shade_mode, chan, packed_d, tile_size, tile_size, rank, nranks, false);
+}
+
 extern "C" int gvdbx_render_tiles_direct(gvdbx_t* h, const void* scninfo, int shade_mode, int chan, uint64_t frame_d,
                                          int tile_size, int rank, int nranks)
 {
-    if (!h) return GVDBX_E_ARG;
-    GxCtx ctx_(h);
-    GxParams P; int mode = 0;
-    int rc = gx_fill_params(h, scninfo, shade_mode, chan, P, mode);
-    if (rc) return rc;
-    if (!frame_d || nranks <= 0 || rank < 0 || rank >= nranks) return gx_fail(h, GVDBX_E_ARG, "rank/nranks/buffer");
-    if (tile_size <= 0 || tile_size % h->block_w || tile_size % h->block_h)
-        return gx_fail(h, GVDBX_E_ARG, "tile_size must be a multiple of the CTA tile");
-    P.out = (uchar4*)frame_d;
-    P.out_stride = P.width;                             // > 0 selects direct addressing in the tile-list kernels
-    P.tile_size = tile_size;
-    P.tiles_x = (P.width + tile_size - 1) / tile_size;
-    P.ntiles = P.tiles_x * ((P.height + tile_size - 1) / tile_size);
-    P.rank = rank; P.nranks = nranks;
-    const int slots = (P.ntiles + nranks - 1) / nranks;
-    gx_kernel_t k = gx_pick(mode, h->sampler, GX_FLAG_TILES | (h->spp > 1 ? GX_FLAG_SPP : 0), h->uniform3);
-    if (!k) return gx_fail(h, GVDBX_E_UNSUPPORTED, "no kernel variant for this mode / sampler combination");
-    dim3 block(h->block_w, h->block_h, 1);
-    dim3 grid((tile_size / h->block_w) * (tile_size / h->block_h), slots, 1);
-    k<<<grid, block, size_t(block.x) * block.y * GX_STACK_BYTES_PER_THREAD, h->stream>>>(P);
-    GX_CUDA(h, cudaGetLastError());
-    return GVDBX_OK;
+    return gx_render_tile_list(h, scninfo, shade_mode, chan, frame_d, tile_size, tile_size, rank, nranks, true);
+}
+
+// Full-width bands of `band_rows` rows, band b of the frame owned by rank b % nranks, packed band after band with a row
+// pitch of gvdbx_band_pitch(width) pixels: every band is one contiguous block of rows, so a rank can copy its share of the
+// frame to the host with one 2-D copy per band (the host frame ring, gvdbx_hostring_*).
+static int gx_band_pitch(const gvdbx_t* h, int width) { return (width + h->block_w - 1) / h->block_w * h->block_w; }
+extern "C" int gvdbx_render_bands(gvdbx_t* h, const void* scninfo, int shade_mode, int chan, uint64_t packed_d, int band_rows,
+                                  int rank, int nranks)
+{
+    if (!h || !scninfo) return GVDBX_E_ARG;
+    int width = 0;
+    memcpy(&width, scninfo, sizeof width);              // ScnInfo.width @ 0
+    return gx_render_tile_list(h, scninfo, shade_mode, chan, packed_d, gx_band_pitch(h, width), band_rows, rank, nranks, false);
 }
 
 // One call per frame and rank for the peer frame ring: [wait until *wait_flag_d >= wait_value] -> this rank's tiles into

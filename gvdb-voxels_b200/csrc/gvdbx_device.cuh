@@ -113,8 +113,9 @@ struct GxParams {
     // ---- sub-pixel sampling (GX_FLAG_SPP): spp rays per pixel on a spp_grid x spp_grid pattern, averaged before packing
     int      spp, spp_grid;
     float    spp_inv_grid, spp_inv;
-    // ---- tile-list mode (multi-GPU): tiles with id % nranks == rank, packed tile after tile
-    int      tile_size, tiles_x, ntiles, rank, nranks;
+    // ---- tile-list mode (multi-GPU): tiles of tile_w x tile_h pixels with id % nranks == rank, packed tile after tile
+    // (square tiles for the peer frame ring; full-width bands — tile_w >= width, tiles_x == 1 — for the host frame ring)
+    int      tile_w, tile_h, tiles_x, ntiles, rank, nranks;
 };
 
 // ------------------------------------------------------------------------------------------------ small vector algebra
@@ -863,17 +864,17 @@ __global__ void __launch_bounds__(256, GX_MINBLOCKS) gx_render_kernel(const __gr
     bool valid;
     if (FLAGS & GX_FLAG_TILES) {
         // blockIdx.y = tile slot of this rank, blockIdx.x = sub-block inside the tile
-        const int ts = P.tile_size;
-        const int sub_x = ts / blockDim.x;
+        const int tw = P.tile_w, th = P.tile_h;
+        const int sub_x = tw / blockDim.x;
         const int tile = blockIdx.y * P.nranks + P.rank;
         if (tile >= P.ntiles) return;
         const int lx = (blockIdx.x % sub_x) * blockDim.x + threadIdx.x;
         const int ly = (blockIdx.x / sub_x) * blockDim.y + threadIdx.y;
-        x = (tile % P.tiles_x) * ts + lx;
-        y = (tile / P.tiles_x) * ts + ly;
+        x = (tile % P.tiles_x) * tw + lx;
+        y = (tile / P.tiles_x) * th + ly;
         // direct mode (out_stride > 0): pixels go straight into a row-major frame (possibly a peer GPU's, over NVLink);
         // packed mode: tile after tile into this rank's own buffer
-        opix = P.out_stride > 0 ? size_t(y) * P.out_stride + x : (size_t(blockIdx.y) * ts + ly) * ts + lx;
+        opix = P.out_stride > 0 ? size_t(y) * P.out_stride + x : (size_t(blockIdx.y) * th + ly) * tw + lx;
         valid = (x < P.width && y < P.height);
     } else {
         x = P.x0 + blockIdx.x * blockDim.x + threadIdx.x;

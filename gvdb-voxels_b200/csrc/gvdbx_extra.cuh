@@ -180,10 +180,10 @@ __device__ __forceinline__ void gx_brick_shadow(const GxParams& P, S& smp, int n
         const float v1 = smp.tri(p1.x + o.x, p1.y + o.y, p1.z + o.z);
         const float v2 = smp.tri(p2.x + o.x, p2.y + o.y, p2.z + o.z);
         const float v3 = smp.tri(p3.x + o.x, p3.y + o.y, p3.z + o.z);
-        const float a0 = __ldg(&P.transfer[gx_transfer_index(v0, P.thresh.x, inv_range)]).w;
-        const float a1 = __ldg(&P.transfer[gx_transfer_index(v1, P.thresh.x, inv_range)]).w;
-        const float a2 = __ldg(&P.transfer[gx_transfer_index(v2, P.thresh.x, inv_range)]).w;
-        const float a3 = __ldg(&P.transfer[gx_transfer_index(v3, P.thresh.x, inv_range)]).w;
+        const float a0 = gx_lut(P.transfer, gx_transfer_index(v0, P.thresh.x, inv_range)).w;
+        const float a1 = gx_lut(P.transfer, gx_transfer_index(v1, P.thresh.x, inv_range)).w;
+        const float a2 = gx_lut(P.transfer, gx_transfer_index(v2, P.thresh.x, inv_range)).w;
+        const float a3 = gx_lut(P.transfer, gx_transfer_index(v3, P.thresh.x, inv_range)).w;
         // one layer: clr.w = 1 - (1 - clr.w) * exp(...), then the parameter step
         #define GX_SHADOW_LAYER(alpha) { cnt.s_tri++; cnt.s_lut++;                                              \
             const float val = exp(P.extinct.x * (alpha) * P.steps.y / (1.0 + s * 0.4));                          \
@@ -248,7 +248,7 @@ __device__ __forceinline__ float4 gx_pixel_section2d(const GxParams& P, S& smp, 
     const float3 offs = make_float3(float(L.vx), float(L.vy), float(L.vz));
     const float3 p = offs + (wpos - vmin);
     cnt.s_tri++; cnt.s_lut++;
-    const float4 clr = __ldg(&P.transfer[gx_transfer_index(smp.tri(p.x, p.y, p.z), P.thresh.x, gx_rcp_approx(P.thresh.z - P.thresh.y))]);
+    const float4 clr = gx_lut(P.transfer, gx_transfer_index(smp.tri(p.x, p.y, p.z), P.thresh.x, gx_rcp_approx(P.thresh.z - P.thresh.y)));
     bgclr = make_float3(bgclr.x + clr.w * (clr.x - bgclr.x), bgclr.y + clr.w * (clr.y - bgclr.y), bgclr.z + clr.w * (clr.z - bgclr.z));
     return make_float4(bgclr.x, bgclr.y, bgclr.z, 1);
 }
@@ -277,7 +277,7 @@ __device__ __forceinline__ float4 gx_pixel_section3d(const GxParams& P, S& smp, 
             const float3 p = offs + (wpos - vmin);
             cnt.s_tri++; cnt.s_lut++;
             t = smp.tri(p.x, p.y, p.z);
-            clr = __ldg(&P.transfer[gx_transfer_index(t, P.thresh.x, gx_rcp_approx(P.thresh.z - P.thresh.y))]);
+            clr = gx_lut(P.transfer, gx_transfer_index(t, P.thresh.x, gx_rcp_approx(P.thresh.z - P.thresh.y)));
             if (P.clr_tex) {                // the section plane takes the voxel's colour too (cuda_gvdb_module.cu:249-252); alpha * 1.0
                 const float4 c = gx_color(P, p);
                 clr.x *= c.x; clr.y *= c.y; clr.z *= c.z;

@@ -49,7 +49,7 @@ static __device__ __forceinline__ void gx_module_params(GxParams& P, const GxVDB
     P.out = outBuf; P.dbg = nullptr; P.counters = nullptr;
     P.out_stride = s.width; P.x0 = 0; P.y0 = 0; P.x1 = s.width; P.y1 = s.height;
     P.spp = 1; P.spp_grid = 1; P.spp_inv_grid = 1.f; P.spp_inv = 1.f;
-    P.tile_size = 0; P.tiles_x = 0; P.ntiles = 0; P.rank = 0; P.nranks = 1;
+    P.tile_w = 0; P.tile_h = 0; P.tiles_x = 0; P.ntiles = 0; P.rank = 0; P.nranks = 1;
 }
 
 template <int MODE>

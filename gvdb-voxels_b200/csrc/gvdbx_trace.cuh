@@ -155,14 +155,18 @@ __device__ __forceinline__ void gx_deep_accumulate_pre(const GxParams& P, float4
 }
 // transfer-function index (cuda_gvdb_dda.cuh:20-23): int(min(1.0, max(0.0, u)) * 16300.0f) with u = (v - THRESH) /
 // (VMAX - VMIN) a float (divide = multiply by the approximate reciprocal) and the clamp / scale / truncation in DOUBLE,
-// i.e. floor of the EXACT product clamp(u) * 16300.  Same integer without the FP64 pipe: round the product in fp32, take
-// its floor f, and step back by one when the exact product (sign of a single fma) lies below f — rounding to nearest can
-// lift the product onto the next integer but never drop it below one.
-__device__ __forceinline__ int gx_transfer_index(float v, float thresh, float inv_range)
+// i.e. floor of the EXACT product x = clamp(u) * 16300 (24 x 14 bits fit a double).  Same integer without the FP64 pipe and
+// with a single conversion: round the product TOWARDS ZERO in fp32 and truncate.  rz(x) is the largest float <= x, and
+// floor(x) < 2^24 is itself a float <= x, so floor(x) <= rz(x) <= x and floor(rz(x)) = floor(x).
+__device__ __forceinline__ unsigned gx_transfer_index(float v, float thresh, float inv_range)
 {
     const float u = fminf(fmaxf((v - thresh) * inv_range, 0.0f), 1.0f);      // NaN -> 0 like max(0.0, NaN)
-    const float f = floorf(__fmul_rn(u, 16300.0f));
-    return int(f) - (__fmaf_rn(u, 16300.0f, -f) < 0.0f ? 1 : 0);
+    return unsigned(__float2int_rz(__fmul_rz(u, 16300.0f)));
+}
+// table entry by 32-bit byte offset from the (uniform) table base: one IMAD.WIDE.U32 instead of a sign-extended 64-bit index
+__device__ __forceinline__ float4 gx_lut(const float4* table, unsigned idx)
+{
+    return __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const char*>(table) + (size_t(idx) << 4)));
 }
 
 // SHADE_VOLUME                                                           cuda_gvdb_raycast.cuh:485-533
@@ -201,7 +205,7 @@ __device__ __forceinline__ void gx2_brick_deep(const GxParams& P, S& smp, int no
             }
             cnt.s_tri++;
             const float raw = smp.tri(p.x + o.x, p.y + o.y, p.z + o.z);
-            if (raw >= minval) { cnt.s_lut++; gx_deep_accumulate(P, clr, __ldg(&P.transfer[gx_transfer_index(raw, thresh, inv_range)])); }
+            if (raw >= minval) { cnt.s_lut++; gx_deep_accumulate(P, clr, gx_lut(P.transfer, gx_transfer_index(raw, thresh, inv_range))); }
             GX_STEP_ADD(p, p); GX_STEP_ADD(wp, wp);
             t.x += dt;
         }
@@ -215,15 +219,15 @@ __device__ __forceinline__ void gx2_brick_deep(const GxParams& P, S& smp, int no
             const float v2 = smp.tri(p2.x + o.x, p2.y + o.y, p2.z + o.z);
             const float v3 = smp.tri(p3.x + o.x, p3.y + o.y, p3.z + o.z);
             const bool a0 = v0 >= minval, a1 = v1 >= minval, a2 = v2 >= minval, a3 = v3 >= minval;
-            // transfer-function reads of the whole round in flight together (entry 0 for rejected samples, unused)
+            // transfer-function reads of the whole round in flight together (the index is valid for every sample; rejected ones are unused)
             // {rgb, exp(EXTINCT * alpha * DIRECTSTEP)} built for this frame by the host side; the module-level drop-in has no
             // host side: plain table, exp per sample
             constexpr bool pre = GX_DEEP_LUT;
             const float4* lut = pre ? P.transfer_deep : P.transfer;
-            const float4 c0 = __ldg(&lut[a0 ? gx_transfer_index(v0, thresh, inv_range) : 0]);
-            const float4 c1 = __ldg(&lut[a1 ? gx_transfer_index(v1, thresh, inv_range) : 0]);
-            const float4 c2 = __ldg(&lut[a2 ? gx_transfer_index(v2, thresh, inv_range) : 0]);
-            const float4 c3 = __ldg(&lut[a3 ? gx_transfer_index(v3, thresh, inv_range) : 0]);
+            const float4 c0 = gx_lut(lut, gx_transfer_index(v0, thresh, inv_range));
+            const float4 c1 = gx_lut(lut, gx_transfer_index(v1, thresh, inv_range));
+            const float4 c2 = gx_lut(lut, gx_transfer_index(v2, thresh, inv_range));
+            const float4 c3 = gx_lut(lut, gx_transfer_index(v3, thresh, inv_range));
             // consume in order; `done` = samples processed (each is followed by one position / t step in the reference)
             int done = 0;
             bool more = k0;             // loop condition for sample 0 (alpha was checked by the for statement)
@@ -320,10 +324,10 @@ __device__ __forceinline__ bool gx3_round(const GxParams& P, S& smp, float3 pos,
         const bool a0 = v0 >= minval, a1 = v1 >= minval, a2 = v2 >= minval, a3 = v3 >= minval;
         constexpr bool pre = GX_DEEP_LUT;
         const float4* lut = pre ? P.transfer_deep : P.transfer;
-        const float4 c0 = __ldg(&lut[a0 ? gx_transfer_index(v0, thresh, inv_range) : 0]);
-        const float4 c1 = __ldg(&lut[a1 ? gx_transfer_index(v1, thresh, inv_range) : 0]);
-        const float4 c2 = __ldg(&lut[a2 ? gx_transfer_index(v2, thresh, inv_range) : 0]);
-        const float4 c3 = __ldg(&lut[a3 ? gx_transfer_index(v3, thresh, inv_range) : 0]);
+        const float4 c0 = gx_lut(lut, gx_transfer_index(v0, thresh, inv_range));
+        const float4 c1 = gx_lut(lut, gx_transfer_index(v1, thresh, inv_range));
+        const float4 c2 = gx_lut(lut, gx_transfer_index(v2, thresh, inv_range));
+        const float4 c3 = gx_lut(lut, gx_transfer_index(v3, thresh, inv_range));
         int done = 0;
         bool more = k0;
         if (more) { done = 1; cnt.s_tri++; if (a0) { cnt.s_lut++; if (pre) gx_deep_accumulate_pre(P, clr, c0); else gx_deep_accumulate(P, clr, c0); } more = k1 && clr.w > acut; }

@@ -125,10 +125,14 @@ class CudaBuffer:
         self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False), "version": 2}
 
 
+RING_EXPORT_BYTES = 160
+
+
 class PeerFrameRing:
-    """Multi-GPU output without a gather: rank 0 owns a ring of `nslots` row-major frames; every rank's render kernel
-    stores the pixels of its tiles straight into the current slot — over NVLink for ranks != 0 (CUDA IPC peer mapping,
-    gvdbx_peer_open) — so render and "gather" are ONE kernel and the only other traffic is two 4-byte flags per frame:
+    """Multi-GPU output without a gather (C entry points gvdbx_ring_*, csrc/gvdbx_multi.cu): rank 0 owns a ring of `nslots`
+    row-major frames; every rank's render kernel stores the pixels of its tiles straight into the current slot — over NVLink
+    for ranks != 0 (CUDA IPC peer mapping) — so render and "gather" are ONE kernel and the only other traffic is two 4-byte
+    flags per frame:
 
       done[slot]      (rank 0's memory)  += 1 by every rank behind its render kernel (system-scope release);
                       rank 0's consumer stream waits for world * uses(slot) before it touches the slot
@@ -136,48 +140,33 @@ class PeerFrameRing:
                       a rank waits for released >= q - nslots before it renders frame q into the same slot again
 
     All waits and signals are stream-ordered device-side operations: no host synchronisation, no NCCL on the data path.
-    `exchange(obj) -> list of every rank's obj` is the bootstrap (torch.distributed.all_gather_object by default)."""
+    This class only ships the bootstrap blobs: `exchange(blob) -> list of every rank's blob in any order`
+    (torch.distributed.all_gather_object by default); connect=False defers gvdbx_ring_connect (ranks sharing one process)."""
 
-    ALIGN = 256
-
-    def __init__(self, renderer, width, height, tile_size, rank, world, nslots=4, exchange=None):
+    def __init__(self, renderer, width, height, tile_size, rank, world, nslots=4, exchange=None, connect=True):
+        import ctypes as C
+        from . import api
         self.r, self.w, self.h, self.ts, self.rank, self.world, self.nslots = renderer, width, height, tile_size, rank, world, nslots
-        self.frame_bytes = (width * height * 4 + self.ALIGN - 1) // self.ALIGN * self.ALIGN
+        self._L = api.lib()
         self.seq = 0
-        self._own, self._opened = [], []
-        if exchange is None:
-            def exchange(obj):
-                import torch.distributed as dist
-                out = [None] * world
-                dist.all_gather_object(out, obj)
-                return out
-        # every rank: a `released` flag of its own; rank 0 additionally: the frame slots followed by the done counters
-        rel_ptr, rel_handle = renderer.peer_alloc(self.ALIGN)
-        self._own.append(rel_ptr)
-        self.released_local = rel_ptr
-        ring_handle = None
-        if rank == 0:
-            ring_ptr, ring_handle = renderer.peer_alloc(self.frame_bytes * nslots + self.ALIGN * nslots)
-            self._own.append(ring_ptr)
-        # (an IPC handle cannot be opened by the process that made it: ranks living in one process — tests — pass raw pointers)
-        handles = exchange({"rank": rank, "pid": os.getpid(), "released": rel_handle, "released_ptr": rel_ptr, "ring": ring_handle,
-                            "ring_ptr": ring_ptr if rank == 0 else None})
-        handles = sorted(handles, key=lambda d: d["rank"])
-        if rank == 0:
-            self.ring_base = ring_ptr
-            self.released_all = [rel_ptr] + [self._open(handles[k], "released") for k in range(1, world)]
-        else:
-            self.ring_base = self._open(handles[0], "ring")
-            self.released_all = None
-        self.frame_ptr = [self.ring_base + s * self.frame_bytes for s in range(nslots)]
-        self.done_ptr = [self.ring_base + nslots * self.frame_bytes + s * self.ALIGN for s in range(nslots)]
+        g = C.c_void_p()
+        blob = (C.c_uint8 * RING_EXPORT_BYTES)()
+        renderer._ck(self._L.gvdbx_ring_create(renderer._h, width, height, tile_size, rank, world, nslots, C.byref(g), blob), "gvdbx_ring_create")
+        self._g = g
+        self.blob = bytes(blob)
+        if connect:
+            if exchange is None:
+                def exchange(obj):
+                    import torch.distributed as dist
+                    out = [None] * world
+                    dist.all_gather_object(out, obj)
+                    return out
+            self.connect(exchange(self.blob))
 
-    def _open(self, entry, key):
-        if entry["pid"] == os.getpid():
-            return entry[key + "_ptr"]
-        p = self.r.peer_open(entry[key])
-        self._opened.append(p)
-        return p
+    def connect(self, blobs):
+        """blobs: every rank's export blob (any order: the rank is the first int32 of a blob)"""
+        blobs = sorted(blobs, key=lambda b: int.from_bytes(b[0:4], "little", signed=True))
+        self.r._ck(self._L.gvdbx_ring_connect(self._g, b"".join(blobs)), "gvdbx_ring_connect")
 
     def check(self):
         """raises GvdbxError if any stream-ordered wait of this rank ran into its ~20 s timeout (lost peer, stalled consumer):
@@ -186,51 +175,84 @@ class PeerFrameRing:
         self.r.sync()
 
     def close(self):
-        try:
-            self.check()
-        finally:
-            self._release_memory()
-
-    def _release_memory(self):
-        for p in self._opened:
-            self.r.peer_close(p)
-        for p in self._own:
-            self.r.peer_free(p)
-        self._opened, self._own = [], []
+        if self._g:
+            g, self._g = self._g, None
+            self.r._ck(self._L.gvdbx_ring_destroy(g), "gvdbx_ring_destroy")
 
     # ---- every rank
-    def submit(self, scninfo, shade):
-        """enqueue this rank's share of the next frame on the renderer's stream; returns the frame's sequence number"""
-        self.seq += 1
-        q = self.seq
-        slot, _ = ring_slot(q, self.nslots)
-        if getattr(self.r, "nlanes", 0):                      # consecutive frames on alternating internal streams
-            self.r.lane_select((q - 1) % self.r.nlanes)
-        # the slot's previous frame (q - nslots) must have been consumed before its pixels are overwritten
-        wait = (self.released_local, q - self.nslots) if q > self.nslots else (0, 0)
-        if hasattr(self.r, "render_tiles_ring"):
-            self.r.render_tiles_ring(scninfo, shade, self.frame_ptr[slot], self.ts, self.rank, self.world, wait[0], wait[1], self.done_ptr[slot])
-        else:
-            if wait[0]:
-                self.r.stream_wait(*wait)
-            self.r.render_tiles_direct(scninfo, shade, self.frame_ptr[slot], self.ts, self.rank, self.world)
-            self.r.stream_signal_add(self.done_ptr[slot], 1)
-        return q
+    def submit(self, scninfo, shade, chan=0):
+        """enqueue this rank's share of the next frame on the renderer's stream / lane; returns the frame's sequence number"""
+        import ctypes as C
+        from .api import _buf
+        p, keep = _buf(scninfo)
+        q = C.c_uint32()
+        self.r._ck(self._L.gvdbx_ring_submit(self._g, p, shade, chan, C.byref(q)), "gvdbx_ring_submit")
+        self.seq = int(q.value)
+        return self.seq
 
     # ---- rank 0 (consumer)
     def acquire(self, q, stream=None):
         """make `stream` wait until every rank has delivered frame q; returns the device pointer of the finished frame"""
-        slot, uses = ring_slot(q, self.nslots)
-        self.r.stream_wait(self.done_ptr[slot], self.world * uses, stream)
-        return self.frame_ptr[slot]
+        import ctypes as C
+        d = C.c_uint64()
+        self.r._ck(self._L.gvdbx_ring_acquire(self._g, int(q), C.c_void_p(stream or 0), C.byref(d)), "gvdbx_ring_acquire")
+        return int(d.value)
 
     def release(self, q, stream=None):
         """behind the consumer's work on `stream`: hand the slot of frame q back to the producers"""
-        self.r.stream_signal_many(self.released_all, q, stream)
+        import ctypes as C
+        self.r._ck(self._L.gvdbx_ring_release(self._g, int(q), C.c_void_p(stream or 0)), "gvdbx_ring_release")
+
+    def frame_ptr_of(self, q):
+        import ctypes as C
+        d = C.c_uint64()
+        self.r._ck(self._L.gvdbx_ring_frame(self._g, int(q), C.byref(d)), "gvdbx_ring_frame")
+        return int(d.value)
 
     def frame_tensor(self, q, torch, device):
-        slot, _ = ring_slot(q, self.nslots)
-        return torch.as_tensor(CudaBuffer(self.frame_ptr[slot], (self.h, self.w, 4)), device=device)
+        return torch.as_tensor(CudaBuffer(self.frame_ptr_of(q), (self.h, self.w, 4)), device=device)
+
+
+class HostFrameRing:
+    """Frames of a multi-GPU render delivered to the HOST (C entry points gvdbx_hostring_*): a ring of row-major frames in a
+    POSIX shared-memory segment page-locked by every process; each rank renders full-width bands of `band_rows` rows and copies
+    ITS bands over ITS OWN PCIe link.  submit(): every rank; wait() / release(): the consumer (rank 0)."""
+
+    def __init__(self, renderer, name, width, height, rank, world, nslots=4, band_rows=32):
+        import ctypes as C
+        from . import api
+        self.r, self.w, self.h, self.rank, self.world, self.nslots = renderer, width, height, rank, world, nslots
+        self._L = api.lib()
+        g = C.c_void_p()
+        renderer._ck(self._L.gvdbx_hostring_create(renderer._h, name.encode(), width, height, band_rows, rank, world, nslots, C.byref(g)),
+                     "gvdbx_hostring_create")
+        self._g = g
+        self.seq = 0
+
+    def submit(self, scninfo, shade, chan=0):
+        import ctypes as C
+        from .api import _buf
+        p, keep = _buf(scninfo)
+        q = C.c_uint32()
+        self.r._ck(self._L.gvdbx_hostring_submit(self._g, p, shade, chan, C.byref(q)), "gvdbx_hostring_submit")
+        self.seq = int(q.value)
+        return self.seq
+
+    def wait(self, q, timeout_ms=30000):
+        """-> numpy view [h, w, 4] uint8 of the finished frame in the shared segment (valid until release(q))"""
+        import ctypes as C
+        ptr = C.c_void_p()
+        self.r._ck(self._L.gvdbx_hostring_wait(self._g, int(q), C.byref(ptr), int(timeout_ms)), "gvdbx_hostring_wait")
+        buf = (C.c_uint8 * (self.w * self.h * 4)).from_address(ptr.value)
+        return np.frombuffer(buf, dtype=np.uint8).reshape(self.h, self.w, 4)
+
+    def release(self, q):
+        self.r._ck(self._L.gvdbx_hostring_release(self._g, int(q)), "gvdbx_hostring_release")
+
+    def close(self):
+        if self._g:
+            g, self._g = self._g, None
+            self._L.gvdbx_hostring_destroy(g)
 
 
 # ------------------------------------------------------------------------------------------------ volume replication

@@ -178,6 +178,52 @@ int  gvdbx_render_debug(gvdbx_t* h, const void* scninfo, int shade_mode, int cha
  * (pulled back by `bias` along the ray) and normal in place, hit = (NOHIT,NOHIT,NOHIT) on a miss. */
 int  gvdbx_raytrace(gvdbx_t* h, const void* scninfo, int chan, uint64_t rays_d, int num_rays, float bias);
 
+/* Full-width bands of `band_rows` rows (band b of the frame belongs to rank b % nranks), packed band after band with a row
+ * pitch of `width` rounded up to the CTA tile width: each band is one contiguous block of rows (gvdbx_hostring_*). */
+int  gvdbx_render_bands(gvdbx_t* h, const void* scninfo, int shade_mode, int chan, uint64_t packed_d, int band_rows, int rank, int nranks);
+
+/* ---- multi-GPU (the reference has none: one VolumeGVDB per device, src/gvdb_volume_gvdb.h:325) ------------------------------
+ * One frame is partitioned in image space, the volume is replicated on every GPU; output bytes are a pure function of the pixel,
+ * hence identical for 1/2/4/8 GPUs.
+ *
+ * (a) one process, several contexts — SURVEY.md 8b's gvdbx_render_multi: ranks[r] (each created on its own device, each with
+ * the volume imported) renders the tile_size^2 tiles r, r + nranks, ... straight into `outbuf_rank0_d`, a width*height RGBA8
+ * buffer on ranks[0]'s device (peer access over NVLink is enabled on first use).  Stream-ordered: ranks[0]'s stream continues
+ * when every context has finished; the other contexts' streams start when ranks[0]'s stream reaches this call. */
+int  gvdbx_render_multi(gvdbx_t* const* ranks, int nranks, const void* scninfo, int shade_mode, int chan, uint64_t outbuf_rank0_d,
+                        int tile_size);
+
+/* (b) one process PER GPU, frames wanted on rank 0's DEVICE: the peer frame ring.  Rank 0 owns `nslots` frames; the other ranks
+ * map them with CUDA IPC and their render kernels store tiles there directly.  Bootstrap: every rank calls _create, the
+ * GVDBX_RING_EXPORT_BYTES blobs are exchanged with whatever the host application has (MPI, sockets, torch.distributed) and passed,
+ * in rank order, to _connect.  Per frame every rank calls _submit once (frames are numbered 1, 2, ...; consecutive frames
+ * alternate between the context's frame lanes); rank 0 additionally _acquire (makes `consumer_stream` wait until every rank has
+ * delivered the frame), consumes on that stream, and _release (hands the slot back).  All waits / signals are stream-ordered
+ * device operations; a wait that runs into its ~20 s timeout raises a sticky error that gvdbx_sync / _destroy report. */
+#define GVDBX_RING_EXPORT_BYTES 160
+typedef struct gvdbx_ring gvdbx_ring_t;
+int  gvdbx_ring_create(gvdbx_t* h, int width, int height, int tile_size, int rank, int nranks, int nslots, gvdbx_ring_t** ring, void* export_blob);
+int  gvdbx_ring_connect(gvdbx_ring_t* ring, const void* all_exports);
+int  gvdbx_ring_submit(gvdbx_ring_t* ring, const void* scninfo, int shade_mode, int chan, uint32_t* frame_seq);
+int  gvdbx_ring_acquire(gvdbx_ring_t* ring, uint32_t frame_seq, void* consumer_stream, uint64_t* frame_d);
+int  gvdbx_ring_release(gvdbx_ring_t* ring, uint32_t frame_seq, void* consumer_stream);
+int  gvdbx_ring_frame(gvdbx_ring_t* ring, uint32_t frame_seq, uint64_t* frame_d);
+int  gvdbx_ring_destroy(gvdbx_ring_t* ring);
+
+/* (c) one process per GPU, frames wanted on the HOST (ReadRenderBuf of a multi-GPU render): a ring of `nslots` row-major frames
+ * in the POSIX shared-memory segment `shm_name` (rank 0 creates it, every process maps and page-locks it).  Every rank renders
+ * full-width bands of `band_rows` rows (band b belongs to rank b % nranks) and copies ITS bands over ITS OWN PCIe link to their
+ * rows of the frame — N links instead of funnelling every frame through rank 0's.  _submit: every rank, once per frame (blocks on
+ * the host only while the slot's previous frame is unreleased); _wait: the consumer (one process) blocks until all ranks have
+ * delivered frame `frame_seq` and gets the host pointer; _release returns the slot. */
+typedef struct gvdbx_hostring gvdbx_hostring_t;
+int  gvdbx_hostring_create(gvdbx_t* h, const char* shm_name, int width, int height, int band_rows, int rank, int nranks, int nslots,
+                           gvdbx_hostring_t** ring);
+int  gvdbx_hostring_submit(gvdbx_hostring_t* ring, const void* scninfo, int shade_mode, int chan, uint32_t* frame_seq);
+int  gvdbx_hostring_wait(gvdbx_hostring_t* ring, uint32_t frame_seq, const void** frame_host, int timeout_ms);
+int  gvdbx_hostring_release(gvdbx_hostring_t* ring, uint32_t frame_seq);
+int  gvdbx_hostring_destroy(gvdbx_hostring_t* ring);
+
 /* Peer memory for one-process-per-GPU rendering into a frame owned by one rank (CUDA IPC; both GPUs in one NVLink /
  * NVSwitch domain).  gvdbx_peer_alloc: zero-filled device buffer + 64-byte handle to ship to the other processes;
  * gvdbx_peer_open: map another process's buffer (peer access is enabled on first use). */
