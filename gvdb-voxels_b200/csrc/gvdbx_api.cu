@@ -112,7 +112,7 @@ extern "C" int gvdbx_set_option(gvdbx_t* h, int option, int value)
     case GVDBX_OPT_DEEP_SHADOW: h->deep_shadow = value ? 1 : 0; break;
     case GVDBX_OPT_STREAM_MEMOPS: h->memops = value ? 1 : 0; break;
     case GVDBX_OPT_VOXEL_MASK: h->use_vmask = value ? 1 : 0; break;
-    case GVDBX_OPT_TRAVERSAL: if (value < 0 || value > 2) return gx_fail(h, GVDBX_E_ARG, "traversal must be 0, 1 or 2"); h->literal = value; break;
+    case GVDBX_OPT_TRAVERSAL: if (value < 0 || value > 4) return gx_fail(h, GVDBX_E_ARG, "traversal must be 0..4"); h->literal = value; break;
     default: return gx_fail(h, GVDBX_E_ARG, "unknown option");
     }
     if (h->block_w * h->block_h > 256 || (h->block_w * h->block_h) % 32 != 0) {
@@ -555,6 +555,17 @@ static gx_kernel_t gx_pick(int mode, int sampler, int flags, bool uni)
 
 static inline float3 f3(const GxF3& a) { return make_float3(a.x, a.y, a.z); }
 
+// deep modes: brick-queue traversal (gx_raycast_deep_q) unless switched off with GVDBX_OPT_TRAVERSAL = 4 (A/B)
+static int gx_queue_flag(const gvdbx_t* h, int mode)
+{
+    return ((mode == GX_MODE_DEEP || mode == GX_MODE_DEEPSHADOW) && (h->literal == 0 || h->literal == 3)) ? GX_FLAG_QUEUE : 0;
+}
+// dynamic shared memory: the traversal stack, plus the brick queue of the queue variants
+static size_t gx_smem_bytes(dim3 block, int flags)
+{
+    return size_t(block.x) * block.y * (GX_STACK_BYTES_PER_THREAD + ((flags & GX_FLAG_QUEUE) ? GX_QUEUE_BYTES_PER_THREAD : 0));
+}
+
 static int gx_fill_params(gvdbx_t* h, const void* scninfo, int shade_mode, int chan, GxParams& P, int& mode, bool force_deep_lut = false)
 {
     if (!h || !scninfo) return GVDBX_E_ARG;
@@ -656,9 +667,10 @@ extern "C" int gvdbx_render(gvdbx_t* h, const void* scninfo, int shade_mode, int
     }
     P.out = (uchar4*)outbuf_d;
     const bool core = (mode <= GX_MODE_DEEP);          // the A/B traversal variants exist for the four core modes only
+    const int qf = gx_queue_flag(h, mode);
     const int flags = h->count ? (GX_FLAG_DEBUG | GX_FLAG_COUNT)
-                    : (h->spp > 1 ? GX_FLAG_SPP
-                    : (core && h->literal == 1 ? GX_FLAG_LITERAL : (core && h->literal == 2 ? GX_FLAG_PACKET : 0)));
+                    : (h->spp > 1 ? (GX_FLAG_SPP | qf)
+                    : (core && h->literal == 1 ? GX_FLAG_LITERAL : (core && h->literal == 2 ? GX_FLAG_PACKET : qf)));
     // counters = 1 and the A/B baseline follow the reference's own work (no brick culling); counters = 2 count what the
     // production kernel really does
     if ((h->count == 1) || (flags & GX_FLAG_LITERAL)) P.range = nullptr;
@@ -673,7 +685,7 @@ extern "C" int gvdbx_render(gvdbx_t* h, const void* scninfo, int shade_mode, int
     }
     dim3 block(h->block_w, h->block_h, 1);
     dim3 grid((P.x1 - P.x0 + block.x - 1) / block.x, (P.y1 - P.y0 + block.y - 1) / block.y, 1);
-    k<<<grid, block, size_t(block.x) * block.y * GX_STACK_BYTES_PER_THREAD, h->stream>>>(P);
+    k<<<grid, block, gx_smem_bytes(block, flags), h->stream>>>(P);
     GX_CUDA(h, cudaGetLastError());
     if (dbg_tmp) { cudaStreamSynchronize(h->stream); cudaFree(dbg_tmp); }
     return GVDBX_OK;
@@ -744,11 +756,12 @@ static int gx_render_tile_list(gvdbx_t* h, const void* scninfo, int shade_mode, 
     P.ntiles = P.tiles_x * ((P.height + tile_h - 1) / tile_h);
     P.rank = rank; P.nranks = nranks;
     const int slots = (P.ntiles + nranks - 1) / nranks;
-    gx_kernel_t k = gx_pick(mode, h->sampler, GX_FLAG_TILES | (h->spp > 1 ? GX_FLAG_SPP : 0), h->uniform3);
+    const int flags = GX_FLAG_TILES | (h->spp > 1 ? GX_FLAG_SPP : 0) | gx_queue_flag(h, mode);
+    gx_kernel_t k = gx_pick(mode, h->sampler, flags, h->uniform3);
     if (!k) return gx_fail(h, GVDBX_E_UNSUPPORTED, "no kernel variant for this mode / sampler combination");
     dim3 block(h->block_w, h->block_h, 1);
     dim3 grid((tile_w / h->block_w) * (tile_h / h->block_h), slots, 1);
-    k<<<grid, block, size_t(block.x) * block.y * GX_STACK_BYTES_PER_THREAD, h->stream>>>(P);
+    k<<<grid, block, gx_smem_bytes(block, flags), h->stream>>>(P);
     GX_CUDA(h, cudaGetLastError());
     return GVDBX_OK;
 }

@@ -659,13 +659,20 @@ template <class S> __device__ __forceinline__ void gx_brick_shadow(const GxParam
 #endif
 template <int MODE, class S>
 __device__ __forceinline__ void gx_raycast_sm(const GxParams& P, S& smp, float3 pos, float3 dir, GxHit& h, GxCount& cnt, int px, int py);
+// brick-queue form of the deep ray cast (gvdbx_trace.cuh): BATCH == 2
+template <class S>
+__device__ __forceinline__ void gx_raycast_deep_q(const GxParams& P, S& smp, float3 pos, float3 dir, GxHit& h, GxCount& cnt);
 
-template <int MODE, bool BATCH, class S>
+template <int MODE, int BATCH, class S>
 __device__ __forceinline__ void gx_raycast(const GxParams& P, S& smp, float3 pos, float3 dir, GxHit& h, GxCount& cnt,
                                            int px, int py)
 {
     if constexpr (GX_STATE_MACHINE && BATCH && (MODE == GX_MODE_TRILINEAR || MODE == GX_MODE_LEVELSET || MODE == GX_MODE_DEEP)) {
         if (MODE != GX_MODE_DEEP || (P.dbuf == nullptr && !P.clr_tex)) { gx_raycast_sm<MODE>(P, smp, pos, dir, h, cnt, px, py); return; }
+    }
+    if constexpr (BATCH == 2 && MODE == GX_MODE_DEEP) {
+        // depth-buffer compositing and per-sample colour take the one-brick-at-a-time path below
+        if (P.dbuf == nullptr && !P.clr_tex) { gx_raycast_deep_q(P, smp, pos, dir, h, cnt); return; }
     }
     GxStack st;
     int lev = P.top_lev;
@@ -762,7 +769,7 @@ __device__ __forceinline__ void gx_hit_color(const GxParams& P, GxHit& h)
 
 // ------------------------------------------------------------------------------------------------ shading
 // Phong + optional shadow ray with the same brick function              cuda_gvdb_module.cu:38-57
-template <int MODE, bool BATCH, class S>
+template <int MODE, int BATCH, class S>
 __device__ __forceinline__ float4 gx_phong(const GxParams& P, S& smp, float3 shit, float3 snorm, float4 sclr, GxCount& cnt,
                                            int px, int py)
 {
@@ -787,6 +794,7 @@ __device__ __forceinline__ float4 gx_phong(const GxParams& P, S& smp, float3 shi
 #define GX_FLAG_TILES   4
 #define GX_FLAG_LITERAL 8      // reference-shaped loops: literal nesting, one sample at a time (A/B baseline)
 #define GX_FLAG_PACKET  16     // vote-converged two-phase traversal of gvdbx_trace.cuh (A/B)
+#define GX_FLAG_QUEUE   64     // deep modes: brick-queue traversal (gx_raycast_deep_q, gvdbx_trace.cuh)
 // default (neither flag): literal nesting of traversal and brick visit, four-samples-per-round brick marchers
 
 template <int MODE, class S>
@@ -795,12 +803,12 @@ __device__ __forceinline__ float4 gx2_trace_pixel(const GxParams& P, S& smp, flo
 
 // section / deep-shadow pixel functions (gvdbx_extra.cuh)
 template <class S> __device__ __forceinline__ float4 gx_pixel_section2d(const GxParams&, S&, int, int, GxCount&);
-template <bool BATCH, class S> __device__ __forceinline__ float4 gx_pixel_section3d(const GxParams&, S&, float3, float3, int, int, GxCount&, GxHit&);
-template <bool BATCH, class S> __device__ __forceinline__ float4 gx_pixel_deepshadow(const GxParams&, S&, float3, float3, int, int, GxCount&, GxHit&, float4&);
+template <int BATCH, class S> __device__ __forceinline__ float4 gx_pixel_section3d(const GxParams&, S&, float3, float3, int, int, GxCount&, GxHit&);
+template <int BATCH, class S> __device__ __forceinline__ float4 gx_pixel_deepshadow(const GxParams&, S&, float3, float3, int, int, GxCount&, GxHit&, float4&);
 
 // One camera ray through pixel (x,y) at sub-pixel offset (ox,oy) — the reference kernels use (0.5, 0.5) — shaded to the
 // float colour the reference packs with make_uchar4(clr*255).           cuda_gvdb_module.cu:60-181, :184-207, :225-298
-template <int MODE, bool BATCH, class S>
+template <int MODE, int BATCH, class S>
 __device__ __forceinline__ float4 gx_shade_pixel(const GxParams& P, S& smp, int x, int y, float ox, float oy,
                                                  GxCount& cnt, GxHit& h, float4& raw)
 {
@@ -892,7 +900,7 @@ __global__ void __launch_bounds__(256, GX_MINBLOCKS) gx_render_kernel(const __gr
 
     float4 clr;
     float4 raw = make_float4(0, 0, 0, 0);
-    constexpr bool BATCH = !(FLAGS & GX_FLAG_LITERAL);
+    constexpr int BATCH = !(FLAGS & GX_FLAG_LITERAL);
     if constexpr ((FLAGS & GX_FLAG_PACKET) != 0) {
         float3 rpos = gx_mmult(P.invxform, P.campos);
         float u = float(x + 0.5f) / float(P.width), v = float(y + 0.5f) / float(P.height);

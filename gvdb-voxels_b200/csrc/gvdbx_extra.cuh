@@ -205,7 +205,7 @@ __device__ __forceinline__ void gx_brick_shadow(const GxParams& P, S& smp, int n
 // march from the first sample position towards the light whose accumulated opacity darkens the colour; composite over
 // the background as gvdbRayDeep does.  The reference defines rayShadowBrick but never calls it; the composition is the one
 // SURVEY.md §8c (ii) specifies, and the parity tests build the same thing from the reference's own device functions.
-template <bool BATCH, class S>
+template <int BATCH, class S>
 __device__ __forceinline__ float4 gx_pixel_deepshadow(const GxParams& P, S& smp, float3 rpos, float3 rdir, int x, int y,
                                                       GxCount& cnt, GxHit& h, float4& raw)
 {
@@ -255,7 +255,7 @@ __device__ __forceinline__ float4 gx_pixel_section2d(const GxParams& P, S& smp, 
 
 // gvdbSection3D: transfer colour on the section plane blended over the trilinear surface found behind it.
 //                                                                         cuda_gvdb_module.cu:225-269
-template <bool BATCH, class S>
+template <int BATCH, class S>
 __device__ __forceinline__ float4 gx_pixel_section3d(const GxParams& P, S& smp, float3 rpos, float3 rdir, int x, int y,
                                                      GxCount& cnt, GxHit& h)
 {

@@ -6,9 +6,18 @@
 typedef void (*gx_kernel_t)(const GxParams);
 
 // AB = also build the two A/B traversal variants (reference-shaped loops, packet traversal): core modes only
+// the brick-queue variants (GX_FLAG_QUEUE) exist for the deep modes
 template <int MODE, int SAMPLER, bool UNI, bool AB>
 static gx_kernel_t gx_pick_flags(int flags)
 {
+    if constexpr (MODE == GX_MODE_DEEP || MODE == GX_MODE_DEEPSHADOW) {
+        switch (flags) {
+        case GX_FLAG_QUEUE: return gx_render_kernel<MODE, SAMPLER, GX_FLAG_QUEUE, UNI>;
+        case GX_FLAG_QUEUE | GX_FLAG_TILES: return gx_render_kernel<MODE, SAMPLER, GX_FLAG_QUEUE | GX_FLAG_TILES, UNI>;
+        case GX_FLAG_QUEUE | GX_FLAG_SPP: return gx_render_kernel<MODE, SAMPLER, GX_FLAG_QUEUE | GX_FLAG_SPP, UNI>;
+        case GX_FLAG_QUEUE | GX_FLAG_TILES | GX_FLAG_SPP: return gx_render_kernel<MODE, SAMPLER, GX_FLAG_QUEUE | GX_FLAG_TILES | GX_FLAG_SPP, UNI>;
+        }
+    }
     switch (flags) {
     case 0: return gx_render_kernel<MODE, SAMPLER, 0, UNI>;
     case GX_FLAG_DEBUG | GX_FLAG_COUNT: return gx_render_kernel<MODE, SAMPLER, GX_FLAG_DEBUG | GX_FLAG_COUNT, UNI>;

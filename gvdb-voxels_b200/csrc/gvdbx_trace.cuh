@@ -244,6 +244,161 @@ __device__ __forceinline__ void gx2_brick_deep(const GxParams& P, S& smp, int no
     clr = make_float4(fminf(clr.x, 1.f), fminf(clr.y, 1.f), fminf(clr.z, 1.f), fmaxf(clr.w, 0.f));
 }
 
+// ------------------------------------------------------------------------------------------------ deep mode: brick queue
+// In the literal nesting (brick march inside the hierarchical-DDA loop) the lanes of a warp enter their bricks in different
+// DDA iterations and with different chord lengths, so the sample rounds — 85 % of the instructions of a deep frame — run at
+// 14-15 of 32 lanes (profiles/r02b_cfg4_deep*.raw.csv).  Here a ray alternates between two phases:
+//   A  walk the hierarchical DDA exactly as gx_raycast does, but instead of marching a brick, append {leaf, entry parameter}
+//      to a small per-thread queue in shared memory (bricks whose value range cannot contribute are dropped right here);
+//      until GX_QK bricks are queued or the traversal ends;
+//   B  march the queued bricks in order in ONE flat loop of four-sample rounds: a lane that leaves a brick starts the next
+//      queued one inside the same loop (a ~30-instruction brick entry), so all lanes that still have work sample together
+//      and chord-length differences average out over GX_QK bricks instead of costing idle lanes per brick.
+// Every lane still executes, on its own ray, exactly the reference's sequence of floating-point operations: the DDA never
+// depends on sample results (only the decision to stop does), each brick is entered with the same parameter, samples are
+// consumed in order and the colour clamp is applied at every brick end like rayDeepBrick does.  What changes is only how
+// many DDA iterations run before the ray is found to be opaque (at most GX_QK - 1 bricks of look-ahead), never the image.
+#ifndef GX_QK
+#define GX_QK 8
+#endif
+#define GX_QUEUE_BYTES_PER_THREAD (8 * GX_QK)
+
+template <class S>
+__device__ __forceinline__ void gx_raycast_deep_q(const GxParams& P, S& smp, float3 pos, float3 dir, GxHit& h, GxCount& cnt)
+{
+    GxStack st;
+    int lev = P.top_lev;
+    cnt.rays++;
+    float3 tStart = gx_ray_box(pos, dir, P.bmin, P.bmax);
+    if (tStart.z == GX_NOHIT) return;
+    if (lev < 1 || lev >= GX_MAXLEV) return;
+    int4 np = gx_node_pos(P, lev, 0);
+    cnt.n_desc++;
+    tStart.x += P.epsilon;
+    st.set(lev, 0, tStart.y - P.epsilon);
+    float      cur_tmax = tStart.y - P.epsilon;
+    gx_ctab_t  ctab = gx_table(P, lev, 0, gx_dim<S>(P, lev));
+    unsigned   res = unsigned(gx_res<S>(P, lev));
+    GxDDA dda;
+    dda.set_ray(pos, dir, tStart);
+    dda.prepare(make_float3(float(np.x), float(np.y), float(np.z)), gx_vdel<S>(P, lev));
+
+    // per-thread queue behind the traversal stack: [entry][thread], conflict-free
+    const int nt = blockDim.x * blockDim.y, tid = threadIdx.y * blockDim.x + threadIdx.x;
+    int*   q_leaf = GxStack::base() + 8 * nt + tid;
+    float* q_tx = reinterpret_cast<float*>(GxStack::base() + (8 + GX_QK) * nt) + tid;
+
+    const float stp = P.steps.x;
+    const float3 wpt = make_float3(__fmul_rn(stp, dir.x), __fmul_rn(stp, dir.y), __fmul_rn(stp, dir.z));
+    const float res0 = float(gx_res<S>(P, 0));
+    const float minval = P.cutoff.x, acut = P.cutoff.y, thresh = P.thresh.x;
+    const float inv_range = gx_rcp_approx(P.thresh.z - P.thresh.y);
+    const float4* lut = GX_DEEP_LUT ? P.transfer_deep : P.transfer;
+    float4& clr = h.clr;
+    int  iter = 0;
+    bool walking = true;                 // the hierarchical DDA has not left the volume / spent its iteration budget yet
+
+    while (walking) {
+        // ---- phase A: queue the next bricks (cuda_gvdb_raycast.cuh:567-610 without the brick call)
+        int qn = 0;
+        while (qn < GX_QK) {
+            if (!(iter < GX_MAX_ITER && lev > 0 && lev <= P.top_lev
+                  && unsigned(dda.p.x) <= res && unsigned(dda.p.y) <= res && unsigned(dda.p.z) <= res)) { walking = false; break; }
+            dda.next();
+            const int dm = gx_dim<S>(P, lev);
+            const int b = (((int(dda.p.z) << dm) + int(dda.p.y)) << dm) + int(dda.p.x);
+            int c = -1;
+            if (unsigned(dda.p.x | dda.p.y | dda.p.z) < res) c = gx_child(ctab, b);
+            cnt.n_dda++;
+            if (c != -1) {
+                if (lev == 1) {
+                    // brick entry of rayDeepBrick that depends on the entry parameter only (:490, first-sample bookkeeping)
+                    const float te = dda.t.x + P.epsilon;
+                    const float ts = stp * ceilf(te / stp);
+                    if (h.hit.x == 0) h.hit.x = ts;
+                    cnt.n_desc++;
+                    // a brick without a sample >= MINVAL only re-applies an idempotent clamp: not queued
+                    if (P.range == nullptr || __ldg(&P.range[c].hi) >= minval) { q_leaf[qn * nt] = c; q_tx[qn * nt] = ts; qn++; }
+                    dda.step();
+                } else {
+                    lev--;
+                    np = gx_node_pos(P, lev, c);
+                    cnt.n_desc++;
+                    dda.t.x += P.epsilon;
+                    cur_tmax = dda.t.y - P.epsilon;
+                    st.set(lev, c, cur_tmax);
+                    ctab = gx_table(P, lev, c, gx_dim<S>(P, lev));
+                    res = unsigned(gx_res<S>(P, lev));
+                    dda.prepare(make_float3(float(np.x), float(np.y), float(np.z)), gx_vdel<S>(P, lev));
+                }
+            } else {
+                dda.step();
+            }
+            while (dda.t.x > cur_tmax && lev <= P.top_lev) {
+                lev++;
+                if (lev <= P.top_lev) {
+                    const int n = st.node(lev);
+                    cur_tmax = st.tmax(lev);
+                    ctab = gx_table(P, lev, n, gx_dim<S>(P, lev));
+                    res = unsigned(gx_res<S>(P, lev));
+                    np = gx_node_pos(P, lev, n);
+                    cnt.n_desc++;
+                    dda.prepare(make_float3(float(np.x), float(np.y), float(np.z)), gx_vdel<S>(P, lev));
+                }
+            }
+            iter++;
+        }
+        if (qn == 0) break;
+
+        // ---- phase B: one flat loop of four-sample rounds over the queued bricks
+        int    qi = 0, it = 0;
+        bool   fresh = true;             // the current queue entry has not been entered yet
+        float3 p = make_float3(0, 0, 0), o = make_float3(0, 0, 0);
+        while (qi < qn) {
+            if (fresh) {                 // brick entry (rayDeepBrick :487-496): sample position from the snapped parameter
+                const GxLeafRec L = gx_leaf(P, q_leaf[qi * nt]);
+                smp.enter(L);
+                const float tx = q_tx[qi * nt];
+                o = make_float3(float(L.vx), float(L.vy), float(L.vz));
+                p = gx_poszero(pos + tx * dir - make_float3(float(L.px), float(L.py), float(L.pz)));
+                it = 0;
+                fresh = false;
+            }
+            bool leave = true;           // this brick ends in this round
+            if (clr.w > acut) {
+                float3 p1, p2, p3;
+                GX_STEP_ADD(p1, p); GX_STEP_ADD(p2, p1); GX_STEP_ADD(p3, p2);
+                const bool k0 = GX_INB(p, res0), k1 = GX_INB(p1, res0), k2 = GX_INB(p2, res0), k3 = GX_INB(p3, res0);
+                const float v0 = smp.tri(p.x + o.x, p.y + o.y, p.z + o.z);
+                const float v1 = smp.tri(p1.x + o.x, p1.y + o.y, p1.z + o.z);
+                const float v2 = smp.tri(p2.x + o.x, p2.y + o.y, p2.z + o.z);
+                const float v3 = smp.tri(p3.x + o.x, p3.y + o.y, p3.z + o.z);
+                const float4 c0 = gx_lut(lut, gx_transfer_index(v0, thresh, inv_range));
+                const float4 c1 = gx_lut(lut, gx_transfer_index(v1, thresh, inv_range));
+                const float4 c2 = gx_lut(lut, gx_transfer_index(v2, thresh, inv_range));
+                const float4 c3 = gx_lut(lut, gx_transfer_index(v3, thresh, inv_range));
+                int done = 0;
+                bool more = k0;
+                #define GX_Q_SAMPLE(v, c, knext) { done++; cnt.s_tri++; if ((v) >= minval) { cnt.s_lut++; if (GX_DEEP_LUT) gx_deep_accumulate_pre(P, clr, c); else gx_deep_accumulate(P, clr, c); } more = (knext) && clr.w > acut; }
+                if (more) GX_Q_SAMPLE(v0, c0, k1)
+                if (more) GX_Q_SAMPLE(v1, c1, k2)
+                if (more) GX_Q_SAMPLE(v2, c2, k3)
+                if (more) GX_Q_SAMPLE(v3, c3, true)
+                #undef GX_Q_SAMPLE
+                it += 4;
+                if (done == 4 && it < GX_MAX_ITER && clr.w > acut) { GX_STEP_ADD(p, p3); leave = false; }
+            }
+            if (leave) {                 // exit of rayDeepBrick (:532) and rayCast's tests behind the brick call (:584-590)
+                clr = make_float4(fminf(clr.x, 1.f), fminf(clr.y, 1.f), fminf(clr.z, 1.f), fmaxf(clr.w, 0.f));
+                if (clr.w <= 0) { clr.w = 0; return; }
+                if (clr.w <= acut) return;          // no later brick can change the colour
+                qi++;
+                fresh = true;
+            }
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ lane state machine
 // The literal nesting (rayCast -> brickFunc inside the loop body) makes a warp pay, for every brick visit, as many
 // sample rounds as its LONGEST chord needs: lanes with a short chord (or none) idle, and ncu shows the marchers at 10-15

@@ -255,6 +255,107 @@ class HostFrameRing:
             self._L.gvdbx_hostring_destroy(g)
 
 
+class PeerFrameRingPy:
+    """Executable model of the peer frame ring protocol that csrc/gvdbx_multi.cu implements (gvdbx_ring_*), written over the
+    low-level entry points (peer_alloc / peer_open / stream_wait / stream_signal_* / render_tiles_direct).  The CPU tests run
+    it with a fake renderer on shared memory (tests/test_peer_ring_gloo.py: two real processes, gloo); the product path is
+    PeerFrameRing above.
+
+    Multi-GPU output without a gather: rank 0 owns a ring of `nslots` row-major frames; every rank's render kernel
+    stores the pixels of its tiles straight into the current slot — over NVLink for ranks != 0 (CUDA IPC peer mapping,
+    gvdbx_peer_open) — so render and "gather" are ONE kernel and the only other traffic is two 4-byte flags per frame:
+
+      done[slot]      (rank 0's memory)  += 1 by every rank behind its render kernel (system-scope release);
+                      rank 0's consumer stream waits for world * uses(slot) before it touches the slot
+      released        (every rank's own memory) = q, written by rank 0 once frame q has been consumed;
+                      a rank waits for released >= q - nslots before it renders frame q into the same slot again
+
+    All waits and signals are stream-ordered device-side operations: no host synchronisation, no NCCL on the data path.
+    `exchange(obj) -> list of every rank's obj` is the bootstrap (torch.distributed.all_gather_object by default)."""
+
+    ALIGN = 256
+
+    def __init__(self, renderer, width, height, tile_size, rank, world, nslots=4, exchange=None):
+        self.r, self.w, self.h, self.ts, self.rank, self.world, self.nslots = renderer, width, height, tile_size, rank, world, nslots
+        self.frame_bytes = (width * height * 4 + self.ALIGN - 1) // self.ALIGN * self.ALIGN
+        self.seq = 0
+        self._own, self._opened = [], []
+        if exchange is None:
+            def exchange(obj):
+                import torch.distributed as dist
+                out = [None] * world
+                dist.all_gather_object(out, obj)
+                return out
+        # every rank: a `released` flag of its own; rank 0 additionally: the frame slots followed by the done counters
+        rel_ptr, rel_handle = renderer.peer_alloc(self.ALIGN)
+        self._own.append(rel_ptr)
+        self.released_local = rel_ptr
+        ring_handle = None
+        if rank == 0:
+            ring_ptr, ring_handle = renderer.peer_alloc(self.frame_bytes * nslots + self.ALIGN * nslots)
+            self._own.append(ring_ptr)
+        # (an IPC handle cannot be opened by the process that made it: ranks living in one process — tests — pass raw pointers)
+        handles = exchange({"rank": rank, "pid": os.getpid(), "released": rel_handle, "released_ptr": rel_ptr, "ring": ring_handle,
+                            "ring_ptr": ring_ptr if rank == 0 else None})
+        handles = sorted(handles, key=lambda d: d["rank"])
+        if rank == 0:
+            self.ring_base = ring_ptr
+            self.released_all = [rel_ptr] + [self._open(handles[k], "released") for k in range(1, world)]
+        else:
+            self.ring_base = self._open(handles[0], "ring")
+            self.released_all = None
+        self.frame_ptr = [self.ring_base + s * self.frame_bytes for s in range(nslots)]
+        self.done_ptr = [self.ring_base + nslots * self.frame_bytes + s * self.ALIGN for s in range(nslots)]
+
+    def _open(self, entry, key):
+        if entry["pid"] == os.getpid():
+            return entry[key + "_ptr"]
+        p = self.r.peer_open(entry[key])
+        self._opened.append(p)
+        return p
+
+    def close(self):
+        for p in self._opened:
+            self.r.peer_close(p)
+        for p in self._own:
+            self.r.peer_free(p)
+        self._opened, self._own = [], []
+
+    # ---- every rank
+    def submit(self, scninfo, shade):
+        """enqueue this rank's share of the next frame on the renderer's stream; returns the frame's sequence number"""
+        self.seq += 1
+        q = self.seq
+        slot, _ = ring_slot(q, self.nslots)
+        if getattr(self.r, "nlanes", 0):                      # consecutive frames on alternating internal streams
+            self.r.lane_select((q - 1) % self.r.nlanes)
+        # the slot's previous frame (q - nslots) must have been consumed before its pixels are overwritten
+        wait = (self.released_local, q - self.nslots) if q > self.nslots else (0, 0)
+        if hasattr(self.r, "render_tiles_ring"):
+            self.r.render_tiles_ring(scninfo, shade, self.frame_ptr[slot], self.ts, self.rank, self.world, wait[0], wait[1], self.done_ptr[slot])
+        else:
+            if wait[0]:
+                self.r.stream_wait(*wait)
+            self.r.render_tiles_direct(scninfo, shade, self.frame_ptr[slot], self.ts, self.rank, self.world)
+            self.r.stream_signal_add(self.done_ptr[slot], 1)
+        return q
+
+    # ---- rank 0 (consumer)
+    def acquire(self, q, stream=None):
+        """make `stream` wait until every rank has delivered frame q; returns the device pointer of the finished frame"""
+        slot, uses = ring_slot(q, self.nslots)
+        self.r.stream_wait(self.done_ptr[slot], self.world * uses, stream)
+        return self.frame_ptr[slot]
+
+    def release(self, q, stream=None):
+        """behind the consumer's work on `stream`: hand the slot of frame q back to the producers"""
+        self.r.stream_signal_many(self.released_all, q, stream)
+
+    def frame_tensor(self, q, torch, device):
+        slot, _ = ring_slot(q, self.nslots)
+        return torch.as_tensor(CudaBuffer(self.frame_ptr[slot], (self.h, self.w, 4)), device=device)
+
+
 # ------------------------------------------------------------------------------------------------ volume replication
 def replicate_volume(renderer, vol, rank, world, device, src=0):
     """Replicate the volume of rank `src` on every rank: pools and atlas travel GPU to GPU (torch.distributed broadcast,

@@ -64,7 +64,7 @@ def test_texture_path_bit_exact_vs_reference(scenes, torch_cuda, preset, mode):
     img, dbg = _render(torch_cuda, r, g[f"scn_{mode}"].tobytes(), MODES[mode], w, h, 0, debug=True)
     assert np.array_equal(img, g[f"rgba_{mode}"]), f"{(img != g[f'rgba_{mode}']).any(axis=2).sum()} pixels differ"
     # production variant (brick range culling on) and the A/B traversals: same bytes
-    for trav in (0, 1, 2):
+    for trav in (0, 1, 2, 4):
         r.set_option(5, trav)
         plain = _render(torch_cuda, r, g[f"scn_{mode}"].tobytes(), MODES[mode], w, h, 0)
         assert np.array_equal(plain, g[f"rgba_{mode}"]), (trav, int((plain != g[f"rgba_{mode}"]).any(axis=2).sum()))
@@ -497,25 +497,12 @@ def test_direct_tiles_and_peer_ring_single_process(scenes, torch_cuda, pkg, ora)
         r.render_tiles_direct(scns[0], 0, frame.data_ptr(), ts, rank, world)
     r.sync()
     assert np.array_equal(frame.cpu().numpy(), want[0])
-    # the ring: the "ranks" share one process, so the bootstrap exchange is a list
-    box = []
-
-    def make(rank):
-        def exchange(obj):
-            box.append(obj)
-            return box if rank == 0 else None
-        return exchange
-    # rank 0 must be built last here (it needs everybody's released flag); others resolve rank 0's ring lazily below
-    rings = {}
-    pending = []
-    for rank in (1, 2):
-        rel_ptr, rel_handle = r.peer_alloc(256)
-        pending.append({"rank": rank, "pid": __import__("os").getpid(), "released": rel_handle, "released_ptr": rel_ptr, "ring": None, "ring_ptr": None})
-    rings[0] = mg.PeerFrameRing(r, w, h, ts, 0, world, nslots=nslots, exchange=lambda obj: [obj] + pending)
-    entry0 = {"rank": 0, "pid": __import__("os").getpid(), "released": None, "released_ptr": rings[0].released_local, "ring": None, "ring_ptr": rings[0].ring_base}
-    for rank in (1, 2):
-        rings[rank] = mg.PeerFrameRing(r, w, h, ts, rank, world, nslots=nslots, exchange=lambda obj: [entry0] + pending)
-        rings[rank].released_local = pending[rank - 1]["released_ptr"]      # the flag rank 0 was told about
+    # the ring (C entry points gvdbx_ring_*): the "ranks" share one process, so the bootstrap exchange is a list and the ring
+    # falls back from IPC handles to raw pointers
+    rings = {rank: mg.PeerFrameRing(r, w, h, ts, rank, world, nslots=nslots, connect=False) for rank in range(world)}
+    blobs = [rings[rank].blob for rank in (2, 0, 1)]          # any order
+    for rank in range(world):
+        rings[rank].connect(blobs)
     consumer = torch.cuda.Stream()
     got = []
     for j in range(nframes):
@@ -529,13 +516,57 @@ def test_direct_tiles_and_peer_ring_single_process(scenes, torch_cuda, pkg, ora)
     r.sync()
     for j in range(nframes):
         assert np.array_equal(got[j].cpu().numpy(), want[j]), j
-    # no wait ran into its timeout
-    flags = torch.as_tensor(mg.CudaBuffer(rings[0].done_ptr[0], (2,), "<u4"), device="cuda").cpu().numpy()
-    assert flags[1] != 0xDEAD
     for k in (1, 2, 0):
-        rings[k].close()
-    for e in pending:
-        r.peer_free(e["released_ptr"])
+        rings[k].close()                             # raises if a stream-ordered wait ran into its timeout
+
+
+def test_host_frame_ring_single_process(scenes, torch_cuda, pkg, ora):
+    """gvdbx_hostring_*: three "ranks" of one process render full-width bands of every frame, copy their bands into the
+    shared page-locked host ring and the consumer gets row-major frames identical to the single-kernel render; a slot is
+    rewritten only after its release (2 slots, 7 frames); band rendering alone (gvdbx_render_bands) checked too."""
+    torch = torch_cuda
+    import os
+    from gvdb_voxels_b200 import multigpu as mg
+    g = golden("cfg1_small")
+    p, vol, r = scenes("cfg1_small")
+    w, h = int(g["width"]), int(g["height"])
+    r.set_sampler(0)
+    world, nslots, nframes, rows = 3, 2, 7, 16
+    scns = [ora.scninfo_for(pkg, p, shade=4, cam_angs=(p.cam_angs[0] + 30.0 * j, p.cam_angs[1], p.cam_angs[2]))[0] for j in range(nframes)]
+    want = [_render(torch, r, s, 4, w, h, 0) for s in scns]
+    assert np.array_equal(want[0], g["rgba_trilinear"])
+    # bands alone: rank k's packed buffer holds bands k, k + world, ...
+    nb = (h + rows - 1) // rows
+    per = (nb + world - 1) // world
+    for rank in range(world):
+        packed = torch.zeros((per, rows, w, 4), dtype=torch.uint8, device="cuda")
+        r.render_bands(scns[0], 4, packed.data_ptr(), rows, rank, world)
+        r.sync()
+        pk = packed.cpu().numpy()
+        for k in range(per):
+            b = k * world + rank
+            if b < nb:
+                y0 = b * rows
+                n = min(rows, h - y0)
+                assert np.array_equal(pk[k, :n], want[0][y0:y0 + n]), (rank, k)
+    name = f"/gvdbx_test_{os.getpid()}"
+    rings = [mg.HostFrameRing(r, name, w, h, rank, world, nslots=nslots, band_rows=rows) for rank in range(world)]
+    got = []
+    for j in range(nframes):
+        if j >= nslots:                              # the consumer lags nslots frames behind the producers
+            q0 = j - nslots + 1
+            got.append(rings[0].wait(q0).copy())
+            rings[0].release(q0)
+        for rank in (1, 2, 0):
+            q = rings[rank].submit(scns[j], 4)
+        assert q == j + 1
+    for q0 in range(nframes - nslots + 1, nframes + 1):
+        got.append(rings[0].wait(q0).copy())
+        rings[0].release(q0)
+    for j in range(nframes):
+        assert np.array_equal(got[j], want[j]), j
+    for ring in rings[::-1]:
+        ring.close()
 
 
 def test_stream_flags_order_two_streams(scenes, torch_cuda, pkg):

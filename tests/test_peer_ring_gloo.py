@@ -1,4 +1,5 @@
-"""World-size-2 CPU test (gloo) of the peer frame ring protocol (gvdb-voxels_b200/multigpu.py::PeerFrameRing): two real
+"""World-size-2 CPU test (gloo) of the peer frame ring protocol (gvdb-voxels_b200/multigpu.py::PeerFrameRingPy, the executable model of
+csrc/gvdbx_multi.cu::gvdbx_ring_*): two real
 processes, "device memory" = POSIX shared memory, the stream-ordered flag operations executed synchronously.  Checks the
 host-side logic the multi-GPU path depends on: handle exchange, slot / use arithmetic, back-pressure (a slot is never
 rewritten before rank 0 released it) and that every finished frame holds every rank's tiles of THAT frame."""
@@ -98,7 +99,7 @@ def _worker(rank, world, port, w, h, ts, nslots, nframes, q):
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     r = FakeRenderer(rank)
-    ring = mg.PeerFrameRing(r, w, h, ts, rank, world, nslots=nslots)
+    ring = mg.PeerFrameRingPy(r, w, h, ts, rank, world, nslots=nslots)
     ok = True
     tx = (w + ts - 1) // ts
     for f in range(nframes):
