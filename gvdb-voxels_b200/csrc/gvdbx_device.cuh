@@ -900,7 +900,7 @@ __global__ void __launch_bounds__(256, GX_MINBLOCKS) gx_render_kernel(const __gr
 
     float4 clr;
     float4 raw = make_float4(0, 0, 0, 0);
-    constexpr int BATCH = !(FLAGS & GX_FLAG_LITERAL);
+    constexpr int BATCH = (FLAGS & GX_FLAG_LITERAL) ? 0 : ((FLAGS & GX_FLAG_QUEUE) ? 2 : 1);   // 0 literal loops, 1 four-sample rounds, 2 + brick queue
     if constexpr ((FLAGS & GX_FLAG_PACKET) != 0) {
         float3 rpos = gx_mmult(P.invxform, P.campos);
         float u = float(x + 0.5f) / float(P.width), v = float(y + 0.5f) / float(P.height);
