@@ -696,6 +696,13 @@ __device__ __forceinline__ void gx_raycast(const GxParams& P, S& smp, float3 pos
     dda.prepare(vmin, gx_vdel<S>(P, lev));
     const float tDepth = gx_depth_max(P, dir, px, py);
 
+    // Level changes.  A descent (:592-597) and every pop of the ascent loop (:603-608) end with HDDAState::Prepare, a pure
+    // function of (ray, t.x, node corner, cell size): when several happen in one iteration only the LAST one survives, so
+    // the level bookkeeping runs where the reference has it and ONE Prepare runs at the end of the iteration — at a single
+    // code site, where the lanes that descended and the lanes that ascended execute it together.
+    int node = 0;
+    bool moved = false;
+
     // loop guard of the reference (cuda_gvdb_raycast.cuh:567): 0 <= p <= res on every axis == unsigned(p) <= res
     for (int iter = 0; iter < GX_MAX_ITER && lev > 0 && lev <= P.top_lev
                        && unsigned(dda.p.x) <= res && unsigned(dda.p.y) <= res && unsigned(dda.p.z) <= res; iter++) {
@@ -730,15 +737,11 @@ __device__ __forceinline__ void gx_raycast(const GxParams& P, S& smp, float3 pos
                 dda.step();
             } else {
                 lev--;
-                np = gx_node_pos(P, lev, c);
                 cnt.n_desc++;
-                vmin = make_float3(float(np.x), float(np.y), float(np.z));
                 dda.t.x += P.epsilon;
                 cur_tmax = dda.t.y - P.epsilon;
                 st.set(lev, c, cur_tmax);
-                ctab = gx_table(P, lev, c, gx_dim<S>(P, lev));
-                res = unsigned(gx_res<S>(P, lev));
-                dda.prepare(vmin, gx_vdel<S>(P, lev));
+                node = c; moved = true;
             }
         } else {
             dda.step();
@@ -746,15 +749,19 @@ __device__ __forceinline__ void gx_raycast(const GxParams& P, S& smp, float3 pos
         while (dda.t.x > cur_tmax && lev <= P.top_lev) {
             lev++;
             if (lev <= P.top_lev) {
-                const int n = st.node(lev);
+                node = st.node(lev);
                 cur_tmax = st.tmax(lev);
-                ctab = gx_table(P, lev, n, gx_dim<S>(P, lev));
-                res = unsigned(gx_res<S>(P, lev));
-                np = gx_node_pos(P, lev, n);
                 cnt.n_desc++;
-                vmin = make_float3(float(np.x), float(np.y), float(np.z));
-                dda.prepare(vmin, gx_vdel<S>(P, lev));
+                moved = true;
             }
+        }
+        if (moved && lev <= P.top_lev) {
+            moved = false;
+            ctab = gx_table(P, lev, node, gx_dim<S>(P, lev));
+            res = unsigned(gx_res<S>(P, lev));
+            np = gx_node_pos(P, lev, node);
+            vmin = make_float3(float(np.x), float(np.y), float(np.z));
+            dda.prepare(vmin, gx_vdel<S>(P, lev));
         }
     }
 }

@@ -295,11 +295,13 @@ __device__ __forceinline__ void gx_raycast_deep_q(const GxParams& P, S& smp, flo
     const float inv_range = gx_rcp_approx(P.thresh.z - P.thresh.y);
     const float4* lut = GX_DEEP_LUT ? P.transfer_deep : P.transfer;
     float4& clr = h.clr;
-    int  iter = 0;
+    int  iter = 0, node = 0;
     bool walking = true;                 // the hierarchical DDA has not left the volume / spent its iteration budget yet
+    bool moved = false;                  // the level changed in this iteration: one Prepare pending
 
     while (walking) {
-        // ---- phase A: queue the next bricks (cuda_gvdb_raycast.cuh:567-610 without the brick call)
+        // ---- phase A: queue the next bricks (cuda_gvdb_raycast.cuh:567-610 without the brick call; one Prepare per
+        // iteration at a single site, see gx_raycast)
         int qn = 0;
         while (qn < GX_QK) {
             if (!(iter < GX_MAX_ITER && lev > 0 && lev <= P.top_lev
@@ -322,14 +324,11 @@ __device__ __forceinline__ void gx_raycast_deep_q(const GxParams& P, S& smp, flo
                     dda.step();
                 } else {
                     lev--;
-                    np = gx_node_pos(P, lev, c);
                     cnt.n_desc++;
                     dda.t.x += P.epsilon;
                     cur_tmax = dda.t.y - P.epsilon;
                     st.set(lev, c, cur_tmax);
-                    ctab = gx_table(P, lev, c, gx_dim<S>(P, lev));
-                    res = unsigned(gx_res<S>(P, lev));
-                    dda.prepare(make_float3(float(np.x), float(np.y), float(np.z)), gx_vdel<S>(P, lev));
+                    node = c; moved = true;
                 }
             } else {
                 dda.step();
@@ -337,14 +336,18 @@ __device__ __forceinline__ void gx_raycast_deep_q(const GxParams& P, S& smp, flo
             while (dda.t.x > cur_tmax && lev <= P.top_lev) {
                 lev++;
                 if (lev <= P.top_lev) {
-                    const int n = st.node(lev);
+                    node = st.node(lev);
                     cur_tmax = st.tmax(lev);
-                    ctab = gx_table(P, lev, n, gx_dim<S>(P, lev));
-                    res = unsigned(gx_res<S>(P, lev));
-                    np = gx_node_pos(P, lev, n);
                     cnt.n_desc++;
-                    dda.prepare(make_float3(float(np.x), float(np.y), float(np.z)), gx_vdel<S>(P, lev));
+                    moved = true;
                 }
+            }
+            if (moved && lev <= P.top_lev) {
+                moved = false;
+                ctab = gx_table(P, lev, node, gx_dim<S>(P, lev));
+                res = unsigned(gx_res<S>(P, lev));
+                np = gx_node_pos(P, lev, node);
+                dda.prepare(make_float3(float(np.x), float(np.y), float(np.z)), gx_vdel<S>(P, lev));
             }
             iter++;
         }
