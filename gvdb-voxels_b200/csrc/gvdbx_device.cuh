@@ -258,7 +258,7 @@ template <class S> __device__ __forceinline__ int gx_res(const GxParams& P, int 
 template <class S> __device__ __forceinline__ int gx_dim(const GxParams& P, int lev) { return S::UNI ? 3 : P.dim[lev]; }
 template <class S> __device__ __forceinline__ float3 gx_vdel(const GxParams& P, int lev)
 {
-    if (S::UNI) { const float v = float(1 << (3 * lev)); return make_float3(v, v, v); }     // 8^lev, exact
+    if (S::UNI) { const float v = __int_as_float((127 + 3 * lev) << 23); return make_float3(v, v, v); }     // 8^lev, exact, from exponent bits
     return P.vdel[lev];
 }
 
@@ -631,15 +631,14 @@ struct GxStack {
 #else
     static __device__ __forceinline__ int* base() { extern __shared__ int gx_stack_smem[]; return gx_stack_smem; }
 #endif
-    static __device__ __forceinline__ int  slot(int lev)
-    {
-        const int nt = blockDim.x * blockDim.y;
-        return (lev - 1) * nt + threadIdx.y * blockDim.x + threadIdx.x;
-    }
-    static __device__ __forceinline__ int  half() { return 4 * blockDim.x * blockDim.y; }
-    __device__ __forceinline__ void  set(int lev, int n, float m) const { base()[slot(lev)] = n; base()[half() + slot(lev)] = __float_as_int(m); }
-    __device__ __forceinline__ int   node(int lev) const { return base()[slot(lev)]; }
-    __device__ __forceinline__ float tmax(int lev) const { return __int_as_float(base()[half() + slot(lev)]); }
+    // this thread's column and the row pitch, computed ONCE per ray: a level change is then one multiply-add and two
+    // shared-memory accesses (level changes happen in more than half of all DDA iterations of a sparse volume)
+    int* col;
+    int  nt;
+    __device__ __forceinline__ GxStack() : nt(blockDim.x * blockDim.y) { col = base() + threadIdx.y * blockDim.x + threadIdx.x; }
+    __device__ __forceinline__ void  set(int lev, int n, float m) const { int* p = col + (lev - 1) * nt; p[0] = n; p[4 * nt] = __float_as_int(m); }
+    __device__ __forceinline__ int   node(int lev) const { return col[(lev - 1) * nt]; }
+    __device__ __forceinline__ float tmax(int lev) const { return __int_as_float(col[(lev + 3) * nt]); }
 };
 
 // four-samples-per-round brick marchers (gvdbx_trace.cuh)

@@ -284,9 +284,9 @@ __device__ __forceinline__ void gx_raycast_deep_q(const GxParams& P, S& smp, flo
     dda.prepare(make_float3(float(np.x), float(np.y), float(np.z)), gx_vdel<S>(P, lev));
 
     // per-thread queue behind the traversal stack: [entry][thread], conflict-free
-    const int nt = blockDim.x * blockDim.y, tid = threadIdx.y * blockDim.x + threadIdx.x;
-    int*   q_leaf = GxStack::base() + 8 * nt + tid;
-    float* q_tx = reinterpret_cast<float*>(GxStack::base() + (8 + GX_QK) * nt) + tid;
+    const int nt = st.nt;
+    int*   q_leaf = st.col + 8 * nt;
+    float* q_tx = reinterpret_cast<float*>(st.col + (8 + GX_QK) * nt);
 
     const float stp = P.steps.x;
     const float3 wpt = make_float3(__fmul_rn(stp, dir.x), __fmul_rn(stp, dir.y), __fmul_rn(stp, dir.z));
