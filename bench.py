@@ -688,42 +688,50 @@ def main():
             sys.stderr.write(f"[bench] frame mismatch: {int(bad.sum())} pixels, by owning rank {np.bincount(owner, minlength=world).tolist()}\n")
     dist.barrier()      # the other ranks must not start the e2e frames (which reuse the ring slots) while rank 0 still compares
 
-    # ---------------- e2e with host buffers: every finished frame ends in pinned host memory on rank 0
-    host = torch.empty((h, w, 4), dtype=torch.uint8).pin_memory()
-    if ring is not None:
-        host_ring = [host] + [torch.empty((h, w, 4), dtype=torch.uint8).pin_memory() for _ in range(a.slots - 1)] if rank == 0 else []
+    # ---------------- e2e with host buffers: every finished frame ends row-major in page-locked host memory that rank 0 reads.
+    # Host frame ring (gvdbx_hostring_*): each rank renders full-width 32-row bands and copies ITS bands over ITS OWN PCIe
+    # link into a shared-memory frame — N links instead of funnelling every frame through rank 0's.
+    hring = mg.HostFrameRing(r, f"/gvdbx_bench_{os.environ.get('MASTER_PORT', '0')}", w, h, rank, world, nslots=a.slots, band_rows=32)
+    checksum = 0
 
-        def to_host(q, cs):
-            with torch.cuda.stream(cs):                     # D2H of the finished frame behind the acquire, on its consumer stream
-                host_ring[(q - 1) % a.slots].copy_(ring.frame_tensor(q, torch, dev), non_blocking=True)
-
-        def step_e2e():
-            step_resident(on_frame=to_host if rank == 0 else None)
-            if rank == 0:
-                for cs in consumers:
-                    cs.synchronize()                        # the caller owns the host frames of this step now
-            r.lane_select(-1)
-    else:
-        def to_host(j, fr):
-            host.copy_(fr, non_blocking=True)                   # D2H of the assembled frame, stream-ordered
-            torch.cuda.current_stream().synchronize()           # the caller owns the host frame now
-
-        def step_e2e():
-            tiled.render_frames(scns, shade, on_frame=to_host)
+    def step_e2e():
+        nonlocal checksum
+        for scn in scns:
+            q = hring.seq + 1
+            if rank == 0 and q > a.slots:               # the consumer lags `slots` frames behind the producers
+                fr = hring.wait(q - a.slots)
+                checksum += int(fr[::97, ::89, 1].sum())    # the caller touches the frame it owns now
+                hring.release(q - a.slots)
+            hring.submit(scn, shade)
     for _ in range(2):
         step_e2e()
     sync_all()
     t0 = time.perf_counter()
     for _ in range(a.steps):
         step_e2e()
+    if rank == 0:                                       # drain: every frame of the timed steps has been handed to the caller
+        for q in range(max(1, hring.seq - a.slots + 1), hring.seq + 1):
+            fr = hring.wait(q)
+            checksum += int(fr[::97, ::89, 1].sum())
+            hring.release(q)
     sync_all()
     dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
     dist.all_reduce(dt, op=dist.ReduceOp.MAX)
     dt = float(dt.item())
+    # the last frame delivered through the host ring equals the single-GPU render of the same camera
+    host_ok = None
+    if rank == 0:
+        ref = torch.zeros_like(frame)
+        r.lane_select(-1)
+        r.render(scns[-1], shade, ref.data_ptr())
+        r.sync()
+        last_host = hring.wait(hring.seq)               # still in its slot (released slots are only rewritten by later frames)
+        host_ok = bool(np.array_equal(ref.cpu().numpy(), last_host))
+    dist.barrier()
+    hring.close()
     e2e = {"value": rays_step * a.steps / dt / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": a.frames * 416 * world,
-           "d2h_bytes_per_step": a.frames * w * h * 4, "ms_per_frame": dt / a.steps / a.frames * 1e3,
-           "api": ("gvdbx_render_tiles_ring per rank into rank 0's frame ring over NVLink + D2H to pinned host on rank 0" if ring is not None
-                   else "gvdbx_render_tiles per rank + NCCL gather + gvdbx_assemble_tiles + D2H to pinned host on rank 0")}
+           "d2h_bytes_per_step": a.frames * w * h * 4, "ms_per_frame": dt / a.steps / a.frames * 1e3, "host_frame_matches_single_gpu": host_ok,
+           "api": "gvdbx_hostring_submit per rank (own 32-row bands -> own PCIe link -> shared page-locked host frame), gvdbx_hostring_wait / _release on rank 0"}
     if ring is not None:
         ring.check()            # no stream-ordered wait ran into its timeout
 

@@ -18,25 +18,25 @@ extern "C" int gvdbx_create(gvdbx_t** out, int cuda_device, void* cuda_stream)
                 e == cudaSuccess ? "device index out of range" : cudaGetErrorString(e));
         return GVDBX_E_CUDA;
     }
-    // adopt the caller's current context (the reference's own, when called from the VolumeGVDB shim); otherwise bind the
-    // primary context of `cuda_device`
+    // adopt the caller's current context when it lives on `cuda_device` (the reference's own, when called from the VolumeGVDB
+    // shim); otherwise bind the primary context of `cuda_device` and leave the caller's current device as it was
     void* cur = nullptr;
     int curdev = -1;
-    if (gx_drv.load() && gx_drv.get(&cur) == 0 && cur != nullptr && gx_drv.dev(&curdev) == 0) {
-        if (curdev != cuda_device) {
-            fprintf(stderr, "gvdbx_create: the current CUDA context is on device %d, not %d\n", curdev, cuda_device);
-            return GVDBX_E_ARG;
-        }
-    } else {
+    const bool have_cur = gx_drv.load() && gx_drv.get(&cur) == 0 && cur != nullptr && gx_drv.dev(&curdev) == 0;
+    if (!have_cur || curdev != cuda_device) {
+        int prev = -1;
+        if (have_cur) cudaGetDevice(&prev);
         if (cudaSetDevice(cuda_device) != cudaSuccess || cudaFree(0) != cudaSuccess) return GVDBX_E_CUDA;
         cur = nullptr;
         if (gx_drv.ok) gx_drv.get(&cur);
+        if (prev >= 0 && prev != cuda_device) cudaSetDevice(prev);
     }
     gvdbx_t* h = new gvdbx_ctx;
     h->device = cuda_device;
     h->cuctx = cur;
     h->stream = (cudaStream_t)cuda_stream;
     h->base_stream = h->stream;
+    GxCtx ctx_(h);
     if (cudaMalloc(&h->d_counters, 8 * sizeof(unsigned long long)) != cudaSuccess) { delete h; return GVDBX_E_CUDA; }
     cudaMemset(h->d_counters, 0, 8 * sizeof(unsigned long long));
     if (cudaMalloc(&h->d_err, sizeof(int)) != cudaSuccess) { cudaFree(h->d_counters); delete h; return GVDBX_E_CUDA; }
