@@ -388,37 +388,47 @@ def count_work(r, scns, shade, frame_d, w, h, mode):
     return tot, float(alg)
 
 
-def roofline_block(key, kernel, ms_total, frames_total, n_gpus, sm_mhz, alg_ref, alg_prod, units_ref, units_prod):
-    """The bound that binds is instruction ISSUE (DRAM sits below 1 % of peak: neighbouring rays share bricks, 99 % of the
-    sectors hit in L1): achieved = warp instructions the kernel executes per frame (ncu sm__inst_executed.sum of the committed
-    capture of this kernel on this input; deterministic) x frames / live CUDA-event time; peak = 148 SMs x 4 schedulers x SM
-    clock measured during the run.  The HBM figures the task's contract asks for are kept next to it: DRAM-measured traffic,
-    and the SURVEY 8(d) algorithmic bytes as an EFFECTIVE bandwidth (can exceed the copy peak by cache reuse)."""
+def roofline_block(key, mode, kernel, ms_total, frames_total, n_gpus, sm_mhz, alg_ref, alg_prod, units_ref, units_prod, tex_peak):
+    """Which unit binds depends on the mode (DRAM never does: it sits below 1 % of peak because neighbouring rays share bricks
+    and 98-99 % of the sectors hit in L1):
+      deep modes    : the TEXTURE units — achieved = fp32 trilinear samples the production kernel takes (counted) / live time,
+                      peak = gvdbx_measure_tex_peak run in this process on this GPU (L1-resident bricks, fetches only);
+      surface modes : instruction ISSUE — achieved = warp instructions per frame (ncu sm__inst_executed of the committed capture
+                      of this kernel on this input; deterministic) x frames / live time, peak = 148 SMs x 4 schedulers x SM
+                      clock measured during the run.
+    The HBM figures the task's contract asks for are kept next to them: DRAM-measured traffic, and the SURVEY 8(d) algorithmic
+    bytes as an EFFECTIVE bandwidth (cache-served, can exceed the copy peak)."""
     hbm_peak, sm_max, src = peaks()
     kc = kernel_counters(key)
     t = ms_total * 1e-3
     clock = (sm_mhz or sm_max) * 1e6
     peak_issue = N_SM * ISSUE_PER_SM * clock * n_gpus / 1e9          # G warp instructions / s, whole job
-    out = {"bound": "issue", "unit": "Ginst/s", "peak": peak_issue, "peak_source": f"{N_SM} SMs x {ISSUE_PER_SM} warp schedulers x {clock / 1e6:.0f} MHz (nvidia-smi during the run) x {n_gpus} GPU(s)",
-           "kernel": kernel, "achieved": None, "frac": None, "traffic": None}
+    issue = {"unit": "Ginst/s", "peak": peak_issue, "achieved": None, "frac": None,
+             "peak_source": f"{N_SM} SMs x {ISSUE_PER_SM} warp schedulers x {clock / 1e6:.0f} MHz (nvidia-smi during the run) x {n_gpus} GPU(s)"}
     if kc:
         inst = float(kc["inst_executed"])
-        out.update(achieved=inst * frames_total / t / 1e9, traffic=kc.get("dram_bytes"),
-                   inst_executed_per_frame=inst, lanes_per_instruction=kc.get("lanes_per_inst"), ipc_ncu=kc.get("ipc"),
-                   tex_pipe_pct=kc.get("tex_pipe_pct"), l1_hit_pct=kc.get("l1_hit_pct"), l2_hit_pct=kc.get("l2_hit_pct"),
-                   counters_from=kc.get("source"))
-        out["frac"] = out["achieved"] / peak_issue
+        issue.update(achieved=inst * frames_total / t / 1e9, inst_executed_per_frame=inst, lanes_per_instruction=kc.get("lanes_per_inst"),
+                     ipc_ncu=kc.get("ipc"), tex_pipe_pct_ncu=kc.get("tex_pipe_pct"), l1_hit_pct=kc.get("l1_hit_pct"), l2_hit_pct=kc.get("l2_hit_pct"),
+                     counters_from=kc.get("source"))
+        issue["frac"] = issue["achieved"] / peak_issue
+    tex = {"unit": "Gsamples/s", "peak": (tex_peak * n_gpus) if tex_peak else None, "achieved": units_prod["s_tri"] / t / 1e9 if units_prod else None,
+           "peak_source": "gvdbx_measure_tex_peak: fp32 trilinear fetches on L1-resident bricks of this atlas, 8 in flight per thread, measured in this run"}
+    tex["frac"] = (tex["achieved"] / tex["peak"]) if tex["peak"] and tex["achieved"] else None
     dram = (kc["dram_bytes"] * frames_total / t / 1e9) if kc and kc.get("dram_bytes") else None
-    out["hbm"] = {"peak": hbm_peak * n_gpus, "unit": "GB/s", "peak_source": src,
-                  "dram_achieved": dram, "dram_frac": (dram / (hbm_peak * n_gpus)) if dram else None,
-                  "effective": alg_ref / t / 1e9, "effective_frac": alg_ref / t / 1e9 / (hbm_peak * n_gpus),
-                  "effective_culled": alg_prod / t / 1e9,
-                  "note": "effective = SURVEY 8(d) algorithmic bytes (32 B per trilinear sample, 4 B per point sample, 8 B per DDA step, 64 B per node "
-                          "record, 4 B per pixel) of the algorithm as the reference runs it / time; effective_culled = the same units counted in the "
-                          "production kernel (value-range culling and occupancy bits skip work); both are cache-served: only `dram_achieved` reaches HBM",
-                  "units_per_step": units_ref, "units_per_step_culled": units_prod,
-                  "bytes_per_unit": {"s_tri": B_TRI, "s_pt": B_PT, "n_dda": B_DDA, "n_desc": B_DESC, "pixel": B_PIX}}
-    return out
+    hbm = {"peak": hbm_peak * n_gpus, "unit": "GB/s", "peak_source": src,
+           "dram_achieved": dram, "dram_frac": (dram / (hbm_peak * n_gpus)) if dram else None,
+           "effective": alg_ref / t / 1e9, "effective_frac": alg_ref / t / 1e9 / (hbm_peak * n_gpus),
+           "effective_culled": alg_prod / t / 1e9,
+           "note": "effective = SURVEY 8(d) algorithmic bytes (32 B per trilinear sample, 4 B per point sample, 8 B per DDA step, 64 B per node "
+                   "record, 4 B per pixel) of the algorithm as the reference runs it / time; effective_culled = the same units counted in the "
+                   "production kernel (value-range culling and occupancy bits skip work); both are cache-served: only `dram_achieved` reaches HBM",
+           "units_timed_region": units_ref, "units_timed_region_culled": units_prod,
+           "bytes_per_unit": {"s_tri": B_TRI, "s_pt": B_PT, "n_dda": B_DDA, "n_desc": B_DESC, "pixel": B_PIX}}
+    bound = "tex" if mode in ("deep", "deepshadow") else "issue"
+    top = tex if bound == "tex" else issue
+    return {"bound": bound, "achieved": top["achieved"], "peak": top["peak"], "unit": top["unit"], "frac": top["frac"],
+            "traffic": kc.get("dram_bytes") if kc else None, "kernel": kernel, "peak_source": top["peak_source"],
+            "issue": issue, "tex": tex, "hbm": hbm}
 
 
 def measure_single(torch, pkg, a, workload, mode, dev, local, steps, warmup, full):
@@ -467,13 +477,14 @@ def measure_single(torch, pkg, a, workload, mode, dev, local, steps, warmup, ful
     res.update(value=rays_step * steps / (ms_total * 1e-3) / 1e6, ms_per_frame=ms_total / steps / a.frames, latency_ms_1lane=lat["mean"],
                latency_1lane=lat, value_1lane=w * h * a.spp / (lat["mean"] * 1e-3) / 1e6)
     dev_resident_gb = (total0 - free0) / 1e9
+    tex_peak = r.measure_tex_peak() if full else None
     r.close()
     del frames_d
     torch.cuda.empty_cache()
     strict = time_e2e(torch, pkg, p, vol, local, a, shade, dshadow, a.frames, max(2, steps // 2), 0)
     res["e2e_strict"] = strict
     extra = {"ms_total": ms_total, "launches": launches, "p": p, "vol": vol, "scns": scns, "shade": shade, "dshadow": dshadow,
-             "clocks": clk, "units_ref": units_ref, "units_prod": units_prod, "alg_ref": alg_ref * a.spp, "alg_prod": alg_prod * a.spp, "device_gb_after_import": dev_resident_gb}
+             "clocks": clk, "tex_peak": tex_peak, "units_ref": units_ref, "units_prod": units_prod, "alg_ref": alg_ref * a.spp, "alg_prod": alg_prod * a.spp, "device_gb_after_import": dev_resident_gb}
     return res, extra
 
 
@@ -582,6 +593,7 @@ def main():
     if rank == 0:
         units_ref, alg_ref = count_work(r, scns, shade, frame, w, h, 1)
         units_prod, alg_prod = count_work(r, scns, shade, frame, w, h, 2)
+    tex_peak = r.measure_tex_peak() if rank == 0 else None
     r.set_spp(a.spp)
     r.lanes(a.lanes)
     launches = 0
@@ -741,8 +753,9 @@ def main():
         return 0
 
     key = f"{a.workload}:{a.mode}:{a.sampler}"
-    roofline = roofline_block(key, f"gx_render_kernel<{a.mode},{a.sampler},tiles>", ms_total, a.frames * a.steps * a.spp, world,
-                              clk["sm_mhz"] if clk else None, alg_ref * a.spp * a.steps, alg_prod * a.spp * a.steps, units_ref, units_prod)
+    scale = lambda u: {k: v * a.steps * a.spp for k, v in u.items()} if u else None
+    roofline = roofline_block(key, a.mode, f"gx_render_kernel<{a.mode},{a.sampler},tiles>", ms_total, a.frames * a.steps * a.spp, world,
+                              clk["sm_mhz"] if clk else None, alg_ref * a.spp * a.steps, alg_prod * a.spp * a.steps, scale(units_ref), scale(units_prod), tex_peak)
     value = rays_step * a.steps / (ms_total * 1e-3) / 1e6
     out = {"metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
            "ms_per_step": ms_total / a.steps, "ms_per_frame": ms_total / a.steps / a.frames, "higher_is_better": True,
@@ -769,8 +782,9 @@ def main_single(torch, pkg, a, dev, local):
     e2e = time_e2e(torch, pkg, p, vol, local, a, shade, dshadow, a.frames, a.steps, a.lanes)
 
     key = f"{a.workload}:{a.mode}:{a.sampler}"
-    roofline = roofline_block(key, f"gx_render_kernel<{a.mode},{a.sampler}>", x["ms_total"], a.frames * a.steps * a.spp, 1, clk_all["sm_mhz"],
-                              x["alg_ref"] * a.steps, x["alg_prod"] * a.steps, x["units_ref"], x["units_prod"])
+    scale = lambda u: {k: v * a.steps * a.spp for k, v in u.items()} if u else None     # counted once per orbit -> the timed region
+    roofline = roofline_block(key, a.mode, f"gx_render_kernel<{a.mode},{a.sampler}>", x["ms_total"], a.frames * a.steps * a.spp, 1, clk_all["sm_mhz"],
+                              x["alg_ref"] * a.steps, x["alg_prod"] * a.steps, scale(x["units_ref"]), scale(x["units_prod"]), x["tex_peak"])
 
     # ---------------- CPU baseline: oracle port on a bounded sample (whole frames of the orbit, ~15 s of CPU work)
     cpu = None

@@ -9,7 +9,7 @@ There is no CPU fallback: every call that needs the device raises GvdbxError whe
 shared library or a CUDA device is missing.
 """
 from .api import (  # noqa: F401
-    GvdbxError, Renderer, Volume, lib, lib_path, HOST_SYMBOLS,
+    GvdbxError, Renderer, Volume, lib, lib_path, HOST_SYMBOLS, render_multi,
     SHADE_VOXEL, SHADE_TRILINEAR, SHADE_LEVELSET, SHADE_VOLUME, SHADE_OFF,
     SHADE_SECTION2D, SHADE_SECTION3D, SHADE_EMPTYSKIP, SHADE_TRICUBIC,
     OPT_SAMPLER, OPT_BLOCK_W, OPT_BLOCK_H, OPT_COUNTERS, OPT_TRAVERSAL, OPT_CULL, OPT_SPP, OPT_DEEP_SHADOW,

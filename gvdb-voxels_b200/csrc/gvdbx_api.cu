@@ -1082,6 +1082,37 @@ extern "C" int gvdbx_sample_points(gvdbx_t* h, int chan, uint64_t xyz_d, int n, 
     return GVDBX_OK;
 }
 
+// fp32 trilinear samples per second of this GPU's texture units on L1-resident bricks of the imported atlas (synchronises)
+extern "C" int gvdbx_measure_tex_peak(gvdbx_t* h, double* gsamples_per_s)
+{
+    if (!h || !gsamples_per_s) return GVDBX_E_ARG;
+    if (!h->have_atlas) return gx_fail(h, GVDBX_E_STATE, "no atlas imported");
+    GxCtx ctx_(h);
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
+    const int blocks = sms * 8, threads = 256, rounds = 512;
+    float* out = nullptr;
+    GX_CUDA(h, cudaMalloc(&out, size_t(blocks) * threads * sizeof(float)));
+    cudaEvent_t e0, e1;
+    GX_CUDA(h, cudaEventCreate(&e0));
+    GX_CUDA(h, cudaEventCreate(&e1));
+    double best = 0.0;
+    for (int rep = 0; rep < 4; rep++) {             // first repetition warms up
+        GX_CUDA(h, cudaEventRecord(e0, h->stream));
+        gx_tex_peak_kernel<<<blocks, threads, 0, h->stream>>>(h->tex, h->ares[0], h->ares[1], h->ares[2], rounds, out);
+        GX_CUDA(h, cudaEventRecord(e1, h->stream));
+        GX_CUDA(h, cudaEventSynchronize(e1));
+        float ms = 0.f;
+        GX_CUDA(h, cudaEventElapsedTime(&ms, e0, e1));
+        const double g = double(blocks) * threads * rounds * 8.0 / (double(ms) * 1e-3) / 1e9;
+        if (rep > 0 && g > best) best = g;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    cudaFree(out);
+    *gsamples_per_s = best;
+    return GVDBX_OK;
+}
+
 // device-buffer helpers for the host mirror (gvdbx_host.cpp is plain C++)
 extern "C" int gvdbx_internal_alloc(gvdbx_t* h, uint64_t* ptr, size_t bytes)
 {

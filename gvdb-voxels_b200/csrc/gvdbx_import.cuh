@@ -155,6 +155,33 @@ __global__ void gx_sample_points_kernel(GxParams P, const float* __restrict__ xy
     out_lin[i] = s.tri(x, y, z);
 }
 
+// ------------------------------------------------------------------------------------------------ texture-unit peak
+// Roofline denominator of the filtered modes: how many fp32 trilinear samples per second the texture units deliver on THIS
+// GPU when nothing else is in the way — every thread marches a short segment through one brick of the imported atlas (so the
+// texels are L1-resident, like a ray marching a brick), eight independent fetches in flight, nothing but the fetches and one
+// add per sample.  Measured by gvdbx_measure_tex_peak, used by bench.py as `roofline.peak` for the TEX-bound deep mode.
+__global__ void __launch_bounds__(256) gx_tex_peak_kernel(cudaTextureObject_t tex, int ares_x, int ares_y, int ares_z, int rounds, float* __restrict__ out)
+{
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+    // one brick-sized region per warp, lanes a fraction of a voxel apart (an 8x4-pixel ray packet inside a brick)
+    const int warp = tid >> 5, lane = tid & 31;
+    const float bx = float((warp * 10) % max(ares_x - 10, 1)) + 1.0f, by = float(((warp / 7) * 10) % max(ares_y - 10, 1)) + 1.0f,
+                bz = float(((warp / 53) * 10) % max(ares_z - 10, 1)) + 1.0f;
+    float x = bx + 0.21f * float(lane & 7), y = by + 0.23f * float(lane >> 3), z = bz;
+    const float dx = 0.11f, dy = 0.07f, dz = 0.22f;
+    float acc = 0.f;
+    for (int r = 0; r < rounds; r++) {
+        float v[8];
+        #pragma unroll
+        for (int k = 0; k < 8; k++) v[k] = tex3D<float>(tex, x + dx * float(k), y + dy * float(k), z + dz * float(k));
+        #pragma unroll
+        for (int k = 0; k < 8; k++) acc += v[k];
+        x += 8.f * dx; y += 8.f * dy; z += 8.f * dz;
+        if (z > bz + 7.5f) { x = bx + 0.21f * float(lane & 7); y = by + 0.23f * float(lane >> 3); z = bz; }
+    }
+    out[tid] = acc;
+}
+
 // ------------------------------------------------------------------------------------------------ deep-mode transfer table
 // {rgb, exp(EXTINCT * alpha * DIRECTSTEP)} for every transfer-function entry: the expression of rayDeepBrick
 // (cuda_gvdb_raycast.cuh:515) evaluated once per entry and frame instead of once per sample (gx_deep_accumulate_pre).

@@ -267,6 +267,10 @@ int  gvdbx_get_counters(gvdbx_t* h, gvdbx_counters* out);
  * texture path and with the linear-load emulation; writes n floats each. */
 int  gvdbx_sample_points(gvdbx_t* h, int chan, uint64_t xyz_d, int n, uint64_t out_tex_d, uint64_t out_lin_d);
 
+/* Measurement aid: fp32 trilinear samples per second (in 1e9) the texture units of this GPU deliver on L1-resident bricks of the
+ * imported atlas with nothing else in the way — the roofline denominator of the TEX-bound deep mode.  Synchronises. */
+int  gvdbx_measure_tex_peak(gvdbx_t* h, double* gsamples_per_s);
+
 #ifdef __cplusplus
 }
 #endif
