@@ -388,6 +388,14 @@ def count_work(r, scns, shade, frame_d, w, h, mode):
     return tot, float(alg)
 
 
+def tex_peaks(r, p):
+    """texture-unit rate (fp32 trilinear Gsamples/s, fetch-only microbenchmark on L1-resident bricks) for lanes 0.2 voxel apart
+    (best case) and for this camera's ray spacing (voxels per pixel at the orbit centre)"""
+    import math
+    spacing = 2.0 * p.cam_dist * math.tan(math.radians(p.fov) / 2.0) / p.height
+    return {"coherent": r.measure_tex_peak(0.2), "at_ray_spacing": r.measure_tex_peak(spacing), "ray_spacing_voxels": spacing}
+
+
 def roofline_block(key, mode, kernel, ms_total, frames_total, n_gpus, sm_mhz, alg_ref, alg_prod, units_ref, units_prod, tex_peak):
     """Which unit binds depends on the mode (DRAM never does: it sits below 1 % of peak because neighbouring rays share bricks
     and 98-99 % of the sectors hit in L1):
@@ -411,8 +419,13 @@ def roofline_block(key, mode, kernel, ms_total, frames_total, n_gpus, sm_mhz, al
                      ipc_ncu=kc.get("ipc"), tex_pipe_pct_ncu=kc.get("tex_pipe_pct"), l1_hit_pct=kc.get("l1_hit_pct"), l2_hit_pct=kc.get("l2_hit_pct"),
                      counters_from=kc.get("source"))
         issue["frac"] = issue["achieved"] / peak_issue
-    tex = {"unit": "Gsamples/s", "peak": (tex_peak * n_gpus) if tex_peak else None, "achieved": units_prod["s_tri"] / t / 1e9 if units_prod else None,
-           "peak_source": "gvdbx_measure_tex_peak: fp32 trilinear fetches on L1-resident bricks of this atlas, 8 in flight per thread, measured in this run"}
+    tex = {"unit": "Gsamples/s", "peak": (tex_peak["at_ray_spacing"] * n_gpus) if tex_peak else None,
+           "achieved": units_prod["s_tri"] / t / 1e9 if units_prod else None,
+           "peak_coherent": (tex_peak["coherent"] * n_gpus) if tex_peak else None, "ray_spacing_voxels": tex_peak["ray_spacing_voxels"] if tex_peak else None,
+           "tex_pipe_busy_pct_ncu": kc.get("tex_pipe_pct") if kc else None,
+           "peak_source": "gvdbx_measure_tex_peak, measured in this run: fp32 trilinear fetches only (8 in flight per thread) on L1-resident bricks of "
+                          "this atlas with the 8x4 lanes of a warp as far apart as this camera's rays (voxels per pixel at the orbit centre); "
+                          "peak_coherent = the same with lanes 0.2 voxel apart"}
     tex["frac"] = (tex["achieved"] / tex["peak"]) if tex["peak"] and tex["achieved"] else None
     dram = (kc["dram_bytes"] * frames_total / t / 1e9) if kc and kc.get("dram_bytes") else None
     hbm = {"peak": hbm_peak * n_gpus, "unit": "GB/s", "peak_source": src,
@@ -477,7 +490,7 @@ def measure_single(torch, pkg, a, workload, mode, dev, local, steps, warmup, ful
     res.update(value=rays_step * steps / (ms_total * 1e-3) / 1e6, ms_per_frame=ms_total / steps / a.frames, latency_ms_1lane=lat["mean"],
                latency_1lane=lat, value_1lane=w * h * a.spp / (lat["mean"] * 1e-3) / 1e6)
     dev_resident_gb = (total0 - free0) / 1e9
-    tex_peak = r.measure_tex_peak() if full else None
+    tex_peak = tex_peaks(r, p) if full else None
     r.close()
     del frames_d
     torch.cuda.empty_cache()
@@ -593,7 +606,7 @@ def main():
     if rank == 0:
         units_ref, alg_ref = count_work(r, scns, shade, frame, w, h, 1)
         units_prod, alg_prod = count_work(r, scns, shade, frame, w, h, 2)
-    tex_peak = r.measure_tex_peak() if rank == 0 else None
+    tex_peak = tex_peaks(r, p) if rank == 0 else None
     r.set_spp(a.spp)
     r.lanes(a.lanes)
     launches = 0

@@ -86,7 +86,7 @@ def lib():
     L.gvdbx_sync.argtypes = [vp]
     L.gvdbx_get_counters.argtypes = [vp, C.POINTER(Counters)]
     L.gvdbx_sample_points.argtypes = [vp, i32, u64, i32, u64, u64]
-    L.gvdbx_measure_tex_peak.argtypes = [vp, C.POINTER(C.c_double)]
+    L.gvdbx_measure_tex_peak.argtypes = [vp, C.c_float, C.POINTER(C.c_double)]
     L.gvdbx_render_tiles_direct.argtypes = [vp, vp, i32, i32, u64, i32, i32, i32]
     L.gvdbx_kernel_params.argtypes = [vp, vp, i32, i32, u64, vp, C.c_size_t]
     L.gvdbx_update_apron.argtypes = [vp, i32, C.c_float]
@@ -390,10 +390,11 @@ class Renderer:
         self._ck(self._L.gvdbx_get_counters(self._h, C.byref(c)), "gvdbx_get_counters")
         return c.as_dict()
 
-    def measure_tex_peak(self):
-        """fp32 trilinear Gsamples/s of the texture units on L1-resident bricks of the imported atlas"""
+    def measure_tex_peak(self, lane_spacing=0.2):
+        """fp32 trilinear Gsamples/s of the texture units on L1-resident bricks of the imported atlas, the 8x4 lanes of a
+        warp `lane_spacing` voxels apart"""
         g = C.c_double()
-        self._ck(self._L.gvdbx_measure_tex_peak(self._h, C.byref(g)), "gvdbx_measure_tex_peak")
+        self._ck(self._L.gvdbx_measure_tex_peak(self._h, C.c_float(lane_spacing), C.byref(g)), "gvdbx_measure_tex_peak")
         return float(g.value)
 
     def sample_points(self, xyz_ptr, n, out_tex_ptr, out_lin_ptr, chan=0):

@@ -1083,9 +1083,9 @@ extern "C" int gvdbx_sample_points(gvdbx_t* h, int chan, uint64_t xyz_d, int n, 
 }
 
 // fp32 trilinear samples per second of this GPU's texture units on L1-resident bricks of the imported atlas (synchronises)
-extern "C" int gvdbx_measure_tex_peak(gvdbx_t* h, double* gsamples_per_s)
+extern "C" int gvdbx_measure_tex_peak(gvdbx_t* h, float lane_spacing, double* gsamples_per_s)
 {
-    if (!h || !gsamples_per_s) return GVDBX_E_ARG;
+    if (!h || !gsamples_per_s || !(lane_spacing >= 0.f) || lane_spacing > 8.f) return GVDBX_E_ARG;
     if (!h->have_atlas) return gx_fail(h, GVDBX_E_STATE, "no atlas imported");
     GxCtx ctx_(h);
     int sms = 148;
@@ -1099,7 +1099,7 @@ extern "C" int gvdbx_measure_tex_peak(gvdbx_t* h, double* gsamples_per_s)
     double best = 0.0;
     for (int rep = 0; rep < 4; rep++) {             // first repetition warms up
         GX_CUDA(h, cudaEventRecord(e0, h->stream));
-        gx_tex_peak_kernel<<<blocks, threads, 0, h->stream>>>(h->tex, h->ares[0], h->ares[1], h->ares[2], rounds, out);
+        gx_tex_peak_kernel<<<blocks, threads, 0, h->stream>>>(h->tex, h->ares[0], h->ares[1], h->ares[2], rounds, lane_spacing, out);
         GX_CUDA(h, cudaEventRecord(e1, h->stream));
         GX_CUDA(h, cudaEventSynchronize(e1));
         float ms = 0.f;

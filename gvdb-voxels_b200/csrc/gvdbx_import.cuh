@@ -160,14 +160,16 @@ __global__ void gx_sample_points_kernel(GxParams P, const float* __restrict__ xy
 // GPU when nothing else is in the way — every thread marches a short segment through one brick of the imported atlas (so the
 // texels are L1-resident, like a ray marching a brick), eight independent fetches in flight, nothing but the fetches and one
 // add per sample.  Measured by gvdbx_measure_tex_peak, used by bench.py as `roofline.peak` for the TEX-bound deep mode.
-__global__ void __launch_bounds__(256) gx_tex_peak_kernel(cudaTextureObject_t tex, int ares_x, int ares_y, int ares_z, int rounds, float* __restrict__ out)
+__global__ void __launch_bounds__(256) gx_tex_peak_kernel(cudaTextureObject_t tex, int ares_x, int ares_y, int ares_z, int rounds, float spacing,
+                                                          float* __restrict__ out)
 {
     const int tid = blockIdx.x * blockDim.x + threadIdx.x;
-    // one brick-sized region per warp, lanes a fraction of a voxel apart (an 8x4-pixel ray packet inside a brick)
+    // one brick-sized region per warp, lanes `spacing` voxels apart in x and y (an 8x4-pixel ray packet inside a brick: the
+    // unit's rate depends on how many distinct texel quads one warp request touches)
     const int warp = tid >> 5, lane = tid & 31;
     const float bx = float((warp * 10) % max(ares_x - 10, 1)) + 1.0f, by = float(((warp / 7) * 10) % max(ares_y - 10, 1)) + 1.0f,
                 bz = float(((warp / 53) * 10) % max(ares_z - 10, 1)) + 1.0f;
-    float x = bx + 0.21f * float(lane & 7), y = by + 0.23f * float(lane >> 3), z = bz;
+    float x = bx + spacing * float(lane & 7), y = by + 1.07f * spacing * float(lane >> 3), z = bz;
     const float dx = 0.11f, dy = 0.07f, dz = 0.22f;
     float acc = 0.f;
     for (int r = 0; r < rounds; r++) {
@@ -177,7 +179,7 @@ __global__ void __launch_bounds__(256) gx_tex_peak_kernel(cudaTextureObject_t te
         #pragma unroll
         for (int k = 0; k < 8; k++) acc += v[k];
         x += 8.f * dx; y += 8.f * dy; z += 8.f * dz;
-        if (z > bz + 7.5f) { x = bx + 0.21f * float(lane & 7); y = by + 0.23f * float(lane >> 3); z = bz; }
+        if (z > bz + 7.5f) { x = bx + spacing * float(lane & 7); y = by + 1.07f * spacing * float(lane >> 3); z = bz; }
     }
     out[tid] = acc;
 }

@@ -268,8 +268,11 @@ int  gvdbx_get_counters(gvdbx_t* h, gvdbx_counters* out);
 int  gvdbx_sample_points(gvdbx_t* h, int chan, uint64_t xyz_d, int n, uint64_t out_tex_d, uint64_t out_lin_d);
 
 /* Measurement aid: fp32 trilinear samples per second (in 1e9) the texture units of this GPU deliver on L1-resident bricks of the
- * imported atlas with nothing else in the way — the roofline denominator of the TEX-bound deep mode.  Synchronises. */
-int  gvdbx_measure_tex_peak(gvdbx_t* h, double* gsamples_per_s);
+ * imported atlas with nothing else in the way (fetches only, 8 in flight per thread) when the 8x4 lanes of a warp sample
+ * `lane_spacing` voxels apart — the unit's rate depends on how many distinct texel quads one warp request touches: ~0.2 = the
+ * best case, the voxels-per-pixel of a camera = what a ray packet of that camera can get.  Roofline denominator of the
+ * TEX-bound deep mode.  Synchronises. */
+int  gvdbx_measure_tex_peak(gvdbx_t* h, float lane_spacing, double* gsamples_per_s);
 
 #ifdef __cplusplus
 }
