@@ -45,7 +45,8 @@ class Counters(C.Structure):
 
 
 def lib_path():
-    return os.path.join(os.path.dirname(os.path.abspath(__file__)), "libgvdbx.so")
+    """in-tree libgvdbx.so; GVDBX_LIB points experiments (A/B builds of the kernels) at another build of the same ABI"""
+    return os.environ.get("GVDBX_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "libgvdbx.so")
 
 
 _LIB = None
