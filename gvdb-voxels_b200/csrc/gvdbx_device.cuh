@@ -661,6 +661,8 @@ __device__ __forceinline__ void gx_raycast_sm(const GxParams& P, S& smp, float3 
 // brick-queue form of the deep ray cast (gvdbx_trace.cuh): BATCH == 2
 template <class S>
 __device__ __forceinline__ void gx_raycast_deep_q(const GxParams& P, S& smp, float3 pos, float3 dir, GxHit& h, GxCount& cnt);
+template <int MODE, class S>
+__device__ __forceinline__ void gx_raycast_surface_q(const GxParams& P, S& smp, float3 pos, float3 dir, GxHit& h, GxCount& cnt);
 
 template <int MODE, int BATCH, class S>
 __device__ __forceinline__ void gx_raycast(const GxParams& P, S& smp, float3 pos, float3 dir, GxHit& h, GxCount& cnt,
@@ -672,6 +674,9 @@ __device__ __forceinline__ void gx_raycast(const GxParams& P, S& smp, float3 pos
     if constexpr (BATCH == 2 && MODE == GX_MODE_DEEP) {
         // depth-buffer compositing and per-sample colour take the one-brick-at-a-time path below
         if (P.dbuf == nullptr && !P.clr_tex) { gx_raycast_deep_q(P, smp, pos, dir, h, cnt); return; }
+    }
+    if constexpr (BATCH == 2 && (MODE == GX_MODE_TRILINEAR || MODE == GX_MODE_LEVELSET)) {
+        if (P.dbuf == nullptr) { gx_raycast_surface_q<MODE>(P, smp, pos, dir, h, cnt); return; }
     }
     GxStack st;
     int lev = P.top_lev;
@@ -872,9 +877,13 @@ template <int MODE, int SAMPLER, int FLAGS, bool UNI>
 #define GX_MINBLOCKS 4
 #endif
 #ifndef GX_QUEUE_MINBLOCKS
-#define GX_QUEUE_MINBLOCKS 3      // brick-queue kernels: 80 registers, no spills (measured 21.1 ms vs 23.6 ms at 64 registers, cfg4 deep 4K)
+#define GX_QUEUE_MINBLOCKS 3      // deep brick-queue kernels: 80 registers, no spills (measured 21.1 ms vs 23.6 ms at 64 registers, cfg4 deep 4K)
 #endif
-__global__ void __launch_bounds__(256, (FLAGS & GX_FLAG_QUEUE) ? GX_QUEUE_MINBLOCKS : GX_MINBLOCKS) gx_render_kernel(const __grid_constant__ GxParams P)
+#ifndef GX_SURFQ_MINBLOCKS
+#define GX_SURFQ_MINBLOCKS 4
+#endif
+__global__ void __launch_bounds__(256, !(FLAGS & GX_FLAG_QUEUE) ? GX_MINBLOCKS : ((MODE == GX_MODE_DEEP || MODE == GX_MODE_DEEPSHADOW) ? GX_QUEUE_MINBLOCKS : GX_SURFQ_MINBLOCKS))
+gx_render_kernel(const __grid_constant__ GxParams P)
 {
     int x, y;
     size_t opix;

@@ -6,11 +6,11 @@
 typedef void (*gx_kernel_t)(const GxParams);
 
 // AB = also build the two A/B traversal variants (reference-shaped loops, packet traversal): core modes only
-// the brick-queue variants (GX_FLAG_QUEUE) exist for the deep modes
+// the brick-queue variants (GX_FLAG_QUEUE) exist for the deep modes and for trilinear / level set
 template <int MODE, int SAMPLER, bool UNI, bool AB>
 static gx_kernel_t gx_pick_flags(int flags)
 {
-    if constexpr (MODE == GX_MODE_DEEP || MODE == GX_MODE_DEEPSHADOW) {
+    if constexpr (MODE == GX_MODE_DEEP || MODE == GX_MODE_DEEPSHADOW || MODE == GX_MODE_TRILINEAR || MODE == GX_MODE_LEVELSET) {
         switch (flags) {
         case GX_FLAG_QUEUE: return gx_render_kernel<MODE, SAMPLER, GX_FLAG_QUEUE, UNI>;
         case GX_FLAG_QUEUE | GX_FLAG_TILES: return gx_render_kernel<MODE, SAMPLER, GX_FLAG_QUEUE | GX_FLAG_TILES, UNI>;

@@ -259,7 +259,7 @@ __device__ __forceinline__ void gx2_brick_deep(const GxParams& P, S& smp, int no
 // consumed in order and the colour clamp is applied at every brick end like rayDeepBrick does.  What changes is only how
 // many DDA iterations run before the ray is found to be opaque (at most GX_QK - 1 bricks of look-ahead), never the image.
 #ifndef GX_QK
-#define GX_QK 8
+#define GX_QK 4              // measured on cfg4 deep 4K: 4 -> 20.7 ms, 8 -> 21.1 ms, 16 -> 21.7 ms (look-ahead waste, shared memory taken from L1)
 #endif
 #ifndef GX_Q_PREFETCH
 #define GX_Q_PREFETCH 0      // measured: prefetching the next round costs registers (spills at 64, 22.5 vs 21.1 ms at 80): off
@@ -433,6 +433,145 @@ __device__ __forceinline__ void gx_raycast_deep_q(const GxParams& P, S& smp, flo
                 if (clr.w <= acut) return;          // no later brick can change the colour
                 qi++;
                 fresh = true;
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ surface modes: brick queue
+// The same two-phase scheme for SHADE_TRILINEAR and SHADE_LEVELSET (primary and shadow rays): phase A queues the next bricks
+// whose value range can contain the surface, phase B marches them in one flat loop of four-sample rounds; the first sample
+// that passes the threshold test ends the ray exactly where raySurfaceTrilinearBrick / rayLevelSetBrick end it
+// (cuda_gvdb_raycast.cuh:281-300, :389-410): bricks are queued in ray order, each is entered with the reference's entry
+// parameter, samples are tested in order.  A hit in the first queued brick wastes the DDA steps that found the others —
+// bricks that can hold the surface are neighbours, so that is a step or two.
+template <int MODE, class S>
+__device__ __forceinline__ void gx_raycast_surface_q(const GxParams& P, S& smp, float3 pos, float3 dir, GxHit& h, GxCount& cnt)
+{
+    constexpr bool LS = (MODE == GX_MODE_LEVELSET);
+    GxStack stk;
+    int lev = P.top_lev;
+    cnt.rays++;
+    float3 tStart = gx_ray_box(pos, dir, P.bmin, P.bmax);
+    if (tStart.z == GX_NOHIT) return;
+    if (lev < 1 || lev >= GX_MAXLEV) return;
+    int4 np = gx_node_pos(P, lev, 0);
+    cnt.n_desc++;
+    tStart.x += P.epsilon;
+    stk.set(lev, 0, tStart.y - P.epsilon);
+    float      cur_tmax = tStart.y - P.epsilon;
+    gx_ctab_t  ctab = gx_table(P, lev, 0, gx_dim<S>(P, lev));
+    unsigned   res = unsigned(gx_res<S>(P, lev));
+    GxDDA dda;
+    dda.set_ray(pos, dir, tStart);
+    dda.prepare(make_float3(float(np.x), float(np.y), float(np.z)), gx_vdel<S>(P, lev));
+
+    const int nt = stk.nt;
+    int*   q_leaf = stk.col + 8 * nt;
+    float* q_tx = reinterpret_cast<float*>(stk.col + (8 + GX_QK) * nt);
+    const float st = P.steps.x, thr = P.thresh.x;       // `st`: the step GX_STEP_FMA advances by
+    const float res0 = float(gx_res<S>(P, 0));
+    int  iter = 0, node = 0;
+    bool walking = true, moved = false;
+
+    while (walking) {
+        // ---- phase A (see gx_raycast_deep_q)
+        int qn = 0;
+        while (qn < GX_QK) {
+            if (!(iter < GX_MAX_ITER && lev > 0 && lev <= P.top_lev
+                  && unsigned(dda.p.x) <= res && unsigned(dda.p.y) <= res && unsigned(dda.p.z) <= res)) { walking = false; break; }
+            dda.next();
+            const int dm = gx_dim<S>(P, lev);
+            const int b = (((int(dda.p.z) << dm) + int(dda.p.y)) << dm) + int(dda.p.x);
+            int c = -1;
+            if (unsigned(dda.p.x | dda.p.y | dda.p.z) < res) c = gx_child(ctab, b);
+            cnt.n_dda++;
+            if (c != -1) {
+                if (lev == 1) {
+                    cnt.n_desc++;
+                    bool keep = true;       // value-range culling: no sample of this brick can pass the threshold test
+                    if (P.range != nullptr) keep = LS ? (__ldg(&P.range[c].lo) < thr) : (__ldg(&P.range[c].hi) >= thr);
+                    if (keep) { q_leaf[qn * nt] = c; q_tx[qn * nt] = dda.t.x + P.epsilon; qn++; }
+                    dda.step();
+                } else {
+                    lev--;
+                    cnt.n_desc++;
+                    dda.t.x += P.epsilon;
+                    cur_tmax = dda.t.y - P.epsilon;
+                    stk.set(lev, c, cur_tmax);
+                    node = c; moved = true;
+                }
+            } else {
+                dda.step();
+            }
+            while (dda.t.x > cur_tmax && lev <= P.top_lev) {
+                lev++;
+                if (lev <= P.top_lev) {
+                    node = stk.node(lev);
+                    cur_tmax = stk.tmax(lev);
+                    cnt.n_desc++;
+                    moved = true;
+                }
+            }
+            if (moved && lev <= P.top_lev) {
+                moved = false;
+                ctab = gx_table(P, lev, node, gx_dim<S>(P, lev));
+                res = unsigned(gx_res<S>(P, lev));
+                np = gx_node_pos(P, lev, node);
+                dda.prepare(make_float3(float(np.x), float(np.y), float(np.z)), gx_vdel<S>(P, lev));
+            }
+            iter++;
+        }
+        if (qn == 0) break;
+
+        // ---- phase B: flat loop of four-sample rounds over the queued bricks
+        int    qi = 0, it = 0;
+        bool   fresh = true;
+        float3 p = make_float3(0, 0, 0), o = make_float3(0, 0, 0);
+        float  tx = 0.f;
+        while (qi < qn) {
+            if (fresh) {
+                const GxLeafRec L = gx_leaf(P, q_leaf[qi * nt]);
+                smp.enter(L);
+                tx = q_tx[qi * nt];
+                if (!LS) tx = st * ceilf(tx / st);            // trilinear: start snapped to the step grid (:286); level set: not (:394)
+                o = make_float3(float(L.vx), float(L.vy), float(L.vz));
+                p = gx_poszero(pos + tx * dir - make_float3(float(L.px), float(L.py), float(L.pz)));
+                it = 0;
+                fresh = false;
+            }
+            float3 p1, p2, p3;
+            GX_STEP_FMA(p1, p); GX_STEP_FMA(p2, p1); GX_STEP_FMA(p3, p2);
+            bool k0, k1, k2, k3;
+            if (LS) { k0 = GX_INB_LE(p, res0); k1 = GX_INB_LE(p1, res0); k2 = GX_INB_LE(p2, res0); k3 = GX_INB_LE(p3, res0); }
+            else    { k0 = GX_INB(p, res0); k1 = GX_INB(p1, res0); k2 = GX_INB(p2, res0); k3 = GX_INB(p3, res0); }
+            const float v0 = smp.tri(p.x + o.x, p.y + o.y, p.z + o.z);
+            const float v1 = smp.tri(p1.x + o.x, p1.y + o.y, p1.z + o.z);
+            const float v2 = smp.tri(p2.x + o.x, p2.y + o.y, p2.z + o.z);
+            const float v3 = smp.tri(p3.x + o.x, p3.y + o.y, p3.z + o.z);
+            const bool t0 = LS ? v0 < thr : v0 >= thr, t1 = LS ? v1 < thr : v1 >= thr, t2 = LS ? v2 < thr : v2 >= thr, t3 = LS ? v3 < thr : v3 >= thr;
+            int k = -1;                      // index of the sample that ends this brick; hit = it passed the threshold test
+            bool hit = false;
+            if (!k0) k = 0; else if (t0) { k = 0; hit = true; }
+            else if (!k1) k = 1; else if (t1) { k = 1; hit = true; p = p1; }
+            else if (!k2) k = 2; else if (t2) { k = 2; hit = true; p = p2; }
+            else if (!k3) k = 3; else if (t3) { k = 3; hit = true; p = p3; }
+            if (hit) {
+                cnt.s_tri += k + (LS ? 2 : 1);
+                const int leaf = q_leaf[qi * nt];
+                const GxLeafRec L = gx_leaf(P, leaf);
+                h.hit = p + make_float3(float(L.px), float(L.py), float(L.pz));
+                h.norm = gx_gradient(smp, p + o, cnt, LS);
+                h.t = tx; h.leaf = leaf; h.vox = gx_i3(gx_floor(h.hit));
+                h.cpos = p + o;
+                return;
+            }
+            if (k >= 0) { cnt.s_tri += k; qi++; fresh = true; }
+            else {
+                cnt.s_tri += 4;
+                it += 4;
+                GX_STEP_FMA(p, p3);
+                if (it >= GX_MAX_ITER) { qi++; fresh = true; }
             }
         }
     }

@@ -64,7 +64,7 @@ def test_texture_path_bit_exact_vs_reference(scenes, torch_cuda, preset, mode):
     img, dbg = _render(torch_cuda, r, g[f"scn_{mode}"].tobytes(), MODES[mode], w, h, 0, debug=True)
     assert np.array_equal(img, g[f"rgba_{mode}"]), f"{(img != g[f'rgba_{mode}']).any(axis=2).sum()} pixels differ"
     # production variant (brick range culling on) and the A/B traversals: same bytes
-    for trav in (0, 1, 2, 4):
+    for trav in (0, 1, 2, 3, 4):
         r.set_option(5, trav)
         plain = _render(torch_cuda, r, g[f"scn_{mode}"].tobytes(), MODES[mode], w, h, 0)
         assert np.array_equal(plain, g[f"rgba_{mode}"]), (trav, int((plain != g[f"rgba_{mode}"]).any(axis=2).sum()))
@@ -355,7 +355,7 @@ def test_full_size_cfg2_levelset_properties(scenes, torch_cuda, ora, pkg):
     lin = _render(torch, r, scn, 6, w, h, 1)
     ok, over1, ps = tolerance_ok(lin, tex)
     assert ok, (over1, ps)
-    for trav in (1, 2):
+    for trav in (1, 2, 3):
         r.set_option(5, trav)
         assert np.array_equal(_render(torch, r, scn, 6, w, h, 0), tex), trav
     r.set_option(5, 0)
