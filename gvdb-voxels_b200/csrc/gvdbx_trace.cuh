@@ -259,7 +259,8 @@ __device__ __forceinline__ void gx2_brick_deep(const GxParams& P, S& smp, int no
 // consumed in order and the colour clamp is applied at every brick end like rayDeepBrick does.  What changes is only how
 // many DDA iterations run before the ray is found to be opaque (at most GX_QK - 1 bricks of look-ahead), never the image.
 #ifndef GX_QK
-#define GX_QK 4              // measured on cfg4 deep 4K: 4 -> 20.7 ms, 8 -> 21.1 ms, 16 -> 21.7 ms (look-ahead waste, shared memory taken from L1)
+#define GX_QK 2              // measured on cfg4 deep 4K: 1 -> 20.9 ms, 2 -> 20.2, 3 / 4 -> 20.6, 8 -> 21.1, 16 -> 21.7 (look-ahead waste and shared
+                             // memory taken from L1 grow with the depth; most of the gain is the flat loop itself)
 #endif
 #ifndef GX_Q_PREFETCH
 #define GX_Q_PREFETCH 0      // measured: prefetching the next round costs registers (spills at 64, 22.5 vs 21.1 ms at 80): off

@@ -64,9 +64,9 @@ extern "C" {
 #define GVDBX_OPT_STREAM_MEMOPS 9 /* 1 = gvdbx_stream_wait uses cuStreamWaitValue32 (front-end wait, unbounded) instead of the bounded polling kernel */
 #define GVDBX_OPT_VOXEL_MASK 10 /* 1 (default) = SHADE_VOXEL tests per-brick occupancy bits (value > THRESH, rebuilt when THRESH or the atlas
                                    changes) instead of one point fetch per voxel step; 0 = fetch (A/B) */
-#define GVDBX_OPT_TRAVERSAL 5   /* 0 = default (four-samples-per-round brick marchers; deep modes: brick-queue traversal), 1 = reference-shaped loops,
-                                   one sample at a time (A/B), 2 = vote-converged two-phase packet traversal (A/B), 3 = same as 0,
-                                   4 = four-sample rounds WITHOUT the brick queue (A/B for the deep modes) */
+#define GVDBX_OPT_TRAVERSAL 5   /* 0 = default (four-samples-per-round brick marchers; deep modes and SHADE_TRILINEAR: brick-queue traversal),
+                                   1 = reference-shaped loops, one sample at a time (A/B), 2 = vote-converged two-phase packet traversal (A/B),
+                                   3 = brick queue also for SHADE_LEVELSET, 4 = four-sample rounds WITHOUT the brick queue (A/B) */
 
 typedef struct gvdbx_ctx gvdbx_t;
 
