@@ -213,6 +213,13 @@ class PeerFrameRing:
         return torch.as_tensor(CudaBuffer(self.frame_ptr_of(q), (self.h, self.w, 4)), device=device)
 
 
+def bands_for_rank(height, band_rows, rank, world):
+    """[(first row, row count)] of the full-width bands rank `rank` renders and copies in the host frame ring (band b of the
+    frame belongs to rank b % world) — the partition gvdbx_hostring_submit / gvdbx_render_bands use"""
+    nb = (height + band_rows - 1) // band_rows
+    return [(b * band_rows, min(band_rows, height - b * band_rows)) for b in range(rank, nb, world)]
+
+
 class HostFrameRing:
     """Frames of a multi-GPU render delivered to the HOST (C entry points gvdbx_hostring_*): a ring of row-major frames in a
     POSIX shared-memory segment page-locked by every process; each rank renders full-width bands of `band_rows` rows and copies

@@ -143,3 +143,30 @@ def test_replicate_volume_two_ranks():
     for p in procs:
         p.join(timeout=60)
     assert all(ok for _, ok in res), res
+
+
+def test_band_partition_covers_every_row_once(pkg):
+    from gvdb_voxels_b200 import multigpu as mg
+    for h, rows, world in ((2160, 32, 8), (1080, 32, 8), (768, 16, 3), (270, 32, 4), (54, 8, 7)):
+        seen = np.zeros(h, np.int32)
+        for rank in range(world):
+            for y0, n in mg.bands_for_rank(h, rows, rank, world):
+                assert n > 0 and y0 % rows == 0 and (y0 // rows) % world == rank
+                seen[y0:y0 + n] += 1
+        assert (seen == 1).all()
+
+
+def test_shim_header_compiles_against_reference_headers(tmp_path):
+    """include/gvdbx_shim.h (the Level-A drop-in a GVDB maintainer adds) is valid C++ against the reference's own gvdb.h —
+    checked wherever the reference sources are present (the GPU box runs it for real: ref_harness_x)."""
+    import os
+    import subprocess
+    from common import ROOT
+    ref = "/root/reference/source/gvdb_library"
+    stub = os.path.join(ROOT, "oracle", "_ref", "obj", "stubinc")
+    if not os.path.isdir(ref) or not os.path.isdir(stub):
+        pytest.skip("reference sources / GL stub headers not present")
+    src = tmp_path / "shim.cpp"
+    src.write_text('#include "gvdbx_shim.h"\nint main() { VolumeGVDBX v; (void)v; return 0; }\n')
+    subprocess.run(["g++", "-std=c++14", "-fsyntax-only", "-w", "-DBUILD_OPENGL", "-DGLEW_STATIC", "-DGLEW_NO_GLU", "-I", os.path.join(ROOT, "include"),
+                    "-I", os.path.join(ref, "src"), "-I", os.path.join(ref, "glew", "include"), "-I", stub, "-I", "/usr/local/cuda/include", str(src)], check=True)
