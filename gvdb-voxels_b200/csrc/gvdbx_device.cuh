@@ -344,6 +344,14 @@ struct GxDDA {
         tSide = ((gx_floor(pFlt) - pFlt + 0.5f) * fstep() + 0.5) * tDel + t.x;
         p = gx_i3(gx_floor(pFlt));
     }
+    // the same with `inv` holding |1 / dir| (the walker, gvdbx_walk.cuh): |vdel * inv| == vdel * |inv| bit for bit, vdel > 0
+    __device__ __forceinline__ void prepare_abs(float3 vmin, float3 vdel)
+    {
+        tDel = vdel * inv;
+        float3 pFlt = (pos + t.x * dir - vmin) / vdel;
+        tSide = ((gx_floor(pFlt) - pFlt + 0.5f) * fstep() + 0.5) * tDel + t.x;
+        p = gx_i3(gx_floor(pFlt));
+    }
     // cuda_gvdb_dda.cuh:70-75 (brick: child size 1, no "+ t.x")
     __device__ __forceinline__ void prepare_leaf(float3 vmin)
     {
@@ -624,7 +632,7 @@ struct GxStackReg {            // register-resident variant (used by the A/B pac
 // Default: the (node, tMax) pair of every level 1..4 lives in dynamic shared memory, [level - 1][thread] — one STS / LDS
 // per access, conflict-free, no select chains and eight registers fewer than the register-resident form (the reference:
 // two dynamically indexed local-memory arrays).  GX_STACK_BYTES_PER_THREAD of dynamic shared memory per thread.
-#define GX_STACK_BYTES_PER_THREAD 32
+#define GX_STACK_BYTES_PER_THREAD 36     // 32 used by GxStack; the walker (gvdbx_walk.cuh) keeps one row of 9 words per thread
 struct GxStack {
 #ifdef GX_REF_LAYOUT    // launched by the reference's own RenderKernel / Render (no dynamic shared memory): room for 16 x 16 CTAs
     static __device__ __forceinline__ int* base() { __shared__ int gx_stack_static[8 * 256]; return gx_stack_static; }
@@ -640,6 +648,8 @@ struct GxStack {
     __device__ __forceinline__ int   node(int lev) const { return col[(lev - 1) * nt]; }
     __device__ __forceinline__ float tmax(int lev) const { return __int_as_float(col[(lev + 3) * nt]); }
 };
+
+#include "gvdbx_walk.cuh"
 
 // four-samples-per-round brick marchers (gvdbx_trace.cuh)
 template <class S> __device__ __forceinline__ void gx2_brick_trilinear(const GxParams&, S&, int, float3, float3, float3, GxHit&, GxCount&);
@@ -664,6 +674,48 @@ __device__ __forceinline__ void gx_raycast_deep_q(const GxParams& P, S& smp, flo
 template <int MODE, class S>
 __device__ __forceinline__ void gx_raycast_surface_q(const GxParams& P, S& smp, float3 pos, float3 dir, GxHit& h, GxCount& cnt);
 
+// rayCast on the lean walker (gvdbx_walk.cuh): the reference's nesting — the brick function runs inside the iteration that
+// found the brick — with the walker's bookkeeping.  GX_LEAN_WALK = 2: the walker runs to the next brick first, the brick
+// function is called behind the loop (lanes of a warp visit their bricks together).
+#ifndef GX_LEAN_WALK
+#define GX_LEAN_WALK 1
+#endif
+template <int MODE, int BATCH, class S>
+__device__ __forceinline__ bool gx_lean_brick(const GxParams& P, S& smp, int c, float3 t, float3 pos, float3 dir, GxHit& h, GxCount& cnt)
+{
+    if constexpr (MODE == GX_MODE_VOXEL)          gx_brick_voxel(P, smp, c, t, pos, dir, h, cnt);
+    else if constexpr (MODE == GX_MODE_TRILINEAR) gx2_brick_trilinear(P, smp, c, t, pos, dir, h, cnt);
+    else if constexpr (MODE == GX_MODE_LEVELSET)  gx2_brick_levelset(P, smp, c, t, pos, dir, h, cnt);
+    else if constexpr (MODE == GX_MODE_DEEP)      { if (!P.clr_tex) gx2_brick_deep(P, smp, c, t, pos, dir, h, cnt, INFINITY);   // per-sample colour: literal marcher
+                                                    else            gx_brick_deep(P, smp, c, t, pos, dir, h, cnt, INFINITY); }
+    else if constexpr (MODE == GX_MODE_TRICUBIC)  gx_brick_tricubic(P, smp, c, t, pos, dir, h, cnt);
+    else if constexpr (MODE == GX_MODE_EMPTYSKIP) h.hit = pos + t.x * dir;
+    else                                          gx_brick_shadow(P, smp, c, t, pos, dir, h, cnt);
+    // rayCast's tests behind the brick call (:584-590); true = the ray is finished
+    if (h.clr.w <= 0) { h.clr.w = 0; return true; }
+    if (h.hit.z != GX_NOHIT) return true;
+    if (MODE == GX_MODE_DEEP && h.clr.w <= P.cutoff.y) return true;
+    return false;
+}
+template <int MODE, int BATCH, class S>
+__device__ __forceinline__ void gx_raycast_lean(const GxParams& P, S& smp, float3 pos, float3 dir, GxHit& h, GxCount& cnt)
+{
+    typedef GxWalk<S, GX_WALK_WORDS> Walk;
+    Walk w;
+    if (!w.start(P, pos, dir, cnt)) return;
+#if GX_LEAN_WALK == 2
+    while (w.next_brick(P, cnt))
+        if (gx_lean_brick<MODE, BATCH>(P, smp, w.leaf, make_float3(w.t_enter, w.t_exit, 0.f), pos, dir, h, cnt)) return;
+#else
+    for (;;) {
+        const int s = w.advance(P, cnt);
+        if (s == Walk::END) return;
+        if (s == Walk::BRICK && gx_lean_brick<MODE, BATCH>(P, smp, w.leaf, make_float3(w.t_enter, w.t_exit, 0.f), pos, dir, h, cnt)) return;
+        w.settle(P, cnt, s == Walk::DESCENDED);
+    }
+#endif
+}
+
 template <int MODE, int BATCH, class S>
 __device__ __forceinline__ void gx_raycast(const GxParams& P, S& smp, float3 pos, float3 dir, GxHit& h, GxCount& cnt,
                                            int px, int py)
@@ -678,6 +730,12 @@ __device__ __forceinline__ void gx_raycast(const GxParams& P, S& smp, float3 pos
     if constexpr (BATCH == 2 && (MODE == GX_MODE_TRILINEAR || MODE == GX_MODE_LEVELSET)) {
         if (P.dbuf == nullptr) { gx_raycast_surface_q<MODE>(P, smp, pos, dir, h, cnt); return; }
     }
+#ifndef GX_REF_LAYOUT
+    // (every BATCH == 1 ray cast of a kernel takes the same route: the walker and GxStack lay the shared-memory stack out differently)
+    if constexpr (GX_LEAN_WALK != 0 && BATCH == 1) {
+        if (P.dbuf == nullptr) { gx_raycast_lean<MODE, BATCH>(P, smp, pos, dir, h, cnt); return; }
+    }
+#endif
     GxStack st;
     int lev = P.top_lev;
     cnt.rays++;

@@ -25,12 +25,13 @@ def main():
     pkg = bench.load_pkg()
     size = tuple(int(x) for x in a.size.split("x")) if a.size else None
     p, vol = bench.build_workload(a.workload, size)
-    shade = bench.MODES[a.mode] if a.mode else p.shade
+    shade, dshadow = bench.MODE[a.mode] if a.mode else (p.shade, 0)
     scns, table = bench.frame_scninfos(pkg, p, shade, 8)
     r = pkg.Renderer(0)
     r.import_topology_host(vol["vdbinfo"], vol["pool0"], vol["pool1"])
     r.import_atlas_host(vol["atlas"])
     r.set_transfer(table)
+    r.set_deep_shadow(dshadow)
     w, h = p.width, p.height
     out = torch.zeros((h, w, 4), dtype=torch.uint8, device="cuda")
 
