@@ -266,31 +266,18 @@ __device__ __forceinline__ void gx2_brick_deep(const GxParams& P, S& smp, int no
 #define GX_Q_PREFETCH 0      // measured: prefetching the next round costs registers (spills at 64, 22.5 vs 21.1 ms at 80): off
 #endif
 #define GX_QUEUE_BYTES_PER_THREAD (8 * GX_QK)
+#define GX_WALK_WORDS_Q (GX_WALK_WORDS + 2 * GX_QK)        // stack + queue, odd stride (9 + even)
 
 template <class S>
 __device__ __forceinline__ void gx_raycast_deep_q(const GxParams& P, S& smp, float3 pos, float3 dir, GxHit& h, GxCount& cnt)
 {
-    GxStack st;
-    int lev = P.top_lev;
-    cnt.rays++;
-    float3 tStart = gx_ray_box(pos, dir, P.bmin, P.bmax);
-    if (tStart.z == GX_NOHIT) return;
-    if (lev < 1 || lev >= GX_MAXLEV) return;
-    int4 np = gx_node_pos(P, lev, 0);
-    cnt.n_desc++;
-    tStart.x += P.epsilon;
-    st.set(lev, 0, tStart.y - P.epsilon);
-    float      cur_tmax = tStart.y - P.epsilon;
-    gx_ctab_t  ctab = gx_table(P, lev, 0, gx_dim<S>(P, lev));
-    unsigned   res = unsigned(gx_res<S>(P, lev));
-    GxDDA dda;
-    dda.set_ray(pos, dir, tStart);
-    dda.prepare(make_float3(float(np.x), float(np.y), float(np.z)), gx_vdel<S>(P, lev));
-
-    // per-thread queue behind the traversal stack: [entry][thread], conflict-free
-    const int nt = st.nt;
-    int*   q_leaf = st.col + 8 * nt;
-    float* q_tx = reinterpret_cast<float*>(st.col + (8 + GX_QK) * nt);
+    typedef GxWalk<S, GX_WALK_WORDS_Q> Walk;
+    Walk w;
+    if (!w.start(P, pos, dir, cnt)) return;
+    // per-thread queue behind the traversal stack in the thread's shared-memory row
+    int*   q_leaf = w.row + 8;
+    float* q_tx = reinterpret_cast<float*>(w.row + 8 + GX_QK);
+    constexpr int nt = 1;                // queue entries of a thread are adjacent words
 
     const float stp = P.steps.x;
     const float3 wpt = make_float3(__fmul_rn(stp, dir.x), __fmul_rn(stp, dir.y), __fmul_rn(stp, dir.z));
@@ -299,62 +286,20 @@ __device__ __forceinline__ void gx_raycast_deep_q(const GxParams& P, S& smp, flo
     const float inv_range = gx_rcp_approx(P.thresh.z - P.thresh.y);
     const float4* lut = GX_DEEP_LUT ? P.transfer_deep : P.transfer;
     float4& clr = h.clr;
-    int  iter = 0, node = 0;
     bool walking = true;                 // the hierarchical DDA has not left the volume / spent its iteration budget yet
-    bool moved = false;                  // the level changed in this iteration: one Prepare pending
 
     while (walking) {
-        // ---- phase A: queue the next bricks (cuda_gvdb_raycast.cuh:567-610 without the brick call; one Prepare per
-        // iteration at a single site, see gx_raycast)
+        // ---- phase A: queue the next bricks (the walker = cuda_gvdb_raycast.cuh:567-610 without the brick call)
         int qn = 0;
-        while (qn < GX_QK) {
-            if (!(iter < GX_MAX_ITER && lev > 0 && lev <= P.top_lev
-                  && unsigned(dda.p.x) <= res && unsigned(dda.p.y) <= res && unsigned(dda.p.z) <= res)) { walking = false; break; }
-            dda.next();
-            const int dm = gx_dim<S>(P, lev);
-            const int b = (((int(dda.p.z) << dm) + int(dda.p.y)) << dm) + int(dda.p.x);
-            int c = -1;
-            if (unsigned(dda.p.x | dda.p.y | dda.p.z) < res) c = gx_child(ctab, b);
-            cnt.n_dda++;
-            if (c != -1) {
-                if (lev == 1) {
-                    // brick entry of rayDeepBrick that depends on the entry parameter only (:490, first-sample bookkeeping)
-                    const float te = dda.t.x + P.epsilon;
-                    const float ts = stp * ceilf(te / stp);
-                    if (h.hit.x == 0) h.hit.x = ts;
-                    cnt.n_desc++;
-                    // a brick without a sample >= MINVAL only re-applies an idempotent clamp: not queued
-                    if (P.range == nullptr || __ldg(&P.range[c].hi) >= minval) { q_leaf[qn * nt] = c; q_tx[qn * nt] = ts; qn++; }
-                    dda.step();
-                } else {
-                    lev--;
-                    cnt.n_desc++;
-                    dda.t.x += P.epsilon;
-                    cur_tmax = dda.t.y - P.epsilon;
-                    st.set(lev, c, cur_tmax);
-                    node = c; moved = true;
-                }
-            } else {
-                dda.step();
-            }
-            while (dda.t.x > cur_tmax && lev <= P.top_lev) {
-                lev++;
-                if (lev <= P.top_lev) {
-                    node = st.node(lev);
-                    cur_tmax = st.tmax(lev);
-                    cnt.n_desc++;
-                    moved = true;
-                }
-            }
-            if (moved && lev <= P.top_lev) {
-                moved = false;
-                ctab = gx_table(P, lev, node, gx_dim<S>(P, lev));
-                res = unsigned(gx_res<S>(P, lev));
-                np = gx_node_pos(P, lev, node);
-                dda.prepare(make_float3(float(np.x), float(np.y), float(np.z)), gx_vdel<S>(P, lev));
-            }
-            iter++;
-        }
+        walking = w.walk(P, cnt, [&](int leaf, float t_enter, float) {
+            // brick entry of rayDeepBrick that depends on the entry parameter only (:490, first-sample bookkeeping)
+            const float ts = stp * ceilf(t_enter / stp);
+            if (h.hit.x == 0) h.hit.x = ts;
+            cnt.n_desc++;
+            // a brick without a sample >= MINVAL only re-applies an idempotent clamp: not queued
+            if (P.range == nullptr || __ldg(&P.range[leaf].hi) >= minval) { q_leaf[qn * nt] = leaf; q_tx[qn * nt] = ts; qn++; }
+            return qn >= GX_QK;
+        });
         if (qn == 0) break;
 
         // ---- phase B: one flat loop of four-sample rounds over the queued bricks.  (GX_Q_PREFETCH = 1, an A/B build option:
@@ -450,79 +395,26 @@ template <int MODE, class S>
 __device__ __forceinline__ void gx_raycast_surface_q(const GxParams& P, S& smp, float3 pos, float3 dir, GxHit& h, GxCount& cnt)
 {
     constexpr bool LS = (MODE == GX_MODE_LEVELSET);
-    GxStack stk;
-    int lev = P.top_lev;
-    cnt.rays++;
-    float3 tStart = gx_ray_box(pos, dir, P.bmin, P.bmax);
-    if (tStart.z == GX_NOHIT) return;
-    if (lev < 1 || lev >= GX_MAXLEV) return;
-    int4 np = gx_node_pos(P, lev, 0);
-    cnt.n_desc++;
-    tStart.x += P.epsilon;
-    stk.set(lev, 0, tStart.y - P.epsilon);
-    float      cur_tmax = tStart.y - P.epsilon;
-    gx_ctab_t  ctab = gx_table(P, lev, 0, gx_dim<S>(P, lev));
-    unsigned   res = unsigned(gx_res<S>(P, lev));
-    GxDDA dda;
-    dda.set_ray(pos, dir, tStart);
-    dda.prepare(make_float3(float(np.x), float(np.y), float(np.z)), gx_vdel<S>(P, lev));
-
-    const int nt = stk.nt;
-    int*   q_leaf = stk.col + 8 * nt;
-    float* q_tx = reinterpret_cast<float*>(stk.col + (8 + GX_QK) * nt);
+    typedef GxWalk<S, GX_WALK_WORDS_Q> Walk;
+    Walk w;
+    if (!w.start(P, pos, dir, cnt)) return;
+    int*   q_leaf = w.row + 8;
+    float* q_tx = reinterpret_cast<float*>(w.row + 8 + GX_QK);
+    constexpr int nt = 1;
     const float st = P.steps.x, thr = P.thresh.x;       // `st`: the step GX_STEP_FMA advances by
     const float res0 = float(gx_res<S>(P, 0));
-    int  iter = 0, node = 0;
-    bool walking = true, moved = false;
+    bool walking = true;
 
     while (walking) {
         // ---- phase A (see gx_raycast_deep_q)
         int qn = 0;
-        while (qn < GX_QK) {
-            if (!(iter < GX_MAX_ITER && lev > 0 && lev <= P.top_lev
-                  && unsigned(dda.p.x) <= res && unsigned(dda.p.y) <= res && unsigned(dda.p.z) <= res)) { walking = false; break; }
-            dda.next();
-            const int dm = gx_dim<S>(P, lev);
-            const int b = (((int(dda.p.z) << dm) + int(dda.p.y)) << dm) + int(dda.p.x);
-            int c = -1;
-            if (unsigned(dda.p.x | dda.p.y | dda.p.z) < res) c = gx_child(ctab, b);
-            cnt.n_dda++;
-            if (c != -1) {
-                if (lev == 1) {
-                    cnt.n_desc++;
-                    bool keep = true;       // value-range culling: no sample of this brick can pass the threshold test
-                    if (P.range != nullptr) keep = LS ? (__ldg(&P.range[c].lo) < thr) : (__ldg(&P.range[c].hi) >= thr);
-                    if (keep) { q_leaf[qn * nt] = c; q_tx[qn * nt] = dda.t.x + P.epsilon; qn++; }
-                    dda.step();
-                } else {
-                    lev--;
-                    cnt.n_desc++;
-                    dda.t.x += P.epsilon;
-                    cur_tmax = dda.t.y - P.epsilon;
-                    stk.set(lev, c, cur_tmax);
-                    node = c; moved = true;
-                }
-            } else {
-                dda.step();
-            }
-            while (dda.t.x > cur_tmax && lev <= P.top_lev) {
-                lev++;
-                if (lev <= P.top_lev) {
-                    node = stk.node(lev);
-                    cur_tmax = stk.tmax(lev);
-                    cnt.n_desc++;
-                    moved = true;
-                }
-            }
-            if (moved && lev <= P.top_lev) {
-                moved = false;
-                ctab = gx_table(P, lev, node, gx_dim<S>(P, lev));
-                res = unsigned(gx_res<S>(P, lev));
-                np = gx_node_pos(P, lev, node);
-                dda.prepare(make_float3(float(np.x), float(np.y), float(np.z)), gx_vdel<S>(P, lev));
-            }
-            iter++;
-        }
+        walking = w.walk(P, cnt, [&](int leaf, float t_enter, float) {
+            cnt.n_desc++;
+            bool keep = true;       // value-range culling: no sample of this brick can pass the threshold test
+            if (P.range != nullptr) keep = LS ? (__ldg(&P.range[leaf].lo) < thr) : (__ldg(&P.range[leaf].hi) >= thr);
+            if (keep) { q_leaf[qn * nt] = leaf; q_tx[qn * nt] = t_enter; qn++; }
+            return qn >= GX_QK;
+        });
         if (qn == 0) break;
 
         // ---- phase B: flat loop of four-sample rounds over the queued bricks

@@ -162,15 +162,19 @@ struct GxWalk {
         }
     }
 
-    // resumable form: walk to the next brick (leaf, t_enter, t_exit); the iteration that found it is completed before
-    // returning (its tail never depends on what the brick function does, only on whether the caller goes on)
-    __device__ __forceinline__ bool next_brick(const GxParams& P, GxCount& cnt)
+    // The reference loop with the brick visit as a functor, called INSIDE the iteration that found the brick (the reference's
+    // nesting): on_brick(leaf, t_enter, t_exit) returns true to stop.  The iteration is completed (settle) before returning,
+    // so the walk can be resumed by calling walk() again.  Returns false when the traversal is over.
+    template <class F>
+    __device__ __forceinline__ bool walk(const GxParams& P, GxCount& cnt, F&& on_brick)
     {
         for (;;) {
             const int s = advance(P, cnt);
             if (s == END) return false;
+            bool stop = false;
+            if (s == BRICK) stop = on_brick(leaf, t_enter, t_exit);
             settle(P, cnt, s == DESCENDED);
-            if (s == BRICK) return true;
+            if (stop) return true;
         }
     }
 };
