@@ -241,7 +241,7 @@ static int gx_import_topology(gvdbx_t* h, const void* vdbinfo, const uint64_t* l
         const int cells = 1 << (3 * v.dim[l]);
         const size_t total = size_t(v.nodecnt[l]) * cells;
         GX_CUDA(h, cudaMalloc(&h->d_child[l], total * sizeof(int)));
-        GX_CUDA(h, cudaMalloc(&h->d_npos[l], size_t(v.nodecnt[l]) * sizeof(int4)));
+        GX_CUDA(h, cudaMalloc(&h->d_npos[l], size_t(v.nodecnt[l]) * sizeof(float4)));
         const int threads = 256;
         const unsigned blocks = (unsigned)((total + threads - 1) / threads);
         const unsigned long long lists = (listcnt && listcnt[l]) ? listcnt[l] : (unsigned long long)v.nodecnt[l];
@@ -560,8 +560,8 @@ static inline float3 f3(const GxF3& a) { return make_float3(a.x, a.y, a.z); }
 // GVDBX_OPT_TRAVERSAL = 3 asks for it; 4 switches the queue off everywhere (A/B)
 static int gx_queue_flag(const gvdbx_t* h, int mode)
 {
-    if (mode == GX_MODE_DEEP || mode == GX_MODE_DEEPSHADOW || mode == GX_MODE_TRILINEAR) return (h->literal == 0 || h->literal == 3) ? GX_FLAG_QUEUE : 0;
-    if (mode == GX_MODE_LEVELSET) return h->literal == 3 ? GX_FLAG_QUEUE : 0;
+    if (mode == GX_MODE_DEEP || mode == GX_MODE_DEEPSHADOW || mode == GX_MODE_TRILINEAR || mode == GX_MODE_LEVELSET)
+        return (h->literal == 0 || h->literal == 3) ? GX_FLAG_QUEUE : 0;
     return 0;
 }
 // dynamic shared memory: the traversal stack, plus the brick queue of the queue variants

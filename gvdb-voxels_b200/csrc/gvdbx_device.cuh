@@ -14,7 +14,7 @@
 //     -> constant-bank reads, instead of the reference's VDBInfo struct in global memory (42 LDG sites per kernel);
 //   * the tree is traversed through compact tables built at import time: per level one int32 child table indexed by
 //     NODE index (4 B per cell, one dependent load per DDA step instead of node->mChildList->clist[b] = 3 loads of
-//     64 B + 8 B), one int4 position record per internal node and one 32-B record per leaf;
+//     64 B + 8 B), one float4 position record per internal node and one 32-B record per leaf;
 //   * the brick atlas is available both as the caller's 3-D array through a texture object (bit-exact hardware
 //     trilinear) and re-laid out brick-major (4 KB per 10^3 brick, contiguous) for plain vectorisable loads with a
 //     software emulation of the texture unit's 1.8 fixed-point filtering;
@@ -90,7 +90,7 @@ struct GxParams {
     float3   bmin, bmax;
     // ---- compact traversal tables
     const int*       child[GX_MAXLEV];   // child[lev][node * cells(lev) + b] = index at lev-1, or -1
-    const int4*      npos[GX_MAXLEV];    // npos[lev][node] = {mPos, 0}            (lev >= 1)
+    const float4*    npos[GX_MAXLEV];    // npos[lev][node] = {float(mPos), 0}: every user converts the corner to float first (lev >= 1)
     const GxLeafRec* leaf;               // leaf[node]                              (lev == 0)
     // ---- the reference's own pools (GX_REF_LAYOUT builds only): VDBInfo::nodelist / nodewid / childlist / childwid
     const char* ref_nodes[GX_MAXLEV];
@@ -267,6 +267,7 @@ template <class S> __device__ __forceinline__ float3 gx_vdel(const GxParams& P, 
 // module-level drop-in, csrc/gvdbx_module.cu): the reference's own pools as VDBInfo points at them — 64-byte node
 // records (mPos@4, mValue@16, mChildList@48) and per-node lists of 64-bit child entries (index = entry >> 16, all ones =
 // no child), kernels/cuda_gvdb_nodes.cuh:24-35, :115-129, :184-196.
+typedef float4 gx_npos_t;          // index-space min corner of a node, converted to float once at import
 #ifdef GX_REF_LAYOUT
 typedef const unsigned long long* gx_ctab_t;
 __device__ __forceinline__ const GxNode* gx_ref_node(const GxParams& P, int lev, int node)
@@ -280,10 +281,10 @@ __device__ __forceinline__ gx_ctab_t gx_table(const GxParams& P, int lev, int no
     return reinterpret_cast<gx_ctab_t>(P.ref_clist[lev] + size_t(listid >> 16) * P.ref_childwid[lev]);
 }
 __device__ __forceinline__ int gx_child(gx_ctab_t t, int b) { return t ? int(__ldg(t + b) >> 16) : -1; }
-__device__ __forceinline__ int4 gx_node_pos(const GxParams& P, int lev, int node)
+__device__ __forceinline__ gx_npos_t gx_node_pos(const GxParams& P, int lev, int node)
 {
     const GxNode* n = gx_ref_node(P, lev, node);
-    return make_int4(n->mPos.x, n->mPos.y, n->mPos.z, 0);
+    return make_float4(float(n->mPos.x), float(n->mPos.y), float(n->mPos.z), 0.f);
 }
 __device__ __forceinline__ GxLeafRec gx_leaf(const GxParams& P, int node)
 {
@@ -297,7 +298,7 @@ __device__ __forceinline__ GxLeafRec gx_leaf(const GxParams& P, int node)
 typedef const int* gx_ctab_t;
 __device__ __forceinline__ gx_ctab_t gx_table(const GxParams& P, int lev, int node, int dim) { return P.child[lev] + (size_t(node) << (3 * dim)); }
 __device__ __forceinline__ int gx_child(gx_ctab_t t, int b) { return __ldg(t + b); }
-__device__ __forceinline__ int4 gx_node_pos(const GxParams& P, int lev, int node) { return __ldg(&P.npos[lev][node]); }
+__device__ __forceinline__ gx_npos_t gx_node_pos(const GxParams& P, int lev, int node) { return __ldg(&P.npos[lev][node]); }
 __device__ __forceinline__ GxLeafRec gx_leaf(const GxParams& P, int node) { return P.leaf[node]; }
 #endif
 
@@ -738,7 +739,7 @@ __device__ __forceinline__ void gx_raycast(const GxParams& P, S& smp, float3 pos
     float3 tStart = gx_ray_box(pos, dir, P.bmin, P.bmax);
     if (tStart.z == GX_NOHIT) return;
     if (lev < 1 || lev >= GX_MAXLEV) return;        // single-brick volume: the reference loop never runs either
-    int4 np = gx_node_pos(P, lev, 0);
+    gx_npos_t np = gx_node_pos(P, lev, 0);
     cnt.n_desc++;
     float3 vmin = make_float3(float(np.x), float(np.y), float(np.z));
 
@@ -936,7 +937,10 @@ template <int MODE, int SAMPLER, int FLAGS, bool UNI>
 #ifndef GX_SURFQ_MINBLOCKS
 #define GX_SURFQ_MINBLOCKS 4
 #endif
-__global__ void __launch_bounds__(256, !(FLAGS & GX_FLAG_QUEUE) ? GX_MINBLOCKS : ((MODE == GX_MODE_DEEP || MODE == GX_MODE_DEEPSHADOW) ? GX_QUEUE_MINBLOCKS : GX_SURFQ_MINBLOCKS))
+#ifndef GX_MAXTHREADS
+#define GX_MAXTHREADS 256
+#endif
+__global__ void __launch_bounds__(GX_MAXTHREADS, !(FLAGS & GX_FLAG_QUEUE) ? GX_MINBLOCKS : ((MODE == GX_MODE_DEEP || MODE == GX_MODE_DEEPSHADOW) ? GX_QUEUE_MINBLOCKS : GX_SURFQ_MINBLOCKS))
 gx_render_kernel(const __grid_constant__ GxParams P)
 {
     int x, y;

@@ -14,7 +14,7 @@
 
 // ------------------------------------------------------------------------------------------------ point query
 // Top-down descent to the leaf that contains index-space point `pos`; returns the leaf index or -1.
-// One int4 position record + one 4-B child-table entry per level instead of the reference's node record (64 B) + child
+// One float4 position record + one 4-B child-table entry per level instead of the reference's node record (64 B) + child
 // list pointer chase.  top_lev == 0 (single brick): the reference returns leaf 0 without any bounds test; so do we.
 template <class S>
 __device__ __forceinline__ int gx_node_at_point(const GxParams& P, float3 pos, GxCount& cnt)
@@ -23,7 +23,7 @@ __device__ __forceinline__ int gx_node_at_point(const GxParams& P, float3 pos, G
     if (lev < 0 || lev >= GX_MAXLEV) return -1;
     int n = 0;
     if (lev == 0) return 0;
-    int4 np = gx_node_pos(P, lev, 0);
+    gx_npos_t np = gx_node_pos(P, lev, 0);
     cnt.n_desc++;
     float3 vmin = make_float3(float(np.x), float(np.y), float(np.z));
     while (lev > 0) {

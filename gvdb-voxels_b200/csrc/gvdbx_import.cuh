@@ -17,7 +17,7 @@ __global__ void gx_clear_import_bits(int* err) { atomicAnd(err, ~(GX_IMPORT_E_CH
 //   gvdb_volume_gvdb.cpp:3015-3023); node->mChildList = Elem(1, lev, ndx) or ID_UNDEFL.
 __global__ void gx_build_child_table(const char* __restrict__ nodelist, int nodewid, int nodecnt,
                                      const char* __restrict__ childlist, int childwid, int cells, unsigned long long listcnt, int childcnt,
-                                     int* __restrict__ child_out, int4* __restrict__ npos_out, int* __restrict__ err)
+                                     int* __restrict__ child_out, float4* __restrict__ npos_out, int* __restrict__ err)
 {
     size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
     size_t total = size_t(nodecnt) * cells;
@@ -36,7 +36,7 @@ __global__ void gx_build_child_table(const char* __restrict__ nodelist, int node
         }
     }
     child_out[i] = c;
-    if (b == 0) npos_out[n] = make_int4(node->mPos.x, node->mPos.y, node->mPos.z, 0);
+    if (b == 0) npos_out[n] = make_float4(float(node->mPos.x), float(node->mPos.y), float(node->mPos.z), 0.f);
 }
 
 // leaf records; a leaf without a brick (mValue.x < 0) keeps vx < 0 and is never sampled

@@ -57,7 +57,7 @@ struct gvdbx_ctx {
     bool       have_topo = false, uniform3 = false;
     GxVDBInfo  vdb;
     int*       d_child[GX_MAXLEV] = {};
-    int4*      d_npos[GX_MAXLEV] = {};
+    float4*    d_npos[GX_MAXLEV] = {};
     GxLeafRec* d_leaf = nullptr;
     // atlas
     bool                have_atlas = false;

@@ -611,7 +611,7 @@ __device__ __forceinline__ void gx_raycast_sm(const GxParams& P, S& smp, float3 
     float3 tStart = gx_ray_box(pos, dir, P.bmin, P.bmax);
     if (tStart.z == GX_NOHIT) return;
     if (lev < 1 || lev >= GX_MAXLEV) return;
-    int4 np = gx_node_pos(P, lev, 0);
+    gx_npos_t np = gx_node_pos(P, lev, 0);
     cnt.n_desc++;
     float3 vmin = make_float3(float(np.x), float(np.y), float(np.z));
     tStart.x += P.epsilon;
@@ -633,7 +633,7 @@ __device__ __forceinline__ void gx_raycast_sm(const GxParams& P, S& smp, float3 
                 cur_tmax = st.tmax(lev);
                 ctab = gx_table(P, lev, n, gx_dim<S>(P, lev));
                 res = unsigned(gx_res<S>(P, lev));
-                const int4 q = gx_node_pos(P, lev, n);
+                const gx_npos_t q = gx_node_pos(P, lev, n);
                 cnt.n_desc++;
                 dda.prepare(make_float3(float(q.x), float(q.y), float(q.z)), gx_vdel<S>(P, lev));
             }
@@ -717,7 +717,7 @@ __device__ __forceinline__ void gx2_start(const GxParams& P, GxTrav& T, float3 p
     float3 tStart = gx_ray_box(pos, dir, P.bmin, P.bmax);
     if (tStart.z == GX_NOHIT) return;
     if (T.lev < 1 || T.lev >= GX_MAXLEV) return;
-    const int4 np = gx_node_pos(P, T.lev, 0);
+    const gx_npos_t np = gx_node_pos(P, T.lev, 0);
     cnt.n_desc++;
     const float3 vmin = make_float3(float(np.x), float(np.y), float(np.z));
     tStart.x += P.epsilon;
@@ -735,7 +735,7 @@ __device__ __forceinline__ void gx2_ascend(const GxParams& P, GxTrav& T, GxCount
     while (T.dda.t.x > T.st.tmax(T.lev) && T.lev <= P.top_lev) {
         T.lev++;
         if (T.lev <= P.top_lev) {
-            const int4 np = gx_node_pos(P, T.lev, T.st.node(T.lev));
+            const gx_npos_t np = gx_node_pos(P, T.lev, T.st.node(T.lev));
             cnt.n_desc++;
             T.dda.prepare(make_float3(float(np.x), float(np.y), float(np.z)), gx_vdel<S>(P, T.lev));
         }
@@ -764,7 +764,7 @@ __device__ __forceinline__ int gx2_dda_iteration(const GxParams& P, GxTrav& T, G
         d.t.x += P.epsilon;
         if (lev == 1) return c;
         T.lev = lev - 1;
-        const int4 np = gx_node_pos(P, lev - 1, c);
+        const gx_npos_t np = gx_node_pos(P, lev - 1, c);
         cnt.n_desc++;
         T.st.set(lev - 1, c, d.t.y - P.epsilon);
         d.prepare(make_float3(float(np.x), float(np.y), float(np.z)), gx_vdel<S>(P, lev - 1));

@@ -55,7 +55,7 @@ struct GxWalk {
     {
         ctab = gx_table(P, lev, node, gx_dim<S>(P, lev));
         res_ = unsigned(gx_res<S>(P, lev));
-        const int4 np = gx_node_pos(P, lev, node);
+        const gx_npos_t np = gx_node_pos(P, lev, node);
         d.prepare_abs(make_float3(float(np.x), float(np.y), float(np.z)), gx_vdel<S>(P, lev));
     }
 
