@@ -115,9 +115,9 @@ extern "C" int gvdbx_set_option(gvdbx_t* h, int option, int value)
     case GVDBX_OPT_TRAVERSAL: if (value < 0 || value > 4) return gx_fail(h, GVDBX_E_ARG, "traversal must be 0..4"); h->literal = value; break;
     default: return gx_fail(h, GVDBX_E_ARG, "unknown option");
     }
-    if (h->block_w * h->block_h > 256 || (h->block_w * h->block_h) % 32 != 0) {
+    if (h->block_w * h->block_h > GX_MAXTHREADS || (h->block_w * h->block_h) % 32 != 0) {
         const bool pending = (option == GVDBX_OPT_BLOCK_W);     // width is set first, height second: only judge the pair
-        if (!pending) { h->block_w = 8; h->block_h = 8; return gx_fail(h, GVDBX_E_ARG, "CTA tile must be a multiple of 32 and at most 256 threads"); }
+        if (!pending) { h->block_w = 8; h->block_h = 8; return gx_fail(h, GVDBX_E_ARG, "CTA tile must be a multiple of 32 and at most 128 threads"); }
     }
     return GVDBX_OK;
 }

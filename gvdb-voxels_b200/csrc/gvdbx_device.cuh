@@ -927,18 +927,21 @@ __device__ __forceinline__ float4 gx_shade_pixel(const GxParams& P, S& smp, int 
 
 #define GX_FLAG_SPP     32     // P.spp sub-pixel samples per pixel, averaged in float before packing
 
+// Launch bounds.  CTAs are at most GX_MAXTHREADS = 128 threads (default 8x8 = two 8x4-pixel warps); the register budget follows
+// from the number of such CTAs per SM: 8 -> 64 registers (surface modes, SHADE_VOXEL: issue-bound, occupancy pays),
+// 7 -> 72 registers (deep brick-queue kernels: no spills at 72; measured cfg4 deep 4K 23.1 ms at 64, 19.7 at 72, 20.1 at 80).
 template <int MODE, int SAMPLER, int FLAGS, bool UNI>
+#ifndef GX_MAXTHREADS
+#define GX_MAXTHREADS 128
+#endif
 #ifndef GX_MINBLOCKS
-#define GX_MINBLOCKS 4
+#define GX_MINBLOCKS 8
 #endif
 #ifndef GX_QUEUE_MINBLOCKS
-#define GX_QUEUE_MINBLOCKS 3      // deep brick-queue kernels: 80 registers, no spills (measured 21.1 ms vs 23.6 ms at 64 registers, cfg4 deep 4K)
+#define GX_QUEUE_MINBLOCKS 7
 #endif
 #ifndef GX_SURFQ_MINBLOCKS
-#define GX_SURFQ_MINBLOCKS 4
-#endif
-#ifndef GX_MAXTHREADS
-#define GX_MAXTHREADS 256
+#define GX_SURFQ_MINBLOCKS 8
 #endif
 __global__ void __launch_bounds__(GX_MAXTHREADS, !(FLAGS & GX_FLAG_QUEUE) ? GX_MINBLOCKS : ((MODE == GX_MODE_DEEP || MODE == GX_MODE_DEEPSHADOW) ? GX_QUEUE_MINBLOCKS : GX_SURFQ_MINBLOCKS))
 gx_render_kernel(const __grid_constant__ GxParams P)
