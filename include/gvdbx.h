@@ -164,7 +164,7 @@ int  gvdbx_assemble_tiles(gvdbx_t* h, uint64_t gathered_d, uint64_t frame_d, int
  * gvdb-voxels_b200/csrc/gvdbx_plugin.cuh take the frame's parameter block (GxParams, by value, __grid_constant__) instead
  * of the reference's (VDBInfo*, chan, outBuf).  This call fills it for `scninfo` (shade_mode selects the per-frame tables
  * that are prepared: occupancy bits for SHADE_VOXEL, derived transfer table for SHADE_VOLUME); params_bytes must equal
- * sizeof(GxParams) of the headers the kernel was built with.  Launch with 32 bytes of dynamic shared memory per thread. */
+ * sizeof(GxParams) of the headers the kernel was built with.  Launch with GVDBX_KERNEL_SMEM(threads) = 36 bytes of dynamic shared memory per thread (the traversal stack). */
 int  gvdbx_kernel_params(gvdbx_t* h, const void* scninfo, int shade_mode, int chan, uint64_t outbuf_d, void* params_out,
                          size_t params_bytes);
 
