@@ -491,13 +491,19 @@ def measure_single(torch, pkg, a, workload, mode, dev, local, steps, warmup, ful
                latency_1lane=lat, value_1lane=w * h * a.spp / (lat["mean"] * 1e-3) / 1e6)
     dev_resident_gb = (total0 - free0) / 1e9
     tex_peak = tex_peaks(r, p) if full else None
+    sampler_ab = None
+    if full:      # the four ways of reading a brick, fetch + filter only, at this camera's ray spacing (csrc/gvdbx_microbench.cuh)
+        sampler_ab = {k: round(v, 2) for k, v in r.measure_sampler_ab(tex_peak["ray_spacing_voxels"]).items()}
+        sampler_ab.update(unit="Gsamples/s", what="fetch + filter only on the imported atlas at this camera's ray spacing: texture unit on the caller's array | "
+                          "brick-major copy, 8 scalar loads | x-pair layout, 4 loads of 8 bytes | brick staged into shared memory by TMA (cp.async.bulk + mbarrier), "
+                          "8 shared-memory loads; the three linear variants run the software model of the unit's filter (~45 instructions per sample)")
     r.close()
     del frames_d
     torch.cuda.empty_cache()
     strict = time_e2e(torch, pkg, p, vol, local, a, shade, dshadow, a.frames, max(2, steps // 2), 0)
     res["e2e_strict"] = strict
     extra = {"ms_total": ms_total, "launches": launches, "p": p, "vol": vol, "scns": scns, "shade": shade, "dshadow": dshadow,
-             "clocks": clk, "tex_peak": tex_peak, "units_ref": units_ref, "units_prod": units_prod, "alg_ref": alg_ref * a.spp, "alg_prod": alg_prod * a.spp, "device_gb_after_import": dev_resident_gb}
+             "clocks": clk, "tex_peak": tex_peak, "sampler_ab": sampler_ab, "units_ref": units_ref, "units_prod": units_prod, "alg_ref": alg_ref * a.spp, "alg_prod": alg_prod * a.spp, "device_gb_after_import": dev_resident_gb}
     return res, extra
 
 
@@ -841,6 +847,8 @@ def main_single(torch, pkg, a, dev, local):
            "e2e": e2e, "e2e_strict": res["e2e_strict"], "gpu_launches": x["launches"], "roofline": roofline, "clocks": clk_all,
            "import_s": res["import_s"], "scene_gen_s": res["scene_gen_s"]}
     out.update(res["parity"])
+    if x.get("sampler_ab"):
+        out["sampler_ab"] = x["sampler_ab"]
     if cpu:
         out["cpu_baseline"] = cpu
     if configs is not None:

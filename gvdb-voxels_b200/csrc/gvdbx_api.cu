@@ -5,6 +5,7 @@
 // caller's current context; everything is stream-ordered on the stream given to gvdbx_create.
 #include "gvdbx_internal.h"
 #include "gvdbx_import.cuh"
+#include "gvdbx_microbench.cuh"
 
 
 extern "C" int gvdbx_create(gvdbx_t** out, int cuda_device, void* cuda_stream)
@@ -1114,6 +1115,53 @@ extern "C" int gvdbx_measure_tex_peak(gvdbx_t* h, float lane_spacing, double* gs
     cudaEventDestroy(e0); cudaEventDestroy(e1);
     cudaFree(out);
     *gsamples_per_s = best;
+    return GVDBX_OK;
+}
+
+// The four ways of reading a brick (csrc/gvdbx_microbench.cuh), fetch + filter only, on the imported atlas: Gsamples/s of
+// [0] the texture unit, [1] brick-major copy + scalar loads, [2] x-pair layout + 8-byte loads, [3] TMA-staged shared memory.
+// Builds the brick-major copy if it does not exist yet (synchronises).
+extern "C" int gvdbx_measure_sampler_ab(gvdbx_t* h, float lane_spacing, double* gsamples_per_s4)
+{
+    if (!h || !gsamples_per_s4 || !(lane_spacing >= 0.f) || lane_spacing > 8.f) return GVDBX_E_ARG;
+    if (!h->have_atlas || !h->have_topo) return gx_fail(h, GVDBX_E_STATE, "needs topology and atlas");
+    if (h->brick_dim != GX_BRICK_DIM) return gx_fail(h, GVDBX_E_UNSUPPORTED, "the sampler A/B microbenchmark is written for 8^3 bricks");
+    int rc = gvdbx_measure_tex_peak(h, lane_spacing, &gsamples_per_s4[0]);
+    if (rc) return rc;
+    GxCtx ctx_(h);
+    rc = gx_ensure_bricks(h);
+    if (rc) return rc;
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
+    const int nb = h->vdb.nodecnt[0] < 4096 ? h->vdb.nodecnt[0] : 4096;
+    const int blocks = sms * 8, threads = 128, visits = 64;
+    float* out = nullptr; float2* pairs = nullptr;
+    GX_CUDA(h, cudaMalloc(&out, size_t(blocks) * threads * sizeof(float)));
+    GX_CUDA(h, cudaMalloc(&pairs, size_t(nb) * GX_BRICK_STRIDE * sizeof(float2)));
+    gx_build_pairs<<<(nb * 1000 + 255) / 256, 256, 0, h->stream>>>(h->d_bricks, pairs, nb);
+    const size_t smem3 = size_t(threads / 32) * 2 * GX_BRICK_STRIDE * sizeof(float) + size_t(threads / 32) * 2 * sizeof(unsigned long long);
+    cudaEvent_t e0, e1;
+    GX_CUDA(h, cudaEventCreate(&e0));
+    GX_CUDA(h, cudaEventCreate(&e1));
+    for (int variant = 1; variant <= 3; variant++) {
+        double best = 0.0;
+        for (int rep = 0; rep < 4; rep++) {             // first repetition warms up
+            GX_CUDA(h, cudaEventRecord(e0, h->stream));
+            if (variant == 1)      gx_linear_peak_kernel<1><<<blocks, threads, 0, h->stream>>>(h->d_bricks, pairs, nb, visits, lane_spacing, out);
+            else if (variant == 2) gx_linear_peak_kernel<2><<<blocks, threads, 0, h->stream>>>(h->d_bricks, pairs, nb, visits, lane_spacing, out);
+            else                   gx_linear_peak_kernel<3><<<blocks, threads, smem3, h->stream>>>(h->d_bricks, pairs, nb, visits, lane_spacing, out);
+            GX_CUDA(h, cudaEventRecord(e1, h->stream));
+            GX_CUDA(h, cudaEventSynchronize(e1));
+            GX_CUDA(h, cudaGetLastError());
+            float ms = 0.f;
+            GX_CUDA(h, cudaEventElapsedTime(&ms, e0, e1));
+            const double g = double(blocks) * threads * visits * GX_MB_SAMPLES / (double(ms) * 1e-3) / 1e9;
+            if (rep > 0 && g > best) best = g;
+        }
+        gsamples_per_s4[variant] = best;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    cudaFree(out); cudaFree(pairs);
     return GVDBX_OK;
 }
 

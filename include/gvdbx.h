@@ -273,6 +273,11 @@ int  gvdbx_sample_points(gvdbx_t* h, int chan, uint64_t xyz_d, int n, uint64_t o
  * best case, the voxels-per-pixel of a camera = what a ray packet of that camera can get.  Roofline denominator of the
  * TEX-bound deep mode.  Synchronises. */
 int  gvdbx_measure_tex_peak(gvdbx_t* h, float lane_spacing, double* gsamples_per_s);
+/* Fetch + filter microbenchmarks of the four ways of reading a brick on the imported atlas (csrc/gvdbx_microbench.cuh), Gsamples/s:
+ * [0] texture unit on the caller's array, [1] brick-major copy + scalar read-only loads, [2] x-pair layout + 8-byte loads,
+ * [3] brick-major blocks staged into shared memory by TMA (cp.async.bulk + mbarrier, two stages per warp).  [1]-[3] run the
+ * software model of the unit's filter.  The numbers behind the texture-versus-linear-load decision. */
+int  gvdbx_measure_sampler_ab(gvdbx_t* h, float lane_spacing, double* gsamples_per_s4);
 
 #ifdef __cplusplus
 }

@@ -1028,3 +1028,13 @@ def test_full_size_cfg5_bit_exact_vs_live_reference(ora, pkg, torch_cuda, tmp_pa
     r.close()
     os.makedirs(os.path.join(refcmp.ROOT, "gpurun_out"), exist_ok=True)
     json.dump(out, open(os.path.join(refcmp.ROOT, "gpurun_out", "cfg5_full_parity.json"), "w"), indent=1)
+
+
+def test_sampler_ab_microbench_runs_and_ranks_the_texture_unit_first(scenes):
+    """the four ways of reading a brick (csrc/gvdbx_microbench.cuh: texture unit, brick-major scalar loads, x-pair 8-byte loads,
+    TMA-staged shared memory): every variant runs, and the decision DESIGN.md records — texture sampler by default — holds"""
+    _, _, r = scenes("cfg1_small")
+    ab = r.measure_sampler_ab(0.5)
+    assert set(ab) == {"tex", "linear_ldg", "linear_pairs_ldg64", "tma_staged_smem"}
+    assert all(v > 1.0 for v in ab.values()), ab
+    assert ab["tex"] > max(ab["linear_ldg"], ab["linear_pairs_ldg64"], ab["tma_staged_smem"]), ab
