@@ -369,6 +369,35 @@ struct GxDDA {
         mz = (tSide.z < tSide.x) & (tSide.z <= tSide.y);
         t.y = mx ? tSide.x : (my ? tSide.y : tSide.z);
     }
+    // Next (:78-83) + Step (:86-90) in one predicated block — (sx, sy, sz) = isign3(dir) as integers; t.y = the selected side,
+    // tSide += float(mask) * tDel (a 0 mask still multiplies: 0 * inf = NaN on an axis-parallel ray exactly like the reference),
+    // p += mask * pStep.  The caller moves t.y into t.x.  6 FSETP, 5 FSEL, 3 FFMA, 3 predicated IADD.
+    __device__ __forceinline__ void next_step(int sx, int sy, int sz)
+    {
+        asm("{\n\t"
+        ".reg .pred mx, my, mz;\n\t"
+        ".reg .f32 fm;\n\t"
+        "setp.lt.ftz.f32 mx, %1, %2;\n\t"
+        "setp.le.and.ftz.f32 mx, %1, %3, mx;\n\t"
+        "setp.lt.ftz.f32 my, %2, %3;\n\t"
+        "setp.le.and.ftz.f32 my, %2, %1, my;\n\t"
+        "setp.lt.ftz.f32 mz, %3, %1;\n\t"
+        "setp.le.and.ftz.f32 mz, %3, %2, mz;\n\t"
+        "selp.f32 %0, %2, %3, my;\n\t"
+        "selp.f32 %0, %1, %0, mx;\n\t"
+        "selp.f32 fm, 0f3F800000, 0f00000000, mx;\n\t"
+        "fma.rn.ftz.f32 %1, fm, %7, %1;\n\t"
+        "selp.f32 fm, 0f3F800000, 0f00000000, my;\n\t"
+        "fma.rn.ftz.f32 %2, fm, %8, %2;\n\t"
+        "selp.f32 fm, 0f3F800000, 0f00000000, mz;\n\t"
+        "fma.rn.ftz.f32 %3, fm, %9, %3;\n\t"
+        "@mx add.s32 %4, %4, %10;\n\t"
+        "@my add.s32 %5, %5, %11;\n\t"
+        "@mz add.s32 %6, %6, %12;\n\t"
+        "}"
+        : "=&f"(t.y), "+f"(tSide.x), "+f"(tSide.y), "+f"(tSide.z), "+r"(p.x), "+r"(p.y), "+r"(p.z)
+        : "f"(tDel.x), "f"(tDel.y), "f"(tDel.z), "r"(sx), "r"(sy), "r"(sz));
+    }
     // cuda_gvdb_dda.cuh:86-90: tSide += float(mask) * tDel (a 0 mask still multiplies: 0 * inf = NaN on an axis-parallel
     // ray, exactly like the reference), p += mask * pStep.  The float mask comes from a select, not an int -> float
     // conversion (quarter-rate pipe).
@@ -452,6 +481,8 @@ __device__ __forceinline__ void gx_brick_voxel(const GxParams& P, S& smp, int no
     GxDDA dda;
     dda.set_ray(pos, dir, t);
     dda.prepare_leaf(vmin);
+    // isign3(dir) from the sign bit: differs from (dir > 0 ? 1 : -1) only for a zero component, whose axis never steps
+    const int sx = (__float_as_int(dir.x) >> 31) | 1, sy = (__float_as_int(dir.y) >> 31) | 1, sz = (__float_as_int(dir.z) >> 31) | 1;
 
     // Occupancy bits instead of one dependent point fetch per voxel step: `value > THRESH` was evaluated once per voxel
     // when THRESH was set (gx_build_voxel_mask, on the exact texel values a centre fetch returns), so the per-step test is
@@ -500,8 +531,7 @@ __device__ __forceinline__ void gx_brick_voxel(const GxParams& P, S& smp, int no
             h.cpos = gx_f3(dda.p) + o;
             return;
         }
-        dda.next();
-        dda.step();
+        dda.next_step(sx, sy, sz);
     }
 }
 

@@ -105,29 +105,7 @@ struct GxWalk {
         // Next (cuda_gvdb_dda.cuh:78-83) + Step (:86-90) in one predicated block: mask = (x < y & x <= z, y < z & y <= x,
         // z < x & z <= y); t.y = the selected side; tSide += float(mask) * tDel — a 0 mask still multiplies, 0 * inf = NaN on
         // an axis-parallel ray exactly like the reference; p += mask * pStep
-        asm("{\n\t"
-            ".reg .pred mx, my, mz;\n\t"
-            ".reg .f32 fm;\n\t"
-            "setp.lt.ftz.f32 mx, %1, %2;\n\t"
-            "setp.le.and.ftz.f32 mx, %1, %3, mx;\n\t"
-            "setp.lt.ftz.f32 my, %2, %3;\n\t"
-            "setp.le.and.ftz.f32 my, %2, %1, my;\n\t"
-            "setp.lt.ftz.f32 mz, %3, %1;\n\t"
-            "setp.le.and.ftz.f32 mz, %3, %2, mz;\n\t"
-            "selp.f32 %0, %2, %3, my;\n\t"
-            "selp.f32 %0, %1, %0, mx;\n\t"
-            "selp.f32 fm, 0f3F800000, 0f00000000, mx;\n\t"
-            "fma.rn.ftz.f32 %1, fm, %7, %1;\n\t"
-            "selp.f32 fm, 0f3F800000, 0f00000000, my;\n\t"
-            "fma.rn.ftz.f32 %2, fm, %8, %2;\n\t"
-            "selp.f32 fm, 0f3F800000, 0f00000000, mz;\n\t"
-            "fma.rn.ftz.f32 %3, fm, %9, %3;\n\t"
-            "@mx add.s32 %4, %4, %10;\n\t"
-            "@my add.s32 %5, %5, %11;\n\t"
-            "@mz add.s32 %6, %6, %12;\n\t"
-            "}"
-            : "=&f"(d.t.y), "+f"(d.tSide.x), "+f"(d.tSide.y), "+f"(d.tSide.z), "+r"(d.p.x), "+r"(d.p.y), "+r"(d.p.z)
-            : "f"(d.tDel.x), "f"(d.tDel.y), "f"(d.tDel.z), "r"(sx), "r"(sy), "r"(sz));
+        d.next_step(sx, sy, sz);
         if (c == -1) { d.t.x = d.t.y; return CONT; }
         if (lev == 1) {
             leaf = c; t_enter = d.t.x + P.epsilon; t_exit = d.t.y;
