@@ -720,9 +720,9 @@ def main():
     dist.barrier()      # the other ranks must not start the e2e frames (which reuse the ring slots) while rank 0 still compares
 
     # ---------------- e2e with host buffers: every finished frame ends row-major in page-locked host memory that rank 0 reads.
-    # Host frame ring (gvdbx_hostring_*): each rank renders full-width 32-row bands and copies ITS bands over ITS OWN PCIe
+    # Host frame ring (gvdbx_hostring_*): each rank renders full-width 16-row bands and copies ITS bands over ITS OWN PCIe
     # link into a shared-memory frame — N links instead of funnelling every frame through rank 0's.
-    hring = mg.HostFrameRing(r, f"/gvdbx_bench_{os.environ.get('MASTER_PORT', '0')}", w, h, rank, world, nslots=a.slots, band_rows=32)
+    hring = mg.HostFrameRing(r, f"/gvdbx_bench_{os.environ.get('MASTER_PORT', '0')}", w, h, rank, world, nslots=a.slots, band_rows=16)
     checksum = 0
 
     def step_e2e():
@@ -762,7 +762,7 @@ def main():
     hring.close()
     e2e = {"value": rays_step * a.steps / dt / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": a.frames * 416 * world,
            "d2h_bytes_per_step": a.frames * w * h * 4, "ms_per_frame": dt / a.steps / a.frames * 1e3, "host_frame_matches_single_gpu": host_ok,
-           "api": "gvdbx_hostring_submit per rank (own 32-row bands -> own PCIe link -> shared page-locked host frame), gvdbx_hostring_wait / _release on rank 0"}
+           "api": "gvdbx_hostring_submit per rank (own 16-row bands, one pitched copy per frame -> own PCIe link -> shared page-locked host frame), gvdbx_hostring_wait / _release on rank 0"}
     if ring is not None:
         ring.check()            # no stream-ordered wait ran into its timeout
 

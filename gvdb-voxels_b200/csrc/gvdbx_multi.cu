@@ -304,7 +304,20 @@ extern "C" int gvdbx_hostring_submit(gvdbx_hostring_t* g, const void* scninfo, i
     if (rc) return rc;
     const int nbands = (g->hgt + g->band_rows - 1) / g->band_rows;
     uint8_t* frame = g->frame(slot);
-    for (int k = 0; k < g->bands_mine; k++) {
+    // A full-width band is one contiguous run of bytes in the packed buffer AND in the row-major frame when the row pitch equals
+    // the width: all complete bands of this rank then travel as ONE pitched copy (a "row" = one band, destination pitch = nranks
+    // bands); only a clipped last band of the frame goes separately.  Otherwise one pitched copy per band.
+    const size_t band_bytes = size_t(g->band_rows) * g->w * 4;
+    int k0 = 0;
+    if (g->pitch == g->w) {
+        int nfull = 0;
+        while (nfull < g->bands_mine && (nfull * g->nranks + g->rank + 1) * g->band_rows <= g->hgt) nfull++;
+        if (nfull > 0)
+            GX_CUDA(h, cudaMemcpy2DAsync(frame + size_t(g->rank) * band_bytes, size_t(g->nranks) * band_bytes, g->packed[slot], band_bytes, band_bytes, nfull,
+                                         cudaMemcpyDeviceToHost, h->stream));
+        k0 = nfull;
+    }
+    for (int k = k0; k < g->bands_mine; k++) {
         const int b = k * g->nranks + g->rank;
         if (b >= nbands) break;
         const int y0 = b * g->band_rows, rows = std::min(g->band_rows, g->hgt - y0);

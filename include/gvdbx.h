@@ -52,7 +52,7 @@ extern "C" {
 /* options for gvdbx_set_option */
 #define GVDBX_OPT_SAMPLER   1   /* 0 = hardware texture fetch (bit-exact vs reference), 1 = linear brick-major loads */
 #define GVDBX_OPT_BLOCK_W   2   /* CTA pixel tile width  (default 8)  */
-#define GVDBX_OPT_BLOCK_H   3   /* CTA pixel tile height (default 8)  */
+#define GVDBX_OPT_BLOCK_H   3   /* CTA pixel tile height (default 8); width x height: a multiple of 32, at most 128 threads */
 #define GVDBX_OPT_COUNTERS  4   /* accumulate work counters during render (slower; for roofline accounting): 1 = the work of the ALGORITHM as the
                                    reference does it (no brick culling: SURVEY.md 8d units), 2 = the work the production kernel does (culling on) */
 #define GVDBX_OPT_CULL      6   /* 1 (default) = skip bricks whose value range cannot satisfy the mode's acceptance test (exact) */

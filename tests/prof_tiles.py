@@ -20,6 +20,7 @@ def main():
     ap.add_argument("--worlds", default="1,2,8")
     ap.add_argument("--tiles", default="16,32,64")
     ap.add_argument("--reps", type=int, default=5)
+    ap.add_argument("--bands", default="", help="also time full-width bands of these heights (the host frame ring's partition)")
     ap.add_argument("--size", default="")
     a = ap.parse_args()
     pkg = bench.load_pkg()
@@ -55,6 +56,27 @@ def main():
                 per.append(timed(lambda: [r.render_tiles_direct(s, shade, out.data_ptr(), ts, rank, world) for s in scns]))
             print(f"world {world} tile {ts}: max {max(per):.4f} min {min(per):.4f} sum {sum(per):.4f} ms/frame; ideal {base / world:.4f}; "
                   f"efficiency {base / world / max(per):.3f}")
+    for world in [int(x) for x in a.worlds.split(",")]:
+        for rows in [int(x) for x in a.bands.split(",") if x]:
+            nb = (h + rows - 1) // rows
+            mine = (nb + world - 1) // world
+            packed = torch.zeros((mine * rows, w, 4), dtype=torch.uint8, device="cuda")
+            for K in (1, 4):
+                streams = [torch.cuda.Stream() for _ in range(K)]
+                per = []
+                for rank in range(world):
+                    def fn():
+                        for j, s in enumerate(scns):
+                            if K > 1:
+                                r.set_stream(streams[j % K].cuda_stream)
+                            r.render_bands(s, shade, packed.data_ptr(), rows, rank, world)
+                        if K > 1:
+                            r.set_stream(None)
+                            for st in streams:
+                                torch.cuda.current_stream().wait_stream(st)
+                    per.append(timed(fn))
+                print(f"world {world} bands of {rows} rows, {K} stream(s): max {max(per):.4f} min {min(per):.4f} ms/frame; ideal {base / world:.4f}; "
+                      f"efficiency {base / world / max(per):.3f}")
     # K streams alternating frames (tails of frame j overlap the head of frame j+1)
     for K in (2, 3, 4):
         streams = [torch.cuda.Stream() for _ in range(K)]
