@@ -214,6 +214,7 @@ struct gvdbx_hostring {
     std::vector<void*> packed;          // one device buffer of this rank's bands per slot
     uint32_t* seqvals = nullptr;        // page-locked: the value each slot's delivery flag takes
     bool registered = false;
+    uint64_t done_d = 0;                // device address of done(0, 0) in the mapped segment (0: not mapped, flags travel by host-to-host copies)
     volatile uint32_t* done(int slot, int r) const { return (volatile uint32_t*)(seg + sizeof(GxHostRingHeader) + (size_t(slot) * nranks + r) * 64); }
     uint8_t* frame(int slot) const { return seg + hdr->frames_offset + size_t(slot) * hdr->frame_bytes; }
 };
@@ -268,8 +269,13 @@ extern "C" int gvdbx_hostring_create(gvdbx_t* h, const char* shm_name, int width
     }
     g->hdr->attached.fetch_add(1);
     // page-lock the segment in THIS process: copies into it are then true asynchronous DMA over this GPU's own PCIe link
-    if (cudaHostRegister(g->seg, g->seg_bytes, cudaHostRegisterPortable) != cudaSuccess) { cudaGetLastError(); g->hdr->attached.fetch_sub(1); return fail("cudaHostRegister of the shared segment"); }
+    if (cudaHostRegister(g->seg, g->seg_bytes, cudaHostRegisterPortable | cudaHostRegisterMapped) != cudaSuccess) { cudaGetLastError(); g->hdr->attached.fetch_sub(1); return fail("cudaHostRegister of the shared segment"); }
     g->registered = true;
+    {
+        void* dp = nullptr;
+        if (cudaHostGetDevicePointer(&dp, (void*)g->done(0, 0), 0) == cudaSuccess && dp) g->done_d = (uint64_t)dp;
+        else cudaGetLastError();
+    }
     g->packed_bytes = size_t(g->bands_mine) * band_rows * g->pitch * 4;
     for (int s = 0; s < nslots; s++) {
         void* p = nullptr;
@@ -324,7 +330,10 @@ extern "C" int gvdbx_hostring_submit(gvdbx_hostring_t* g, const void* scninfo, i
         GX_CUDA(h, cudaMemcpy2DAsync(frame + size_t(y0) * g->w * 4, size_t(g->w) * 4, (const uint8_t*)g->packed[slot] + size_t(k) * g->band_rows * g->pitch * 4,
                                      size_t(g->pitch) * 4, size_t(g->w) * 4, rows, cudaMemcpyDeviceToHost, h->stream));
     }
-    // delivery flag: a 4-byte copy behind the band copies on the same stream (page-locked source and destination)
+    // delivery flag: a one-thread kernel behind the band copies on the same stream release-stores the sequence number straight
+    // into the mapped shared segment (no host thread of the CUDA driver involved, unlike a host-to-host cudaMemcpyAsync: eight
+    // ranks polling on sixteen host cores otherwise delay each other's flags)
+    if (g->done_d) return gvdbx_stream_signal(h, nullptr, g->done_d + (size_t(slot) * g->nranks + g->rank) * 64, q);
     g->seqvals[slot] = q;
     GX_CUDA(h, cudaMemcpyAsync((void*)g->done(slot, g->rank), &g->seqvals[slot], sizeof(uint32_t), cudaMemcpyHostToHost, h->stream));
     return GVDBX_OK;
