@@ -321,7 +321,7 @@ def make_mirror(pkg, p, vol, dev_index, a, dshadow):
     return v
 
 
-def time_e2e(torch, pkg, p, vol, dev_index, a, shade, dshadow, frames, steps, lanes):
+def time_e2e(torch, pkg, p, vol, dev_index, a, shade, dshadow, frames, steps, lanes, bands=0):
     """through the reference-facing API (VolumeGVDB mirror) with HOST buffers.  lanes > 0: pipelined — render buffer k lives on
     frame lane k, ReadRenderBufAsync into pinned host memory, SyncRenderBuf hands the frame to the caller before its buffer is
     reused.  lanes == 0: the strict drop-in sequence — one render buffer, Render() then the synchronous ReadRenderBuf() into
@@ -333,6 +333,7 @@ def time_e2e(torch, pkg, p, vol, dev_index, a, shade, dshadow, frames, steps, la
     for k in range(nbuf):
         v.AddRenderBuf(k, w, h, 4)
     v.SetRenderLanes(lanes)
+    v.SetReadbackBands(bands)          # strict sequence only: 0 = automatic (~2 MB per band), 1 = one launch per frame
     if lanes:
         hosts = [torch.empty((h, w, 4), dtype=torch.uint8).pin_memory().numpy() for _ in range(nbuf)]
     else:
@@ -371,7 +372,8 @@ def time_e2e(torch, pkg, p, vol, dev_index, a, shade, dshadow, frames, steps, la
     return {"value": rays * steps / dt / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": frames * 416, "d2h_bytes_per_step": frames * w * h * 4,
             "ms_per_frame": dt / steps / frames * 1e3,
             "api": (f"VolumeGVDB mirror: SetCamera + Render(rbuf = frame % {nbuf}) + ReadRenderBufAsync into pinned host memory + SyncRenderBuf" if lanes
-                    else "VolumeGVDB mirror, strict drop-in sequence: SetCamera + Render(rbuf 0) + synchronous ReadRenderBuf into pageable host memory")}
+                    else "VolumeGVDB mirror, strict drop-in sequence: SetCamera + Render(rbuf 0) + synchronous ReadRenderBuf into pageable host memory "
+                         "(the library renders the frame in ~2 MB bands on two internal streams and copies each band as it finishes)")}
 
 
 def count_work(r, scns, shade, frame_d, w, h, mode):

@@ -24,7 +24,7 @@ EXPORTED_SYMBOLS = [
     "gvdbx_import_atlas_array", "gvdbx_import_atlas_host", "gvdbx_import_atlas_device", "gvdbx_import_color_array", "gvdbx_import_color_host", "gvdbx_clear_color", "gvdbx_set_transfer",
     "gvdbx_render", "gvdbx_render_tiles", "gvdbx_tiles_per_rank", "gvdbx_assemble_tiles",
     "gvdbx_render_debug", "gvdbx_raytrace", "gvdbx_read_buffer", "gvdbx_sync", "gvdbx_get_counters",
-    "gvdbx_sample_points", "gvdbx_measure_tex_peak", "gvdbx_measure_sampler_ab", "gvdbx_kernel_params", "gvdbx_update_apron", "gvdbx_update_apron_faces", "gvdbx_export_atlas_host", "gvdbx_render_tiles_direct", "gvdbx_render_tiles_ring", "gvdbx_peer_alloc", "gvdbx_peer_free", "gvdbx_peer_open",
+    "gvdbx_sample_points", "gvdbx_render_banded", "gvdbx_read_banded", "gvdbx_measure_tex_peak", "gvdbx_measure_sampler_ab", "gvdbx_kernel_params", "gvdbx_update_apron", "gvdbx_update_apron_faces", "gvdbx_export_atlas_host", "gvdbx_render_tiles_direct", "gvdbx_render_tiles_ring", "gvdbx_peer_alloc", "gvdbx_peer_free", "gvdbx_peer_open",
     "gvdbx_peer_close", "gvdbx_stream_signal", "gvdbx_stream_signal_add", "gvdbx_stream_signal_many", "gvdbx_stream_wait", "gvdbx_set_stream",
     "gvdbx_render_bands", "gvdbx_render_multi", "gvdbx_ring_create", "gvdbx_ring_connect", "gvdbx_ring_submit", "gvdbx_ring_acquire",
     "gvdbx_ring_release", "gvdbx_ring_frame", "gvdbx_ring_destroy", "gvdbx_hostring_create", "gvdbx_hostring_submit", "gvdbx_hostring_wait",
@@ -105,6 +105,8 @@ def lib():
     L.gvdbx_stream_signal_many.argtypes = [vp, vp, C.POINTER(u64), i32, C.c_uint32]
     L.gvdbx_set_stream.argtypes = [vp, vp]
     L.gvdbx_read_buffer_async.argtypes = [vp, u64, vp, C.c_size_t]
+    L.gvdbx_render_banded.argtypes = [vp, vp, i32, i32, u64, i32]
+    L.gvdbx_read_banded.argtypes = [vp, u64, vp, C.c_size_t]
     u32 = C.c_uint32
     L.gvdbx_render_bands.argtypes = [vp, vp, i32, i32, u64, i32, i32, i32]
     L.gvdbx_render_multi.argtypes = [C.POINTER(vp), i32, vp, i32, i32, u64, i32]
@@ -359,6 +361,15 @@ class Renderer:
     def lanes_join(self):
         self._ck(self._L.gvdbx_lanes_join(self._h), "gvdbx_lanes_join")
 
+    def render_banded(self, scninfo, shade, out_ptr, nbands, chan=0):
+        """the frame as nbands horizontal bands on two alternating internal streams (for read_banded's overlapped copy)"""
+        p, keep = _buf(scninfo)
+        self._ck(self._L.gvdbx_render_banded(self._h, p, shade, chan, int(out_ptr), int(nbands)), "gvdbx_render_banded")
+
+    def read_banded(self, buf_ptr, host_array):
+        """synchronous copy of a frame rendered by render_banded, band after band as they finish"""
+        self._ck(self._L.gvdbx_read_banded(self._h, int(buf_ptr), host_array.ctypes.data_as(C.c_void_p), host_array.nbytes), "gvdbx_read_banded")
+
     def read_into_async(self, buf_ptr, host_array):
         self._ck(self._L.gvdbx_read_buffer_async(self._h, int(buf_ptr), host_array.ctypes.data_as(C.c_void_p), host_array.nbytes),
                  "gvdbx_read_buffer_async")
@@ -425,7 +436,7 @@ HOST_SYMBOLS = [
     "gvdbxh_scene_params", "gvdbxh_cross_section", "gvdbxh_linear_transfer", "gvdbxh_transfer_table", "gvdbxh_set_res", "gvdbxh_prepare_render",
     "gvdbxh_import_topology_host", "gvdbxh_import_atlas_host", "gvdbxh_commit_transfer",
     "gvdbxh_load_vbx", "gvdbxh_save_vbx", "gvdbxh_vdbinfo", "gvdbxh_set_epsilon", "gvdbxh_add_render_buf",
-    "gvdbxh_render", "gvdbxh_read_render_buf", "gvdbxh_set_render_lanes", "gvdbxh_read_render_buf_async", "gvdbxh_sync_render_buf", "gvdbxh_set_option", "gvdbxh_last_error",
+    "gvdbxh_render", "gvdbxh_read_render_buf", "gvdbxh_set_render_lanes", "gvdbxh_set_readback_bands", "gvdbxh_read_render_buf_async", "gvdbxh_sync_render_buf", "gvdbxh_set_option", "gvdbxh_last_error",
 ]
 
 
@@ -558,6 +569,10 @@ class Volume:
             out = np.empty((h, w, bpp), dtype=np.uint8)
         self._ck(self._L.gvdbxh_read_render_buf(self._h, chan, out.ctypes.data_as(C.c_void_p)), "ReadRenderBuf")
         return out
+
+    def SetReadbackBands(self, n):
+        """Render without lanes: bands per frame for the overlapped synchronous read-back (0 = automatic, 1 = off)"""
+        self._ck(self._L.gvdbxh_set_readback_bands(self._h, int(n)), "SetReadbackBands")
 
     def SetRenderLanes(self, n):
         """extension: render buffer j lives on frame lane j % n, so frames in different render buffers overlap"""

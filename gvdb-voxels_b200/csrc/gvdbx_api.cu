@@ -93,6 +93,11 @@ extern "C" int gvdbx_destroy(gvdbx_t* h)
     if (h->d_counters) cudaFree(h->d_counters);
     if (h->d_err) cudaFree(h->d_err);
     if (h->build_ev) cudaEventDestroy(h->build_ev);
+    if (h->band_streams[0]) {
+        for (int k = 0; k < 2; k++) { cudaStreamSynchronize(h->band_streams[k]); cudaStreamDestroy(h->band_streams[k]); cudaEventDestroy(h->band_join[k]); }
+        cudaStreamDestroy(h->band_copy); cudaEventDestroy(h->band_fork);
+        for (int b = 0; b < GX_MAX_BANDS; b++) cudaEventDestroy(h->band_ev[b]);
+    }
     }
     delete h;
     return GVDBX_OK;
@@ -1027,6 +1032,78 @@ extern "C" int gvdbx_read_buffer(gvdbx_t* h, uint64_t buf_d, void* host, size_t 
     GxCtx ctx_(h);
     GX_CUDA(h, cudaMemcpyAsync(host, (const void*)buf_d, bytes, cudaMemcpyDeviceToHost, h->stream));
     GX_CUDA(h, cudaStreamSynchronize(h->stream));
+    return GVDBX_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ banded render + overlapped read-back
+// The strict drop-in sequence is Render() (asynchronous) followed by ReadRenderBuf() (synchronous copy into the caller's pageable
+// memory): kernel and copy in series, 33 MB per 4K frame.  gvdbx_render_banded renders the same frame as horizontal bands,
+// consecutive bands alternating between two internal streams (the tail of band b overlaps band b + 1, like the frame lanes) with an
+// event behind each; gvdbx_read_banded copies band after band as they finish, so all but the last band's copy hides behind the
+// rendering of the bands below it.  Same bytes in the same buffer; the caller's sequence does not change.
+static int gx_band_setup(gvdbx_t* h)
+{
+    if (h->band_streams[0]) return GVDBX_OK;
+    for (int k = 0; k < 2; k++) {
+        GX_CUDA(h, cudaStreamCreateWithFlags(&h->band_streams[k], cudaStreamNonBlocking));
+        GX_CUDA(h, cudaEventCreateWithFlags(&h->band_join[k], cudaEventDisableTiming));
+    }
+    GX_CUDA(h, cudaStreamCreateWithFlags(&h->band_copy, cudaStreamNonBlocking));
+    GX_CUDA(h, cudaEventCreateWithFlags(&h->band_fork, cudaEventDisableTiming));
+    for (int b = 0; b < GX_MAX_BANDS; b++) GX_CUDA(h, cudaEventCreateWithFlags(&h->band_ev[b], cudaEventDisableTiming));
+    return GVDBX_OK;
+}
+
+extern "C" int gvdbx_render_banded(gvdbx_t* h, const void* scninfo, int shade_mode, int chan, uint64_t outbuf_d, int nbands)
+{
+    if (!h || !scninfo || !outbuf_d || nbands < 1 || nbands > GX_MAX_BANDS) return GVDBX_E_ARG;
+    GxCtx ctx_(h);
+    GxScnInfo s;
+    memcpy(&s, scninfo, sizeof s);
+    h->band_n = 0;
+    if (shade_mode == GVDBX_SHADE_OFF || nbands == 1 || s.height < nbands * h->block_h)
+        return gvdbx_render(h, scninfo, shade_mode, chan, outbuf_d, 0, 0, 0, 0);
+    int rc = gx_band_setup(h);
+    if (rc) return rc;
+    // whatever the frame needs built (occupancy bits for a new THRESH, brick-major copy) is enqueued on the caller's stream first:
+    // the band streams fork behind it
+    { GxParams P; int mode = 0; rc = gx_fill_params(h, scninfo, shade_mode, chan, P, mode); if (rc) return rc; }
+    cudaStream_t saved_stream = h->stream;
+    const int saved_lane = h->cur_lane;
+    GX_CUDA(h, cudaEventRecord(h->band_fork, saved_stream));
+    for (int k = 0; k < 2; k++) GX_CUDA(h, cudaStreamWaitEvent(h->band_streams[k], h->band_fork, 0));
+    const int rows = ((s.height + nbands - 1) / nbands + h->block_h - 1) / h->block_h * h->block_h;
+    int nb = 0;
+    for (int y0 = 0; y0 < s.height && rc == GVDBX_OK; y0 += rows, nb++) {
+        const int k = nb & 1;
+        h->stream = h->band_streams[k];
+        h->cur_lane = int(h->lanes.size()) + k;            // private slots for the per-frame derived tables of the two band streams
+        rc = gvdbx_render(h, scninfo, shade_mode, chan, outbuf_d, 0, y0, s.width, std::min(rows, s.height - y0));
+        if (rc == GVDBX_OK && cudaEventRecord(h->band_ev[nb], h->band_streams[k]) != cudaSuccess) rc = GVDBX_E_CUDA;
+    }
+    h->stream = saved_stream;
+    h->cur_lane = saved_lane;
+    for (int k = 0; k < 2; k++) {                           // later work on the caller's stream is ordered behind every band
+        GX_CUDA(h, cudaEventRecord(h->band_join[k], h->band_streams[k]));
+        GX_CUDA(h, cudaStreamWaitEvent(saved_stream, h->band_join[k], 0));
+    }
+    if (rc) return rc;
+    h->band_n = nb; h->band_rows = rows; h->band_w = s.width; h->band_h = s.height; h->band_buf = outbuf_d;
+    return GVDBX_OK;
+}
+
+extern "C" int gvdbx_read_banded(gvdbx_t* h, uint64_t buf_d, void* host, size_t bytes)
+{
+    if (!h || !buf_d || !host) return GVDBX_E_ARG;
+    if (h->band_n == 0 || h->band_buf != buf_d || bytes != size_t(h->band_w) * h->band_h * 4) return gvdbx_read_buffer(h, buf_d, host, bytes);
+    GxCtx ctx_(h);
+    for (int b = 0; b < h->band_n; b++) {
+        const int y0 = b * h->band_rows, rows = std::min(h->band_rows, h->band_h - y0);
+        const size_t off = size_t(y0) * h->band_w * 4, n = size_t(rows) * h->band_w * 4;
+        GX_CUDA(h, cudaEventSynchronize(h->band_ev[b]));
+        GX_CUDA(h, cudaMemcpyAsync((char*)host + off, (const char*)buf_d + off, n, cudaMemcpyDeviceToHost, h->band_copy));
+        GX_CUDA(h, cudaStreamSynchronize(h->band_copy));
+    }
     return GVDBX_OK;
 }
 

@@ -119,6 +119,7 @@ public:
     // enqueued there, so frames in different render buffers overlap.  ReadRenderBufAsync returns at once; the host
     // buffer (pinned) is valid after SyncRenderBuf(chan).
     int  SetRenderLanes(int n);
+    void SetReadbackBands(int n) { mReadbackBands = n; }    // 0 = automatic (~2 MB of pixels per band), 1 = one launch per frame
     int  ReadRenderBufAsync(int chan, unsigned char* outptr);
     int  SyncRenderBuf(int chan);
     void PrepareRender(int w, int h, char shading);                          // :4254-4306 (fills mScnInfo)
@@ -146,6 +147,7 @@ private:
     int       mMaxIter = 256;
     std::string mErr;
     int       mLanes = 0;
+    int       mReadbackBands = 0;       // Render without lanes: bands per frame for the overlapped read-back (0 = ~2 MB per band, 1 = off)
 };
 
 }  // namespace gvdbx
@@ -177,6 +179,7 @@ int   gvdbxh_add_render_buf(gvdbxh_volume*, int chan, int w, int h, int bpp);
 int   gvdbxh_render(gvdbxh_volume*, int shading, int chan, int rbuf);
 int   gvdbxh_read_render_buf(gvdbxh_volume*, int chan, void* out);
 int   gvdbxh_set_render_lanes(gvdbxh_volume*, int n);
+int   gvdbxh_set_readback_bands(gvdbxh_volume*, int n);
 int   gvdbxh_read_render_buf_async(gvdbxh_volume*, int chan, void* out);
 int   gvdbxh_sync_render_buf(gvdbxh_volume*, int chan);
 int   gvdbxh_set_option(gvdbxh_volume*, int option, int value);

@@ -46,12 +46,18 @@ struct GxDriver {
 };
 inline GxDriver gx_drv;
 
+#define GX_MAX_BANDS 16
 struct gvdbx_ctx {
     int          device = 0;
     void*        cuctx = nullptr;       // the CUcontext every entry point runs in (adopted at creation)
     cudaStream_t stream = nullptr;
     std::string  err;
     // options
+    // banded render + overlapped read-back (gvdbx_render_banded / gvdbx_read_banded)
+    cudaStream_t band_streams[2] = {nullptr, nullptr}, band_copy = nullptr;
+    cudaEvent_t  band_join[2] = {nullptr, nullptr}, band_fork = nullptr, band_ev[GX_MAX_BANDS] = {};
+    int          band_n = 0, band_rows = 0, band_w = 0, band_h = 0;
+    uint64_t     band_buf = 0;
     int sampler = GX_SAMPLER_TEX, block_w = 8, block_h = 8, count = 0, literal = 0, spp = 1, deep_shadow = 0, memops = 0;
     // topology
     bool       have_topo = false, uniform3 = false;

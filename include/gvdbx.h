@@ -272,6 +272,14 @@ int  gvdbx_sample_points(gvdbx_t* h, int chan, uint64_t xyz_d, int n, uint64_t o
  * `lane_spacing` voxels apart — the unit's rate depends on how many distinct texel quads one warp request touches: ~0.2 = the
  * best case, the voxels-per-pixel of a camera = what a ray packet of that camera can get.  Roofline denominator of the
  * TEX-bound deep mode.  Synchronises. */
+/* Strict drop-in sequence, overlapped inside the library: VolumeGVDB::Render is asynchronous and ReadRenderBuf a synchronous copy
+ * into pageable memory (src/gvdb_volume_gvdb.cpp:4241-4251), kernel and copy in series.  gvdbx_render_banded renders the frame as
+ * `nbands` (1..16) horizontal bands on two alternating internal streams, an event behind each band; gvdbx_read_banded then copies
+ * band after band as they finish — all but the last band's copy hides behind the rendering below it.  Same bytes, same buffer;
+ * later work on the context's stream is ordered behind every band.  gvdbx_read_banded of a buffer that was not rendered in bands
+ * is gvdbx_read_buffer. */
+int  gvdbx_render_banded(gvdbx_t* h, const void* scninfo, int shade_mode, int chan, uint64_t outbuf_d, int nbands);
+int  gvdbx_read_banded(gvdbx_t* h, uint64_t buf_d, void* host, size_t bytes);
 int  gvdbx_measure_tex_peak(gvdbx_t* h, float lane_spacing, double* gsamples_per_s);
 /* Fetch + filter microbenchmarks of the four ways of reading a brick on the imported atlas (csrc/gvdbx_microbench.cuh), Gsamples/s:
  * [0] texture unit on the caller's array, [1] brick-major copy + scalar read-only loads, [2] x-pair layout + 8-byte loads,

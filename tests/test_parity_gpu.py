@@ -1038,3 +1038,32 @@ def test_sampler_ab_microbench_runs_and_ranks_the_texture_unit_first(scenes):
     assert set(ab) == {"tex", "linear_ldg", "linear_pairs_ldg64", "tma_staged_smem"}
     assert all(v > 1.0 for v in ab.values()), ab
     assert ab["tex"] > max(ab["linear_ldg"], ab["linear_pairs_ldg64"], ab["tma_staged_smem"]), ab
+
+
+@pytest.mark.parametrize("preset,mode", [("cfg3_small", "voxel"), ("cfg4_small", "deep"), ("cfg2_small", "levelset")])
+def test_banded_render_and_overlapped_readback_same_bytes(scenes, ora, pkg, torch_cuda, preset, mode):
+    """gvdbx_render_banded + gvdbx_read_banded (the strict Render + ReadRenderBuf sequence with the copy overlapped inside the
+    library) deliver the bytes of one plain launch, for band counts that do and do not divide the frame height, also when the
+    occupancy bits have to be rebuilt for a new THRESH in the banded call itself"""
+    torch = torch_cuda
+    p, vol, r = scenes(preset)
+    scn, _ = ora.scninfo_for(pkg, p)
+    shade = MODES[mode]
+    w, h = p.width, p.height
+    plain = _render(torch, r, scn, shade, w, h, 0)
+    out = torch.zeros((h, w, 4), dtype=torch.uint8, device="cuda")
+    for nb in (2, 3, 5, 8):
+        out.zero_()
+        r.render_banded(scn, shade, out.data_ptr(), nb)
+        host = np.full((h, w, 4), 7, np.uint8)
+        r.read_banded(out.data_ptr(), host)
+        assert np.array_equal(host, plain), (preset, mode, nb)
+        r.sync()
+        assert np.array_equal(out.cpu().numpy(), plain)
+    if mode == "voxel":         # a new THRESH: the mask rebuild is enqueued before the band streams fork
+        scn3 = bytearray(scn)
+        scn3[372:376] = np.float32(0.75).tobytes()
+        r.render_banded(bytes(scn3), shade, out.data_ptr(), 4)
+        host = np.zeros((h, w, 4), np.uint8)
+        r.read_banded(out.data_ptr(), host)
+        assert np.array_equal(host, _render(torch, r, bytes(scn3), shade, w, h, 0))
