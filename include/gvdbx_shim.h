@@ -56,6 +56,24 @@ public:
         if (gvdbx_render(mX, getScnInfo(), shading, chan, (uint64_t)mRenderBuf[rbuf].gpu, 0, 0, 0, 0) != 0) fail();
     }
 
+    /* The same frame rendered in `bands` horizontal bands + the read-back that overlaps with them (gvdbx_render_banded /
+     * gvdbx_read_banded): RenderX(..., bands) followed by ReadRenderBufX() is Render() followed by ReadRenderBuf() with the
+     * device-to-host copy of band b hidden behind the rendering of the bands below it.  The reference's own ReadRenderBuf
+     * stays valid after a banded RenderX (work on the context's stream is ordered behind every band). */
+    void RenderX(char shading, uchar chan, uchar rbuf, int bands)
+    {
+        int w = (int)mRenderBuf[rbuf].stride, h = (int)(mRenderBuf[rbuf].max / mRenderBuf[rbuf].stride);
+        const bool topo_dirty = mVDBInfo.update || !mSynced;
+        PrepareRender(w, h, shading);
+        PrepareVDB();
+        if (topo_dirty && !SyncX(chan)) return;
+        if (gvdbx_render_banded(mX, getScnInfo(), shading, chan, (uint64_t)mRenderBuf[rbuf].gpu, bands) != 0) fail();
+    }
+    void ReadRenderBufX(uchar rbuf, unsigned char* outptr)
+    {
+        if (gvdbx_read_banded(mX, (uint64_t)mRenderBuf[rbuf].gpu, outptr, (size_t)mRenderBuf[rbuf].size) != 0) fail();
+    }
+
     /* UpdateApron(chan, boundval) on the shared CUarray, keeping libgvdbx's derived tables coherent (no re-import) */
     void UpdateApronX(uchar chan = 0, float boundval = 0.0f)
     {

@@ -506,8 +506,17 @@ int main(int argc, char** argv)
                 if (memcmp(&imgx[i], &img[i], 4)) xdiff++;
                 if (memcmp(&img[i], &img[0], 4)) xnonbg++;
             }
+            // and as bands with the overlapped read-back (RenderX(..., bands) + ReadRenderBufX), then once more through the
+            // reference's own ReadRenderBuf behind a banded RenderX: any difference counts as a mismatch of the shim
+            for (int pass = 0; pass < 2; pass++) {
+                std::vector<unsigned char> imgb((size_t)w * h * 4, 0xA5);
+                cuMemsetD8(gvdb.mRenderBuf[0].gpu, 0xA5, (size_t)w * h * 4);
+                gvdb.RenderX(m.shade, 0, 0, pass == 0 ? 3 : 5);
+                if (pass == 0) gvdb.ReadRenderBufX(0, imgb.data()); else gvdb.ReadRenderBuf(0, imgb.data());
+                for (size_t i = 0; i < imgb.size(); i += 4) if (memcmp(&imgb[i], &img[i], 4)) xdiff++;
+            }
             if (!nodump) dump(outdir + "/outx_" + m.name + ".rgba", imgx.data(), imgx.size());
-            fprintf(stderr, "[ref] %s: RenderX %.3f ms/frame, %ld of %d pixels differ from Render()\n", m.name, xms, xdiff, w * h);
+            fprintf(stderr, "[ref] %s: RenderX %.3f ms/frame, %ld of %d pixels differ from Render() (plain + banded + banded read by the reference)\n", m.name, xms, xdiff, w * h);
         }
 #endif
         char buf[384];
