@@ -1061,7 +1061,7 @@ extern "C" int gvdbx_render_banded(gvdbx_t* h, const void* scninfo, int shade_mo
     GxScnInfo s;
     memcpy(&s, scninfo, sizeof s);
     h->band_n = 0;
-    if (shade_mode == GVDBX_SHADE_OFF || nbands == 1 || s.height < nbands * h->block_h)
+    if (shade_mode == GVDBX_SHADE_OFF || nbands == 1 || s.height < nbands * h->block_h || h->count)      // work counters are per launch
         return gvdbx_render(h, scninfo, shade_mode, chan, outbuf_d, 0, 0, 0, 0);
     int rc = gx_band_setup(h);
     if (rc) return rc;
