@@ -395,7 +395,12 @@ def tex_peaks(r, p):
     (best case) and for this camera's ray spacing (voxels per pixel at the orbit centre)"""
     import math
     spacing = 2.0 * p.cam_dist * math.tan(math.radians(p.fov) / 2.0) / p.height
-    return {"coherent": r.measure_tex_peak(0.2), "at_ray_spacing": r.measure_tex_peak(spacing), "ray_spacing_voxels": spacing}
+    out = {"coherent": r.measure_tex_peak(0.2), "at_ray_spacing": r.measure_tex_peak(spacing), "ray_spacing_voxels": spacing}
+    try:        # the deep marcher's inner loop alone (needs a transfer function): fetch + table gather + colour update, no traversal
+        out["sample_loop"] = r.measure_deep_loop_peak(spacing)
+    except Exception:
+        out["sample_loop"] = None
+    return out
 
 
 def roofline_block(key, mode, kernel, ms_total, frames_total, n_gpus, sm_mhz, alg_ref, alg_prod, units_ref, units_prod, tex_peak):
@@ -429,6 +434,12 @@ def roofline_block(key, mode, kernel, ms_total, frames_total, n_gpus, sm_mhz, al
                           "this atlas with the 8x4 lanes of a warp as far apart as this camera's rays (voxels per pixel at the orbit centre); "
                           "peak_coherent = the same with lanes 0.2 voxel apart"}
     tex["frac"] = (tex["achieved"] / tex["peak"]) if tex["peak"] and tex["achieved"] else None
+    if tex_peak and tex_peak.get("sample_loop"):
+        tex["peak_sample_loop"] = tex_peak["sample_loop"] * n_gpus
+        tex["frac_of_sample_loop"] = (tex["achieved"] / tex["peak_sample_loop"]) if tex["achieved"] else None
+        tex["sample_loop_is"] = ("gvdbx_measure_deep_loop_peak, measured in this run: the deep marcher's four-sample round alone (4 fetches, 4 transfer indices, "
+                                 "4 table gathers of 16 bytes, 4 colour updates with their separately rounded products), no traversal, no brick changes, every lane "
+                                 "busy, L1-resident bricks: achieved / this = what traversal, brick changes, lane imbalance and cache misses cost")
     dram = (kc["dram_bytes"] * frames_total / t / 1e9) if kc and kc.get("dram_bytes") else None
     hbm = {"peak": hbm_peak * n_gpus, "unit": "GB/s", "peak_source": src,
            "dram_achieved": dram, "dram_frac": (dram / (hbm_peak * n_gpus)) if dram else None,

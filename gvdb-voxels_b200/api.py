@@ -24,7 +24,7 @@ EXPORTED_SYMBOLS = [
     "gvdbx_import_atlas_array", "gvdbx_import_atlas_host", "gvdbx_import_atlas_device", "gvdbx_import_color_array", "gvdbx_import_color_host", "gvdbx_clear_color", "gvdbx_set_transfer",
     "gvdbx_render", "gvdbx_render_tiles", "gvdbx_tiles_per_rank", "gvdbx_assemble_tiles",
     "gvdbx_render_debug", "gvdbx_raytrace", "gvdbx_read_buffer", "gvdbx_sync", "gvdbx_get_counters",
-    "gvdbx_sample_points", "gvdbx_render_banded", "gvdbx_read_banded", "gvdbx_measure_tex_peak", "gvdbx_measure_sampler_ab", "gvdbx_kernel_params", "gvdbx_update_apron", "gvdbx_update_apron_faces", "gvdbx_export_atlas_host", "gvdbx_render_tiles_direct", "gvdbx_render_tiles_ring", "gvdbx_peer_alloc", "gvdbx_peer_free", "gvdbx_peer_open",
+    "gvdbx_sample_points", "gvdbx_render_banded", "gvdbx_read_banded", "gvdbx_measure_tex_peak", "gvdbx_measure_sampler_ab", "gvdbx_measure_deep_loop_peak", "gvdbx_kernel_params", "gvdbx_update_apron", "gvdbx_update_apron_faces", "gvdbx_export_atlas_host", "gvdbx_render_tiles_direct", "gvdbx_render_tiles_ring", "gvdbx_peer_alloc", "gvdbx_peer_free", "gvdbx_peer_open",
     "gvdbx_peer_close", "gvdbx_stream_signal", "gvdbx_stream_signal_add", "gvdbx_stream_signal_many", "gvdbx_stream_wait", "gvdbx_set_stream",
     "gvdbx_render_bands", "gvdbx_render_multi", "gvdbx_ring_create", "gvdbx_ring_connect", "gvdbx_ring_submit", "gvdbx_ring_acquire",
     "gvdbx_ring_release", "gvdbx_ring_frame", "gvdbx_ring_destroy", "gvdbx_hostring_create", "gvdbx_hostring_submit", "gvdbx_hostring_wait",
@@ -89,6 +89,7 @@ def lib():
     L.gvdbx_sample_points.argtypes = [vp, i32, u64, i32, u64, u64]
     L.gvdbx_measure_tex_peak.argtypes = [vp, C.c_float, C.POINTER(C.c_double)]
     L.gvdbx_measure_sampler_ab.argtypes = [vp, C.c_float, C.POINTER(C.c_double)]
+    L.gvdbx_measure_deep_loop_peak.argtypes = [vp, C.c_float, C.POINTER(C.c_double)]
     L.gvdbx_render_tiles_direct.argtypes = [vp, vp, i32, i32, u64, i32, i32, i32]
     L.gvdbx_kernel_params.argtypes = [vp, vp, i32, i32, u64, vp, C.c_size_t]
     L.gvdbx_update_apron.argtypes = [vp, i32, C.c_float]
@@ -408,6 +409,12 @@ class Renderer:
         warp `lane_spacing` voxels apart"""
         g = C.c_double()
         self._ck(self._L.gvdbx_measure_tex_peak(self._h, C.c_float(lane_spacing), C.byref(g)), "gvdbx_measure_tex_peak")
+        return float(g.value)
+
+    def measure_deep_loop_peak(self, lane_spacing=0.2):
+        """Gsamples/s of the deep marcher's inner loop alone (fetch + transfer index + table gather + colour update, no traversal)"""
+        g = C.c_double()
+        self._ck(self._L.gvdbx_measure_deep_loop_peak(self._h, C.c_float(lane_spacing), C.byref(g)), "gvdbx_measure_deep_loop_peak")
         return float(g.value)
 
     def measure_sampler_ab(self, lane_spacing=0.2):

@@ -1242,6 +1242,41 @@ extern "C" int gvdbx_measure_sampler_ab(gvdbx_t* h, float lane_spacing, double* 
     return GVDBX_OK;
 }
 
+// Gsamples/s of the deep marcher's inner loop alone (csrc/gvdbx_microbench.cuh): fetch + transfer index + table gather + colour
+// update, four samples per round, no traversal.  Needs the atlas and a transfer function (gvdbx_set_transfer); synchronises.
+extern "C" int gvdbx_measure_deep_loop_peak(gvdbx_t* h, float lane_spacing, double* gsamples_per_s)
+{
+    if (!h || !gsamples_per_s || !(lane_spacing >= 0.f) || lane_spacing > 8.f) return GVDBX_E_ARG;
+    if (!h->have_atlas) return gx_fail(h, GVDBX_E_STATE, "no atlas imported");
+    if (!h->d_transfer) return gx_fail(h, GVDBX_E_STATE, "no transfer function (gvdbx_set_transfer)");
+    GxCtx ctx_(h);
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
+    const int blocks = sms * 14, threads = 128, rounds = 1024;
+    float* out = nullptr;
+    GX_CUDA(h, cudaMalloc(&out, size_t(blocks) * threads * sizeof(float)));
+    cudaEvent_t e0, e1;
+    GX_CUDA(h, cudaEventCreate(&e0));
+    GX_CUDA(h, cudaEventCreate(&e1));
+    double best = 0.0;
+    for (int rep = 0; rep < 4; rep++) {             // first repetition warms up
+        GX_CUDA(h, cudaEventRecord(e0, h->stream));
+        gx_deep_loop_peak_kernel<<<blocks, threads, 0, h->stream>>>(h->tex, h->d_transfer, h->ares[0], h->ares[1], h->ares[2], rounds, lane_spacing,
+                                                                    0.1f, 1.0f, 0.005f, 1.5f, out);
+        GX_CUDA(h, cudaEventRecord(e1, h->stream));
+        GX_CUDA(h, cudaEventSynchronize(e1));
+        GX_CUDA(h, cudaGetLastError());
+        float ms = 0.f;
+        GX_CUDA(h, cudaEventElapsedTime(&ms, e0, e1));
+        const double g = double(blocks) * threads * rounds * 4.0 / (double(ms) * 1e-3) / 1e9;
+        if (rep > 0 && g > best) best = g;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    cudaFree(out);
+    *gsamples_per_s = best;
+    return GVDBX_OK;
+}
+
 // device-buffer helpers for the host mirror (gvdbx_host.cpp is plain C++)
 extern "C" int gvdbx_internal_alloc(gvdbx_t* h, uint64_t* ptr, size_t bytes)
 {

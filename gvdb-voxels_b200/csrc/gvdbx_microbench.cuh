@@ -12,7 +12,7 @@
 //              8 shared-memory loads + the same filter
 // The filter arithmetic (~45 integer / float instructions per sample) is identical in 1-3; what differs is where the texels come from.
 #pragma once
-#include "gvdbx_device.cuh"
+#include "gvdbx_trace.cuh"
 
 // weights of the unit's filter for brick-local texel coordinates (see GxSampler<GX_SAMPLER_LINEAR>::tri)
 struct GxSoftW { int ix, iy, iz, ix1, iy1, iz1; float w[8]; };
@@ -129,4 +129,41 @@ __global__ void __launch_bounds__(128) gx_linear_peak_kernel(const float* __rest
         if (VARIANT == 3) __syncwarp();     // every lane has finished reading this stage before it is refilled
     }
     out[tid] = acc;
+}
+
+// ------------------------------------------------------------------------------------------------ deep sample loop alone
+// Ceiling of the deep marcher's INNER loop on this GPU: the four-sample round of gx_raycast_deep_q — four texture fetches, four
+// transfer-index computations, four 16-byte table gathers, four emission / absorption updates with their separately rounded
+// products — and nothing else: no traversal, no brick entries, no partial rounds, every lane always active, bricks L1-resident,
+// the same 8x4 packet geometry as gx_tex_peak_kernel.  deep achieved / this = what traversal, brick changes, lane imbalance and
+// cache misses cost; this / texture peak = what the per-sample arithmetic and the table gather cost.
+__global__ void __launch_bounds__(128, 7) gx_deep_loop_peak_kernel(cudaTextureObject_t tex, const float4* __restrict__ lut, int ares_x, int ares_y, int ares_z,
+                                                                   int rounds, float spacing, float thresh, float inv_range, float minval, float albedo,
+                                                                   float* __restrict__ out)
+{
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
+    const float bx = float((warp * 10) % max(ares_x - 10, 1)) + 1.0f, by = float(((warp / 7) * 10) % max(ares_y - 10, 1)) + 1.0f,
+                bz = float(((warp / 53) * 10) % max(ares_z - 10, 1)) + 1.0f;
+    float3 p = make_float3(bx + spacing * float(lane & 7), by + 1.07f * spacing * float(lane >> 3), bz);
+    const float3 wpt = make_float3(0.11f, 0.07f, 0.22f);
+    GxParams P;                                  // only the field gx_deep_accumulate_pre reads
+    P.extinct.y = albedo;
+    float4 clr = make_float4(0.f, 0.f, 0.f, 1.f);
+    for (int r = 0; r < rounds; r++) {
+        float3 p1, p2, p3;
+        GX_STEP_ADD(p1, p); GX_STEP_ADD(p2, p1); GX_STEP_ADD(p3, p2);
+        const float v0 = tex3D<float>(tex, p.x, p.y, p.z), v1 = tex3D<float>(tex, p1.x, p1.y, p1.z);
+        const float v2 = tex3D<float>(tex, p2.x, p2.y, p2.z), v3 = tex3D<float>(tex, p3.x, p3.y, p3.z);
+        const float4 c0 = gx_lut(lut, gx_transfer_index(v0, thresh, inv_range)), c1 = gx_lut(lut, gx_transfer_index(v1, thresh, inv_range));
+        const float4 c2 = gx_lut(lut, gx_transfer_index(v2, thresh, inv_range)), c3 = gx_lut(lut, gx_transfer_index(v3, thresh, inv_range));
+        if (v0 >= minval) gx_deep_accumulate_pre(P, clr, c0);
+        if (v1 >= minval) gx_deep_accumulate_pre(P, clr, c1);
+        if (v2 >= minval) gx_deep_accumulate_pre(P, clr, c2);
+        if (v3 >= minval) gx_deep_accumulate_pre(P, clr, c3);
+        if (!(clr.w > 0.01f)) clr.w = 1.0f;      // the marcher would stop here; the benchmark keeps the lane busy
+        GX_STEP_ADD(p, p3);
+        if (p.z > bz + 7.5f) p = make_float3(bx + spacing * float(lane & 7), by + 1.07f * spacing * float(lane >> 3), bz);
+    }
+    out[tid] = clr.x + clr.y + clr.z + clr.w;
 }

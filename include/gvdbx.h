@@ -286,6 +286,9 @@ int  gvdbx_measure_tex_peak(gvdbx_t* h, float lane_spacing, double* gsamples_per
  * [3] brick-major blocks staged into shared memory by TMA (cp.async.bulk + mbarrier, two stages per warp).  [1]-[3] run the
  * software model of the unit's filter.  The numbers behind the texture-versus-linear-load decision. */
 int  gvdbx_measure_sampler_ab(gvdbx_t* h, float lane_spacing, double* gsamples_per_s4);
+/* Gsamples/s of the deep marcher's inner loop alone — four fetches, four transfer indices, four 16-byte table gathers, four colour
+ * updates per round, no traversal, every lane busy, L1-resident bricks: the ceiling of the sample loop; needs gvdbx_set_transfer. */
+int  gvdbx_measure_deep_loop_peak(gvdbx_t* h, float lane_spacing, double* gsamples_per_s);
 
 #ifdef __cplusplus
 }

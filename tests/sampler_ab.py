@@ -18,8 +18,11 @@ def main():
     r = pkg.Renderer(0)
     r.import_topology_host(vol["vdbinfo"], vol["pool0"], vol["pool1"])
     r.import_atlas_host(vol["atlas"])
+    _, table = bench.frame_scninfos(pkg, p, 7, 1)
+    r.set_transfer(table)
     for s in spacings:
-        print(json.dumps({"workload": wl, "lane_spacing_voxels": s, **{k: round(v, 1) for k, v in r.measure_sampler_ab(s).items()}}), flush=True)
+        print(json.dumps({"workload": wl, "lane_spacing_voxels": s, **{k: round(v, 1) for k, v in r.measure_sampler_ab(s).items()},
+                          "deep_sample_loop": round(r.measure_deep_loop_peak(s), 1)}), flush=True)
     r.close()
 
 

@@ -1035,6 +1035,8 @@ def test_sampler_ab_microbench_runs_and_ranks_the_texture_unit_first(scenes):
     TMA-staged shared memory): every variant runs, and the decision DESIGN.md records — texture sampler by default — holds"""
     _, _, r = scenes("cfg1_small")
     ab = r.measure_sampler_ab(0.5)
+    loop = r.measure_deep_loop_peak(0.5)        # the deep marcher's inner loop alone: below the fetch-only rate, above zero
+    assert 1.0 < loop < ab["tex"], (loop, ab)
     assert set(ab) == {"tex", "linear_ldg", "linear_pairs_ldg64", "tma_staged_smem"}
     assert all(v > 1.0 for v in ab.values()), ab
     assert ab["tex"] > max(ab["linear_ldg"], ab["linear_pairs_ldg64"], ab["tma_staged_smem"]), ab
