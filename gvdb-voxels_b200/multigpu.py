@@ -1,11 +1,15 @@
-"""Image-space tiling across ranks (one process per GPU, torch.distributed for the plumbing).
+"""Image-space tiling across ranks (one process per GPU, torch.distributed only for bootstrap blobs, barriers and the
+replication of the volume).  Thin ctypes callers of the C entry points in csrc/gvdbx_multi.cu — the protocols live there.
 
-The volume is replicated on every GPU; a frame is cut into tile_size x tile_size tiles numbered row-major and dealt
-round-robin: rank r renders tiles r, r+world, r+2*world, ... into a packed buffer of `slots` tiles
-(gvdbx_render_tiles).  Rays that miss the volume are nearly free, so small interleaved tiles balance the load where
-contiguous bands would not.  The only exchange step is the gather of finished tiles on rank 0 (NCCL over NVLink),
-enqueued directly behind the render kernel; rank 0 then scatters [world][slots][tile] back into a row-major frame
-(gvdbx_assemble_tiles).  The output bytes are a pure function of the pixel, hence identical for 1/2/4/8 GPUs.
+The volume is replicated on every GPU; output bytes are a pure function of the pixel, hence identical for 1/2/4/8 GPUs.
+
+* PeerFrameRing (default, frames wanted on rank 0's DEVICE): tile_size x tile_size tiles dealt round-robin; every rank's
+  tile-list kernel stores its pixels straight into rank 0's frame over NVLink (CUDA IPC mapping); two 4-byte flags per frame
+  order producers and consumer, all waits / signals are stream-ordered device operations (gvdbx_ring_*).
+* HostFrameRing (frames wanted on the HOST): full-width bands dealt round-robin; every rank copies ITS bands over ITS OWN PCIe
+  link into a shared page-locked POSIX shm frame, one pitched copy + a one-thread flag kernel per frame (gvdbx_hostring_*).
+* TiledFrame (`bench.py --exchange nccl`, the first implementation, kept as the NCCL path north_star names): packed tile slots
+  (gvdbx_render_tiles) + an NCCL gather on rank 0 + gvdbx_assemble_tiles.
 
 The reference has no multi-GPU path at all; this file is the north-star extension around Render().
 """
