@@ -1255,14 +1255,23 @@ extern "C" int gvdbx_measure_deep_loop_peak(gvdbx_t* h, float lane_spacing, doub
     const int blocks = sms * 14, threads = 128, rounds = 1024;
     float* out = nullptr;
     GX_CUDA(h, cudaMalloc(&out, size_t(blocks) * threads * sizeof(float)));
+    cudaTextureObject_t lut_tex = 0;
+    if (getenv("GVDBX_LUT_TEX")) {                  // A/B: table entries fetched through a linear float4 texture instead of 16-byte loads
+        cudaResourceDesc rd = {}; rd.resType = cudaResourceTypeLinear; rd.res.linear.devPtr = h->d_transfer;
+        rd.res.linear.desc = cudaCreateChannelDesc<float4>(); rd.res.linear.sizeInBytes = GVDBX_TRANSFER_ENTRIES * sizeof(float4);
+        cudaTextureDesc td = {}; td.readMode = cudaReadModeElementType; td.filterMode = cudaFilterModePoint; td.addressMode[0] = cudaAddressModeClamp;
+        GX_CUDA(h, cudaCreateTextureObject(&lut_tex, &rd, &td, nullptr));
+    }
     cudaEvent_t e0, e1;
     GX_CUDA(h, cudaEventCreate(&e0));
     GX_CUDA(h, cudaEventCreate(&e1));
     double best = 0.0;
     for (int rep = 0; rep < 4; rep++) {             // first repetition warms up
         GX_CUDA(h, cudaEventRecord(e0, h->stream));
-        gx_deep_loop_peak_kernel<<<blocks, threads, 0, h->stream>>>(h->tex, h->d_transfer, h->ares[0], h->ares[1], h->ares[2], rounds, lane_spacing,
-                                                                    0.1f, 1.0f, 0.005f, 1.5f, out);
+        if (!lut_tex) gx_deep_loop_peak_kernel<0><<<blocks, threads, 0, h->stream>>>(h->tex, h->d_transfer, 0, h->ares[0], h->ares[1], h->ares[2], rounds, lane_spacing,
+                                                                                    0.1f, 1.0f, 0.005f, 1.5f, out);
+        else          gx_deep_loop_peak_kernel<1><<<blocks, threads, 0, h->stream>>>(h->tex, h->d_transfer, lut_tex, h->ares[0], h->ares[1], h->ares[2], rounds, lane_spacing,
+                                                                                    0.1f, 1.0f, 0.005f, 1.5f, out);
         GX_CUDA(h, cudaEventRecord(e1, h->stream));
         GX_CUDA(h, cudaEventSynchronize(e1));
         GX_CUDA(h, cudaGetLastError());
@@ -1272,6 +1281,7 @@ extern "C" int gvdbx_measure_deep_loop_peak(gvdbx_t* h, float lane_spacing, doub
         if (rep > 0 && g > best) best = g;
     }
     cudaEventDestroy(e0); cudaEventDestroy(e1);
+    if (lut_tex) cudaDestroyTextureObject(lut_tex);
     cudaFree(out);
     *gsamples_per_s = best;
     return GVDBX_OK;

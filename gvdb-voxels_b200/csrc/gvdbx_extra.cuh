@@ -176,14 +176,18 @@ __device__ __forceinline__ void gx_brick_shadow(const GxParams& P, S& smp, int n
         float3 p1, p2, p3;
         GX_STEP_ADD(p1, p); GX_STEP_ADD(p2, p1); GX_STEP_ADD(p3, p2);
         const bool k1 = GX_INB(p1, res0), k2 = GX_INB(p2, res0), k3 = GX_INB(p3, res0);
-        const float v0 = smp.tri(p.x + o.x, p.y + o.y, p.z + o.z);
-        const float v1 = smp.tri(p1.x + o.x, p1.y + o.y, p1.z + o.z);
-        const float v2 = smp.tri(p2.x + o.x, p2.y + o.y, p2.z + o.z);
-        const float v3 = smp.tri(p3.x + o.x, p3.y + o.y, p3.z + o.z);
+        const float v0 = smp.tri(p.x + o.x, p.y + o.y, p.z + o.z);       // the loop condition holds for the first sample
+        const float v1 = GX_TRI_IF(k1, p1), v2 = GX_TRI_IF(k2, p2), v3 = GX_TRI_IF(k3, p3);
         const float a0 = gx_lut(P.transfer, gx_transfer_index(v0, P.thresh.x, inv_range)).w;
+#if GX_PRED_FETCH
+        const float a1 = k1 ? gx_lut(P.transfer, gx_transfer_index(v1, P.thresh.x, inv_range)).w : 0.f;
+        const float a2 = k2 ? gx_lut(P.transfer, gx_transfer_index(v2, P.thresh.x, inv_range)).w : 0.f;
+        const float a3 = k3 ? gx_lut(P.transfer, gx_transfer_index(v3, P.thresh.x, inv_range)).w : 0.f;
+#else
         const float a1 = gx_lut(P.transfer, gx_transfer_index(v1, P.thresh.x, inv_range)).w;
         const float a2 = gx_lut(P.transfer, gx_transfer_index(v2, P.thresh.x, inv_range)).w;
         const float a3 = gx_lut(P.transfer, gx_transfer_index(v3, P.thresh.x, inv_range)).w;
+#endif
         // one layer: clr.w = 1 - (1 - clr.w) * exp(...), then the parameter step
         #define GX_SHADOW_LAYER(alpha) { cnt.s_tri++; cnt.s_lut++;                                              \
             const float val = exp(P.extinct.x * (alpha) * P.steps.y / (1.0 + s * 0.4));                          \

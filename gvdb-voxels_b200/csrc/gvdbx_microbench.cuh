@@ -137,7 +137,10 @@ __global__ void __launch_bounds__(128) gx_linear_peak_kernel(const float* __rest
 // products — and nothing else: no traversal, no brick entries, no partial rounds, every lane always active, bricks L1-resident,
 // the same 8x4 packet geometry as gx_tex_peak_kernel.  deep achieved / this = what traversal, brick changes, lane imbalance and
 // cache misses cost; this / texture peak = what the per-sample arithmetic and the table gather cost.
-__global__ void __launch_bounds__(128, 7) gx_deep_loop_peak_kernel(cudaTextureObject_t tex, const float4* __restrict__ lut, int ares_x, int ares_y, int ares_z,
+// LUTMODE 0: the table gather is a 16-byte read-only load (the production path); 1: a float4 point fetch through a linear
+// texture object over the same table (A/B: does the texture path gather 16-byte entries cheaper than the LSU path?)
+template <int LUTMODE>
+__global__ void __launch_bounds__(128, 7) gx_deep_loop_peak_kernel(cudaTextureObject_t tex, const float4* __restrict__ lut, cudaTextureObject_t lut_tex, int ares_x, int ares_y, int ares_z,
                                                                    int rounds, float spacing, float thresh, float inv_range, float minval, float albedo,
                                                                    float* __restrict__ out)
 {
@@ -155,8 +158,14 @@ __global__ void __launch_bounds__(128, 7) gx_deep_loop_peak_kernel(cudaTextureOb
         GX_STEP_ADD(p1, p); GX_STEP_ADD(p2, p1); GX_STEP_ADD(p3, p2);
         const float v0 = tex3D<float>(tex, p.x, p.y, p.z), v1 = tex3D<float>(tex, p1.x, p1.y, p1.z);
         const float v2 = tex3D<float>(tex, p2.x, p2.y, p2.z), v3 = tex3D<float>(tex, p3.x, p3.y, p3.z);
-        const float4 c0 = gx_lut(lut, gx_transfer_index(v0, thresh, inv_range)), c1 = gx_lut(lut, gx_transfer_index(v1, thresh, inv_range));
-        const float4 c2 = gx_lut(lut, gx_transfer_index(v2, thresh, inv_range)), c3 = gx_lut(lut, gx_transfer_index(v3, thresh, inv_range));
+        float4 c0, c1, c2, c3;
+        if (LUTMODE == 0) {
+            c0 = gx_lut(lut, gx_transfer_index(v0, thresh, inv_range)); c1 = gx_lut(lut, gx_transfer_index(v1, thresh, inv_range));
+            c2 = gx_lut(lut, gx_transfer_index(v2, thresh, inv_range)); c3 = gx_lut(lut, gx_transfer_index(v3, thresh, inv_range));
+        } else {
+            c0 = tex1Dfetch<float4>(lut_tex, int(gx_transfer_index(v0, thresh, inv_range))); c1 = tex1Dfetch<float4>(lut_tex, int(gx_transfer_index(v1, thresh, inv_range)));
+            c2 = tex1Dfetch<float4>(lut_tex, int(gx_transfer_index(v2, thresh, inv_range))); c3 = tex1Dfetch<float4>(lut_tex, int(gx_transfer_index(v3, thresh, inv_range)));
+        }
         if (v0 >= minval) gx_deep_accumulate_pre(P, clr, c0);
         if (v1 >= minval) gx_deep_accumulate_pre(P, clr, c1);
         if (v2 >= minval) gx_deep_accumulate_pre(P, clr, c2);

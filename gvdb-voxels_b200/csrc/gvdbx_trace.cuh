@@ -35,6 +35,15 @@ __device__ __forceinline__ float3 gx_poszero(float3 p) { return make_float3(gx_p
 __device__ __forceinline__ unsigned gx_maxbits(float3 q) { return max(max(__float_as_uint(q.x), __float_as_uint(q.y)), __float_as_uint(q.z)); }
 #define GX_INB(q, hi)    (gx_maxbits(q) <  __float_as_uint(hi))
 #define GX_INB_LE(q, hi) (gx_maxbits(q) <= __float_as_uint(hi))
+// filtered fetch of a sample that is only consumed if it lies inside the brick (`k`): predicated off otherwise
+#ifndef GX_PRED_FETCH
+#define GX_PRED_FETCH 1
+#endif
+#if GX_PRED_FETCH
+#define GX_TRI_IF(k, q) ((k) ? smp.tri((q).x + o.x, (q).y + o.y, (q).z + o.z) : 0.f)
+#else
+#define GX_TRI_IF(k, q) (smp.tri((q).x + o.x, (q).y + o.y, (q).z + o.z))
+#endif
 #define GX_STEP_FMA(dst, src) { (dst).x = __fmaf_rn(st, dir.x, (src).x); (dst).y = __fmaf_rn(st, dir.y, (src).y); (dst).z = __fmaf_rn(st, dir.z, (src).z); }
 #define GX_STEP_ADD(dst, src) { (dst).x = __fadd_rn((src).x, wpt.x); (dst).y = __fadd_rn((src).y, wpt.y); (dst).z = __fadd_rn((src).z, wpt.z); }
 
@@ -57,10 +66,10 @@ __device__ __forceinline__ void gx2_brick_trilinear(const GxParams& P, S& smp, i
         float3 p1, p2, p3;
         GX_STEP_FMA(p1, p); GX_STEP_FMA(p2, p1); GX_STEP_FMA(p3, p2);
         const bool k0 = GX_INB(p, res0), k1 = GX_INB(p1, res0), k2 = GX_INB(p2, res0), k3 = GX_INB(p3, res0);
-        const float v0 = smp.tri(p.x + o.x, p.y + o.y, p.z + o.z);
-        const float v1 = smp.tri(p1.x + o.x, p1.y + o.y, p1.z + o.z);
-        const float v2 = smp.tri(p2.x + o.x, p2.y + o.y, p2.z + o.z);
-        const float v3 = smp.tri(p3.x + o.x, p3.y + o.y, p3.z + o.z);
+        const float v0 = GX_TRI_IF(k0, p);
+        const float v1 = GX_TRI_IF(k1, p1);
+        const float v2 = GX_TRI_IF(k2, p2);
+        const float v3 = GX_TRI_IF(k3, p3);
         int k = -1;                      // index of the sample that ends the loop, hit = it passed the threshold
         bool hit = false;
         if (!k0) k = 0; else if (v0 >= thr) { k = 0; hit = true; }
@@ -101,10 +110,10 @@ __device__ __forceinline__ void gx2_brick_levelset(const GxParams& P, S& smp, in
         float3 p1, p2, p3;
         GX_STEP_FMA(p1, p); GX_STEP_FMA(p2, p1); GX_STEP_FMA(p3, p2);
         const bool k0 = GX_INB_LE(p, res0), k1 = GX_INB_LE(p1, res0), k2 = GX_INB_LE(p2, res0), k3 = GX_INB_LE(p3, res0);
-        const float v0 = smp.tri(p.x + o.x, p.y + o.y, p.z + o.z);
-        const float v1 = smp.tri(p1.x + o.x, p1.y + o.y, p1.z + o.z);
-        const float v2 = smp.tri(p2.x + o.x, p2.y + o.y, p2.z + o.z);
-        const float v3 = smp.tri(p3.x + o.x, p3.y + o.y, p3.z + o.z);
+        const float v0 = GX_TRI_IF(k0, p);
+        const float v1 = GX_TRI_IF(k1, p1);
+        const float v2 = GX_TRI_IF(k2, p2);
+        const float v3 = GX_TRI_IF(k3, p3);
         int k = -1;
         bool hit = false;
         if (!k0) k = 0; else if (v0 < thr) { k = 0; hit = true; }
@@ -262,6 +271,8 @@ __device__ __forceinline__ void gx2_brick_deep(const GxParams& P, S& smp, int no
 #define GX_QK 2              // measured on cfg4 deep 4K: 1 -> 20.9 ms, 2 -> 20.2, 3 / 4 -> 20.6, 8 -> 21.1, 16 -> 21.7 (look-ahead waste and shared
                              // memory taken from L1 grow with the depth; most of the gain is the flat loop itself)
 #endif
+// GX_PRED_FETCH = 1 (default): fetches / table reads of samples behind the brick's end are predicated off (0: issued and discarded,
+// the A/B baseline; measured cfg4 deep 4K 19.67 -> 18.91 ms, deep + shadow 20.62 -> 20.16 ms)
 #ifndef GX_Q_PREFETCH
 #define GX_Q_PREFETCH 0      // measured: prefetching the next round costs registers (spills at 64, 22.5 vs 21.1 ms at 80): off
 #endif
@@ -336,10 +347,19 @@ __device__ __forceinline__ void gx_raycast_deep_q(const GxParams& P, S& smp, flo
                 else
 #endif
                 {
+#if GX_PRED_FETCH
+                    // a sample behind the brick's end is never consumed (samples are taken in order and `more` stops at the first
+                    // one outside): its fetch and its table read are predicated off instead of issued and discarded
+                    v0 = k0 ? smp.tri(p.x + o.x, p.y + o.y, p.z + o.z) : 0.f;
+                    v1 = k1 ? smp.tri(p1.x + o.x, p1.y + o.y, p1.z + o.z) : 0.f;
+                    v2 = k2 ? smp.tri(p2.x + o.x, p2.y + o.y, p2.z + o.z) : 0.f;
+                    v3 = k3 ? smp.tri(p3.x + o.x, p3.y + o.y, p3.z + o.z) : 0.f;
+#else
                     v0 = smp.tri(p.x + o.x, p.y + o.y, p.z + o.z);
                     v1 = smp.tri(p1.x + o.x, p1.y + o.y, p1.z + o.z);
                     v2 = smp.tri(p2.x + o.x, p2.y + o.y, p2.z + o.z);
                     v3 = smp.tri(p3.x + o.x, p3.y + o.y, p3.z + o.z);
+#endif
                 }
 #if GX_Q_PREFETCH
                 if (kn) {
@@ -351,10 +371,18 @@ __device__ __forceinline__ void gx_raycast_deep_q(const GxParams& P, S& smp, flo
                     w3 = smp.tri(q3.x + o.x, q3.y + o.y, q3.z + o.z);
                 }
 #endif
+#if GX_PRED_FETCH
+                const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                const float4 c0 = (k0 && v0 >= minval) ? gx_lut(lut, gx_transfer_index(v0, thresh, inv_range)) : z4;
+                const float4 c1 = (k1 && v1 >= minval) ? gx_lut(lut, gx_transfer_index(v1, thresh, inv_range)) : z4;
+                const float4 c2 = (k2 && v2 >= minval) ? gx_lut(lut, gx_transfer_index(v2, thresh, inv_range)) : z4;
+                const float4 c3 = (k3 && v3 >= minval) ? gx_lut(lut, gx_transfer_index(v3, thresh, inv_range)) : z4;
+#else
                 const float4 c0 = gx_lut(lut, gx_transfer_index(v0, thresh, inv_range));
                 const float4 c1 = gx_lut(lut, gx_transfer_index(v1, thresh, inv_range));
                 const float4 c2 = gx_lut(lut, gx_transfer_index(v2, thresh, inv_range));
                 const float4 c3 = gx_lut(lut, gx_transfer_index(v3, thresh, inv_range));
+#endif
                 int done = 0;
                 bool more = k0;
                 #define GX_Q_SAMPLE(v, c, knext) { done++; cnt.s_tri++; if ((v) >= minval) { cnt.s_lut++; if (GX_DEEP_LUT) gx_deep_accumulate_pre(P, clr, c); else gx_deep_accumulate(P, clr, c); } more = (knext) && clr.w > acut; }
@@ -438,10 +466,10 @@ __device__ __forceinline__ void gx_raycast_surface_q(const GxParams& P, S& smp, 
             bool k0, k1, k2, k3;
             if (LS) { k0 = GX_INB_LE(p, res0); k1 = GX_INB_LE(p1, res0); k2 = GX_INB_LE(p2, res0); k3 = GX_INB_LE(p3, res0); }
             else    { k0 = GX_INB(p, res0); k1 = GX_INB(p1, res0); k2 = GX_INB(p2, res0); k3 = GX_INB(p3, res0); }
-            const float v0 = smp.tri(p.x + o.x, p.y + o.y, p.z + o.z);
-            const float v1 = smp.tri(p1.x + o.x, p1.y + o.y, p1.z + o.z);
-            const float v2 = smp.tri(p2.x + o.x, p2.y + o.y, p2.z + o.z);
-            const float v3 = smp.tri(p3.x + o.x, p3.y + o.y, p3.z + o.z);
+            const float v0 = GX_TRI_IF(k0, p);
+            const float v1 = GX_TRI_IF(k1, p1);
+            const float v2 = GX_TRI_IF(k2, p2);
+            const float v3 = GX_TRI_IF(k3, p3);
             const bool t0 = LS ? v0 < thr : v0 >= thr, t1 = LS ? v1 < thr : v1 >= thr, t2 = LS ? v2 < thr : v2 >= thr, t3 = LS ? v3 < thr : v3 >= thr;
             int k = -1;                      // index of the sample that ends this brick; hit = it passed the threshold test
             bool hit = false;
