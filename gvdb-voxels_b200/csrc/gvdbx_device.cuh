@@ -959,7 +959,9 @@ __device__ __forceinline__ float4 gx_shade_pixel(const GxParams& P, S& smp, int 
 
 // Launch bounds.  CTAs are at most GX_MAXTHREADS = 128 threads (default 8x8 = two 8x4-pixel warps); the register budget follows
 // from the number of such CTAs per SM: 8 -> 64 registers (surface modes, SHADE_VOXEL: issue-bound, occupancy pays),
-// 7 -> 72 registers (deep brick-queue kernels: no spills at 72; measured cfg4 deep 4K 23.1 ms at 64, 19.7 at 72, 20.1 at 80).
+// the deep brick-queue kernels included since the walker gives six registers back while the bricks are marched (GxWalk::resume):
+// measured cfg4 deep + shadow 4K 20.17 ms at 72 registers / 28 warps per SM, 19.43 ms at 64 registers / 32 warps (deep: 18.93 -> 18.66);
+// before that step 64 registers spilled (23.1 ms against 19.7 at 72 and 20.1 at 80).
 template <int MODE, int SAMPLER, int FLAGS, bool UNI>
 #ifndef GX_MAXTHREADS
 #define GX_MAXTHREADS 128
@@ -968,7 +970,7 @@ template <int MODE, int SAMPLER, int FLAGS, bool UNI>
 #define GX_MINBLOCKS 8
 #endif
 #ifndef GX_QUEUE_MINBLOCKS
-#define GX_QUEUE_MINBLOCKS 7
+#define GX_QUEUE_MINBLOCKS 8
 #endif
 #ifndef GX_SURFQ_MINBLOCKS
 #define GX_SURFQ_MINBLOCKS 8

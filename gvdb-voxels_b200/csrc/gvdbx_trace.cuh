@@ -302,6 +302,7 @@ __device__ __forceinline__ void gx_raycast_deep_q(const GxParams& P, S& smp, flo
     while (walking) {
         // ---- phase A: queue the next bricks (the walker = cuda_gvdb_raycast.cuh:567-610 without the brick call)
         int qn = 0;
+        w.resume(P);
         walking = w.walk(P, cnt, [&](int leaf, float t_enter, float) {
             // brick entry of rayDeepBrick that depends on the entry parameter only (:490, first-sample bookkeeping)
             const float ts = stp * ceilf(t_enter / stp);
@@ -436,6 +437,7 @@ __device__ __forceinline__ void gx_raycast_surface_q(const GxParams& P, S& smp, 
     while (walking) {
         // ---- phase A (see gx_raycast_deep_q)
         int qn = 0;
+        w.resume(P);
         walking = w.walk(P, cnt, [&](int leaf, float t_enter, float) {
             cnt.n_desc++;
             bool keep = true;       // value-range culling: no sample of this brick can pass the threshold test

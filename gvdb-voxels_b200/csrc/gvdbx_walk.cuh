@@ -26,6 +26,9 @@
 // words per thread of dynamic shared memory: 4 node ids (levels 1..4) + 4 exit parameters + padding to an odd stride;
 // queue kernels append 2 * GX_QK words (leaf, entry parameter per queued brick) and pad again
 #define GX_WALK_WORDS 9
+#ifndef GX_WALK_RESUME
+#define GX_WALK_RESUME 1      // tDel and the step signs are recomputed when the walk resumes behind a sample loop (0: kept live, A/B)
+#endif
 
 template <class S, int ROW_WORDS>
 struct GxWalk {
@@ -138,6 +141,19 @@ struct GxWalk {
             if (lev > P.top_lev) iter = GX_MAX_ITER;          // the root was popped: the next guard ends the walk
             else if (changed) prepare(P);
         }
+    }
+
+    // Before walk() is called again after a long pause (the sample loop of the brick-queue ray casts): the per-level step tDel and
+    // the step signs are recomputed from (level, |1/dir|, dir) — the same expressions, the same bits — so that these six
+    // registers are not live while the bricks are marched.
+    __device__ __forceinline__ void resume(const GxParams& P)
+    {
+#if GX_WALK_RESUME
+        if (lev <= P.top_lev) d.tDel = gx_vdel<S>(P, lev) * d.inv;
+        asm volatile("shr.s32 %0, %1, 31;\n\tor.b32 %0, %0, 1;" : "=r"(sx) : "r"(__float_as_int(d.dir.x)));
+        asm volatile("shr.s32 %0, %1, 31;\n\tor.b32 %0, %0, 1;" : "=r"(sy) : "r"(__float_as_int(d.dir.y)));
+        asm volatile("shr.s32 %0, %1, 31;\n\tor.b32 %0, %0, 1;" : "=r"(sz) : "r"(__float_as_int(d.dir.z)));
+#endif
     }
 
     // The reference loop with the brick visit as a functor, called INSIDE the iteration that found the brick (the reference's
