@@ -4,7 +4,7 @@
 //
 // Same per-ray arithmetic as the reference loop — every t, tSide and cell index is produced by the same sequence of
 // floating-point operations — with the bookkeeping around it reduced to what one iteration needs (ncu source view of the
-// literal form, profiles/r02h_cfg3_voxel: ~70 issued instructions per iteration on the no-level-change path, 13 of them
+// literal form, SHADE_VOXEL 4K, profiles/r02_summary.md: ~70 issued instructions per iteration on the no-level-change path, 13 of them
 // recomputing a shared-memory address, 12 stepping the cell index, 6 re-testing loop guards):
 //
 //   * Next() and Step() are FUSED.  The reference steps the DDA of the current level only if the cell is empty or after the
@@ -17,7 +17,9 @@
 //   * the step signs (isign3(dir)) are three integer registers, so a cell step is three predicated adds;
 //   * the (node, tMax) stack of a thread is ONE row of GX_WALK_WORDS words in shared memory, odd stride = conflict-free,
 //     addressed as row + level with immediate offsets: a push or pop is one address instruction and two accesses;
-//   * level changes of one iteration (descent or pops) end in ONE Prepare at one code site (as before).
+//   * level changes of one iteration (descent or pops) end in ONE Prepare at one code site (as before);
+//   * resumable: walk() returns after the iteration that found a brick is complete; the brick-queue ray casts call resume()
+//     before walking on, which recomputes tDel and the step signs so that they are not live across the sample loop.
 //
 // The depth-buffer clip (`t.x > tDepth`, :571) is not part of the walker: rays of a frame with a depth buffer bound take the
 // literal loop of gx_raycast.
@@ -80,7 +82,7 @@ struct GxWalk {
         // isign3(dir) (cuda_math.cuh:1541-1545: +1 for dir > 0, else -1) from the sign bit.  The two differ only for a zero
         // (or flushed subnormal) component, and that axis never steps: its tDel is infinite, its tSide +inf or NaN, and both
         // comparisons of its mask are false
-        // (volatile: the compiler would otherwise rematerialise the three integers from dir at every step)
+        // (volatile: keeps the front end from rematerialising the three integers from dir at every step; ptxas still may under pressure)
         asm volatile("shr.s32 %0, %1, 31;\n\tor.b32 %0, %0, 1;" : "=r"(sx) : "r"(__float_as_int(dir.x)));
         asm volatile("shr.s32 %0, %1, 31;\n\tor.b32 %0, %0, 1;" : "=r"(sy) : "r"(__float_as_int(dir.y)));
         asm volatile("shr.s32 %0, %1, 31;\n\tor.b32 %0, %0, 1;" : "=r"(sz) : "r"(__float_as_int(dir.z)));
