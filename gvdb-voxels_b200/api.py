@@ -89,7 +89,7 @@ def lib():
     L.gvdbx_sample_points.argtypes = [vp, i32, u64, i32, u64, u64]
     L.gvdbx_measure_tex_peak.argtypes = [vp, C.c_float, C.POINTER(C.c_double)]
     L.gvdbx_measure_sampler_ab.argtypes = [vp, C.c_float, C.POINTER(C.c_double)]
-    L.gvdbx_measure_deep_loop_peak.argtypes = [vp, C.c_float, C.POINTER(C.c_double)]
+    L.gvdbx_measure_deep_loop_peak.argtypes = [vp, C.c_float, i32, C.POINTER(C.c_double)]
     L.gvdbx_render_tiles_direct.argtypes = [vp, vp, i32, i32, u64, i32, i32, i32]
     L.gvdbx_kernel_params.argtypes = [vp, vp, i32, i32, u64, vp, C.c_size_t]
     L.gvdbx_update_apron.argtypes = [vp, i32, C.c_float]
@@ -411,10 +411,11 @@ class Renderer:
         self._ck(self._L.gvdbx_measure_tex_peak(self._h, C.c_float(lane_spacing), C.byref(g)), "gvdbx_measure_tex_peak")
         return float(g.value)
 
-    def measure_deep_loop_peak(self, lane_spacing=0.2):
-        """Gsamples/s of the deep marcher's inner loop alone (fetch + transfer index + table gather + colour update, no traversal)"""
+    def measure_deep_loop_peak(self, lane_spacing=0.2, table_through_texture=False):
+        """Gsamples/s of the deep marcher's inner loop alone (fetch + transfer index + table gather + colour update, no traversal);
+        table_through_texture: A/B variant that reads the transfer table through a float4 texture object"""
         g = C.c_double()
-        self._ck(self._L.gvdbx_measure_deep_loop_peak(self._h, C.c_float(lane_spacing), C.byref(g)), "gvdbx_measure_deep_loop_peak")
+        self._ck(self._L.gvdbx_measure_deep_loop_peak(self._h, C.c_float(lane_spacing), 1 if table_through_texture else 0, C.byref(g)), "gvdbx_measure_deep_loop_peak")
         return float(g.value)
 
     def measure_sampler_ab(self, lane_spacing=0.2):

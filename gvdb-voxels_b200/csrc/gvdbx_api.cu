@@ -1244,7 +1244,9 @@ extern "C" int gvdbx_measure_sampler_ab(gvdbx_t* h, float lane_spacing, double* 
 
 // Gsamples/s of the deep marcher's inner loop alone (csrc/gvdbx_microbench.cuh): fetch + transfer index + table gather + colour
 // update, four samples per round, no traversal.  Needs the atlas and a transfer function (gvdbx_set_transfer); synchronises.
-extern "C" int gvdbx_measure_deep_loop_peak(gvdbx_t* h, float lane_spacing, double* gsamples_per_s)
+// table_through_texture = 1 reads the transfer table through a float4 texture object instead of 16-byte loads (measured slower:
+// 274 against 349 Gsamples/s — the production kernels use the loads).
+extern "C" int gvdbx_measure_deep_loop_peak(gvdbx_t* h, float lane_spacing, int table_through_texture, double* gsamples_per_s)
 {
     if (!h || !gsamples_per_s || !(lane_spacing >= 0.f) || lane_spacing > 8.f) return GVDBX_E_ARG;
     if (!h->have_atlas) return gx_fail(h, GVDBX_E_STATE, "no atlas imported");
@@ -1256,7 +1258,7 @@ extern "C" int gvdbx_measure_deep_loop_peak(gvdbx_t* h, float lane_spacing, doub
     float* out = nullptr;
     GX_CUDA(h, cudaMalloc(&out, size_t(blocks) * threads * sizeof(float)));
     cudaTextureObject_t lut_tex = 0;
-    if (getenv("GVDBX_LUT_TEX")) {                  // A/B: table entries fetched through a linear float4 texture instead of 16-byte loads
+    if (table_through_texture) {                    // A/B: table entries fetched through a linear float4 texture instead of 16-byte loads
         cudaResourceDesc rd = {}; rd.resType = cudaResourceTypeLinear; rd.res.linear.devPtr = h->d_transfer;
         rd.res.linear.desc = cudaCreateChannelDesc<float4>(); rd.res.linear.sizeInBytes = GVDBX_TRANSFER_ENTRIES * sizeof(float4);
         cudaTextureDesc td = {}; td.readMode = cudaReadModeElementType; td.filterMode = cudaFilterModePoint; td.addressMode[0] = cudaAddressModeClamp;

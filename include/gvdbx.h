@@ -288,7 +288,8 @@ int  gvdbx_measure_tex_peak(gvdbx_t* h, float lane_spacing, double* gsamples_per
 int  gvdbx_measure_sampler_ab(gvdbx_t* h, float lane_spacing, double* gsamples_per_s4);
 /* Gsamples/s of the deep marcher's inner loop alone — four fetches, four transfer indices, four 16-byte table gathers, four colour
  * updates per round, no traversal, every lane busy, L1-resident bricks: the ceiling of the sample loop; needs gvdbx_set_transfer. */
-int  gvdbx_measure_deep_loop_peak(gvdbx_t* h, float lane_spacing, double* gsamples_per_s);
+int  gvdbx_measure_deep_loop_peak(gvdbx_t* h, float lane_spacing, int table_through_texture /* A/B: 1 = float4 texture fetches instead of 16-byte loads */,
+                                  double* gsamples_per_s);
 
 #ifdef __cplusplus
 }

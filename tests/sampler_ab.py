@@ -22,7 +22,8 @@ def main():
     r.set_transfer(table)
     for s in spacings:
         print(json.dumps({"workload": wl, "lane_spacing_voxels": s, **{k: round(v, 1) for k, v in r.measure_sampler_ab(s).items()},
-                          "deep_sample_loop": round(r.measure_deep_loop_peak(s), 1)}), flush=True)
+                          "deep_sample_loop": round(r.measure_deep_loop_peak(s), 1),
+                          "deep_sample_loop_table_through_texture": round(r.measure_deep_loop_peak(s, True), 1)}), flush=True)
     r.close()
 
 
